@@ -1,0 +1,217 @@
+/*
+ * farms_b200.h -- C ABI of the B200-native batched FARMS stepping engine.
+ *
+ * The reference (farmsim/farms_mujoco) has no C ABI of its own for this path:
+ * its native code is Cython `cpdef` functions called with Python objects
+ * (farms_mujoco/sensors/sensors.pxd:12-29, farms_mujoco/swimming/drag.pyx:152,
+ * 389) and its physics is the third-party MuJoCo C library reached through
+ * dm_control (farms_mujoco/simulation/simulation.py:53,83-89,156,175).  Each
+ * entry point below therefore cites the reference interface it replaces; the
+ * binding a reference maintainer would add is shown in INTEGRATION.md.
+ *
+ * Conventions
+ *   - plain C types only; all pointers are HOST pointers unless the name ends
+ *     in `_dev` (device pointers, e.g. a torch tensor's data_ptr()).
+ *   - every function returns 0 on success, <0 on error; fb_last_error() gives
+ *     the message of the last failing call made on the calling thread.
+ *   - the engine owns all device buffers; views are borrowed and stay valid
+ *     until fb_destroy().
+ *   - one handle = one device + one stream; calls on one handle are not
+ *     re-entrant.  Handles on different devices may be driven concurrently.
+ *   - reals cross the ABI as float64 (the reference's dtype, sensors.pyx:
+ *     156-157); the device computes in float32.
+ */
+#ifndef FARMS_B200_H_
+#define FARMS_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FB_ABI_VERSION 1
+
+/* joint / geom enums follow MuJoCo's mjtJoint / mjtGeom numbering */
+enum { FB_JNT_FREE = 0, FB_JNT_BALL = 1, FB_JNT_SLIDE = 2, FB_JNT_HINGE = 3 };
+enum { FB_GEOM_PLANE = 0, FB_GEOM_SPHERE = 2, FB_GEOM_CAPSULE = 3 };
+
+/* Compiled model: the mjModel subset the path reads.
+ * Replaces: mjcf.Physics.from_mjcf_model(mjcf_model), simulation.py:53. */
+typedef struct FbModel {
+  int32_t nbody, njnt, nq, nv, nu, ngeom, ncand, nM;
+  /* <option> (mjcf.py:1326-1403) */
+  double timestep;
+  double gravity[3];
+  double impratio;
+  int32_t solver_iterations;
+  double tolerance;
+  double meaninertia;
+  /* bodies [nbody]; body 0 is the world; depth-first order (parent < child) */
+  const int32_t *body_parentid, *body_jntid, *body_dofadr, *body_dofnum;
+  const double *body_pos, *body_quat, *body_ipos, *body_iquat; /* 3,4,3,4 */
+  const double *body_mass, *body_inertia, *body_invweight0;    /* 1,3,2 */
+  /* joints [njnt] (<=1 per body) */
+  const int32_t *jnt_type, *jnt_bodyid, *jnt_qposadr, *jnt_dofadr, *jnt_limited;
+  const double *jnt_pos, *jnt_axis, *jnt_stiffness, *jnt_range, *jnt_margin;
+  const double *jnt_solref, *jnt_solimp; /* 2,5 */
+  /* dofs [nv] */
+  const int32_t *dof_bodyid, *dof_jntid, *dof_parentid, *dof_Madr;
+  const double *dof_damping, *dof_armature, *dof_invweight0;
+  const double *qpos0, *qpos_spring; /* [nq] */
+  /* collision geoms [ngeom] */
+  const int32_t *geom_type, *geom_bodyid;
+  const double *geom_pos, *geom_quat, *geom_size; /* 3,4,3 */
+  /* plane-vs-{sphere, capsule end} candidates [ncand], parameters pre-mixed */
+  const int32_t *cand_geom1, *cand_geom2, *cand_end;
+  const double *cand_friction, *cand_solref, *cand_solimp, *cand_margin, *cand_gap;
+  /* actuators [nu]: force = gain0*ctrl + bias0 + bias1*q + bias2*qvel */
+  const int32_t *actuator_trnid, *actuator_ctrllimited, *actuator_forcelimited;
+  const double *actuator_gainprm, *actuator_biasprm;          /* 3,3 */
+  const double *actuator_ctrlrange, *actuator_forcerange, *actuator_gear;
+  /* keyframe 0 (task.py:137 physics.reset(keyframe_id=0)) */
+  const double *key_qpos, *key_qvel;
+} FbModel;
+
+/* farms-side contract: index maps (physics.py:188-393), swimming tables
+ * (drag.pyx:333-387), units (physics.py:428-523).  Replaces:
+ * get_physics2data_maps() + SwimmingHandler.__init__(). */
+typedef struct FbFarms {
+  int32_t n_links, n_joints, n_contacts, n_xfrc, n_swim;
+  int32_t link_cols, joint_cols, contact_cols, xfrc_cols; /* 20,18,12,6 */
+  /* joint-row column indices (layout.py; farms_core sensor_convention) */
+  int32_t col_joint_position, col_joint_velocity, col_joint_torque, col_joint_limit_force;
+  const int32_t *link_body;          /* [n_links]  xpos2data == xquat2data == xipos2data */
+  const int32_t *joint_qposadr;      /* [n_joints] qpos2data */
+  const int32_t *joint_dofadr;       /* [n_joints] qvel2data */
+  const int32_t *joint_jntid;        /* [n_joints] joint of jointlimitfrc_<j>, -1 if absent */
+  const int32_t *joint_act_position; /* [n_joints] actuator of actuatorfrc_position_<j>, -1 */
+  const int32_t *joint_act_velocity; /* [n_joints] actuator of actuatorfrc_velocity_<j>, -1 */
+  const int32_t *joint_act_torque;   /* [n_joints] actuator of actuatorfrc_torque_<j>, -1 (empty in the reference) */
+  const int32_t *cand_sensor;        /* [ncand,4] contact-sensor index for the keys (g1,g2) (g2,g1) (g1,-1) (g2,-1), -1 if absent; signs -1,+1,-1,+1 (sensors.pyx:163-170) */
+  const int32_t *xfrc_body;          /* [n_xfrc] data2xfrc */
+  /* swimming links (drag.pyx:353-385) */
+  const int32_t *swim_links_index, *swim_xfrc_index; /* [n_swim] */
+  const double *swim_mass, *swim_height, *swim_density; /* [n_swim] */
+  const double *swim_coefficients;   /* [n_swim,2,3] */
+  int32_t water_drag, water_sph, water_buoyancy;
+  double water_surface, water_density, water_viscosity;
+  double water_velocity[3];
+  double meters, seconds, kilograms;
+} FbFarms;
+
+/* On-device controller (replaces the per-step Python of task.py:288-346):
+ * ctrl[act_position[j]] = offset[j] + amplitude[j]*sin(2*pi*frequency[j]*t
+ *                         - phase_lag[j] + env_phase[env]),  t = iteration*timestep.
+ * Joints with act id -1 are skipped.  All arrays are host pointers. */
+typedef struct FbWaveController {
+  int32_t n;                  /* number of controlled joints */
+  const int32_t *actuator;    /* [n] ctrl index written (maps['ctrl']['pos']) */
+  const double *amplitude, *frequency, *phase_lag, *offset; /* [n] */
+} FbWaveController;
+
+typedef struct FbHandle FbHandle;
+
+/* Device log: farms layout per environment, float32.
+ *   links    [n_envs][ring][n_links   ][20]
+ *   joints   [n_envs][ring][n_joints  ][18]
+ *   contacts [n_envs][ring][n_contacts][12]
+ *   xfrc     [n_envs][ring][n_xfrc    ][6]
+ * i.e. log.<kind>_dev + env*<kind>_env_stride is exactly the reference's
+ * data.sensors.<kind>.array ([buffer_size, n_items, n_cols], task.py:158). */
+typedef struct FbLogView {
+  float *links_dev, *joints_dev, *contacts_dev, *xfrc_dev;
+  int64_t links_env_stride, joints_env_stride, contacts_env_stride, xfrc_env_stride; /* in floats */
+  int32_t ring, n_envs;
+} FbLogView;
+
+/* Device state views (float32), one row per environment. */
+typedef struct FbStateView {
+  float *qpos_dev;   /* [n_envs][nq] */
+  float *qvel_dev;   /* [n_envs][nv] */
+  float *ctrl_dev;   /* [n_envs][nu] */
+  float *xfrc_applied_dev; /* [n_envs][nbody][6] world wrench applied at xipos (force, torque) */
+  float *qpos_spring_dev;  /* [n_envs][nq] */
+  float *env_phase_dev;    /* [n_envs] */
+  int32_t *flags_dev;      /* [n_envs] bit0: non-finite state (PhysicsError analogue, simulation.py:157-161); bit1: contact overflow; bit2: solver not converged */
+  int64_t *iteration_dev;  /* [n_envs] physics steps taken since reset */
+} FbStateView;
+
+/* mjData-like derived quantities of the state at the START of the last step
+ * (SURVEY.md Appendix D-1), float32, written when fb_step(..., want_derived=1).
+ * These are what physics.data.{xpos,xquat,xipos,sensordata,contact} expose. */
+typedef struct FbDerivedView {
+  float *xpos_dev, *xquat_dev, *xipos_dev;  /* [n_envs][nbody][3|4|3] */
+  float *linvel_dev, *angvel_dev;           /* [n_envs][nbody][3] framelinvel / frameangvel (objtype=body) */
+  float *actuator_force_dev;                /* [n_envs][nu] */
+  float *jnt_limit_force_dev;               /* [n_envs][njnt] */
+  float *qacc_dev;                          /* [n_envs][nv] */
+  int32_t *ncon_dev;                        /* [n_envs] */
+  int32_t *con_cand_dev;                    /* [n_envs][maxcon] candidate index of each contact */
+  float *con_dist_dev;                      /* [n_envs][maxcon] */
+  float *con_pos_dev;                       /* [n_envs][maxcon][3] */
+  float *con_frame_dev;                     /* [n_envs][maxcon][9] */
+  float *con_force_dev;                     /* [n_envs][maxcon][3] mj_contactForce (normal, t1, t2) */
+  int32_t maxcon;
+} FbDerivedView;
+
+const char *fb_last_error(void);
+int fb_abi_version(void);
+
+/* Create an engine for n_envs environments on CUDA device `device`, with a
+ * log ring of `ring_steps` rows (task.py:62 buffer_size).  team_lanes = lanes
+ * cooperating on one environment (1,2,4,8,16,32; 0 = automatic). */
+int fb_create(const FbModel *model, const FbFarms *farms, int n_envs, int device,
+              int ring_steps, int team_lanes, FbHandle **out);
+void fb_destroy(FbHandle *h);
+
+/* Episode reset (task.py:87-154 + dm_control reset -> mj_forward): state <-
+ * qpos0/qvel0 ([n_envs,nq]/[n_envs,nv] host float64, NULL -> keyframe 0),
+ * ctrl <- 0, iteration <- 0; runs the forward pass and writes log row 0. */
+int fb_reset(FbHandle *h, const double *qpos0, const double *qvel0);
+
+/* Control inputs (task.py:307,317,332,343-346). */
+int fb_set_ctrl(FbHandle *h, const double *ctrl);                 /* [n_envs][nu] */
+int fb_set_qpos_spring(FbHandle *h, const double *qpos_spring);   /* [n_envs][nq] */
+int fb_set_env_phase(FbHandle *h, const double *phase);           /* [n_envs] */
+int fb_set_wave_controller(FbHandle *h, const FbWaveController *c); /* NULL -> off */
+/* Water velocity (drag.pyx:417-419 set_water_velocity). */
+int fb_set_water_velocity(FbHandle *h, double vx, double vy, double vz);
+/* Drag on/off overrides for the fused swimming step (drag.pyx:393-395). */
+int fb_set_swimming(FbHandle *h, int drag, int buoyancy);
+
+/* Advance every environment by n_steps physics steps (simulation.py:155-156
+ * env.step -> mj_step, with task.before_step's sensor logging, the swimming
+ * callback and the controller fused in).  Step j writes log row (j+1) % ring.
+ * Asynchronous on the handle's stream unless sync != 0. */
+int fb_step(FbHandle *h, int n_steps, int want_derived, int sync);
+int fb_synchronize(FbHandle *h);
+/* CUDA-event time of the last fb_step launch in milliseconds (after sync). */
+int fb_last_step_ms(FbHandle *h, float *ms);
+/* number of kernels launched by this handle so far */
+int64_t fb_launch_count(FbHandle *h);
+
+int fb_log_view(FbHandle *h, FbLogView *out);
+int fb_state_view(FbHandle *h, FbStateView *out);
+int fb_derived_view(FbHandle *h, FbDerivedView *out);
+
+/* Copy one environment's log to host float64 arrays shaped like the
+ * reference's data.sensors.<kind>.array (NULL pointers are skipped). */
+int fb_export_farms(FbHandle *h, int env, double *links, double *joints,
+                    double *contacts, double *xfrc);
+/* Host-buffer convenience used by the end-to-end benchmark: upload qpos/qvel
+ * for all envs, step, download the last log row of every env.
+ *   qpos/qvel: [n_envs][nq|nv] float32 host (pinned recommended)
+ *   links_row: [n_envs][n_links][20] float32 host */
+int fb_step_host(FbHandle *h, const float *qpos, const float *qvel, int n_steps,
+                 float *links_row, float *joints_row);
+
+/* introspection */
+int fb_team_lanes(FbHandle *h);
+int fb_smem_bytes_per_env(FbHandle *h);
+int fb_device_ptr_stream(FbHandle *h, void **stream_out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FARMS_B200_H_ */
