@@ -1,0 +1,1270 @@
+/*
+ * fb_device.h -- the fused FARMS step: MuJoCo-subset forward dynamics, soft
+ * constraints, semi-implicit Euler, farms sensor log rows and the swimming
+ * drag model, for ONE environment cooperatively executed by a TEAM of lanes
+ * (TEAM = 8, 16 or 32 lanes of one warp; the environment's working set lives
+ * in shared memory as component-major SoA arrays, see DevLayout).
+ *
+ * Algorithm references (SURVEY.md Appendix A restates the third-party MuJoCo
+ * pipeline; the farms parts follow the reference source directly):
+ *   step order            mj_step via farms_mujoco/simulation/simulation.py:156
+ *   log rows              farms_mujoco/simulation/physics.py:449-524
+ *   contact aggregation   farms_mujoco/sensors/sensors.pyx:20-190
+ *   drag / buoyancy       farms_mujoco/swimming/drag.pyx:152-268,389-411
+ *   hook order            farms_mujoco/simulation/task.py:168-186
+ *
+ * The file compiles in two ways:
+ *   - nvcc (sm_100a): the product.  Team primitives are warp shuffles,
+ *     __ballot_sync and __syncwarp on the team's lane mask.
+ *   - g++ with -DFB_HOST_EMU (tests/emu only): TEAM = 1, primitives collapse to
+ *     identities.  This is a unit-test harness for the arithmetic and indexing
+ *     in fp32 on the CPU-only development box; it is never loaded by the
+ *     product path.
+ */
+#ifndef FB_DEVICE_H_
+#define FB_DEVICE_H_
+
+#include "fb_model.h"
+
+#ifdef FB_HOST_EMU
+#include <cmath>
+#define FB_DEV static inline
+#define FB_MEM inline
+#define FB_LDG(p) (*(p))
+static inline float fb_rsqrt(float x) { return 1.0f/sqrtf(x); }
+static inline void fb_sincos(float x, float *s, float *c) { *s = sinf(x); *c = cosf(x); }
+#else
+#define FB_DEV __device__ __forceinline__
+#define FB_MEM __device__ __forceinline__
+#define FB_LDG(p) __ldg(p)
+__device__ __forceinline__ float fb_rsqrt(float x) { return 1.0f/sqrtf(x); }
+__device__ __forceinline__ void fb_sincos(float x, float *s, float *c) { sincosf(x, s, c); }
+#endif
+
+#ifdef FB_HOST_EMU
+#define FB_POPC(x) __builtin_popcount(x)
+#define FB_FLAG_OR(ptr, bit) (*(ptr) |= (bit))
+#else
+#define FB_POPC(x) __popc(x)
+#define FB_FLAG_OR(ptr, bit) atomicOr((ptr), (bit))
+#endif
+
+#define MI(name, i) FB_LDG(m.I + m.o.name + (i))
+#define MF(name, i) FB_LDG(m.F + m.o.name + (i))
+
+/* flags (FbStateView.flags_dev) */
+#define FB_FLAG_NONFINITE 1
+#define FB_FLAG_CONTACT_OVERFLOW 2
+#define FB_FLAG_SOLVER 4
+
+/* per-environment global pointers */
+struct EnvPtrs {
+  float *qpos, *qvel, *ctrl, *xfrc_applied, *qpos_spring;
+  float env_phase;
+  int *flags;
+  /* derived (FbDerivedView) */
+  float *d_xpos, *d_xquat, *d_xipos, *d_linvel, *d_angvel, *d_actf, *d_limf, *d_qacc;
+  int *d_ncon, *d_con_cand;
+  float *d_con_dist, *d_con_pos, *d_con_frame, *d_con_force;
+  /* solver scratch */
+  float *J3;     /* [3*maxcon][nv] contact-frame rows of the point Jacobian */
+  float *efc;    /* [5][maxefc]: aref, D, res, jp, force */
+  float *prod3;  /* [2][3*maxcon] */
+  /* log rows of this step */
+  float *row_links, *row_joints, *row_contacts, *row_xfrc;
+};
+
+/* ------------------------------------------------------------ team ops */
+template <int TEAM> struct TeamOps {
+#ifdef FB_HOST_EMU
+  static inline void sync(unsigned) {}
+  static inline float sum(unsigned, float v) { return v; }
+  static inline float max(unsigned, float v) { return v; }
+  static inline float min(unsigned, float v) { return v; }
+  static inline unsigned ballot(unsigned, int, int pred) { return pred ? 1u : 0u; }
+#else
+  static __device__ __forceinline__ void sync(unsigned mask) { __syncwarp(mask); }
+  static __device__ __forceinline__ float sum(unsigned mask, float v) {
+#pragma unroll
+    for (int o = TEAM/2; o > 0; o >>= 1) v += __shfl_xor_sync(mask, v, o);
+    return v;
+  }
+  static __device__ __forceinline__ float max(unsigned mask, float v) {
+#pragma unroll
+    for (int o = TEAM/2; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(mask, v, o));
+    return v;
+  }
+  static __device__ __forceinline__ float min(unsigned mask, float v) {
+#pragma unroll
+    for (int o = TEAM/2; o > 0; o >>= 1) v = fminf(v, __shfl_xor_sync(mask, v, o));
+    return v;
+  }
+  /* team-local ballot: bit i = predicate of team lane i */
+  static __device__ __forceinline__ unsigned ballot(unsigned mask, int base, int pred) {
+    unsigned b = __ballot_sync(mask, pred);
+    return TEAM == 32 ? b : ((b >> base) & ((1u << TEAM) - 1u));
+  }
+#endif
+};
+
+/* --------------------------------------------------------- small algebra */
+struct Quat { float w, x, y, z; };
+
+FB_DEV Quat q_mul(Quat a, Quat b) {
+  Quat r;
+  r.w = a.w*b.w - a.x*b.x - a.y*b.y - a.z*b.z;
+  r.x = a.w*b.x + a.x*b.w + a.y*b.z - a.z*b.y;
+  r.y = a.w*b.y - a.x*b.z + a.y*b.w + a.z*b.x;
+  r.z = a.w*b.z + a.x*b.y - a.y*b.x + a.z*b.w;
+  return r;
+}
+FB_DEV Quat q_normalize(Quat q) {
+  float n2 = q.w*q.w + q.x*q.x + q.y*q.y + q.z*q.z;
+  if (n2 < 1e-30f) { Quat i = {1.f, 0.f, 0.f, 0.f}; return i; }
+  float s = fb_rsqrt(n2);
+  Quat r = {q.w*s, q.x*s, q.y*s, q.z*s};
+  return r;
+}
+FB_DEV void q_mat(Quat q, float *R) {
+  float w = q.w, x = q.x, y = q.y, z = q.z;
+  R[0] = w*w + x*x - y*y - z*z; R[1] = 2*(x*y - w*z);         R[2] = 2*(x*z + w*y);
+  R[3] = 2*(x*y + w*z);         R[4] = w*w - x*x + y*y - z*z; R[5] = 2*(y*z - w*x);
+  R[6] = 2*(x*z - w*y);         R[7] = 2*(y*z + w*x);         R[8] = w*w - x*x - y*y + z*z;
+}
+FB_DEV void m_rot(const float *R, float x, float y, float z, float *o) {
+  o[0] = R[0]*x + R[1]*y + R[2]*z;
+  o[1] = R[3]*x + R[4]*y + R[5]*z;
+  o[2] = R[6]*x + R[7]*y + R[8]*z;
+}
+FB_DEV void m_rot_t(const float *R, float x, float y, float z, float *o) {
+  o[0] = R[0]*x + R[3]*y + R[6]*z;
+  o[1] = R[1]*x + R[4]*y + R[7]*z;
+  o[2] = R[2]*x + R[5]*y + R[8]*z;
+}
+FB_DEV void v_cross(const float *a, const float *b, float *r) {
+  float x = a[1]*b[2] - a[2]*b[1], y = a[2]*b[0] - a[0]*b[2], z = a[0]*b[1] - a[1]*b[0];
+  r[0] = x; r[1] = y; r[2] = z;
+}
+/* 10-number spatial inertia times [ang; lin] (mju_mulInertVec) */
+FB_DEV void inert_vec(const float *i, const float *v, float *r) {
+  r[0] = i[0]*v[0] + i[3]*v[1] + i[4]*v[2] - i[8]*v[4] + i[7]*v[5];
+  r[1] = i[3]*v[0] + i[1]*v[1] + i[5]*v[2] + i[8]*v[3] - i[6]*v[5];
+  r[2] = i[4]*v[0] + i[5]*v[1] + i[2]*v[2] - i[7]*v[3] + i[6]*v[4];
+  r[3] = i[8]*v[1] - i[7]*v[2] + i[9]*v[3];
+  r[4] = i[6]*v[2] - i[8]*v[0] + i[9]*v[4];
+  r[5] = i[7]*v[0] - i[6]*v[1] + i[9]*v[5];
+}
+/* vel x_m v (mju_crossMotion) */
+FB_DEV void cross_motion(const float *vel, const float *v, float *r) {
+  r[0] = -vel[2]*v[1] + vel[1]*v[2];
+  r[1] =  vel[2]*v[0] - vel[0]*v[2];
+  r[2] = -vel[1]*v[0] + vel[0]*v[1];
+  r[3] = -vel[2]*v[4] + vel[1]*v[5] - vel[5]*v[1] + vel[4]*v[2];
+  r[4] =  vel[2]*v[3] - vel[0]*v[5] + vel[5]*v[0] - vel[3]*v[2];
+  r[5] = -vel[1]*v[3] + vel[0]*v[4] - vel[4]*v[0] + vel[3]*v[1];
+}
+/* vel x* f (mju_crossForce) */
+FB_DEV void cross_force(const float *vel, const float *f, float *r) {
+  r[0] = -vel[2]*f[1] + vel[1]*f[2] - vel[5]*f[4] + vel[4]*f[5];
+  r[1] =  vel[2]*f[0] - vel[0]*f[2] + vel[5]*f[3] - vel[3]*f[5];
+  r[2] = -vel[1]*f[0] + vel[0]*f[1] - vel[4]*f[3] + vel[3]*f[4];
+  r[3] = -vel[2]*f[4] + vel[1]*f[5];
+  r[4] =  vel[2]*f[3] - vel[0]*f[5];
+  r[5] = -vel[1]*f[3] + vel[0]*f[4];
+}
+FB_DEV float v_normalize3(float *v) {
+  float n = sqrtf(v[0]*v[0] + v[1]*v[1] + v[2]*v[2]);
+  if (n < 1e-15f) { v[0] = 1.f; v[1] = 0.f; v[2] = 0.f; return n; }
+  float s = 1.0f/n;
+  v[0] *= s; v[1] *= s; v[2] *= s;
+  return n;
+}
+FB_DEV int pack_idx(int row, int col) { return row*(row + 1)/2 + col; }  /* row >= col */
+
+/* impedance sigmoid (mj getimpedance) */
+FB_DEV float fb_impedance(const float *solimp, float pos_minus_margin) {
+  float dmin = fminf(FB_MAXIMP, fmaxf(FB_MINIMP, solimp[0]));
+  float dmax = fminf(FB_MAXIMP, fmaxf(FB_MINIMP, solimp[1]));
+  float width = fmaxf(FB_MINVAL, solimp[2]);
+  float mid = fminf(FB_MAXIMP, fmaxf(FB_MINIMP, solimp[3]));
+  float power = fmaxf(1.0f, solimp[4]);
+  if (dmin == dmax || width <= FB_MINVAL) return 0.5f*(dmin + dmax);
+  float x = fabsf(pos_minus_margin)/width, y;
+  if (x >= 1.f) return dmax;
+  if (x <= 0.f) return dmin;
+  if (power == 1.f) y = x;
+  else if (x <= mid) y = powf(x, power)/powf(mid, power - 1.f);
+  else y = 1.f - powf(1.f - x, power)/powf(1.f - mid, power - 1.f);
+  return dmin + y*(dmax - dmin);
+}
+/* K, B, imp, R of one soft-constraint row (mj_makeImpedance) */
+FB_DEV void fb_row_params(float timestep, const float *solref_in, const float *solimp,
+                          float pos_minus_margin, float diag_approx,
+                          float *K, float *B, float *imp, float *R) {
+  float sr0 = solref_in[0], sr1 = solref_in[1];
+  if (sr0 > 0.f) sr0 = fmaxf(sr0, 2.f*timestep);
+  float dmax = fminf(FB_MAXIMP, fmaxf(FB_MINIMP, solimp[1]));
+  *imp = fb_impedance(solimp, pos_minus_margin);
+  *R = fmaxf(FB_MINVAL, (1.f - *imp)*diag_approx/(*imp));
+  if (sr0 > 0.f) {
+    *K = 1.f/fmaxf(FB_MINVAL, dmax*dmax*sr0*sr0*sr1*sr1);
+    *B = 2.f/fmaxf(FB_MINVAL, dmax*sr0);
+  } else {
+    *K = -sr0/fmaxf(FB_MINVAL, dmax*dmax);
+    *B = -sr1/fmaxf(FB_MINVAL, dmax);
+  }
+}
+
+/* ===================================================================== */
+template <int TEAM> struct FbStep {
+  typedef TeamOps<TEAM> T;
+  const DevModel &m;
+  float *s;     /* shared floats of this environment */
+  int *si;      /* shared ints of this environment */
+  EnvPtrs g;
+  int lane, base;
+  unsigned mask;
+  float comx, comy, comz;
+  int ncon, nlim;
+
+  FB_MEM FbStep(const DevModel &m_, float *s_, int *si_, const EnvPtrs &g_, int lane_, int base_,
+                unsigned mask_)
+      : m(m_), s(s_), si(si_), g(g_), lane(lane_), base(base_), mask(mask_),
+        comx(0.f), comy(0.f), comz(0.f), ncon(0), nlim(0) {}
+
+  FB_MEM void sync() { T::sync(mask); }
+
+  /* ------------------------------------------------------------ init */
+  FB_MEM void init_world() {
+    const int nb = m.nbody;
+    if (lane == 0) {
+      float *xpos = s + m.L.xpos, *xquat = s + m.L.xquat, *xipos = s + m.L.xipos;
+      float *cvel = s + m.L.cvel, *cin = s + m.L.cinert, *xf = s + m.L.xfrc;
+      for (int k = 0; k < 3; k++) { xpos[k*nb] = 0.f; xipos[k*nb] = 0.f; }
+      xquat[0] = 1.f; xquat[nb] = 0.f; xquat[2*nb] = 0.f; xquat[3*nb] = 0.f;
+      for (int k = 0; k < 6; k++) { cvel[k*nb] = 0.f; xf[k*nb] = 0.f; }
+      for (int k = 0; k < 10; k++) cin[k*nb] = 0.f;
+    }
+  }
+
+  /* ------------------------------------------------- A.1 kinematics */
+  FB_MEM void kinematics() {
+    const int nb = m.nbody, nj = m.njnt;
+    float *qpos = s + m.L.qpos, *xpos = s + m.L.xpos, *xquat = s + m.L.xquat;
+    float *xanchor = s + m.L.xanchor, *xaxis = s + m.L.xaxis;
+    for (int lv = 0; lv < m.nlevel; lv++) {
+      int i0 = MI(lvl_start, lv), i1 = MI(lvl_start, lv + 1);
+      for (int idx = i0 + lane; idx < i1; idx += TEAM) {
+        int b = MI(lvl_body, idx), p = MI(body_parent, b), jid = MI(body_jnt, b);
+        float pos[3], R[9], t[3];
+        Quat q;
+        int jtype = jid >= 0 ? MI(jnt_type, jid) : -1;
+        if (jtype == FB_JNT_FREE) {
+          int qa = MI(jnt_qposadr, jid);
+          pos[0] = qpos[qa]; pos[1] = qpos[qa+1]; pos[2] = qpos[qa+2];
+          Quat qq = {qpos[qa+3], qpos[qa+4], qpos[qa+5], qpos[qa+6]};
+          q = q_normalize(qq);
+          qpos[qa+3] = q.w; qpos[qa+4] = q.x; qpos[qa+5] = q.y; qpos[qa+6] = q.z;
+          xanchor[jid] = pos[0]; xanchor[nj + jid] = pos[1]; xanchor[2*nj + jid] = pos[2];
+          xaxis[jid] = 0.f; xaxis[nj + jid] = 0.f; xaxis[2*nj + jid] = 1.f;
+        } else {
+          Quat pq = {xquat[p], xquat[nb + p], xquat[2*nb + p], xquat[3*nb + p]};
+          q_mat(pq, R);
+          m_rot(R, MF(body_pos, 3*b), MF(body_pos, 3*b+1), MF(body_pos, 3*b+2), t);
+          pos[0] = xpos[p] + t[0]; pos[1] = xpos[nb + p] + t[1]; pos[2] = xpos[2*nb + p] + t[2];
+          Quat bq = {MF(body_quat, 4*b), MF(body_quat, 4*b+1), MF(body_quat, 4*b+2),
+                     MF(body_quat, 4*b+3)};
+          q = q_mul(pq, bq);
+          if (jid >= 0) {
+            int qa = MI(jnt_qposadr, jid);
+            float jp[3] = {MF(jnt_pos, 3*jid), MF(jnt_pos, 3*jid+1), MF(jnt_pos, 3*jid+2)};
+            float ja[3] = {MF(jnt_axis, 3*jid), MF(jnt_axis, 3*jid+1), MF(jnt_axis, 3*jid+2)};
+            float anchor[3], axis[3];
+            q_mat(q, R);
+            m_rot(R, jp[0], jp[1], jp[2], t);
+            anchor[0] = pos[0] + t[0]; anchor[1] = pos[1] + t[1]; anchor[2] = pos[2] + t[2];
+            m_rot(R, ja[0], ja[1], ja[2], axis);
+            xanchor[jid] = anchor[0]; xanchor[nj + jid] = anchor[1]; xanchor[2*nj + jid] = anchor[2];
+            xaxis[jid] = axis[0]; xaxis[nj + jid] = axis[1]; xaxis[2*nj + jid] = axis[2];
+            float dq = qpos[qa] - MF(jnt_qpos0, jid);
+            if (jtype == FB_JNT_HINGE) {
+              float sn, cs;
+              fb_sincos(0.5f*dq, &sn, &cs);
+              Quat ql = {cs, ja[0]*sn, ja[1]*sn, ja[2]*sn};
+              q = q_mul(q, ql);
+              q_mat(q, R);
+              m_rot(R, jp[0], jp[1], jp[2], t);
+              pos[0] = anchor[0] - t[0]; pos[1] = anchor[1] - t[1]; pos[2] = anchor[2] - t[2];
+            } else {
+              pos[0] += axis[0]*dq; pos[1] += axis[1]*dq; pos[2] += axis[2]*dq;
+            }
+          }
+        }
+        q = q_normalize(q);
+        xpos[b] = pos[0]; xpos[nb + b] = pos[1]; xpos[2*nb + b] = pos[2];
+        xquat[b] = q.w; xquat[nb + b] = q.x; xquat[2*nb + b] = q.y; xquat[3*nb + b] = q.z;
+      }
+      sync();
+    }
+  }
+
+  FB_MEM Quat body_quat(int b) const {
+    const float *xquat = s + m.L.xquat;
+    const int nb = m.nbody;
+    Quat q = {xquat[b], xquat[nb + b], xquat[2*nb + b], xquat[3*nb + b]};
+    return q;
+  }
+
+  /* ------------------------------------- A.2 xipos, com, cinert, cdof */
+  FB_MEM void com_pos() {
+    const int nb = m.nbody, nj = m.njnt, nv = m.nv;
+    float *xpos = s + m.L.xpos, *xipos = s + m.L.xipos, *cin = s + m.L.cinert;
+    float sx = 0.f, sy = 0.f, sz = 0.f;
+    for (int b = 1 + lane; b < nb; b += TEAM) {
+      float R[9], t[3];
+      q_mat(body_quat(b), R);
+      m_rot(R, MF(body_ipos, 3*b), MF(body_ipos, 3*b+1), MF(body_ipos, 3*b+2), t);
+      float x = xpos[b] + t[0], y = xpos[nb + b] + t[1], z = xpos[2*nb + b] + t[2];
+      xipos[b] = x; xipos[nb + b] = y; xipos[2*nb + b] = z;
+      float mb = MF(body_mass, b);
+      sx += mb*x; sy += mb*y; sz += mb*z;
+    }
+    sx = T::sum(mask, sx); sy = T::sum(mask, sy); sz = T::sum(mask, sz);
+    sync();
+    if (m.inv_total_mass > 0.f) {
+      comx = sx*m.inv_total_mass; comy = sy*m.inv_total_mass; comz = sz*m.inv_total_mass;
+    } else {
+      comx = xipos[1]; comy = xipos[nb + 1]; comz = xipos[2*nb + 1];
+    }
+    for (int b = 1 + lane; b < nb; b += TEAM) {
+      Quat bi = {MF(body_iquat, 4*b), MF(body_iquat, 4*b+1), MF(body_iquat, 4*b+2),
+                 MF(body_iquat, 4*b+3)};
+      float M[9];
+      q_mat(q_mul(body_quat(b), bi), M);
+      float i0 = MF(body_inertia, 3*b), i1 = MF(body_inertia, 3*b+1), i2 = MF(body_inertia, 3*b+2);
+      float mb = MF(body_mass, b);
+      float dx = xipos[b] - comx, dy = xipos[nb + b] - comy, dz = xipos[2*nb + b] - comz;
+      cin[0*nb + b] = M[0]*M[0]*i0 + M[1]*M[1]*i1 + M[2]*M[2]*i2 + mb*(dy*dy + dz*dz);
+      cin[1*nb + b] = M[3]*M[3]*i0 + M[4]*M[4]*i1 + M[5]*M[5]*i2 + mb*(dx*dx + dz*dz);
+      cin[2*nb + b] = M[6]*M[6]*i0 + M[7]*M[7]*i1 + M[8]*M[8]*i2 + mb*(dx*dx + dy*dy);
+      cin[3*nb + b] = M[0]*M[3]*i0 + M[1]*M[4]*i1 + M[2]*M[5]*i2 - mb*dx*dy;
+      cin[4*nb + b] = M[0]*M[6]*i0 + M[1]*M[7]*i1 + M[2]*M[8]*i2 - mb*dx*dz;
+      cin[5*nb + b] = M[3]*M[6]*i0 + M[4]*M[7]*i1 + M[5]*M[8]*i2 - mb*dy*dz;
+      cin[6*nb + b] = mb*dx; cin[7*nb + b] = mb*dy; cin[8*nb + b] = mb*dz; cin[9*nb + b] = mb;
+    }
+    /* cdof about com, world axes */
+    float *cdof = s + m.L.cdof;
+    const float *xanchor = s + m.L.xanchor, *xaxis = s + m.L.xaxis;
+    for (int j = lane; j < nj; j += TEAM) {
+      int da = MI(jnt_dofadr, j), jtype = MI(jnt_type, j);
+      float off[3] = {comx - xanchor[j], comy - xanchor[nj + j], comz - xanchor[2*nj + j]};
+      if (jtype == FB_JNT_FREE) {
+        float R[9];
+        q_mat(body_quat(MI(jnt_body, j)), R);
+        for (int i = 0; i < 3; i++) {
+          for (int k = 0; k < 6; k++) cdof[k*nv + da + i] = (k == 3 + i) ? 1.f : 0.f;
+          float ax[3] = {R[i], R[3 + i], R[6 + i]}, cr[3];
+          v_cross(ax, off, cr);
+          int d = da + 3 + i;
+          cdof[d] = ax[0]; cdof[nv + d] = ax[1]; cdof[2*nv + d] = ax[2];
+          cdof[3*nv + d] = cr[0]; cdof[4*nv + d] = cr[1]; cdof[5*nv + d] = cr[2];
+        }
+      } else {
+        float ax[3] = {xaxis[j], xaxis[nj + j], xaxis[2*nj + j]};
+        if (jtype == FB_JNT_HINGE) {
+          float cr[3];
+          v_cross(ax, off, cr);
+          cdof[da] = ax[0]; cdof[nv + da] = ax[1]; cdof[2*nv + da] = ax[2];
+          cdof[3*nv + da] = cr[0]; cdof[4*nv + da] = cr[1]; cdof[5*nv + da] = cr[2];
+        } else {
+          cdof[da] = 0.f; cdof[nv + da] = 0.f; cdof[2*nv + da] = 0.f;
+          cdof[3*nv + da] = ax[0]; cdof[4*nv + da] = ax[1]; cdof[5*nv + da] = ax[2];
+        }
+      }
+    }
+    sync();
+  }
+
+  /* ---------------- A.4 comVel + the forward half of RNE (cacc) */
+  FB_MEM void com_vel_acc() {
+    const int nb = m.nbody, nv = m.nv;
+    float *cvel = s + m.L.cvel, *cacc = s + m.L.cacc;
+    const float *cdof = s + m.L.cdof, *qvel = s + m.L.qvel;
+    if (lane == 0) {
+      cacc[0] = 0.f; cacc[nb] = 0.f; cacc[2*nb] = 0.f;
+      cacc[3*nb] = -m.grav[0]; cacc[4*nb] = -m.grav[1]; cacc[5*nb] = -m.grav[2];
+    }
+    sync();
+    for (int lv = 0; lv < m.nlevel; lv++) {
+      int i0 = MI(lvl_start, lv), i1 = MI(lvl_start, lv + 1);
+      for (int idx = i0 + lane; idx < i1; idx += TEAM) {
+        int b = MI(lvl_body, idx), p = MI(body_parent, b), jid = MI(body_jnt, b);
+        float cv[6], ca[6];
+        for (int k = 0; k < 6; k++) { cv[k] = cvel[k*nb + p]; ca[k] = cacc[k*nb + p]; }
+        if (jid >= 0) {
+          int da = MI(jnt_dofadr, jid);
+          if (MI(jnt_type, jid) == FB_JNT_FREE) {
+            /* translations: cdof_dot = 0 */
+            for (int i = 0; i < 3; i++) {
+              float qv = qvel[da + i];
+              for (int k = 0; k < 6; k++) cv[k] += cdof[k*nv + da + i]*qv;
+            }
+            float dd[3][6];
+            for (int i = 3; i < 6; i++) {
+              float cd[6];
+              for (int k = 0; k < 6; k++) cd[k] = cdof[k*nv + da + i];
+              cross_motion(cv, cd, dd[i-3]);
+            }
+            for (int i = 3; i < 6; i++) {
+              float qv = qvel[da + i];
+              for (int k = 0; k < 6; k++) {
+                ca[k] += dd[i-3][k]*qv;
+                cv[k] += cdof[k*nv + da + i]*qv;
+              }
+            }
+          } else {
+            float cd[6], dd[6], qv = qvel[da];
+            for (int k = 0; k < 6; k++) cd[k] = cdof[k*nv + da];
+            cross_motion(cv, cd, dd);
+            for (int k = 0; k < 6; k++) { ca[k] += dd[k]*qv; cv[k] += cd[k]*qv; }
+          }
+        }
+        for (int k = 0; k < 6; k++) { cvel[k*nb + b] = cv[k]; cacc[k*nb + b] = ca[k]; }
+      }
+      sync();
+    }
+  }
+
+  /* --- per-body bias wrench minus applied wrench; crb init; backward sweep */
+  FB_MEM void body_forces_and_crb() {
+    const int nb = m.nbody;
+    const float *cin = s + m.L.cinert, *cvel = s + m.L.cvel, *cacc = s + m.L.cacc;
+    const float *xipos = s + m.L.xipos, *xf = s + m.L.xfrc;
+    float *cfrc = s + m.L.cfrc, *crb = s + m.L.crb;
+    for (int b = lane; b < nb; b += TEAM) {
+      float I[10], v[6], a[6], t0[6], t1[6], t2[6];
+      for (int k = 0; k < 10; k++) { I[k] = cin[k*nb + b]; crb[k*nb + b] = I[k]; }
+      for (int k = 0; k < 6; k++) { v[k] = cvel[k*nb + b]; a[k] = cacc[k*nb + b]; }
+      inert_vec(I, a, t0);
+      inert_vec(I, v, t1);
+      cross_force(v, t1, t2);
+      /* xfrc_applied: world force F, torque T at xipos -> spatial force about com */
+      float F[3] = {xf[b], xf[nb + b], xf[2*nb + b]};
+      float Tq[3] = {xf[3*nb + b], xf[4*nb + b], xf[5*nb + b]};
+      float off[3] = {xipos[b] - comx, xipos[nb + b] - comy, xipos[2*nb + b] - comz}, cr[3];
+      v_cross(off, F, cr);
+      if (b == 0) { for (int k = 0; k < 6; k++) cfrc[k*nb] = 0.f; continue; }
+      cfrc[0*nb + b] = t0[0] + t2[0] - (Tq[0] + cr[0]);
+      cfrc[1*nb + b] = t0[1] + t2[1] - (Tq[1] + cr[1]);
+      cfrc[2*nb + b] = t0[2] + t2[2] - (Tq[2] + cr[2]);
+      cfrc[3*nb + b] = t0[3] + t2[3] - F[0];
+      cfrc[4*nb + b] = t0[4] + t2[4] - F[1];
+      cfrc[5*nb + b] = t0[5] + t2[5] - F[2];
+    }
+    sync();
+    /* children -> parents, deepest level first; parents gather (deterministic) */
+    for (int lv = m.nlevel - 2; lv >= 0; lv--) {
+      int i0 = MI(lvl_start, lv), i1 = MI(lvl_start, lv + 1);
+      for (int idx = i0 + lane; idx < i1; idx += TEAM) {
+        int p = MI(lvl_body, idx);
+        for (int c = MI(body_firstchild, p); c >= 0; c = MI(body_nextsib, c)) {
+          for (int k = 0; k < 10; k++) crb[k*nb + p] += crb[k*nb + c];
+          for (int k = 0; k < 6; k++) cfrc[k*nb + p] += cfrc[k*nb + c];
+        }
+      }
+      sync();
+    }
+  }
+
+  /* ----------- A.3 mass matrix entries, bias, actuation, passive -> fsm */
+  FB_MEM void mass_matrix_and_smooth() {
+    const int nb = m.nbody, nv = m.nv, nu = m.nu;
+    const float *crb = s + m.L.crb, *cfrc = s + m.L.cfrc, *cdof = s + m.L.cdof;
+    const float *qpos = s + m.L.qpos, *qvel = s + m.L.qvel, *ctrl = s + m.L.ctrl;
+    float *buf = s + m.L.buf, *fsm = s + m.L.fsm, *qM = s + m.L.qM, *actf = s + m.L.actf;
+    for (int d = lane; d < nv; d += TEAM) {
+      int b = MI(dof_body, d);
+      float I[10], c[6], r[6], bias = 0.f;
+      for (int k = 0; k < 10; k++) I[k] = crb[k*nb + b];
+      for (int k = 0; k < 6; k++) { c[k] = cdof[k*nv + d]; bias += c[k]*cfrc[k*nb + b]; }
+      inert_vec(I, c, r);
+      for (int k = 0; k < 6; k++) buf[k*nv + d] = r[k];
+      fsm[d] = -bias;
+    }
+    for (int a = lane; a < nu; a += TEAM) {
+      int j = MI(act_jnt, a);
+      float gear = MF(act_gear, a);
+      float len = gear*qpos[MI(jnt_qposadr, j)], vel = gear*qvel[MI(jnt_dofadr, j)];
+      float c = ctrl[a];
+      if (MI(act_ctrllimited, a)) c = fminf(MF(act_ctrlrange, 2*a+1), fmaxf(MF(act_ctrlrange, 2*a), c));
+      float f = MF(act_gain, a)*c + MF(act_bias, 3*a) + MF(act_bias, 3*a+1)*len + MF(act_bias, 3*a+2)*vel;
+      if (MI(act_forcelimited, a)) f = fminf(MF(act_forcerange, 2*a+1), fmaxf(MF(act_forcerange, 2*a), f));
+      actf[a] = f;
+    }
+    sync();
+    for (int e = lane; e < m.nM; e += TEAM) {
+      int i = MI(ent_i, e), j = MI(ent_j, e);
+      float v = 0.f;
+      for (int k = 0; k < 6; k++) v += cdof[k*nv + j]*buf[k*nv + i];
+      if (i == j) v += MF(dof_armature, i);
+      qM[e] = v;
+    }
+    for (int d = lane; d < nv; d += TEAM) {
+      int j = MI(dof_jnt, d);
+      float f = fsm[d];
+      if (MI(jnt_type, j) != FB_JNT_FREE) {
+        int qa = MI(jnt_qposadr, j);
+        float stiff = MF(jnt_stiffness, j);
+        if (stiff != 0.f) f -= stiff*(qpos[qa] - g.qpos_spring[qa]);
+        int a0 = MI(jnt_actstart, j), a1 = MI(jnt_actstart, j + 1);
+        for (int t = a0; t < a1; t++) { int a = MI(act_sorted, t); f += MF(act_gear, a)*actf[a]; }
+      }
+      f -= MF(dof_damping, d)*qvel[d];
+      fsm[d] = f;
+    }
+    sync();
+  }
+
+  /* ------------------------------ sparse L'DL (mj_factorI) and solve */
+  FB_MEM void factor(float hdamp) {
+    const int nv = m.nv;
+    const float *qM = s + m.L.qM;
+    float *qLD = s + m.L.qLD, *dinv = s + m.L.dinv;
+    for (int e = lane; e < m.nM; e += TEAM) {
+      int i = MI(ent_i, e);
+      float v = qM[e];
+      if (hdamp != 0.f && i == MI(ent_j, e)) v += hdamp*MF(dof_damping, i);
+      qLD[e] = v;
+    }
+    sync();
+    for (int k = nv - 1; k >= 0; k--) {
+      int nk = MI(dof_nanc, k), adr = MI(dof_Madr, k);
+      if (nk > 1) {
+        float inv = 1.0f/qLD[adr];
+        /* lane owns ancestor row s: row(a_s)[t-s] -= L_ks * M_kt / M_kk */
+        for (int sdx = 1 + lane; sdx < nk; sdx += TEAM) {
+          int as = MI(ent_j, adr + sdx), ra = MI(dof_Madr, as);
+          float tmp = qLD[adr + sdx]*inv;
+          for (int t = sdx; t < nk; t++) qLD[ra + t - sdx] -= tmp*qLD[adr + t];
+        }
+        sync();
+        for (int sdx = 1 + lane; sdx < nk; sdx += TEAM) qLD[adr + sdx] *= inv;
+        sync();
+      }
+    }
+    for (int k = lane; k < nv; k += TEAM) dinv[k] = 1.0f/qLD[MI(dof_Madr, k)];
+    sync();
+  }
+
+  /* x <- inv(L'DL) x, x in shared memory */
+  FB_MEM void solve_ld(float *x) {
+    const int nv = m.nv;
+    const float *qLD = s + m.L.qLD, *dinv = s + m.L.dinv;
+    for (int k = nv - 1; k > 0; k--) {
+      int nk = MI(dof_nanc, k), adr = MI(dof_Madr, k);
+      if (nk > 1) {
+        float xk = x[k];
+        for (int sdx = 1 + lane; sdx < nk; sdx += TEAM) x[MI(ent_j, adr + sdx)] -= qLD[adr + sdx]*xk;
+        sync();
+      }
+    }
+    for (int k = lane; k < nv; k += TEAM) x[k] *= dinv[k];
+    sync();
+    for (int k = 1; k < nv; k++) {
+      int nk = MI(dof_nanc, k), adr = MI(dof_Madr, k);
+      if (nk > 1) {
+        float part = 0.f;
+        for (int sdx = 1 + lane; sdx < nk; sdx += TEAM) part += qLD[adr + sdx]*x[MI(ent_j, adr + sdx)];
+        part = T::sum(mask, part);
+        if (lane == 0) x[k] -= part;
+        sync();
+      }
+    }
+  }
+
+  /* ---------------------------------- A.6/A.7 constraint detection */
+  FB_MEM void detect_constraints() {
+    const int nb = m.nbody, nj = m.njnt;
+    const float *qpos = s + m.L.qpos, *qvel = s + m.L.qvel, *xpos = s + m.L.xpos;
+    float *limf = s + m.L.limf;
+    float *aref = g.efc, *D = g.efc + m.maxefc;
+    int *con_cand = si + m.L.con_cand;
+    /* joint limits: candidate lc = 2*j + side_index (0 lower, 1 upper) */
+    float cnt = 0.f;
+    for (int j = lane; j < nj; j += TEAM) {
+      limf[j] = 0.f;
+      int limited = MI(jnt_limited, j) && MI(jnt_type, j) != FB_JNT_FREE;
+      float value = limited ? qpos[MI(jnt_qposadr, j)] : 0.f;
+      float margin = MF(jnt_margin, j);
+      for (int sd = 0; sd < 2; sd++) {
+        float side = sd ? 1.f : -1.f;
+        float dist = side*(MF(jnt_range, 2*j + sd) - value);
+        float d = 0.f, ar = 0.f;
+        if (limited && dist < margin) {
+          float sr[2] = {MF(jnt_solref, 2*j), MF(jnt_solref, 2*j+1)}, si5[5];
+          for (int k = 0; k < 5; k++) si5[k] = MF(jnt_solimp, 5*j + k);
+          int dof = MI(jnt_dofadr, j);
+          float K, B, imp, R;
+          fb_row_params(m.timestep, sr, si5, dist - margin, MF(dof_invw, dof), &K, &B, &imp, &R);
+          d = 1.0f/R;
+          ar = -B*(-side*qvel[dof]) - K*imp*(dist - margin);
+          cnt += 1.f;
+        }
+        D[2*j + sd] = d;
+        aref[2*j + sd] = ar;
+      }
+    }
+    nlim = (int)(T::sum(mask, cnt) + 0.5f);
+    /* plane vs sphere / capsule end; compact in candidate order */
+    int n = 0;
+    for (int c0 = 0; c0 < m.ncand; c0 += TEAM) {
+      int c = c0 + lane;
+      int hit = 0;
+      float dist = 0.f, centre[3] = {0.f, 0.f, 0.f}, nrm[3] = {0.f, 0.f, 1.f}, R[9], radius = 0.f;
+      int b = 0;
+      if (c < m.ncand) {
+        b = MI(cand_body, c);
+        q_mat(body_quat(b), R);
+        float t[3];
+        m_rot(R, MF(cand_lpos, 3*c), MF(cand_lpos, 3*c+1), MF(cand_lpos, 3*c+2), t);
+        centre[0] = xpos[b] + t[0]; centre[1] = xpos[nb + b] + t[1]; centre[2] = xpos[2*nb + b] + t[2];
+        nrm[0] = MF(cand_pn, 3*c); nrm[1] = MF(cand_pn, 3*c+1); nrm[2] = MF(cand_pn, 3*c+2);
+        radius = MF(cand_radius, c);
+        float cdist = centre[0]*nrm[0] + centre[1]*nrm[1] + centre[2]*nrm[2] - MF(cand_pd, c);
+        dist = cdist - radius;
+        hit = dist < MF(cand_margin, c) - MF(cand_gap, c);
+      }
+      unsigned bits = T::ballot(mask, base, hit);
+      if (hit) {
+        int i = n + FB_POPC(bits & ((1u << lane) - 1u));
+        con_cand[i] = c;
+        g.d_con_cand[i] = c;
+        g.d_con_dist[i] = dist;
+        float f[9];
+        for (int k = 0; k < 3; k++) {
+          g.d_con_pos[3*i + k] = centre[k] - nrm[k]*(radius + 0.5f*dist);
+          f[k] = nrm[k];
+        }
+        if (MI(cand_iscapsule, c)) {
+          m_rot(R, MF(cand_laxis, 3*c), MF(cand_laxis, 3*c+1), MF(cand_laxis, 3*c+2), f + 3);
+        } else {
+          f[3] = f[4] = f[5] = 0.f;
+        }
+        /* mju_makeFrame */
+        v_normalize3(f);
+        if (sqrtf(f[3]*f[3] + f[4]*f[4] + f[5]*f[5]) < 0.5f) {
+          f[3] = f[4] = f[5] = 0.f;
+          if (f[1] < 0.5f && f[1] > -0.5f) f[4] = 1.f; else f[5] = 1.f;
+        }
+        float dt = f[0]*f[3] + f[1]*f[4] + f[2]*f[5];
+        f[3] -= dt*f[0]; f[4] -= dt*f[1]; f[5] -= dt*f[2];
+        v_normalize3(f + 3);
+        v_cross(f, f + 3, f + 6);
+        for (int k = 0; k < 9; k++) g.d_con_frame[9*i + k] = f[k];
+      }
+      n += FB_POPC(bits);
+    }
+    ncon = n;
+    if (lane == 0) *g.d_ncon = n;
+    sync();
+  }
+
+  /* ---------------------------- contact rows: J3, D, aref (A.7) */
+  FB_MEM void make_contact_rows() {
+    const int nv = m.nv, nj = m.njnt;
+    const float *cdof = s + m.L.cdof, *qvel = s + m.L.qvel;
+    const int *con_cand = si + m.L.con_cand;
+    float *aref = g.efc, *D = g.efc + m.maxefc;
+    for (int i = 0; i < ncon; i++) {
+      int c = con_cand[i], b = MI(cand_body, c);
+      float off[3] = {g.d_con_pos[3*i] - comx, g.d_con_pos[3*i+1] - comy, g.d_con_pos[3*i+2] - comz};
+      float f[9];
+      for (int k = 0; k < 9; k++) f[k] = g.d_con_frame[9*i + k];
+      for (int v = lane; v < nv; v += TEAM) {
+        float j0 = 0.f, j1 = 0.f, j2 = 0.f;
+        if ((unsigned)MI(body_ancmask, b*m.nmaskw + (v >> 5)) >> (v & 31) & 1u) {
+          float ang[3] = {cdof[v], cdof[nv + v], cdof[2*nv + v]}, cr[3];
+          v_cross(ang, off, cr);
+          float lx = cdof[3*nv + v] + cr[0], ly = cdof[4*nv + v] + cr[1], lz = cdof[5*nv + v] + cr[2];
+          j0 = f[0]*lx + f[1]*ly + f[2]*lz;
+          j1 = f[3]*lx + f[4]*ly + f[5]*lz;
+          j2 = f[6]*lx + f[7]*ly + f[8]*lz;
+        }
+        g.J3[(3*i)*nv + v] = j0; g.J3[(3*i+1)*nv + v] = j1; g.J3[(3*i+2)*nv + v] = j2;
+      }
+    }
+    sync();
+    j3_times(qvel);  /* prod3 <- J3 qvel */
+    for (int i = lane; i < ncon; i += TEAM) {
+      int c = con_cand[i];
+      float mu = MF(cand_friction, c), dist = g.d_con_dist[i];
+      float includemargin = MF(cand_margin, c) - MF(cand_gap, c);
+      float sr[2] = {MF(cand_solref, 2*c), MF(cand_solref, 2*c+1)}, si5[5];
+      for (int k = 0; k < 5; k++) si5[k] = MF(cand_solimp, 5*c + k);
+      float tran = MF(cand_invw, c);
+      float K, B, imp, R;
+      fb_row_params(m.timestep, sr, si5, dist - includemargin, tran + mu*mu*tran, &K, &B, &imp, &R);
+      float impratio = fmaxf(FB_MINVAL, m.impratio);
+      float R1 = R/impratio;
+      float cmu2 = mu*mu*(R1/R);
+      float Rpy = fmaxf(FB_MINVAL, 2.f*cmu2*R1);
+      float vn = g.prod3[3*i], vt1 = g.prod3[3*i+1], vt2 = g.prod3[3*i+2];
+      for (int sub = 0; sub < 4; sub++) {
+        float sg = (sub & 1) ? -1.f : 1.f;
+        float vel = vn + sg*mu*((sub < 2) ? vt1 : vt2);
+        int r = 2*nj + 4*i + sub;
+        D[r] = 1.0f/Rpy;
+        aref[r] = -B*vel - K*imp*(dist - includemargin);
+      }
+    }
+    sync();
+  }
+
+  /* prod3[r3] <- sum_v J3[r3][v] x[v] */
+  FB_MEM void j3_times(const float *x) {
+    const int nv = m.nv;
+    for (int r3 = 0; r3 < 3*ncon; r3++) {
+      float part = 0.f;
+      for (int v = lane; v < nv; v += TEAM) part += g.J3[r3*nv + v]*x[v];
+      part = T::sum(mask, part);
+      if (lane == 0) g.prod3[r3] = part;
+    }
+    sync();
+  }
+
+  /* out[r] <- J_r x for every row (limit candidates, then contact rows) */
+  FB_MEM void rows_apply(const float *x, float *out) {
+    const int nj = m.njnt;
+    j3_times(x);
+    for (int j = lane; j < nj; j += TEAM) {
+      float xv = x[MI(jnt_dofadr, j)];
+      out[2*j] = xv;       /* lower: jac = +1 */
+      out[2*j + 1] = -xv;  /* upper: jac = -1 */
+    }
+    const int *con_cand = si + m.L.con_cand;
+    for (int i = lane; i < ncon; i += TEAM) {
+      float mu = MF(cand_friction, con_cand[i]);
+      float pn = g.prod3[3*i], p1 = g.prod3[3*i+1], p2 = g.prod3[3*i+2];
+      int r = 2*nj + 4*i;
+      out[r] = pn + mu*p1; out[r+1] = pn - mu*p1; out[r+2] = pn + mu*p2; out[r+3] = pn - mu*p2;
+    }
+    sync();
+  }
+
+  /* out[v] (+)= sum_r J_r[v] y[r];  y in global efc scratch */
+  FB_MEM void rows_tapply(const float *y, float *out, int accumulate) {
+    const int nv = m.nv, nj = m.njnt;
+    const int *con_cand = si + m.L.con_cand;
+    float *y3 = g.prod3 + 3*m.maxcon;
+    for (int i = lane; i < ncon; i += TEAM) {
+      float mu = MF(cand_friction, con_cand[i]);
+      const float *yy = y + 2*nj + 4*i;
+      y3[3*i] = yy[0] + yy[1] + yy[2] + yy[3];
+      y3[3*i+1] = mu*(yy[0] - yy[1]);
+      y3[3*i+2] = mu*(yy[2] - yy[3]);
+    }
+    sync();
+    for (int v = lane; v < nv; v += TEAM) {
+      float acc = accumulate ? out[v] : 0.f;
+      int j = MI(dof_jnt, v);
+      if (MI(jnt_type, j) != FB_JNT_FREE) acc += y[2*j] - y[2*j + 1];
+      for (int r3 = 0; r3 < 3*ncon; r3++) acc += g.J3[r3*nv + v]*y3[r3];
+      out[v] = acc;
+    }
+    sync();
+  }
+
+  /* dense packed symmetric matvec: out = Md x */
+  FB_MEM void md_times(const float *x, float *out) {
+    const int nv = m.nv;
+    const float *Md = s + m.L.Md;
+    for (int u = lane; u < nv; u += TEAM) {
+      float acc = 0.f;
+      for (int v = 0; v <= u; v++) acc += Md[pack_idx(u, v)]*x[v];
+      for (int v = u + 1; v < nv; v++) acc += Md[pack_idx(v, u)]*x[v];
+      out[u] = acc;
+    }
+    sync();
+  }
+
+  /* ------------------------------------ A.8 primal Newton, exact line search */
+  FB_MEM void solve_constraints(float *tmp1, float *tmp2) {
+    const int nv = m.nv, nj = m.njnt;
+    const int nrow = 2*nj + 4*ncon;
+    const int *con_cand = si + m.L.con_cand;
+    float *qacc = s + m.L.qacc, *fsm = s + m.L.fsm, *fcon = s + m.L.fcon;
+    float *grad = s + m.L.grad, *p = s + m.L.pvec, *Md = s + m.L.Md, *H = s + m.L.H;
+    const float *qM = s + m.L.qM;
+    float *aref = g.efc, *D = g.efc + m.maxefc, *res = g.efc + 2*m.maxefc,
+          *jp = g.efc + 3*m.maxefc, *frc = g.efc + 4*m.maxefc;
+    /* dense packed copy of M */
+    for (int e = lane; e < m.npack; e += TEAM) Md[e] = 0.f;
+    sync();
+    for (int e = lane; e < m.nM; e += TEAM) Md[pack_idx(MI(ent_i, e), MI(ent_j, e))] = qM[e];
+    sync();
+    int maxit = m.solver_iterations < 50 ? m.solver_iterations : 50;
+    for (int it = 0; it < maxit; it++) {
+      rows_apply(qacc, res);
+      for (int r = lane; r < nrow; r += TEAM) {
+        float rr = res[r] - aref[r];
+        res[r] = rr;
+        frc[r] = (rr < 0.f) ? D[r]*rr : 0.f;   /* y = D min(0, res) */
+      }
+      sync();
+      md_times(qacc, tmp1);                      /* tmp1 = M a */
+      for (int v = lane; v < nv; v += TEAM) { tmp1[v] -= fsm[v]; grad[v] = tmp1[v]; }
+      sync();
+      rows_tapply(frc, grad, 1);                 /* grad = M a - fsm + J' y */
+      float gn = 0.f;
+      for (int v = lane; v < nv; v += TEAM) gn += grad[v]*grad[v];
+      gn = T::sum(mask, gn);
+      if (sqrtf(gn)*m.solver_scale < m.tolerance) break;
+      /* H = M + sum_active D J'J (packed lower) */
+      for (int e = lane; e < m.npack; e += TEAM) {
+        int u = (int)((sqrtf(8.f*(float)e + 1.f) - 1.f)*0.5f);
+        while (pack_idx(u + 1, 0) <= e) u++;
+        while (pack_idx(u, 0) > e) u--;
+        int v = e - pack_idx(u, 0);
+        float h = Md[e];
+        if (u == v) {
+          int j = MI(dof_jnt, u);
+          if (MI(jnt_type, j) != FB_JNT_FREE) {
+            if (res[2*j] < 0.f) h += D[2*j];
+            if (res[2*j+1] < 0.f) h += D[2*j+1];
+          }
+        }
+        for (int i = 0; i < ncon; i++) {
+          int c = con_cand[i], b = MI(cand_body, c);
+          unsigned wu = (unsigned)MI(body_ancmask, b*m.nmaskw + (u >> 5));
+          unsigned wv = (unsigned)MI(body_ancmask, b*m.nmaskw + (v >> 5));
+          if (!((wu >> (u & 31)) & (wv >> (v & 31)) & 1u)) continue;
+          int r = 2*nj + 4*i;
+          float d = D[r], mu = MF(cand_friction, c);
+          float nu_ = g.J3[(3*i)*nv + u], nv_ = g.J3[(3*i)*nv + v];
+          float t1u = mu*g.J3[(3*i+1)*nv + u], t1v = mu*g.J3[(3*i+1)*nv + v];
+          float t2u = mu*g.J3[(3*i+2)*nv + u], t2v = mu*g.J3[(3*i+2)*nv + v];
+          if (res[r] < 0.f) h += d*(nu_ + t1u)*(nv_ + t1v);
+          if (res[r+1] < 0.f) h += d*(nu_ - t1u)*(nv_ - t1v);
+          if (res[r+2] < 0.f) h += d*(nu_ + t2u)*(nv_ + t2v);
+          if (res[r+3] < 0.f) h += d*(nu_ - t2u)*(nv_ - t2v);
+        }
+        H[e] = h;
+      }
+      sync();
+      /* in-place packed Cholesky H = L L' */
+      int bad = 0;
+      for (int j = 0; j < nv; j++) {
+        float djj = H[pack_idx(j, j)];
+        if (!(djj > 0.f)) { bad = 1; break; }
+        float dj = sqrtf(djj), idj = 1.0f/dj;
+        sync();
+        for (int i = j + 1 + lane; i < nv; i += TEAM) H[pack_idx(i, j)] *= idj;
+        if (lane == 0) H[pack_idx(j, j)] = dj;
+        sync();
+        for (int i = j + 1 + lane; i < nv; i += TEAM) {
+          float lij = H[pack_idx(i, j)];
+          int rowi = pack_idx(i, 0);
+          for (int k = j + 1; k <= i; k++) H[rowi + k] -= lij*H[pack_idx(k, j)];
+        }
+        sync();
+      }
+      if (bad) { if (lane == 0) FB_FLAG_OR(g.flags, FB_FLAG_SOLVER); break; }
+      /* p = -H^-1 grad : forward (into tmp2), backward (into p) */
+      for (int j = 0; j < nv; j++) {
+        float yj = -grad[j]/H[pack_idx(j, j)];
+        sync();
+        for (int i = j + 1 + lane; i < nv; i += TEAM) grad[i] += H[pack_idx(i, j)]*yj;
+        if (lane == 0) tmp2[j] = yj;
+        sync();
+      }
+      for (int j = nv - 1; j >= 0; j--) {
+        float xj = tmp2[j]/H[pack_idx(j, j)];
+        sync();
+        for (int i = lane; i < j; i += TEAM) tmp2[i] -= H[pack_idx(j, i)]*xj;
+        if (lane == 0) p[j] = xj;
+        sync();
+      }
+      /* exact line search on phi'(alpha) = g0 + alpha pMp + sum D jp min(0, res + alpha jp) */
+      rows_apply(p, jp);
+      md_times(p, tmp2);
+      float pMp = 0.f, g0 = 0.f;
+      for (int v = lane; v < nv; v += TEAM) { pMp += p[v]*tmp2[v]; g0 += p[v]*tmp1[v]; }
+      pMp = T::sum(mask, pMp);
+      g0 = T::sum(mask, g0);
+      float lo = 0.f, hi = 3.0e38f;
+      for (int r = lane; r < nrow; r += TEAM) {
+        float dr = D[r], jr = jp[r];
+        if (dr <= 0.f || jr == 0.f) continue;
+        float al = -res[r]/jr;
+        if (!(al > 0.f)) continue;
+        float gv = g0 + al*pMp;
+        for (int q = 0; q < nrow; q++) {
+          float dq = D[q];
+          if (dq > 0.f) gv += dq*jp[q]*fminf(0.f, res[q] + al*jp[q]);
+        }
+        if (gv <= 0.f) lo = fmaxf(lo, al); else hi = fminf(hi, al);
+      }
+      lo = T::max(mask, lo);
+      hi = T::min(mask, hi);
+      float am = hi < 1.0e38f ? 0.5f*(lo + hi) : lo + 1.0f;
+      float glo = 0.f, slope = 0.f;
+      for (int r = lane; r < nrow; r += TEAM) {
+        float dr = D[r];
+        if (dr <= 0.f) continue;
+        float jr = jp[r];
+        glo += dr*jr*fminf(0.f, res[r] + lo*jr);
+        if (res[r] + am*jr < 0.f) slope += dr*jr*jr;
+      }
+      glo = T::sum(mask, glo) + g0 + lo*pMp;
+      slope = T::sum(mask, slope) + pMp;
+      float alpha = slope > 0.f ? lo - glo/slope : 1.0f;
+      if (!(alpha > 0.f) || alpha != alpha) alpha = lo > 0.f ? lo : 1.0f;
+      if (hi < 1.0e38f && alpha > hi) alpha = hi;
+      float st = 0.f, a2 = 0.f;
+      for (int v = lane; v < nv; v += TEAM) {
+        float dv = alpha*p[v], nvv = qacc[v] + dv;
+        st += dv*dv; a2 += nvv*nvv;
+      }
+      st = T::sum(mask, st);
+      a2 = T::sum(mask, a2);
+      sync();
+      for (int v = lane; v < nv; v += TEAM) qacc[v] += alpha*p[v];
+      sync();
+      if (st <= 1e-14f*a2) break;
+    }
+    /* constraint forces */
+    rows_apply(qacc, res);
+    for (int r = lane; r < nrow; r += TEAM) {
+      float rr = res[r] - aref[r];
+      frc[r] = (rr < 0.f) ? -D[r]*rr : 0.f;
+    }
+    sync();
+    rows_tapply(frc, fcon, 0);
+    float *limf = s + m.L.limf;
+    for (int j = lane; j < nj; j += TEAM) {
+      /* jointlimitfrc = efc_force of the joint's first active limit row */
+      limf[j] = D[2*j] > 0.f ? frc[2*j] : (D[2*j+1] > 0.f ? frc[2*j+1] : 0.f);
+    }
+    for (int i = lane; i < ncon; i += TEAM) {
+      float mu = MF(cand_friction, con_cand[i]);
+      const float *f = frc + 2*nj + 4*i;
+      g.d_con_force[3*i] = f[0] + f[1] + f[2] + f[3];
+      g.d_con_force[3*i+1] = (f[0] - f[1])*mu;
+      g.d_con_force[3*i+2] = (f[2] - f[3])*mu;
+    }
+    sync();
+  }
+
+  /* --------------------------------------- mj_forward for this state */
+  FB_MEM void forward(int want_qacc) {
+    const int nv = m.nv;
+    float *fsm = s + m.L.fsm, *qacc = s + m.L.qacc, *fcon = s + m.L.fcon;
+    kinematics();
+    com_pos();
+    com_vel_acc();
+    body_forces_and_crb();
+    mass_matrix_and_smooth();
+    detect_constraints();
+    for (int v = lane; v < nv; v += TEAM) fcon[v] = 0.f;
+    int active = (nlim + ncon) > 0;
+    if (active || want_qacc || !m.any_damping) {
+      factor(0.f);
+      for (int v = lane; v < nv; v += TEAM) qacc[v] = fsm[v];
+      sync();
+      solve_ld(qacc);
+      if (active) {
+        if (ncon > 0) make_contact_rows();
+        solve_constraints(s + m.L.tmp1, s + m.L.tmp2);
+      }
+    }
+    sync();
+  }
+
+  /* ------------------------------------------- A.10 Euler integrator */
+  FB_MEM void euler() {
+    const int nv = m.nv, nj = m.njnt;
+    float *qpos = s + m.L.qpos, *qvel = s + m.L.qvel, *fsm = s + m.L.fsm, *fcon = s + m.L.fcon;
+    float *x = s + m.L.grad;
+    const float h = m.timestep;
+    if (m.any_damping) {
+      factor(h);
+      for (int v = lane; v < nv; v += TEAM) x[v] = fsm[v] + fcon[v];
+      sync();
+      solve_ld(x);
+    } else {
+      const float *qacc = s + m.L.qacc;
+      for (int v = lane; v < nv; v += TEAM) x[v] = qacc[v];
+      sync();
+    }
+    for (int v = lane; v < nv; v += TEAM) qvel[v] += h*x[v];
+    sync();
+    int bad = 0;
+    for (int j = lane; j < nj; j += TEAM) {
+      int qa = MI(jnt_qposadr, j), da = MI(jnt_dofadr, j);
+      if (MI(jnt_type, j) == FB_JNT_FREE) {
+        for (int k = 0; k < 3; k++) qpos[qa + k] += h*qvel[da + k];
+        float w[3] = {qvel[da + 3], qvel[da + 4], qvel[da + 5]};
+        float angle = h*v_normalize3(w), sn, cs;
+        fb_sincos(0.5f*angle, &sn, &cs);
+        Quat qr = {cs, w[0]*sn, w[1]*sn, w[2]*sn};
+        Quat q0 = {qpos[qa + 3], qpos[qa + 4], qpos[qa + 5], qpos[qa + 6]};
+        Quat qn = q_normalize(q_mul(q_normalize(q0), qr));
+        qpos[qa + 3] = qn.w; qpos[qa + 4] = qn.x; qpos[qa + 5] = qn.y; qpos[qa + 6] = qn.z;
+        for (int k = 0; k < 7; k++) bad |= !(fabsf(qpos[qa + k]) < 1e30f);
+      } else {
+        qpos[qa] += h*qvel[da];
+        bad |= !(fabsf(qpos[qa]) < 1e30f);
+      }
+    }
+    if (bad) FB_FLAG_OR(g.flags, FB_FLAG_NONFINITE);
+    sync();
+  }
+
+  /* ------------- physics2data + cycontacts2data + drag (fused log stage) */
+  FB_MEM void body_velocity(int b, float *lin, float *ang) const {
+    const int nb = m.nbody;
+    const float *cvel = s + m.L.cvel, *xipos = s + m.L.xipos;
+    ang[0] = cvel[b]; ang[1] = cvel[nb + b]; ang[2] = cvel[2*nb + b];
+    float off[3] = {xipos[b] - comx, xipos[nb + b] - comy, xipos[2*nb + b] - comz}, cr[3];
+    v_cross(ang, off, cr);
+    lin[0] = cvel[3*nb + b] + cr[0]; lin[1] = cvel[4*nb + b] + cr[1]; lin[2] = cvel[5*nb + b] + cr[2];
+  }
+
+  FB_MEM void write_log() {
+    const int nb = m.nbody, nj = m.njnt;
+    const float *xpos = s + m.L.xpos, *xipos = s + m.L.xipos;
+    const float *qpos = s + m.L.qpos, *qvel = s + m.L.qvel, *actf = s + m.L.actf;
+    const float *limf = s + m.L.limf;
+    float *xf = s + m.L.xfrc;
+    /* links: physics.py:449-466 + :435-446 */
+    for (int l = lane; l < m.n_links; l += TEAM) {
+      int b = MI(link_body, l);
+      Quat q = body_quat(b);
+      float lin[3], ang[3];
+      body_velocity(b, lin, ang);
+      float *row = g.row_links + 20*l;
+      float im = m.inv_meters;
+      row[0] = xipos[b]*im; row[1] = xipos[nb + b]*im; row[2] = xipos[2*nb + b]*im;
+      row[3] = q.x; row[4] = q.y; row[5] = q.z; row[6] = q.w;
+      row[7] = xpos[b]*im; row[8] = xpos[nb + b]*im; row[9] = xpos[2*nb + b]*im;
+      row[10] = q.x; row[11] = q.y; row[12] = q.z; row[13] = q.w;
+      row[14] = lin[0]*m.inv_velocity; row[15] = lin[1]*m.inv_velocity; row[16] = lin[2]*m.inv_velocity;
+      row[17] = ang[0]*m.inv_angvel; row[18] = ang[1]*m.inv_angvel; row[19] = ang[2]*m.inv_angvel;
+    }
+    /* joints: physics.py:481-524 (the torque family is empty in the reference, D-4) */
+    for (int j = lane; j < m.n_joints; j += TEAM) {
+      float *row = g.row_joints + m.joint_cols*j;
+      for (int k = 0; k < m.joint_cols; k++) row[k] = 0.f;
+      row[m.col_jpos] = qpos[MI(fj_qposadr, j)];
+      row[m.col_jvel] = qvel[MI(fj_dofadr, j)]*m.inv_angvel;
+      float trq = 0.f;
+      int ap = MI(fj_actpos, j), av = MI(fj_actvel, j), at = MI(fj_acttrq, j);
+      if (ap >= 0) trq += actf[ap];
+      if (av >= 0) trq += actf[av];
+      if (at >= 0) trq += actf[at];
+      row[m.col_jtrq] = trq*m.inv_torques;
+      int jid = MI(fj_jntid, j);
+      row[m.col_jlim] = jid >= 0 ? limf[jid]*m.inv_torques : 0.f;
+    }
+    /* contacts: sensors.pyx:140-190 */
+    const int *con_cand = si + m.L.con_cand;
+    for (int sx = lane; sx < m.n_contacts; sx += TEAM) {
+      float acc[12], nsum = 0.f;
+      for (int k = 0; k < 12; k++) acc[k] = 0.f;
+      for (int i = 0; i < ncon; i++) {
+        int c = con_cand[i];
+        for (int key = 0; key < 4; key++) {
+          if (MI(cand_sensor, 4*c + key) != sx) continue;
+          float sg = (key & 1) ? 1.f : -1.f;
+          float fn = g.d_con_force[3*i], f1 = g.d_con_force[3*i+1], f2 = g.d_con_force[3*i+2];
+          const float *fr = g.d_con_frame + 9*i;
+          float tot[3];
+          for (int k = 0; k < 3; k++) {
+            float re = sg*fn*fr[k], fri = sg*f1*fr[3+k] + sg*f2*fr[6+k];
+            acc[k] += re; acc[3+k] += fri; tot[k] = re + fri; acc[6+k] += tot[k];
+          }
+          float nrm = sqrtf(tot[0]*tot[0] + tot[1]*tot[1] + tot[2]*tot[2]);
+          for (int k = 0; k < 3; k++) acc[9+k] += nrm*g.d_con_pos[3*i + k];
+          nsum += nrm;
+        }
+      }
+      float *row = g.row_contacts + 12*sx;
+      float ip = nsum > 0.f ? 1.0f/nsum : 1.0f;
+      for (int k = 0; k < 9; k++) row[k] = acc[k]*m.inv_newtons;
+      for (int k = 0; k < 3; k++) row[9+k] = acc[9+k]*ip*m.inv_meters;
+    }
+    /* xfrc rows + xfrc_applied for the next step (drag.pyx:152-268, section 3.4) */
+    for (int x = lane; x < m.n_xfrc; x += TEAM) {
+      float *row = g.row_xfrc + 6*x;
+      for (int k = 0; k < 6; k++) row[k] = 0.f;
+      int b = MI(xfrc_body, x);
+      for (int k = 0; k < 6; k++) xf[k*nb + b] = 0.f;
+    }
+    sync();
+    if (m.water_drag) {
+      for (int i = lane; i < m.n_swim; i += TEAM) {
+        int l = MI(swim_link, i), xi = MI(swim_xfrc, i), b = MI(link_body, l);
+        float pz = xipos[2*nb + b]*m.inv_meters;
+        if (pz > m.water_surface) continue;           /* drag.pyx:192-194 */
+        float R[9], lin[3], ang[3], vl[3], wl[3], uw[3], buoy[3] = {0.f, 0.f, 0.f};
+        q_mat(body_quat(b), R);
+        body_velocity(b, lin, ang);
+        m_rot_t(R, lin[0]*m.inv_velocity, lin[1]*m.inv_velocity, lin[2]*m.inv_velocity, vl);
+        m_rot_t(R, ang[0]*m.inv_angvel, ang[1]*m.inv_angvel, ang[2]*m.inv_angvel, wl);
+        float mass = MF(swim_mass, i);
+        if (m.water_buoyancy && mass > 0.f && pz < m.water_surface) {
+          float frac = fminf(fmaxf(m.water_surface - pz, 0.f)/MF(swim_height, i), 1.f);
+          float lift = -1000.f*mass*(-9.81f)/MF(swim_density, i)*frac;
+          m_rot_t(R, 0.f, 0.f, lift, buoy);
+        }
+        m_rot_t(R, m.water_velocity[0], m.water_velocity[1], m.water_velocity[2], uw);
+        float F[3], Tq[3];
+        for (int k = 0; k < 3; k++) {
+          float v = vl[k] - uw[k], w = wl[k];
+          float sv = v < 0.f ? -v*v : v*v, sw = w < 0.f ? -w*w : w*w;
+          F[k] = sv*m.water_viscosity*MF(swim_coef, 6*i + k) + buoy[k];
+          Tq[k] = sw*MF(swim_coef, 6*i + 3 + k);
+        }
+        float *row = g.row_xfrc + 6*xi;
+        for (int k = 0; k < 3; k++) { row[k] = F[k]; row[3+k] = Tq[k]; }
+        int bx = MI(xfrc_body, xi);
+        float Rx[9], wf[3], wt[3];
+        q_mat(body_quat(bx), Rx);
+        m_rot(Rx, F[0], F[1], F[2], wf);
+        m_rot(Rx, Tq[0], Tq[1], Tq[2], wt);
+        for (int k = 0; k < 3; k++) { xf[k*nb + bx] = wf[k]*m.newtons; xf[(3+k)*nb + bx] = wt[k]*m.torques; }
+      }
+    }
+    (void)nj;
+    sync();
+  }
+
+  /* mjData-like derived quantities of the state the last forward() saw */
+  FB_MEM void write_derived() {
+    const int nb = m.nbody, nv = m.nv, nu = m.nu, nj = m.njnt;
+    const float *xpos = s + m.L.xpos, *xipos = s + m.L.xipos;
+    for (int b = lane; b < nb; b += TEAM) {
+      Quat q = body_quat(b);
+      float lin[3], ang[3];
+      body_velocity(b, lin, ang);
+      for (int k = 0; k < 3; k++) {
+        g.d_xpos[3*b + k] = xpos[k*nb + b];
+        g.d_xipos[3*b + k] = xipos[k*nb + b];
+        g.d_linvel[3*b + k] = lin[k];
+        g.d_angvel[3*b + k] = ang[k];
+      }
+      g.d_xquat[4*b] = q.w; g.d_xquat[4*b+1] = q.x; g.d_xquat[4*b+2] = q.y; g.d_xquat[4*b+3] = q.z;
+    }
+    for (int a = lane; a < nu; a += TEAM) g.d_actf[a] = (s + m.L.actf)[a];
+    for (int j = lane; j < nj; j += TEAM) g.d_limf[j] = (s + m.L.limf)[j];
+    for (int v = lane; v < nv; v += TEAM) g.d_qacc[v] = (s + m.L.qacc)[v];
+  }
+
+  /* on-device travelling-wave controller (replaces task.py:288-321 per-step Python) */
+  FB_MEM void wave_control(float time) {
+    float *ctrl = s + m.L.ctrl;
+    for (int i = lane; i < m.n_wc; i += TEAM) {
+      float ph = 6.283185307179586f*MF(wc_freq, i)*time - MF(wc_lag, i) + g.env_phase;
+      ctrl[MI(wc_act, i)] = MF(wc_off, i) + MF(wc_amp, i)*sinf(ph);
+    }
+    sync();
+  }
+
+  FB_MEM void load_state() {
+    float *qpos = s + m.L.qpos, *qvel = s + m.L.qvel, *ctrl = s + m.L.ctrl, *xf = s + m.L.xfrc;
+    const int nb = m.nbody;
+    for (int i = lane; i < m.nq; i += TEAM) qpos[i] = g.qpos[i];
+    for (int i = lane; i < m.nv; i += TEAM) qvel[i] = g.qvel[i];
+    for (int i = lane; i < m.nu; i += TEAM) ctrl[i] = g.ctrl[i];
+    for (int i = lane; i < 6*nb; i += TEAM) { int b = i/6, k = i - 6*b; xf[k*nb + b] = g.xfrc_applied[i]; }
+    sync();
+  }
+
+  FB_MEM void store_state() {
+    const float *qpos = s + m.L.qpos, *qvel = s + m.L.qvel, *ctrl = s + m.L.ctrl, *xf = s + m.L.xfrc;
+    const int nb = m.nbody;
+    for (int i = lane; i < m.nq; i += TEAM) g.qpos[i] = qpos[i];
+    for (int i = lane; i < m.nv; i += TEAM) g.qvel[i] = qvel[i];
+    if (m.n_wc > 0) for (int i = lane; i < m.nu; i += TEAM) g.ctrl[i] = ctrl[i];
+    for (int i = lane; i < 6*nb; i += TEAM) { int b = i/6, k = i - 6*b; g.xfrc_applied[i] = xf[k*nb + b]; }
+  }
+};
+
+/* ===================================================================== */
+/* launch parameters: device base pointers of the whole batch */
+enum { FB_MODE_STEP = 0, FB_MODE_RESET = 1 };
+
+struct FbParams {
+  DevModel m;
+  int n_envs, n_steps, ring, mode, want_derived;
+  long long it0;                  /* physics steps taken since reset */
+  float *qpos, *qvel, *ctrl, *xfrc_applied, *qpos_spring, *env_phase;
+  int *flags;
+  long long *iteration;
+  float *d_xpos, *d_xquat, *d_xipos, *d_linvel, *d_angvel, *d_actf, *d_limf, *d_qacc;
+  int *d_ncon, *d_con_cand;
+  float *d_con_dist, *d_con_pos, *d_con_frame, *d_con_force;
+  float *J3, *efc, *prod3;
+  float *log_links, *log_joints, *log_contacts, *log_xfrc;
+  long long links_env_stride, joints_env_stride, contacts_env_stride, xfrc_env_stride;
+};
+
+FB_DEV EnvPtrs fb_env_ptrs(const FbParams &P, int env) {
+  const DevModel &m = P.m;
+  EnvPtrs g;
+  size_t e = (size_t)env;
+  g.qpos = P.qpos + e*m.nq; g.qvel = P.qvel + e*m.nv; g.ctrl = P.ctrl + e*(m.nu > 0 ? m.nu : 1);
+  g.xfrc_applied = P.xfrc_applied + e*6*m.nbody; g.qpos_spring = P.qpos_spring + e*m.nq;
+  g.env_phase = P.env_phase[env];
+  g.flags = P.flags + env;
+  g.d_xpos = P.d_xpos + e*3*m.nbody; g.d_xquat = P.d_xquat + e*4*m.nbody;
+  g.d_xipos = P.d_xipos + e*3*m.nbody; g.d_linvel = P.d_linvel + e*3*m.nbody;
+  g.d_angvel = P.d_angvel + e*3*m.nbody; g.d_actf = P.d_actf + e*(m.nu > 0 ? m.nu : 1);
+  g.d_limf = P.d_limf + e*m.njnt; g.d_qacc = P.d_qacc + e*m.nv;
+  int mc = m.maxcon > 0 ? m.maxcon : 1;
+  g.d_ncon = P.d_ncon + env; g.d_con_cand = P.d_con_cand + e*mc;
+  g.d_con_dist = P.d_con_dist + e*mc; g.d_con_pos = P.d_con_pos + e*3*mc;
+  g.d_con_frame = P.d_con_frame + e*9*mc; g.d_con_force = P.d_con_force + e*3*mc;
+  g.J3 = P.J3 + e*3*mc*m.nv; g.efc = P.efc + e*5*m.maxefc; g.prod3 = P.prod3 + e*6*mc;
+  g.row_links = g.row_joints = g.row_contacts = g.row_xfrc = 0;
+  return g;
+}
+
+/* Reset: forward at the loaded state, log row 0.  Step k of a launch: control,
+ * forward (derived quantities of the pre-step state), Euler, log row
+ * (it0+k+1) % ring = {derived of the pre-step state, qpos/qvel of the new
+ * state}, then the drag wrench for the next step. */
+template <int TEAM>
+FB_DEV void fb_run_env(const FbParams &P, int env, float *s, int *si, int lane, int base,
+                       unsigned mask) {
+  const DevModel &m = P.m;
+  FbStep<TEAM> st(m, s, si, fb_env_ptrs(P, env), lane, base, mask);
+  st.init_world();
+  st.load_state();
+  const size_t e = (size_t)env;
+  const int n = P.mode == FB_MODE_RESET ? 1 : P.n_steps;
+  for (int k = 0; k < n; k++) {
+    long long row;
+    if (P.mode == FB_MODE_RESET) {
+      st.forward(1);
+      row = 0;
+    } else {
+      if (m.n_wc > 0) st.wave_control((float)(P.it0 + k)*m.timestep);
+      int wd = P.want_derived && k == n - 1;
+      st.forward(wd);
+      if (wd) st.write_derived();
+      st.euler();
+      row = (P.it0 + k + 1) % P.ring;
+    }
+    st.g.row_links = P.log_links + e*P.links_env_stride + row*(long long)(m.n_links*20);
+    st.g.row_joints = P.log_joints + e*P.joints_env_stride + row*(long long)(m.n_joints*m.joint_cols);
+    st.g.row_contacts = P.log_contacts + e*P.contacts_env_stride + row*(long long)(m.n_contacts*12);
+    st.g.row_xfrc = P.log_xfrc + e*P.xfrc_env_stride + row*(long long)(m.n_xfrc*6);
+    st.write_log();
+    if (P.mode == FB_MODE_RESET) st.write_derived();
+  }
+  st.store_state();
+  if (lane == 0) P.iteration[env] = P.mode == FB_MODE_RESET ? 0 : P.it0 + P.n_steps;
+}
+
+#endif /* FB_DEVICE_H_ */

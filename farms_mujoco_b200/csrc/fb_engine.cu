@@ -1,0 +1,555 @@
+/*
+ * fb_engine.cu -- C ABI (include/farms_b200.h) of the batched FARMS stepping
+ * engine and its CUDA kernels for sm_100a.
+ *
+ * One CUDA thread TEAM (8/16/32 lanes of a warp) steps one environment; the
+ * environment's working set is staged in shared memory for the n_steps of a
+ * launch, so HBM only sees the initial/final state and the farms log rows.
+ *
+ * Built as the product with nvcc (-gencode arch=compute_100a,code=sm_100a).
+ * The same file compiles with g++ -DFB_HOST_EMU into tests/emu/libfb_emu.so, a
+ * unit-test harness that runs the device code serially on the host (TEAM = 1)
+ * so the arithmetic can be checked on the GPU-less development box.  The
+ * product never loads that library.
+ */
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "fb_device.h"
+
+#ifndef FB_HOST_EMU
+#include <cuda_runtime.h>
+#endif
+
+static thread_local std::string g_error;
+static int fail(const std::string &msg) { g_error = msg; return -1; }
+
+/* ------------------------------------------------------- memory backend */
+#ifdef FB_HOST_EMU
+typedef int fbStream;
+static int dev_alloc(void **p, size_t bytes) { *p = calloc(bytes ? bytes : 1, 1); return *p ? 0 : -1; }
+static void dev_free(void *p) { free(p); }
+static int dev_zero(void *p, size_t bytes, fbStream) { memset(p, 0, bytes); return 0; }
+static int h2d(void *d, const void *h, size_t bytes, fbStream) { memcpy(d, h, bytes); return 0; }
+static int d2h(void *h, const void *d, size_t bytes, fbStream) { memcpy(h, d, bytes); return 0; }
+static int dev_sync(fbStream) { return 0; }
+static const char *dev_error() { return "emulation backend error"; }
+#else
+typedef cudaStream_t fbStream;
+static int dev_alloc(void **p, size_t bytes) {
+  if (cudaMalloc(p, bytes ? bytes : 1) != cudaSuccess) return -1;
+  return cudaMemset(*p, 0, bytes ? bytes : 1) == cudaSuccess ? 0 : -1;
+}
+static void dev_free(void *p) { cudaFree(p); }
+static int dev_zero(void *p, size_t bytes, fbStream st) { return cudaMemsetAsync(p, 0, bytes, st) == cudaSuccess ? 0 : -1; }
+static int h2d(void *d, const void *h, size_t bytes, fbStream st) { return cudaMemcpyAsync(d, h, bytes, cudaMemcpyHostToDevice, st) == cudaSuccess ? 0 : -1; }
+static int d2h(void *h, const void *d, size_t bytes, fbStream st) { return cudaMemcpyAsync(h, d, bytes, cudaMemcpyDeviceToHost, st) == cudaSuccess ? 0 : -1; }
+static int dev_sync(fbStream st) { return cudaStreamSynchronize(st) == cudaSuccess ? 0 : -1; }
+static const char *dev_error() { return cudaGetErrorString(cudaGetLastError()); }
+#endif
+
+/* --------------------------------------------------------------- kernels */
+#ifndef FB_HOST_EMU
+template <int TEAM>
+__global__ void __launch_bounds__(128)
+fb_step_kernel(const __grid_constant__ FbParams P) {
+  extern __shared__ __align__(16) float fb_smem[];
+  const DevModel &m = P.m;
+  const int tid = threadIdx.x, team = tid/TEAM, lane = tid % TEAM;
+  const int env = blockIdx.x*(blockDim.x/TEAM) + team;
+  if (env >= P.n_envs) return;
+  const int base = (tid & 31)/TEAM*TEAM;
+  const unsigned mask = TEAM == 32 ? 0xffffffffu : (((1u << (TEAM & 31)) - 1u) << base);
+  float *s = fb_smem + (size_t)team*(m.L.n_float + m.L.n_int);
+  int *si = reinterpret_cast<int *>(s + m.L.n_float);
+  fb_run_env<TEAM>(P, env, s, si, lane, base, mask);
+}
+
+/* last written log row of every environment -> dense [n_envs][row] buffers */
+__global__ void fb_gather_rows_kernel(const float *__restrict__ log, long long env_stride,
+                                      long long row, int row_floats, int n_envs,
+                                      float *__restrict__ out) {
+  long long i = (long long)blockIdx.x*blockDim.x + threadIdx.x;
+  long long total = (long long)n_envs*row_floats;
+  if (i >= total) return;
+  long long env = i/row_floats, k = i - env*row_floats;
+  out[i] = log[env*env_stride + row*row_floats + k];
+}
+#endif
+
+/* ---------------------------------------------------------------- handle */
+struct FbHandle {
+  FbHostModel hm;
+  FbParams P;
+  int device, team, envs_per_block, threads;
+  size_t smem_bytes;
+  fbStream stream;
+  std::vector<void *> allocs;
+  int32_t *I_dev;
+  float *F_dev;
+  long long launches;
+  long long it;            /* physics steps since reset */
+  float last_ms;
+  float *gather_links, *gather_joints;   /* fb_step_host staging */
+  /* wave-controller copies (owned) */
+  std::vector<int32_t> wc_act;
+  std::vector<double> wc_amp, wc_freq, wc_lag, wc_off;
+  bool has_wc;
+  /* host copies of the user structs' arrays are not kept: hm holds the blobs */
+  FbModel fm_shallow; FbFarms ff_shallow; bool has_farms;
+  std::vector<std::vector<int32_t>> keep_i;
+  std::vector<std::vector<double>> keep_d;
+#ifndef FB_HOST_EMU
+  cudaEvent_t ev0, ev1;
+#endif
+};
+
+template <typename Tp> static int alloc_arr(FbHandle *h, Tp **p, size_t count) {
+  void *q = nullptr;
+  if (dev_alloc(&q, count*sizeof(Tp))) return -1;
+  h->allocs.push_back(q);
+  *p = static_cast<Tp *>(q);
+  return 0;
+}
+
+static const int32_t *keep_int(FbHandle *h, const int32_t *p, size_t n) {
+  h->keep_i.emplace_back(p, p + n);
+  if (h->keep_i.back().empty()) h->keep_i.back().push_back(0);
+  return h->keep_i.back().data();
+}
+static const double *keep_dbl(FbHandle *h, const double *p, size_t n) {
+  h->keep_d.emplace_back(p, p + n);
+  if (h->keep_d.back().empty()) h->keep_d.back().push_back(0.0);
+  return h->keep_d.back().data();
+}
+
+/* deep copies so that fb_set_wave_controller / fb_set_swimming can rebuild */
+static void deep_copy_model(FbHandle *h, const FbModel *m, const FbFarms *f) {
+  FbModel &d = h->fm_shallow;
+  d = *m;
+  const int nb = m->nbody, nj = m->njnt, nv = m->nv, nu = m->nu, ng = m->ngeom, nc = m->ncand;
+#define KI(field, n) d.field = keep_int(h, m->field, (size_t)(n))
+#define KD(field, n) d.field = keep_dbl(h, m->field, (size_t)(n))
+  KI(body_parentid, nb); KI(body_jntid, nb); KI(body_dofadr, nb); KI(body_dofnum, nb);
+  KD(body_pos, 3*nb); KD(body_quat, 4*nb); KD(body_ipos, 3*nb); KD(body_iquat, 4*nb);
+  KD(body_mass, nb); KD(body_inertia, 3*nb); KD(body_invweight0, 2*nb);
+  KI(jnt_type, nj); KI(jnt_bodyid, nj); KI(jnt_qposadr, nj); KI(jnt_dofadr, nj); KI(jnt_limited, nj);
+  KD(jnt_pos, 3*nj); KD(jnt_axis, 3*nj); KD(jnt_stiffness, nj); KD(jnt_range, 2*nj);
+  KD(jnt_margin, nj); KD(jnt_solref, 2*nj); KD(jnt_solimp, 5*nj);
+  KI(dof_bodyid, nv); KI(dof_jntid, nv); KI(dof_parentid, nv); KI(dof_Madr, nv);
+  KD(dof_damping, nv); KD(dof_armature, nv); KD(dof_invweight0, nv);
+  KD(qpos0, m->nq); KD(qpos_spring, m->nq);
+  KI(geom_type, ng); KI(geom_bodyid, ng); KD(geom_pos, 3*ng); KD(geom_quat, 4*ng); KD(geom_size, 3*ng);
+  KI(cand_geom1, nc); KI(cand_geom2, nc); KI(cand_end, nc);
+  KD(cand_friction, nc); KD(cand_solref, 2*nc); KD(cand_solimp, 5*nc); KD(cand_margin, nc); KD(cand_gap, nc);
+  KI(actuator_trnid, nu); KI(actuator_ctrllimited, nu); KI(actuator_forcelimited, nu);
+  KD(actuator_gainprm, 3*nu); KD(actuator_biasprm, 3*nu); KD(actuator_ctrlrange, 2*nu);
+  KD(actuator_forcerange, 2*nu); KD(actuator_gear, nu);
+  KD(key_qpos, m->nq); KD(key_qvel, nv);
+#undef KI
+#undef KD
+  h->has_farms = f != nullptr;
+  if (f) {
+    FbFarms &e = h->ff_shallow;
+    e = *f;
+#define KI(field, n) e.field = keep_int(h, f->field, (size_t)(n))
+#define KD(field, n) e.field = keep_dbl(h, f->field, (size_t)(n))
+    KI(link_body, f->n_links); KI(joint_qposadr, f->n_joints); KI(joint_dofadr, f->n_joints);
+    KI(joint_jntid, f->n_joints); KI(joint_act_position, f->n_joints);
+    KI(joint_act_velocity, f->n_joints); KI(joint_act_torque, f->n_joints);
+    KI(cand_sensor, 4*nc); KI(xfrc_body, f->n_xfrc);
+    KI(swim_links_index, f->n_swim); KI(swim_xfrc_index, f->n_swim);
+    KD(swim_mass, f->n_swim); KD(swim_height, f->n_swim); KD(swim_density, f->n_swim);
+    KD(swim_coefficients, 6*f->n_swim);
+#undef KI
+#undef KD
+  }
+}
+
+/* (re)build the device model tables from the handle's host copies */
+static int upload_model(FbHandle *h) {
+  FbWaveController wc;
+  wc.n = (int)h->wc_act.size();
+  wc.actuator = h->wc_act.data(); wc.amplitude = h->wc_amp.data(); wc.frequency = h->wc_freq.data();
+  wc.phase_lag = h->wc_lag.data(); wc.offset = h->wc_off.data();
+  DevLayout keepL = h->hm.m.L;
+  bool had = h->I_dev != nullptr;
+  if (!fb_build_model(&h->fm_shallow, h->has_farms ? &h->ff_shallow : nullptr,
+                      h->has_wc ? &wc : nullptr, h->hm))
+    return fail("unsupported model: " + h->hm.error);
+  if (had && memcmp(&keepL, &h->hm.m.L, sizeof(DevLayout)) != 0) return fail("layout changed on rebuild");
+  if (h->I_dev) { dev_sync(h->stream); dev_free(h->I_dev); dev_free(h->F_dev); }
+  void *pi = nullptr, *pf = nullptr;
+  if (dev_alloc(&pi, h->hm.I.size()*sizeof(int32_t)) || dev_alloc(&pf, h->hm.F.size()*sizeof(float)))
+    return fail("device allocation of the model tables failed");
+  h->I_dev = static_cast<int32_t *>(pi);
+  h->F_dev = static_cast<float *>(pf);
+  if (h2d(h->I_dev, h->hm.I.data(), h->hm.I.size()*sizeof(int32_t), h->stream) ||
+      h2d(h->F_dev, h->hm.F.data(), h->hm.F.size()*sizeof(float), h->stream) || dev_sync(h->stream))
+    return fail("model upload failed");
+  h->P.m = h->hm.m;
+  h->P.m.I = h->I_dev;
+  h->P.m.F = h->F_dev;
+  return 0;
+}
+
+static int launch(FbHandle *h, int mode, int n_steps, int want_derived) {
+  FbParams &P = h->P;
+  P.mode = mode; P.n_steps = n_steps; P.want_derived = want_derived; P.it0 = h->it;
+#ifdef FB_HOST_EMU
+  const DevModel &m = P.m;
+  std::vector<float> s((size_t)m.L.n_float + 8, 0.f);
+  std::vector<int> si((size_t)m.L.n_int + 8, 0);
+  for (int env = 0; env < P.n_envs; env++)
+    fb_run_env<1>(P, env, s.data(), si.data(), 0, 0, 1u);
+  h->last_ms = 0.f;
+#else
+  int blocks = (P.n_envs + h->envs_per_block - 1)/h->envs_per_block;
+  cudaEventRecord(h->ev0, h->stream);
+  switch (h->team) {
+    case 8: fb_step_kernel<8><<<blocks, h->threads, h->smem_bytes, h->stream>>>(P); break;
+    case 16: fb_step_kernel<16><<<blocks, h->threads, h->smem_bytes, h->stream>>>(P); break;
+    default: fb_step_kernel<32><<<blocks, h->threads, h->smem_bytes, h->stream>>>(P); break;
+  }
+  cudaEventRecord(h->ev1, h->stream);
+  if (cudaGetLastError() != cudaSuccess) return fail(std::string("kernel launch failed: ") + dev_error());
+#endif
+  h->launches++;
+  if (mode == FB_MODE_RESET) h->it = 0; else h->it += n_steps;
+  return 0;
+}
+
+/* ------------------------------------------------------------------ ABI */
+extern "C" {
+
+const char *fb_last_error(void) { return g_error.c_str(); }
+int fb_abi_version(void) { return FB_ABI_VERSION; }
+
+void fb_destroy(FbHandle *h) {
+  if (!h) return;
+  dev_sync(h->stream);
+  for (void *p : h->allocs) dev_free(p);
+  if (h->I_dev) dev_free(h->I_dev);
+  if (h->F_dev) dev_free(h->F_dev);
+#ifndef FB_HOST_EMU
+  cudaEventDestroy(h->ev0); cudaEventDestroy(h->ev1);
+  cudaStreamDestroy(h->stream);
+#endif
+  delete h;
+}
+
+int fb_create(const FbModel *model, const FbFarms *farms, int n_envs, int device, int ring_steps,
+              int team_lanes, FbHandle **out) {
+  if (!model || !out) return fail("fb_create: null argument");
+  if (n_envs < 1 || ring_steps < 1) return fail("fb_create: n_envs and ring_steps must be >= 1");
+  FbHandle *h = new (std::nothrow) FbHandle();
+  if (!h) return fail("out of host memory");
+  h->device = device; h->I_dev = nullptr; h->F_dev = nullptr; h->launches = 0; h->it = 0;
+  h->last_ms = 0.f; h->has_wc = false; h->gather_links = h->gather_joints = nullptr;
+  memset(&h->P, 0, sizeof(h->P));
+#ifdef FB_HOST_EMU
+  h->stream = 0;
+  h->team = 1;
+  (void)team_lanes;
+#else
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+    delete h;
+    return fail("no CUDA device: the engine has no CPU fallback");
+  }
+  if (device < 0 || device >= ndev) { delete h; return fail("fb_create: bad device index"); }
+  cudaSetDevice(device);
+  cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking);
+  cudaEventCreate(&h->ev0); cudaEventCreate(&h->ev1);
+  if (team_lanes != 0 && team_lanes != 8 && team_lanes != 16 && team_lanes != 32) {
+    fb_destroy(h);
+    return fail("fb_create: team_lanes must be 0, 8, 16 or 32");
+  }
+  h->team = team_lanes;
+#endif
+  deep_copy_model(h, model, farms);
+  if (upload_model(h)) { fb_destroy(h); return -1; }
+  const DevModel &m = h->hm.m;
+#ifndef FB_HOST_EMU
+  if (h->team == 0) h->team = m.nbody > 20 ? 32 : (m.nbody > 10 ? 16 : 8);
+  size_t per_env = (size_t)(m.L.n_float + m.L.n_int)*sizeof(float);
+  int max_smem = 0;
+  cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
+  if (per_env > (size_t)max_smem) { fb_destroy(h); return fail("model working set exceeds shared memory"); }
+  int epb = 128/h->team;
+  while (epb > 1 && per_env*epb > (size_t)max_smem/2) epb >>= 1;
+  h->envs_per_block = epb;
+  h->threads = epb*h->team;
+  h->smem_bytes = per_env*epb;
+  cudaError_t ce = cudaSuccess;
+  switch (h->team) {
+    case 8: ce = cudaFuncSetAttribute(fb_step_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_bytes); break;
+    case 16: ce = cudaFuncSetAttribute(fb_step_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_bytes); break;
+    default: ce = cudaFuncSetAttribute(fb_step_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_bytes); break;
+  }
+  if (ce != cudaSuccess) { fb_destroy(h); return fail(std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(ce)); }
+#else
+  h->envs_per_block = 1; h->threads = 1;
+  h->smem_bytes = (size_t)(m.L.n_float + m.L.n_int)*sizeof(float);
+#endif
+  FbParams &P = h->P;
+  P.n_envs = n_envs; P.ring = ring_steps;
+  const size_t n = (size_t)n_envs, nb = m.nbody, mc = m.maxcon > 0 ? m.maxcon : 1, nu = m.nu > 0 ? m.nu : 1;
+  P.links_env_stride = (long long)ring_steps*m.n_links*20;
+  P.joints_env_stride = (long long)ring_steps*m.n_joints*m.joint_cols;
+  P.contacts_env_stride = (long long)ring_steps*m.n_contacts*12;
+  P.xfrc_env_stride = (long long)ring_steps*m.n_xfrc*6;
+  int bad = 0;
+  bad |= alloc_arr(h, &P.qpos, n*m.nq); bad |= alloc_arr(h, &P.qvel, n*m.nv);
+  bad |= alloc_arr(h, &P.ctrl, n*nu); bad |= alloc_arr(h, &P.xfrc_applied, n*6*nb);
+  bad |= alloc_arr(h, &P.qpos_spring, n*m.nq); bad |= alloc_arr(h, &P.env_phase, n);
+  bad |= alloc_arr(h, &P.flags, n); bad |= alloc_arr(h, &P.iteration, n);
+  bad |= alloc_arr(h, &P.d_xpos, n*3*nb); bad |= alloc_arr(h, &P.d_xquat, n*4*nb);
+  bad |= alloc_arr(h, &P.d_xipos, n*3*nb); bad |= alloc_arr(h, &P.d_linvel, n*3*nb);
+  bad |= alloc_arr(h, &P.d_angvel, n*3*nb); bad |= alloc_arr(h, &P.d_actf, n*nu);
+  bad |= alloc_arr(h, &P.d_limf, n*(m.njnt > 0 ? m.njnt : 1)); bad |= alloc_arr(h, &P.d_qacc, n*m.nv);
+  bad |= alloc_arr(h, &P.d_ncon, n); bad |= alloc_arr(h, &P.d_con_cand, n*mc);
+  bad |= alloc_arr(h, &P.d_con_dist, n*mc); bad |= alloc_arr(h, &P.d_con_pos, n*3*mc);
+  bad |= alloc_arr(h, &P.d_con_frame, n*9*mc); bad |= alloc_arr(h, &P.d_con_force, n*3*mc);
+  bad |= alloc_arr(h, &P.J3, n*3*mc*m.nv); bad |= alloc_arr(h, &P.efc, n*5*(m.maxefc > 0 ? m.maxefc : 1));
+  bad |= alloc_arr(h, &P.prod3, n*6*mc);
+  bad |= alloc_arr(h, &P.log_links, n*(size_t)P.links_env_stride);
+  bad |= alloc_arr(h, &P.log_joints, n*(size_t)P.joints_env_stride);
+  bad |= alloc_arr(h, &P.log_contacts, n*(size_t)P.contacts_env_stride);
+  bad |= alloc_arr(h, &P.log_xfrc, n*(size_t)P.xfrc_env_stride);
+  bad |= alloc_arr(h, &h->gather_links, n*m.n_links*20);
+  bad |= alloc_arr(h, &h->gather_joints, n*m.n_joints*m.joint_cols);
+  if (bad) { fb_destroy(h); return fail("device allocation failed (n_envs x ring too large?)"); }
+  /* qpos_spring <- model value for every environment */
+  std::vector<float> spring((size_t)n*m.nq);
+  for (size_t e = 0; e < n; e++)
+    for (int i = 0; i < m.nq; i++) spring[e*m.nq + i] = (float)model->qpos_spring[i];
+  if (h2d(P.qpos_spring, spring.data(), spring.size()*sizeof(float), h->stream) || dev_sync(h->stream)) {
+    fb_destroy(h);
+    return fail("upload failed");
+  }
+  *out = h;
+  return fb_reset(h, nullptr, nullptr);
+}
+
+int fb_reset(FbHandle *h, const double *qpos0, const double *qvel0) {
+  if (!h) return fail("null handle");
+  const DevModel &m = h->hm.m;
+  const size_t n = (size_t)h->P.n_envs;
+  std::vector<float> q(n*m.nq), v(n*m.nv);
+  for (size_t e = 0; e < n; e++) {
+    for (int i = 0; i < m.nq; i++)
+      q[e*m.nq + i] = qpos0 ? (float)qpos0[e*m.nq + i] : h->hm.F[h->hm.m.o.key_qpos + i];
+    for (int i = 0; i < m.nv; i++)
+      v[e*m.nv + i] = qvel0 ? (float)qvel0[e*m.nv + i] : h->hm.F[h->hm.m.o.key_qvel + i];
+  }
+  FbParams &P = h->P;
+  int bad = h2d(P.qpos, q.data(), q.size()*sizeof(float), h->stream);
+  bad |= h2d(P.qvel, v.data(), v.size()*sizeof(float), h->stream);
+  bad |= dev_zero(P.ctrl, n*(m.nu > 0 ? m.nu : 1)*sizeof(float), h->stream);
+  bad |= dev_zero(P.xfrc_applied, n*6*m.nbody*sizeof(float), h->stream);
+  bad |= dev_zero(P.flags, n*sizeof(int), h->stream);
+  bad |= dev_sync(h->stream);   /* q, v are stack-owned */
+  if (bad) return fail(std::string("fb_reset: ") + dev_error());
+  h->it = 0;
+  if (launch(h, FB_MODE_RESET, 1, 1)) return -1;
+  return dev_sync(h->stream) ? fail(std::string("fb_reset: ") + dev_error()) : 0;
+}
+
+static int upload_doubles(FbHandle *h, float *dst, const double *src, size_t count, const char *what) {
+  if (!h || !src) return fail(std::string(what) + ": null argument");
+  std::vector<float> tmp(count);
+  for (size_t i = 0; i < count; i++) tmp[i] = (float)src[i];
+  if (h2d(dst, tmp.data(), count*sizeof(float), h->stream) || dev_sync(h->stream))
+    return fail(std::string(what) + ": " + dev_error());
+  return 0;
+}
+
+int fb_set_ctrl(FbHandle *h, const double *ctrl) {
+  return upload_doubles(h, h->P.ctrl, ctrl, (size_t)h->P.n_envs*h->hm.m.nu, "fb_set_ctrl");
+}
+int fb_set_qpos_spring(FbHandle *h, const double *qs) {
+  return upload_doubles(h, h->P.qpos_spring, qs, (size_t)h->P.n_envs*h->hm.m.nq, "fb_set_qpos_spring");
+}
+int fb_set_env_phase(FbHandle *h, const double *phase) {
+  return upload_doubles(h, h->P.env_phase, phase, (size_t)h->P.n_envs, "fb_set_env_phase");
+}
+
+int fb_set_wave_controller(FbHandle *h, const FbWaveController *c) {
+  if (!h) return fail("null handle");
+  h->has_wc = c != nullptr && c->n > 0;
+  h->wc_act.clear(); h->wc_amp.clear(); h->wc_freq.clear(); h->wc_lag.clear(); h->wc_off.clear();
+  if (h->has_wc) {
+    for (int i = 0; i < c->n; i++) {
+      if (c->actuator[i] < 0 || c->actuator[i] >= h->hm.m.nu) return fail("wave controller: bad actuator index");
+      h->wc_act.push_back(c->actuator[i]);
+      h->wc_amp.push_back(c->amplitude[i]); h->wc_freq.push_back(c->frequency[i]);
+      h->wc_lag.push_back(c->phase_lag[i]); h->wc_off.push_back(c->offset ? c->offset[i] : 0.0);
+    }
+  }
+  return upload_model(h);
+}
+
+int fb_set_water_velocity(FbHandle *h, double vx, double vy, double vz) {
+  if (!h) return fail("null handle");
+  if (!h->has_farms) return fail("no farms tables");
+  h->ff_shallow.water_velocity[0] = vx; h->ff_shallow.water_velocity[1] = vy; h->ff_shallow.water_velocity[2] = vz;
+  h->P.m.water_velocity[0] = (float)vx; h->P.m.water_velocity[1] = (float)vy; h->P.m.water_velocity[2] = (float)vz;
+  h->hm.m.water_velocity[0] = (float)vx; h->hm.m.water_velocity[1] = (float)vy; h->hm.m.water_velocity[2] = (float)vz;
+  return 0;
+}
+
+int fb_set_swimming(FbHandle *h, int drag, int buoyancy) {
+  if (!h) return fail("null handle");
+  if (!h->has_farms) return fail("no farms tables");
+  h->ff_shallow.water_drag = drag; h->ff_shallow.water_buoyancy = buoyancy;
+  h->P.m.water_drag = h->hm.m.water_drag = drag != 0;
+  h->P.m.water_buoyancy = h->hm.m.water_buoyancy = buoyancy != 0;
+  return 0;
+}
+
+int fb_step(FbHandle *h, int n_steps, int want_derived, int sync) {
+  if (!h) return fail("null handle");
+  if (n_steps < 1) return fail("fb_step: n_steps must be >= 1");
+  if (launch(h, FB_MODE_STEP, n_steps, want_derived)) return -1;
+  if (sync && dev_sync(h->stream)) return fail(std::string("fb_step: ") + dev_error());
+  return 0;
+}
+
+int fb_synchronize(FbHandle *h) {
+  if (!h) return fail("null handle");
+  return dev_sync(h->stream) ? fail(std::string("fb_synchronize: ") + dev_error()) : 0;
+}
+
+int fb_last_step_ms(FbHandle *h, float *ms) {
+  if (!h || !ms) return fail("null argument");
+#ifndef FB_HOST_EMU
+  if (cudaEventSynchronize(h->ev1) != cudaSuccess) return fail(dev_error());
+  if (cudaEventElapsedTime(&h->last_ms, h->ev0, h->ev1) != cudaSuccess) return fail(dev_error());
+#endif
+  *ms = h->last_ms;
+  return 0;
+}
+
+int64_t fb_launch_count(FbHandle *h) { return h ? h->launches : 0; }
+
+int fb_log_view(FbHandle *h, FbLogView *out) {
+  if (!h || !out) return fail("null argument");
+  const FbParams &P = h->P;
+  out->links_dev = P.log_links; out->joints_dev = P.log_joints;
+  out->contacts_dev = P.log_contacts; out->xfrc_dev = P.log_xfrc;
+  out->links_env_stride = P.links_env_stride; out->joints_env_stride = P.joints_env_stride;
+  out->contacts_env_stride = P.contacts_env_stride; out->xfrc_env_stride = P.xfrc_env_stride;
+  out->ring = P.ring; out->n_envs = P.n_envs;
+  return 0;
+}
+
+int fb_state_view(FbHandle *h, FbStateView *out) {
+  if (!h || !out) return fail("null argument");
+  const FbParams &P = h->P;
+  out->qpos_dev = P.qpos; out->qvel_dev = P.qvel; out->ctrl_dev = P.ctrl;
+  out->xfrc_applied_dev = P.xfrc_applied; out->qpos_spring_dev = P.qpos_spring;
+  out->env_phase_dev = P.env_phase; out->flags_dev = P.flags;
+  out->iteration_dev = reinterpret_cast<int64_t *>(P.iteration);
+  return 0;
+}
+
+int fb_derived_view(FbHandle *h, FbDerivedView *out) {
+  if (!h || !out) return fail("null argument");
+  const FbParams &P = h->P;
+  out->xpos_dev = P.d_xpos; out->xquat_dev = P.d_xquat; out->xipos_dev = P.d_xipos;
+  out->linvel_dev = P.d_linvel; out->angvel_dev = P.d_angvel; out->actuator_force_dev = P.d_actf;
+  out->jnt_limit_force_dev = P.d_limf; out->qacc_dev = P.d_qacc; out->ncon_dev = P.d_ncon;
+  out->con_cand_dev = P.d_con_cand; out->con_dist_dev = P.d_con_dist; out->con_pos_dev = P.d_con_pos;
+  out->con_frame_dev = P.d_con_frame; out->con_force_dev = P.d_con_force;
+  out->maxcon = h->hm.m.maxcon > 0 ? h->hm.m.maxcon : 1;
+  return 0;
+}
+
+/* raw copies between host and the engine's device buffers (ctypes hosts
+ * without torch use these; `what` selects the buffer) */
+int fb_copy_to_host(FbHandle *h, const void *dev_ptr, void *host_ptr, int64_t bytes) {
+  if (!h || !dev_ptr || !host_ptr) return fail("null argument");
+  if (d2h(host_ptr, dev_ptr, (size_t)bytes, h->stream) || dev_sync(h->stream)) return fail(dev_error());
+  return 0;
+}
+int fb_copy_to_device(FbHandle *h, void *dev_ptr, const void *host_ptr, int64_t bytes) {
+  if (!h || !dev_ptr || !host_ptr) return fail("null argument");
+  if (h2d(dev_ptr, host_ptr, (size_t)bytes, h->stream) || dev_sync(h->stream)) return fail(dev_error());
+  return 0;
+}
+
+int fb_export_farms(FbHandle *h, int env, double *links, double *joints, double *contacts,
+                    double *xfrc) {
+  if (!h) return fail("null handle");
+  const FbParams &P = h->P;
+  if (env < 0 || env >= P.n_envs) return fail("fb_export_farms: env out of range");
+  struct Item { double *dst; const float *src; long long stride; } items[4] = {
+    {links, P.log_links, P.links_env_stride}, {joints, P.log_joints, P.joints_env_stride},
+    {contacts, P.log_contacts, P.contacts_env_stride}, {xfrc, P.log_xfrc, P.xfrc_env_stride}};
+  for (const Item &it : items) {
+    if (!it.dst || it.stride == 0) continue;
+    std::vector<float> tmp((size_t)it.stride);
+    if (d2h(tmp.data(), it.src + (size_t)env*it.stride, tmp.size()*sizeof(float), h->stream) ||
+        dev_sync(h->stream))
+      return fail(std::string("fb_export_farms: ") + dev_error());
+    for (size_t i = 0; i < tmp.size(); i++) it.dst[i] = (double)tmp[i];
+  }
+  return 0;
+}
+
+int fb_step_host(FbHandle *h, const float *qpos, const float *qvel, int n_steps, float *links_row,
+                 float *joints_row) {
+  if (!h) return fail("null handle");
+  FbParams &P = h->P;
+  const DevModel &m = h->hm.m;
+  const size_t n = (size_t)P.n_envs;
+  if (qpos && h2d(P.qpos, qpos, n*m.nq*sizeof(float), h->stream)) return fail(dev_error());
+  if (qvel && h2d(P.qvel, qvel, n*m.nv*sizeof(float), h->stream)) return fail(dev_error());
+  if (launch(h, FB_MODE_STEP, n_steps, 0)) return -1;
+  long long row = h->it % P.ring;
+  const int lf = m.n_links*20, jf = m.n_joints*m.joint_cols;
+#ifdef FB_HOST_EMU
+  for (size_t e = 0; e < n; e++) {
+    if (links_row) memcpy(links_row + e*lf, P.log_links + e*P.links_env_stride + row*lf, lf*sizeof(float));
+    if (joints_row) memcpy(joints_row + e*jf, P.log_joints + e*P.joints_env_stride + row*jf, jf*sizeof(float));
+  }
+#else
+  if (links_row && lf) {
+    long long total = (long long)n*lf;
+    fb_gather_rows_kernel<<<(unsigned)((total + 255)/256), 256, 0, h->stream>>>(
+        P.log_links, P.links_env_stride, row, lf, P.n_envs, h->gather_links);
+    h->launches++;
+    if (d2h(links_row, h->gather_links, (size_t)total*sizeof(float), h->stream)) return fail(dev_error());
+  }
+  if (joints_row && jf) {
+    long long total = (long long)n*jf;
+    fb_gather_rows_kernel<<<(unsigned)((total + 255)/256), 256, 0, h->stream>>>(
+        P.log_joints, P.joints_env_stride, row, jf, P.n_envs, h->gather_joints);
+    h->launches++;
+    if (d2h(joints_row, h->gather_joints, (size_t)total*sizeof(float), h->stream)) return fail(dev_error());
+  }
+#endif
+  if (dev_sync(h->stream)) return fail(std::string("fb_step_host: ") + dev_error());
+  return 0;
+}
+
+int fb_team_lanes(FbHandle *h) { return h ? h->team : 0; }
+int fb_smem_bytes_per_env(FbHandle *h) {
+  return h ? (int)((h->hm.m.L.n_float + h->hm.m.L.n_int)*sizeof(float)) : 0;
+}
+int fb_device_ptr_stream(FbHandle *h, void **stream_out) {
+  if (!h || !stream_out) return fail("null argument");
+#ifdef FB_HOST_EMU
+  *stream_out = nullptr;
+#else
+  *stream_out = (void *)h->stream;
+#endif
+  return 0;
+}
+
+}  /* extern "C" */

@@ -1,0 +1,390 @@
+/*
+ * fb_model.h -- device-side model tables of the batched FARMS stepping engine.
+ *
+ * FbModel/FbFarms (include/farms_b200.h, float64 host arrays) are flattened by
+ * fb_build_model() into two blobs (int32 + float32) plus a table of offsets;
+ * the same DevModel struct is handed to the CUDA kernels by value and to the
+ * host emulation build used by the CPU unit tests (tests/emu).  Plain C++,
+ * no CUDA headers.
+ *
+ * What the tables describe follows the MuJoCo subset of SURVEY.md Appendix A
+ * (reference call sites: farms_mujoco/simulation/simulation.py:53,156) and the
+ * farms index maps of farms_mujoco/simulation/physics.py:188-393.
+ */
+#ifndef FB_MODEL_H_
+#define FB_MODEL_H_
+
+#include <cmath>
+#include <cstdint>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/farms_b200.h"
+
+/* MuJoCo constants (third party; isolated here, mirrored in mjcf_subset.py) */
+#define FB_MINVAL 1e-15f
+#define FB_MINIMP 0.0001f
+#define FB_MAXIMP 0.9999f
+
+/* offsets (in elements) into the int blob I and the float blob F */
+struct DevOffsets {
+  /* ints */
+  int body_parent, body_jnt, body_dofadr, body_dofnum, body_firstchild, body_nextsib,
+      body_lastdof, body_ancmask, lvl_start, lvl_body;
+  int jnt_type, jnt_body, jnt_qposadr, jnt_dofadr, jnt_limited, jnt_actstart, act_sorted;
+  int dof_body, dof_jnt, dof_parent, dof_Madr, dof_nanc;
+  int ent_i, ent_j;
+  int cand_body, cand_iscapsule, cand_sensor;
+  int act_jnt, act_ctrllimited, act_forcelimited;
+  int link_body, fj_qposadr, fj_dofadr, fj_jntid, fj_actpos, fj_actvel, fj_acttrq, xfrc_body,
+      swim_link, swim_xfrc, body_xfrcrow, wc_act;
+  /* floats */
+  int body_pos, body_quat, body_ipos, body_iquat, body_mass, body_inertia, body_invw;
+  int jnt_pos, jnt_axis, jnt_stiffness, jnt_range, jnt_margin, jnt_solref, jnt_solimp, jnt_qpos0;
+  int dof_damping, dof_armature, dof_invw;
+  int cand_lpos, cand_laxis, cand_radius, cand_pn, cand_pd, cand_friction, cand_solref,
+      cand_solimp, cand_margin, cand_gap, cand_invw;
+  int act_gain, act_bias, act_ctrlrange, act_forcerange, act_gear;
+  int swim_mass, swim_height, swim_density, swim_coef;
+  int wc_amp, wc_freq, wc_lag, wc_off;
+  int key_qpos, key_qvel;
+};
+
+/* per-environment shared-memory layout (float offsets; component-major SoA:
+ * element (k, i) of an array with N items lives at off + k*N + i) */
+struct DevLayout {
+  int qpos, qvel, ctrl, actf, xpos, xquat, xipos, xanchor, xaxis, cinert, cdof, cvel, xfrc,
+      qM, qLD, dinv, fsm, qacc, fcon, grad, pvec, tmp1, tmp2, limf, scratch;
+  /* aliases inside scratch */
+  int crb, cacc, cfrc, buf, Md, H;
+  int n_float;   /* floats per env */
+  int con_cand;  /* int region: con_cand[maxcon] */
+  int n_int;
+};
+
+struct DevModel {
+  int nbody, njnt, nq, nv, nu, ncand, nM, nlevel, nmaskw;
+  int n_links, n_joints, n_contacts, n_xfrc, n_swim, n_wc;
+  int maxcon, maxefc, npack; /* npack = nv*(nv+1)/2 */
+  int solver_iterations, any_damping, any_stiffness, any_limit;
+  int col_jpos, col_jvel, col_jtrq, col_jlim;
+  int link_cols, joint_cols, contact_cols, xfrc_cols;
+  int water_drag, water_buoyancy;
+  float timestep, grav[3], impratio, inv_total_mass, solver_scale, tolerance;
+  float water_surface, water_viscosity, water_velocity[3];
+  /* log scaling: value_SI = value_sim * inv_<unit> (physics.py:428-523) */
+  float inv_meters, inv_velocity, inv_angvel, inv_torques, inv_newtons;
+  float newtons, torques;
+  const int32_t *I;
+  const float *F;
+  DevOffsets o;
+  DevLayout L;
+};
+
+/* ---------------------------------------------------------------- builder */
+struct FbHostModel {
+  std::vector<int32_t> I;
+  std::vector<float> F;
+  DevModel m;  /* I/F pointers left null; the caller patches them */
+  std::string error;
+};
+
+namespace fbdetail {
+inline int put_i(std::vector<int32_t> &I, const std::vector<int32_t> &v) {
+  int off = (int)I.size();
+  I.insert(I.end(), v.begin(), v.end());
+  if (v.empty()) I.push_back(0);
+  return off;
+}
+inline int put_f(std::vector<float> &F, const std::vector<double> &v) {
+  int off = (int)F.size();
+  for (double x : v) F.push_back((float)x);
+  if (v.empty()) F.push_back(0.f);
+  while (F.size() % 4) F.push_back(0.f);
+  return off;
+}
+inline std::vector<int32_t> vi(const int32_t *p, int n) { return std::vector<int32_t>(p, p + n); }
+inline std::vector<double> vd(const double *p, int n) { return std::vector<double>(p, p + n); }
+inline void quat2mat(const double *q, double *m) {
+  double w = q[0], x = q[1], y = q[2], z = q[3];
+  m[0] = w*w + x*x - y*y - z*z; m[1] = 2*(x*y - w*z);         m[2] = 2*(x*z + w*y);
+  m[3] = 2*(x*y + w*z);         m[4] = w*w - x*x + y*y - z*z; m[5] = 2*(y*z - w*x);
+  m[6] = 2*(x*z - w*y);         m[7] = 2*(y*z + w*x);         m[8] = w*w - x*x - y*y + z*z;
+}
+}  // namespace fbdetail
+
+/* Flatten FbModel + FbFarms.  Returns false and sets out.error when the model
+ * leaves the supported subset. */
+inline bool fb_build_model(const FbModel *fm, const FbFarms *ff, const FbWaveController *wc,
+                           FbHostModel &out) {
+  using namespace fbdetail;
+  DevModel &m = out.m;
+  std::memset(&m, 0, sizeof(m));
+  std::vector<int32_t> &I = out.I;
+  std::vector<float> &F = out.F;
+  I.clear(); F.clear();
+  const int nb = fm->nbody, nj = fm->njnt, nv = fm->nv, nu = fm->nu, nc = fm->ncand;
+  if (nb < 2 || nv < 1) { out.error = "model has no moving body"; return false; }
+  m.nbody = nb; m.njnt = nj; m.nq = fm->nq; m.nv = nv; m.nu = nu; m.ncand = nc; m.nM = fm->nM;
+  m.timestep = (float)fm->timestep;
+  for (int k = 0; k < 3; k++) m.grav[k] = (float)fm->gravity[k];
+  m.impratio = (float)fm->impratio;
+  m.solver_iterations = fm->solver_iterations > 0 ? fm->solver_iterations : 100;
+  m.tolerance = (float)fm->tolerance;
+  m.solver_scale = (float)(1.0/(fm->meaninertia*(nv > 1 ? nv : 1)));
+
+  /* tree tables */
+  std::vector<int32_t> depth(nb, 0), firstchild(nb, -1), nextsib(nb, -1), lastchild(nb, -1),
+      lastdof(nb, -1);
+  int roots = 0, maxdepth = 0;
+  double total_mass = 0;
+  for (int b = 1; b < nb; b++) {
+    int p = fm->body_parentid[b];
+    if (p < 0 || p >= b) { out.error = "bodies must be in depth-first order"; return false; }
+    if (p == 0) roots++;
+    depth[b] = depth[p] + 1;
+    if (depth[b] > maxdepth) maxdepth = depth[b];
+    if (lastchild[p] < 0) firstchild[p] = b; else nextsib[lastchild[p]] = b;
+    lastchild[p] = b;
+    lastdof[b] = fm->body_dofnum[b] > 0 ? fm->body_dofadr[b] + fm->body_dofnum[b] - 1 : lastdof[p];
+    total_mass += fm->body_mass[b];
+  }
+  if (roots != 1) { out.error = "exactly one kinematic tree is supported (static bodies must be fused)"; return false; }
+  m.inv_total_mass = total_mass > 1e-15 ? (float)(1.0/total_mass) : 0.f;
+  m.nlevel = maxdepth;
+  std::vector<int32_t> lvl_start(maxdepth + 1, 0), lvl_body;
+  for (int l = 1; l <= maxdepth; l++) {
+    lvl_start[l-1] = (int)lvl_body.size();
+    for (int b = 1; b < nb; b++) if (depth[b] == l) lvl_body.push_back(b);
+  }
+  lvl_start[maxdepth] = (int)lvl_body.size();
+  m.nmaskw = (nv + 31)/32;
+  std::vector<int32_t> ancmask((size_t)nb*m.nmaskw, 0);
+  for (int b = 1; b < nb; b++)
+    for (int d = lastdof[b]; d >= 0; d = fm->dof_parentid[d])
+      ancmask[(size_t)b*m.nmaskw + d/32] |= (int32_t)(1u << (d % 32));
+
+  DevOffsets &o = m.o;
+  o.body_parent = put_i(I, vi(fm->body_parentid, nb));
+  o.body_jnt = put_i(I, vi(fm->body_jntid, nb));
+  o.body_dofadr = put_i(I, vi(fm->body_dofadr, nb));
+  o.body_dofnum = put_i(I, vi(fm->body_dofnum, nb));
+  o.body_firstchild = put_i(I, firstchild);
+  o.body_nextsib = put_i(I, nextsib);
+  o.body_lastdof = put_i(I, lastdof);
+  o.body_ancmask = put_i(I, ancmask);
+  o.lvl_start = put_i(I, lvl_start);
+  o.lvl_body = put_i(I, lvl_body);
+
+  /* joints + actuators grouped by joint */
+  std::vector<int32_t> actstart(nj + 1, 0), act_sorted;
+  for (int j = 0; j < nj; j++) {
+    actstart[j] = (int)act_sorted.size();
+    for (int a = 0; a < nu; a++) if (fm->actuator_trnid[a] == j) act_sorted.push_back(a);
+  }
+  actstart[nj] = (int)act_sorted.size();
+  std::vector<double> jqpos0(nj, 0.0);
+  m.any_limit = 0; m.any_stiffness = 0;
+  for (int j = 0; j < nj; j++) {
+    jqpos0[j] = fm->qpos0[fm->jnt_qposadr[j]];
+    if (fm->jnt_type[j] == FB_JNT_BALL) { out.error = "ball joints are outside the FARMS schema"; return false; }
+    if (fm->jnt_limited[j] && fm->jnt_type[j] != FB_JNT_FREE) m.any_limit = 1;
+    if (fm->jnt_stiffness[j] != 0) m.any_stiffness = 1;
+  }
+  o.jnt_type = put_i(I, vi(fm->jnt_type, nj));
+  o.jnt_body = put_i(I, vi(fm->jnt_bodyid, nj));
+  o.jnt_qposadr = put_i(I, vi(fm->jnt_qposadr, nj));
+  o.jnt_dofadr = put_i(I, vi(fm->jnt_dofadr, nj));
+  o.jnt_limited = put_i(I, vi(fm->jnt_limited, nj));
+  o.jnt_actstart = put_i(I, actstart);
+  o.act_sorted = put_i(I, act_sorted);
+
+  /* dofs + sparse mass-matrix entry table */
+  std::vector<int32_t> nanc(nv, 0), ent_i(fm->nM, 0), ent_j(fm->nM, 0);
+  m.any_damping = 0;
+  for (int d = 0; d < nv; d++) {
+    int adr = fm->dof_Madr[d];
+    for (int a = d; a >= 0; a = fm->dof_parentid[a]) {
+      if (adr >= fm->nM) { out.error = "dof_Madr/nM mismatch"; return false; }
+      ent_i[adr] = d; ent_j[adr] = a; adr++; nanc[d]++;
+    }
+    if (fm->dof_damping[d] > 0) m.any_damping = 1;
+  }
+  o.dof_body = put_i(I, vi(fm->dof_bodyid, nv));
+  o.dof_jnt = put_i(I, vi(fm->dof_jntid, nv));
+  o.dof_parent = put_i(I, vi(fm->dof_parentid, nv));
+  o.dof_Madr = put_i(I, vi(fm->dof_Madr, nv));
+  o.dof_nanc = put_i(I, nanc);
+  o.ent_i = put_i(I, ent_i);
+  o.ent_j = put_i(I, ent_j);
+
+  /* collision candidates: plane (static, world frame) vs sphere / capsule end */
+  std::vector<int32_t> cbody(nc), ccaps(nc);
+  std::vector<double> lpos(3*nc), laxis(3*nc), rad(nc), pn(3*nc), pd(nc), cinvw(nc);
+  for (int c = 0; c < nc; c++) {
+    int g1 = fm->cand_geom1[c], g2 = fm->cand_geom2[c];
+    if (fm->geom_bodyid[g1] != 0 || fm->geom_type[g1] != FB_GEOM_PLANE) {
+      out.error = "collision candidates must be world planes vs tree geoms"; return false;
+    }
+    double pm[9], gm[9];
+    quat2mat(fm->geom_quat + 4*g1, pm);
+    quat2mat(fm->geom_quat + 4*g2, gm);
+    double n[3] = { pm[2], pm[5], pm[8] }, ax[3] = { gm[2], gm[5], gm[8] };
+    double off = fm->cand_end[c]*fm->geom_size[3*g2+1];
+    cbody[c] = fm->geom_bodyid[g2];
+    ccaps[c] = fm->cand_end[c] != 0;
+    for (int k = 0; k < 3; k++) {
+      lpos[3*c+k] = fm->geom_pos[3*g2+k] + off*ax[k];
+      laxis[3*c+k] = ax[k];
+      pn[3*c+k] = n[k];
+    }
+    rad[c] = fm->geom_size[3*g2];
+    pd[c] = n[0]*fm->geom_pos[3*g1] + n[1]*fm->geom_pos[3*g1+1] + n[2]*fm->geom_pos[3*g1+2];
+    cinvw[c] = fm->body_invweight0[2*0] + fm->body_invweight0[2*cbody[c]];
+  }
+  o.cand_body = put_i(I, cbody);
+  o.cand_iscapsule = put_i(I, ccaps);
+  o.cand_sensor = put_i(I, ff ? vi(ff->cand_sensor, 4*nc) : std::vector<int32_t>(4*nc, -1));
+  o.act_jnt = put_i(I, vi(fm->actuator_trnid, nu));
+  o.act_ctrllimited = put_i(I, vi(fm->actuator_ctrllimited, nu));
+  o.act_forcelimited = put_i(I, vi(fm->actuator_forcelimited, nu));
+
+  /* farms tables */
+  m.n_links = ff ? ff->n_links : 0;
+  m.n_joints = ff ? ff->n_joints : 0;
+  m.n_contacts = ff ? ff->n_contacts : 0;
+  m.n_xfrc = ff ? ff->n_xfrc : 0;
+  m.n_swim = ff ? ff->n_swim : 0;
+  m.link_cols = ff ? ff->link_cols : 20;
+  m.joint_cols = ff ? ff->joint_cols : 18;
+  m.contact_cols = ff ? ff->contact_cols : 12;
+  m.xfrc_cols = ff ? ff->xfrc_cols : 6;
+  if (m.link_cols != 20 || m.contact_cols != 12 || m.xfrc_cols != 6 || m.joint_cols % 2) {
+    out.error = "unexpected farms row widths (expected 20 / even / 12 / 6)"; return false;
+  }
+  m.col_jpos = ff ? ff->col_joint_position : 0;
+  m.col_jvel = ff ? ff->col_joint_velocity : 1;
+  m.col_jtrq = ff ? ff->col_joint_torque : 11;
+  m.col_jlim = ff ? ff->col_joint_limit_force : 16;
+  o.link_body = put_i(I, ff ? vi(ff->link_body, m.n_links) : std::vector<int32_t>());
+  o.fj_qposadr = put_i(I, ff ? vi(ff->joint_qposadr, m.n_joints) : std::vector<int32_t>());
+  o.fj_dofadr = put_i(I, ff ? vi(ff->joint_dofadr, m.n_joints) : std::vector<int32_t>());
+  o.fj_jntid = put_i(I, ff ? vi(ff->joint_jntid, m.n_joints) : std::vector<int32_t>());
+  o.fj_actpos = put_i(I, ff ? vi(ff->joint_act_position, m.n_joints) : std::vector<int32_t>());
+  o.fj_actvel = put_i(I, ff ? vi(ff->joint_act_velocity, m.n_joints) : std::vector<int32_t>());
+  o.fj_acttrq = put_i(I, ff ? vi(ff->joint_act_torque, m.n_joints) : std::vector<int32_t>());
+  o.xfrc_body = put_i(I, ff ? vi(ff->xfrc_body, m.n_xfrc) : std::vector<int32_t>());
+  o.swim_link = put_i(I, ff ? vi(ff->swim_links_index, m.n_swim) : std::vector<int32_t>());
+  o.swim_xfrc = put_i(I, ff ? vi(ff->swim_xfrc_index, m.n_swim) : std::vector<int32_t>());
+  /* body -> xfrc row (the downstream applier zeroes xfrc_applied, then fills data2xfrc) */
+  std::vector<int32_t> body_xfrcrow(nb, -1);
+  for (int x = 0; x < m.n_xfrc; x++) {
+    int b = ff->xfrc_body[x];
+    if (b < 0 || b >= nb) { out.error = "xfrc_body out of range"; return false; }
+    body_xfrcrow[b] = x;
+  }
+  o.body_xfrcrow = put_i(I, body_xfrcrow);
+  m.n_wc = wc ? wc->n : 0;
+  o.wc_act = put_i(I, wc ? vi(wc->actuator, wc->n) : std::vector<int32_t>());
+
+  /* floats */
+  std::vector<double> invw(nb);
+  for (int b = 0; b < nb; b++) invw[b] = fm->body_invweight0[2*b];
+  o.body_pos = put_f(F, vd(fm->body_pos, 3*nb));
+  o.body_quat = put_f(F, vd(fm->body_quat, 4*nb));
+  o.body_ipos = put_f(F, vd(fm->body_ipos, 3*nb));
+  o.body_iquat = put_f(F, vd(fm->body_iquat, 4*nb));
+  o.body_mass = put_f(F, vd(fm->body_mass, nb));
+  o.body_inertia = put_f(F, vd(fm->body_inertia, 3*nb));
+  o.body_invw = put_f(F, invw);
+  o.jnt_pos = put_f(F, vd(fm->jnt_pos, 3*nj));
+  o.jnt_axis = put_f(F, vd(fm->jnt_axis, 3*nj));
+  o.jnt_stiffness = put_f(F, vd(fm->jnt_stiffness, nj));
+  o.jnt_range = put_f(F, vd(fm->jnt_range, 2*nj));
+  o.jnt_margin = put_f(F, vd(fm->jnt_margin, nj));
+  o.jnt_solref = put_f(F, vd(fm->jnt_solref, 2*nj));
+  o.jnt_solimp = put_f(F, vd(fm->jnt_solimp, 5*nj));
+  o.jnt_qpos0 = put_f(F, jqpos0);
+  o.dof_damping = put_f(F, vd(fm->dof_damping, nv));
+  o.dof_armature = put_f(F, vd(fm->dof_armature, nv));
+  o.dof_invw = put_f(F, vd(fm->dof_invweight0, nv));
+  o.cand_lpos = put_f(F, lpos);
+  o.cand_laxis = put_f(F, laxis);
+  o.cand_radius = put_f(F, rad);
+  o.cand_pn = put_f(F, pn);
+  o.cand_pd = put_f(F, pd);
+  o.cand_friction = put_f(F, vd(fm->cand_friction, nc));
+  o.cand_solref = put_f(F, vd(fm->cand_solref, 2*nc));
+  o.cand_solimp = put_f(F, vd(fm->cand_solimp, 5*nc));
+  o.cand_margin = put_f(F, vd(fm->cand_margin, nc));
+  o.cand_gap = put_f(F, vd(fm->cand_gap, nc));
+  o.cand_invw = put_f(F, cinvw);
+  std::vector<double> gain(nu);
+  for (int a = 0; a < nu; a++) gain[a] = fm->actuator_gainprm[3*a];
+  o.act_gain = put_f(F, gain);
+  o.act_bias = put_f(F, vd(fm->actuator_biasprm, 3*nu));
+  o.act_ctrlrange = put_f(F, vd(fm->actuator_ctrlrange, 2*nu));
+  o.act_forcerange = put_f(F, vd(fm->actuator_forcerange, 2*nu));
+  o.act_gear = put_f(F, vd(fm->actuator_gear, nu));
+  o.swim_mass = put_f(F, ff ? vd(ff->swim_mass, m.n_swim) : std::vector<double>());
+  o.swim_height = put_f(F, ff ? vd(ff->swim_height, m.n_swim) : std::vector<double>());
+  o.swim_density = put_f(F, ff ? vd(ff->swim_density, m.n_swim) : std::vector<double>());
+  o.swim_coef = put_f(F, ff ? vd(ff->swim_coefficients, 6*m.n_swim) : std::vector<double>());
+  o.wc_amp = put_f(F, wc ? vd(wc->amplitude, wc->n) : std::vector<double>());
+  o.wc_freq = put_f(F, wc ? vd(wc->frequency, wc->n) : std::vector<double>());
+  o.wc_lag = put_f(F, wc ? vd(wc->phase_lag, wc->n) : std::vector<double>());
+  o.wc_off = put_f(F, wc ? vd(wc->offset, wc->n) : std::vector<double>());
+  o.key_qpos = put_f(F, vd(fm->key_qpos, fm->nq));
+  o.key_qvel = put_f(F, vd(fm->key_qvel, nv));
+
+  /* water + units */
+  double meters = ff ? ff->meters : 1.0, seconds = ff ? ff->seconds : 1.0,
+         kilograms = ff ? ff->kilograms : 1.0;
+  double velocity = meters/seconds, accel = meters/(seconds*seconds);
+  double newtons = kilograms*accel, torques = kilograms*meters*meters/(seconds*seconds);
+  m.inv_meters = (float)(1.0/meters);
+  m.inv_velocity = (float)(1.0/velocity);
+  m.inv_angvel = (float)seconds;
+  m.inv_torques = (float)(1.0/torques);
+  m.inv_newtons = (float)(1.0/newtons);
+  m.newtons = (float)newtons;
+  m.torques = (float)torques;
+  m.water_drag = ff ? (ff->water_drag != 0) : 0;
+  m.water_buoyancy = ff ? (ff->water_buoyancy != 0) : 0;
+  m.water_surface = ff ? (float)ff->water_surface : 0.f;
+  m.water_viscosity = ff ? (float)ff->water_viscosity : 1.f;
+  for (int k = 0; k < 3; k++) m.water_velocity[k] = ff ? (float)ff->water_velocity[k] : 0.f;
+
+  /* shared-memory layout */
+  m.maxcon = nc;
+  m.maxefc = 2*nj + 4*nc;
+  m.npack = nv*(nv + 1)/2;
+  DevLayout &L = m.L;
+  int off = 0;
+  auto take = [&off](int n) { int r = off; off += (n + 3) & ~3; return r; };
+  L.qpos = take(fm->nq); L.qvel = take(nv); L.ctrl = take(nu); L.actf = take(nu);
+  L.xpos = take(3*nb); L.xquat = take(4*nb); L.xipos = take(3*nb);
+  L.xanchor = take(3*nj); L.xaxis = take(3*nj);
+  L.cinert = take(10*nb); L.cdof = take(6*nv); L.cvel = take(6*nb); L.xfrc = take(6*nb);
+  L.qM = take(fm->nM); L.qLD = take(fm->nM); L.dinv = take(nv);
+  L.fsm = take(nv); L.qacc = take(nv); L.fcon = take(nv); L.grad = take(nv); L.pvec = take(nv);
+  L.tmp1 = take(nv); L.tmp2 = take(nv);
+  L.limf = take(nj);
+  L.scratch = off;
+  int s = off;
+  auto stake = [&s](int n) { int r = s; s += (n + 3) & ~3; return r; };
+  L.crb = stake(10*nb); L.cacc = stake(6*nb); L.cfrc = stake(6*nb); L.buf = stake(6*nv);
+  int natural = s - off;
+  int need = nc > 0 || m.any_limit ? 2*((m.npack + 3) & ~3) : 0;
+  L.Md = L.scratch;
+  L.H = L.scratch + ((m.npack + 3) & ~3);
+  off += natural > need ? natural : need;
+  L.n_float = off;
+  L.con_cand = 0;
+  L.n_int = (m.maxcon + 3) & ~3;
+  if (L.n_int == 0) L.n_int = 4;
+  return true;
+}
+
+#endif /* FB_MODEL_H_ */

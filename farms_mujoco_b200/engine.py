@@ -1,0 +1,367 @@
+"""Batched physics over the C ABI (include/farms_b200.h).
+
+``BatchedPhysics`` stands where dm_control's ``Physics`` stands in the reference
+(farms_mujoco/simulation/simulation.py:53 ``mjcf.Physics.from_mjcf_model`` and
+:156 ``env.step`` -> ``mj_step``): it owns the compiled model and the state of
+``n_envs`` independent environments and advances all of them with one call.
+There is no CPU fallback: construction raises when the CUDA library is missing
+or no GPU is present.
+"""
+
+import ctypes as ct
+import os
+
+import numpy as np
+
+from . import cabi
+from .data import AnimatData
+from .layout import sc
+from .mjcf_subset import parse_mjcf
+from .simulation.physics import FarmsTables, get_sensor_maps, get_physics2data_maps
+from .units import SimulationUnitScaling
+
+_PKG = os.path.dirname(os.path.abspath(__file__))
+DEFAULT_LIBRARY = os.path.join(_PKG, 'libfarmsb200.so')
+
+# name, restype, argtypes -- every symbol include/farms_b200.h declares
+_H = ct.c_void_p
+ABI_SYMBOLS = {
+    'fb_last_error': (ct.c_char_p, []),
+    'fb_abi_version': (ct.c_int, []),
+    'fb_create': (ct.c_int, [ct.POINTER(cabi.FbModel), ct.POINTER(cabi.FbFarms), ct.c_int,
+                             ct.c_int, ct.c_int, ct.c_int, ct.POINTER(_H)]),
+    'fb_destroy': (None, [_H]),
+    'fb_reset': (ct.c_int, [_H, cabi.c_double_p, cabi.c_double_p]),
+    'fb_set_ctrl': (ct.c_int, [_H, cabi.c_double_p]),
+    'fb_set_qpos_spring': (ct.c_int, [_H, cabi.c_double_p]),
+    'fb_set_env_phase': (ct.c_int, [_H, cabi.c_double_p]),
+    'fb_set_wave_controller': (ct.c_int, [_H, ct.POINTER(cabi.FbWaveController)]),
+    'fb_set_water_velocity': (ct.c_int, [_H, ct.c_double, ct.c_double, ct.c_double]),
+    'fb_set_swimming': (ct.c_int, [_H, ct.c_int, ct.c_int]),
+    'fb_step': (ct.c_int, [_H, ct.c_int, ct.c_int, ct.c_int]),
+    'fb_synchronize': (ct.c_int, [_H]),
+    'fb_last_step_ms': (ct.c_int, [_H, ct.POINTER(ct.c_float)]),
+    'fb_launch_count': (ct.c_int64, [_H]),
+    'fb_log_view': (ct.c_int, [_H, ct.POINTER(cabi.FbLogView)]),
+    'fb_state_view': (ct.c_int, [_H, ct.POINTER(cabi.FbStateView)]),
+    'fb_derived_view': (ct.c_int, [_H, ct.POINTER(cabi.FbDerivedView)]),
+    'fb_export_farms': (ct.c_int, [_H, ct.c_int, cabi.c_double_p, cabi.c_double_p,
+                                   cabi.c_double_p, cabi.c_double_p]),
+    'fb_step_host': (ct.c_int, [_H, ct.c_void_p, ct.c_void_p, ct.c_int, ct.c_void_p, ct.c_void_p]),
+    'fb_copy_to_host': (ct.c_int, [_H, ct.c_void_p, ct.c_void_p, ct.c_int64]),
+    'fb_copy_to_device': (ct.c_int, [_H, ct.c_void_p, ct.c_void_p, ct.c_int64]),
+    'fb_team_lanes': (ct.c_int, [_H]),
+    'fb_smem_bytes_per_env': (ct.c_int, [_H]),
+    'fb_device_ptr_stream': (ct.c_int, [_H, ct.POINTER(ct.c_void_p)]),
+}
+
+_LIBS = {}
+
+
+class EngineError(RuntimeError):
+    """Raised for every non-zero return of the C ABI (message = fb_last_error)."""
+
+
+def load_library(path=None):
+    """dlopen the engine and bind every ABI symbol.  No fallback of any kind."""
+    path = os.path.abspath(path or DEFAULT_LIBRARY)
+    if path in _LIBS:
+        return _LIBS[path]
+    if not os.path.exists(path):
+        raise EngineError(
+            f'{path} not found: build it with `python -c "import __graft_entry__ as g; g.build()"` '
+            '(nvcc, sm_100a).  The engine has no CPU fallback.')
+    lib = ct.CDLL(path)
+    for name, (restype, argtypes) in ABI_SYMBOLS.items():
+        fn = getattr(lib, name)
+        fn.restype = restype
+        fn.argtypes = argtypes
+    if lib.fb_abi_version() != 1:
+        raise EngineError('ABI version mismatch')
+    _LIBS[path] = lib
+    return lib
+
+
+class _DeviceArray:
+    """Zero-copy handle on an engine-owned device buffer (``__cuda_array_interface__``)."""
+
+    def __init__(self, ptr, shape, typestr, owner):
+        self.ptr, self.shape, self.typestr, self.owner = int(ptr), tuple(shape), typestr, owner
+        self.__cuda_array_interface__ = {
+            'shape': self.shape, 'typestr': typestr, 'data': (self.ptr, False), 'version': 2,
+            'strides': None,
+        }
+
+
+def _ptr(p):
+    return ct.cast(p, ct.c_void_p).value or 0
+
+
+class BatchedPhysics:
+    """``n_envs`` copies of one compiled FARMS model stepping in lockstep."""
+    # pylint: disable=too-many-instance-attributes,too-many-public-methods
+
+    def __init__(self, model, n_envs, links_names, joints_names, contacts_names=(), xfrc_names=(),
+                 animat_options=None, arena_options=None, units=None, buffer_size=1, device=0,
+                 team_lanes=0, library=None):
+        # pylint: disable=too-many-arguments,too-many-locals
+        self.lib = load_library(library)
+        self.model = model
+        self.n_envs = int(n_envs)
+        self.buffer_size = int(buffer_size)
+        self.units = units if units is not None else SimulationUnitScaling()
+        names = AnimatData.from_sensors_names(
+            timestep=model.timestep, buffer_size=1, links=list(links_names),
+            joints=list(joints_names), contacts=list(contacts_names), xfrc=list(xfrc_names))
+        self.names = names.sensors
+        self.maps = {'sensors': get_sensor_maps(model)}
+        get_physics2data_maps(model, self.names, self.maps['sensors'])
+        self.tables = FarmsTables(model, self.names, self.maps['sensors'], animat_options,
+                                  arena_options, self.units)
+        self._cmodel = cabi.model_to_c(model)
+        self._cfarms = cabi.farms_to_c(self.tables)
+        handle = _H()
+        self._handle = None
+        self._check(self.lib.fb_create(self._cmodel.byref(), self._cfarms.byref(), self.n_envs,
+                                       int(device), self.buffer_size, int(team_lanes),
+                                       ct.byref(handle)))
+        self._handle = handle
+        self._log = cabi.FbLogView()
+        self._state = cabi.FbStateView()
+        self._derived = cabi.FbDerivedView()
+        self._check(self.lib.fb_log_view(handle, ct.byref(self._log)))
+        self._check(self.lib.fb_state_view(handle, ct.byref(self._state)))
+        self._check(self.lib.fb_derived_view(handle, ct.byref(self._derived)))
+        self.iteration = 0
+
+    @classmethod
+    def from_spec(cls, spec, n_envs, buffer_size=1, **kwargs):
+        """Build from an ``AnimatSpec`` (models.py): MJCF text + option objects."""
+        model = parse_mjcf(spec.mjcf)
+        return cls(model, n_envs, spec.links_names, spec.joints_names, spec.contacts_names,
+                   spec.xfrc_names, animat_options=spec.animat_options,
+                   arena_options=spec.arena_options, units=spec.simulation_options.units,
+                   buffer_size=buffer_size, **kwargs)
+
+    # ------------------------------------------------------------------ utils
+    def _check(self, code):
+        if code != 0:
+            raise EngineError(self.lib.fb_last_error().decode())
+
+    def close(self):
+        if self._handle is not None:
+            self.lib.fb_destroy(self._handle)
+            self._handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:  # pylint: disable=broad-except
+            pass
+
+    def _read(self, ptr, shape, dtype=np.float32):
+        out = np.empty(shape, dtype=dtype)
+        self._check(self.lib.fb_copy_to_host(self._handle, _ptr(ptr), out.ctypes.data, out.nbytes))
+        return out
+
+    def _write(self, ptr, values, dtype=np.float32):
+        arr = np.ascontiguousarray(values, dtype=dtype)
+        self._check(self.lib.fb_copy_to_device(self._handle, _ptr(ptr), arr.ctypes.data, arr.nbytes))
+
+    def device_array(self, ptr, shape, typestr='<f4'):
+        """Zero-copy view for ``torch.as_tensor(..., device='cuda')`` / cupy."""
+        return _DeviceArray(_ptr(ptr), shape, typestr, self)
+
+    # ------------------------------------------------------------ state I/O
+    def reset(self, qpos=None, qvel=None):
+        """``physics.reset(keyframe_id=0)`` + the reset's ``mj_forward`` (task.py:137)."""
+        qp = None if qpos is None else np.ascontiguousarray(qpos, dtype=np.float64)
+        qv = None if qvel is None else np.ascontiguousarray(qvel, dtype=np.float64)
+        if qp is not None:
+            assert qp.shape == (self.n_envs, self.model.nq), qp.shape
+        if qv is not None:
+            assert qv.shape == (self.n_envs, self.model.nv), qv.shape
+        self._check(self.lib.fb_reset(
+            self._handle,
+            None if qp is None else qp.ctypes.data_as(cabi.c_double_p),
+            None if qv is None else qv.ctypes.data_as(cabi.c_double_p)))
+        self.iteration = 0
+
+    def step(self, n_steps=1, want_derived=False, sync=True):
+        """``n_steps`` x (control -> mj_step -> log row -> drag) for every environment."""
+        self._check(self.lib.fb_step(self._handle, int(n_steps), int(bool(want_derived)),
+                                     int(bool(sync))))
+        self.iteration += int(n_steps)
+
+    def synchronize(self):
+        self._check(self.lib.fb_synchronize(self._handle))
+
+    def last_step_ms(self):
+        ms = ct.c_float()
+        self._check(self.lib.fb_last_step_ms(self._handle, ct.byref(ms)))
+        return float(ms.value)
+
+    def launch_count(self):
+        return int(self.lib.fb_launch_count(self._handle))
+
+    def set_ctrl(self, ctrl):
+        arr = np.ascontiguousarray(ctrl, dtype=np.float64)
+        assert arr.shape == (self.n_envs, self.model.nu), arr.shape
+        self._check(self.lib.fb_set_ctrl(self._handle, arr.ctypes.data_as(cabi.c_double_p)))
+
+    def set_qpos_spring(self, qpos_spring):
+        arr = np.ascontiguousarray(qpos_spring, dtype=np.float64)
+        assert arr.shape == (self.n_envs, self.model.nq), arr.shape
+        self._check(self.lib.fb_set_qpos_spring(self._handle, arr.ctypes.data_as(cabi.c_double_p)))
+
+    def set_env_phase(self, phase):
+        arr = np.ascontiguousarray(phase, dtype=np.float64)
+        assert arr.shape == (self.n_envs,), arr.shape
+        self._check(self.lib.fb_set_env_phase(self._handle, arr.ctypes.data_as(cabi.c_double_p)))
+
+    def set_wave_controller(self, actuators, amplitude, frequency, phase_lag, offset=None):
+        """On-device travelling-wave position control (include/farms_b200.h FbWaveController)."""
+        if actuators is None or len(actuators) == 0:
+            self._check(self.lib.fb_set_wave_controller(self._handle, None))
+            return
+        n = len(actuators)
+        keep = cabi.Marshalled(cabi.FbWaveController())
+        keep.struct.n = n
+        keep.set_int('actuator', actuators)
+        keep.set_double('amplitude', amplitude)
+        keep.set_double('frequency', frequency)
+        keep.set_double('phase_lag', phase_lag)
+        keep.set_double('offset', np.zeros(n) if offset is None else offset)
+        self._check(self.lib.fb_set_wave_controller(self._handle, keep.byref()))
+
+    def set_water_velocity(self, velocity):
+        self._check(self.lib.fb_set_water_velocity(self._handle, *[float(v) for v in velocity]))
+
+    def set_swimming(self, drag, buoyancy):
+        self._check(self.lib.fb_set_swimming(self._handle, int(bool(drag)), int(bool(buoyancy))))
+
+    # --------------------------------------------------------------- views
+    @property
+    def qpos(self):
+        return self._read(self._state.qpos_dev, (self.n_envs, self.model.nq))
+
+    @property
+    def qvel(self):
+        return self._read(self._state.qvel_dev, (self.n_envs, self.model.nv))
+
+    @property
+    def ctrl(self):
+        return self._read(self._state.ctrl_dev, (self.n_envs, max(1, self.model.nu)))[:, :self.model.nu]
+
+    @property
+    def xfrc_applied(self):
+        return self._read(self._state.xfrc_applied_dev, (self.n_envs, self.model.nbody, 6))
+
+    @property
+    def flags(self):
+        return self._read(self._state.flags_dev, (self.n_envs,), np.int32)
+
+    def set_state(self, qpos=None, qvel=None):
+        """Overwrite qpos/qvel without re-running the reset forward pass."""
+        if qpos is not None:
+            self._write(self._state.qpos_dev, qpos)
+        if qvel is not None:
+            self._write(self._state.qvel_dev, qvel)
+
+    def derived(self):
+        """mjData-like quantities of the state the last step/reset ran forward on."""
+        d, n, m = self._derived, self.n_envs, self.model
+        mc = int(d.maxcon)
+        out = dict(
+            xpos=self._read(d.xpos_dev, (n, m.nbody, 3)), xquat=self._read(d.xquat_dev, (n, m.nbody, 4)),
+            xipos=self._read(d.xipos_dev, (n, m.nbody, 3)),
+            linvel=self._read(d.linvel_dev, (n, m.nbody, 3)),
+            angvel=self._read(d.angvel_dev, (n, m.nbody, 3)),
+            actuator_force=self._read(d.actuator_force_dev, (n, max(1, m.nu)))[:, :m.nu],
+            jnt_limit_force=self._read(d.jnt_limit_force_dev, (n, max(1, m.njnt))),
+            qacc=self._read(d.qacc_dev, (n, m.nv)),
+            ncon=self._read(d.ncon_dev, (n,), np.int32),
+            con_cand=self._read(d.con_cand_dev, (n, mc), np.int32),
+            con_dist=self._read(d.con_dist_dev, (n, mc)),
+            con_pos=self._read(d.con_pos_dev, (n, mc, 3)),
+            con_frame=self._read(d.con_frame_dev, (n, mc, 9)),
+            con_force=self._read(d.con_force_dev, (n, mc, 3)),
+        )
+        return out
+
+    def log_arrays(self, env=None):
+        """Host copy of the device log: dict of ``[n_envs, ring, n_items, n_cols]`` float32
+        (or ``[ring, n_items, n_cols]`` for one ``env``: exactly the reference's
+        ``data.sensors.<kind>.array`` shape, task.py:158)."""
+        log, names = self._log, self.names
+        shapes = dict(
+            links=(log.links_dev, len(names.links.names), sc.link_size, log.links_env_stride),
+            joints=(log.joints_dev, len(names.joints.names), sc.joint_size, log.joints_env_stride),
+            contacts=(log.contacts_dev, len(names.contacts.names), sc.contact_size,
+                      log.contacts_env_stride),
+            xfrc=(log.xfrc_dev, len(names.xfrc.names), sc.xfrc_size, log.xfrc_env_stride),
+        )
+        out = {}
+        for kind, (ptr, n_items, cols, stride) in shapes.items():
+            if n_items == 0:
+                shape = (self.n_envs, self.buffer_size, 0, cols)
+                out[kind] = np.zeros(shape if env is None else shape[1:], dtype=np.float32)
+                continue
+            if env is None:
+                out[kind] = self._read(ptr, (self.n_envs, self.buffer_size, n_items, cols))
+            else:
+                base = _ptr(ptr) + 4*int(env)*int(stride)
+                out[kind] = self._read(base, (self.buffer_size, n_items, cols))
+        return out
+
+    def export_farms(self, env, data=None):
+        """Fill (or create) a reference-shaped float64 ``AnimatData`` for one environment."""
+        names = self.names
+        if data is None:
+            data = AnimatData.from_sensors_names(
+                timestep=self.model.timestep, buffer_size=self.buffer_size,
+                links=names.links.names, joints=names.joints.names,
+                contacts=names.contacts.names, xfrc=names.xfrc.names)
+        ptrs = []
+        for arr in (data.sensors.links.array, data.sensors.joints.array,
+                    data.sensors.contacts.array, data.sensors.xfrc.array):
+            assert arr.dtype == np.float64 and arr.flags['C_CONTIGUOUS']
+            ptrs.append(arr.ctypes.data_as(cabi.c_double_p) if arr.size else None)
+        self._check(self.lib.fb_export_farms(self._handle, int(env), *ptrs))
+        return data
+
+    def step_host(self, qpos, qvel, n_steps, links_row, joints_row):
+        """End-to-end call on HOST float32 buffers (pinned recommended): upload
+        qpos/qvel, step, download the last links/joints log row of every env."""
+        def addr(arr):
+            if arr is None:
+                return None
+            if hasattr(arr, 'data_ptr'):
+                return arr.data_ptr()
+            return arr.ctypes.data
+        self._check(self.lib.fb_step_host(self._handle, addr(qpos), addr(qvel), int(n_steps),
+                                          addr(links_row), addr(joints_row)))
+        self.iteration += int(n_steps)
+
+    # ---------------------------------------------------------- introspection
+    @property
+    def team_lanes(self):
+        return int(self.lib.fb_team_lanes(self._handle))
+
+    @property
+    def smem_bytes_per_env(self):
+        return int(self.lib.fb_smem_bytes_per_env(self._handle))
+
+    @property
+    def log_view(self):
+        return self._log
+
+    @property
+    def state_view(self):
+        return self._state
+
+    @property
+    def log_bytes_per_env_step(self):
+        n = self.names
+        return 4*(sc.link_size*len(n.links.names) + sc.joint_size*len(n.joints.names)
+                  + sc.contact_size*len(n.contacts.names) + sc.xfrc_size*len(n.xfrc.names))

@@ -233,10 +233,15 @@ def _finish(name, links, joints_cfg, swimming, drag_coefficients, water, arena_z
         model_name=name, links=links, joints_opts=joints_opts, motors=motors,
         spawn_pose=spawn_pose, sim=sim, arena_z=arena_z,
         water_height=water.height, friction=friction)
+    def coefficients(link):
+        # a callable gives per-link coefficients (real FARMS animats scale them with the
+        # link's size; explicit quadratic drag is unstable when c*|v|*dt/m approaches 1)
+        coefs = drag_coefficients(link) if callable(drag_coefficients) else drag_coefficients
+        return [list(coefs[0]), list(coefs[1])]
+
     links_opts = [
         LinkOptions(name=link.name, swimming=swimming, density=1000.0,
-                    drag_coefficients=[list(drag_coefficients[0]), list(drag_coefficients[1])],
-                    friction=list(friction))
+                    drag_coefficients=coefficients(link), friction=list(friction))
         for link in links
     ]
     animat_options = AnimatOptions(
@@ -359,9 +364,14 @@ def salamander(swimming=False, timestep=1e-3, n_iterations=1000):
         water = WaterOptions(height=None)
         spawn = [0.0, 0.0, limb + r_foot + 0.002, 0.0, 0.0, 0.0]
         arena_z = 0.0
+    def drag(link):
+        if 'leg' in link.name:   # ~ frontal area / r^5 scaling of the 8 mm limb segments
+            return [[-0.025, -0.25, -0.25], [-1e-8, -1e-8, -1e-8]]
+        return [[-0.5, -5.0, -5.0], [-1e-3, -1e-3, -1e-3]]
+
     return _finish(
         'salamander', links, joints_cfg, swimming=swimming,
-        drag_coefficients=[[-0.5, -5.0, -5.0], [-1e-3, -1e-3, -1e-3]],
+        drag_coefficients=drag,
         water=water, arena_z=arena_z, spawn_pose=spawn, contacts_names=contacts,
         timestep=timestep, n_iterations=n_iterations, friction=[1.0, 0.0, 0.0])
 

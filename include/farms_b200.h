@@ -206,6 +206,11 @@ int fb_export_farms(FbHandle *h, int env, double *links, double *joints,
 int fb_step_host(FbHandle *h, const float *qpos, const float *qvel, int n_steps,
                  float *links_row, float *joints_row);
 
+/* Raw copies between host memory and the engine's device buffers (pointers
+ * taken from the views above); for hosts without torch (plain ctypes). */
+int fb_copy_to_host(FbHandle *h, const void *dev_ptr, void *host_ptr, int64_t bytes);
+int fb_copy_to_device(FbHandle *h, void *dev_ptr, const void *host_ptr, int64_t bytes);
+
 /* introspection */
 int fb_team_lanes(FbHandle *h);
 int fb_smem_bytes_per_env(FbHandle *h);

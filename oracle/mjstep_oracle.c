@@ -471,8 +471,12 @@ void orc_make_constraint(const FbModel *m, OrcData *d) {
                 m->cand_solref + 2*c, m->cand_solimp + 5*c, ORC_CNSTR_CONTACT_PYRAMIDAL, i);
       }
     }
-    /* pyramidal: all edges share Rpy = 2 mu^2 R(first edge) */
-    double Rpy = fmax(MJ_MINVAL, 2*mu*mu*d->efc_R[first]);
+    /* mj_makeImpedance: R[1] = R[0]/impratio, contact.mu = friction*sqrt(R[1]/R[0]);
+     * pyramidal edges all get Rpy = 2 contact.mu^2 R[1] */
+    double impratio = fmax(MJ_MINVAL, m->impratio);
+    double R1 = d->efc_R[first]/impratio;
+    double cmu = mu*sqrt(R1/d->efc_R[first]);
+    double Rpy = fmax(MJ_MINVAL, 2*cmu*cmu*R1);
     for (int k = 0; k < 4; k++) d->efc_R[first+k] = Rpy;
   }
   for (int r = 0; r < d->nefc; r++) d->efc_D[r] = 1/d->efc_R[r];
