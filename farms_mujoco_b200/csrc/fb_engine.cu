@@ -42,7 +42,10 @@ static const char *dev_error() { return "emulation backend error"; }
 typedef cudaStream_t fbStream;
 static int dev_alloc(void **p, size_t bytes) {
   if (cudaMalloc(p, bytes ? bytes : 1) != cudaSuccess) return -1;
-  return cudaMemset(*p, 0, bytes ? bytes : 1) == cudaSuccess ? 0 : -1;
+  /* the memset runs on the legacy stream, which the handle's non-blocking
+   * stream does not order against: wait for it before anyone uploads */
+  if (cudaMemset(*p, 0, bytes ? bytes : 1) != cudaSuccess) return -1;
+  return cudaDeviceSynchronize() == cudaSuccess ? 0 : -1;
 }
 static void dev_free(void *p) { cudaFree(p); }
 static int dev_zero(void *p, size_t bytes, fbStream st) { return cudaMemsetAsync(p, 0, bytes, st) == cudaSuccess ? 0 : -1; }
@@ -502,12 +505,13 @@ int fb_export_farms(FbHandle *h, int env, double *links, double *joints, double 
   return 0;
 }
 
-int fb_step_host(FbHandle *h, const float *qpos, const float *qvel, int n_steps, float *links_row,
-                 float *joints_row) {
+int fb_step_host(FbHandle *h, const float *ctrl, const float *qpos, const float *qvel,
+                 int n_steps, float *links_row, float *joints_row) {
   if (!h) return fail("null handle");
   FbParams &P = h->P;
   const DevModel &m = h->hm.m;
   const size_t n = (size_t)P.n_envs;
+  if (ctrl && m.nu > 0 && h2d(P.ctrl, ctrl, n*m.nu*sizeof(float), h->stream)) return fail(dev_error());
   if (qpos && h2d(P.qpos, qpos, n*m.nq*sizeof(float), h->stream)) return fail(dev_error());
   if (qvel && h2d(P.qvel, qvel, n*m.nv*sizeof(float), h->stream)) return fail(dev_error());
   if (launch(h, FB_MODE_STEP, n_steps, 0)) return -1;

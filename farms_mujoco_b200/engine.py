@@ -47,7 +47,8 @@ ABI_SYMBOLS = {
     'fb_derived_view': (ct.c_int, [_H, ct.POINTER(cabi.FbDerivedView)]),
     'fb_export_farms': (ct.c_int, [_H, ct.c_int, cabi.c_double_p, cabi.c_double_p,
                                    cabi.c_double_p, cabi.c_double_p]),
-    'fb_step_host': (ct.c_int, [_H, ct.c_void_p, ct.c_void_p, ct.c_int, ct.c_void_p, ct.c_void_p]),
+    'fb_step_host': (ct.c_int, [_H, ct.c_void_p, ct.c_void_p, ct.c_void_p, ct.c_int, ct.c_void_p,
+                                ct.c_void_p]),
     'fb_copy_to_host': (ct.c_int, [_H, ct.c_void_p, ct.c_void_p, ct.c_int64]),
     'fb_copy_to_device': (ct.c_int, [_H, ct.c_void_p, ct.c_void_p, ct.c_int64]),
     'fb_team_lanes': (ct.c_int, [_H]),
@@ -330,17 +331,18 @@ class BatchedPhysics:
         self._check(self.lib.fb_export_farms(self._handle, int(env), *ptrs))
         return data
 
-    def step_host(self, qpos, qvel, n_steps, links_row, joints_row):
+    def step_host(self, n_steps, ctrl=None, qpos=None, qvel=None, links_row=None, joints_row=None):
         """End-to-end call on HOST float32 buffers (pinned recommended): upload
-        qpos/qvel, step, download the last links/joints log row of every env."""
+        ctrl/qpos/qvel (each optional), step, download the last links/joints log
+        row of every environment."""
         def addr(arr):
             if arr is None:
                 return None
             if hasattr(arr, 'data_ptr'):
                 return arr.data_ptr()
             return arr.ctypes.data
-        self._check(self.lib.fb_step_host(self._handle, addr(qpos), addr(qvel), int(n_steps),
-                                          addr(links_row), addr(joints_row)))
+        self._check(self.lib.fb_step_host(self._handle, addr(ctrl), addr(qpos), addr(qvel),
+                                          int(n_steps), addr(links_row), addr(joints_row)))
         self.iteration += int(n_steps)
 
     # ---------------------------------------------------------- introspection

@@ -199,12 +199,16 @@ int fb_derived_view(FbHandle *h, FbDerivedView *out);
  * reference's data.sensors.<kind>.array (NULL pointers are skipped). */
 int fb_export_farms(FbHandle *h, int env, double *links, double *joints,
                     double *contacts, double *xfrc);
-/* Host-buffer convenience used by the end-to-end benchmark: upload qpos/qvel
- * for all envs, step, download the last log row of every env.
- *   qpos/qvel: [n_envs][nq|nv] float32 host (pinned recommended)
- *   links_row: [n_envs][n_links][20] float32 host */
-int fb_step_host(FbHandle *h, const float *qpos, const float *qvel, int n_steps,
-                 float *links_row, float *joints_row);
+/* End-to-end call on HOST buffers (pinned recommended), the batched analogue of
+ * one outer iteration of the reference loop (task.py:168-186: control written
+ * by host code, env.step, sensors read by host code):
+ *   ctrl / qpos / qvel: [n_envs][nu|nq|nv] float32 host, each may be NULL (keep
+ *       the device-resident value); uploaded before stepping
+ *   n_steps physics steps with the inputs held
+ *   links_row / joints_row: [n_envs][n_links][20] / [n_envs][n_joints][joint_cols]
+ *       float32 host, the last log row of every environment (NULL -> skipped) */
+int fb_step_host(FbHandle *h, const float *ctrl, const float *qpos, const float *qvel,
+                 int n_steps, float *links_row, float *joints_row);
 
 /* Raw copies between host memory and the engine's device buffers (pointers
  * taken from the views above); for hosts without torch (plain ctypes). */

@@ -1,0 +1,143 @@
+"""CUDA path vs the fp64 oracle, through the C ABI, on the same seeded inputs.
+
+Tolerances (fp32 device arithmetic vs fp64 oracle, scaled error = max|a-b| /
+max(1, max|b|)): single step 5e-4 on qpos/qvel and on every log column;
+20-step rollouts 5e-4 (swimming) / 5e-3 (ground contact, where the active set
+of the soft-contact solver amplifies rounding).  BASELINE.json's north_star
+asks 1e-5 relative for a single step; fp32 solves of the (ill-conditioned)
+mass matrix reach 2e-5 .. 6e-5 on these models -- measured values in DESIGN.md.
+"""
+
+import numpy as np
+import pytest
+
+from conftest import make_case, oracle_rollout, scaled_error
+
+pytestmark = pytest.mark.gpu
+
+MODELS = ['swimmer8', 'salamander_swim', 'salamander', 'centipede']
+
+
+def _run(cuda_library, name, n_envs, n_steps, team=0, seed=0, **kw):
+    from farms_mujoco_b200.engine import BatchedPhysics
+    spec, model, qpos0, qvel0, ctrl = make_case(name, n_envs, seed=seed, **kw)
+    physics = BatchedPhysics.from_spec(spec, n_envs, buffer_size=n_steps + 1, team_lanes=team,
+                                       library=cuda_library)
+    physics.reset(qpos0, qvel0)
+    physics.set_ctrl(ctrl)
+    physics.step(n_steps, want_derived=True)
+    return spec, model, qpos0, qvel0, ctrl, physics
+
+
+def _compare(spec, model, physics, qpos0, qvel0, ctrl, envs, n_steps, tol):
+    qpos, qvel, logs = physics.qpos, physics.qvel, physics.log_arrays()
+    assert not physics.flags.any(), physics.flags
+    worst = {}
+    for env in envs:
+        _, data, states = oracle_rollout(spec, model, physics.tables, n_steps + 1, qpos0[env],
+                                         qvel0[env], ctrl[env])
+        ref_q, ref_v = states[-1]
+        errs = {'qpos': scaled_error(qpos[env], ref_q), 'qvel': scaled_error(qvel[env], ref_v)}
+        for kind in ('links', 'joints', 'contacts', 'xfrc'):
+            errs[kind] = scaled_error(logs[kind][env], getattr(data.sensors, kind).array)
+        for key, val in errs.items():
+            worst[key] = max(worst.get(key, 0.0), val)
+    print(spec.name, n_steps, 'steps:', {k: f'{v:.2e}' for k, v in worst.items()})
+    for key, val in worst.items():
+        assert val < tol, (key, val, worst)
+
+
+@pytest.mark.parametrize('name', MODELS)
+def test_single_step(cuda_library, name):
+    n_envs = 40
+    spec, model, qpos0, qvel0, ctrl, physics = _run(cuda_library, name, n_envs, 1)
+    _compare(spec, model, physics, qpos0, qvel0, ctrl, [0, 1, 17, n_envs - 1], 1, 5e-4)
+
+
+@pytest.mark.parametrize('name,tol', [('swimmer8', 5e-4), ('salamander_swim', 5e-4),
+                                      ('salamander', 5e-3), ('centipede', 5e-3)])
+def test_twenty_steps(cuda_library, name, tol):
+    n_envs = 33
+    spec, model, qpos0, qvel0, ctrl, physics = _run(cuda_library, name, n_envs, 20)
+    _compare(spec, model, physics, qpos0, qvel0, ctrl, [0, 16, n_envs - 1], 20, tol)
+
+
+@pytest.mark.parametrize('team', [8, 16, 32])
+def test_team_sizes_agree(cuda_library, team):
+    """Every team width runs the same arithmetic up to reduction order."""
+    spec, model, qpos0, qvel0, ctrl, physics = _run(cuda_library, 'salamander', 24, 5, team=team)
+    assert physics.team_lanes == team
+    _compare(spec, model, physics, qpos0, qvel0, ctrl, [0, 23], 5, 2e-4)
+
+
+def test_launch_split_is_invariant(cuda_library):
+    """20 steps in one launch == 4 launches of 5 (state round-trips through HBM)."""
+    from farms_mujoco_b200.engine import BatchedPhysics
+    spec, model, qpos0, qvel0, ctrl = make_case('salamander_swim', 16)
+    outs = []
+    for chunks in ([20], [5, 5, 5, 5]):
+        physics = BatchedPhysics.from_spec(spec, 16, buffer_size=21, library=cuda_library)
+        physics.reset(qpos0, qvel0)
+        physics.set_ctrl(ctrl)
+        for n in chunks:
+            physics.step(n)
+        outs.append((physics.qpos, physics.qvel, physics.log_arrays()))
+    assert np.array_equal(outs[0][0], outs[1][0])
+    assert np.array_equal(outs[0][1], outs[1][1])
+    for kind in ('links', 'joints', 'contacts', 'xfrc'):
+        assert np.array_equal(outs[0][2][kind], outs[1][2][kind]), kind
+
+
+def test_derived_quantities(cuda_library):
+    """FbDerivedView == the oracle's mjData fields for the pre-step state."""
+    from oracle.oracle import OraclePhysics
+    spec, model, qpos0, qvel0, ctrl, physics = _run(cuda_library, 'salamander', 8, 1)
+    der = physics.derived()
+    for env in (0, 7):
+        orc = OraclePhysics(model)
+        orc.reset(keyframe_id=0)
+        orc.data.qpos[:] = qpos0[env]
+        orc.data.qvel[:] = qvel0[env]
+        orc.data.ctrl[:] = ctrl[env]
+        orc.forward()
+        assert scaled_error(der['xpos'][env], orc.data.xpos) < 1e-6
+        assert scaled_error(der['xquat'][env], orc.data.xquat) < 1e-6
+        assert scaled_error(der['xipos'][env], orc.data.xipos) < 1e-6
+        assert scaled_error(der['linvel'][env], orc.arrays['body_linvel'].reshape(-1, 3)) < 1e-5
+        assert scaled_error(der['angvel'][env], orc.arrays['body_angvel'].reshape(-1, 3)) < 1e-5
+        assert scaled_error(der['actuator_force'][env], orc.data.actuator_force) < 1e-5
+        assert scaled_error(der['qacc'][env], orc.data.qacc) < 1e-4
+        assert der['ncon'][env] == orc.ncon
+        n = orc.ncon
+        assert np.array_equal(der['con_cand'][env][:n], orc.arrays['con_cand'][:n])
+        assert scaled_error(der['con_pos'][env][:n], orc.arrays['con_pos'].reshape(-1, 3)[:n]) < 1e-6
+        ref_force = orc.arrays['con_force'].reshape(-1, 6)[:n, :3]
+        assert scaled_error(der['con_force'][env][:n], ref_force) < 1e-4
+
+
+def test_full_size_properties(cuda_library):
+    """BASELINE size (16,384 swimming salamanders): size-independent properties."""
+    from farms_mujoco_b200.engine import BatchedPhysics
+    from farms_mujoco_b200 import models, mjcf_subset
+    spec = models.MODELS['salamander_swim']()
+    model = mjcf_subset.parse_mjcf(spec.mjcf)
+    n = 16384
+    rng = np.random.default_rng(3)
+    qpos0 = np.tile(model.key_qpos, (n, 1))
+    qpos0[:, 7:] += rng.uniform(-0.1, 0.1, size=(1, model.nq - 7))   # same state in every env
+    physics = BatchedPhysics.from_spec(spec, n, buffer_size=4, library=cuda_library)
+    physics.reset(qpos0, None)
+    physics.step(3)
+    qpos, qvel = physics.qpos, physics.qvel
+    # identical inputs -> bit-identical outputs in every environment
+    assert np.array_equal(qpos, np.broadcast_to(qpos[0], qpos.shape))
+    assert np.array_equal(qvel, np.broadcast_to(qvel[0], qvel.shape))
+    # unit quaternions, finite state, no divergence flag
+    assert np.allclose(np.linalg.norm(qpos[:, 3:7], axis=1), 1.0, atol=1e-6)
+    assert np.isfinite(qpos).all() and np.isfinite(qvel).all()
+    assert not physics.flags.any()
+    links = physics.log_arrays(env=n - 1)['links']
+    assert np.array_equal(links, physics.log_arrays(env=0)['links'])
+    # log quaternions are xyzw unit quaternions; CoM and URDF orientation columns equal
+    assert np.allclose(np.linalg.norm(links[:, :, 3:7], axis=-1), 1.0, atol=1e-5)
+    assert np.array_equal(links[:, :, 3:7], links[:, :, 10:14])
