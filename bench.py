@@ -52,19 +52,7 @@ def parse_args():
 
 
 # ------------------------------------------------------------------ inputs
-def synthetic_inputs(model, env_ids, seed=1234):
-    """Per-env initial joint angles U(-0.1, 0.1) and controller phase U(0, 2 pi),
-    drawn in env-id order so any env subset is reproducible."""
-    import torch
-    n_total = int(max(env_ids)) + 1
-    gen = torch.Generator().manual_seed(seed)
-    nj = model.nq - 7
-    angles = (torch.rand((n_total, nj), generator=gen, dtype=torch.float64)*0.2 - 0.1).numpy()
-    phase = (torch.rand((n_total,), generator=gen, dtype=torch.float64)*2*np.pi).numpy()
-    qpos = np.tile(model.key_qpos, (len(env_ids), 1))
-    qpos[:, 7:] += angles[env_ids]
-    qvel = np.tile(model.key_qvel, (len(env_ids), 1))
-    return qpos, qvel, phase[env_ids]
+from farms_mujoco_b200.sharding import synthetic_inputs, gather_env_statistics  # noqa: E402
 
 
 def wave_controller(spec, model):
@@ -311,10 +299,7 @@ def run_b200(args, rank, world, local_rank):
 
     # ---- optional end-of-rollout gather of per-env statistics (NCCL)
     stats = torch.as_tensor(physics.qpos[:, :3].astype(np.float32), device='cuda')
-    if world > 1:
-        gathered = [torch.empty_like(stats) for _ in range(world)]
-        dist.all_gather(gathered, stats)
-        stats = torch.cat(gathered)
+    stats = gather_env_statistics(stats, world)
     flags = int(np.count_nonzero(physics.flags))
 
     if rank == 0:

@@ -420,10 +420,12 @@ def parse_mjcf(xml_text: str) -> Model:
                 world_geoms.append((geom, pos, quat))
             fused_into[body.name] = 'world'
             continue
-        if is_static(body) and body.parent is not world and body.parent.name in fused_into:
-            # referenced static body under a fused parent: re-root at the world
-            pos, quat = world_pose(body)
-            body.pos, body.quat, body.parent = pos, quat, world
+        # re-root bodies whose ancestors were fused onto the nearest kept ancestor
+        while body.parent is not world and body.parent.name in fused_into:
+            par = body.parent
+            body.pos = par.pos + quat2mat(par.quat) @ body.pos
+            body.quat = quat_mul(par.quat, body.quat)
+            body.parent = par.parent
         kept.append(body)
 
     index = {id(b): i for i, b in enumerate(kept)}

@@ -1,0 +1,123 @@
+"""Device code (fb_device.h) compiled for the host (TEAM = 1) vs the fp64 oracle.
+
+This checks the fp32 arithmetic, the indexing and the C-ABI marshalling of the
+CUDA path on the GPU-less box.  It is NOT the product path and proves nothing
+about parallel execution: the `-m gpu` tests do that on a B200.
+"""
+
+import numpy as np
+import pytest
+
+from conftest import make_case, oracle_rollout, scaled_error
+
+
+def _run(emu_library, name, n_envs, n_steps, **kw):
+    from farms_mujoco_b200.engine import BatchedPhysics
+    spec, model, qpos0, qvel0, ctrl = make_case(name, n_envs, **kw)
+    physics = BatchedPhysics.from_spec(spec, n_envs, buffer_size=n_steps + 1, library=emu_library)
+    physics.reset(qpos0, qvel0)
+    physics.set_ctrl(ctrl)
+    physics.step(n_steps, want_derived=True)
+    return spec, model, qpos0, qvel0, ctrl, physics
+
+
+@pytest.mark.parametrize('name,tol', [('swimmer8', 5e-4), ('salamander_swim', 5e-4),
+                                      ('salamander', 5e-3), ('centipede', 5e-3)])
+def test_rollout_matches_oracle(emu_library, name, tol):
+    n_steps = 12
+    spec, model, qpos0, qvel0, ctrl, physics = _run(emu_library, name, 3, n_steps)
+    logs = physics.log_arrays()
+    assert not physics.flags.any()
+    for env in range(3):
+        _, data, states = oracle_rollout(spec, model, physics.tables, n_steps + 1, qpos0[env],
+                                         qvel0[env], ctrl[env])
+        assert scaled_error(physics.qpos[env], states[-1][0]) < tol
+        assert scaled_error(physics.qvel[env], states[-1][1]) < tol
+        for kind in ('links', 'joints', 'contacts', 'xfrc'):
+            assert scaled_error(logs[kind][env], getattr(data.sensors, kind).array) < tol, kind
+
+
+def test_log_layout_is_reference_layout(emu_library):
+    """Row k: links/contacts of state k-1 (k=0: state 0), joints qpos/qvel of state k
+    (SURVEY.md Appendix D-1); quaternions xyzw; unwritten joint columns stay zero."""
+    from farms_mujoco_b200.layout import sc
+    spec, model, qpos0, qvel0, ctrl, physics = _run(emu_library, 'salamander_swim', 2, 3)
+    logs = physics.log_arrays(env=1)
+    links, joints = logs['links'], logs['joints']
+    assert links.shape == (4, 28, 20) and joints.shape == (4, 27, 18)
+    assert np.array_equal(links[0], links[1])                      # both show state 0
+    assert not np.array_equal(links[1], links[2])
+    assert np.allclose(joints[0, :, sc.joint_position], qpos0[1, 7:], atol=1e-7)
+    assert np.allclose(joints[3, :, sc.joint_position], physics.qpos[1, 7:], atol=0)
+    written = [sc.joint_position, sc.joint_velocity, sc.joint_torque, sc.joint_limit_force]
+    others = [c for c in range(sc.joint_size) if c not in written]
+    assert not joints[:, :, others].any()
+    assert np.allclose(np.linalg.norm(links[:, :, 3:7], axis=-1), 1, atol=1e-6)
+    assert np.array_equal(links[:, :, 3:7], links[:, :, 10:14])    # D-3
+    exported = physics.export_farms(1)
+    assert exported.sensors.links.array.dtype == np.float64
+    assert np.array_equal(exported.sensors.links.array, links.astype(np.float64))
+
+
+def test_units_scaling(emu_library):
+    """MJCF authored in scaled units, logs in SI (physics.py:428-523): a model
+    scaled by `meters` logs the same SI numbers."""
+    from farms_mujoco_b200.engine import BatchedPhysics
+    from farms_mujoco_b200 import models, mjcf_subset
+    from farms_mujoco_b200.units import SimulationUnitScaling
+    spec = models.swimmer8()
+    model = mjcf_subset.parse_mjcf(spec.mjcf)
+    base = BatchedPhysics.from_spec(spec, 1, buffer_size=2, library=emu_library)
+    units = SimulationUnitScaling(meters=1.0, seconds=1.0, kilograms=1.0)
+    spec.simulation_options.units = units
+    same = BatchedPhysics.from_spec(spec, 1, buffer_size=2, library=emu_library)
+    assert np.array_equal(base.log_arrays()['links'], same.log_arrays()['links'])
+    assert base.tables.meters == 1.0 and model.nv == 13
+
+
+def test_wave_controller_equals_host_controller(emu_library):
+    from farms_mujoco_b200.engine import BatchedPhysics
+    from farms_mujoco_b200.models import travelling_wave_parameters
+    spec, model, qpos0, qvel0, _ = make_case('swimmer8', 2)
+    joints, amp, freq, lag = travelling_wave_parameters(spec)
+    acts = [model.actuator_id(f'actuator_position_{j}') for j in joints]
+    phase = np.array([0.3, 1.7])
+    dev = BatchedPhysics.from_spec(spec, 2, buffer_size=6, library=emu_library)
+    dev.set_env_phase(phase)
+    dev.set_wave_controller(acts, amp, freq, lag)
+    dev.reset(qpos0, qvel0)
+    dev.step(5)
+    host = BatchedPhysics.from_spec(spec, 2, buffer_size=6, library=emu_library)
+    host.reset(qpos0, qvel0)
+    for it in range(5):
+        ctrl = np.zeros((2, model.nu))
+        ctrl[:, acts] = amp*np.sin(2*np.pi*freq*it*model.timestep - lag + phase[:, None])
+        host.set_ctrl(ctrl)
+        host.step(1)
+    assert np.allclose(dev.qpos, host.qpos, atol=2e-6)
+    assert np.allclose(dev.qvel, host.qvel, atol=2e-4)
+
+
+def test_swimming_switches(emu_library):
+    from farms_mujoco_b200.engine import BatchedPhysics
+    spec, model, qpos0, qvel0, ctrl = make_case('swimmer8', 1)
+    physics = BatchedPhysics.from_spec(spec, 1, buffer_size=3, library=emu_library)
+    physics.set_swimming(False, False)
+    physics.reset(qpos0, qvel0)
+    physics.step(2)
+    assert not physics.log_arrays()['xfrc'].any() and not physics.xfrc_applied.any()
+    physics.set_swimming(True, True)
+    physics.set_water_velocity([0.1, 0.0, 0.0])
+    physics.reset(qpos0, qvel0)
+    physics.step(2)
+    assert physics.log_arrays()['xfrc'].any() and physics.xfrc_applied.any()
+
+
+def test_errors_are_reported(emu_library):
+    from farms_mujoco_b200.engine import BatchedPhysics, EngineError
+    spec, model, qpos0, qvel0, ctrl = make_case('swimmer8', 1)
+    physics = BatchedPhysics.from_spec(spec, 1, library=emu_library)
+    with pytest.raises(EngineError, match='n_steps'):
+        physics.step(0)
+    with pytest.raises(EngineError, match='actuator'):
+        physics.set_wave_controller([999], [1.0], [1.0], [0.0])

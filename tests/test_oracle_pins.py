@@ -1,0 +1,191 @@
+"""Pins for the fp64 CPU oracle (PARITY UNPINNED against MuJoCo: the reference
+ships no golden vectors and MuJoCo is absent).  These are
+the substitute pins: analytic known answers and self-consistency identities."""
+
+import numpy as np
+import pytest
+
+from farms_mujoco_b200 import mjcf_subset as ms
+from farms_mujoco_b200 import models
+from oracle.oracle import OraclePhysics
+
+
+def _mjcf(body_xml, option='timestep="0.001" gravity="0 0 -9.81"', extra=''):
+    return f'''<mujoco model="t">
+  <compiler angle="radian" inertiafromgeom="false"/>
+  <option {option} integrator="Euler" cone="pyramidal"/>
+  <worldbody>
+    <geom name="floor" type="plane" size="5 5 0.1" friction="1 0 0" contype="1" conaffinity="1" condim="3"/>
+    {body_xml}
+  </worldbody>
+  {extra}
+</mujoco>'''
+
+
+def test_free_fall_discrete_recurrence():
+    """Semi-implicit Euler: v_n = -g n h, z_n = z0 - g h^2 n(n+1)/2 (exact)."""
+    xml = _mjcf('''<body name="ball" pos="0 0 5"><freejoint name="root"/>
+      <inertial pos="0 0 0" mass="2" diaginertia="0.1 0.1 0.1"/>
+      <geom name="g" type="sphere" size="0.1" contype="1" conaffinity="0" friction="1 0 0"/></body>''')
+    phys = OraclePhysics(ms.parse_mjcf(xml))
+    n, h, g = 200, 1e-3, 9.81
+    phys.step(n)
+    assert phys.data.qvel[2] == pytest.approx(-g*n*h, rel=1e-12)
+    assert phys.data.qpos[2] == pytest.approx(5 - g*h*h*n*(n + 1)/2, rel=1e-12)
+    assert np.allclose(phys.data.qpos[3:7], [1, 0, 0, 0])
+
+
+def test_hinge_pendulum_matches_closed_form_map():
+    """Point-mass pendulum (fixed base): qacc = -(g/l) sin(q); q' integrates the new velocity."""
+    xml = _mjcf('''<body name="base" pos="0 0 2"><body name="arm" pos="0 0 0">
+      <joint name="j" type="hinge" axis="0 1 0" pos="0 0 0" damping="0" limited="false"/>
+      <inertial pos="0 0 -0.5" mass="1" diaginertia="1e-9 1e-9 1e-9"/></body></body>''')
+    model = ms.parse_mjcf(xml)
+    phys = OraclePhysics(model)
+    phys.data.qpos[0] = 0.3
+    q, v, h = 0.3, 0.0, 1e-3
+    for _ in range(300):
+        phys.step()
+        acc = -(9.81*0.5)/(0.25 + 1e-9)*np.sin(q)
+        v += h*acc
+        q += h*v
+    assert phys.data.qpos[0] == pytest.approx(q, rel=1e-9)
+    assert phys.data.qvel[0] == pytest.approx(v, rel=1e-9)
+
+
+@pytest.mark.parametrize('name', ['swimmer8', 'salamander', 'centipede'])
+def test_crb_mass_matrix_equals_jacobian_definition(name):
+    """CRB (orc_crb) == sum_b m Jp'Jp + Jr' I Jr at a random configuration."""
+    spec = models.MODELS[name]()
+    model = ms.parse_mjcf(spec.mjcf)
+    phys = OraclePhysics(model)
+    rng = np.random.default_rng(1)
+    phys.data.qpos[7:] = rng.uniform(-0.5, 0.5, model.nq - 7)
+    quat = rng.normal(size=4)
+    phys.data.qpos[3:7] = quat/np.linalg.norm(quat)
+    phys.forward()
+    dense, _ = ms.dense_mass_matrix(model, phys.data.qpos.copy())
+    crb = phys.full_mass_matrix()
+    assert np.abs(crb - dense).max() < 1e-12*np.abs(dense).max()
+    # L'DL solve residual
+    rhs = rng.normal(size=model.nv)
+    assert np.allclose(crb @ phys.data.qacc, phys.arrays['qfrc_smooth'] + phys.arrays['qfrc_constraint'],
+                       rtol=1e-8, atol=1e-9*np.abs(phys.arrays['qfrc_smooth']).max()) or phys.nefc
+    x = np.linalg.solve(crb, rhs)
+    assert np.allclose(crb @ x, rhs)
+
+
+def test_momentum_drift_is_first_order_in_timestep():
+    """Free-floating chain, internal actuation only, no gravity: the continuous system
+    conserves linear momentum exactly, so the drift of semi-implicit Euler must shrink
+    linearly with the timestep (it does only if CRB, RNE bias and actuation agree)."""
+    drift = []
+    for dt, n in ((1e-3, 50), (1e-4, 500)):
+        spec = models.swimmer8()
+        xml = spec.mjcf.replace('gravity="0.0 0.0 -9.81"', 'gravity="0.0 0.0 0.0"')
+        xml = xml.replace('timestep="0.001"', f'timestep="{dt}"')
+        model = ms.parse_mjcf(xml)
+        assert model.timestep == dt and not model.gravity.any()
+        phys = OraclePhysics(model)
+        phys.data.ctrl[:] = np.random.default_rng(2).uniform(-0.5, 0.5, model.nu)
+        phys.step_raw(n)
+        phys.forward()
+        lin = phys.arrays['body_linvel'].reshape(-1, 3)
+        drift.append(np.linalg.norm((model.body_mass[:, None]*lin).sum(axis=0)))
+    assert drift[0]/drift[1] == pytest.approx(10.0, rel=0.02)
+    assert drift[1] < 2e-3
+
+
+def test_sphere_rests_on_plane_with_weight_balanced():
+    """Resting sphere: total contact normal force = m g, penetration > 0, friction <= mu N."""
+    xml = _mjcf('''<body name="ball" pos="0 0 0.1"><freejoint name="root"/>
+      <inertial pos="0 0 0" mass="1.5" diaginertia="0.01 0.01 0.01"/>
+      <geom name="g" type="sphere" size="0.1" contype="1" conaffinity="0" friction="1 0 0"/></body>''')
+    phys = OraclePhysics(ms.parse_mjcf(xml))
+    for _ in range(3000):
+        phys.step()
+    assert phys.ncon == 1
+    force = phys.contact_force(0)
+    assert force[0] == pytest.approx(1.5*9.81, rel=1e-6)
+    assert phys.data.contact[0].dist < 0
+    assert np.hypot(force[1], force[2]) <= 1.0*force[0] + 1e-9
+    assert abs(phys.data.qvel[2]) < 1e-8
+
+
+def test_solver_kkt_conditions():
+    """At the solver's answer: f >= 0, f = -D min(0, J a - aref), M a = qfrc_smooth + J' f."""
+    spec = models.salamander()
+    model = ms.parse_mjcf(spec.mjcf)
+    phys = OraclePhysics(model)
+    rng = np.random.default_rng(5)
+    phys.data.qpos[2] -= 0.004
+    phys.data.qvel[:] = rng.uniform(-0.5, 0.5, model.nv)
+    phys.forward()
+    assert phys.nefc > 0
+    efc = phys.efc()
+    resid = efc['J'] @ phys.data.qacc - efc['aref']
+    assert (efc['force'] >= 0).all()
+    assert np.allclose(efc['force'], -efc['D']*np.minimum(0, resid), rtol=1e-9, atol=1e-12)
+    lhs = phys.full_mass_matrix() @ phys.data.qacc
+    rhs = phys.arrays['qfrc_smooth'] + efc['J'].T @ efc['force']
+    assert np.abs(lhs - rhs).max() < 1e-8*max(1.0, np.abs(rhs).max())
+
+
+def test_joint_limit_force_pushes_back():
+    spec = models.swimmer8()
+    model = ms.parse_mjcf(spec.mjcf)
+    phys = OraclePhysics(model)
+    phys.data.qpos[7] = 1.05   # beyond the +1.0 rad limit
+    phys.data.ctrl[model.actuator_id('actuator_position_joint_0')] = 1.05   # no actuator pull-back
+    phys.forward()
+    assert phys.nefc == 1
+    assert phys.arrays['jnt_limit_force'][1] > 0
+    assert phys.arrays['qfrc_constraint'][6] < 0
+
+
+def test_terminal_velocity_under_quadratic_drag():
+    """Sinking link: v_t = sqrt(m g_eff / (|c| viscosity)) with buoyancy off (drag.pyx:83-88)."""
+    from farms_mujoco_b200.data import AnimatData
+    from farms_mujoco_b200.simulation.physics import FarmsTables
+    from oracle import farms_oracle as fo
+    spec = models.swimmer8()
+    spec.arena_options.water.buoyancy = False
+    spec.arena_options.water.height = 100.0
+    for link in spec.animat_options.morphology.links:
+        link.drag_coefficients = [[-4.0, -4.0, -4.0], [-1e-3, -1e-3, -1e-3]]
+    model = ms.parse_mjcf(spec.mjcf)
+    phys = OraclePhysics(model)
+    data = AnimatData.from_sensors_names(1e-3, 1, spec.links_names, spec.joints_names,
+                                         spec.contacts_names, spec.xfrc_names)
+    maps = fo.make_maps(model, data)
+    tables = FarmsTables(model, data.sensors, maps['sensors'], spec.animat_options,
+                         spec.arena_options, spec.simulation_options.units)
+    handler = fo.SwimmingHandlerOracle(data, tables)
+    units = spec.simulation_options.units
+    for _ in range(1200):   # ~0.7 m of sinking, well above the floor at z = -2
+        fo.physics2data(phys, 0, data, maps, units)
+        handler.step(0)
+        fo.apply_xfrc(phys, data, 0, maps['sensors'], units)
+        phys.step()
+    mass = model.body_mass[2]
+    assert abs(phys.data.qvel[2]) == pytest.approx(np.sqrt(mass*9.81/4.0), rel=2e-3)
+
+
+def test_buoyancy_matches_formula():
+    """drag.pyx:139-149: lift = 1000 m g / rho_link * clamp((surface - z)/height, 0, 1)."""
+    from oracle import farms_oracle as fo
+    from farms_mujoco_b200.layout import sc
+    links = np.zeros((1, 1, sc.link_size))
+    links[0, 0, 2] = -0.004                      # 4 mm under the surface
+    links[0, 0, [6, 13]] = 1.0                   # identity orientations (xyzw)
+    xfrc = np.zeros((1, 1, 6))
+    water = dict(surface=0.0, velocity=np.zeros(3), viscosity=1.0)
+    done = fo.drag_forces(0, links, 0, xfrc, 0, np.zeros((2, 3)), water, mass=0.2, height=0.01,
+                          density=800.0, gravity=-9.81, use_buoyancy=True)
+    assert done
+    assert xfrc[0, 0, 2] == pytest.approx(1000*0.2*9.81/800.0*0.4)
+    links[0, 0, 2] = 0.5                          # above the surface: row untouched
+    xfrc[:] = 7.0
+    assert not fo.drag_forces(0, links, 0, xfrc, 0, np.zeros((2, 3)), water, mass=0.2, height=0.01,
+                              density=800.0, gravity=-9.81, use_buoyancy=True)
+    assert (xfrc == 7.0).all()
