@@ -29,12 +29,14 @@
 #ifdef FB_HOST_EMU
 #include <cmath>
 #define FB_DEV static inline
+#define FB_UNROLL
 #define FB_MEM inline
 #define FB_LDG(p) (*(p))
 static inline float fb_rsqrt(float x) { return 1.0f/sqrtf(x); }
 static inline void fb_sincos(float x, float *s, float *c) { *s = sinf(x); *c = cosf(x); }
 #else
 #define FB_DEV __device__ __forceinline__
+#define FB_UNROLL _Pragma("unroll")
 #define FB_MEM __device__ __forceinline__
 #define FB_LDG(p) __ldg(p)
 __device__ __forceinline__ float fb_rsqrt(float x) { return 1.0f/sqrtf(x); }
@@ -124,6 +126,13 @@ FB_DEV Quat q_normalize(Quat q) {
   float s = fb_rsqrt(n2);
   Quat r = {q.w*s, q.x*s, q.y*s, q.z*s};
   return r;
+}
+/* v' = q v q* for a unit quaternion: v + w t + u x t with t = 2 u x v */
+FB_DEV void q_rot(Quat q, const float *v, float *o) {
+  float tx = 2.f*(q.y*v[2] - q.z*v[1]), ty = 2.f*(q.z*v[0] - q.x*v[2]), tz = 2.f*(q.x*v[1] - q.y*v[0]);
+  o[0] = v[0] + q.w*tx + (q.y*tz - q.z*ty);
+  o[1] = v[1] + q.w*ty + (q.z*tx - q.x*tz);
+  o[2] = v[2] + q.w*tz + (q.x*ty - q.y*tx);
 }
 FB_DEV void q_mat(Quat q, float *R) {
   float w = q.w, x = q.x, y = q.y, z = q.z;
@@ -218,6 +227,8 @@ FB_DEV void fb_row_params(float timestep, const float *solref_in, const float *s
 /* ===================================================================== */
 template <int TEAM> struct FbStep {
   typedef TeamOps<TEAM> T;
+  /* bodies per lane held in registers by the subtree-sum phase (nbody <= BPL*TEAM) */
+  static const int BPL = TEAM >= 8 ? 2 : 64;
   const DevModel &m;
   float *s;     /* shared floats of this environment */
   int *si;      /* shared ints of this environment */
@@ -248,64 +259,91 @@ template <int TEAM> struct FbStep {
   }
 
   /* ------------------------------------------------- A.1 kinematics */
+  /* Body frames by pointer jumping instead of a walk over tree depth: every body
+   * starts with its transform relative to the parent, then ceil(log2(depth)) rounds
+   * compose it with the transform of its 2^r-th ancestor (rigid transforms are
+   * associative; the world absorbs).  All lanes work in every round. */
   FB_MEM void kinematics() {
-    const int nb = m.nbody, nj = m.njnt;
-    float *qpos = s + m.L.qpos, *xpos = s + m.L.xpos, *xquat = s + m.L.xquat;
-    float *xanchor = s + m.L.xanchor, *xaxis = s + m.L.xaxis;
-    for (int lv = 0; lv < m.nlevel; lv++) {
-      int i0 = MI(lvl_start, lv), i1 = MI(lvl_start, lv + 1);
-      for (int idx = i0 + lane; idx < i1; idx += TEAM) {
-        int b = MI(lvl_body, idx), p = MI(body_parent, b), jid = MI(body_jnt, b);
-        float pos[3], R[9], t[3];
-        Quat q;
+    const int nb = m.nbody, nj = m.njnt, R = m.nround_anc;
+    float *qpos = s + m.L.qpos;
+    float *mainP = s + m.L.xpos, *mainQ = s + m.L.xquat;
+    float *altP = s + m.L.altB, *altQ = s + m.L.altB + 3*nb;
+    float *curP = (R & 1) ? altP : mainP, *curQ = (R & 1) ? altQ : mainQ;
+    float *nxtP = (R & 1) ? mainP : altP, *nxtQ = (R & 1) ? mainQ : altQ;
+    for (int b = lane; b < nb; b += TEAM) {
+      float lp[3] = {0.f, 0.f, 0.f};
+      Quat lq = {1.f, 0.f, 0.f, 0.f};
+      if (b > 0) {
+        int jid = MI(body_jnt, b);
         int jtype = jid >= 0 ? MI(jnt_type, jid) : -1;
         if (jtype == FB_JNT_FREE) {
           int qa = MI(jnt_qposadr, jid);
-          pos[0] = qpos[qa]; pos[1] = qpos[qa+1]; pos[2] = qpos[qa+2];
+          lp[0] = qpos[qa]; lp[1] = qpos[qa+1]; lp[2] = qpos[qa+2];
           Quat qq = {qpos[qa+3], qpos[qa+4], qpos[qa+5], qpos[qa+6]};
-          q = q_normalize(qq);
-          qpos[qa+3] = q.w; qpos[qa+4] = q.x; qpos[qa+5] = q.y; qpos[qa+6] = q.z;
-          xanchor[jid] = pos[0]; xanchor[nj + jid] = pos[1]; xanchor[2*nj + jid] = pos[2];
-          xaxis[jid] = 0.f; xaxis[nj + jid] = 0.f; xaxis[2*nj + jid] = 1.f;
+          lq = q_normalize(qq);
+          qpos[qa+3] = lq.w; qpos[qa+4] = lq.x; qpos[qa+5] = lq.y; qpos[qa+6] = lq.z;
         } else {
-          Quat pq = {xquat[p], xquat[nb + p], xquat[2*nb + p], xquat[3*nb + p]};
-          q_mat(pq, R);
-          m_rot(R, MF(body_pos, 3*b), MF(body_pos, 3*b+1), MF(body_pos, 3*b+2), t);
-          pos[0] = xpos[p] + t[0]; pos[1] = xpos[nb + p] + t[1]; pos[2] = xpos[2*nb + p] + t[2];
+          lp[0] = MF(body_pos, 3*b); lp[1] = MF(body_pos, 3*b+1); lp[2] = MF(body_pos, 3*b+2);
           Quat bq = {MF(body_quat, 4*b), MF(body_quat, 4*b+1), MF(body_quat, 4*b+2),
                      MF(body_quat, 4*b+3)};
-          q = q_mul(pq, bq);
+          lq = bq;
           if (jid >= 0) {
-            int qa = MI(jnt_qposadr, jid);
-            float jp[3] = {MF(jnt_pos, 3*jid), MF(jnt_pos, 3*jid+1), MF(jnt_pos, 3*jid+2)};
             float ja[3] = {MF(jnt_axis, 3*jid), MF(jnt_axis, 3*jid+1), MF(jnt_axis, 3*jid+2)};
-            float anchor[3], axis[3];
-            q_mat(q, R);
-            m_rot(R, jp[0], jp[1], jp[2], t);
-            anchor[0] = pos[0] + t[0]; anchor[1] = pos[1] + t[1]; anchor[2] = pos[2] + t[2];
-            m_rot(R, ja[0], ja[1], ja[2], axis);
-            xanchor[jid] = anchor[0]; xanchor[nj + jid] = anchor[1]; xanchor[2*nj + jid] = anchor[2];
-            xaxis[jid] = axis[0]; xaxis[nj + jid] = axis[1]; xaxis[2*nj + jid] = axis[2];
-            float dq = qpos[qa] - MF(jnt_qpos0, jid);
+            float dq = qpos[MI(jnt_qposadr, jid)] - MF(jnt_qpos0, jid);
             if (jtype == FB_JNT_HINGE) {
-              float sn, cs;
+              float jp[3] = {MF(jnt_pos, 3*jid), MF(jnt_pos, 3*jid+1), MF(jnt_pos, 3*jid+2)};
+              float sn, cs, t0[3], t1[3];
               fb_sincos(0.5f*dq, &sn, &cs);
               Quat ql = {cs, ja[0]*sn, ja[1]*sn, ja[2]*sn};
-              q = q_mul(q, ql);
-              q_mat(q, R);
-              m_rot(R, jp[0], jp[1], jp[2], t);
-              pos[0] = anchor[0] - t[0]; pos[1] = anchor[1] - t[1]; pos[2] = anchor[2] - t[2];
+              lq = q_mul(bq, ql);
+              q_rot(bq, jp, t0);        /* anchor offset before ... */
+              q_rot(lq, jp, t1);        /* ... and after the joint rotation */
+              lp[0] += t0[0] - t1[0]; lp[1] += t0[1] - t1[1]; lp[2] += t0[2] - t1[2];
             } else {
-              pos[0] += axis[0]*dq; pos[1] += axis[1]*dq; pos[2] += axis[2]*dq;
+              float t0[3];
+              q_rot(bq, ja, t0);
+              lp[0] += t0[0]*dq; lp[1] += t0[1]*dq; lp[2] += t0[2]*dq;
             }
           }
         }
-        q = q_normalize(q);
-        xpos[b] = pos[0]; xpos[nb + b] = pos[1]; xpos[2*nb + b] = pos[2];
-        xquat[b] = q.w; xquat[nb + b] = q.x; xquat[2*nb + b] = q.y; xquat[3*nb + b] = q.z;
+      }
+      curP[b] = lp[0]; curP[nb + b] = lp[1]; curP[2*nb + b] = lp[2];
+      curQ[b] = lq.w; curQ[nb + b] = lq.x; curQ[2*nb + b] = lq.y; curQ[3*nb + b] = lq.z;
+    }
+    sync();
+    for (int r = 0; r < R; r++) {
+      for (int b = lane; b < nb; b += TEAM) {
+        int a = MI(body_anc, r*nb + b);
+        Quat qa = {curQ[a], curQ[nb + a], curQ[2*nb + a], curQ[3*nb + a]};
+        Quat qb = {curQ[b], curQ[nb + b], curQ[2*nb + b], curQ[3*nb + b]};
+        float pb[3] = {curP[b], curP[nb + b], curP[2*nb + b]}, t[3];
+        q_rot(qa, pb, t);
+        Quat q = q_mul(qa, qb);
+        if (r == R - 1) q = q_normalize(q);
+        nxtP[b] = curP[a] + t[0]; nxtP[nb + b] = curP[nb + a] + t[1]; nxtP[2*nb + b] = curP[2*nb + a] + t[2];
+        nxtQ[b] = q.w; nxtQ[nb + b] = q.x; nxtQ[2*nb + b] = q.y; nxtQ[3*nb + b] = q.z;
       }
       sync();
+      float *tp = curP; curP = nxtP; nxtP = tp;
+      float *tq = curQ; curQ = nxtQ; nxtQ = tq;
     }
+    /* joint anchors and axes in the world frame */
+    float *xanchor = s + m.L.xanchor, *xaxis = s + m.L.xaxis;
+    for (int j = lane; j < nj; j += TEAM) {
+      int b = MI(jnt_body, j);
+      float anchor[3] = {mainP[b], mainP[nb + b], mainP[2*nb + b]}, axis[3] = {0.f, 0.f, 1.f};
+      if (MI(jnt_type, j) != FB_JNT_FREE) {
+        Quat q = {mainQ[b], mainQ[nb + b], mainQ[2*nb + b], mainQ[3*nb + b]};
+        float jp[3] = {MF(jnt_pos, 3*j), MF(jnt_pos, 3*j+1), MF(jnt_pos, 3*j+2)};
+        float ja[3] = {MF(jnt_axis, 3*j), MF(jnt_axis, 3*j+1), MF(jnt_axis, 3*j+2)}, t[3];
+        q_rot(q, jp, t);
+        anchor[0] += t[0]; anchor[1] += t[1]; anchor[2] += t[2];
+        q_rot(q, ja, axis);
+      }
+      xanchor[j] = anchor[0]; xanchor[nj + j] = anchor[1]; xanchor[2*nj + j] = anchor[2];
+      xaxis[j] = axis[0]; xaxis[nj + j] = axis[1]; xaxis[2*nj + j] = axis[2];
+    }
+    sync();
   }
 
   FB_MEM Quat body_quat(int b) const {
@@ -386,65 +424,92 @@ template <int TEAM> struct FbStep {
   }
 
   /* ---------------- A.4 comVel + the forward half of RNE (cacc) */
-  FB_MEM void com_vel_acc() {
-    const int nb = m.nbody, nv = m.nv;
-    float *cvel = s + m.L.cvel, *cacc = s + m.L.cacc;
-    const float *cdof = s + m.L.cdof, *qvel = s + m.L.qvel;
-    if (lane == 0) {
-      cacc[0] = 0.f; cacc[nb] = 0.f; cacc[2*nb] = 0.f;
-      cacc[3*nb] = -m.grav[0]; cacc[4*nb] = -m.grav[1]; cacc[5*nb] = -m.grav[2];
-    }
-    sync();
-    for (int lv = 0; lv < m.nlevel; lv++) {
-      int i0 = MI(lvl_start, lv), i1 = MI(lvl_start, lv + 1);
-      for (int idx = i0 + lane; idx < i1; idx += TEAM) {
-        int b = MI(lvl_body, idx), p = MI(body_parent, b), jid = MI(body_jnt, b);
-        float cv[6], ca[6];
-        for (int k = 0; k < 6; k++) { cv[k] = cvel[k*nb + p]; ca[k] = cacc[k*nb + p]; }
-        if (jid >= 0) {
-          int da = MI(jnt_dofadr, jid);
-          if (MI(jnt_type, jid) == FB_JNT_FREE) {
-            /* translations: cdof_dot = 0 */
-            for (int i = 0; i < 3; i++) {
-              float qv = qvel[da + i];
-              for (int k = 0; k < 6; k++) cv[k] += cdof[k*nv + da + i]*qv;
-            }
-            float dd[3][6];
-            for (int i = 3; i < 6; i++) {
-              float cd[6];
-              for (int k = 0; k < 6; k++) cd[k] = cdof[k*nv + da + i];
-              cross_motion(cv, cd, dd[i-3]);
-            }
-            for (int i = 3; i < 6; i++) {
-              float qv = qvel[da + i];
-              for (int k = 0; k < 6; k++) {
-                ca[k] += dd[i-3][k]*qv;
-                cv[k] += cdof[k*nv + da + i]*qv;
-              }
-            }
-          } else {
-            float cd[6], dd[6], qv = qvel[da];
-            for (int k = 0; k < 6; k++) cd[k] = cdof[k*nv + da];
-            cross_motion(cv, cd, dd);
-            for (int k = 0; k < 6; k++) { ca[k] += dd[k]*qv; cv[k] += cd[k]*qv; }
-          }
-        }
-        for (int k = 0; k < 6; k++) { cvel[k*nb + b] = cv[k]; cacc[k*nb + b] = ca[k]; }
+  /* cdof are all expressed about one point in world axes, so cvel[b] is the plain sum
+   * of cdof*qvel over b's ancestor dofs and cacc[b] - cacc[world] the sum of
+   * cdof_dot*qvel: two ancestor prefix sums by pointer jumping. */
+  FB_MEM void prefix_sum6(float *mainb, float *altb) {
+    const int nb = m.nbody, R = m.nround_anc;
+    float *cur = (R & 1) ? altb : mainb, *nxt = (R & 1) ? mainb : altb;
+    for (int r = 0; r < R; r++) {
+      for (int b = lane; b < nb; b += TEAM) {
+        int a = MI(body_anc, r*nb + b);
+        for (int k = 0; k < 6; k++) nxt[k*nb + b] = cur[k*nb + b] + cur[k*nb + a];
       }
       sync();
+      float *t = cur; cur = nxt; nxt = t;
     }
   }
 
-  /* --- per-body bias wrench minus applied wrench; crb init; backward sweep */
+  FB_MEM void com_vel_acc() {
+    const int nb = m.nbody, nv = m.nv, R = m.nround_anc;
+    const float *cdof = s + m.L.cdof, *qvel = s + m.L.qvel;
+    float *cvel = s + m.L.cvel, *cacc = s + m.L.cacc;
+    float *valt = s + m.L.cfrc, *aalt = s + m.L.crb;
+    float *v0 = (R & 1) ? valt : cvel;
+    for (int b = lane; b < nb; b += TEAM) {
+      float v[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+      if (b > 0) {
+        int da = MI(body_dofadr, b), dn = MI(body_dofnum, b);
+        for (int i = 0; i < dn; i++) {
+          float qv = qvel[da + i];
+          for (int k = 0; k < 6; k++) v[k] += cdof[k*nv + da + i]*qv;
+        }
+      }
+      for (int k = 0; k < 6; k++) v0[k*nb + b] = v[k];
+    }
+    sync();
+    prefix_sum6(cvel, valt);
+    float *a0 = (R & 1) ? aalt : cacc;
+    for (int b = lane; b < nb; b += TEAM) {
+      float acc[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+      int jid = b > 0 ? MI(body_jnt, b) : -1;
+      if (jid >= 0) {
+        int p = MI(body_parent, b), da = MI(jnt_dofadr, jid);
+        float cv[6];
+        for (int k = 0; k < 6; k++) cv[k] = cvel[k*nb + p];
+        if (MI(jnt_type, jid) == FB_JNT_FREE) {
+          for (int i = 0; i < 3; i++) {         /* translations: cdof_dot = 0 */
+            float qv = qvel[da + i];
+            for (int k = 0; k < 6; k++) cv[k] += cdof[k*nv + da + i]*qv;
+          }
+          for (int i = 3; i < 6; i++) {         /* all three use cv after the translations */
+            float cd[6], dd[6], qv = qvel[da + i];
+            for (int k = 0; k < 6; k++) cd[k] = cdof[k*nv + da + i];
+            cross_motion(cv, cd, dd);
+            for (int k = 0; k < 6; k++) acc[k] += dd[k]*qv;
+          }
+        } else {
+          float cd[6], dd[6], qv = qvel[da];
+          for (int k = 0; k < 6; k++) cd[k] = cdof[k*nv + da];
+          cross_motion(cv, cd, dd);
+          for (int k = 0; k < 6; k++) acc[k] = dd[k]*qv;
+        }
+      }
+      for (int k = 0; k < 6; k++) a0[k*nb + b] = acc[k];
+    }
+    sync();
+    prefix_sum6(cacc, aalt);   /* cacc[world] = [0; -gravity] is added by the consumer */
+  }
+
+  /* --- per-body bias wrench minus applied wrench; composite inertia and wrench of
+   * every subtree.  Bodies are in depth-first preorder, so a subtree is the id range
+   * [b, b + size): its sum is assembled from power-of-two windows W_r[i] = sum of
+   * 2^r consecutive bodies (doubling), following the bits of `size`.  No subtraction
+   * of large prefixes, every lane busy, fixed summation order. */
   FB_MEM void body_forces_and_crb() {
-    const int nb = m.nbody;
+    const int nb = m.nbody, R2 = m.nround_sub;
     const float *cin = s + m.L.cinert, *cvel = s + m.L.cvel, *cacc = s + m.L.cacc;
     const float *xipos = s + m.L.xipos, *xf = s + m.L.xfrc;
-    float *cfrc = s + m.L.cfrc, *crb = s + m.L.crb;
-    for (int b = lane; b < nb; b += TEAM) {
+    float *A = s + m.L.crb, *B = s + m.L.altB;   /* 16 components x nb: crb | cfrc */
+    float own[BPL][16];
+FB_UNROLL
+    for (int slot = 0; slot < BPL; slot++) {
+      int b = lane + slot*TEAM;
+      if (b >= nb) continue;
       float I[10], v[6], a[6], t0[6], t1[6], t2[6];
-      for (int k = 0; k < 10; k++) { I[k] = cin[k*nb + b]; crb[k*nb + b] = I[k]; }
+      for (int k = 0; k < 10; k++) I[k] = cin[k*nb + b];
       for (int k = 0; k < 6; k++) { v[k] = cvel[k*nb + b]; a[k] = cacc[k*nb + b]; }
+      a[3] -= m.grav[0]; a[4] -= m.grav[1]; a[5] -= m.grav[2];
       inert_vec(I, a, t0);
       inert_vec(I, v, t1);
       cross_force(v, t1, t2);
@@ -453,27 +518,56 @@ template <int TEAM> struct FbStep {
       float Tq[3] = {xf[3*nb + b], xf[4*nb + b], xf[5*nb + b]};
       float off[3] = {xipos[b] - comx, xipos[nb + b] - comy, xipos[2*nb + b] - comz}, cr[3];
       v_cross(off, F, cr);
-      if (b == 0) { for (int k = 0; k < 6; k++) cfrc[k*nb] = 0.f; continue; }
-      cfrc[0*nb + b] = t0[0] + t2[0] - (Tq[0] + cr[0]);
-      cfrc[1*nb + b] = t0[1] + t2[1] - (Tq[1] + cr[1]);
-      cfrc[2*nb + b] = t0[2] + t2[2] - (Tq[2] + cr[2]);
-      cfrc[3*nb + b] = t0[3] + t2[3] - F[0];
-      cfrc[4*nb + b] = t0[4] + t2[4] - F[1];
-      cfrc[5*nb + b] = t0[5] + t2[5] - F[2];
+      for (int k = 0; k < 10; k++) own[slot][k] = I[k];
+      for (int k = 0; k < 3; k++) {
+        own[slot][10 + k] = b > 0 ? t0[k] + t2[k] - (Tq[k] + cr[k]) : 0.f;
+        own[slot][13 + k] = b > 0 ? t0[3+k] + t2[3+k] - F[k] : 0.f;
+      }
+    }
+    sync();   /* cacc (aliases B) has been consumed by every lane */
+FB_UNROLL
+    for (int slot = 0; slot < BPL; slot++) {
+      int b = lane + slot*TEAM;
+      if (b >= nb) continue;
+      for (int k = 0; k < 16; k++) A[k*nb + b] = own[slot][k];
     }
     sync();
-    /* children -> parents, deepest level first; parents gather (deterministic) */
-    for (int lv = m.nlevel - 2; lv >= 0; lv--) {
-      int i0 = MI(lvl_start, lv), i1 = MI(lvl_start, lv + 1);
-      for (int idx = i0 + lane; idx < i1; idx += TEAM) {
-        int p = MI(lvl_body, idx);
-        for (int c = MI(body_firstchild, p); c >= 0; c = MI(body_nextsib, c)) {
-          for (int k = 0; k < 10; k++) crb[k*nb + p] += crb[k*nb + c];
-          for (int k = 0; k < 6; k++) cfrc[k*nb + p] += cfrc[k*nb + c];
+    float acc[BPL][16];
+    int pos[BPL], size[BPL];
+FB_UNROLL
+    for (int slot = 0; slot < BPL; slot++) {
+      int b = lane + slot*TEAM;
+      pos[slot] = b;
+      size[slot] = b < nb ? MI(body_size, b) : 0;
+      for (int k = 0; k < 16; k++) acc[slot][k] = 0.f;
+    }
+    float *cur = A, *nxt = B;
+    for (int r = 0; r < R2; r++) {
+      const int w = 1 << r;
+FB_UNROLL
+      for (int slot = 0; slot < BPL; slot++) {
+        int b = lane + slot*TEAM;
+        if (b >= nb) continue;
+        if ((size[slot] >> r) & 1) {
+          int p = pos[slot];
+          for (int k = 0; k < 16; k++) acc[slot][k] += cur[k*nb + p];
+          pos[slot] = p + w;
+        }
+        if (r + 1 < R2) {
+          if (b + w < nb) for (int k = 0; k < 16; k++) nxt[k*nb + b] = cur[k*nb + b] + cur[k*nb + b + w];
+          else for (int k = 0; k < 16; k++) nxt[k*nb + b] = cur[k*nb + b];
         }
       }
       sync();
+      float *t = cur; cur = nxt; nxt = t;
     }
+FB_UNROLL
+    for (int slot = 0; slot < BPL; slot++) {
+      int b = lane + slot*TEAM;
+      if (b >= nb) continue;
+      for (int k = 0; k < 16; k++) A[k*nb + b] = acc[slot][k];
+    }
+    sync();
   }
 
   /* ----------- A.3 mass matrix entries, bias, actuation, passive -> fsm */
@@ -525,9 +619,11 @@ template <int TEAM> struct FbStep {
     sync();
   }
 
-  /* ------------------------------ sparse L'DL (mj_factorI) and solve */
+  /* ------------- scheduled sparse L'DL (mj_factorI) and solve (mj_solveLD) */
+  /* qLD keeps the UNSCALED rows (U_ks = M_ks after elimination of k's descendants) and
+   * dinv the inverse pivots, L_ks = U_ks*dinv[k]; the stage/lane schedule comes from
+   * fb_build_model (deepest pivots first, one lane per destination word). */
   FB_MEM void factor(float hdamp) {
-    const int nv = m.nv;
     const float *qM = s + m.L.qM;
     float *qLD = s + m.L.qLD, *dinv = s + m.L.dinv;
     for (int e = lane; e < m.nM; e += TEAM) {
@@ -537,48 +633,53 @@ template <int TEAM> struct FbStep {
       qLD[e] = v;
     }
     sync();
-    for (int k = nv - 1; k >= 0; k--) {
-      int nk = MI(dof_nanc, k), adr = MI(dof_Madr, k);
-      if (nk > 1) {
-        float inv = 1.0f/qLD[adr];
-        /* lane owns ancestor row s: row(a_s)[t-s] -= L_ks * M_kt / M_kk */
-        for (int sdx = 1 + lane; sdx < nk; sdx += TEAM) {
-          int as = MI(ent_j, adr + sdx), ra = MI(dof_Madr, as);
-          float tmp = qLD[adr + sdx]*inv;
-          for (int t = sdx; t < nk; t++) qLD[ra + t - sdx] -= tmp*qLD[adr + t];
-        }
-        sync();
-        for (int sdx = 1 + lane; sdx < nk; sdx += TEAM) qLD[adr + sdx] *= inv;
-        sync();
+    const int NS = m.nstage;
+    for (int st = 0; st < NS; st++) {
+      int p0 = MI(st_pivstart, st), p1 = MI(st_pivstart, st + 1);
+      for (int i = p0 + lane; i < p1; i += TEAM) {
+        int k = MI(st_piv, i);
+        dinv[k] = 1.0f/qLD[MI(dof_Madr, k)];
       }
+      sync();
+      int o0 = MI(fop_start, st*TEAM + lane), o1 = MI(fop_start, st*TEAM + lane + 1);
+      for (int o = o0; o < o1; o++) {
+        unsigned w0 = (unsigned)MI(fop, 2*o), w1 = (unsigned)MI(fop, 2*o + 1);
+        qLD[w0 & 0xffffu] -= qLD[w0 >> 16]*dinv[w1 >> 16]*qLD[w1 & 0xffffu];
+      }
+      sync();
     }
-    for (int k = lane; k < nv; k += TEAM) dinv[k] = 1.0f/qLD[MI(dof_Madr, k)];
-    sync();
   }
 
   /* x <- inv(L'DL) x, x in shared memory */
   FB_MEM void solve_ld(float *x) {
-    const int nv = m.nv;
     const float *qLD = s + m.L.qLD, *dinv = s + m.L.dinv;
-    for (int k = nv - 1; k > 0; k--) {
-      int nk = MI(dof_nanc, k), adr = MI(dof_Madr, k);
-      if (nk > 1) {
-        float xk = x[k];
-        for (int sdx = 1 + lane; sdx < nk; sdx += TEAM) x[MI(ent_j, adr + sdx)] -= qLD[adr + sdx]*xk;
-        sync();
+    float *y = s + m.L.tmp1;
+    const int NS = m.nstage;
+    /* y = D^-1 L^-T x: leaves to root */
+    for (int st = 0; st < NS; st++) {
+      int p0 = MI(st_pivstart, st), p1 = MI(st_pivstart, st + 1);
+      for (int i = p0 + lane; i < p1; i += TEAM) {
+        int k = MI(st_piv, i);
+        y[k] = x[k]*dinv[k];
       }
+      sync();
+      int o0 = MI(sop_start, st*TEAM + lane), o1 = MI(sop_start, st*TEAM + lane + 1);
+      for (int o = o0; o < o1; o++) {
+        unsigned w0 = (unsigned)MI(sop, 2*o), w1 = (unsigned)MI(sop, 2*o + 1);
+        x[w0 & 0xffffu] -= qLD[w0 >> 16]*y[w1 >> 16];
+      }
+      sync();
     }
-    for (int k = lane; k < nv; k += TEAM) x[k] *= dinv[k];
-    sync();
-    for (int k = 1; k < nv; k++) {
-      int nk = MI(dof_nanc, k), adr = MI(dof_Madr, k);
-      if (nk > 1) {
-        float part = 0.f;
-        for (int sdx = 1 + lane; sdx < nk; sdx += TEAM) part += qLD[adr + sdx]*x[MI(ent_j, adr + sdx)];
-        part = T::sum(mask, part);
-        if (lane == 0) x[k] -= part;
-        sync();
+    /* x = L^-1 y: root to leaves, each dof gathers its (final) ancestors */
+    for (int st = NS - 1; st >= 0; st--) {
+      int p0 = MI(st_pivstart, st), p1 = MI(st_pivstart, st + 1);
+      for (int i = p0 + lane; i < p1; i += TEAM) {
+        int k = MI(st_piv, i), nk = MI(dof_nanc, k), adr = MI(dof_Madr, k);
+        float acc = 0.f;
+        for (int sdx = 1; sdx < nk; sdx++) acc += qLD[adr + sdx]*x[MI(ent_j, adr + sdx)];
+        x[k] = y[k] - dinv[k]*acc;
       }
+      sync();
     }
   }
 

@@ -182,7 +182,7 @@ static int upload_model(FbHandle *h) {
   DevLayout keepL = h->hm.m.L;
   bool had = h->I_dev != nullptr;
   if (!fb_build_model(&h->fm_shallow, h->has_farms ? &h->ff_shallow : nullptr,
-                      h->has_wc ? &wc : nullptr, h->hm))
+                      h->has_wc ? &wc : nullptr, h->team, h->hm))
     return fail("unsupported model: " + h->hm.error);
   if (had && memcmp(&keepL, &h->hm.m.L, sizeof(DevLayout)) != 0) return fail("layout changed on rebuild");
   if (h->I_dev) { dev_sync(h->stream); dev_free(h->I_dev); dev_free(h->F_dev); }
@@ -273,12 +273,16 @@ int fb_create(const FbModel *model, const FbFarms *farms, int n_envs, int device
     return fail("fb_create: team_lanes must be 0, 8, 16 or 32");
   }
   h->team = team_lanes;
+  if (h->team == 0) h->team = model->nbody > 20 ? 32 : (model->nbody > 10 ? 16 : 8);
+  if (model->nbody > 2*h->team) {
+    fb_destroy(h);
+    return fail("fb_create: nbody exceeds 2*team_lanes (the subtree sums keep two bodies per lane in registers)");
+  }
 #endif
   deep_copy_model(h, model, farms);
   if (upload_model(h)) { fb_destroy(h); return -1; }
   const DevModel &m = h->hm.m;
 #ifndef FB_HOST_EMU
-  if (h->team == 0) h->team = m.nbody > 20 ? 32 : (m.nbody > 10 ? 16 : 8);
   size_t per_env = (size_t)(m.L.n_float + m.L.n_int)*sizeof(float);
   int max_smem = 0;
   cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);

@@ -31,10 +31,11 @@
 struct DevOffsets {
   /* ints */
   int body_parent, body_jnt, body_dofadr, body_dofnum, body_firstchild, body_nextsib,
-      body_lastdof, body_ancmask, lvl_start, lvl_body;
+      body_lastdof, body_ancmask, lvl_start, lvl_body, body_anc, body_size;
   int jnt_type, jnt_body, jnt_qposadr, jnt_dofadr, jnt_limited, jnt_actstart, act_sorted;
   int dof_body, dof_jnt, dof_parent, dof_Madr, dof_nanc;
   int ent_i, ent_j;
+  int st_pivstart, st_piv, fop_start, fop, sop_start, sop;   /* elimination schedule */
   int cand_body, cand_iscapsule, cand_sensor;
   int act_jnt, act_ctrllimited, act_forcelimited;
   int link_body, fj_qposadr, fj_dofadr, fj_jntid, fj_actpos, fj_actvel, fj_acttrq, xfrc_body,
@@ -57,7 +58,7 @@ struct DevLayout {
   int qpos, qvel, ctrl, actf, xpos, xquat, xipos, xanchor, xaxis, cinert, cdof, cvel, xfrc,
       qM, qLD, dinv, fsm, qacc, fcon, grad, pvec, tmp1, tmp2, limf, scratch;
   /* aliases inside scratch */
-  int crb, cacc, cfrc, buf, Md, H;
+  int crb, cacc, cfrc, buf, altB, Md, H;
   int n_float;   /* floats per env */
   int con_cand;  /* int region: con_cand[maxcon] */
   int n_int;
@@ -65,6 +66,8 @@ struct DevLayout {
 
 struct DevModel {
   int nbody, njnt, nq, nv, nu, ncand, nM, nlevel, nmaskw;
+  int nstage, sched_team;
+  int nround_anc, nround_sub; /* pointer-jumping rounds (ancestors), doubling rounds (subtrees) */    /* stages of the scheduled sparse factor/solve; lanes it was built for */
   int n_links, n_joints, n_contacts, n_xfrc, n_swim, n_wc;
   int maxcon, maxefc, npack; /* npack = nv*(nv+1)/2 */
   int solver_iterations, any_damping, any_stiffness, any_limit;
@@ -117,7 +120,7 @@ inline void quat2mat(const double *q, double *m) {
 /* Flatten FbModel + FbFarms.  Returns false and sets out.error when the model
  * leaves the supported subset. */
 inline bool fb_build_model(const FbModel *fm, const FbFarms *ff, const FbWaveController *wc,
-                           FbHostModel &out) {
+                           int team, FbHostModel &out) {
   using namespace fbdetail;
   DevModel &m = out.m;
   std::memset(&m, 0, sizeof(m));
@@ -176,6 +179,34 @@ inline bool fb_build_model(const FbModel *fm, const FbFarms *ff, const FbWaveCon
   o.body_ancmask = put_i(I, ancmask);
   o.lvl_start = put_i(I, lvl_start);
   o.lvl_body = put_i(I, lvl_body);
+  /* pointer jumping: body_anc[r*nb + b] = 2^r-th ancestor of b (world absorbs) */
+  {
+    int R = 0;
+    while ((1 << R) < maxdepth) R++;
+    m.nround_anc = R;
+    std::vector<int32_t> anc((size_t)(R > 0 ? R : 1)*nb, 0);
+    for (int b = 0; b < nb; b++) anc[b] = b > 0 ? fm->body_parentid[b] : 0;
+    for (int r = 1; r < R; r++)
+      for (int b = 0; b < nb; b++) anc[(size_t)r*nb + b] = anc[(size_t)(r-1)*nb + anc[(size_t)(r-1)*nb + b]];
+    o.body_anc = put_i(I, anc);
+    /* subtree sizes; subtrees must be contiguous id ranges (depth-first preorder) */
+    std::vector<int32_t> size(nb, 1);
+    for (int b = nb - 1; b > 0; b--) size[fm->body_parentid[b]] += size[b];
+    int maxsize = 1;
+    for (int b = 1; b < nb; b++) {
+      for (int c = b + 1; c < b + size[b]; c++) {
+        int a = c;
+        while (a > b) a = fm->body_parentid[a];
+        if (a != b) { out.error = "bodies are not in depth-first preorder"; return false; }
+      }
+      if (size[b] > maxsize) maxsize = size[b];
+    }
+    int R2 = 0;
+    while ((1 << R2) < maxsize) R2++;
+    if ((1 << R2) == maxsize) R2++;     /* bit R2-1 must be able to hold maxsize */
+    m.nround_sub = R2;
+    o.body_size = put_i(I, size);
+  }
 
   /* joints + actuators grouped by joint */
   std::vector<int32_t> actstart(nj + 1, 0), act_sorted;
@@ -218,6 +249,81 @@ inline bool fb_build_model(const FbModel *fm, const FbFarms *ff, const FbWaveCon
   o.dof_nanc = put_i(I, nanc);
   o.ent_i = put_i(I, ent_i);
   o.ent_j = put_i(I, ent_j);
+
+  /* Scheduled sparse L'DL and back-substitution.  Pivots are grouped into stages by
+   * tree depth (deepest first): every pivot of a stage has all its descendants
+   * eliminated, pivots of one stage lie in different branches.  Within a stage the
+   * update operations are grouped by destination and each group is pinned to one lane,
+   * so concurrent lanes never write the same word and the summation order is fixed
+   * (bit-reproducible).  Factor op: qLD[dst] -= qLD[a]*qLD[b]*dinv[piv];
+   * solve op: x[dst] -= qLD[adr]*y[piv]. */
+  {
+    if (team < 1) team = 1;
+    int maxdd = 0;
+    for (int d = 0; d < nv; d++) if (nanc[d] > maxdd) maxdd = nanc[d];
+    const int NS = maxdd;
+    m.nstage = NS; m.sched_team = team;
+    std::vector<int32_t> pivstart(NS + 1, 0), piv;
+    std::vector<int32_t> fstart((size_t)NS*team + 1, 0), fops, sstart((size_t)NS*team + 1, 0), sops;
+    for (int st = 0; st < NS; st++) {
+      int depth = maxdd - st;
+      pivstart[st] = (int)piv.size();
+      struct Op { int dst, a, b, k; };
+      std::vector<Op> f, sv;
+      for (int k = 0; k < nv; k++) {
+        if (nanc[k] != depth) continue;
+        piv.push_back(k);
+        int adr = fm->dof_Madr[k], nk = nanc[k];
+        for (int s1 = 1; s1 < nk; s1++) {
+          int as = ent_j[adr + s1], ra = fm->dof_Madr[as];
+          for (int t = s1; t < nk; t++) f.push_back({ra + t - s1, adr + s1, adr + t, k});
+          sv.push_back({as, adr + s1, 0, k});
+        }
+      }
+      auto distribute = [&](std::vector<Op> &ops, std::vector<int32_t> &start,
+                            std::vector<int32_t> &words) {
+        /* group by dst, largest groups first, each to the currently lightest lane */
+        std::vector<std::vector<Op>> groups;
+        std::vector<int> where(65536, -1);
+        for (const Op &op : ops) {
+          if (where[op.dst] < 0) { where[op.dst] = (int)groups.size(); groups.emplace_back(); }
+          groups[where[op.dst]].push_back(op);
+        }
+        std::vector<int> order(groups.size());
+        for (size_t i = 0; i < order.size(); i++) order[i] = (int)i;
+        for (size_t i = 1; i < order.size(); i++)      /* stable insertion sort by size desc */
+          for (size_t j = i; j > 0 && groups[order[j]].size() > groups[order[j-1]].size(); j--)
+            std::swap(order[j], order[j-1]);
+        std::vector<std::vector<Op>> lanes(team);
+        for (int gi : order) {
+          int best = 0;
+          for (int l = 1; l < team; l++) if (lanes[l].size() < lanes[best].size()) best = l;
+          lanes[best].insert(lanes[best].end(), groups[gi].begin(), groups[gi].end());
+        }
+        for (int l = 0; l < team; l++) {
+          start[(size_t)st*team + l] = (int)words.size()/2;
+          for (const Op &op : lanes[l]) {
+            words.push_back(op.dst | (op.a << 16));
+            words.push_back(op.b | (op.k << 16));
+          }
+        }
+      };
+      distribute(f, fstart, fops);
+      distribute(sv, sstart, sops);
+    }
+    pivstart[NS] = (int)piv.size();
+    fstart[(size_t)NS*team] = (int)fops.size()/2;
+    sstart[(size_t)NS*team] = (int)sops.size()/2;
+    if (fm->nM >= 65536 || nv >= 65536) { out.error = "model too large for the 16-bit op encoding"; return false; }
+    o.st_pivstart = put_i(I, pivstart);
+    o.st_piv = put_i(I, piv);
+    o.fop_start = put_i(I, fstart);
+    while (I.size() % 2) I.push_back(0);
+    o.fop = put_i(I, fops);
+    o.sop_start = put_i(I, sstart);
+    while (I.size() % 2) I.push_back(0);
+    o.sop = put_i(I, sops);
+  }
 
   /* collision candidates: plane (static, world frame) vs sphere / capsule end */
   std::vector<int32_t> cbody(nc), ccaps(nc);
@@ -372,14 +478,23 @@ inline bool fb_build_model(const FbModel *fm, const FbFarms *ff, const FbWaveCon
   L.tmp1 = take(nv); L.tmp2 = take(nv);
   L.limf = take(nj);
   L.scratch = off;
-  int s = off;
-  auto stake = [&s](int n) { int r = s; s += (n + 3) & ~3; return r; };
-  L.crb = stake(10*nb); L.cacc = stake(6*nb); L.cfrc = stake(6*nb); L.buf = stake(6*nv);
-  int natural = s - off;
-  int need = nc > 0 || m.any_limit ? 2*((m.npack + 3) & ~3) : 0;
-  L.Md = L.scratch;
-  L.H = L.scratch + ((m.npack + 3) & ~3);
-  off += natural > need ? natural : need;
+  /* scratch: A = [crb(10nb) | cfrc(6nb)], B = 16nb floats (second buffer of the doubling
+   * sums; cacc, buf and the kinematics ping-pong buffer alias into it), see fb_device.h */
+  {
+    auto pad4 = [](int n) { return (n + 3) & ~3; };
+    int nbp = pad4(nb);
+    (void)nbp;
+    L.crb = L.scratch;
+    L.cfrc = L.scratch + 10*nb;
+    L.altB = L.scratch + pad4(16*nb);
+    L.cacc = L.altB;
+    L.buf = L.altB;
+    int natural = pad4(16*nb) + pad4(16*nb > 6*nv ? 16*nb : 6*nv);
+    int need = nc > 0 || m.any_limit ? 2*pad4(m.npack) : 0;
+    L.Md = L.scratch;
+    L.H = L.scratch + pad4(m.npack);
+    off += natural > need ? natural : need;
+  }
   L.n_float = off;
   L.con_cand = 0;
   L.n_int = (m.maxcon + 3) & ~3;

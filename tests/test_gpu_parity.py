@@ -62,12 +62,14 @@ def test_twenty_steps(cuda_library, name, tol):
     _compare(spec, model, physics, qpos0, qvel0, ctrl, [0, 16, n_envs - 1], 20, tol)
 
 
-@pytest.mark.parametrize('team', [8, 16, 32])
-def test_team_sizes_agree(cuda_library, team):
-    """Every team width runs the same arithmetic up to reduction order."""
-    spec, model, qpos0, qvel0, ctrl, physics = _run(cuda_library, 'salamander', 24, 5, team=team)
+@pytest.mark.parametrize('team,name', [(8, 'swimmer8'), (16, 'swimmer8'), (16, 'salamander'),
+                                       (32, 'salamander'), (32, 'centipede')])
+def test_team_sizes_agree(cuda_library, team, name):
+    """Every team width runs the same arithmetic up to reduction order (a team of T lanes
+    holds at most 2*T bodies)."""
+    spec, model, qpos0, qvel0, ctrl, physics = _run(cuda_library, name, 24, 5, team=team)
     assert physics.team_lanes == team
-    _compare(spec, model, physics, qpos0, qvel0, ctrl, [0, 23], 5, 2e-4)
+    _compare(spec, model, physics, qpos0, qvel0, ctrl, [0, 23], 5, 1e-3)
 
 
 def test_launch_split_is_invariant(cuda_library):
