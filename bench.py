@@ -48,6 +48,7 @@ def parse_args():
     ap.add_argument('--cpu-seconds', type=float, default=12.0)
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-e2e', action='store_true')
+    ap.add_argument('--no-fast', action='store_true', help='team kernel only (comparison runs)')
     return ap.parse_args()
 
 
@@ -213,8 +214,9 @@ def run_b200(args, rank, world, local_rank):
                                        team_lanes=args.team)
     physics.set_env_phase(phase)
     physics.set_wave_controller(*wave_controller(spec, model))
+    if args.no_fast:
+        physics.set_fast_path(False)
     physics.reset(qpos0, qvel0)
-    launches0 = physics.launch_count()
 
     stream_ptr = __import__('ctypes').c_void_p()
     physics._check(physics.lib.fb_device_ptr_stream(physics._handle, __import__('ctypes').byref(stream_ptr)))
@@ -244,6 +246,7 @@ def run_b200(args, rank, world, local_rank):
     for _ in range(args.warmup):
         physics.step(args.inner, sync=False)
     physics.synchronize()
+    launches0 = physics.launch_count()
     sampler = ClockSampler(local_rank)
     sampler.start()
     kernel_ms = []
@@ -257,7 +260,8 @@ def run_b200(args, rank, world, local_rank):
     clocks = sampler.summary()
     env_steps = n_local*world*args.inner*args.steps
     value = env_steps/(total_ms*1e-3)
-    launches = physics.launch_count() - launches0 - args.warmup
+    launches = physics.launch_count() - launches0
+    handed_over = physics.last_pending if physics.fast_path else n_local
 
     # ---- end-to-end arm on pinned host buffers
     e2e = None
@@ -327,8 +331,14 @@ def run_b200(args, rank, world, local_rank):
                 'workload': (f'{args.model}: {n_local} envs/GPU x {world} GPU, drag+buoyancy, full '
                              'links/joints/contacts/xfrc log, on-device travelling-wave control'),
                 'n_envs': n_local*world, 'physics_steps_per_step': args.inner, 'timestep': model.timestep,
-                'nv': model.nv, 'nbody': model.nbody, 'team_lanes': physics.team_lanes,
-                'smem_bytes_per_env': physics.smem_bytes_per_env,
+                'nv': model.nv, 'nbody': model.nbody,
+                'kernels': ('fb_fast_kernel (1 thread = 1 env, articulated-body recursion) then '
+                            'fb_step_kernel (lane team = 1 env, constraint solver) on the hand-overs'
+                            if physics.fast_path else 'fb_step_kernel only'),
+                'fast_envs_per_block': physics.fast_path,
+                'fast_smem_bytes_per_env': physics.fast_smem_bytes_per_env,
+                'handed_over_envs_last_launch': handed_over,
+                'team_lanes': physics.team_lanes, 'team_smem_bytes_per_env': physics.smem_bytes_per_env,
                 'l2_policy': (f'no flush: each step appends {n_local*args.inner*b_log/1e6:.0f} MB of new '
                               f'log rows to a {n_local*args.ring*b_log/1e9:.1f} GB ring (> 126 MB L2)'),
                 'diverged_envs': flags,
@@ -339,11 +349,14 @@ def run_b200(args, rank, world, local_rank):
             'roofline': {
                 'bound': 'hbm', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s',
                 'frac': achieved/peak, 'traffic': traffic,
-                'kernel': f'fb_step_kernel<{physics.team_lanes}>', 'kernel_ms': k_ms,
+                'kernel': (f'fb_fast_kernel<{physics.fast_path}>' if physics.fast_path
+                           else f'fb_step_kernel<{physics.team_lanes}>'),
+                'kernel_ms': k_ms,
                 'algorithmic_bytes_per_env_step': b_log,
                 'peak_source': 'MEASURED_PEAKS.json hbm_gbs (of measured)' if peaks else 'fallback 6650',
-                'note': ('log-write bytes only; the step kernel is FP32-issue/latency bound, see '
-                         'profiles/ for issue-slot utilisation'),
+                'note': ('log-write bytes only (the one HBM stream of the step); kernel_ms is the CUDA-event '
+                         'time of one fb_step launch pair on the engine stream; the step is FP32-issue/'
+                         'latency bound, see profiles/ for issue-slot utilisation'),
             },
         }
         if not args.no_cpu_baseline and world == 1:

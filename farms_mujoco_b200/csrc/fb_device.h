@@ -1308,6 +1308,12 @@ struct FbParams {
   float *J3, *efc, *prod3;
   float *log_links, *log_joints, *log_contacts, *log_xfrc;
   long long links_env_stride, joints_env_stride, contacts_env_stride, xfrc_env_stride;
+  /* hand-over from the environment-per-thread kernel (fb_fast.h): environments that met
+   * a limit or a contact, the step they stopped at, and how many there are.  The
+   * counter is double-buffered by launch parity; use_pending = 0 -> every environment
+   * from step 0. */
+  int *pending, *pending_count, *steps_done;
+  int use_pending, parity;
 };
 
 FB_DEV EnvPtrs fb_env_ptrs(const FbParams &P, int env) {
@@ -1336,7 +1342,7 @@ FB_DEV EnvPtrs fb_env_ptrs(const FbParams &P, int env) {
  * (it0+k+1) % ring = {derived of the pre-step state, qpos/qvel of the new
  * state}, then the drag wrench for the next step. */
 template <int TEAM>
-FB_DEV void fb_run_env(const FbParams &P, int env, float *s, int *si, int lane, int base,
+FB_DEV void fb_run_env(const FbParams &P, int env, int k0, float *s, int *si, int lane, int base,
                        unsigned mask) {
   const DevModel &m = P.m;
   FbStep<TEAM> st(m, s, si, fb_env_ptrs(P, env), lane, base, mask);
@@ -1344,7 +1350,7 @@ FB_DEV void fb_run_env(const FbParams &P, int env, float *s, int *si, int lane, 
   st.load_state();
   const size_t e = (size_t)env;
   const int n = P.mode == FB_MODE_RESET ? 1 : P.n_steps;
-  for (int k = 0; k < n; k++) {
+  for (int k = k0; k < n; k++) {
     long long row;
     if (P.mode == FB_MODE_RESET) {
       st.forward(1);

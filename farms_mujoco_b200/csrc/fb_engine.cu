@@ -19,7 +19,7 @@
 #include <string>
 #include <vector>
 
-#include "fb_device.h"
+#include "fb_fast.h"
 
 #ifndef FB_HOST_EMU
 #include <cuda_runtime.h>
@@ -63,13 +63,37 @@ fb_step_kernel(const __grid_constant__ FbParams P) {
   extern __shared__ __align__(16) float fb_smem[];
   const DevModel &m = P.m;
   const int tid = threadIdx.x, team = tid/TEAM, lane = tid % TEAM;
-  const int env = blockIdx.x*(blockDim.x/TEAM) + team;
-  if (env >= P.n_envs) return;
+  int env = blockIdx.x*(blockDim.x/TEAM) + team, k0 = 0;
+  if (P.use_pending) {
+    /* only the environments the per-thread kernel handed over, from the step they stopped at */
+    if (env >= P.pending_count[P.parity]) return;
+    env = P.pending[env];
+    k0 = P.steps_done[env];
+  } else if (env >= P.n_envs) {
+    return;
+  }
   const int base = (tid & 31)/TEAM*TEAM;
   const unsigned mask = TEAM == 32 ? 0xffffffffu : (((1u << (TEAM & 31)) - 1u) << base);
   float *s = fb_smem + (size_t)team*(m.L.n_float + m.L.n_int);
   int *si = reinterpret_cast<int *>(s + m.L.n_float);
-  fb_run_env<TEAM>(P, env, s, si, lane, base, mask);
+  fb_run_env<TEAM>(P, env, k0, s, si, lane, base, mask);
+}
+
+/* environment-per-thread kernel (fb_fast.h): no barriers, no shuffles; BLK threads =
+ * BLK environments whose working sets interleave in shared memory */
+template <int BLK>
+__global__ void __launch_bounds__(BLK)
+fb_fast_kernel(const __grid_constant__ FbParams P) {
+  extern __shared__ __align__(16) float fb_smem[];
+  const int env = blockIdx.x*BLK + threadIdx.x;
+  if (blockIdx.x == 0 && threadIdx.x == 0) P.pending_count[P.parity ^ 1] = 0;   /* for the next launch */
+  if (env >= P.n_envs) return;
+  FbFast<BLK> st(P, fb_smem + threadIdx.x, env);
+  const int done = st.run();
+  if (done < P.n_steps) {
+    P.steps_done[env] = done;
+    P.pending[atomicAdd(P.pending_count + P.parity, 1)] = env;
+  }
 }
 
 /* last written log row of every environment -> dense [n_envs][row] buffers */
@@ -90,6 +114,9 @@ struct FbHandle {
   FbParams P;
   int device, team, envs_per_block, threads;
   size_t smem_bytes;
+  int fast_enabled, fast_block;     /* environment-per-thread kernel: on/off, threads per block */
+  size_t fast_smem_bytes;
+  long long launch_parity;
   fbStream stream;
   std::vector<void *> allocs;
   int32_t *I_dev;
@@ -203,16 +230,41 @@ static int upload_model(FbHandle *h) {
 static int launch(FbHandle *h, int mode, int n_steps, int want_derived) {
   FbParams &P = h->P;
   P.mode = mode; P.n_steps = n_steps; P.want_derived = want_derived; P.it0 = h->it;
+  /* The per-thread kernel advances every environment while it is unconstrained; the
+   * team kernel finishes the ones it handed over.  Reset and derived-view requests go
+   * to the team kernel alone (it is the one that produces mjData-like quantities). */
+  const int use_fast = h->fast_enabled && P.m.X.ok && mode == FB_MODE_STEP && !want_derived;
+  P.use_pending = use_fast;
+  P.parity = (int)(h->launch_parity & 1);
+  if (use_fast) h->launch_parity++;
 #ifdef FB_HOST_EMU
   const DevModel &m = P.m;
+  if (use_fast) {
+    P.pending_count[P.parity ^ 1] = 0;
+    std::vector<float> fs((size_t)m.X.n_float + 8, 0.f);
+    for (int env = 0; env < P.n_envs; env++) {
+      FbFast<1> st(P, fs.data(), env);
+      int done = st.run();
+      if (done < n_steps) { P.steps_done[env] = done; P.pending[P.pending_count[P.parity]++] = env; }
+    }
+  }
   std::vector<float> s((size_t)m.L.n_float + 8, 0.f);
   std::vector<int> si((size_t)m.L.n_int + 8, 0);
-  for (int env = 0; env < P.n_envs; env++)
-    fb_run_env<1>(P, env, s.data(), si.data(), 0, 0, 1u);
+  const int count = use_fast ? P.pending_count[P.parity] : P.n_envs;
+  for (int i = 0; i < count; i++) {
+    int env = use_fast ? P.pending[i] : i;
+    fb_run_env<1>(P, env, use_fast ? P.steps_done[env] : 0, s.data(), si.data(), 0, 0, 1u);
+  }
   h->last_ms = 0.f;
 #else
   int blocks = (P.n_envs + h->envs_per_block - 1)/h->envs_per_block;
   cudaEventRecord(h->ev0, h->stream);
+  if (use_fast) {
+    int fblocks = (P.n_envs + h->fast_block - 1)/h->fast_block;
+    if (h->fast_block == 64) fb_fast_kernel<64><<<fblocks, 64, h->fast_smem_bytes, h->stream>>>(P);
+    else fb_fast_kernel<32><<<fblocks, 32, h->fast_smem_bytes, h->stream>>>(P);
+    h->launches++;
+  }
   switch (h->team) {
     case 8: fb_step_kernel<8><<<blocks, h->threads, h->smem_bytes, h->stream>>>(P); break;
     case 16: fb_step_kernel<16><<<blocks, h->threads, h->smem_bytes, h->stream>>>(P); break;
@@ -253,6 +305,8 @@ int fb_create(const FbModel *model, const FbFarms *farms, int n_envs, int device
   if (!h) return fail("out of host memory");
   h->device = device; h->I_dev = nullptr; h->F_dev = nullptr; h->launches = 0; h->it = 0;
   h->last_ms = 0.f; h->has_wc = false; h->gather_links = h->gather_joints = nullptr;
+  h->fast_enabled = 1; h->fast_block = 1; h->fast_smem_bytes = 0; h->launch_parity = 0;
+  if (const char *ev = getenv("FARMS_B200_FAST")) h->fast_enabled = atoi(ev) != 0;
   memset(&h->P, 0, sizeof(h->P));
 #ifdef FB_HOST_EMU
   h->stream = 0;
@@ -299,6 +353,21 @@ int fb_create(const FbModel *model, const FbFarms *farms, int n_envs, int device
     default: ce = cudaFuncSetAttribute(fb_step_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_bytes); break;
   }
   if (ce != cudaSuccess) { fb_destroy(h); return fail(std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(ce)); }
+  /* environment-per-thread kernel: 64 environments per block when their working sets fit
+   * the SM's shared memory, else 32; models beyond that run on the team kernel alone */
+  {
+    size_t per_thread = (size_t)m.X.n_float*sizeof(float);
+    if (m.X.ok && per_thread*64 <= (size_t)max_smem) h->fast_block = 64;
+    else if (m.X.ok && per_thread*32 <= (size_t)max_smem) h->fast_block = 32;
+    else h->fast_enabled = 0;
+    if (h->fast_enabled) {
+      h->fast_smem_bytes = per_thread*h->fast_block;
+      ce = h->fast_block == 64
+          ? cudaFuncSetAttribute(fb_fast_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->fast_smem_bytes)
+          : cudaFuncSetAttribute(fb_fast_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->fast_smem_bytes);
+      if (ce != cudaSuccess) { fb_destroy(h); return fail(std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(ce)); }
+    }
+  }
 #else
   h->envs_per_block = 1; h->threads = 1;
   h->smem_bytes = (size_t)(m.L.n_float + m.L.n_int)*sizeof(float);
@@ -315,6 +384,7 @@ int fb_create(const FbModel *model, const FbFarms *farms, int n_envs, int device
   bad |= alloc_arr(h, &P.ctrl, n*nu); bad |= alloc_arr(h, &P.xfrc_applied, n*6*nb);
   bad |= alloc_arr(h, &P.qpos_spring, n*m.nq); bad |= alloc_arr(h, &P.env_phase, n);
   bad |= alloc_arr(h, &P.flags, n); bad |= alloc_arr(h, &P.iteration, n);
+  bad |= alloc_arr(h, &P.pending, n); bad |= alloc_arr(h, &P.pending_count, 2); bad |= alloc_arr(h, &P.steps_done, n);
   bad |= alloc_arr(h, &P.d_xpos, n*3*nb); bad |= alloc_arr(h, &P.d_xquat, n*4*nb);
   bad |= alloc_arr(h, &P.d_xipos, n*3*nb); bad |= alloc_arr(h, &P.d_linvel, n*3*nb);
   bad |= alloc_arr(h, &P.d_angvel, n*3*nb); bad |= alloc_arr(h, &P.d_actf, n*nu);
@@ -543,6 +613,26 @@ int fb_step_host(FbHandle *h, const float *ctrl, const float *qpos, const float 
   }
 #endif
   if (dev_sync(h->stream)) return fail(std::string("fb_step_host: ") + dev_error());
+  return 0;
+}
+
+int fb_set_fast_path(FbHandle *h, int enable) {
+  if (!h) return fail("null handle");
+  h->fast_enabled = enable != 0;
+  return 0;
+}
+/* 0: team kernel only; otherwise the environments per block of the per-thread kernel */
+int fb_fast_path(FbHandle *h) {
+  if (!h) return 0;
+  return h->fast_enabled && h->hm.m.X.ok ? h->fast_block : 0;
+}
+int fb_fast_smem_bytes_per_env(FbHandle *h) { return h ? (int)(h->hm.m.X.n_float*sizeof(float)) : 0; }
+/* environments the team kernel had to finish in the last fb_step (synchronises) */
+int fb_last_pending(FbHandle *h, int *count) {
+  if (!h || !count) return fail("null argument");
+  int both[2] = {0, 0};
+  if (d2h(both, h->P.pending_count, sizeof(both), h->stream) || dev_sync(h->stream)) return fail(dev_error());
+  *count = h->P.use_pending ? both[h->P.parity] : h->P.n_envs;
   return 0;
 }
 

@@ -50,7 +50,24 @@ struct DevOffsets {
   int swim_mass, swim_height, swim_density, swim_coef;
   int wc_amp, wc_freq, wc_lag, wc_off;
   int key_qpos, key_qvel;
+  /* tables of the environment-per-thread path (fb_fast.h) */
+  int ft_flags, ft_slot, ft_pslot, ft_link, ft_fj, ft_swim, ft_chkstart, ft_actwc;   /* ints */
+  int ft_dpos, ft_inertia, ft_hloc, ft_chk;                                          /* floats */
 };
+
+/* environment-per-thread path: per-environment shared-memory layout, in floats;
+ * element i of an array lives at (off + i)*BLOCK + thread (fb_fast.h) */
+struct DevFastLayout {
+  int ok;          /* 1 when the model fits the path's subset */
+  int qpos, qvel, quat, org, vel, wrench, u, dinv, trq, slots;
+  int nslot, n_float, any_jpos;
+};
+
+/* ft_flags bits */
+#define FT_ADD_CARRY 1    /* child b+1 hands its articulated inertia over in registers */
+#define FT_HAS_SLOT 2     /* has children that are not b+1: they accumulate into slot ft_slot[b] */
+#define FT_TO_CARRY 4     /* parent is b-1 */
+#define FT_FIRST_WRITER 8 /* first child (descending order) to write the parent's slot */
 
 /* per-environment shared-memory layout (float offsets; component-major SoA:
  * element (k, i) of an array with N items lives at off + k*N + i) */
@@ -83,6 +100,7 @@ struct DevModel {
   const float *F;
   DevOffsets o;
   DevLayout L;
+  DevFastLayout X;
 };
 
 /* ---------------------------------------------------------------- builder */
@@ -443,6 +461,110 @@ inline bool fb_build_model(const FbModel *fm, const FbFarms *ff, const FbWaveCon
   o.wc_off = put_f(F, wc ? vd(wc->offset, wc->n) : std::vector<double>());
   o.key_qpos = put_f(F, vd(fm->key_qpos, fm->nq));
   o.key_qvel = put_f(F, vd(fm->key_qvel, nv));
+
+
+  /* ---- environment-per-thread path (fb_fast.h): articulated-body recursion tables */
+  {
+    DevFastLayout &X = m.X;
+    X.ok = 1;
+    std::vector<int32_t> flags(nb, 0), slot(nb, -1), pslot(nb, -1), blink(nb, -1), bfj(nb, -1),
+        bswim(nb, -1), chkstart(nb + 1, 0), actwc(nu > 0 ? nu : 1, -1);
+    std::vector<double> dpos(3*nb, 0.0), inertia(6*nb, 0.0), hloc(3*nb, 0.0), chk;
+    int nslot = 0;
+    X.any_jpos = 0;
+    for (int b = 1; b < nb; b++) {
+      int p = fm->body_parentid[b], dn = fm->body_dofnum[b], jid = fm->body_jntid[b];
+      int jt = jid >= 0 ? fm->jnt_type[jid] : -1;
+      if (!(dn == 0 || (dn == 1 && (jt == FB_JNT_HINGE || jt == FB_JNT_SLIDE)) ||
+            (dn == 6 && jt == FB_JNT_FREE && p == 0 && b == 1)))
+        X.ok = 0;
+      if (jt == FB_JNT_FREE)
+        for (int k = 0; k < 6; k++)
+          if (fm->dof_damping[fm->jnt_dofadr[jid] + k] != 0 || fm->dof_armature[fm->jnt_dofadr[jid] + k] != 0)
+            X.ok = 0;
+      double jp[3] = {0, 0, 0}, pjp[3] = {0, 0, 0};
+      if (jid >= 0 && jt != FB_JNT_FREE) for (int k = 0; k < 3; k++) jp[k] = fm->jnt_pos[3*jid + k];
+      int pj = fm->body_jntid[p];
+      if (p > 0 && pj >= 0 && fm->jnt_type[pj] != FB_JNT_FREE) for (int k = 0; k < 3; k++) pjp[k] = fm->jnt_pos[3*pj + k];
+      for (int k = 0; k < 3; k++) {
+        if (jp[k] != 0) X.any_jpos = 1;
+        dpos[3*b + k] = fm->body_pos[3*b + k] - pjp[k];
+        hloc[3*b + k] = fm->body_ipos[3*b + k] - jp[k];
+      }
+      /* body inertia about its com in body axes: Riq diag(I) Riq' as xx yy zz xy xz yz */
+      double R[9];
+      quat2mat(fm->body_iquat + 4*b, R);
+      const double *I3 = fm->body_inertia + 3*b;
+      auto el = [&](int i, int j) { return R[3*i]*R[3*j]*I3[0] + R[3*i+1]*R[3*j+1]*I3[1] + R[3*i+2]*R[3*j+2]*I3[2]; };
+      inertia[6*b] = el(0, 0); inertia[6*b+1] = el(1, 1); inertia[6*b+2] = el(2, 2);
+      inertia[6*b+3] = el(0, 1); inertia[6*b+4] = el(0, 2); inertia[6*b+5] = el(1, 2);
+      if (p == b - 1) { flags[b] |= FT_TO_CARRY; if (p > 0) flags[p] |= FT_ADD_CARRY; }
+      else if (p > 0 && slot[p] < 0) { slot[p] = nslot++; flags[p] |= FT_HAS_SLOT; }
+      if (p != b - 1 && p > 0) pslot[b] = slot[p];
+    }
+    /* descending order: the first child to reach a slot stores, the others accumulate */
+    {
+      std::vector<int> seen(nslot > 0 ? nslot : 1, 0);
+      for (int b = nb - 1; b > 0; b--)
+        if (pslot[b] >= 0 && !seen[pslot[b]]) { seen[pslot[b]] = 1; flags[b] |= FT_FIRST_WRITER; }
+    }
+    for (int l = 0; l < m.n_links; l++) {
+      int b = ff->link_body[l];
+      if (b < 1 || b >= nb || blink[b] >= 0) X.ok = 0; else blink[b] = l;
+    }
+    for (int j = 0; j < m.n_joints; j++) {
+      int jid = ff->joint_jntid[j];
+      /* the row reads qpos/qvel of its own joint and sits on that joint's body */
+      if (jid < 0 || jid >= nj || fm->jnt_type[jid] == FB_JNT_FREE || ff->joint_qposadr[j] != fm->jnt_qposadr[jid] ||
+          ff->joint_dofadr[j] != fm->jnt_dofadr[jid] || bfj[fm->jnt_bodyid[jid]] >= 0) { X.ok = 0; continue; }
+      bfj[fm->jnt_bodyid[jid]] = j;
+    }
+    for (int i = 0; i < m.n_swim; i++) {
+      int l = ff->swim_links_index[i], xi = ff->swim_xfrc_index[i];
+      if (l < 0 || l >= m.n_links || xi < 0 || xi >= m.n_xfrc) { X.ok = 0; continue; }
+      int b = ff->link_body[l];
+      if (ff->xfrc_body[xi] != b || b < 1 || b >= nb || bswim[b] >= 0) { X.ok = 0; continue; }
+      bswim[b] = i;
+    }
+    if (wc) for (int i = 0; i < wc->n; i++) {
+      int a = wc->actuator[i];
+      if (a < 0 || a >= nu || actwc[a] >= 0) X.ok = 0; else actwc[a] = i;
+    }
+    /* conservative plane checks per body: no candidate of the body can be active while
+     * n.xpos - pd >= reach, reach = max(|lpos| + radius + margin - gap) over its candidates */
+    for (int b = 0; b < nb; b++) {
+      chkstart[b] = (int)chk.size()/4;
+      for (int c = 0; c < nc; c++) {
+        if (cbody[c] != b) continue;
+        double r = std::sqrt(lpos[3*c]*lpos[3*c] + lpos[3*c+1]*lpos[3*c+1] + lpos[3*c+2]*lpos[3*c+2])
+                   + rad[c] + fm->cand_margin[c] - fm->cand_gap[c];
+        r *= 1.0 + 1e-5; r += 1e-6;
+        bool merged = false;
+        for (size_t t = (size_t)chkstart[b]; t < chk.size()/4; t++)
+          if (chk[4*t] == pn[3*c] && chk[4*t+1] == pn[3*c+1] && chk[4*t+2] == pn[3*c+2]) {
+            /* same plane normal: keep the larger offset */
+            if (pd[c] + r > chk[4*t+3]) chk[4*t+3] = pd[c] + r;
+            merged = true;
+            break;
+          }
+        if (!merged) { chk.push_back(pn[3*c]); chk.push_back(pn[3*c+1]); chk.push_back(pn[3*c+2]); chk.push_back(pd[c] + r); }
+      }
+    }
+    chkstart[nb] = (int)chk.size()/4;
+    o.ft_flags = put_i(I, flags); o.ft_slot = put_i(I, slot); o.ft_pslot = put_i(I, pslot);
+    o.ft_link = put_i(I, blink); o.ft_fj = put_i(I, bfj); o.ft_swim = put_i(I, bswim);
+    o.ft_chkstart = put_i(I, chkstart); o.ft_actwc = put_i(I, actwc);
+    o.ft_dpos = put_f(F, dpos); o.ft_inertia = put_f(F, inertia); o.ft_hloc = put_f(F, hloc);
+    o.ft_chk = put_f(F, chk);
+    int foff = 0;
+    auto ftake = [&foff](int n) { int r = foff; foff += n; return r; };
+    X.qpos = ftake(fm->nq); X.qvel = ftake(nv);
+    X.quat = ftake(4*nb); X.org = ftake(3*nb); X.vel = ftake(6*nb); X.wrench = ftake(6*nb);
+    X.u = ftake(nb); X.dinv = ftake(nb); X.trq = ftake(nb);
+    X.slots = ftake(27*nslot);
+    X.nslot = nslot;
+    X.n_float = foff;
+  }
 
   /* water + units */
   double meters = ff ? ff->meters : 1.0, seconds = ff ? ff->seconds : 1.0,

@@ -51,6 +51,10 @@ ABI_SYMBOLS = {
                                 ct.c_void_p]),
     'fb_copy_to_host': (ct.c_int, [_H, ct.c_void_p, ct.c_void_p, ct.c_int64]),
     'fb_copy_to_device': (ct.c_int, [_H, ct.c_void_p, ct.c_void_p, ct.c_int64]),
+    'fb_set_fast_path': (ct.c_int, [_H, ct.c_int]),
+    'fb_fast_path': (ct.c_int, [_H]),
+    'fb_fast_smem_bytes_per_env': (ct.c_int, [_H]),
+    'fb_last_pending': (ct.c_int, [_H, ct.POINTER(ct.c_int)]),
     'fb_team_lanes': (ct.c_int, [_H]),
     'fb_smem_bytes_per_env': (ct.c_int, [_H]),
     'fb_device_ptr_stream': (ct.c_int, [_H, ct.POINTER(ct.c_void_p)]),
@@ -349,6 +353,27 @@ class BatchedPhysics:
     @property
     def team_lanes(self):
         return int(self.lib.fb_team_lanes(self._handle))
+
+    def set_fast_path(self, enable):
+        """Kernel selection (include/farms_b200.h): ``False`` sends every environment
+        to the team kernel; the default runs the environment-per-thread kernel first."""
+        self._check(self.lib.fb_set_fast_path(self._handle, int(bool(enable))))
+
+    @property
+    def fast_path(self):
+        """0 = team kernel only, else environments per block of the per-thread kernel."""
+        return int(self.lib.fb_fast_path(self._handle))
+
+    @property
+    def fast_smem_bytes_per_env(self):
+        return int(self.lib.fb_fast_smem_bytes_per_env(self._handle))
+
+    @property
+    def last_pending(self):
+        """Environments the team kernel had to finish in the last ``step``."""
+        count = ct.c_int(0)
+        self._check(self.lib.fb_last_pending(self._handle, ct.byref(count)))
+        return int(count.value)
 
     @property
     def smem_bytes_per_env(self):

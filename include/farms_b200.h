@@ -215,6 +215,18 @@ int fb_step_host(FbHandle *h, const float *ctrl, const float *qpos, const float 
 int fb_copy_to_host(FbHandle *h, const void *dev_ptr, void *host_ptr, int64_t bytes);
 int fb_copy_to_device(FbHandle *h, void *dev_ptr, const void *host_ptr, int64_t bytes);
 
+/* Kernel selection.  By default fb_step first runs the environment-per-thread kernel
+ * (articulated-body recursion, csrc/fb_fast.h), which advances every environment while
+ * no joint limit or contact is active, and then the team kernel (csrc/fb_device.h) on
+ * the environments that were handed over.  enable = 0 sends everything to the team
+ * kernel (tests compare the two).  fb_fast_path: 0 = team kernel only (disabled or the
+ * model is outside the per-thread subset), else environments per block.
+ * fb_last_pending: environments the team kernel had to finish in the last fb_step. */
+int fb_set_fast_path(FbHandle *h, int enable);
+int fb_fast_path(FbHandle *h);
+int fb_fast_smem_bytes_per_env(FbHandle *h);
+int fb_last_pending(FbHandle *h, int *count);
+
 /* introspection */
 int fb_team_lanes(FbHandle *h);
 int fb_smem_bytes_per_env(FbHandle *h);

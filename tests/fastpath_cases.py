@@ -1,0 +1,87 @@
+"""Cases shared by the emulation (CPU) and GPU parity tests of the two-kernel step:
+environment-per-thread kernel first, team kernel on what it hands over."""
+
+import numpy as np
+
+from conftest import make_case, oracle_rollout, scaled_error
+
+
+def compare_with_oracle(spec, model, physics, qpos0, qvel0, ctrl, envs, n_steps, tol):
+    qpos, qvel, logs = physics.qpos, physics.qvel, physics.log_arrays()
+    assert not physics.flags.any(), physics.flags
+    worst = {}
+    for env in envs:
+        _, data, states = oracle_rollout(spec, model, physics.tables, n_steps + 1, qpos0[env],
+                                         qvel0[env], ctrl[env])
+        ref_q, ref_v = states[-1]
+        errs = {'qpos': scaled_error(qpos[env], ref_q), 'qvel': scaled_error(qvel[env], ref_v)}
+        for kind in ('links', 'joints', 'contacts', 'xfrc'):
+            errs[kind] = scaled_error(logs[kind][env], getattr(data.sensors, kind).array)
+        for key, val in errs.items():
+            worst[key] = max(worst.get(key, 0.0), val)
+    print(spec.name, n_steps, 'steps:', {k: f'{v:.2e}' for k, v in worst.items()})
+    for key, val in worst.items():
+        assert val < tol, (key, val, worst)
+    return worst
+
+
+def check_hand_over(library, name, n_envs, n_steps=16, tol=5e-4):
+    """Joints start just inside their upper limit and move into it: the per-thread kernel
+    takes the first steps, hands an environment over when its limit becomes active (a
+    different step in every environment, some never), and the team kernel finishes the
+    launch with the limit row in the solver.  The log must be the oracle's throughout."""
+    from farms_mujoco_b200.engine import BatchedPhysics
+    from farms_mujoco_b200.layout import sc
+    spec, model, qpos0, qvel0, ctrl = make_case(name, n_envs, qvel_scale=0.0, ctrl_scale=0.0)
+    rng = np.random.default_rng(5)
+    hi = np.asarray(model.jnt_range).reshape(-1, 2)[:, 1]
+    gain = np.asarray(model.actuator_gainprm).reshape(model.nu, -1)[:, 0]
+    bias = np.asarray(model.actuator_biasprm).reshape(model.nu, -1)
+    trn = np.asarray(model.actuator_trnid).reshape(model.nu, -1)[:, 0]
+    position_act = {int(trn[a]): a for a in range(model.nu) if gain[a] != 0 and bias[a, 1] == -gain[a]}
+    qpos0[:, 7:] = 0.0
+    qvel0[:] = 0.0
+    ctrl[:] = 0.0
+    joint = rng.integers(1, model.njnt, size=n_envs)            # joint 0 is the free joint
+    driven = rng.uniform(size=n_envs) < 0.7
+    driven[0], driven[-1] = True, False
+    rows = np.arange(n_envs)
+    qadr = np.asarray(model.jnt_qposadr)[joint]
+    # start a little inside the upper limit; the position actuator of a driven joint pulls
+    # it through the limit after a few steps (a different number in every environment)
+    qpos0[rows, qadr] = hi[joint] - rng.uniform(0.0, 0.004, size=n_envs)
+    for e in range(n_envs):
+        ctrl[e, position_act[int(joint[e])]] = hi[joint[e]] + (0.6 if driven[e] else -0.2)
+    physics = BatchedPhysics.from_spec(spec, n_envs, buffer_size=n_steps + 1, library=library)
+    assert physics.fast_path
+    physics.reset(qpos0, qvel0)
+    physics.set_ctrl(ctrl)
+    physics.step(n_steps)
+    pending = physics.last_pending
+    assert 0 < pending < n_envs, pending
+    envs = sorted({0, 1, n_envs//2, n_envs - 2, n_envs - 1})
+    compare_with_oracle(spec, model, physics, qpos0, qvel0, ctrl, envs, n_steps, tol)
+    limit_force = physics.log_arrays()['joints'][:, :, :, sc.joint_limit_force]
+    assert (np.abs(limit_force).max(axis=(1, 2)) > 0).sum() == pending
+    assert pending == int(driven.sum())
+
+
+def check_paths_agree(library, name, n_envs, n_steps=10, tol=1e-4):
+    """Per-thread kernel (ABA) vs team kernel (CRB + L'DL) on the same unconstrained rollout."""
+    from farms_mujoco_b200.engine import BatchedPhysics
+    spec, model, qpos0, qvel0, ctrl = make_case(name, n_envs)
+    outs = {}
+    for fast in (True, False):
+        physics = BatchedPhysics.from_spec(spec, n_envs, buffer_size=n_steps + 1, library=library)
+        physics.set_fast_path(fast)
+        assert bool(physics.fast_path) == fast
+        physics.reset(qpos0, qvel0)
+        physics.set_ctrl(ctrl)
+        physics.step(n_steps)
+        assert physics.last_pending == (0 if fast else n_envs)
+        outs[fast] = (physics.qpos, physics.qvel, physics.log_arrays(), physics.xfrc_applied)
+    assert scaled_error(outs[True][0], outs[False][0]) < tol
+    assert scaled_error(outs[True][1], outs[False][1]) < tol
+    assert scaled_error(outs[True][3], outs[False][3]) < tol
+    for kind in ('links', 'joints', 'contacts', 'xfrc'):
+        assert scaled_error(outs[True][2][kind], outs[False][2][kind]) < tol, kind

@@ -37,6 +37,33 @@ def test_rollout_matches_oracle(emu_library, name, tol):
             assert scaled_error(logs[kind][env], getattr(data.sensors, kind).array) < tol, kind
 
 
+@pytest.mark.parametrize('name,tol', [('swimmer8', 2e-5), ('salamander_swim', 2e-5),
+                                      ('salamander', 5e-3)])
+def test_fast_path_rollout_matches_oracle(emu_library, name, tol):
+    """Default fb_step: environment-per-thread kernel (+ team kernel on the hand-overs)."""
+    import fastpath_cases
+    from farms_mujoco_b200.engine import BatchedPhysics
+    n_steps = 12
+    spec, model, qpos0, qvel0, ctrl = make_case(name, 3)
+    physics = BatchedPhysics.from_spec(spec, 3, buffer_size=n_steps + 1, library=emu_library)
+    assert physics.fast_path
+    physics.reset(qpos0, qvel0)
+    physics.set_ctrl(ctrl)
+    physics.step(n_steps)
+    assert physics.last_pending == (3 if name == 'salamander' else 0)
+    fastpath_cases.compare_with_oracle(spec, model, physics, qpos0, qvel0, ctrl, range(3), n_steps, tol)
+
+
+def test_fast_path_hand_over(emu_library):
+    import fastpath_cases
+    fastpath_cases.check_hand_over(emu_library, 'swimmer8', n_envs=9)
+
+
+def test_fast_and_team_paths_agree(emu_library):
+    import fastpath_cases
+    fastpath_cases.check_paths_agree(emu_library, 'salamander_swim', n_envs=2)
+
+
 def test_log_layout_is_reference_layout(emu_library):
     """Row k: links/contacts of state k-1 (k=0: state 0), joints qpos/qvel of state k
     (SURVEY.md Appendix D-1); quaternions xyzw; unwritten joint columns stay zero."""

@@ -1,11 +1,14 @@
 """CUDA path vs the fp64 oracle, through the C ABI, on the same seeded inputs.
 
-Tolerances (fp32 device arithmetic vs fp64 oracle, scaled error = max|a-b| /
-max(1, max|b|)): single step 5e-4 on qpos/qvel and on every log column;
-20-step rollouts 5e-4 (swimming) / 5e-3 (ground contact, where the active set
-of the soft-contact solver amplifies rounding).  BASELINE.json's north_star
-asks 1e-5 relative for a single step; fp32 solves of the (ill-conditioned)
-mass matrix reach 2e-5 .. 6e-5 on these models -- measured values in DESIGN.md.
+Two kernels are checked (include/farms_b200.h, fb_set_fast_path):
+  * 'fast': the default fb_step -- the environment-per-thread kernel (articulated-body
+    recursion) plus the team kernel on whatever it hands over.  Unconstrained (swimming)
+    steps: single step 1e-5 (BASELINE.json north_star), 20 steps 5e-5.
+  * 'team': the team kernel alone (CRB + L'DL + constraint solver, as MuJoCo does it).
+    fp32 solves of the ill-conditioned mass matrix reach 2e-5 .. 6e-5; tolerance 5e-4 for
+    a single step and for 20 swimming steps, 5e-3 for 20 steps of ground contact (the
+    active set of the soft-contact solver amplifies rounding).
+Scaled error = max|a-b| / max(1, max|b|).  Measured values in DESIGN.md.
 """
 
 import numpy as np
@@ -18,14 +21,25 @@ pytestmark = pytest.mark.gpu
 MODELS = ['swimmer8', 'salamander_swim', 'salamander', 'centipede']
 
 
-def _run(cuda_library, name, n_envs, n_steps, team=0, seed=0, **kw):
+SWIMMING = ('swimmer8', 'salamander_swim')
+
+
+def _run(cuda_library, name, n_envs, n_steps, team=0, seed=0, path='team', **kw):
     from farms_mujoco_b200.engine import BatchedPhysics
     spec, model, qpos0, qvel0, ctrl = make_case(name, n_envs, seed=seed, **kw)
     physics = BatchedPhysics.from_spec(spec, n_envs, buffer_size=n_steps + 1, team_lanes=team,
                                        library=cuda_library)
+    physics.set_fast_path(path == 'fast')
     physics.reset(qpos0, qvel0)
     physics.set_ctrl(ctrl)
-    physics.step(n_steps, want_derived=True)
+    if path == 'fast':
+        assert physics.fast_path in (32, 64)
+        physics.step(n_steps)
+        # swimming models stay unconstrained here; ground models are handed over at step 0
+        assert physics.last_pending == (0 if name in SWIMMING else n_envs)
+    else:
+        assert physics.fast_path == 0
+        physics.step(n_steps, want_derived=True)
     return spec, model, qpos0, qvel0, ctrl, physics
 
 
@@ -47,19 +61,35 @@ def _compare(spec, model, physics, qpos0, qvel0, ctrl, envs, n_steps, tol):
         assert val < tol, (key, val, worst)
 
 
+@pytest.mark.parametrize('path', ['fast', 'team'])
 @pytest.mark.parametrize('name', MODELS)
-def test_single_step(cuda_library, name):
-    n_envs = 40
-    spec, model, qpos0, qvel0, ctrl, physics = _run(cuda_library, name, n_envs, 1)
-    _compare(spec, model, physics, qpos0, qvel0, ctrl, [0, 1, 17, n_envs - 1], 1, 5e-4)
+def test_single_step(cuda_library, name, path):
+    n_envs = 70
+    spec, model, qpos0, qvel0, ctrl, physics = _run(cuda_library, name, n_envs, 1, path=path)
+    tol = 1e-5 if path == 'fast' and name in SWIMMING else 5e-4
+    _compare(spec, model, physics, qpos0, qvel0, ctrl, [0, 1, 17, 65, n_envs - 1], 1, tol)
 
 
+@pytest.mark.parametrize('path', ['fast', 'team'])
 @pytest.mark.parametrize('name,tol', [('swimmer8', 5e-4), ('salamander_swim', 5e-4),
                                       ('salamander', 5e-3), ('centipede', 5e-3)])
-def test_twenty_steps(cuda_library, name, tol):
+def test_twenty_steps(cuda_library, name, tol, path):
     n_envs = 33
-    spec, model, qpos0, qvel0, ctrl, physics = _run(cuda_library, name, n_envs, 20)
+    spec, model, qpos0, qvel0, ctrl, physics = _run(cuda_library, name, n_envs, 20, path=path)
+    if path == 'fast' and name in SWIMMING:
+        tol = 5e-5
     _compare(spec, model, physics, qpos0, qvel0, ctrl, [0, 16, n_envs - 1], 20, tol)
+
+
+@pytest.mark.parametrize('name', ['swimmer8', 'salamander_swim'])
+def test_hand_over_mid_launch(cuda_library, name):
+    import fastpath_cases
+    fastpath_cases.check_hand_over(cuda_library, name, n_envs=70)
+
+
+def test_paths_agree(cuda_library):
+    import fastpath_cases
+    fastpath_cases.check_paths_agree(cuda_library, 'salamander_swim', n_envs=96)
 
 
 @pytest.mark.parametrize('team,name', [(8, 'swimmer8'), (16, 'swimmer8'), (16, 'salamander'),
