@@ -81,14 +81,20 @@ fb_step_kernel(const __grid_constant__ FbParams P) {
 
 /* environment-per-thread kernel (fb_fast.h): no barriers, no shuffles; BLK threads =
  * BLK environments whose working sets interleave in shared memory */
+struct FbFastParams {
+  FbParams P;
+  FastRec rec[FB_FAST_MAXBODY];   /* per-body records, read from the constant bank */
+};
+
 template <int BLK>
 __global__ void __launch_bounds__(BLK)
-fb_fast_kernel(const __grid_constant__ FbParams P) {
+fb_fast_kernel(const __grid_constant__ FbFastParams Q) {
   extern __shared__ __align__(16) float fb_smem[];
+  const FbParams &P = Q.P;
   const int env = blockIdx.x*BLK + threadIdx.x;
   if (blockIdx.x == 0 && threadIdx.x == 0) P.pending_count[P.parity ^ 1] = 0;   /* for the next launch */
   if (env >= P.n_envs) return;
-  FbFast<BLK> st(P, fb_smem + threadIdx.x, env);
+  FbFast<BLK> st(P, Q.rec, fb_smem + threadIdx.x, env);
   const int done = st.run();
   if (done < P.n_steps) {
     P.steps_done[env] = done;
@@ -117,6 +123,9 @@ struct FbHandle {
   int fast_enabled, fast_block;     /* environment-per-thread kernel: on/off, threads per block */
   size_t fast_smem_bytes;
   long long launch_parity;
+#ifndef FB_HOST_EMU
+  FbFastParams *fastQ;               /* host staging of the per-thread kernel's parameters */
+#endif
   fbStream stream;
   std::vector<void *> allocs;
   int32_t *I_dev;
@@ -224,6 +233,13 @@ static int upload_model(FbHandle *h) {
   h->P.m = h->hm.m;
   h->P.m.I = h->I_dev;
   h->P.m.F = h->F_dev;
+#ifndef FB_HOST_EMU
+  if (h->hm.m.X.ok) {
+    if (!h->fastQ) h->fastQ = new FbFastParams();
+    memset(h->fastQ->rec, 0, sizeof(h->fastQ->rec));
+    memcpy(h->fastQ->rec, h->hm.rec.data(), sizeof(FastRec)*h->hm.rec.size());
+  }
+#endif
   return 0;
 }
 
@@ -243,7 +259,7 @@ static int launch(FbHandle *h, int mode, int n_steps, int want_derived) {
     P.pending_count[P.parity ^ 1] = 0;
     std::vector<float> fs((size_t)m.X.n_float + 8, 0.f);
     for (int env = 0; env < P.n_envs; env++) {
-      FbFast<1> st(P, fs.data(), env);
+      FbFast<1> st(P, h->hm.rec.data(), fs.data(), env);
       int done = st.run();
       if (done < n_steps) { P.steps_done[env] = done; P.pending[P.pending_count[P.parity]++] = env; }
     }
@@ -261,8 +277,9 @@ static int launch(FbHandle *h, int mode, int n_steps, int want_derived) {
   cudaEventRecord(h->ev0, h->stream);
   if (use_fast) {
     int fblocks = (P.n_envs + h->fast_block - 1)/h->fast_block;
-    if (h->fast_block == 64) fb_fast_kernel<64><<<fblocks, 64, h->fast_smem_bytes, h->stream>>>(P);
-    else fb_fast_kernel<32><<<fblocks, 32, h->fast_smem_bytes, h->stream>>>(P);
+    h->fastQ->P = P;
+    if (h->fast_block == 64) fb_fast_kernel<64><<<fblocks, 64, h->fast_smem_bytes, h->stream>>>(*h->fastQ);
+    else fb_fast_kernel<32><<<fblocks, 32, h->fast_smem_bytes, h->stream>>>(*h->fastQ);
     h->launches++;
   }
   switch (h->team) {
@@ -293,6 +310,7 @@ void fb_destroy(FbHandle *h) {
 #ifndef FB_HOST_EMU
   cudaEventDestroy(h->ev0); cudaEventDestroy(h->ev1);
   cudaStreamDestroy(h->stream);
+  delete h->fastQ;
 #endif
   delete h;
 }
@@ -306,6 +324,9 @@ int fb_create(const FbModel *model, const FbFarms *farms, int n_envs, int device
   h->device = device; h->I_dev = nullptr; h->F_dev = nullptr; h->launches = 0; h->it = 0;
   h->last_ms = 0.f; h->has_wc = false; h->gather_links = h->gather_joints = nullptr;
   h->fast_enabled = 1; h->fast_block = 1; h->fast_smem_bytes = 0; h->launch_parity = 0;
+#ifndef FB_HOST_EMU
+  h->fastQ = nullptr;
+#endif
   if (const char *ev = getenv("FARMS_B200_FAST")) h->fast_enabled = atoi(ev) != 0;
   memset(&h->P, 0, sizeof(h->P));
 #ifdef FB_HOST_EMU
@@ -375,10 +396,13 @@ int fb_create(const FbModel *model, const FbFarms *farms, int n_envs, int device
   FbParams &P = h->P;
   P.n_envs = n_envs; P.ring = ring_steps;
   const size_t n = (size_t)n_envs, nb = m.nbody, mc = m.maxcon > 0 ? m.maxcon : 1, nu = m.nu > 0 ? m.nu : 1;
-  P.links_env_stride = (long long)ring_steps*m.n_links*20;
-  P.joints_env_stride = (long long)ring_steps*m.n_joints*m.joint_cols;
-  P.contacts_env_stride = (long long)ring_steps*m.n_contacts*12;
-  P.xfrc_env_stride = (long long)ring_steps*m.n_xfrc*6;
+  /* environment strides are padded to 16 bytes so that the alignment of a log row does
+   * not depend on the environment (vector stores of the per-thread kernel) */
+  auto pad4 = [](long long v) { return (v + 3) & ~3LL; };
+  P.links_env_stride = pad4((long long)ring_steps*m.n_links*20);
+  P.joints_env_stride = pad4((long long)ring_steps*m.n_joints*m.joint_cols);
+  P.contacts_env_stride = pad4((long long)ring_steps*m.n_contacts*12);
+  P.xfrc_env_stride = pad4((long long)ring_steps*m.n_xfrc*6);
   int bad = 0;
   bad |= alloc_arr(h, &P.qpos, n*m.nq); bad |= alloc_arr(h, &P.qvel, n*m.nv);
   bad |= alloc_arr(h, &P.ctrl, n*nu); bad |= alloc_arr(h, &P.xfrc_applied, n*6*nb);
@@ -565,12 +589,15 @@ int fb_export_farms(FbHandle *h, int env, double *links, double *joints, double 
   if (!h) return fail("null handle");
   const FbParams &P = h->P;
   if (env < 0 || env >= P.n_envs) return fail("fb_export_farms: env out of range");
-  struct Item { double *dst; const float *src; long long stride; } items[4] = {
-    {links, P.log_links, P.links_env_stride}, {joints, P.log_joints, P.joints_env_stride},
-    {contacts, P.log_contacts, P.contacts_env_stride}, {xfrc, P.log_xfrc, P.xfrc_env_stride}};
+  const DevModel &dm = h->hm.m;
+  struct Item { double *dst; const float *src; long long stride, count; } items[4] = {
+    {links, P.log_links, P.links_env_stride, (long long)P.ring*dm.n_links*20},
+    {joints, P.log_joints, P.joints_env_stride, (long long)P.ring*dm.n_joints*dm.joint_cols},
+    {contacts, P.log_contacts, P.contacts_env_stride, (long long)P.ring*dm.n_contacts*12},
+    {xfrc, P.log_xfrc, P.xfrc_env_stride, (long long)P.ring*dm.n_xfrc*6}};
   for (const Item &it : items) {
-    if (!it.dst || it.stride == 0) continue;
-    std::vector<float> tmp((size_t)it.stride);
+    if (!it.dst || it.count == 0) continue;
+    std::vector<float> tmp((size_t)it.count);
     if (d2h(tmp.data(), it.src + (size_t)env*it.stride, tmp.size()*sizeof(float), h->stream) ||
         dev_sync(h->stream))
       return fail(std::string("fb_export_farms: ") + dev_error());

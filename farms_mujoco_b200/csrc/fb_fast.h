@@ -146,53 +146,36 @@ FB_UNROLL
   }
 }
 
+#ifdef FB_HOST_EMU
+FB_DEV float fb_rcp(float x) { return 1.0f/x; }
+#else
+FB_DEV float fb_rcp(float x) { return __frcp_rn(x); }
+#endif
+
 template <int BLK> struct FbFast {
   const FbParams &P;
   const DevModel &m;
+  const FastRec *rec; /* [nbody], constant bank (kernel parameters) */
   float *s;           /* shared floats, already offset by the thread index */
   const int env;
   float env_phase;
-  const float *g_ctrl, *g_spring;
+  float rootpos[3];   /* world position the anchors are measured from (the floating root) */
 
-  FB_MEM FbFast(const FbParams &P_, float *s_, int env_)
-      : P(P_), m(P_.m), s(s_), env(env_) {
+  FB_MEM FbFast(const FbParams &P_, const FastRec *rec_, float *s_, int env_)
+      : P(P_), m(P_.m), rec(rec_), s(s_), env(env_) {
     env_phase = P.env_phase[env];
-    g_ctrl = P.ctrl + (size_t)env*(m.nu > 0 ? m.nu : 1);
-    g_spring = P.qpos_spring + (size_t)env*m.nq;
+    rootpos[0] = rootpos[1] = rootpos[2] = 0.f;
   }
 
-  FB_MEM float &S(int off, int i) const { return s[(size_t)(off + i)*BLK]; }
+  FB_MEM float *block(int b) const { return s + (m.X.body0 + FB_NF*(b - 1))*BLK; }
+  FB_MEM float &root(int i) const { return s[(m.X.root0 + i)*BLK]; }
+  FB_MEM float *slot(int i) const { return s + (m.X.slots + 27*i)*BLK; }
 
-  FB_MEM Quat quat_of(int b) const {
-    Quat q = {S(m.X.quat, 4*b), S(m.X.quat, 4*b+1), S(m.X.quat, 4*b+2), S(m.X.quat, 4*b+3)};
-    return q;
-  }
-
-  /* r = anchor(b) - anchor(parent) in world axes.  qp/Rp: orientation of the parent
-   * (identity for the world), Rb: rotation of b, dq: joint coordinate minus qpos0.
-   * The anchor is fixed in the frame of b BEFORE its joint rotation (MuJoCo xanchor). */
-  FB_MEM void anchor_offset(int b, int jtype, int jid, Quat qp, const float *Rp, const float *Rb,
-                            float dq, float *r) const {
-    m_rot(Rp, MF(ft_dpos, 3*b), MF(ft_dpos, 3*b+1), MF(ft_dpos, 3*b+2), r);
-    if (jid >= 0 && jtype != FB_JNT_FREE) {
-      if (m.X.any_jpos) {
-        Quat bq = {MF(body_quat, 4*b), MF(body_quat, 4*b+1), MF(body_quat, 4*b+2), MF(body_quat, 4*b+3)};
-        float Rpre[9], t[3];
-        q_mat(q_normalize(q_mul(qp, bq)), Rpre);
-        m_rot(Rpre, MF(jnt_pos, 3*jid), MF(jnt_pos, 3*jid+1), MF(jnt_pos, 3*jid+2), t);
-        r[0] += t[0]; r[1] += t[1]; r[2] += t[2];
-      }
-      if (jtype == FB_JNT_SLIDE) {
-        float ax[3];
-        m_rot(Rb, MF(jnt_axis, 3*jid), MF(jnt_axis, 3*jid+1), MF(jnt_axis, 3*jid+2), ax);
-        r[0] += ax[0]*dq; r[1] += ax[1]*dq; r[2] += ax[2]*dq;
-      }
-    }
-  }
-
-  /* sum of gear*force of the joint's actuators and the farms joint_torque sum */
-  FB_MEM void actuation(int jid, int fj, float q, float qd, float time, int store_ctrl,
-                        float *tau, float *trq_log) const {
+  /* generic actuation (clamps, gears, partial logging): force sum and farms joint_torque */
+  FB_MEM void actuation_generic(const FastRec &rc, float q, float qd, float time, int store_ctrl,
+                                float *tau, float *trq_log) const {
+    const int jid = rc.jid, fj = rc.fj;
+    const float *g_ctrl = P.ctrl + (size_t)env*(m.nu > 0 ? m.nu : 1);
     int a0 = MI(jnt_actstart, jid), a1 = MI(jnt_actstart, jid + 1);
     int ap = -1, av = -1, at = -1;
     if (fj >= 0) { ap = MI(fj_actpos, fj); av = MI(fj_actvel, fj); at = MI(fj_acttrq, fj); }
@@ -222,17 +205,52 @@ template <int BLK> struct FbFast {
   FB_MEM void load_state() {
     const float *gq = P.qpos + (size_t)env*m.nq, *gv = P.qvel + (size_t)env*m.nv;
     const float *gx = P.xfrc_applied + (size_t)env*6*m.nbody;
-    for (int i = 0; i < m.nq; i++) S(m.X.qpos, i) = gq[i];
-    for (int i = 0; i < m.nv; i++) S(m.X.qvel, i) = gv[i];
-    for (int i = 0; i < 6*m.nbody; i++) S(m.X.wrench, i) = gx[i];
+    const float *g_ctrl = P.ctrl + (size_t)env*(m.nu > 0 ? m.nu : 1);
+    for (int b = 1; b < m.nbody; b++) {
+      const FastRec &rc = rec[b];
+      float *pb = block(b);
+      if (rc.jtype == FB_JNT_FREE) {
+        for (int k = 0; k < 7; k++) root(k) = gq[rc.qa + k];
+        for (int k = 0; k < 6; k++) root(7 + k) = gv[rc.da + k];
+      } else if (rc.jtype >= 0) {
+        pb[FB_Q*BLK] = gq[rc.qa];
+        pb[FB_QD*BLK] = gv[rc.da];
+        /* constant part of the joint's actuation over this launch (ctrl is held), and of
+         * the actuators the farms joint_torque column leaves out */
+        float tc = rc.T0, tu = rc.T0U;
+        if (rc.flags & FT_ACT_SIMPLE) {
+          int ap = -1, av = -1, at = -1;
+          if (rc.fj >= 0) { ap = MI(fj_actpos, rc.fj); av = MI(fj_actvel, rc.fj); at = MI(fj_acttrq, rc.fj); }
+          for (int t = MI(jnt_actstart, rc.jid); t < MI(jnt_actstart, rc.jid + 1); t++) {
+            int a = MI(act_sorted, t);
+            if (a == rc.wave_act) continue;
+            float f = MF(act_gain, a)*g_ctrl[a];
+            tc += f;
+            if (!(a == ap || a == av || a == at)) tu += f;
+          }
+        }
+        pb[FB_TC*BLK] = tc;
+        pb[FB_TU*BLK] = tu;
+      }
+      for (int k = 0; k < 6; k++) pb[(FB_W + k)*BLK] = gx[6*b + k];
+    }
   }
 
   FB_MEM void store_state(long long iteration) {
     float *gq = P.qpos + (size_t)env*m.nq, *gv = P.qvel + (size_t)env*m.nv;
     float *gx = P.xfrc_applied + (size_t)env*6*m.nbody;
-    for (int i = 0; i < m.nq; i++) gq[i] = S(m.X.qpos, i);
-    for (int i = 0; i < m.nv; i++) gv[i] = S(m.X.qvel, i);
-    for (int i = 0; i < 6*m.nbody; i++) gx[i] = S(m.X.wrench, i);
+    for (int b = 1; b < m.nbody; b++) {
+      const FastRec &rc = rec[b];
+      const float *pb = block(b);
+      if (rc.jtype == FB_JNT_FREE) {
+        for (int k = 0; k < 7; k++) gq[rc.qa + k] = root(k);
+        for (int k = 0; k < 6; k++) gv[rc.da + k] = root(7 + k);
+      } else if (rc.jtype >= 0) {
+        gq[rc.qa] = pb[FB_Q*BLK];
+        gv[rc.da] = pb[FB_QD*BLK];
+      }
+      for (int k = 0; k < 6; k++) gx[6*b + k] = pb[(FB_W + k)*BLK];
+    }
     P.iteration[env] = iteration;
   }
 
@@ -242,87 +260,89 @@ template <int BLK> struct FbFast {
     const int nb = m.nbody;
     int active = 0;
     for (int b = 1; b < nb; b++) {
-      const int p = MI(body_parent, b), jid = MI(body_jnt, b);
-      const int jtype = jid >= 0 ? MI(jnt_type, jid) : -1;
-      Quat qp = {1.f, 0.f, 0.f, 0.f};
-      float op[3] = {0.f, 0.f, 0.f}, vp[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-      if (p > 0) {
-        qp = quat_of(p);
-FB_UNROLL
-        for (int k = 0; k < 3; k++) op[k] = S(m.X.org, 3*p + k);
-FB_UNROLL
-        for (int k = 0; k < 6; k++) vp[k] = S(m.X.vel, 6*p + k);
-      }
+      const FastRec &rc = rec[b];
+      float *pb = block(b);
+      const int jtype = rc.jtype;
       Quat q;
-      float o[3], xpos[3], v[6], R[9];
+      float o[3], v[6], R[9];
       if (jtype == FB_JNT_FREE) {
-        const int qa = MI(jnt_qposadr, jid), da = MI(jnt_dofadr, jid);
-        Quat qq = {S(m.X.qpos, qa+3), S(m.X.qpos, qa+4), S(m.X.qpos, qa+5), S(m.X.qpos, qa+6)};
+        Quat qq = {root(3), root(4), root(5), root(6)};
         q = q_normalize(qq);
-        S(m.X.qpos, qa+3) = q.w; S(m.X.qpos, qa+4) = q.x; S(m.X.qpos, qa+5) = q.y; S(m.X.qpos, qa+6) = q.z;
+        root(3) = q.w; root(4) = q.x; root(5) = q.y; root(6) = q.z;
         q_mat(q, R);
 FB_UNROLL
-        for (int k = 0; k < 3; k++) { o[k] = S(m.X.qpos, qa + k); xpos[k] = o[k]; v[3 + k] = S(m.X.qvel, da + k); }
-        m_rot(R, S(m.X.qvel, da+3), S(m.X.qvel, da+4), S(m.X.qvel, da+5), v);
+        for (int k = 0; k < 3; k++) { rootpos[k] = root(k); o[k] = 0.f; v[3 + k] = root(7 + k); }
+        m_rot(R, root(10), root(11), root(12), v);
       } else {
+        Quat qp = {1.f, 0.f, 0.f, 0.f};
+        float op[3] = {0.f, 0.f, 0.f}, vp[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        if (rc.parent > 0) {
+          const float *pp = block(rc.parent);
+          qp.w = pp[(FB_QUAT)*BLK]; qp.x = pp[(FB_QUAT + 1)*BLK]; qp.y = pp[(FB_QUAT + 2)*BLK]; qp.z = pp[(FB_QUAT + 3)*BLK];
+FB_UNROLL
+          for (int k = 0; k < 3; k++) op[k] = pp[(FB_ORG + k)*BLK];
+FB_UNROLL
+          for (int k = 0; k < 6; k++) vp[k] = pp[(FB_VEL + k)*BLK];
+        }
         float Rp[9], r[3], dq = 0.f, qd = 0.f;
         q_mat(qp, Rp);
-        Quat bq = {MF(body_quat, 4*b), MF(body_quat, 4*b+1), MF(body_quat, 4*b+2), MF(body_quat, 4*b+3)};
+        m_rot(Rp, rc.dpos[0], rc.dpos[1], rc.dpos[2], r);
+        Quat bq = {rc.bquat[0], rc.bquat[1], rc.bquat[2], rc.bquat[3]};
         q = q_mul(qp, bq);
-        float ja[3] = {0.f, 0.f, 0.f};
-        if (jid >= 0) {
-          const int qa = MI(jnt_qposadr, jid), da = MI(jnt_dofadr, jid);
-          const float qj = S(m.X.qpos, qa);
-          qd = S(m.X.qvel, da);
-          dq = qj - MF(jnt_qpos0, jid);
-          ja[0] = MF(jnt_axis, 3*jid); ja[1] = MF(jnt_axis, 3*jid+1); ja[2] = MF(jnt_axis, 3*jid+2);
+        if (rc.flags & FT_HAS_JPOS) {      /* the anchor is fixed in the frame before the joint rotation */
+          float Rpre[9], t[3];
+          q_mat(q_normalize(q), Rpre);
+          m_rot(Rpre, rc.jpos[0], rc.jpos[1], rc.jpos[2], t);
+          r[0] += t[0]; r[1] += t[1]; r[2] += t[2];
+        }
+        if (jtype >= 0) {
+          const float qj = pb[FB_Q*BLK];
+          qd = pb[FB_QD*BLK];
+          dq = qj - rc.qpos0;
           if (jtype == FB_JNT_HINGE) {
             float sn, cs;
             fb_sincos(0.5f*dq, &sn, &cs);
-            Quat ql = {cs, ja[0]*sn, ja[1]*sn, ja[2]*sn};
+            Quat ql = {cs, rc.axis[0]*sn, rc.axis[1]*sn, rc.axis[2]*sn};
             q = q_mul(q, ql);
           }
-          if (MI(jnt_limited, jid)) {
-            const float margin = MF(jnt_margin, jid);
-            if (qj - MF(jnt_range, 2*jid) < margin || MF(jnt_range, 2*jid+1) - qj < margin) active = 1;
-          }
+          if ((rc.flags & FT_LIMITED) && (qj - rc.lo < rc.margin || rc.hi - qj < rc.margin)) active = 1;
         }
         q = q_normalize(q);
         q_mat(q, R);
-        anchor_offset(b, jtype, jid, qp, Rp, R, dq, r);
         float ax[3] = {0.f, 0.f, 0.f}, cr[3];
-        if (jid >= 0) m_rot(R, ja[0], ja[1], ja[2], ax);
+        if (jtype >= 0) m_rot(R, rc.axis[0], rc.axis[1], rc.axis[2], ax);
+        if (jtype == FB_JNT_SLIDE) { r[0] += ax[0]*dq; r[1] += ax[1]*dq; r[2] += ax[2]*dq; }
         v_cross(vp, r, cr);                      /* w_parent x r */
 FB_UNROLL
         for (int k = 0; k < 3; k++) {
           o[k] = op[k] + r[k];
           v[k] = vp[k] + (jtype == FB_JNT_HINGE ? ax[k]*qd : 0.f);
           v[3 + k] = vp[3 + k] + cr[k] + (jtype == FB_JNT_SLIDE ? ax[k]*qd : 0.f);
-          xpos[k] = o[k];
-        }
-        if (jid >= 0 && m.X.any_jpos) {
-          float t[3];
-          m_rot(R, MF(jnt_pos, 3*jid), MF(jnt_pos, 3*jid+1), MF(jnt_pos, 3*jid+2), t);
-          xpos[0] -= t[0]; xpos[1] -= t[1]; xpos[2] -= t[2];
         }
       }
-      S(m.X.quat, 4*b) = q.w; S(m.X.quat, 4*b+1) = q.x; S(m.X.quat, 4*b+2) = q.y; S(m.X.quat, 4*b+3) = q.z;
+      pb[(FB_QUAT)*BLK] = q.w; pb[(FB_QUAT + 1)*BLK] = q.x; pb[(FB_QUAT + 2)*BLK] = q.y; pb[(FB_QUAT + 3)*BLK] = q.z;
 FB_UNROLL
-      for (int k = 0; k < 3; k++) S(m.X.org, 3*b + k) = o[k];
+      for (int k = 0; k < 3; k++) pb[(FB_ORG + k)*BLK] = o[k];
 FB_UNROLL
-      for (int k = 0; k < 6; k++) S(m.X.vel, 6*b + k) = v[k];
+      for (int k = 0; k < 6; k++) pb[(FB_VEL + k)*BLK] = v[k];
+      float xpos[3] = {rootpos[0] + o[0], rootpos[1] + o[1], rootpos[2] + o[2]};
+      if (rc.flags & FT_HAS_JPOS) {
+        float t[3];
+        m_rot(R, rc.jpos[0], rc.jpos[1], rc.jpos[2], t);
+        xpos[0] -= t[0]; xpos[1] -= t[1]; xpos[2] -= t[2];
+      }
       /* conservative plane bound */
-      for (int t = MI(ft_chkstart, b); t < MI(ft_chkstart, b + 1); t++)
+      if (rc.chk[0]*xpos[0] + rc.chk[1]*xpos[1] + rc.chk[2]*xpos[2] < rc.chk[3]) active = 1;
+      for (int t = rc.chk0; t < rc.chk1; t++)
         if (MF(ft_chk, 4*t)*xpos[0] + MF(ft_chk, 4*t+1)*xpos[1] + MF(ft_chk, 4*t+2)*xpos[2] < MF(ft_chk, 4*t+3)) active = 1;
       /* links row: physics.py:449-466 + :435-446 */
-      const int l = MI(ft_link, b);
-      if (l >= 0) {
+      if (rc.link >= 0) {
         float h[3], cr[3];
-        m_rot(R, MF(ft_hloc, 3*b), MF(ft_hloc, 3*b+1), MF(ft_hloc, 3*b+2), h);   /* com - anchor */
+        m_rot(R, rc.hloc[0], rc.hloc[1], rc.hloc[2], h);   /* com - anchor */
         v_cross(v, h, cr);
         const float im = m.inv_meters, iv = m.inv_velocity, iw = m.inv_angvel;
-        float *row = row_links + 20*l;
-        fb_st4(row, (o[0] + h[0])*im, (o[1] + h[1])*im, (o[2] + h[2])*im, q.x);
+        float *row = row_links + 20*rc.link;
+        fb_st4(row, (rootpos[0] + o[0] + h[0])*im, (rootpos[1] + o[1] + h[1])*im, (rootpos[2] + o[2] + h[2])*im, q.x);
         fb_st4(row + 4, q.y, q.z, q.w, xpos[0]*im);
         fb_st4(row + 8, xpos[1]*im, xpos[2]*im, q.x, q.y);
         fb_st4(row + 12, q.z, q.w, (v[3] + cr[0])*iv, (v[4] + cr[1])*iv);
@@ -343,26 +363,25 @@ FB_UNROLL
 FB_UNROLL
     for (int k = 0; k < 9; k++) C.H[k] = 0.f;
     for (int b = nb - 1; b >= 1; b--) {
-      const int p = MI(body_parent, b), jid = MI(body_jnt, b), flags = MI(ft_flags, b);
-      const int jtype = jid >= 0 ? MI(jnt_type, jid) : -1;
-      const Quat q = quat_of(b);
+      const FastRec &rc = rec[b];
+      float *pb = block(b);
+      const int jtype = rc.jtype, flags = rc.flags;
+      const Quat q = {pb[(FB_QUAT)*BLK], pb[(FB_QUAT + 1)*BLK], pb[(FB_QUAT + 2)*BLK], pb[(FB_QUAT + 3)*BLK]};
       float R[9], v[6], fx[6];
       q_mat(q, R);
 FB_UNROLL
-      for (int k = 0; k < 6; k++) { v[k] = S(m.X.vel, 6*b + k); fx[k] = S(m.X.wrench, 6*b + k); }
+      for (int k = 0; k < 6; k++) { v[k] = pb[(FB_VEL + k)*BLK]; fx[k] = pb[(FB_W + k)*BLK]; }
       /* rigid-body inertia about the anchor */
-      const float mass = MF(body_mass, b);
-      float h[3], Ib[6], Iw[6];
-      m_rot(R, MF(ft_hloc, 3*b), MF(ft_hloc, 3*b+1), MF(ft_hloc, 3*b+2), h);
-FB_UNROLL
-      for (int k = 0; k < 6; k++) Ib[k] = MF(ft_inertia, 6*b + k);
+      const float mass = rc.mass;
+      float h[3], Iw[6];
+      m_rot(R, rc.hloc[0], rc.hloc[1], rc.hloc[2], h);
       {
         /* Iw = R Ib R' */
         float T[9];
 FB_UNROLL
         for (int i = 0; i < 3; i++) {
           float ri[3] = {R[3*i], R[3*i+1], R[3*i+2]}, t[3];
-          sym_mul(Ib, ri, t);
+          sym_mul(rc.Ib, ri, t);
           T[3*i] = t[0]; T[3*i+1] = t[1]; T[3*i+2] = t[2];       /* row i of R Ib */
         }
         Iw[0] = T[0]*R[0] + T[1]*R[1] + T[2]*R[2];
@@ -408,13 +427,12 @@ FB_UNROLL
         for (int k = 0; k < 9; k++) I.H[k] += C.H[k];
       }
       if (flags & FT_HAS_SLOT) {
-        const int so = m.X.slots + 27*MI(ft_slot, b);
+        const float *so = slot(rc.slot);
 FB_UNROLL
-        for (int k = 0; k < 6; k++) { I.A[k] += S(so, k); I.M[k] += S(so, 15 + k); pA[k] += S(so, 21 + k); }
+        for (int k = 0; k < 6; k++) { I.A[k] += so[k*BLK]; I.M[k] += so[(15 + k)*BLK]; pA[k] += so[(21 + k)*BLK]; }
 FB_UNROLL
-        for (int k = 0; k < 9; k++) I.H[k] += S(so, 6 + k);
+        for (int k = 0; k < 9; k++) I.H[k] += so[(6 + k)*BLK];
       }
-      float dq = 0.f;
       if (jtype == FB_JNT_FREE) {
         /* floating root: I a + pA = 0 for the (gravity-free frame) acceleration */
         float K[6][6], rhs[6];
@@ -431,23 +449,31 @@ FB_UNROLL
         solve6(K, rhs, aroot);
         continue;
       }
-      if (jid >= 0) {
-        const int qa = MI(jnt_qposadr, jid), da = MI(jnt_dofadr, jid);
-        const float qj = S(m.X.qpos, qa), qd = S(m.X.qvel, da);
-        dq = qj - MF(jnt_qpos0, jid);
+      if (jtype >= 0) {
+        const float qj = pb[FB_Q*BLK], qd = pb[FB_QD*BLK];
         float ax[3], U[6], c[6], tau, trq;
-        m_rot(R, MF(jnt_axis, 3*jid), MF(jnt_axis, 3*jid+1), MF(jnt_axis, 3*jid+2), ax);
-        actuation(jid, MI(ft_fj, b), qj, qd, time, store_ctrl, &tau, &trq);
-        const float stiff = MF(jnt_stiffness, jid), damp = MF(dof_damping, da);
-        if (stiff != 0.f) tau -= stiff*(qj - g_spring[qa]);
-        tau -= damp*qd;
+        m_rot(R, rc.axis[0], rc.axis[1], rc.axis[2], ax);
+        if (flags & FT_ACT_SIMPLE) {
+          tau = pb[FB_TC*BLK] + rc.Kq*qj + rc.Kqd*qd;
+          if (flags & FT_HAS_WAVE) {
+            float ph = 6.283185307179586f*rc.wfreq*time - rc.wlag + env_phase;
+            float cw = rc.woff + rc.wamp*sinf(ph);
+            tau += rc.wgain*cw;
+            if (store_ctrl) P.ctrl[(size_t)env*m.nu + rc.wave_act] = cw;
+          }
+          trq = tau - (pb[FB_TU*BLK] + rc.KqU*qj + rc.KqdU*qd);
+        } else {
+          actuation_generic(rc, qj, qd, time, store_ctrl, &tau, &trq);
+        }
+        if (rc.stiffness != 0.f) tau -= rc.stiffness*(qj - P.qpos_spring[(size_t)env*m.nq + rc.qa]);
+        tau -= rc.damping*qd;
         float d, u;
+        float aq[3] = {ax[0]*qd, ax[1]*qd, ax[2]*qd};
         if (jtype == FB_JNT_HINGE) {
           sym_mul(I.A, ax, U);
           ht_mul(I.H, ax, U + 3);
           d = ax[0]*U[0] + ax[1]*U[1] + ax[2]*U[2];
           u = tau - (ax[0]*pA[0] + ax[1]*pA[1] + ax[2]*pA[2]);
-          float aq[3] = {ax[0]*qd, ax[1]*qd, ax[2]*qd};
           v_cross(v, aq, c);
           v_cross(v + 3, aq, c + 3);
         } else {
@@ -455,19 +481,20 @@ FB_UNROLL
           sym_mul(I.M, ax, U + 3);
           d = ax[0]*U[3] + ax[1]*U[4] + ax[2]*U[5];
           u = tau - (ax[0]*pA[3] + ax[1]*pA[4] + ax[2]*pA[5]);
-          float aq[3] = {ax[0]*qd, ax[1]*qd, ax[2]*qd};
           c[0] = c[1] = c[2] = 0.f;
           v_cross(v, aq, c + 3);
         }
-        d += MF(dof_armature, da) + hdt*damp;
-        const float dinv = 1.0f/d;
+        d += rc.armature + hdt*rc.damping;
+        const float dinv = fb_rcp(d);
         /* Ia = I - U U'/d */
         sym_rank1(I.A, U, dinv);
         sym_rank1(I.M, U + 3, dinv);
 FB_UNROLL
-        for (int i = 0; i < 3; i++)
+        for (int i = 0; i < 3; i++) {
+          const float ui = dinv*U[i];
 FB_UNROLL
-          for (int j = 0; j < 3; j++) I.H[3*i + j] -= dinv*U[i]*U[3 + j];
+          for (int j = 0; j < 3; j++) I.H[3*i + j] -= ui*U[3 + j];
+        }
         /* pa = pA + Ia c + U u/d */
         float t0[3], t1[3];
         const float ud = u*dinv;
@@ -478,16 +505,16 @@ FB_UNROLL
 FB_UNROLL
         for (int k = 0; k < 3; k++) pA[3 + k] += t0[k] + t1[k] + U[3 + k]*ud;
 FB_UNROLL
-        for (int k = 0; k < 6; k++) S(m.X.wrench, 6*b + k) = U[k];
-        S(m.X.u, b) = u; S(m.X.dinv, b) = dinv; S(m.X.trq, b) = trq;
+        for (int k = 0; k < 6; k++) pb[(FB_W + k)*BLK] = U[k];
+        pb[FB_U*BLK] = u; pb[FB_DINV*BLK] = dinv; pb[FB_TRQ*BLK] = trq;
       }
-      if (p == 0) continue;        /* fixed base: nothing above */
+      if (rc.parent == 0) continue;        /* fixed base: nothing above */
       /* move to the parent's anchor and hand over */
       {
-        float Rp[9], r[3];
-        const Quat qp = quat_of(p);
-        q_mat(qp, Rp);
-        anchor_offset(b, jtype, jid, qp, Rp, R, dq, r);
+        const float *pp = block(rc.parent);
+        float r[3];
+FB_UNROLL
+        for (int k = 0; k < 3; k++) r[k] = pb[(FB_ORG + k)*BLK] - pp[(FB_ORG + k)*BLK];
         art_shift(I, pA, r);
       }
       if (flags & FT_TO_CARRY) {
@@ -495,38 +522,38 @@ FB_UNROLL
 FB_UNROLL
         for (int k = 0; k < 6; k++) pc[k] = pA[k];
       } else {
-        const int so = m.X.slots + 27*MI(ft_pslot, b);
+        float *so = slot(rc.pslot);
         if (flags & FT_FIRST_WRITER) {
 FB_UNROLL
-          for (int k = 0; k < 6; k++) { S(so, k) = I.A[k]; S(so, 15 + k) = I.M[k]; S(so, 21 + k) = pA[k]; }
+          for (int k = 0; k < 6; k++) { so[k*BLK] = I.A[k]; so[(15 + k)*BLK] = I.M[k]; so[(21 + k)*BLK] = pA[k]; }
 FB_UNROLL
-          for (int k = 0; k < 9; k++) S(so, 6 + k) = I.H[k];
+          for (int k = 0; k < 9; k++) so[(6 + k)*BLK] = I.H[k];
         } else {
 FB_UNROLL
-          for (int k = 0; k < 6; k++) { S(so, k) += I.A[k]; S(so, 15 + k) += I.M[k]; S(so, 21 + k) += pA[k]; }
+          for (int k = 0; k < 6; k++) { so[k*BLK] += I.A[k]; so[(15 + k)*BLK] += I.M[k]; so[(21 + k)*BLK] += pA[k]; }
 FB_UNROLL
-          for (int k = 0; k < 9; k++) S(so, 6 + k) += I.H[k];
+          for (int k = 0; k < 9; k++) so[(6 + k)*BLK] += I.H[k];
         }
       }
     }
   }
 
   /* ---- pass 3: root -> leaves, accelerations, Euler, joints / xfrc rows, drag */
-  FB_MEM int pass_accel(const float *aroot, float *row_joints, float *row_xfrc) {
+  FB_MEM int pass_accel(const float *aroot, float *row_joints, float *row_xfrc, int jpar, int xpar) {
     const int nb = m.nbody;
     const float hdt = m.timestep;
     float ac[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};   /* carry: acceleration of body b-1 */
     int bad = 0;
     for (int b = 1; b < nb; b++) {
-      const int p = MI(body_parent, b), jid = MI(body_jnt, b), flags = MI(ft_flags, b);
-      const int jtype = jid >= 0 ? MI(jnt_type, jid) : -1;
-      const Quat q = quat_of(b);
+      const FastRec &rc = rec[b];
+      float *pb = block(b);
+      const int jtype = rc.jtype, flags = rc.flags;
+      const Quat q = {pb[(FB_QUAT)*BLK], pb[(FB_QUAT + 1)*BLK], pb[(FB_QUAT + 2)*BLK], pb[(FB_QUAT + 3)*BLK]};
       float R[9], v[6], a[6];
       q_mat(q, R);
 FB_UNROLL
-      for (int k = 0; k < 6; k++) v[k] = S(m.X.vel, 6*b + k);
+      for (int k = 0; k < 6; k++) v[k] = pb[(FB_VEL + k)*BLK];
       if (jtype == FB_JNT_FREE) {
-        const int qa = MI(jnt_qposadr, jid), da = MI(jnt_dofadr, jid);
 FB_UNROLL
         for (int k = 0; k < 6; k++) a[k] = aroot[k];
         float cr[3], wl[3], w[3];
@@ -534,52 +561,45 @@ FB_UNROLL
         m_rot_t(R, a[0], a[1], a[2], wl);
 FB_UNROLL
         for (int k = 0; k < 3; k++) {
-          float vn = S(m.X.qvel, da + k) + hdt*(a[3 + k] + m.grav[k] + cr[k]);
-          S(m.X.qvel, da + k) = vn;
-          float pn = S(m.X.qpos, qa + k) + hdt*vn;
-          S(m.X.qpos, qa + k) = pn;
-          w[k] = S(m.X.qvel, da + 3 + k) + hdt*wl[k];
-          S(m.X.qvel, da + 3 + k) = w[k];
+          float vn = root(7 + k) + hdt*(a[3 + k] + m.grav[k] + cr[k]);
+          root(7 + k) = vn;
+          float pn = root(k) + hdt*vn;
+          root(k) = pn;
+          w[k] = root(10 + k) + hdt*wl[k];
+          root(10 + k) = w[k];
           bad |= !(fabsf(pn) < 1e30f);
         }
         float angle = hdt*v_normalize3(w), sn, cs;
         fb_sincos(0.5f*angle, &sn, &cs);
         Quat qr = {cs, w[0]*sn, w[1]*sn, w[2]*sn};
         Quat qn = q_normalize(q_mul(q, qr));
-        S(m.X.qpos, qa+3) = qn.w; S(m.X.qpos, qa+4) = qn.x; S(m.X.qpos, qa+5) = qn.y; S(m.X.qpos, qa+6) = qn.z;
+        root(3) = qn.w; root(4) = qn.x; root(5) = qn.y; root(6) = qn.z;
         bad |= !(fabsf(qn.w) < 1e30f) | !(fabsf(qn.x) < 1e30f) | !(fabsf(qn.y) < 1e30f) | !(fabsf(qn.z) < 1e30f);
       } else {
         float ap[6] = {0.f, 0.f, 0.f, -m.grav[0], -m.grav[1], -m.grav[2]};
-        float Rp[9] = {1.f, 0.f, 0.f, 0.f, 1.f, 0.f, 0.f, 0.f, 1.f}, r[3], cr[3];
-        Quat qp = {1.f, 0.f, 0.f, 0.f};
-        if (p > 0) {
-          qp = quat_of(p);
-          q_mat(qp, Rp);
+        float r[3] = {0.f, 0.f, 0.f}, cr[3];
+        if (rc.parent > 0) {
+          const float *pp = block(rc.parent);
+FB_UNROLL
+          for (int k = 0; k < 3; k++) r[k] = pb[(FB_ORG + k)*BLK] - pp[(FB_ORG + k)*BLK];
           if (flags & FT_TO_CARRY) {
 FB_UNROLL
             for (int k = 0; k < 6; k++) ap[k] = ac[k];
           } else {
-            const int so = m.X.slots + 27*MI(ft_pslot, b);
+            const float *so = slot(rc.pslot);
 FB_UNROLL
-            for (int k = 0; k < 6; k++) ap[k] = S(so, k);
+            for (int k = 0; k < 6; k++) ap[k] = so[k*BLK];
           }
         }
-        float dq = 0.f, qj = 0.f, qd = 0.f;
-        int qa = 0, da = 0;
-        if (jid >= 0) {
-          qa = MI(jnt_qposadr, jid); da = MI(jnt_dofadr, jid);
-          qj = S(m.X.qpos, qa); qd = S(m.X.qvel, da);
-          dq = qj - MF(jnt_qpos0, jid);
-        }
-        anchor_offset(b, jtype, jid, qp, Rp, R, dq, r);
         v_cross(ap, r, cr);
 FB_UNROLL
         for (int k = 0; k < 3; k++) { a[k] = ap[k]; a[3 + k] = ap[3 + k] + cr[k]; }
-        if (jid >= 0) {
+        if (jtype >= 0) {
+          const float qj = pb[FB_Q*BLK], qd = pb[FB_QD*BLK];
           float ax[3], U[6];
-          m_rot(R, MF(jnt_axis, 3*jid), MF(jnt_axis, 3*jid+1), MF(jnt_axis, 3*jid+2), ax);
+          m_rot(R, rc.axis[0], rc.axis[1], rc.axis[2], ax);
 FB_UNROLL
-          for (int k = 0; k < 6; k++) U[k] = S(m.X.wrench, 6*b + k);
+          for (int k = 0; k < 6; k++) U[k] = pb[(FB_W + k)*BLK];
           float aq[3] = {ax[0]*qd, ax[1]*qd, ax[2]*qd}, c[3];
           if (jtype == FB_JNT_HINGE) {
             v_cross(v, aq, c);
@@ -591,63 +611,63 @@ FB_UNROLL
             a[3] += c[0]; a[4] += c[1]; a[5] += c[2];
           }
           float ua = U[0]*a[0] + U[1]*a[1] + U[2]*a[2] + U[3]*a[3] + U[4]*a[4] + U[5]*a[5];
-          const float qdd = (S(m.X.u, b) - ua)*S(m.X.dinv, b);
-          const int o3 = jtype == FB_JNT_HINGE ? 0 : 3;
-          a[o3] += ax[0]*qdd; a[o3 + 1] += ax[1]*qdd; a[o3 + 2] += ax[2]*qdd;
+          const float qdd = (pb[FB_U*BLK] - ua)*pb[FB_DINV*BLK];
+          if (jtype == FB_JNT_HINGE) { a[0] += ax[0]*qdd; a[1] += ax[1]*qdd; a[2] += ax[2]*qdd; }
+          else { a[3] += ax[0]*qdd; a[4] += ax[1]*qdd; a[5] += ax[2]*qdd; }
           const float qdn = qd + hdt*qdd, qn = qj + hdt*qdn;
-          S(m.X.qvel, da) = qdn;
-          S(m.X.qpos, qa) = qn;
+          pb[FB_QD*BLK] = qdn;
+          pb[FB_Q*BLK] = qn;
           bad |= !(fabsf(qn) < 1e30f);
           /* joints row: physics.py:481-524 (new position/velocity, forces of the old state) */
-          const int fj = MI(ft_fj, b);
-          if (fj >= 0) {
-            float *row = row_joints + m.joint_cols*fj;
-            const float trq = S(m.X.trq, b)*m.inv_torques;
-            for (int k = 0; k < m.joint_cols; k += 2) {
-              float x0 = 0.f, x1 = 0.f;
-              if (k == (m.col_jpos & ~1)) { if (m.col_jpos & 1) x1 = qn; else x0 = qn; }
-              if (k == (m.col_jvel & ~1)) { if (m.col_jvel & 1) x1 = qdn*m.inv_angvel; else x0 = qdn*m.inv_angvel; }
-              if (k == (m.col_jtrq & ~1)) { if (m.col_jtrq & 1) x1 = trq; else x0 = trq; }
-              fb_st2(row + k, x0, x1);
+          if (rc.fj >= 0) {
+            float *row = row_joints + m.joint_cols*rc.fj;
+            const float trq = pb[FB_TRQ*BLK]*m.inv_torques, jv = qdn*m.inv_angvel;
+            const int cp = m.col_jpos, cv = m.col_jvel, ct = m.col_jtrq, cols = m.joint_cols;
+#define FB_JCOL(c_) ((c_) == cp ? qn : ((c_) == cv ? jv : ((c_) == ct ? trq : 0.f)))
+            /* 16-byte stores where the row allows it (rows are 8-byte aligned) */
+            int c = 0;
+            if ((jpar + cols*rc.fj) & 2) { fb_st2(row, FB_JCOL(0), FB_JCOL(1)); c = 2; }
+            for (; c + 4 <= cols; c += 4) {
+              const bool special = (cp >= c && cp < c + 4) || (cv >= c && cv < c + 4) || (ct >= c && ct < c + 4);
+              if (special) fb_st4(row + c, FB_JCOL(c), FB_JCOL(c + 1), FB_JCOL(c + 2), FB_JCOL(c + 3));
+              else fb_st4(row + c, 0.f, 0.f, 0.f, 0.f);
             }
+            if (c < cols) fb_st2(row + c, FB_JCOL(c), FB_JCOL(c + 1));
+#undef FB_JCOL
           }
         }
       }
 FB_UNROLL
       for (int k = 0; k < 6; k++) ac[k] = a[k];
       if (flags & FT_HAS_SLOT) {
-        const int so = m.X.slots + 27*MI(ft_slot, b);
+        float *so = slot(rc.slot);
 FB_UNROLL
-        for (int k = 0; k < 6; k++) S(so, k) = a[k];
+        for (int k = 0; k < 6; k++) so[k*BLK] = a[k];
       }
       /* xfrc row + the wrench applied during the next step (drag.pyx:152-268, 3.4) */
-      const int xr = MI(body_xfrcrow, b);
-      if (xr >= 0) {
+      if (rc.xr >= 0) {
         float F[3] = {0.f, 0.f, 0.f}, Tq[3] = {0.f, 0.f, 0.f}, wf[3] = {0.f, 0.f, 0.f}, wt[3] = {0.f, 0.f, 0.f};
-        const int i = MI(ft_swim, b);
-        if (m.water_drag && i >= 0) {
+        if (m.water_drag && rc.swim >= 0) {
           float h[3], cr[3], lin[3], vl[3], wl[3], uw[3], buoy[3] = {0.f, 0.f, 0.f};
-          m_rot(R, MF(ft_hloc, 3*b), MF(ft_hloc, 3*b+1), MF(ft_hloc, 3*b+2), h);
-          const float pz = (S(m.X.org, 3*b + 2) + h[2])*m.inv_meters;
+          m_rot(R, rc.hloc[0], rc.hloc[1], rc.hloc[2], h);
+          const float pz = (rootpos[2] + pb[(FB_ORG + 2)*BLK] + h[2])*m.inv_meters;
           if (!(pz > m.water_surface)) {                 /* drag.pyx:192-194 */
             v_cross(v, h, cr);
 FB_UNROLL
             for (int k = 0; k < 3; k++) lin[k] = v[3 + k] + cr[k];
             m_rot_t(R, lin[0]*m.inv_velocity, lin[1]*m.inv_velocity, lin[2]*m.inv_velocity, vl);
             m_rot_t(R, v[0]*m.inv_angvel, v[1]*m.inv_angvel, v[2]*m.inv_angvel, wl);
-            const float mass = MF(swim_mass, i);
-            if (m.water_buoyancy && mass > 0.f && pz < m.water_surface) {
-              float frac = fminf(fmaxf(m.water_surface - pz, 0.f)/MF(swim_height, i), 1.f);
-              float lift = -1000.f*mass*(-9.81f)/MF(swim_density, i)*frac;
-              m_rot_t(R, 0.f, 0.f, lift, buoy);
+            if (m.water_buoyancy && rc.lift > 0.f && pz < m.water_surface) {
+              float frac = fminf(fmaxf(m.water_surface - pz, 0.f)/rc.height, 1.f);
+              m_rot_t(R, 0.f, 0.f, rc.lift*frac, buoy);
             }
             m_rot_t(R, m.water_velocity[0], m.water_velocity[1], m.water_velocity[2], uw);
 FB_UNROLL
             for (int k = 0; k < 3; k++) {
               float vv = vl[k] - uw[k], w = wl[k];
               float sv = vv < 0.f ? -vv*vv : vv*vv, sw = w < 0.f ? -w*w : w*w;
-              F[k] = sv*m.water_viscosity*MF(swim_coef, 6*i + k) + buoy[k];
-              Tq[k] = sw*MF(swim_coef, 6*i + 3 + k);
+              F[k] = sv*m.water_viscosity*rc.coef[k] + buoy[k];
+              Tq[k] = sw*rc.coef[3 + k];
             }
             m_rot(R, F[0], F[1], F[2], wf);
             m_rot(R, Tq[0], Tq[1], Tq[2], wt);
@@ -655,15 +675,16 @@ FB_UNROLL
             for (int k = 0; k < 3; k++) { wf[k] *= m.newtons; wt[k] *= m.torques; }
           }
         }
-        float *row = row_xfrc + 6*xr;
-        fb_st2(row, F[0], F[1]); fb_st2(row + 2, F[2], Tq[0]); fb_st2(row + 4, Tq[1], Tq[2]);
+        float *row = row_xfrc + 6*rc.xr;
+        if ((xpar + 6*rc.xr) & 2) { fb_st2(row, F[0], F[1]); fb_st4(row + 2, F[2], Tq[0], Tq[1], Tq[2]); }
+        else { fb_st4(row, F[0], F[1], F[2], Tq[0]); fb_st2(row + 4, Tq[1], Tq[2]); }
 FB_UNROLL
-        for (int k = 0; k < 3; k++) { S(m.X.wrench, 6*b + k) = wf[k]; S(m.X.wrench, 6*b + 3 + k) = wt[k]; }
+        for (int k = 0; k < 3; k++) { pb[(FB_W + k)*BLK] = wf[k]; pb[(FB_W + 3 + k)*BLK] = wt[k]; }
       } else {
         /* user-applied wrench: persistent, re-read (the slot held U during this step) */
         const float *gx = P.xfrc_applied + ((size_t)env*m.nbody + b)*6;
 FB_UNROLL
-        for (int k = 0; k < 6; k++) S(m.X.wrench, 6*b + k) = gx[k];
+        for (int k = 0; k < 6; k++) pb[(FB_W + k)*BLK] = gx[k];
       }
     }
     return bad;
@@ -685,7 +706,11 @@ FB_UNROLL
       if (pass_poses(row_links)) break;
       float aroot[6] = {0.f, 0.f, 0.f, -m.grav[0], -m.grav[1], -m.grav[2]};
       pass_inertia(time, aroot, k == n - 1 && m.n_wc > 0);   /* ctrl is left as the team path leaves it */
-      int bad = pass_accel(aroot, row_joints, row_xfrc);
+      /* float offsets of the rows inside the environment's log (environment strides are
+       * multiples of 4 floats): they decide where 16-byte stores are aligned */
+      const int jpar = (int)((row*(long long)(m.n_joints*m.joint_cols)) & 3);
+      const int xpar = (int)((row*(long long)(m.n_xfrc*6)) & 3);
+      int bad = pass_accel(aroot, row_joints, row_xfrc, jpar, xpar);
       /* no contact is active on this path: the contacts rows are zero (sensors.pyx:140-190) */
       for (int i = 0; i < m.n_contacts*3; i++) fb_st4(row_contacts + 4*i, 0.f, 0.f, 0.f, 0.f);
       if (bad) FB_FLAG_OR(P.flags + env, FB_FLAG_NONFINITE);

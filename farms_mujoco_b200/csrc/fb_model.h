@@ -51,23 +51,54 @@ struct DevOffsets {
   int wc_amp, wc_freq, wc_lag, wc_off;
   int key_qpos, key_qvel;
   /* tables of the environment-per-thread path (fb_fast.h) */
-  int ft_flags, ft_slot, ft_pslot, ft_link, ft_fj, ft_swim, ft_chkstart, ft_actwc;   /* ints */
-  int ft_dpos, ft_inertia, ft_hloc, ft_chk;                                          /* floats */
+  int ft_actwc;   /* int   [nu] wave index of an actuator, -1 */
+  int ft_chk;     /* float [nchk][4] conservative plane checks (normal, offset) */
 };
 
-/* environment-per-thread path: per-environment shared-memory layout, in floats;
- * element i of an array lives at (off + i)*BLOCK + thread (fb_fast.h) */
+/* ---- environment-per-thread path (fb_fast.h) ------------------------------------ */
+#define FB_FAST_MAXBODY 64
+/* flags of FastRec */
+#define FT_ADD_CARRY 1      /* child b+1 hands its articulated inertia over in registers */
+#define FT_HAS_SLOT 2       /* has children that are not b+1: they accumulate into slot `slot` */
+#define FT_TO_CARRY 4       /* parent is b-1 */
+#define FT_FIRST_WRITER 8   /* first child (descending order) to write the parent's slot */
+#define FT_LIMITED 16
+#define FT_ACT_SIMPLE 32    /* unclamped actuators, gear 1, all logged: one linear form */
+#define FT_HAS_WAVE 64
+#define FT_HAS_JPOS 128
+
+/* Everything the recursion needs about one body, resolved at model build: no index
+ * chasing in the kernel.  The table travels in the kernel parameters (constant bank),
+ * so every lane of a warp reads it with uniform, hoistable loads.  72 words. */
+struct FastRec {
+  int32_t parent, jtype, qa, da;          /* joint type -1: welded; qa/da: qpos/qvel address */
+  int32_t flags, slot, pslot, link;       /* link: farms link row, -1 */
+  int32_t fj, xr, swim, jid;              /* farms joint row, xfrc row, swim index, joint id */
+  int32_t chk0, chk1, wave_act, pad0;     /* plane-check range; ctrl index the wave writes */
+  float dpos[3], mass;                    /* body_pos - jnt_pos(parent); body mass */
+  float bquat[4];
+  float axis[3], qpos0;
+  float jpos[3], margin;
+  float lo, hi, stiffness, damping;
+  float armature, Kq, Kqd, T0;            /* simple actuation: T0 + Kq q + Kqd qd (+ ctrl terms) */
+  float hloc[3], wgain;                   /* com - anchor (body axes); gear*gain of the wave actuator */
+  float Ib[6], wfreq, wlag;               /* inertia about the com, body axes (xx yy zz xy xz yz) */
+  float wamp, woff, lift, height;         /* lift = 1000*9.81*mass/density (drag.pyx:142-145) */
+  float coef[6], KqU, KqdU;               /* KqU/KqdU/T0U: the part of the actuation that the */
+  float T0U, nchk_pad[3];                 /* farms joint_torque column does not log */
+  float chk[4];                           /* first conservative plane check (normal, offset) */
+};
+
+/* per-environment shared-memory layout, in floats; element i of an environment lives at
+ * i*BLOCK + thread.  One block of FB_NF floats per moving body, then the floating
+ * root's qpos/qvel, then the accumulation slots. */
+enum { FB_QUAT = 0, FB_ORG = 4, FB_VEL = 7, FB_W = 13, FB_U = 19, FB_DINV = 20, FB_TRQ = 21,
+       FB_Q = 22, FB_QD = 23, FB_TC = 24, FB_TU = 25, FB_NF = 26 };
 struct DevFastLayout {
   int ok;          /* 1 when the model fits the path's subset */
-  int qpos, qvel, quat, org, vel, wrench, u, dinv, trq, slots;
-  int nslot, n_float, any_jpos;
+  int body0, root0, slots;
+  int nslot, n_float;
 };
-
-/* ft_flags bits */
-#define FT_ADD_CARRY 1    /* child b+1 hands its articulated inertia over in registers */
-#define FT_HAS_SLOT 2     /* has children that are not b+1: they accumulate into slot ft_slot[b] */
-#define FT_TO_CARRY 4     /* parent is b-1 */
-#define FT_FIRST_WRITER 8 /* first child (descending order) to write the parent's slot */
 
 /* per-environment shared-memory layout (float offsets; component-major SoA:
  * element (k, i) of an array with N items lives at off + k*N + i) */
@@ -108,6 +139,7 @@ struct FbHostModel {
   std::vector<int32_t> I;
   std::vector<float> F;
   DevModel m;  /* I/F pointers left null; the caller patches them */
+  std::vector<FastRec> rec;   /* [nbody] when m.X.ok */
   std::string error;
 };
 
@@ -463,84 +495,148 @@ inline bool fb_build_model(const FbModel *fm, const FbFarms *ff, const FbWaveCon
   o.key_qvel = put_f(F, vd(fm->key_qvel, nv));
 
 
-  /* ---- environment-per-thread path (fb_fast.h): articulated-body recursion tables */
+  /* ---- environment-per-thread path (fb_fast.h): articulated-body recursion records */
   {
     DevFastLayout &X = m.X;
-    X.ok = 1;
-    std::vector<int32_t> flags(nb, 0), slot(nb, -1), pslot(nb, -1), blink(nb, -1), bfj(nb, -1),
-        bswim(nb, -1), chkstart(nb + 1, 0), actwc(nu > 0 ? nu : 1, -1);
-    std::vector<double> dpos(3*nb, 0.0), inertia(6*nb, 0.0), hloc(3*nb, 0.0), chk;
+    X.ok = nb <= FB_FAST_MAXBODY;
+    std::vector<FastRec> &rec = out.rec;
+    rec.assign(nb, FastRec());
+    std::memset(rec.data(), 0, sizeof(FastRec)*nb);
+    std::vector<int32_t> actwc(nu > 0 ? nu : 1, -1);
+    std::vector<double> chk;
+    if (wc) for (int i = 0; i < wc->n; i++) {
+      int a = wc->actuator[i];
+      if (a < 0 || a >= nu || actwc[a] >= 0) X.ok = 0; else actwc[a] = i;
+    }
     int nslot = 0;
-    X.any_jpos = 0;
+    for (int b = 0; b < nb; b++) { rec[b].slot = rec[b].pslot = rec[b].link = rec[b].fj = rec[b].xr = rec[b].swim = -1; rec[b].jtype = -1; rec[b].jid = -1; rec[b].wave_act = -1; }
     for (int b = 1; b < nb; b++) {
+      FastRec &r = rec[b];
       int p = fm->body_parentid[b], dn = fm->body_dofnum[b], jid = fm->body_jntid[b];
       int jt = jid >= 0 ? fm->jnt_type[jid] : -1;
       if (!(dn == 0 || (dn == 1 && (jt == FB_JNT_HINGE || jt == FB_JNT_SLIDE)) ||
             (dn == 6 && jt == FB_JNT_FREE && p == 0 && b == 1)))
         X.ok = 0;
+      if (dn == 0) jid = -1, jt = -1;
+      r.parent = p; r.jtype = jt; r.jid = jid;
+      r.qa = jid >= 0 ? fm->jnt_qposadr[jid] : 0;
+      r.da = jid >= 0 ? fm->jnt_dofadr[jid] : 0;
       if (jt == FB_JNT_FREE)
         for (int k = 0; k < 6; k++)
-          if (fm->dof_damping[fm->jnt_dofadr[jid] + k] != 0 || fm->dof_armature[fm->jnt_dofadr[jid] + k] != 0)
-            X.ok = 0;
+          if (fm->dof_damping[r.da + k] != 0 || fm->dof_armature[r.da + k] != 0) X.ok = 0;
       double jp[3] = {0, 0, 0}, pjp[3] = {0, 0, 0};
       if (jid >= 0 && jt != FB_JNT_FREE) for (int k = 0; k < 3; k++) jp[k] = fm->jnt_pos[3*jid + k];
-      int pj = fm->body_jntid[p];
+      int pj = fm->body_dofnum[p] > 0 ? fm->body_jntid[p] : -1;
       if (p > 0 && pj >= 0 && fm->jnt_type[pj] != FB_JNT_FREE) for (int k = 0; k < 3; k++) pjp[k] = fm->jnt_pos[3*pj + k];
       for (int k = 0; k < 3; k++) {
-        if (jp[k] != 0) X.any_jpos = 1;
-        dpos[3*b + k] = fm->body_pos[3*b + k] - pjp[k];
-        hloc[3*b + k] = fm->body_ipos[3*b + k] - jp[k];
+        if (jp[k] != 0) r.flags |= FT_HAS_JPOS;
+        r.dpos[k] = (float)(fm->body_pos[3*b + k] - pjp[k]);
+        r.hloc[k] = (float)(fm->body_ipos[3*b + k] - jp[k]);
+        r.jpos[k] = (float)jp[k];
       }
+      for (int k = 0; k < 4; k++) r.bquat[k] = (float)fm->body_quat[4*b + k];
+      r.mass = (float)fm->body_mass[b];
       /* body inertia about its com in body axes: Riq diag(I) Riq' as xx yy zz xy xz yz */
       double R[9];
       quat2mat(fm->body_iquat + 4*b, R);
       const double *I3 = fm->body_inertia + 3*b;
       auto el = [&](int i, int j) { return R[3*i]*R[3*j]*I3[0] + R[3*i+1]*R[3*j+1]*I3[1] + R[3*i+2]*R[3*j+2]*I3[2]; };
-      inertia[6*b] = el(0, 0); inertia[6*b+1] = el(1, 1); inertia[6*b+2] = el(2, 2);
-      inertia[6*b+3] = el(0, 1); inertia[6*b+4] = el(0, 2); inertia[6*b+5] = el(1, 2);
-      if (p == b - 1) { flags[b] |= FT_TO_CARRY; if (p > 0) flags[p] |= FT_ADD_CARRY; }
-      else if (p > 0 && slot[p] < 0) { slot[p] = nslot++; flags[p] |= FT_HAS_SLOT; }
-      if (p != b - 1 && p > 0) pslot[b] = slot[p];
+      r.Ib[0] = (float)el(0, 0); r.Ib[1] = (float)el(1, 1); r.Ib[2] = (float)el(2, 2);
+      r.Ib[3] = (float)el(0, 1); r.Ib[4] = (float)el(0, 2); r.Ib[5] = (float)el(1, 2);
+      if (p == b - 1) { r.flags |= FT_TO_CARRY; if (p > 0) rec[p].flags |= FT_ADD_CARRY; }
+      else if (p > 0 && rec[p].slot < 0) { rec[p].slot = nslot++; rec[p].flags |= FT_HAS_SLOT; }
+      if (p != b - 1 && p > 0) r.pslot = rec[p].slot;
+      if (jid >= 0 && jt != FB_JNT_FREE) {
+        for (int k = 0; k < 3; k++) r.axis[k] = (float)fm->jnt_axis[3*jid + k];
+        r.qpos0 = (float)fm->qpos0[r.qa];
+        r.margin = (float)fm->jnt_margin[jid];
+        r.lo = (float)fm->jnt_range[2*jid]; r.hi = (float)fm->jnt_range[2*jid + 1];
+        if (fm->jnt_limited[jid]) r.flags |= FT_LIMITED;
+        r.stiffness = (float)fm->jnt_stiffness[jid];
+        r.damping = (float)fm->dof_damping[r.da];
+        r.armature = (float)fm->dof_armature[r.da];
+      }
     }
     /* descending order: the first child to reach a slot stores, the others accumulate */
     {
       std::vector<int> seen(nslot > 0 ? nslot : 1, 0);
       for (int b = nb - 1; b > 0; b--)
-        if (pslot[b] >= 0 && !seen[pslot[b]]) { seen[pslot[b]] = 1; flags[b] |= FT_FIRST_WRITER; }
+        if (rec[b].pslot >= 0 && !seen[rec[b].pslot]) { seen[rec[b].pslot] = 1; rec[b].flags |= FT_FIRST_WRITER; }
     }
     for (int l = 0; l < m.n_links; l++) {
       int b = ff->link_body[l];
-      if (b < 1 || b >= nb || blink[b] >= 0) X.ok = 0; else blink[b] = l;
+      if (b < 1 || b >= nb || rec[b].link >= 0) X.ok = 0; else rec[b].link = l;
     }
     for (int j = 0; j < m.n_joints; j++) {
       int jid = ff->joint_jntid[j];
       /* the row reads qpos/qvel of its own joint and sits on that joint's body */
       if (jid < 0 || jid >= nj || fm->jnt_type[jid] == FB_JNT_FREE || ff->joint_qposadr[j] != fm->jnt_qposadr[jid] ||
-          ff->joint_dofadr[j] != fm->jnt_dofadr[jid] || bfj[fm->jnt_bodyid[jid]] >= 0) { X.ok = 0; continue; }
-      bfj[fm->jnt_bodyid[jid]] = j;
+          ff->joint_dofadr[j] != fm->jnt_dofadr[jid] || rec[fm->jnt_bodyid[jid]].fj >= 0) { X.ok = 0; continue; }
+      rec[fm->jnt_bodyid[jid]].fj = j;
+    }
+    for (int x = 0; x < m.n_xfrc; x++) {
+      int b = ff->xfrc_body[x];
+      if (b < 1 || rec[b].xr >= 0) X.ok = 0; else rec[b].xr = x;
     }
     for (int i = 0; i < m.n_swim; i++) {
       int l = ff->swim_links_index[i], xi = ff->swim_xfrc_index[i];
       if (l < 0 || l >= m.n_links || xi < 0 || xi >= m.n_xfrc) { X.ok = 0; continue; }
       int b = ff->link_body[l];
-      if (ff->xfrc_body[xi] != b || b < 1 || b >= nb || bswim[b] >= 0) { X.ok = 0; continue; }
-      bswim[b] = i;
+      if (ff->xfrc_body[xi] != b || b < 1 || b >= nb || rec[b].swim >= 0 || rec[b].xr != xi) { X.ok = 0; continue; }
+      rec[b].swim = i;
+      rec[b].lift = (float)(1000.0*9.81*ff->swim_mass[i]/ff->swim_density[i]);
+      if (!(ff->swim_mass[i] > 0)) rec[b].lift = 0.f;
+      rec[b].height = (float)ff->swim_height[i];
+      for (int k = 0; k < 6; k++) rec[b].coef[k] = (float)ff->swim_coefficients[6*i + k];
     }
-    if (wc) for (int i = 0; i < wc->n; i++) {
-      int a = wc->actuator[i];
-      if (a < 0 || a >= nu || actwc[a] >= 0) X.ok = 0; else actwc[a] = i;
+    /* actuation: one linear form per joint when nothing clamps, gears are 1 and the farms
+     * joint_torque column sums exactly the joint's actuators (physics.py:510-524) */
+    for (int b = 1; b < nb; b++) {
+      FastRec &r = rec[b];
+      if (r.jid < 0 || r.jtype == FB_JNT_FREE) continue;
+      bool simple = true;
+      int nwave = 0;
+      double Kq = 0, Kqd = 0, T0 = 0, KqU = 0, KqdU = 0, T0U = 0;
+      for (int a = 0; a < nu; a++) {
+        if (fm->actuator_trnid[a] != r.jid) continue;
+        if (fm->actuator_ctrllimited[a] || fm->actuator_forcelimited[a] || fm->actuator_gear[a] != 1.0) simple = false;
+        bool logged = r.fj >= 0 && (ff->joint_act_position[r.fj] == a || ff->joint_act_velocity[r.fj] == a ||
+                                    ff->joint_act_torque[r.fj] == a);
+        T0 += fm->actuator_biasprm[3*a]; Kq += fm->actuator_biasprm[3*a + 1]; Kqd += fm->actuator_biasprm[3*a + 2];
+        if (!logged) {
+          T0U += fm->actuator_biasprm[3*a]; KqU += fm->actuator_biasprm[3*a + 1]; KqdU += fm->actuator_biasprm[3*a + 2];
+        }
+        if (actwc[a] >= 0) {
+          int w = actwc[a];
+          nwave++;
+          if (!logged && r.fj >= 0) simple = false;
+          r.wave_act = a;
+          r.wgain = (float)fm->actuator_gainprm[3*a];
+          r.wamp = (float)wc->amplitude[w]; r.woff = (float)(wc->offset ? wc->offset[w] : 0.0);
+          r.wfreq = (float)wc->frequency[w]; r.wlag = (float)wc->phase_lag[w];
+        }
+      }
+      if (nwave > 1) simple = false;
+      if (simple) {
+        r.flags |= FT_ACT_SIMPLE;
+        if (nwave == 1) r.flags |= FT_HAS_WAVE;
+        r.Kq = (float)Kq; r.Kqd = (float)Kqd; r.T0 = (float)T0;
+        r.KqU = (float)KqU; r.KqdU = (float)KqdU; r.T0U = (float)T0U;
+      } else {
+        r.wave_act = -1;
+      }
     }
     /* conservative plane checks per body: no candidate of the body can be active while
      * n.xpos - pd >= reach, reach = max(|lpos| + radius + margin - gap) over its candidates */
     for (int b = 0; b < nb; b++) {
-      chkstart[b] = (int)chk.size()/4;
+      rec[b].chk0 = (int)chk.size()/4;
       for (int c = 0; c < nc; c++) {
         if (cbody[c] != b) continue;
         double r = std::sqrt(lpos[3*c]*lpos[3*c] + lpos[3*c+1]*lpos[3*c+1] + lpos[3*c+2]*lpos[3*c+2])
                    + rad[c] + fm->cand_margin[c] - fm->cand_gap[c];
         r *= 1.0 + 1e-5; r += 1e-6;
         bool merged = false;
-        for (size_t t = (size_t)chkstart[b]; t < chk.size()/4; t++)
+        for (size_t t = (size_t)rec[b].chk0; t < chk.size()/4; t++)
           if (chk[4*t] == pn[3*c] && chk[4*t+1] == pn[3*c+1] && chk[4*t+2] == pn[3*c+2]) {
             /* same plane normal: keep the larger offset */
             if (pd[c] + r > chk[4*t+3]) chk[4*t+3] = pd[c] + r;
@@ -549,21 +645,21 @@ inline bool fb_build_model(const FbModel *fm, const FbFarms *ff, const FbWaveCon
           }
         if (!merged) { chk.push_back(pn[3*c]); chk.push_back(pn[3*c+1]); chk.push_back(pn[3*c+2]); chk.push_back(pd[c] + r); }
       }
+      rec[b].chk1 = (int)chk.size()/4;
+      /* the first check travels in the record; chk0..chk1 are the remaining ones */
+      rec[b].chk[0] = rec[b].chk[1] = rec[b].chk[2] = 0.f; rec[b].chk[3] = -1e30f;
+      if (rec[b].chk1 > rec[b].chk0) {
+        for (int k = 0; k < 4; k++) rec[b].chk[k] = (float)chk[4*(size_t)rec[b].chk0 + k];
+        rec[b].chk0++;
+      }
     }
-    chkstart[nb] = (int)chk.size()/4;
-    o.ft_flags = put_i(I, flags); o.ft_slot = put_i(I, slot); o.ft_pslot = put_i(I, pslot);
-    o.ft_link = put_i(I, blink); o.ft_fj = put_i(I, bfj); o.ft_swim = put_i(I, bswim);
-    o.ft_chkstart = put_i(I, chkstart); o.ft_actwc = put_i(I, actwc);
-    o.ft_dpos = put_f(F, dpos); o.ft_inertia = put_f(F, inertia); o.ft_hloc = put_f(F, hloc);
+    o.ft_actwc = put_i(I, actwc);
     o.ft_chk = put_f(F, chk);
-    int foff = 0;
-    auto ftake = [&foff](int n) { int r = foff; foff += n; return r; };
-    X.qpos = ftake(fm->nq); X.qvel = ftake(nv);
-    X.quat = ftake(4*nb); X.org = ftake(3*nb); X.vel = ftake(6*nb); X.wrench = ftake(6*nb);
-    X.u = ftake(nb); X.dinv = ftake(nb); X.trq = ftake(nb);
-    X.slots = ftake(27*nslot);
+    X.body0 = 0;
+    X.root0 = FB_NF*(nb - 1);
+    X.slots = X.root0 + 13;
     X.nslot = nslot;
-    X.n_float = foff;
+    X.n_float = X.slots + 27*nslot;
   }
 
   /* water + units */

@@ -313,7 +313,11 @@ class BatchedPhysics:
                 out[kind] = np.zeros(shape if env is None else shape[1:], dtype=np.float32)
                 continue
             if env is None:
-                out[kind] = self._read(ptr, (self.n_envs, self.buffer_size, n_items, cols))
+                # the environment stride may be padded (16-byte alignment of the rows)
+                flat = self._read(ptr, (self.n_envs, int(stride)))
+                used = self.buffer_size*n_items*cols
+                out[kind] = np.ascontiguousarray(flat[:, :used]).reshape(
+                    self.n_envs, self.buffer_size, n_items, cols)
             else:
                 base = _ptr(ptr) + 4*int(env)*int(stride)
                 out[kind] = self._read(base, (self.buffer_size, n_items, cols))

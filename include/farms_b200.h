@@ -118,7 +118,8 @@ typedef struct FbHandle FbHandle;
  *   contacts [n_envs][ring][n_contacts][12]
  *   xfrc     [n_envs][ring][n_xfrc    ][6]
  * i.e. log.<kind>_dev + env*<kind>_env_stride is exactly the reference's
- * data.sensors.<kind>.array ([buffer_size, n_items, n_cols], task.py:158). */
+ * data.sensors.<kind>.array ([buffer_size, n_items, n_cols], task.py:158).  The
+ * environment strides are rounded up to a multiple of 4 floats (16 bytes). */
 typedef struct FbLogView {
   float *links_dev, *joints_dev, *contacts_dev, *xfrc_dev;
   int64_t links_env_stride, joints_env_stride, contacts_env_stride, xfrc_env_stride; /* in floats */

@@ -99,7 +99,7 @@ def test_team_sizes_agree(cuda_library, team, name):
     holds at most 2*T bodies)."""
     spec, model, qpos0, qvel0, ctrl, physics = _run(cuda_library, name, 24, 5, team=team)
     assert physics.team_lanes == team
-    _compare(spec, model, physics, qpos0, qvel0, ctrl, [0, 23], 5, 1e-3)
+    _compare(spec, model, physics, qpos0, qvel0, ctrl, [0, 23], 5, 5e-3 if name != 'swimmer8' else 5e-4)
 
 
 def test_launch_split_is_invariant(cuda_library):
