@@ -1314,6 +1314,8 @@ struct FbParams {
    * from step 0. */
   int *pending, *pending_count, *steps_done;
   int use_pending, parity;
+  float *fast_scratch;            /* [n_scratch][fast_scratch_stride]: second half of the per-thread state */
+  long long fast_scratch_stride;
 };
 
 FB_DEV EnvPtrs fb_env_ptrs(const FbParams &P, int env) {

@@ -94,7 +94,8 @@ fb_fast_kernel(const __grid_constant__ FbFastParams Q) {
   const int env = blockIdx.x*BLK + threadIdx.x;
   if (blockIdx.x == 0 && threadIdx.x == 0) P.pending_count[P.parity ^ 1] = 0;   /* for the next launch */
   if (env >= P.n_envs) return;
-  FbFast<BLK> st(P, Q.rec, fb_smem + threadIdx.x, env);
+  /* thread t of the grid owns column t of the L2-resident scratch */
+  FbFast<BLK> st(P, Q.rec, fb_smem + threadIdx.x, P.fast_scratch + env, (size_t)P.fast_scratch_stride, env);
   const int done = st.run();
   if (done < P.n_steps) {
     P.steps_done[env] = done;
@@ -257,9 +258,9 @@ static int launch(FbHandle *h, int mode, int n_steps, int want_derived) {
   const DevModel &m = P.m;
   if (use_fast) {
     P.pending_count[P.parity ^ 1] = 0;
-    std::vector<float> fs((size_t)m.X.n_float + 8, 0.f);
+    std::vector<float> fs((size_t)m.X.n_float + 8, 0.f), fg((size_t)m.X.n_scratch + 8, 0.f);
     for (int env = 0; env < P.n_envs; env++) {
-      FbFast<1> st(P, h->hm.rec.data(), fs.data(), env);
+      FbFast<1> st(P, h->hm.rec.data(), fs.data(), fg.data(), 1, env);
       int done = st.run();
       if (done < n_steps) { P.steps_done[env] = done; P.pending[P.pending_count[P.parity]++] = env; }
     }
@@ -278,8 +279,7 @@ static int launch(FbHandle *h, int mode, int n_steps, int want_derived) {
   if (use_fast) {
     int fblocks = (P.n_envs + h->fast_block - 1)/h->fast_block;
     h->fastQ->P = P;
-    if (h->fast_block == 64) fb_fast_kernel<64><<<fblocks, 64, h->fast_smem_bytes, h->stream>>>(*h->fastQ);
-    else fb_fast_kernel<32><<<fblocks, 32, h->fast_smem_bytes, h->stream>>>(*h->fastQ);
+    fb_fast_kernel<32><<<fblocks, 32, h->fast_smem_bytes, h->stream>>>(*h->fastQ);
     h->launches++;
   }
   switch (h->team) {
@@ -374,18 +374,17 @@ int fb_create(const FbModel *model, const FbFarms *farms, int n_envs, int device
     default: ce = cudaFuncSetAttribute(fb_step_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_bytes); break;
   }
   if (ce != cudaSuccess) { fb_destroy(h); return fail(std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(ce)); }
-  /* environment-per-thread kernel: 64 environments per block when their working sets fit
-   * the SM's shared memory, else 32; models beyond that run on the team kernel alone */
+  /* environment-per-thread kernel: one warp (32 environments) per block, as many blocks per
+   * SM as their shared-memory working sets allow; models beyond that run on the team kernel */
   {
     size_t per_thread = (size_t)m.X.n_float*sizeof(float);
-    if (m.X.ok && per_thread*64 <= (size_t)max_smem) h->fast_block = 64;
-    else if (m.X.ok && per_thread*32 <= (size_t)max_smem) h->fast_block = 32;
-    else h->fast_enabled = 0;
+    h->fast_block = 32;
+    if (!m.X.ok || per_thread*32 > (size_t)max_smem) h->fast_enabled = 0;
     if (h->fast_enabled) {
       h->fast_smem_bytes = per_thread*h->fast_block;
-      ce = h->fast_block == 64
-          ? cudaFuncSetAttribute(fb_fast_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->fast_smem_bytes)
-          : cudaFuncSetAttribute(fb_fast_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->fast_smem_bytes);
+      ce = cudaFuncSetAttribute(fb_fast_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->fast_smem_bytes);
+      if (ce == cudaSuccess)
+        ce = cudaFuncSetAttribute(fb_fast_kernel<32>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
       if (ce != cudaSuccess) { fb_destroy(h); return fail(std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(ce)); }
     }
   }
@@ -409,6 +408,9 @@ int fb_create(const FbModel *model, const FbFarms *farms, int n_envs, int device
   bad |= alloc_arr(h, &P.qpos_spring, n*m.nq); bad |= alloc_arr(h, &P.env_phase, n);
   bad |= alloc_arr(h, &P.flags, n); bad |= alloc_arr(h, &P.iteration, n);
   bad |= alloc_arr(h, &P.pending, n); bad |= alloc_arr(h, &P.pending_count, 2); bad |= alloc_arr(h, &P.steps_done, n);
+  P.fast_scratch_stride = (long long)((n + 31) & ~(size_t)31);
+  P.fast_scratch = nullptr;
+  if (m.X.ok) bad |= alloc_arr(h, &P.fast_scratch, (size_t)P.fast_scratch_stride*(m.X.n_scratch > 0 ? m.X.n_scratch : 1));
   bad |= alloc_arr(h, &P.d_xpos, n*3*nb); bad |= alloc_arr(h, &P.d_xquat, n*4*nb);
   bad |= alloc_arr(h, &P.d_xipos, n*3*nb); bad |= alloc_arr(h, &P.d_linvel, n*3*nb);
   bad |= alloc_arr(h, &P.d_angvel, n*3*nb); bad |= alloc_arr(h, &P.d_actf, n*nu);

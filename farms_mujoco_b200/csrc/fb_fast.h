@@ -42,10 +42,12 @@
 FB_DEV void fb_st4(float *p, float a, float b, float c, float d) { p[0] = a; p[1] = b; p[2] = c; p[3] = d; }
 FB_DEV void fb_st2(float *p, float a, float b) { p[0] = a; p[1] = b; }
 #else
+/* log rows are written once and not read back by the step: streaming (evict-first) stores
+ * keep them from pushing the L2-resident scratch out */
 FB_DEV void fb_st4(float *p, float a, float b, float c, float d) {
-  *reinterpret_cast<float4 *>(p) = make_float4(a, b, c, d);
+  __stcs(reinterpret_cast<float4 *>(p), make_float4(a, b, c, d));
 }
-FB_DEV void fb_st2(float *p, float a, float b) { *reinterpret_cast<float2 *>(p) = make_float2(a, b); }
+FB_DEV void fb_st2(float *p, float a, float b) { __stcs(reinterpret_cast<float2 *>(p), make_float2(a, b)); }
 #endif
 
 /* articulated inertia about a point, world axes:  [ A  H ] [w]   A, M symmetric
@@ -148,8 +150,13 @@ FB_UNROLL
 
 #ifdef FB_HOST_EMU
 FB_DEV float fb_rcp(float x) { return 1.0f/x; }
+FB_DEV float fb_ld_scr(const float *p) { return *p; }
+FB_DEV void fb_st_scr(float *p, float v) { *p = v; }
 #else
 FB_DEV float fb_rcp(float x) { return __frcp_rn(x); }
+/* the scratch lives in L2: bypass L1 both ways */
+FB_DEV float fb_ld_scr(const float *p) { return __ldcg(p); }
+FB_DEV void fb_st_scr(float *p, float v) { __stcg(p, v); }
 #endif
 
 template <int BLK> struct FbFast {
@@ -158,17 +165,22 @@ template <int BLK> struct FbFast {
   const FastRec *rec; /* [nbody], constant bank (kernel parameters) */
   float *s;           /* shared floats, already offset by the thread index */
   const int env;
+  float *gs;          /* global scratch of this thread (stride GS floats between elements) */
+  const size_t GS;
   float env_phase;
+  float rt[13];       /* floating root: qpos[7], qvel[6] (registers) */
   float rootpos[3];   /* world position the anchors are measured from (the floating root) */
 
-  FB_MEM FbFast(const FbParams &P_, const FastRec *rec_, float *s_, int env_)
-      : P(P_), m(P_.m), rec(rec_), s(s_), env(env_) {
+  FB_MEM FbFast(const FbParams &P_, const FastRec *rec_, float *s_, float *gs_, size_t GS_, int env_)
+      : P(P_), m(P_.m), rec(rec_), s(s_), env(env_), gs(gs_), GS(GS_) {
     env_phase = P.env_phase[env];
     rootpos[0] = rootpos[1] = rootpos[2] = 0.f;
+FB_UNROLL
+    for (int k = 0; k < 13; k++) rt[k] = 0.f;
   }
 
   FB_MEM float *block(int b) const { return s + (m.X.body0 + FB_NF*(b - 1))*BLK; }
-  FB_MEM float &root(int i) const { return s[(m.X.root0 + i)*BLK]; }
+  FB_MEM float *gblock(int b) const { return gs + (size_t)(FG_NF*(b - 1))*GS; }
   FB_MEM float *slot(int i) const { return s + (m.X.slots + 27*i)*BLK; }
 
   /* generic actuation (clamps, gears, partial logging): force sum and farms joint_torque */
@@ -208,13 +220,15 @@ template <int BLK> struct FbFast {
     const float *g_ctrl = P.ctrl + (size_t)env*(m.nu > 0 ? m.nu : 1);
     for (int b = 1; b < m.nbody; b++) {
       const FastRec &rc = rec[b];
-      float *pb = block(b);
+      float *pg = gblock(b);
       if (rc.jtype == FB_JNT_FREE) {
-        for (int k = 0; k < 7; k++) root(k) = gq[rc.qa + k];
-        for (int k = 0; k < 6; k++) root(7 + k) = gv[rc.da + k];
+FB_UNROLL
+        for (int k = 0; k < 7; k++) rt[k] = gq[rc.qa + k];
+FB_UNROLL
+        for (int k = 0; k < 6; k++) rt[7 + k] = gv[rc.da + k];
       } else if (rc.jtype >= 0) {
-        pb[FB_Q*BLK] = gq[rc.qa];
-        pb[FB_QD*BLK] = gv[rc.da];
+        pg[FG_Q*GS] = gq[rc.qa];
+        pg[FG_QD*GS] = gv[rc.da];
         /* constant part of the joint's actuation over this launch (ctrl is held), and of
          * the actuators the farms joint_torque column leaves out */
         float tc = rc.T0, tu = rc.T0U;
@@ -229,10 +243,10 @@ template <int BLK> struct FbFast {
             if (!(a == ap || a == av || a == at)) tu += f;
           }
         }
-        pb[FB_TC*BLK] = tc;
-        pb[FB_TU*BLK] = tu;
+        pg[FG_TC*GS] = tc;
+        pg[FG_TU*GS] = tu;
       }
-      for (int k = 0; k < 6; k++) pb[(FB_W + k)*BLK] = gx[6*b + k];
+      for (int k = 0; k < 6; k++) pg[(FG_W + k)*GS] = gx[6*b + k];
     }
   }
 
@@ -241,15 +255,17 @@ template <int BLK> struct FbFast {
     float *gx = P.xfrc_applied + (size_t)env*6*m.nbody;
     for (int b = 1; b < m.nbody; b++) {
       const FastRec &rc = rec[b];
-      const float *pb = block(b);
+      const float *pg = gblock(b);
       if (rc.jtype == FB_JNT_FREE) {
-        for (int k = 0; k < 7; k++) gq[rc.qa + k] = root(k);
-        for (int k = 0; k < 6; k++) gv[rc.da + k] = root(7 + k);
+FB_UNROLL
+        for (int k = 0; k < 7; k++) gq[rc.qa + k] = rt[k];
+FB_UNROLL
+        for (int k = 0; k < 6; k++) gv[rc.da + k] = rt[7 + k];
       } else if (rc.jtype >= 0) {
-        gq[rc.qa] = pb[FB_Q*BLK];
-        gv[rc.da] = pb[FB_QD*BLK];
+        gq[rc.qa] = pg[FG_Q*GS];
+        gv[rc.da] = pg[FG_QD*GS];
       }
-      for (int k = 0; k < 6; k++) gx[6*b + k] = pb[(FB_W + k)*BLK];
+      for (int k = 0; k < 6; k++) gx[6*b + k] = pg[(FG_W + k)*GS];
     }
     P.iteration[env] = iteration;
   }
@@ -259,20 +275,24 @@ template <int BLK> struct FbFast {
   FB_MEM int pass_poses(float *row_links) {
     const int nb = m.nbody;
     int active = 0;
+    /* scratch values are fetched one body ahead: the L2 round trip overlaps the arithmetic */
+    float nq = fb_ld_scr(gblock(1) + FG_Q*GS), nqd = fb_ld_scr(gblock(1) + FG_QD*GS);
     for (int b = 1; b < nb; b++) {
       const FastRec &rc = rec[b];
       float *pb = block(b);
+      const float cq = nq, cqd = nqd;
+      if (b + 1 < nb) { const float *pn = gblock(b + 1); nq = fb_ld_scr(pn + FG_Q*GS); nqd = fb_ld_scr(pn + FG_QD*GS); }
       const int jtype = rc.jtype;
       Quat q;
       float o[3], v[6], R[9];
       if (jtype == FB_JNT_FREE) {
-        Quat qq = {root(3), root(4), root(5), root(6)};
+        Quat qq = {rt[3], rt[4], rt[5], rt[6]};
         q = q_normalize(qq);
-        root(3) = q.w; root(4) = q.x; root(5) = q.y; root(6) = q.z;
+        rt[3] = q.w; rt[4] = q.x; rt[5] = q.y; rt[6] = q.z;
         q_mat(q, R);
 FB_UNROLL
-        for (int k = 0; k < 3; k++) { rootpos[k] = root(k); o[k] = 0.f; v[3 + k] = root(7 + k); }
-        m_rot(R, root(10), root(11), root(12), v);
+        for (int k = 0; k < 3; k++) { rootpos[k] = rt[k]; o[k] = 0.f; v[3 + k] = rt[7 + k]; }
+        m_rot(R, rt[10], rt[11], rt[12], v);
       } else {
         Quat qp = {1.f, 0.f, 0.f, 0.f};
         float op[3] = {0.f, 0.f, 0.f}, vp[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
@@ -296,8 +316,8 @@ FB_UNROLL
           r[0] += t[0]; r[1] += t[1]; r[2] += t[2];
         }
         if (jtype >= 0) {
-          const float qj = pb[FB_Q*BLK];
-          qd = pb[FB_QD*BLK];
+          const float qj = cq;
+          qd = cqd;
           dq = qj - rc.qpos0;
           if (jtype == FB_JNT_HINGE) {
             float sn, cs;
@@ -362,15 +382,34 @@ FB_UNROLL
     for (int k = 0; k < 6; k++) { C.A[k] = 0.f; C.M[k] = 0.f; pc[k] = 0.f; }
 FB_UNROLL
     for (int k = 0; k < 9; k++) C.H[k] = 0.f;
+    float nx[10];        /* W[6], q, qd, tc, tu of the next body to visit */
+    {
+      const float *pn = gblock(nb - 1);
+FB_UNROLL
+      for (int k = 0; k < 6; k++) nx[k] = fb_ld_scr(pn + (FG_W + k)*GS);
+      nx[6] = fb_ld_scr(pn + FG_Q*GS); nx[7] = fb_ld_scr(pn + FG_QD*GS);
+      nx[8] = fb_ld_scr(pn + FG_TC*GS); nx[9] = fb_ld_scr(pn + FG_TU*GS);
+    }
     for (int b = nb - 1; b >= 1; b--) {
       const FastRec &rc = rec[b];
       float *pb = block(b);
+      float *pg = gblock(b);
       const int jtype = rc.jtype, flags = rc.flags;
+      float cx[10];
+FB_UNROLL
+      for (int k = 0; k < 10; k++) cx[k] = nx[k];
+      if (b > 1) {
+        const float *pn = gblock(b - 1);
+FB_UNROLL
+        for (int k = 0; k < 6; k++) nx[k] = fb_ld_scr(pn + (FG_W + k)*GS);
+        nx[6] = fb_ld_scr(pn + FG_Q*GS); nx[7] = fb_ld_scr(pn + FG_QD*GS);
+        nx[8] = fb_ld_scr(pn + FG_TC*GS); nx[9] = fb_ld_scr(pn + FG_TU*GS);
+      }
       const Quat q = {pb[(FB_QUAT)*BLK], pb[(FB_QUAT + 1)*BLK], pb[(FB_QUAT + 2)*BLK], pb[(FB_QUAT + 3)*BLK]};
       float R[9], v[6], fx[6];
       q_mat(q, R);
 FB_UNROLL
-      for (int k = 0; k < 6; k++) { v[k] = pb[(FB_VEL + k)*BLK]; fx[k] = pb[(FB_W + k)*BLK]; }
+      for (int k = 0; k < 6; k++) { v[k] = pb[(FB_VEL + k)*BLK]; fx[k] = cx[k]; }
       /* rigid-body inertia about the anchor */
       const float mass = rc.mass;
       float h[3], Iw[6];
@@ -450,18 +489,18 @@ FB_UNROLL
         continue;
       }
       if (jtype >= 0) {
-        const float qj = pb[FB_Q*BLK], qd = pb[FB_QD*BLK];
+        const float qj = cx[6], qd = cx[7];
         float ax[3], U[6], c[6], tau, trq;
         m_rot(R, rc.axis[0], rc.axis[1], rc.axis[2], ax);
         if (flags & FT_ACT_SIMPLE) {
-          tau = pb[FB_TC*BLK] + rc.Kq*qj + rc.Kqd*qd;
+          tau = cx[8] + rc.Kq*qj + rc.Kqd*qd;
           if (flags & FT_HAS_WAVE) {
             float ph = 6.283185307179586f*rc.wfreq*time - rc.wlag + env_phase;
             float cw = rc.woff + rc.wamp*sinf(ph);
             tau += rc.wgain*cw;
             if (store_ctrl) P.ctrl[(size_t)env*m.nu + rc.wave_act] = cw;
           }
-          trq = tau - (pb[FB_TU*BLK] + rc.KqU*qj + rc.KqdU*qd);
+          trq = tau - (cx[9] + rc.KqU*qj + rc.KqdU*qd);
         } else {
           actuation_generic(rc, qj, qd, time, store_ctrl, &tau, &trq);
         }
@@ -505,8 +544,8 @@ FB_UNROLL
 FB_UNROLL
         for (int k = 0; k < 3; k++) pA[3 + k] += t0[k] + t1[k] + U[3 + k]*ud;
 FB_UNROLL
-        for (int k = 0; k < 6; k++) pb[(FB_W + k)*BLK] = U[k];
-        pb[FB_U*BLK] = u; pb[FB_DINV*BLK] = dinv; pb[FB_TRQ*BLK] = trq;
+        for (int k = 0; k < 6; k++) fb_st_scr(pg + (FG_W + k)*GS, U[k]);
+        fb_st_scr(pg + FG_U*GS, u); fb_st_scr(pg + FG_DINV*GS, dinv); fb_st_scr(pg + FG_TRQ*GS, trq);
       }
       if (rc.parent == 0) continue;        /* fixed base: nothing above */
       /* move to the parent's anchor and hand over */
@@ -544,10 +583,27 @@ FB_UNROLL
     const float hdt = m.timestep;
     float ac[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};   /* carry: acceleration of body b-1 */
     int bad = 0;
+    float nx[11];        /* U[6], u, 1/d, trq, q, qd of the next body to visit */
+    {
+      const float *pn = gblock(1);
+FB_UNROLL
+      for (int k = 0; k < 9; k++) nx[k] = fb_ld_scr(pn + (FG_W + k)*GS);     /* W, U, DINV, TRQ are contiguous */
+      nx[9] = fb_ld_scr(pn + FG_Q*GS); nx[10] = fb_ld_scr(pn + FG_QD*GS);
+    }
     for (int b = 1; b < nb; b++) {
       const FastRec &rc = rec[b];
       float *pb = block(b);
+      float *pg = gblock(b);
       const int jtype = rc.jtype, flags = rc.flags;
+      float cx[11];
+FB_UNROLL
+      for (int k = 0; k < 11; k++) cx[k] = nx[k];
+      if (b + 1 < nb) {
+        const float *pn = gblock(b + 1);
+FB_UNROLL
+        for (int k = 0; k < 9; k++) nx[k] = fb_ld_scr(pn + (FG_W + k)*GS);
+        nx[9] = fb_ld_scr(pn + FG_Q*GS); nx[10] = fb_ld_scr(pn + FG_QD*GS);
+      }
       const Quat q = {pb[(FB_QUAT)*BLK], pb[(FB_QUAT + 1)*BLK], pb[(FB_QUAT + 2)*BLK], pb[(FB_QUAT + 3)*BLK]};
       float R[9], v[6], a[6];
       q_mat(q, R);
@@ -561,19 +617,19 @@ FB_UNROLL
         m_rot_t(R, a[0], a[1], a[2], wl);
 FB_UNROLL
         for (int k = 0; k < 3; k++) {
-          float vn = root(7 + k) + hdt*(a[3 + k] + m.grav[k] + cr[k]);
-          root(7 + k) = vn;
-          float pn = root(k) + hdt*vn;
-          root(k) = pn;
-          w[k] = root(10 + k) + hdt*wl[k];
-          root(10 + k) = w[k];
+          float vn = rt[7 + k] + hdt*(a[3 + k] + m.grav[k] + cr[k]);
+          rt[7 + k] = vn;
+          float pn = rt[k] + hdt*vn;
+          rt[k] = pn;
+          w[k] = rt[10 + k] + hdt*wl[k];
+          rt[10 + k] = w[k];
           bad |= !(fabsf(pn) < 1e30f);
         }
         float angle = hdt*v_normalize3(w), sn, cs;
         fb_sincos(0.5f*angle, &sn, &cs);
         Quat qr = {cs, w[0]*sn, w[1]*sn, w[2]*sn};
         Quat qn = q_normalize(q_mul(q, qr));
-        root(3) = qn.w; root(4) = qn.x; root(5) = qn.y; root(6) = qn.z;
+        rt[3] = qn.w; rt[4] = qn.x; rt[5] = qn.y; rt[6] = qn.z;
         bad |= !(fabsf(qn.w) < 1e30f) | !(fabsf(qn.x) < 1e30f) | !(fabsf(qn.y) < 1e30f) | !(fabsf(qn.z) < 1e30f);
       } else {
         float ap[6] = {0.f, 0.f, 0.f, -m.grav[0], -m.grav[1], -m.grav[2]};
@@ -595,11 +651,11 @@ FB_UNROLL
 FB_UNROLL
         for (int k = 0; k < 3; k++) { a[k] = ap[k]; a[3 + k] = ap[3 + k] + cr[k]; }
         if (jtype >= 0) {
-          const float qj = pb[FB_Q*BLK], qd = pb[FB_QD*BLK];
+          const float qj = cx[9], qd = cx[10];
           float ax[3], U[6];
           m_rot(R, rc.axis[0], rc.axis[1], rc.axis[2], ax);
 FB_UNROLL
-          for (int k = 0; k < 6; k++) U[k] = pb[(FB_W + k)*BLK];
+          for (int k = 0; k < 6; k++) U[k] = cx[k];
           float aq[3] = {ax[0]*qd, ax[1]*qd, ax[2]*qd}, c[3];
           if (jtype == FB_JNT_HINGE) {
             v_cross(v, aq, c);
@@ -611,29 +667,36 @@ FB_UNROLL
             a[3] += c[0]; a[4] += c[1]; a[5] += c[2];
           }
           float ua = U[0]*a[0] + U[1]*a[1] + U[2]*a[2] + U[3]*a[3] + U[4]*a[4] + U[5]*a[5];
-          const float qdd = (pb[FB_U*BLK] - ua)*pb[FB_DINV*BLK];
+          const float qdd = (cx[6] - ua)*cx[7];
           if (jtype == FB_JNT_HINGE) { a[0] += ax[0]*qdd; a[1] += ax[1]*qdd; a[2] += ax[2]*qdd; }
           else { a[3] += ax[0]*qdd; a[4] += ax[1]*qdd; a[5] += ax[2]*qdd; }
           const float qdn = qd + hdt*qdd, qn = qj + hdt*qdn;
-          pb[FB_QD*BLK] = qdn;
-          pb[FB_Q*BLK] = qn;
+          fb_st_scr(pg + FG_QD*GS, qdn);
+          fb_st_scr(pg + FG_Q*GS, qn);
           bad |= !(fabsf(qn) < 1e30f);
           /* joints row: physics.py:481-524 (new position/velocity, forces of the old state) */
           if (rc.fj >= 0) {
             float *row = row_joints + m.joint_cols*rc.fj;
-            const float trq = pb[FB_TRQ*BLK]*m.inv_torques, jv = qdn*m.inv_angvel;
+            const float trq = cx[8]*m.inv_torques, jv = qdn*m.inv_angvel;
             const int cp = m.col_jpos, cv = m.col_jvel, ct = m.col_jtrq, cols = m.joint_cols;
+            const bool odd = ((jpar + cols*rc.fj) & 2) != 0;      /* row starts 8 bytes off a 16-byte line */
+            if (m.X.jrow_std) {
+              /* farms layout: 18 columns, position 0, velocity 1, torque 11 */
+              if (odd) {
+                fb_st2(row, qn, jv); fb_st4(row + 2, 0.f, 0.f, 0.f, 0.f); fb_st4(row + 6, 0.f, 0.f, 0.f, 0.f);
+                fb_st4(row + 10, 0.f, trq, 0.f, 0.f); fb_st4(row + 14, 0.f, 0.f, 0.f, 0.f);
+              } else {
+                fb_st4(row, qn, jv, 0.f, 0.f); fb_st4(row + 4, 0.f, 0.f, 0.f, 0.f); fb_st4(row + 8, 0.f, 0.f, 0.f, trq);
+                fb_st4(row + 12, 0.f, 0.f, 0.f, 0.f); fb_st2(row + 16, 0.f, 0.f);
+              }
+            } else {
 #define FB_JCOL(c_) ((c_) == cp ? qn : ((c_) == cv ? jv : ((c_) == ct ? trq : 0.f)))
-            /* 16-byte stores where the row allows it (rows are 8-byte aligned) */
-            int c = 0;
-            if ((jpar + cols*rc.fj) & 2) { fb_st2(row, FB_JCOL(0), FB_JCOL(1)); c = 2; }
-            for (; c + 4 <= cols; c += 4) {
-              const bool special = (cp >= c && cp < c + 4) || (cv >= c && cv < c + 4) || (ct >= c && ct < c + 4);
-              if (special) fb_st4(row + c, FB_JCOL(c), FB_JCOL(c + 1), FB_JCOL(c + 2), FB_JCOL(c + 3));
-              else fb_st4(row + c, 0.f, 0.f, 0.f, 0.f);
-            }
-            if (c < cols) fb_st2(row + c, FB_JCOL(c), FB_JCOL(c + 1));
+              int c = 0;
+              if (odd) { fb_st2(row, FB_JCOL(0), FB_JCOL(1)); c = 2; }
+              for (; c + 4 <= cols; c += 4) fb_st4(row + c, FB_JCOL(c), FB_JCOL(c + 1), FB_JCOL(c + 2), FB_JCOL(c + 3));
+              if (c < cols) fb_st2(row + c, FB_JCOL(c), FB_JCOL(c + 1));
 #undef FB_JCOL
+            }
           }
         }
       }
@@ -679,12 +742,12 @@ FB_UNROLL
         if ((xpar + 6*rc.xr) & 2) { fb_st2(row, F[0], F[1]); fb_st4(row + 2, F[2], Tq[0], Tq[1], Tq[2]); }
         else { fb_st4(row, F[0], F[1], F[2], Tq[0]); fb_st2(row + 4, Tq[1], Tq[2]); }
 FB_UNROLL
-        for (int k = 0; k < 3; k++) { pb[(FB_W + k)*BLK] = wf[k]; pb[(FB_W + 3 + k)*BLK] = wt[k]; }
+        for (int k = 0; k < 3; k++) { fb_st_scr(pg + (FG_W + k)*GS, wf[k]); fb_st_scr(pg + (FG_W + 3 + k)*GS, wt[k]); }
       } else {
         /* user-applied wrench: persistent, re-read (the slot held U during this step) */
         const float *gx = P.xfrc_applied + ((size_t)env*m.nbody + b)*6;
 FB_UNROLL
-        for (int k = 0; k < 6; k++) pb[(FB_W + k)*BLK] = gx[k];
+        for (int k = 0; k < 6; k++) fb_st_scr(pg + (FG_W + k)*GS, gx[k]);
       }
     }
     return bad;

@@ -90,14 +90,19 @@ struct FastRec {
 };
 
 /* per-environment shared-memory layout, in floats; element i of an environment lives at
- * i*BLOCK + thread.  One block of FB_NF floats per moving body, then the floating
- * root's qpos/qvel, then the accumulation slots. */
-enum { FB_QUAT = 0, FB_ORG = 4, FB_VEL = 7, FB_W = 13, FB_U = 19, FB_DINV = 20, FB_TRQ = 21,
-       FB_Q = 22, FB_QD = 23, FB_TC = 24, FB_TU = 25, FB_NF = 26 };
+ * i*BLOCK + thread.  One block of FB_NF floats per moving body (pose and velocity), then
+ * the accumulation slots; the floating root's qpos/qvel live in registers. */
+enum { FB_QUAT = 0, FB_ORG = 4, FB_VEL = 7, FB_NF = 13 };
+/* second half of the per-body state, kept in an L2-resident global scratch (element i of
+ * thread t at i*n_threads + t: coalesced) so that four warps of environments fit one SM */
+enum { FG_W = 0, FG_U = 6, FG_DINV = 7, FG_TRQ = 8, FG_Q = 9, FG_QD = 10, FG_TC = 11, FG_TU = 12,
+       FG_NF = 13 };
 struct DevFastLayout {
   int ok;          /* 1 when the model fits the path's subset */
-  int body0, root0, slots;
-  int nslot, n_float;
+  int body0, slots;
+  int nslot, n_float;   /* shared floats per environment */
+  int n_scratch;        /* global scratch floats per environment */
+  int jrow_std;         /* farms joint row = 18 columns, position 0, velocity 1, torque 11 */
 };
 
 /* per-environment shared-memory layout (float offsets; component-major SoA:
@@ -656,10 +661,11 @@ inline bool fb_build_model(const FbModel *fm, const FbFarms *ff, const FbWaveCon
     o.ft_actwc = put_i(I, actwc);
     o.ft_chk = put_f(F, chk);
     X.body0 = 0;
-    X.root0 = FB_NF*(nb - 1);
-    X.slots = X.root0 + 13;
+    X.slots = FB_NF*(nb - 1);
     X.nslot = nslot;
     X.n_float = X.slots + 27*nslot;
+    X.n_scratch = FG_NF*(nb - 1);
+    X.jrow_std = m.joint_cols == 18 && m.col_jpos == 0 && m.col_jvel == 1 && m.col_jtrq == 11;
   }
 
   /* water + units */

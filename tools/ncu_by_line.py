@@ -91,7 +91,7 @@ print('--- by function: inst%  sample%  avg-threads')
 for fn, (n, s, t) in sorted(fn_tot.items(), key=lambda kv: -kv[1][1]):
     print(f'{fn:28s} {100*n/tot:6.2f}% {100*s/max(1,tots):6.2f}%  {t/max(1,n):5.1f}')
 print('--- top lines by samples')
-for (f, ln), (n, s, t) in sorted(line_tot.items(), key=lambda kv: -kv[1][1])[:45]:
+for (f, ln), (n, s, t) in sorted(line_tot.items(), key=lambda kv: -kv[1][int(os.environ.get("BY_INST","0")) ^ 1])[:int(os.environ.get("TOPN","45"))]:
     text = sources[f][ln-1].strip()[:80] if f in sources and ln <= len(sources[f]) else ''
     st = line_stall[(f, ln)]
     top = sorted(zip(st, [h[6:] for _, h in stall_cols]), reverse=True)[:2]
