@@ -85,9 +85,9 @@ class FbLogView(ct.Structure):
     _fields_ = [
         ('links_dev', c_float_p), ('joints_dev', c_float_p), ('contacts_dev', c_float_p),
         ('xfrc_dev', c_float_p),
-        ('links_env_stride', ct.c_int64), ('joints_env_stride', ct.c_int64),
-        ('contacts_env_stride', ct.c_int64), ('xfrc_env_stride', ct.c_int64),
-        ('ring', ct.c_int32), ('n_envs', ct.c_int32),
+        ('links_vec', ct.c_int32), ('joints_vec', ct.c_int32),
+        ('contacts_vec', ct.c_int32), ('xfrc_vec', ct.c_int32),
+        ('ring', ct.c_int32), ('n_envs', ct.c_int32), ('env_pad', ct.c_int32),
     ]
 
 

@@ -72,9 +72,17 @@ struct EnvPtrs {
   float *J3;     /* [3*maxcon][nv] contact-frame rows of the point Jacobian */
   float *efc;    /* [5][maxefc]: aref, D, res, jp, force */
   float *prod3;  /* [2][3*maxcon] */
-  /* log rows of this step */
+  /* log rows of this step: element (item, col) of a kind with C columns stored in vectors of
+   * V lives at row[(item*(C/V) + col/V)*ev + col%V], ev = env_pad*V (FbLogView) */
   float *row_links, *row_joints, *row_contacts, *row_xfrc;
+  long long ev_links, ev_joints, ev_contacts, ev_xfrc;
 };
+
+/* vector widths of the device log (floats of one row stored contiguously per environment) */
+#define FB_VEC_LINKS 4
+#define FB_VEC_JOINTS 2
+#define FB_VEC_CONTACTS 4
+#define FB_VEC_XFRC 2
 
 /* ------------------------------------------------------------ team ops */
 template <int TEAM> struct TeamOps {
@@ -1143,29 +1151,33 @@ FB_UNROLL
       Quat q = body_quat(b);
       float lin[3], ang[3];
       body_velocity(b, lin, ang);
-      float *row = g.row_links + 20*l;
+      float *row = g.row_links + (long long)l*(20/FB_VEC_LINKS)*g.ev_links;
+#define FB_L(c_) row[((c_)/FB_VEC_LINKS)*g.ev_links + ((c_) % FB_VEC_LINKS)]
       float im = m.inv_meters;
-      row[0] = xipos[b]*im; row[1] = xipos[nb + b]*im; row[2] = xipos[2*nb + b]*im;
-      row[3] = q.x; row[4] = q.y; row[5] = q.z; row[6] = q.w;
-      row[7] = xpos[b]*im; row[8] = xpos[nb + b]*im; row[9] = xpos[2*nb + b]*im;
-      row[10] = q.x; row[11] = q.y; row[12] = q.z; row[13] = q.w;
-      row[14] = lin[0]*m.inv_velocity; row[15] = lin[1]*m.inv_velocity; row[16] = lin[2]*m.inv_velocity;
-      row[17] = ang[0]*m.inv_angvel; row[18] = ang[1]*m.inv_angvel; row[19] = ang[2]*m.inv_angvel;
+      FB_L(0) = xipos[b]*im; FB_L(1) = xipos[nb + b]*im; FB_L(2) = xipos[2*nb + b]*im;
+      FB_L(3) = q.x; FB_L(4) = q.y; FB_L(5) = q.z; FB_L(6) = q.w;
+      FB_L(7) = xpos[b]*im; FB_L(8) = xpos[nb + b]*im; FB_L(9) = xpos[2*nb + b]*im;
+      FB_L(10) = q.x; FB_L(11) = q.y; FB_L(12) = q.z; FB_L(13) = q.w;
+      FB_L(14) = lin[0]*m.inv_velocity; FB_L(15) = lin[1]*m.inv_velocity; FB_L(16) = lin[2]*m.inv_velocity;
+      FB_L(17) = ang[0]*m.inv_angvel; FB_L(18) = ang[1]*m.inv_angvel; FB_L(19) = ang[2]*m.inv_angvel;
+#undef FB_L
     }
     /* joints: physics.py:481-524 (the torque family is empty in the reference, D-4) */
     for (int j = lane; j < m.n_joints; j += TEAM) {
-      float *row = g.row_joints + m.joint_cols*j;
-      for (int k = 0; k < m.joint_cols; k++) row[k] = 0.f;
-      row[m.col_jpos] = qpos[MI(fj_qposadr, j)];
-      row[m.col_jvel] = qvel[MI(fj_dofadr, j)]*m.inv_angvel;
+      float *row = g.row_joints + (long long)j*(m.joint_cols/FB_VEC_JOINTS)*g.ev_joints;
+#define FB_J(c_) row[((c_)/FB_VEC_JOINTS)*g.ev_joints + ((c_) % FB_VEC_JOINTS)]
+      for (int k = 0; k < m.joint_cols; k++) FB_J(k) = 0.f;
+      FB_J(m.col_jpos) = qpos[MI(fj_qposadr, j)];
+      FB_J(m.col_jvel) = qvel[MI(fj_dofadr, j)]*m.inv_angvel;
       float trq = 0.f;
       int ap = MI(fj_actpos, j), av = MI(fj_actvel, j), at = MI(fj_acttrq, j);
       if (ap >= 0) trq += actf[ap];
       if (av >= 0) trq += actf[av];
       if (at >= 0) trq += actf[at];
-      row[m.col_jtrq] = trq*m.inv_torques;
+      FB_J(m.col_jtrq) = trq*m.inv_torques;
       int jid = MI(fj_jntid, j);
-      row[m.col_jlim] = jid >= 0 ? limf[jid]*m.inv_torques : 0.f;
+      FB_J(m.col_jlim) = jid >= 0 ? limf[jid]*m.inv_torques : 0.f;
+#undef FB_J
     }
     /* contacts: sensors.pyx:140-190 */
     const int *con_cand = si + m.L.con_cand;
@@ -1189,15 +1201,17 @@ FB_UNROLL
           nsum += nrm;
         }
       }
-      float *row = g.row_contacts + 12*sx;
+      float *row = g.row_contacts + (long long)sx*(12/FB_VEC_CONTACTS)*g.ev_contacts;
+#define FB_C(c_) row[((c_)/FB_VEC_CONTACTS)*g.ev_contacts + ((c_) % FB_VEC_CONTACTS)]
       float ip = nsum > 0.f ? 1.0f/nsum : 1.0f;
-      for (int k = 0; k < 9; k++) row[k] = acc[k]*m.inv_newtons;
-      for (int k = 0; k < 3; k++) row[9+k] = acc[9+k]*ip*m.inv_meters;
+      for (int k = 0; k < 9; k++) FB_C(k) = acc[k]*m.inv_newtons;
+      for (int k = 0; k < 3; k++) FB_C(9+k) = acc[9+k]*ip*m.inv_meters;
+#undef FB_C
     }
     /* xfrc rows + xfrc_applied for the next step (drag.pyx:152-268, section 3.4) */
     for (int x = lane; x < m.n_xfrc; x += TEAM) {
-      float *row = g.row_xfrc + 6*x;
-      for (int k = 0; k < 6; k++) row[k] = 0.f;
+      float *row = g.row_xfrc + (long long)x*(6/FB_VEC_XFRC)*g.ev_xfrc;
+      for (int k = 0; k < 6; k++) row[(k/FB_VEC_XFRC)*g.ev_xfrc + (k % FB_VEC_XFRC)] = 0.f;
       int b = MI(xfrc_body, x);
       for (int k = 0; k < 6; k++) xf[k*nb + b] = 0.f;
     }
@@ -1226,8 +1240,11 @@ FB_UNROLL
           F[k] = sv*m.water_viscosity*MF(swim_coef, 6*i + k) + buoy[k];
           Tq[k] = sw*MF(swim_coef, 6*i + 3 + k);
         }
-        float *row = g.row_xfrc + 6*xi;
-        for (int k = 0; k < 3; k++) { row[k] = F[k]; row[3+k] = Tq[k]; }
+        float *row = g.row_xfrc + (long long)xi*(6/FB_VEC_XFRC)*g.ev_xfrc;
+        for (int k = 0; k < 3; k++) {
+          row[(k/FB_VEC_XFRC)*g.ev_xfrc + (k % FB_VEC_XFRC)] = F[k];
+          row[((3+k)/FB_VEC_XFRC)*g.ev_xfrc + ((3+k) % FB_VEC_XFRC)] = Tq[k];
+        }
         int bx = MI(xfrc_body, xi);
         float Rx[9], wf[3], wt[3];
         q_mat(body_quat(bx), Rx);
@@ -1306,8 +1323,10 @@ struct FbParams {
   int *d_ncon, *d_con_cand;
   float *d_con_dist, *d_con_pos, *d_con_frame, *d_con_force;
   float *J3, *efc, *prod3;
+  /* device log, environment-minor (FbLogView): element (env, it, item, col) of a kind with N
+   * items, C columns, vector width V at (((it*N + item)*(C/V) + col/V)*env_pad + env)*V + col%V */
   float *log_links, *log_joints, *log_contacts, *log_xfrc;
-  long long links_env_stride, joints_env_stride, contacts_env_stride, xfrc_env_stride;
+  long long env_pad;
   /* hand-over from the environment-per-thread kernel (fb_fast.h): environments that met
    * a limit or a contact, the step they stopped at, and how many there are.  The
    * counter is double-buffered by launch parity; use_pending = 0 -> every environment
@@ -1317,6 +1336,12 @@ struct FbParams {
   float *fast_scratch;            /* [n_scratch][fast_scratch_stride]: second half of the per-thread state */
   long long fast_scratch_stride;
 };
+
+/* start of ring row `it` for one environment: floats_per_row = N*C of the kind */
+FB_DEV float *fb_log_row(float *base, long long it, long long floats_per_row, long long env_pad, int vec,
+                         size_t env) {
+  return base + it*floats_per_row*env_pad + env*vec;
+}
 
 FB_DEV EnvPtrs fb_env_ptrs(const FbParams &P, int env) {
   const DevModel &m = P.m;
@@ -1336,6 +1361,8 @@ FB_DEV EnvPtrs fb_env_ptrs(const FbParams &P, int env) {
   g.d_con_frame = P.d_con_frame + e*9*mc; g.d_con_force = P.d_con_force + e*3*mc;
   g.J3 = P.J3 + e*3*mc*m.nv; g.efc = P.efc + e*5*m.maxefc; g.prod3 = P.prod3 + e*6*mc;
   g.row_links = g.row_joints = g.row_contacts = g.row_xfrc = 0;
+  g.ev_links = P.env_pad*FB_VEC_LINKS; g.ev_joints = P.env_pad*FB_VEC_JOINTS;
+  g.ev_contacts = P.env_pad*FB_VEC_CONTACTS; g.ev_xfrc = P.env_pad*FB_VEC_XFRC;
   return g;
 }
 
@@ -1365,10 +1392,10 @@ FB_DEV void fb_run_env(const FbParams &P, int env, int k0, float *s, int *si, in
       st.euler();
       row = (P.it0 + k + 1) % P.ring;
     }
-    st.g.row_links = P.log_links + e*P.links_env_stride + row*(long long)(m.n_links*20);
-    st.g.row_joints = P.log_joints + e*P.joints_env_stride + row*(long long)(m.n_joints*m.joint_cols);
-    st.g.row_contacts = P.log_contacts + e*P.contacts_env_stride + row*(long long)(m.n_contacts*12);
-    st.g.row_xfrc = P.log_xfrc + e*P.xfrc_env_stride + row*(long long)(m.n_xfrc*6);
+    st.g.row_links = fb_log_row(P.log_links, row, m.n_links*20, P.env_pad, FB_VEC_LINKS, e);
+    st.g.row_joints = fb_log_row(P.log_joints, row, m.n_joints*m.joint_cols, P.env_pad, FB_VEC_JOINTS, e);
+    st.g.row_contacts = fb_log_row(P.log_contacts, row, m.n_contacts*12, P.env_pad, FB_VEC_CONTACTS, e);
+    st.g.row_xfrc = fb_log_row(P.log_xfrc, row, m.n_xfrc*6, P.env_pad, FB_VEC_XFRC, e);
     st.write_log();
     if (P.mode == FB_MODE_RESET) st.write_derived();
   }

@@ -103,15 +103,26 @@ fb_fast_kernel(const __grid_constant__ FbFastParams Q) {
   }
 }
 
-/* last written log row of every environment -> dense [n_envs][row] buffers */
-__global__ void fb_gather_rows_kernel(const float *__restrict__ log, long long env_stride,
-                                      long long row, int row_floats, int n_envs,
-                                      float *__restrict__ out) {
+/* ring row `row` of every environment -> dense [n_envs][row_floats] (the reference's row
+ * layout); threads run over (vector, env) with env fastest: coalesced reads */
+__global__ void fb_gather_rows_kernel(const float *__restrict__ log, long long row, int row_floats,
+                                      int vec, long long env_pad, int n_envs, float *__restrict__ out) {
   long long i = (long long)blockIdx.x*blockDim.x + threadIdx.x;
-  long long total = (long long)n_envs*row_floats;
-  if (i >= total) return;
-  long long env = i/row_floats, k = i - env*row_floats;
-  out[i] = log[env*env_stride + row*row_floats + k];
+  const int nvec = row_floats/vec;
+  if (i >= (long long)nvec*n_envs) return;
+  const long long g = i/n_envs, env = i - g*n_envs;
+  const float *src = log + ((row*nvec + g)*env_pad + env)*vec;
+  float *dst = out + env*row_floats + g*vec;
+  for (int k = 0; k < vec; k++) dst[k] = src[k];
+}
+
+/* the whole ring of one environment -> dense [ring][row_floats] */
+__global__ void fb_gather_env_kernel(const float *__restrict__ log, int ring, int row_floats, int vec,
+                                     long long env_pad, int env, float *__restrict__ out) {
+  long long i = (long long)blockIdx.x*blockDim.x + threadIdx.x;
+  if (i >= (long long)ring*row_floats) return;
+  const long long lin = i/vec;       /* (it*nvec + g) */
+  out[i] = log[(lin*env_pad + env)*vec + (i - lin*vec)];
 }
 #endif
 
@@ -135,6 +146,7 @@ struct FbHandle {
   long long it;            /* physics steps since reset */
   float last_ms;
   float *gather_links, *gather_joints;   /* fb_step_host staging */
+  float *gather_env;                     /* fb_export_farms staging: one environment's ring of one kind */
   /* wave-controller copies (owned) */
   std::vector<int32_t> wc_act;
   std::vector<double> wc_amp, wc_freq, wc_lag, wc_off;
@@ -322,7 +334,7 @@ int fb_create(const FbModel *model, const FbFarms *farms, int n_envs, int device
   FbHandle *h = new (std::nothrow) FbHandle();
   if (!h) return fail("out of host memory");
   h->device = device; h->I_dev = nullptr; h->F_dev = nullptr; h->launches = 0; h->it = 0;
-  h->last_ms = 0.f; h->has_wc = false; h->gather_links = h->gather_joints = nullptr;
+  h->last_ms = 0.f; h->has_wc = false; h->gather_links = h->gather_joints = h->gather_env = nullptr;
   h->fast_enabled = 1; h->fast_block = 1; h->fast_smem_bytes = 0; h->launch_parity = 0;
 #ifndef FB_HOST_EMU
   h->fastQ = nullptr;
@@ -395,13 +407,8 @@ int fb_create(const FbModel *model, const FbFarms *farms, int n_envs, int device
   FbParams &P = h->P;
   P.n_envs = n_envs; P.ring = ring_steps;
   const size_t n = (size_t)n_envs, nb = m.nbody, mc = m.maxcon > 0 ? m.maxcon : 1, nu = m.nu > 0 ? m.nu : 1;
-  /* environment strides are padded to 16 bytes so that the alignment of a log row does
-   * not depend on the environment (vector stores of the per-thread kernel) */
-  auto pad4 = [](long long v) { return (v + 3) & ~3LL; };
-  P.links_env_stride = pad4((long long)ring_steps*m.n_links*20);
-  P.joints_env_stride = pad4((long long)ring_steps*m.n_joints*m.joint_cols);
-  P.contacts_env_stride = pad4((long long)ring_steps*m.n_contacts*12);
-  P.xfrc_env_stride = pad4((long long)ring_steps*m.n_xfrc*6);
+  /* environment-minor log: rows of 32 consecutive environments are contiguous per vector */
+  P.env_pad = (long long)((n_envs + 31) & ~31);
   int bad = 0;
   bad |= alloc_arr(h, &P.qpos, n*m.nq); bad |= alloc_arr(h, &P.qvel, n*m.nv);
   bad |= alloc_arr(h, &P.ctrl, n*nu); bad |= alloc_arr(h, &P.xfrc_applied, n*6*nb);
@@ -420,10 +427,18 @@ int fb_create(const FbModel *model, const FbFarms *farms, int n_envs, int device
   bad |= alloc_arr(h, &P.d_con_frame, n*9*mc); bad |= alloc_arr(h, &P.d_con_force, n*3*mc);
   bad |= alloc_arr(h, &P.J3, n*3*mc*m.nv); bad |= alloc_arr(h, &P.efc, n*5*(m.maxefc > 0 ? m.maxefc : 1));
   bad |= alloc_arr(h, &P.prod3, n*6*mc);
-  bad |= alloc_arr(h, &P.log_links, n*(size_t)P.links_env_stride);
-  bad |= alloc_arr(h, &P.log_joints, n*(size_t)P.joints_env_stride);
-  bad |= alloc_arr(h, &P.log_contacts, n*(size_t)P.contacts_env_stride);
-  bad |= alloc_arr(h, &P.log_xfrc, n*(size_t)P.xfrc_env_stride);
+  const size_t ep = (size_t)P.env_pad*ring_steps;
+  bad |= alloc_arr(h, &P.log_links, ep*m.n_links*20);
+  bad |= alloc_arr(h, &P.log_joints, ep*m.n_joints*m.joint_cols);
+  bad |= alloc_arr(h, &P.log_contacts, ep*m.n_contacts*12);
+  bad |= alloc_arr(h, &P.log_xfrc, ep*m.n_xfrc*6);
+  {
+    size_t big = (size_t)ring_steps*m.n_links*20;
+    if ((size_t)ring_steps*m.n_joints*m.joint_cols > big) big = (size_t)ring_steps*m.n_joints*m.joint_cols;
+    if ((size_t)ring_steps*m.n_contacts*12 > big) big = (size_t)ring_steps*m.n_contacts*12;
+    if ((size_t)ring_steps*m.n_xfrc*6 > big) big = (size_t)ring_steps*m.n_xfrc*6;
+    bad |= alloc_arr(h, &h->gather_env, big > 0 ? big : 1);
+  }
   bad |= alloc_arr(h, &h->gather_links, n*m.n_links*20);
   bad |= alloc_arr(h, &h->gather_joints, n*m.n_joints*m.joint_cols);
   if (bad) { fb_destroy(h); return fail("device allocation failed (n_envs x ring too large?)"); }
@@ -545,8 +560,9 @@ int fb_log_view(FbHandle *h, FbLogView *out) {
   const FbParams &P = h->P;
   out->links_dev = P.log_links; out->joints_dev = P.log_joints;
   out->contacts_dev = P.log_contacts; out->xfrc_dev = P.log_xfrc;
-  out->links_env_stride = P.links_env_stride; out->joints_env_stride = P.joints_env_stride;
-  out->contacts_env_stride = P.contacts_env_stride; out->xfrc_env_stride = P.xfrc_env_stride;
+  out->links_vec = FB_VEC_LINKS; out->joints_vec = FB_VEC_JOINTS;
+  out->contacts_vec = FB_VEC_CONTACTS; out->xfrc_vec = FB_VEC_XFRC;
+  out->env_pad = (int32_t)P.env_pad;
   out->ring = P.ring; out->n_envs = P.n_envs;
   return 0;
 }
@@ -592,18 +608,28 @@ int fb_export_farms(FbHandle *h, int env, double *links, double *joints, double 
   const FbParams &P = h->P;
   if (env < 0 || env >= P.n_envs) return fail("fb_export_farms: env out of range");
   const DevModel &dm = h->hm.m;
-  struct Item { double *dst; const float *src; long long stride, count; } items[4] = {
-    {links, P.log_links, P.links_env_stride, (long long)P.ring*dm.n_links*20},
-    {joints, P.log_joints, P.joints_env_stride, (long long)P.ring*dm.n_joints*dm.joint_cols},
-    {contacts, P.log_contacts, P.contacts_env_stride, (long long)P.ring*dm.n_contacts*12},
-    {xfrc, P.log_xfrc, P.xfrc_env_stride, (long long)P.ring*dm.n_xfrc*6}};
+  struct Item { double *dst; const float *src; int row_floats, vec; } items[4] = {
+    {links, P.log_links, dm.n_links*20, FB_VEC_LINKS},
+    {joints, P.log_joints, dm.n_joints*dm.joint_cols, FB_VEC_JOINTS},
+    {contacts, P.log_contacts, dm.n_contacts*12, FB_VEC_CONTACTS},
+    {xfrc, P.log_xfrc, dm.n_xfrc*6, FB_VEC_XFRC}};
   for (const Item &it : items) {
-    if (!it.dst || it.count == 0) continue;
-    std::vector<float> tmp((size_t)it.count);
-    if (d2h(tmp.data(), it.src + (size_t)env*it.stride, tmp.size()*sizeof(float), h->stream) ||
-        dev_sync(h->stream))
+    if (!it.dst || it.row_floats == 0) continue;
+    const size_t count = (size_t)P.ring*it.row_floats;
+    std::vector<float> tmp(count);
+#ifdef FB_HOST_EMU
+    for (size_t i = 0; i < count; i++) {
+      size_t lin = i/it.vec;
+      tmp[i] = it.src[(lin*P.env_pad + env)*it.vec + (i - lin*it.vec)];
+    }
+#else
+    fb_gather_env_kernel<<<(unsigned)((count + 255)/256), 256, 0, h->stream>>>(
+        it.src, P.ring, it.row_floats, it.vec, P.env_pad, env, h->gather_env);
+    h->launches++;
+    if (d2h(tmp.data(), h->gather_env, count*sizeof(float), h->stream) || dev_sync(h->stream))
       return fail(std::string("fb_export_farms: ") + dev_error());
-    for (size_t i = 0; i < tmp.size(); i++) it.dst[i] = (double)tmp[i];
+#endif
+    for (size_t i = 0; i < count; i++) it.dst[i] = (double)tmp[i];
   }
   return 0;
 }
@@ -622,23 +648,29 @@ int fb_step_host(FbHandle *h, const float *ctrl, const float *qpos, const float 
   const int lf = m.n_links*20, jf = m.n_joints*m.joint_cols;
 #ifdef FB_HOST_EMU
   for (size_t e = 0; e < n; e++) {
-    if (links_row) memcpy(links_row + e*lf, P.log_links + e*P.links_env_stride + row*lf, lf*sizeof(float));
-    if (joints_row) memcpy(joints_row + e*jf, P.log_joints + e*P.joints_env_stride + row*jf, jf*sizeof(float));
+    for (int i = 0; links_row && i < lf; i++) {
+      long long g = i/FB_VEC_LINKS;
+      links_row[e*lf + i] = P.log_links[((row*(lf/FB_VEC_LINKS) + g)*P.env_pad + e)*FB_VEC_LINKS + i % FB_VEC_LINKS];
+    }
+    for (int i = 0; joints_row && i < jf; i++) {
+      long long g = i/FB_VEC_JOINTS;
+      joints_row[e*jf + i] = P.log_joints[((row*(jf/FB_VEC_JOINTS) + g)*P.env_pad + e)*FB_VEC_JOINTS + i % FB_VEC_JOINTS];
+    }
   }
 #else
   if (links_row && lf) {
-    long long total = (long long)n*lf;
+    long long total = (long long)n*(lf/FB_VEC_LINKS);
     fb_gather_rows_kernel<<<(unsigned)((total + 255)/256), 256, 0, h->stream>>>(
-        P.log_links, P.links_env_stride, row, lf, P.n_envs, h->gather_links);
+        P.log_links, row, lf, FB_VEC_LINKS, P.env_pad, P.n_envs, h->gather_links);
     h->launches++;
-    if (d2h(links_row, h->gather_links, (size_t)total*sizeof(float), h->stream)) return fail(dev_error());
+    if (d2h(links_row, h->gather_links, (size_t)n*lf*sizeof(float), h->stream)) return fail(dev_error());
   }
   if (joints_row && jf) {
-    long long total = (long long)n*jf;
+    long long total = (long long)n*(jf/FB_VEC_JOINTS);
     fb_gather_rows_kernel<<<(unsigned)((total + 255)/256), 256, 0, h->stream>>>(
-        P.log_joints, P.joints_env_stride, row, jf, P.n_envs, h->gather_joints);
+        P.log_joints, row, jf, FB_VEC_JOINTS, P.env_pad, P.n_envs, h->gather_joints);
     h->launches++;
-    if (d2h(joints_row, h->gather_joints, (size_t)total*sizeof(float), h->stream)) return fail(dev_error());
+    if (d2h(joints_row, h->gather_joints, (size_t)n*jf*sizeof(float), h->stream)) return fail(dev_error());
   }
 #endif
   if (dev_sync(h->stream)) return fail(std::string("fb_step_host: ") + dev_error());

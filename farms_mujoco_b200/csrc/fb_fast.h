@@ -361,12 +361,13 @@ FB_UNROLL
         m_rot(R, rc.hloc[0], rc.hloc[1], rc.hloc[2], h);   /* com - anchor */
         v_cross(v, h, cr);
         const float im = m.inv_meters, iv = m.inv_velocity, iw = m.inv_angvel;
-        float *row = row_links + 20*rc.link;
+        const long long ev = P.env_pad*FB_VEC_LINKS;
+        float *row = row_links + (long long)(5*rc.link)*ev;     /* five 16-byte vectors, each coalesced across the warp */
         fb_st4(row, (rootpos[0] + o[0] + h[0])*im, (rootpos[1] + o[1] + h[1])*im, (rootpos[2] + o[2] + h[2])*im, q.x);
-        fb_st4(row + 4, q.y, q.z, q.w, xpos[0]*im);
-        fb_st4(row + 8, xpos[1]*im, xpos[2]*im, q.x, q.y);
-        fb_st4(row + 12, q.z, q.w, (v[3] + cr[0])*iv, (v[4] + cr[1])*iv);
-        fb_st4(row + 16, (v[5] + cr[2])*iv, v[0]*iw, v[1]*iw, v[2]*iw);
+        fb_st4(row + ev, q.y, q.z, q.w, xpos[0]*im);
+        fb_st4(row + 2*ev, xpos[1]*im, xpos[2]*im, q.x, q.y);
+        fb_st4(row + 3*ev, q.z, q.w, (v[3] + cr[0])*iv, (v[4] + cr[1])*iv);
+        fb_st4(row + 4*ev, (v[5] + cr[2])*iv, v[0]*iw, v[1]*iw, v[2]*iw);
       }
     }
     return active;
@@ -578,7 +579,7 @@ FB_UNROLL
   }
 
   /* ---- pass 3: root -> leaves, accelerations, Euler, joints / xfrc rows, drag */
-  FB_MEM int pass_accel(const float *aroot, float *row_joints, float *row_xfrc, int jpar, int xpar) {
+  FB_MEM int pass_accel(const float *aroot, float *row_joints, float *row_xfrc) {
     const int nb = m.nbody;
     const float hdt = m.timestep;
     float ac[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};   /* carry: acceleration of body b-1 */
@@ -676,25 +677,18 @@ FB_UNROLL
           bad |= !(fabsf(qn) < 1e30f);
           /* joints row: physics.py:481-524 (new position/velocity, forces of the old state) */
           if (rc.fj >= 0) {
-            float *row = row_joints + m.joint_cols*rc.fj;
-            const float trq = cx[8]*m.inv_torques, jv = qdn*m.inv_angvel;
+            const long long ev = P.env_pad*FB_VEC_JOINTS;
             const int cp = m.col_jpos, cv = m.col_jvel, ct = m.col_jtrq, cols = m.joint_cols;
-            const bool odd = ((jpar + cols*rc.fj) & 2) != 0;      /* row starts 8 bytes off a 16-byte line */
+            float *row = row_joints + (long long)((cols/2)*rc.fj)*ev;   /* 8-byte vectors, coalesced across the warp */
+            const float trq = cx[8]*m.inv_torques, jv = qdn*m.inv_angvel;
             if (m.X.jrow_std) {
               /* farms layout: 18 columns, position 0, velocity 1, torque 11 */
-              if (odd) {
-                fb_st2(row, qn, jv); fb_st4(row + 2, 0.f, 0.f, 0.f, 0.f); fb_st4(row + 6, 0.f, 0.f, 0.f, 0.f);
-                fb_st4(row + 10, 0.f, trq, 0.f, 0.f); fb_st4(row + 14, 0.f, 0.f, 0.f, 0.f);
-              } else {
-                fb_st4(row, qn, jv, 0.f, 0.f); fb_st4(row + 4, 0.f, 0.f, 0.f, 0.f); fb_st4(row + 8, 0.f, 0.f, 0.f, trq);
-                fb_st4(row + 12, 0.f, 0.f, 0.f, 0.f); fb_st2(row + 16, 0.f, 0.f);
-              }
+              fb_st2(row, qn, jv);
+FB_UNROLL
+              for (int g = 1; g < 9; g++) fb_st2(row + g*ev, 0.f, g == 5 ? trq : 0.f);
             } else {
 #define FB_JCOL(c_) ((c_) == cp ? qn : ((c_) == cv ? jv : ((c_) == ct ? trq : 0.f)))
-              int c = 0;
-              if (odd) { fb_st2(row, FB_JCOL(0), FB_JCOL(1)); c = 2; }
-              for (; c + 4 <= cols; c += 4) fb_st4(row + c, FB_JCOL(c), FB_JCOL(c + 1), FB_JCOL(c + 2), FB_JCOL(c + 3));
-              if (c < cols) fb_st2(row + c, FB_JCOL(c), FB_JCOL(c + 1));
+              for (int c = 0; c < cols; c += 2) fb_st2(row + (c/2)*ev, FB_JCOL(c), FB_JCOL(c + 1));
 #undef FB_JCOL
             }
           }
@@ -738,9 +732,9 @@ FB_UNROLL
             for (int k = 0; k < 3; k++) { wf[k] *= m.newtons; wt[k] *= m.torques; }
           }
         }
-        float *row = row_xfrc + 6*rc.xr;
-        if ((xpar + 6*rc.xr) & 2) { fb_st2(row, F[0], F[1]); fb_st4(row + 2, F[2], Tq[0], Tq[1], Tq[2]); }
-        else { fb_st4(row, F[0], F[1], F[2], Tq[0]); fb_st2(row + 4, Tq[1], Tq[2]); }
+        const long long ev = P.env_pad*FB_VEC_XFRC;
+        float *row = row_xfrc + (long long)(3*rc.xr)*ev;
+        fb_st2(row, F[0], F[1]); fb_st2(row + ev, F[2], Tq[0]); fb_st2(row + 2*ev, Tq[1], Tq[2]);
 FB_UNROLL
         for (int k = 0; k < 3; k++) { fb_st_scr(pg + (FG_W + k)*GS, wf[k]); fb_st_scr(pg + (FG_W + 3 + k)*GS, wt[k]); }
       } else {
@@ -761,21 +755,17 @@ FB_UNROLL
     int k = 0;
     for (; k < n; k++) {
       const long long row = (P.it0 + k + 1) % P.ring;
-      float *row_links = P.log_links + e*P.links_env_stride + row*(long long)(m.n_links*20);
-      float *row_joints = P.log_joints + e*P.joints_env_stride + row*(long long)(m.n_joints*m.joint_cols);
-      float *row_contacts = P.log_contacts + e*P.contacts_env_stride + row*(long long)(m.n_contacts*12);
-      float *row_xfrc = P.log_xfrc + e*P.xfrc_env_stride + row*(long long)(m.n_xfrc*6);
+      float *row_links = fb_log_row(P.log_links, row, m.n_links*20, P.env_pad, FB_VEC_LINKS, e);
+      float *row_joints = fb_log_row(P.log_joints, row, m.n_joints*m.joint_cols, P.env_pad, FB_VEC_JOINTS, e);
+      float *row_contacts = fb_log_row(P.log_contacts, row, m.n_contacts*12, P.env_pad, FB_VEC_CONTACTS, e);
+      float *row_xfrc = fb_log_row(P.log_xfrc, row, m.n_xfrc*6, P.env_pad, FB_VEC_XFRC, e);
       const float time = (float)(P.it0 + k)*m.timestep;
       if (pass_poses(row_links)) break;
       float aroot[6] = {0.f, 0.f, 0.f, -m.grav[0], -m.grav[1], -m.grav[2]};
       pass_inertia(time, aroot, k == n - 1 && m.n_wc > 0);   /* ctrl is left as the team path leaves it */
-      /* float offsets of the rows inside the environment's log (environment strides are
-       * multiples of 4 floats): they decide where 16-byte stores are aligned */
-      const int jpar = (int)((row*(long long)(m.n_joints*m.joint_cols)) & 3);
-      const int xpar = (int)((row*(long long)(m.n_xfrc*6)) & 3);
-      int bad = pass_accel(aroot, row_joints, row_xfrc, jpar, xpar);
+      int bad = pass_accel(aroot, row_joints, row_xfrc);
       /* no contact is active on this path: the contacts rows are zero (sensors.pyx:140-190) */
-      for (int i = 0; i < m.n_contacts*3; i++) fb_st4(row_contacts + 4*i, 0.f, 0.f, 0.f, 0.f);
+      for (int i = 0; i < m.n_contacts*3; i++) fb_st4(row_contacts + i*(P.env_pad*FB_VEC_CONTACTS), 0.f, 0.f, 0.f, 0.f);
       if (bad) FB_FLAG_OR(P.flags + env, FB_FLAG_NONFINITE);
     }
     store_state(P.it0 + k);

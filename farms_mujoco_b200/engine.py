@@ -81,7 +81,7 @@ def load_library(path=None):
         fn = getattr(lib, name)
         fn.restype = restype
         fn.argtypes = argtypes
-    if lib.fb_abi_version() != 1:
+    if lib.fb_abi_version() != 2:
         raise EngineError('ABI version mismatch')
     _LIBS[path] = lib
     return lib
@@ -300,27 +300,26 @@ class BatchedPhysics:
         ``data.sensors.<kind>.array`` shape, task.py:158)."""
         log, names = self._log, self.names
         shapes = dict(
-            links=(log.links_dev, len(names.links.names), sc.link_size, log.links_env_stride),
-            joints=(log.joints_dev, len(names.joints.names), sc.joint_size, log.joints_env_stride),
-            contacts=(log.contacts_dev, len(names.contacts.names), sc.contact_size,
-                      log.contacts_env_stride),
-            xfrc=(log.xfrc_dev, len(names.xfrc.names), sc.xfrc_size, log.xfrc_env_stride),
+            links=(log.links_dev, len(names.links.names), sc.link_size, log.links_vec),
+            joints=(log.joints_dev, len(names.joints.names), sc.joint_size, log.joints_vec),
+            contacts=(log.contacts_dev, len(names.contacts.names), sc.contact_size, log.contacts_vec),
+            xfrc=(log.xfrc_dev, len(names.xfrc.names), sc.xfrc_size, log.xfrc_vec),
         )
         out = {}
-        for kind, (ptr, n_items, cols, stride) in shapes.items():
+        ring, pad = self.buffer_size, int(log.env_pad)
+        for kind, (ptr, n_items, cols, vec) in shapes.items():
             if n_items == 0:
-                shape = (self.n_envs, self.buffer_size, 0, cols)
+                shape = (self.n_envs, ring, 0, cols)
                 out[kind] = np.zeros(shape if env is None else shape[1:], dtype=np.float32)
                 continue
+            # device layout [ring][items][cols/V][env_pad][V] (include/farms_b200.h, FbLogView)
+            raw = self._read(ptr, (ring, n_items, cols//vec, pad, vec))
             if env is None:
-                # the environment stride may be padded (16-byte alignment of the rows)
-                flat = self._read(ptr, (self.n_envs, int(stride)))
-                used = self.buffer_size*n_items*cols
-                out[kind] = np.ascontiguousarray(flat[:, :used]).reshape(
-                    self.n_envs, self.buffer_size, n_items, cols)
+                arr = raw[:, :, :, :self.n_envs, :].transpose(3, 0, 1, 2, 4)
+                out[kind] = np.ascontiguousarray(arr).reshape(self.n_envs, ring, n_items, cols)
             else:
-                base = _ptr(ptr) + 4*int(env)*int(stride)
-                out[kind] = self._read(base, (self.buffer_size, n_items, cols))
+                arr = raw[:, :, :, int(env), :]
+                out[kind] = np.ascontiguousarray(arr).reshape(ring, n_items, cols)
         return out
 
     def export_farms(self, env, data=None):

@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define FB_ABI_VERSION 1
+#define FB_ABI_VERSION 2
 
 /* joint / geom enums follow MuJoCo's mjtJoint / mjtGeom numbering */
 enum { FB_JNT_FREE = 0, FB_JNT_BALL = 1, FB_JNT_SLIDE = 2, FB_JNT_HINGE = 3 };
@@ -112,18 +112,21 @@ typedef struct FbWaveController {
 
 typedef struct FbHandle FbHandle;
 
-/* Device log: farms layout per environment, float32.
- *   links    [n_envs][ring][n_links   ][20]
- *   joints   [n_envs][ring][n_joints  ][18]
- *   contacts [n_envs][ring][n_contacts][12]
- *   xfrc     [n_envs][ring][n_xfrc    ][6]
- * i.e. log.<kind>_dev + env*<kind>_env_stride is exactly the reference's
- * data.sensors.<kind>.array ([buffer_size, n_items, n_cols], task.py:158).  The
- * environment strides are rounded up to a multiple of 4 floats (16 bytes). */
+/* Device log, float32, environment-minor so that the 32 environments of a warp write one
+ * contiguous run per store.  A kind with N items and C columns is stored in vectors of V
+ * columns (links 4, joints 2, contacts 4, xfrc 2):
+ *
+ *   <kind>_dev[ (((it*N + item)*(C/V) + col/V)*env_pad + env)*V + col%V ]
+ *
+ * i.e. the 5-D strided array [ring][N][C/V][env_pad][V]; indexed (env, it, item, col) it holds
+ * exactly the reference's data.sensors.<kind>.array[it, item, col] ([buffer_size, n_items,
+ * n_cols], task.py:158) of environment env.  fb_export_farms() returns one environment in
+ * the reference's own (contiguous, float64) layout; fb_step_host() returns the last row of
+ * every environment as dense [n_envs][N][C]. */
 typedef struct FbLogView {
   float *links_dev, *joints_dev, *contacts_dev, *xfrc_dev;
-  int64_t links_env_stride, joints_env_stride, contacts_env_stride, xfrc_env_stride; /* in floats */
-  int32_t ring, n_envs;
+  int32_t links_vec, joints_vec, contacts_vec, xfrc_vec; /* V of each kind */
+  int32_t ring, n_envs, env_pad;                         /* env_pad = n_envs rounded up to 32 */
 } FbLogView;
 
 /* Device state views (float32), one row per environment. */

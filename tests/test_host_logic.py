@@ -147,7 +147,7 @@ def test_abi_header_symbols_are_exported(cuda_library):
     lib = ct.CDLL(cuda_library)
     for name in declared:
         assert hasattr(lib, name), name
-    assert engine.load_library(cuda_library).fb_abi_version() == 1
+    assert engine.load_library(cuda_library).fb_abi_version() == 2
 
 
 def test_struct_mirrors_match_header_field_order():
