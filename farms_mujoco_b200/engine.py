@@ -247,6 +247,11 @@ class BatchedPhysics:
 
     # --------------------------------------------------------------- views
     @property
+    def qpos_spring(self):
+        """``model.qpos_spring`` per environment (task.py:343-346), float64 host copy."""
+        return self._read(self._state.qpos_spring_dev, (self.n_envs, self.model.nq)).astype(np.float64)
+
+    @property
     def qpos(self):
         return self._read(self._state.qpos_dev, (self.n_envs, self.model.nq))
 
@@ -321,6 +326,25 @@ class BatchedPhysics:
                 arr = raw[:, :, :, int(env), :]
                 out[kind] = np.ascontiguousarray(arr).reshape(ring, n_items, cols)
         return out
+
+    def log_row(self, kind, index):
+        """Ring row ``index`` of one log kind for every environment: ``[n_envs, n_items,
+        n_cols]`` float32 (what ``physics2data`` wrote into ``data.sensors.<kind>.array
+        [index]`` in the reference, physics.py:527-545)."""
+        log, names = self._log, self.names
+        ptr, n_items, cols, vec = dict(
+            links=(log.links_dev, len(names.links.names), sc.link_size, log.links_vec),
+            joints=(log.joints_dev, len(names.joints.names), sc.joint_size, log.joints_vec),
+            contacts=(log.contacts_dev, len(names.contacts.names), sc.contact_size, log.contacts_vec),
+            xfrc=(log.xfrc_dev, len(names.xfrc.names), sc.xfrc_size, log.xfrc_vec),
+        )[kind]
+        if n_items == 0:
+            return np.zeros((self.n_envs, 0, cols), dtype=np.float32)
+        pad = int(log.env_pad)
+        base = _ptr(ptr) + 4*int(index)*n_items*cols*pad
+        raw = self._read(base, (n_items, cols//vec, pad, vec))
+        arr = raw[:, :, :self.n_envs, :].transpose(2, 0, 1, 3)
+        return np.ascontiguousarray(arr).reshape(self.n_envs, n_items, cols)
 
     def export_farms(self, env, data=None):
         """Fill (or create) a reference-shaped float64 ``AnimatData`` for one environment."""

@@ -213,3 +213,23 @@ class FarmsTables:
         self.meters, self.seconds, self.kilograms = units.as_tuple()
         # bodies whose root joint is free: used by host-side sanity checks only
         self.free_root = bool(model.njnt and model.jnt_type[0] == JNT_FREE)
+
+
+def physics2data(physics, iteration, data, maps, units, links_only=False):
+    """Sensors data collection (farms_mujoco/simulation/physics.py:527-545).
+
+    The gathers, the unit scaling, the contact aggregation and the drag model of the
+    reference run inside the CUDA step (csrc/fb_fast.h, csrc/fb_device.h: ring row
+    ``iteration`` of the device log *is* what the reference writes into
+    ``data.sensors.<kind>.array[iteration]``).  This mirror only copies that row to the
+    host-side ``data`` (``BatchedAnimatData``: a leading environment axis), for callers
+    that keep the reference's per-iteration protocol.  ``maps`` and ``units`` were
+    compiled into the engine's tables at construction.
+    """
+    del maps, units
+    sensors = data.sensors
+    sensors.links.array[:, iteration] = physics.log_row('links', iteration)
+    if not links_only:
+        sensors.joints.array[:, iteration] = physics.log_row('joints', iteration)
+        if sensors.contacts.array.shape[2]:
+            sensors.contacts.array[:, iteration] = physics.log_row('contacts', iteration)

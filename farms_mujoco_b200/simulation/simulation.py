@@ -1,0 +1,225 @@
+"""Simulation (mirror of farms_mujoco/simulation/simulation.py for the batched engine).
+
+``Simulation`` keeps the reference's constructor arguments, ``iteration``, ``run``,
+``iterator``, ``postprocess`` and ``save_mjcf_xml``; it steps ``n_envs`` independent
+copies of the model on one B200 instead of one copy on one CPU core.
+
+dm_control is not in this image: the three lines of ``Environment.step`` the reference
+relies on are restated in ``Simulation.step``: the first call
+resets (``initialize_episode``, no physics step), every later call is
+``before_step -> physics.step(n_sub_steps) -> after_step`` and non-finite states raise
+``PhysicsError`` (simulation.py:157-161).
+
+Fused stepping: when no callback and no host-side controller needs to see every
+iteration (``task.device_controller`` or no controller, no callbacks) ``run`` advances
+``chunk`` iterations per kernel launch (``fb_step(h, K)``); the device log then holds
+exactly the rows the per-iteration loop would have produced, and ``postprocess`` reads
+them back.  ``chunk=1`` is the reference's ordering step for step.
+"""
+
+import os
+
+import numpy as np
+import yaml
+
+from ..engine import BatchedPhysics
+from ..mjcf_subset import parse_mjcf
+from .task import ExperimentTask
+
+
+class PhysicsError(RuntimeError):
+    """Diverged state (dm_control.rl.control.PhysicsError, simulation.py:13,157)"""
+
+
+def extract_sub_dict(dictionary, keys):
+    """Extract sub-dictionary (simulation.py:24-30)"""
+    return {key: dictionary.pop(key) for key in keys if key in dictionary}
+
+
+class Simulation:
+    """Simulation (simulation.py:33-213), batched"""
+    # pylint: disable=too-many-instance-attributes
+
+    def __init__(self, mjcf_model, base_link, simulation_options, legacy_step=False, **kwargs):
+        assert not legacy_step, 'legacy_step (mj_step2/mj_step1) gives wrong contact forces (simulation.py:34-38)'
+        self._mjcf_model = mjcf_model
+        self.options = simulation_options
+        self.pause = not self.options.play
+        self.handle_exceptions = kwargs.pop('handle_exceptions', False)
+        engine_kwargs = extract_sub_dict(kwargs, (
+            'n_envs', 'links_names', 'joints_names', 'contacts_names', 'xfrc_names', 'arena_options',
+            'device', 'team_lanes', 'library', 'qpos0', 'qvel0'))
+        env_kwargs = extract_sub_dict(kwargs, ('control_timestep', 'n_sub_steps', 'flat_observation'))
+        self.n_sub_steps = int(env_kwargs.get('n_sub_steps', 1) or 1)
+        self.chunk = int(kwargs.pop('chunk', 0))
+        assert self.options.headless, 'the viewer is outside the batched path'
+        self._qpos0, self._qvel0 = engine_kwargs.pop('qpos0', None), engine_kwargs.pop('qvel0', None)
+        buffer_size = kwargs.get('buffer_size', 0) or self.options.buffer_size or self.options.n_iterations
+        kwargs['buffer_size'] = buffer_size
+        model = parse_mjcf(mjcf_model) if isinstance(mjcf_model, str) else mjcf_model
+        animat_options = kwargs.get('animat_options')
+        self.physics = BatchedPhysics(
+            model, engine_kwargs.pop('n_envs', 1),
+            links_names=engine_kwargs.pop('links_names'), joints_names=engine_kwargs.pop('joints_names'),
+            contacts_names=engine_kwargs.pop('contacts_names', ()), xfrc_names=engine_kwargs.pop('xfrc_names', ()),
+            animat_options=animat_options, arena_options=engine_kwargs.pop('arena_options', None),
+            units=self.options.units, buffer_size=buffer_size, **engine_kwargs)
+        self.task = ExperimentTask(
+            base_link=base_link,
+            n_iterations=self.options.n_iterations,
+            timestep=self.options.timestep,
+            units=self.options.units,
+            substeps=self.options.num_sub_steps,
+            restart=False,
+            **kwargs,
+        )
+        self._reset_next_step = True
+
+    @property
+    def iteration(self):
+        """Iteration"""
+        return self.task.iteration
+
+    @classmethod
+    def from_spec(cls, spec, n_envs=1, **kwargs):
+        """From an ``AnimatSpec`` (models.py): the MJCF text farms_mujoco's ``setup_mjcf_xml``
+        would build plus the option objects.  Stands where ``from_sdf`` stands in the
+        reference (simulation.py:96-124); the SDF -> MJCF conversion itself is init-time
+        host code outside this path."""
+        return cls(
+            mjcf_model=spec.mjcf, base_link=spec.base_link, simulation_options=spec.simulation_options,
+            animat_options=spec.animat_options, arena_options=spec.arena_options, n_envs=n_envs,
+            links_names=spec.links_names, joints_names=spec.joints_names,
+            contacts_names=spec.contacts_names, xfrc_names=spec.xfrc_names, **kwargs)
+
+    @classmethod
+    def from_sdf(cls, simulation_options, animat_options, arena_options, **kwargs):
+        """The reference builds the MJCF from SDF files here (simulation.py:96-124, mjcf.py:1174);
+        that conversion needs farms_core's SDF reader, trimesh and dm_control.mjcf and is not
+        part of the stepping path: build the MJCF with farms_mujoco and use ``Simulation(...)``
+        or ``from_spec``."""
+        raise NotImplementedError(cls.from_sdf.__doc__)
+
+    def save_mjcf_xml(self, path, verbose=False):
+        """Save simulation to mjcf xml (simulation.py:126-132)"""
+        text = self._mjcf_model if isinstance(self._mjcf_model, str) else ''
+        if verbose:
+            print(text)
+        with open(path, 'w+', encoding='utf-8') as xml_file:
+            xml_file.write(text)
+
+    # ----------------------------------------------------------- Environment.step
+    def _check_physics(self):
+        flags = self.physics.flags
+        if (flags & 1).any():
+            raise PhysicsError(f'non-finite state in environments {np.flatnonzero(flags & 1)[:8].tolist()}')
+
+    def step(self, action=None):
+        """dm_control ``Environment.step``"""
+        if self._reset_next_step:
+            self._reset_next_step = False
+            self.task.initialize_episode(self.physics)
+            if self._qpos0 is not None or self._qvel0 is not None:
+                self.physics.reset(self._qpos0, self._qvel0)
+            return
+        self.task.before_step(action, self.physics)
+        self.physics.step(self.n_sub_steps)
+        self._check_physics()
+        self.task.after_step(self.physics)
+        if self.task.get_termination(self.physics):
+            self._reset_next_step = True
+
+    def _can_fuse(self):
+        task = self.task
+        return (not task.callbacks and (task.controller is None or task.device_controller)
+                and task.substeps == 1 and self.n_sub_steps == 1)
+
+    def run(self):
+        """Run simulation (simulation.py:134-162): ``sim_iterations`` calls of ``step``, the
+        first of which is the reset"""
+        n_calls = self.task.sim_iterations
+        try:
+            self.step()
+            done = 1
+            chunk = self.chunk if self.chunk > 0 else 64
+            while done < n_calls:
+                if self._can_fuse() and chunk > 1:
+                    # K iterations in one launch: the device writes the K log rows itself
+                    k = min(chunk, n_calls - done, self.task.n_iterations - self.task.iteration)
+                    assert self.task.iteration + k <= self.task.n_iterations
+                    self.physics.step(k)
+                    self._check_physics()
+                    self.task.sim_iteration += k
+                    self.task.iteration += k
+                    done += k
+                else:
+                    self.step()
+                    done += 1
+        except PhysicsError as err:
+            if self.handle_exceptions:
+                return
+            raise err
+        self.sync_data()
+
+    def iterator(self, show_progress=True, verbose=True):
+        """Run simulation (simulation.py:164-179)"""
+        del show_progress, verbose
+        # as in the reference, the first env.step (inside the first iteration) is the reset
+        for iteration in range(self.task.n_iterations):
+            yield iteration
+            for _ in range(self.task.substeps):
+                self.step()
+
+    def sync_data(self):
+        """Device log -> ``task.data`` (every row written so far).  The per-iteration loop fills
+        ``task.data`` as it goes; after fused launches this brings the host copy up to date."""
+        logs = self.physics.log_arrays()
+        sensors = self.task.data.sensors
+        for kind in ('links', 'joints', 'contacts', 'xfrc'):
+            target = getattr(sensors, kind).array
+            if target.size:
+                target[...] = logs[kind]
+
+    def postprocess(self, iteration, log_path='', plot=False, **kwargs):
+        """Postprocessing after simulation (simulation.py:181-213).  The reference writes
+        ``simulation.hdf5`` through farms_core; h5py is not in this image, so the same arrays
+        go to ``simulation.npz`` (keys ``<kind>`` and ``<kind>_names``); options as YAML."""
+        del kwargs
+        assert not plot, 'plotting is outside the batched path'
+        times = np.arange(0, self.task.timestep*self.task.n_iterations, self.task.timestep)[:iteration]
+        if log_path:
+            os.makedirs(log_path, exist_ok=True)
+            self.sync_data()
+            sensors = self.task.data.sensors
+            payload = {'times': times, 'timestep': self.task.timestep}
+            for kind in ('links', 'joints', 'contacts', 'xfrc'):
+                arr = getattr(sensors, kind)
+                payload[kind] = arr.array[:, :iteration]
+                payload[f'{kind}_names'] = np.array([str(n) for n in arr.names])
+            np.savez_compressed(os.path.join(log_path, 'simulation.npz'), **payload)
+            with open(os.path.join(log_path, 'simulation_options.yaml'), 'w', encoding='utf-8') as out:
+                yaml.safe_dump(_plain(self.options), out)
+            if self.task.animat_options is not None:
+                with open(os.path.join(log_path, 'animat_options.yaml'), 'w', encoding='utf-8') as out:
+                    yaml.safe_dump(_plain(self.task.animat_options), out)
+        return times
+
+
+def _plain(obj):
+    """Dataclass / numpy -> YAML-friendly builtins."""
+    import dataclasses  # pylint: disable=import-outside-toplevel
+    if dataclasses.is_dataclass(obj):
+        return {f.name: _plain(getattr(obj, f.name)) for f in dataclasses.fields(obj)}
+    if isinstance(obj, dict):
+        return {str(k): _plain(v) for k, v in obj.items()}
+    if isinstance(obj, (list, tuple)):
+        return [_plain(v) for v in obj]
+    if isinstance(obj, np.ndarray):
+        return obj.tolist()
+    if isinstance(obj, (np.floating, np.integer)):
+        return obj.item()
+    if isinstance(obj, (str, int, float, bool)) or obj is None:
+        return obj
+    if hasattr(obj, '__dict__'):
+        return {k: _plain(v) for k, v in vars(obj).items() if not k.startswith('_')}
+    return str(obj)

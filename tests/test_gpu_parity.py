@@ -173,3 +173,34 @@ def test_full_size_properties(cuda_library):
     # log quaternions are xyzw unit quaternions; CoM and URDF orientation columns equal
     assert np.allclose(np.linalg.norm(links[:, :, 3:7], axis=-1), 1.0, atol=1e-5)
     assert np.array_equal(links[:, :, 3:7], links[:, :, 10:14])
+
+
+def test_simulation_layer(cuda_library):
+    """Reference-facing loop (Simulation.run, fused launches, on-device controller) on the GPU
+    vs the oracle's replay of the reference's Simulation.run."""
+    from oracle.oracle import OraclePhysics
+    from oracle import farms_oracle as fo
+    from farms_mujoco_b200 import models, mjcf_subset
+    from farms_mujoco_b200.control import TravellingWaveController
+    from farms_mujoco_b200.models import travelling_wave_parameters
+    from farms_mujoco_b200.simulation.simulation import Simulation
+    n_it, n_envs = 24, 96
+    spec = models.salamander(swimming=True, n_iterations=n_it)
+    model = mjcf_subset.parse_mjcf(spec.mjcf)
+    joints, amp, freq, lag = travelling_wave_parameters(spec)
+    phase = np.linspace(0.0, 3.0, n_envs)
+    sim = Simulation.from_spec(spec, n_envs=n_envs, chunk=8, library=cuda_library,
+                               controller=TravellingWaveController(joints, amp, freq, lag, env_phase=phase))
+    sim.run()
+    assert sim.task.device_controller and sim.iteration == n_it - 1
+    acts = [model.actuator_id(f'actuator_position_{j}') for j in joints]
+    for env in (0, 50, n_envs - 1):
+        def controller(iteration, time, env=env):
+            ctrl = np.zeros(model.nu)
+            ctrl[acts] = amp*np.sin(2*np.pi*freq*time - lag + phase[env])
+            return ctrl
+        data, _ = fo.reference_rollout(OraclePhysics(model), spec, sim.physics.tables, n_it,
+                                       controller=controller)
+        for kind in ('links', 'joints', 'contacts', 'xfrc'):
+            ours = getattr(sim.task.data.sensors, kind).array[env]
+            assert scaled_error(ours, getattr(data.sensors, kind).array) < 5e-5, kind

@@ -1,0 +1,148 @@
+"""The reference-facing Python layer (Simulation / ExperimentTask / TaskCallback /
+SwimmingHandler / physics2data mirrors) on the host-emulation build: hook order,
+iteration bookkeeping, per-iteration vs fused stepping, parity with the oracle's replay of
+``Simulation.run`` (oracle/farms_oracle.py: reference_rollout)."""
+
+import os
+
+import numpy as np
+
+from conftest import scaled_error
+from farms_mujoco_b200 import models, mjcf_subset
+from farms_mujoco_b200.control import AnimatController, ControlType, TravellingWaveController
+from farms_mujoco_b200.models import travelling_wave_parameters
+from farms_mujoco_b200.simulation.simulation import Simulation
+from farms_mujoco_b200.simulation.task import ExperimentTask, TaskCallback
+from farms_mujoco_b200.swimming.drag import SwimmingHandler, WaterProperties
+from farms_mujoco_b200.sensors.sensors import cycontacts2data
+
+
+class Recorder(TaskCallback):
+    def __init__(self, **kwargs):
+        super().__init__(**kwargs)
+        self.calls = []
+
+    def initialize_episode(self, task, physics):
+        self.calls.append(('init', task.iteration))
+
+    def before_step(self, task, action, physics):
+        self.calls.append(('before', task.iteration))
+
+    def after_step(self, task, physics):
+        self.calls.append(('after', task.iteration))
+
+
+class HostWave(AnimatController):
+    """A controller with no device form: evaluated on the host every iteration."""
+
+    def __init__(self, joints, amp, freq, lag, phase):
+        super().__init__(joints_names=[list(joints), [], []])
+        self.amp, self.freq, self.lag, self.phase = amp, freq, lag, np.asarray(phase)
+
+    def positions(self, iteration, time, timestep):
+        values = self.amp*np.sin(2*np.pi*self.freq*time - self.lag + self.phase[:, None])
+        return {j: values[:, i] for i, j in enumerate(self.joints_names[ControlType.POSITION])}
+
+
+def test_hook_order_and_iteration_bookkeeping(emu_library):
+    """task.py:168-186,348-369 + Appendix B: the first step resets; n calls = n-1 steps."""
+    spec = models.swimmer8(n_iterations=6)
+    cb = Recorder()
+    sim = Simulation.from_spec(spec, n_envs=2, callbacks=[cb], library=emu_library)
+    sim.run()
+    assert cb.calls[0] == ('init', 0)
+    assert cb.calls[1:5] == [('before', 0), ('after', 1), ('before', 1), ('after', 2)]
+    assert len(cb.calls) == 1 + 2*5 and sim.iteration == 5
+    assert sim.task.sim_iterations == 6 and sim.physics.iteration == 5
+    assert isinstance(sim.task, ExperimentTask)
+    assert sim.task.data.sensors.links.array.shape == (2, 6, 8, 20)
+    assert sim.task.data.sensors.links.array.dtype == np.float64
+    assert np.allclose(sim.task.data.sensors.links.masses, 0.15917403, atol=1e-6)
+
+
+def test_per_iteration_loop_matches_reference_replay(emu_library):
+    """Host controller, one launch per iteration: the reference's ordering exactly."""
+    from oracle.oracle import OraclePhysics
+    from oracle import farms_oracle as fo
+    n_it, phase = 10, [0.3, 1.1]
+    spec = models.salamander(swimming=True, n_iterations=n_it)
+    model = mjcf_subset.parse_mjcf(spec.mjcf)
+    joints, amp, freq, lag = travelling_wave_parameters(spec)
+    sim = Simulation.from_spec(spec, n_envs=2, controller=HostWave(joints, amp, freq, lag, phase),
+                               library=emu_library)
+    assert sim.task.device_controller is False
+    sim.run()
+    acts = [model.actuator_id(f'actuator_position_{j}') for j in joints]
+    for env in range(2):
+        def controller(iteration, time, env=env):
+            ctrl = np.zeros(model.nu)
+            ctrl[acts] = amp*np.sin(2*np.pi*freq*time - lag + phase[env])
+            return ctrl
+        data, states = fo.reference_rollout(OraclePhysics(model), spec, sim.physics.tables, n_it,
+                                            controller=controller)
+        for kind in ('links', 'joints', 'contacts', 'xfrc'):
+            ours = getattr(sim.task.data.sensors, kind).array[env]
+            assert scaled_error(ours, getattr(data.sensors, kind).array) < 2e-5, kind
+        assert scaled_error(sim.physics.qpos[env], states[-1][0]) < 2e-5
+
+
+def test_fused_launches_equal_per_iteration_loop(emu_library):
+    spec = models.swimmer8(n_iterations=40)
+    joints, amp, freq, lag = travelling_wave_parameters(spec)
+    logs = []
+    for callbacks, chunk in (([Recorder()], 0), ([], 16), ([], 1)):
+        ctl = TravellingWaveController(joints, amp, freq, lag, env_phase=[0.0, 0.5, 1.0])
+        sim = Simulation.from_spec(spec, n_envs=3, controller=ctl, callbacks=callbacks, chunk=chunk,
+                                   library=emu_library)
+        sim.run()
+        assert sim.task.device_controller and sim.iteration == 39
+        logs.append({k: getattr(sim.task.data.sensors, k).array.copy() for k in ('links', 'joints', 'xfrc')})
+    for other in logs[1:]:
+        for kind, arr in logs[0].items():
+            assert np.array_equal(arr, other[kind]), kind
+
+
+def test_iterator_and_postprocess(emu_library, tmp_path):
+    spec = models.swimmer8(n_iterations=5)
+    sim = Simulation.from_spec(spec, n_envs=1, library=emu_library)
+    seen = list(sim.iterator(show_progress=False))
+    assert seen == [0, 1, 2, 3, 4] and sim.iteration == 4
+    times = sim.postprocess(sim.iteration, log_path=str(tmp_path))
+    assert len(times) == 4
+    saved = np.load(os.path.join(tmp_path, 'simulation.npz'))
+    assert saved['links'].shape == (1, 4, 8, 20) and list(saved['links_names']) == spec.links_names
+    assert os.path.exists(os.path.join(tmp_path, 'simulation_options.yaml'))
+    assert os.path.exists(os.path.join(tmp_path, 'animat_options.yaml'))
+
+
+def test_swimming_handler_and_contact_mirrors(emu_library):
+    """drag.pyx:309-419 / sensors.pyx:140-190 protocol on top of the fused device step."""
+    spec = models.salamander(swimming=True, n_iterations=4)
+    sim = Simulation.from_spec(spec, n_envs=2, library=emu_library)
+    sim.step()                                   # reset
+    task, physics = sim.task, sim.physics
+    handler = SwimmingHandler(task.data, spec.animat_options, spec.arena_options,
+                              spec.simulation_options.units, physics)
+    assert handler.n_links == len(spec.xfrc_names) and handler.drag and handler.buoyancy
+    assert isinstance(handler.water, WaterProperties) and handler.water.surface() == 0.0
+    sim.step()
+    handler.step(1)
+    assert task.data.sensors.xfrc.array[:, 1].any()
+    assert np.array_equal(task.data.sensors.xfrc.array[:, 1], physics.log_row('xfrc', 1).astype(np.float64))
+    handler.set_water_velocity([0.2, 0.0, 0.0])
+    assert handler.water.velocity().tolist() == [0.2, 0.0, 0.0]
+    cycontacts2data(physics, 1, task.data.sensors.contacts, task.maps['sensors']['geompair2data'], 1.0, 1.0)
+    assert not task.data.sensors.contacts.array[:, 1].any()      # swimming: no contact
+
+
+def test_physics_error_is_raised_or_handled(emu_library):
+    from farms_mujoco_b200.simulation.simulation import PhysicsError
+    import pytest
+    spec = models.swimmer8(n_iterations=4)
+    bad = np.tile(mjcf_subset.parse_mjcf(spec.mjcf).key_qvel, (1, 1)).astype(float)
+    bad[0, 0] = np.inf
+    sim = Simulation.from_spec(spec, n_envs=1, qvel0=bad, library=emu_library)
+    with pytest.raises(PhysicsError):
+        sim.run()
+    sim = Simulation.from_spec(spec, n_envs=1, qvel0=bad, handle_exceptions=True, library=emu_library)
+    sim.run()     # swallowed, as simulation.py:157-161 does with handle_exceptions
