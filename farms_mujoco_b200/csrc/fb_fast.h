@@ -159,6 +159,18 @@ FB_DEV float fb_ld_scr(const float *p) { return __ldcg(p); }
 FB_DEV void fb_st_scr(float *p, float v) { __stcg(p, v); }
 #endif
 
+/* sin and cos of a half joint angle: minimax polynomials on |x| <= pi/4 (the cephes sinf /
+ * cosf kernels, < 1 ulp), the library sincosf beyond (|joint angle| > pi/2 is rare) */
+FB_DEV void fb_sincos_half(float x, float *sn, float *cs) {
+  if (fabsf(x) <= 0.78539816f) {
+    const float z = x*x;
+    *sn = x + x*z*(-1.6666654611e-1f + z*(8.3321608736e-3f + z*(-1.9515295891e-4f)));
+    *cs = 1.0f - 0.5f*z + z*z*(4.166664568298827e-2f + z*(-1.388731625493765e-3f + z*2.443315711809948e-5f));
+  } else {
+    fb_sincos(x, sn, cs);
+  }
+}
+
 template <int BLK> struct FbFast {
   const FbParams &P;
   const DevModel &m;
@@ -214,10 +226,28 @@ FB_UNROLL
     *trq_log = lsum;
   }
 
-  FB_MEM void load_state() {
-    const float *gq = P.qpos + (size_t)env*m.nq, *gv = P.qvel + (size_t)env*m.nv;
-    const float *gx = P.xfrc_applied + (size_t)env*6*m.nbody;
-    const float *g_ctrl = P.ctrl + (size_t)env*(m.nu > 0 ? m.nu : 1);
+  /* State enters and leaves through a shared-memory tile when the block is a full warp: the
+   * warp copies the contiguous [32 envs][n] blocks of qpos / qvel / ctrl / xfrc_applied with
+   * coalesced accesses and every thread then picks its own row from the tile (the body blocks
+   * are not live outside the step loop).  coop = 0: plain per-thread global accesses. */
+  FB_MEM void load_state(int coop, int lane) {
+    const int nq = m.nq, nv = m.nv, nu = m.nu > 0 ? m.nu : 1, nx = 6*m.nbody;
+    const float *gq = P.qpos + (size_t)env*nq, *gv = P.qvel + (size_t)env*nv;
+    const float *gx = P.xfrc_applied + (size_t)env*nx;
+    const float *g_ctrl = P.ctrl + (size_t)env*nu;
+#ifndef FB_HOST_EMU
+    if (coop) {
+      float *tile = s - lane;
+      const size_t e0 = (size_t)(env - lane);
+      for (int i = lane; i < 32*nq; i += 32) tile[i] = P.qpos[e0*nq + i];
+      for (int i = lane; i < 32*nv; i += 32) tile[32*nq + i] = P.qvel[e0*nv + i];
+      for (int i = lane; i < 32*nu; i += 32) tile[32*(nq + nv) + i] = P.ctrl[e0*nu + i];
+      for (int i = lane; i < 32*nx; i += 32) tile[32*(nq + nv + nu) + i] = P.xfrc_applied[e0*nx + i];
+      __syncwarp();
+      gq = tile + lane*nq; gv = tile + 32*nq + lane*nv;
+      g_ctrl = tile + 32*(nq + nv) + lane*nu; gx = tile + 32*(nq + nv + nu) + lane*nx;
+    }
+#endif
     for (int b = 1; b < m.nbody; b++) {
       const FastRec &rc = rec[b];
       float *pg = gblock(b);
@@ -227,8 +257,8 @@ FB_UNROLL
 FB_UNROLL
         for (int k = 0; k < 6; k++) rt[7 + k] = gv[rc.da + k];
       } else if (rc.jtype >= 0) {
-        pg[FG_Q*GS] = gq[rc.qa];
-        pg[FG_QD*GS] = gv[rc.da];
+        fb_st_scr(pg + FG_Q*GS, gq[rc.qa]);
+        fb_st_scr(pg + FG_QD*GS, gv[rc.da]);
         /* constant part of the joint's actuation over this launch (ctrl is held), and of
          * the actuators the farms joint_torque column leaves out */
         float tc = rc.T0, tu = rc.T0U;
@@ -243,16 +273,28 @@ FB_UNROLL
             if (!(a == ap || a == av || a == at)) tu += f;
           }
         }
-        pg[FG_TC*GS] = tc;
-        pg[FG_TU*GS] = tu;
+        fb_st_scr(pg + FG_TC*GS, tc);
+        fb_st_scr(pg + FG_TU*GS, tu);
       }
-      for (int k = 0; k < 6; k++) pg[(FG_W + k)*GS] = gx[6*b + k];
+      for (int k = 0; k < 6; k++) fb_st_scr(pg + (FG_W + k)*GS, gx[6*b + k]);
     }
+#ifndef FB_HOST_EMU
+    if (coop) __syncwarp();      /* the tile becomes the body blocks */
+#endif
   }
 
-  FB_MEM void store_state(long long iteration) {
-    float *gq = P.qpos + (size_t)env*m.nq, *gv = P.qvel + (size_t)env*m.nv;
-    float *gx = P.xfrc_applied + (size_t)env*6*m.nbody;
+  FB_MEM void store_state(long long iteration, int coop, int lane) {
+    const int nq = m.nq, nv = m.nv, nx = 6*m.nbody;
+    float *gq = P.qpos + (size_t)env*nq, *gv = P.qvel + (size_t)env*nv;
+    float *gx = P.xfrc_applied + (size_t)env*nx;
+#ifndef FB_HOST_EMU
+    if (coop) {
+      __syncwarp();              /* every lane is done with its body blocks */
+      float *tile = s - lane;
+      gq = tile + lane*nq; gv = tile + 32*nq + lane*nv; gx = tile + 32*(nq + nv) + lane*nx;
+      for (int k = 0; k < 6; k++) gx[k] = 0.f;      /* the world body carries no wrench */
+    }
+#endif
     for (int b = 1; b < m.nbody; b++) {
       const FastRec &rc = rec[b];
       const float *pg = gblock(b);
@@ -262,11 +304,21 @@ FB_UNROLL
 FB_UNROLL
         for (int k = 0; k < 6; k++) gv[rc.da + k] = rt[7 + k];
       } else if (rc.jtype >= 0) {
-        gq[rc.qa] = pg[FG_Q*GS];
-        gv[rc.da] = pg[FG_QD*GS];
+        gq[rc.qa] = fb_ld_scr(pg + FG_Q*GS);
+        gv[rc.da] = fb_ld_scr(pg + FG_QD*GS);
       }
-      for (int k = 0; k < 6; k++) gx[6*b + k] = pg[(FG_W + k)*GS];
+      for (int k = 0; k < 6; k++) gx[6*b + k] = fb_ld_scr(pg + (FG_W + k)*GS);
     }
+#ifndef FB_HOST_EMU
+    if (coop) {
+      __syncwarp();
+      const float *tile = s - lane;
+      const size_t e0 = (size_t)(env - lane);
+      for (int i = lane; i < 32*nq; i += 32) P.qpos[e0*nq + i] = tile[i];
+      for (int i = lane; i < 32*nv; i += 32) P.qvel[e0*nv + i] = tile[32*nq + i];
+      for (int i = lane; i < 32*nx; i += 32) P.xfrc_applied[e0*nx + i] = tile[32*(nq + nv) + i];
+    }
+#endif
     P.iteration[env] = iteration;
   }
 
@@ -277,11 +329,14 @@ FB_UNROLL
     int active = 0;
     /* scratch values are fetched one body ahead: the L2 round trip overlaps the arithmetic */
     float nq = fb_ld_scr(gblock(1) + FG_Q*GS), nqd = fb_ld_scr(gblock(1) + FG_QD*GS);
+    float *pb = block(1) - FB_NF*BLK;
+    const float *pn = gblock(1);
     for (int b = 1; b < nb; b++) {
       const FastRec &rc = rec[b];
-      float *pb = block(b);
+      pb += FB_NF*BLK;
+      pn += (size_t)FG_NF*GS;
       const float cq = nq, cqd = nqd;
-      if (b + 1 < nb) { const float *pn = gblock(b + 1); nq = fb_ld_scr(pn + FG_Q*GS); nqd = fb_ld_scr(pn + FG_QD*GS); }
+      if (b + 1 < nb) { nq = fb_ld_scr(pn + FG_Q*GS); nqd = fb_ld_scr(pn + FG_QD*GS); }
       const int jtype = rc.jtype;
       Quat q;
       float o[3], v[6], R[9];
@@ -297,7 +352,7 @@ FB_UNROLL
         Quat qp = {1.f, 0.f, 0.f, 0.f};
         float op[3] = {0.f, 0.f, 0.f}, vp[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
         if (rc.parent > 0) {
-          const float *pp = block(rc.parent);
+          const float *pp = (s + rc.pblk*BLK);
           qp.w = pp[(FB_QUAT)*BLK]; qp.x = pp[(FB_QUAT + 1)*BLK]; qp.y = pp[(FB_QUAT + 2)*BLK]; qp.z = pp[(FB_QUAT + 3)*BLK];
 FB_UNROLL
           for (int k = 0; k < 3; k++) op[k] = pp[(FB_ORG + k)*BLK];
@@ -321,7 +376,7 @@ FB_UNROLL
           dq = qj - rc.qpos0;
           if (jtype == FB_JNT_HINGE) {
             float sn, cs;
-            fb_sincos(0.5f*dq, &sn, &cs);
+            fb_sincos_half(0.5f*dq, &sn, &cs);
             Quat ql = {cs, rc.axis[0]*sn, rc.axis[1]*sn, rc.axis[2]*sn};
             q = q_mul(q, ql);
           }
@@ -391,16 +446,18 @@ FB_UNROLL
       nx[6] = fb_ld_scr(pn + FG_Q*GS); nx[7] = fb_ld_scr(pn + FG_QD*GS);
       nx[8] = fb_ld_scr(pn + FG_TC*GS); nx[9] = fb_ld_scr(pn + FG_TU*GS);
     }
+    float *pb = block(nb - 1) + FB_NF*BLK;
+    float *pg = gblock(nb - 1) + (size_t)FG_NF*GS;
     for (int b = nb - 1; b >= 1; b--) {
       const FastRec &rc = rec[b];
-      float *pb = block(b);
-      float *pg = gblock(b);
+      pb -= FB_NF*BLK;
+      pg -= (size_t)FG_NF*GS;
       const int jtype = rc.jtype, flags = rc.flags;
       float cx[10];
 FB_UNROLL
       for (int k = 0; k < 10; k++) cx[k] = nx[k];
       if (b > 1) {
-        const float *pn = gblock(b - 1);
+        const float *pn = pg - (size_t)FG_NF*GS;
 FB_UNROLL
         for (int k = 0; k < 6; k++) nx[k] = fb_ld_scr(pn + (FG_W + k)*GS);
         nx[6] = fb_ld_scr(pn + FG_Q*GS); nx[7] = fb_ld_scr(pn + FG_QD*GS);
@@ -415,7 +472,14 @@ FB_UNROLL
       const float mass = rc.mass;
       float h[3], Iw[6];
       m_rot(R, rc.hloc[0], rc.hloc[1], rc.hloc[2], h);
-      {
+      if (flags & FT_AXISYM) {
+        /* Iw = Ia 1 + dI n n', n = R n_body */
+        float n[3];
+        m_rot(R, rc.Ib[2], rc.Ib[3], rc.Ib[4], n);
+        const float ia = rc.Ib[0], d0 = rc.Ib[1]*n[0], d1 = rc.Ib[1]*n[1], d2 = rc.Ib[1]*n[2];
+        Iw[0] = ia + d0*n[0]; Iw[1] = ia + d1*n[1]; Iw[2] = ia + d2*n[2];
+        Iw[3] = d0*n[1]; Iw[4] = d0*n[2]; Iw[5] = d1*n[2];
+      } else {
         /* Iw = R Ib R' */
         float T[9];
 FB_UNROLL
@@ -551,7 +615,7 @@ FB_UNROLL
       if (rc.parent == 0) continue;        /* fixed base: nothing above */
       /* move to the parent's anchor and hand over */
       {
-        const float *pp = block(rc.parent);
+        const float *pp = (s + rc.pblk*BLK);
         float r[3];
 FB_UNROLL
         for (int k = 0; k < 3; k++) r[k] = pb[(FB_ORG + k)*BLK] - pp[(FB_ORG + k)*BLK];
@@ -591,16 +655,18 @@ FB_UNROLL
       for (int k = 0; k < 9; k++) nx[k] = fb_ld_scr(pn + (FG_W + k)*GS);     /* W, U, DINV, TRQ are contiguous */
       nx[9] = fb_ld_scr(pn + FG_Q*GS); nx[10] = fb_ld_scr(pn + FG_QD*GS);
     }
+    float *pb = block(1) - FB_NF*BLK;
+    float *pg = gblock(1) - (size_t)FG_NF*GS;
     for (int b = 1; b < nb; b++) {
       const FastRec &rc = rec[b];
-      float *pb = block(b);
-      float *pg = gblock(b);
+      pb += FB_NF*BLK;
+      pg += (size_t)FG_NF*GS;
       const int jtype = rc.jtype, flags = rc.flags;
       float cx[11];
 FB_UNROLL
       for (int k = 0; k < 11; k++) cx[k] = nx[k];
       if (b + 1 < nb) {
-        const float *pn = gblock(b + 1);
+        const float *pn = pg + (size_t)FG_NF*GS;
 FB_UNROLL
         for (int k = 0; k < 9; k++) nx[k] = fb_ld_scr(pn + (FG_W + k)*GS);
         nx[9] = fb_ld_scr(pn + FG_Q*GS); nx[10] = fb_ld_scr(pn + FG_QD*GS);
@@ -627,7 +693,7 @@ FB_UNROLL
           bad |= !(fabsf(pn) < 1e30f);
         }
         float angle = hdt*v_normalize3(w), sn, cs;
-        fb_sincos(0.5f*angle, &sn, &cs);
+        fb_sincos_half(0.5f*angle, &sn, &cs);
         Quat qr = {cs, w[0]*sn, w[1]*sn, w[2]*sn};
         Quat qn = q_normalize(q_mul(q, qr));
         rt[3] = qn.w; rt[4] = qn.x; rt[5] = qn.y; rt[6] = qn.z;
@@ -636,7 +702,7 @@ FB_UNROLL
         float ap[6] = {0.f, 0.f, 0.f, -m.grav[0], -m.grav[1], -m.grav[2]};
         float r[3] = {0.f, 0.f, 0.f}, cr[3];
         if (rc.parent > 0) {
-          const float *pp = block(rc.parent);
+          const float *pp = (s + rc.pblk*BLK);
 FB_UNROLL
           for (int k = 0; k < 3; k++) r[k] = pb[(FB_ORG + k)*BLK] - pp[(FB_ORG + k)*BLK];
           if (flags & FT_TO_CARRY) {
@@ -748,8 +814,8 @@ FB_UNROLL
   }
 
   /* Returns the number of steps taken here (n_steps unless a constraint appeared). */
-  FB_MEM int run() {
-    load_state();
+  FB_MEM int run(int coop, int lane) {
+    load_state(coop, lane);
     const size_t e = (size_t)env;
     const int n = P.n_steps;
     int k = 0;
@@ -768,7 +834,7 @@ FB_UNROLL
       for (int i = 0; i < m.n_contacts*3; i++) fb_st4(row_contacts + i*(P.env_pad*FB_VEC_CONTACTS), 0.f, 0.f, 0.f, 0.f);
       if (bad) FB_FLAG_OR(P.flags + env, FB_FLAG_NONFINITE);
     }
-    store_state(P.it0 + k);
+    store_state(P.it0 + k, coop, lane);
     return k;
   }
 };

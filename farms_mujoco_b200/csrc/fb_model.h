@@ -66,6 +66,7 @@ struct DevOffsets {
 #define FT_ACT_SIMPLE 32    /* unclamped actuators, gear 1, all logged: one linear form */
 #define FT_HAS_WAVE 64
 #define FT_HAS_JPOS 128
+#define FT_AXISYM 256        /* inertia = Ib[0]*1 + Ib[1]*n n', n = Ib[2..4] (capsule, cylinder, sphere) */
 
 /* Everything the recursion needs about one body, resolved at model build: no index
  * chasing in the kernel.  The table travels in the kernel parameters (constant bank),
@@ -74,7 +75,7 @@ struct FastRec {
   int32_t parent, jtype, qa, da;          /* joint type -1: welded; qa/da: qpos/qvel address */
   int32_t flags, slot, pslot, link;       /* link: farms link row, -1 */
   int32_t fj, xr, swim, jid;              /* farms joint row, xfrc row, swim index, joint id */
-  int32_t chk0, chk1, wave_act, pad0;     /* plane-check range; ctrl index the wave writes */
+  int32_t chk0, chk1, wave_act, pblk;     /* plane-check range; ctrl index the wave writes; FB_NF*(parent-1) */
   float dpos[3], mass;                    /* body_pos - jnt_pos(parent); body mass */
   float bquat[4];
   float axis[3], qpos0;
@@ -103,6 +104,7 @@ struct DevFastLayout {
   int nslot, n_float;   /* shared floats per environment */
   int n_scratch;        /* global scratch floats per environment */
   int jrow_std;         /* farms joint row = 18 columns, position 0, velocity 1, torque 11 */
+  int coop_io;          /* [32][nq + nv + nu + 6 nbody] fits the warp's shared memory: tiled state I/O */
 };
 
 /* per-environment shared-memory layout (float offsets; component-major SoA:
@@ -524,6 +526,7 @@ inline bool fb_build_model(const FbModel *fm, const FbFarms *ff, const FbWaveCon
         X.ok = 0;
       if (dn == 0) jid = -1, jt = -1;
       r.parent = p; r.jtype = jt; r.jid = jid;
+      r.pblk = FB_NF*(p - 1);
       r.qa = jid >= 0 ? fm->jnt_qposadr[jid] : 0;
       r.da = jid >= 0 ? fm->jnt_dofadr[jid] : 0;
       if (jt == FB_JNT_FREE)
@@ -548,6 +551,16 @@ inline bool fb_build_model(const FbModel *fm, const FbFarms *ff, const FbWaveCon
       auto el = [&](int i, int j) { return R[3*i]*R[3*j]*I3[0] + R[3*i+1]*R[3*j+1]*I3[1] + R[3*i+2]*R[3*j+2]*I3[2]; };
       r.Ib[0] = (float)el(0, 0); r.Ib[1] = (float)el(1, 1); r.Ib[2] = (float)el(2, 2);
       r.Ib[3] = (float)el(0, 1); r.Ib[4] = (float)el(0, 2); r.Ib[5] = (float)el(1, 2);
+      /* two equal principal moments: Ia*1 + (Ic - Ia) n n', n the odd principal axis */
+      for (int odd = 0; odd < 3; odd++) {
+        int e1 = (odd + 1) % 3, e2 = (odd + 2) % 3;
+        if (I3[e1] == I3[e2]) {
+          r.flags |= FT_AXISYM;
+          r.Ib[0] = (float)I3[e1]; r.Ib[1] = (float)(I3[odd] - I3[e1]);
+          r.Ib[2] = (float)R[odd]; r.Ib[3] = (float)R[3 + odd]; r.Ib[4] = (float)R[6 + odd]; r.Ib[5] = 0.f;
+          break;
+        }
+      }
       if (p == b - 1) { r.flags |= FT_TO_CARRY; if (p > 0) rec[p].flags |= FT_ADD_CARRY; }
       else if (p > 0 && rec[p].slot < 0) { rec[p].slot = nslot++; rec[p].flags |= FT_HAS_SLOT; }
       if (p != b - 1 && p > 0) r.pslot = rec[p].slot;
@@ -666,6 +679,7 @@ inline bool fb_build_model(const FbModel *fm, const FbFarms *ff, const FbWaveCon
     X.n_float = X.slots + 27*nslot;
     X.n_scratch = FG_NF*(nb - 1);
     X.jrow_std = m.joint_cols == 18 && m.col_jpos == 0 && m.col_jvel == 1 && m.col_jtrq == 11;
+    X.coop_io = fm->nq + nv + (nu > 0 ? nu : 1) + 6*nb <= X.n_float;
   }
 
   /* water + units */
