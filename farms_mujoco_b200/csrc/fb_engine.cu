@@ -94,8 +94,9 @@ fb_fast_kernel(const __grid_constant__ FbFastParams Q) {
   const int env = blockIdx.x*BLK + threadIdx.x;
   if (blockIdx.x == 0 && threadIdx.x == 0) P.pending_count[P.parity ^ 1] = 0;   /* for the next launch */
   if (env >= P.n_envs) return;
-  /* thread t of the grid owns column t of the L2-resident scratch */
-  FbFast<BLK> st(P, Q.rec, fb_smem + threadIdx.x, P.fast_scratch + env, (size_t)P.fast_scratch_stride, env);
+  /* L2-resident scratch [block][field][lane]: compile-time strides, coalesced */
+  FbFast<BLK> st(P, Q.rec, fb_smem + threadIdx.x,
+                 P.fast_scratch + (size_t)blockIdx.x*P.m.X.n_scratch*BLK + threadIdx.x, env);
   /* full warps move their state through a shared-memory tile (coalesced); a partial last
    * block, or a model whose state rows do not fit the tile, uses per-thread accesses */
   const int coop = BLK == 32 && P.m.X.coop_io && (blockIdx.x + 1)*BLK <= P.n_envs;
@@ -275,7 +276,7 @@ static int launch(FbHandle *h, int mode, int n_steps, int want_derived) {
     P.pending_count[P.parity ^ 1] = 0;
     std::vector<float> fs((size_t)m.X.n_float + 8, 0.f), fg((size_t)m.X.n_scratch + 8, 0.f);
     for (int env = 0; env < P.n_envs; env++) {
-      FbFast<1> st(P, h->hm.rec.data(), fs.data(), fg.data(), 1, env);
+      FbFast<1> st(P, h->hm.rec.data(), fs.data(), fg.data(), env);
       int done = st.run(0, 0);
       if (done < n_steps) { P.steps_done[env] = done; P.pending[P.pending_count[P.parity]++] = env; }
     }

@@ -177,14 +177,13 @@ template <int BLK> struct FbFast {
   const FastRec *rec; /* [nbody], constant bank (kernel parameters) */
   float *s;           /* shared floats, already offset by the thread index */
   const int env;
-  float *gs;          /* global scratch of this thread (stride GS floats between elements) */
-  const size_t GS;
+  float *gs;          /* global scratch of this thread: element i at gs[i*BLK] ([warp][field][lane]) */
   float env_phase;
   float rt[13];       /* floating root: qpos[7], qvel[6] (registers) */
   float rootpos[3];   /* world position the anchors are measured from (the floating root) */
 
-  FB_MEM FbFast(const FbParams &P_, const FastRec *rec_, float *s_, float *gs_, size_t GS_, int env_)
-      : P(P_), m(P_.m), rec(rec_), s(s_), env(env_), gs(gs_), GS(GS_) {
+  FB_MEM FbFast(const FbParams &P_, const FastRec *rec_, float *s_, float *gs_, int env_)
+      : P(P_), m(P_.m), rec(rec_), s(s_), env(env_), gs(gs_) {
     env_phase = P.env_phase[env];
     rootpos[0] = rootpos[1] = rootpos[2] = 0.f;
 FB_UNROLL
@@ -192,7 +191,7 @@ FB_UNROLL
   }
 
   FB_MEM float *block(int b) const { return s + (m.X.body0 + FB_NF*(b - 1))*BLK; }
-  FB_MEM float *gblock(int b) const { return gs + (size_t)(FG_NF*(b - 1))*GS; }
+  FB_MEM float *gblock(int b) const { return gs + FG_NF*(b - 1)*BLK; }
   FB_MEM float *slot(int i) const { return s + (m.X.slots + 27*i)*BLK; }
 
   /* generic actuation (clamps, gears, partial logging): force sum and farms joint_torque */
@@ -257,8 +256,8 @@ FB_UNROLL
 FB_UNROLL
         for (int k = 0; k < 6; k++) rt[7 + k] = gv[rc.da + k];
       } else if (rc.jtype >= 0) {
-        fb_st_scr(pg + FG_Q*GS, gq[rc.qa]);
-        fb_st_scr(pg + FG_QD*GS, gv[rc.da]);
+        fb_st_scr(pg + FG_Q*BLK, gq[rc.qa]);
+        fb_st_scr(pg + FG_QD*BLK, gv[rc.da]);
         /* constant part of the joint's actuation over this launch (ctrl is held), and of
          * the actuators the farms joint_torque column leaves out */
         float tc = rc.T0, tu = rc.T0U;
@@ -273,10 +272,10 @@ FB_UNROLL
             if (!(a == ap || a == av || a == at)) tu += f;
           }
         }
-        fb_st_scr(pg + FG_TC*GS, tc);
-        fb_st_scr(pg + FG_TU*GS, tu);
+        fb_st_scr(pg + FG_TC*BLK, tc);
+        fb_st_scr(pg + FG_TU*BLK, tu);
       }
-      for (int k = 0; k < 6; k++) fb_st_scr(pg + (FG_W + k)*GS, gx[6*b + k]);
+      for (int k = 0; k < 6; k++) fb_st_scr(pg + (FG_W + k)*BLK, gx[6*b + k]);
     }
 #ifndef FB_HOST_EMU
     if (coop) __syncwarp();      /* the tile becomes the body blocks */
@@ -304,10 +303,10 @@ FB_UNROLL
 FB_UNROLL
         for (int k = 0; k < 6; k++) gv[rc.da + k] = rt[7 + k];
       } else if (rc.jtype >= 0) {
-        gq[rc.qa] = fb_ld_scr(pg + FG_Q*GS);
-        gv[rc.da] = fb_ld_scr(pg + FG_QD*GS);
+        gq[rc.qa] = fb_ld_scr(pg + FG_Q*BLK);
+        gv[rc.da] = fb_ld_scr(pg + FG_QD*BLK);
       }
-      for (int k = 0; k < 6; k++) gx[6*b + k] = fb_ld_scr(pg + (FG_W + k)*GS);
+      for (int k = 0; k < 6; k++) gx[6*b + k] = fb_ld_scr(pg + (FG_W + k)*BLK);
     }
 #ifndef FB_HOST_EMU
     if (coop) {
@@ -328,15 +327,15 @@ FB_UNROLL
     const int nb = m.nbody;
     int active = 0;
     /* scratch values are fetched one body ahead: the L2 round trip overlaps the arithmetic */
-    float nq = fb_ld_scr(gblock(1) + FG_Q*GS), nqd = fb_ld_scr(gblock(1) + FG_QD*GS);
+    float nq = fb_ld_scr(gblock(1) + FG_Q*BLK), nqd = fb_ld_scr(gblock(1) + FG_QD*BLK);
     float *pb = block(1) - FB_NF*BLK;
     const float *pn = gblock(1);
     for (int b = 1; b < nb; b++) {
       const FastRec &rc = rec[b];
       pb += FB_NF*BLK;
-      pn += (size_t)FG_NF*GS;
+      pn += FG_NF*BLK;
       const float cq = nq, cqd = nqd;
-      if (b + 1 < nb) { nq = fb_ld_scr(pn + FG_Q*GS); nqd = fb_ld_scr(pn + FG_QD*GS); }
+      if (b + 1 < nb) { nq = fb_ld_scr(pn + FG_Q*BLK); nqd = fb_ld_scr(pn + FG_QD*BLK); }
       const int jtype = rc.jtype;
       Quat q;
       float o[3], v[6], R[9];
@@ -442,26 +441,26 @@ FB_UNROLL
     {
       const float *pn = gblock(nb - 1);
 FB_UNROLL
-      for (int k = 0; k < 6; k++) nx[k] = fb_ld_scr(pn + (FG_W + k)*GS);
-      nx[6] = fb_ld_scr(pn + FG_Q*GS); nx[7] = fb_ld_scr(pn + FG_QD*GS);
-      nx[8] = fb_ld_scr(pn + FG_TC*GS); nx[9] = fb_ld_scr(pn + FG_TU*GS);
+      for (int k = 0; k < 6; k++) nx[k] = fb_ld_scr(pn + (FG_W + k)*BLK);
+      nx[6] = fb_ld_scr(pn + FG_Q*BLK); nx[7] = fb_ld_scr(pn + FG_QD*BLK);
+      nx[8] = fb_ld_scr(pn + FG_TC*BLK); nx[9] = fb_ld_scr(pn + FG_TU*BLK);
     }
     float *pb = block(nb - 1) + FB_NF*BLK;
-    float *pg = gblock(nb - 1) + (size_t)FG_NF*GS;
+    float *pg = gblock(nb - 1) + FG_NF*BLK;
     for (int b = nb - 1; b >= 1; b--) {
       const FastRec &rc = rec[b];
       pb -= FB_NF*BLK;
-      pg -= (size_t)FG_NF*GS;
+      pg -= FG_NF*BLK;
       const int jtype = rc.jtype, flags = rc.flags;
       float cx[10];
 FB_UNROLL
       for (int k = 0; k < 10; k++) cx[k] = nx[k];
       if (b > 1) {
-        const float *pn = pg - (size_t)FG_NF*GS;
+        const float *pn = pg - FG_NF*BLK;
 FB_UNROLL
-        for (int k = 0; k < 6; k++) nx[k] = fb_ld_scr(pn + (FG_W + k)*GS);
-        nx[6] = fb_ld_scr(pn + FG_Q*GS); nx[7] = fb_ld_scr(pn + FG_QD*GS);
-        nx[8] = fb_ld_scr(pn + FG_TC*GS); nx[9] = fb_ld_scr(pn + FG_TU*GS);
+        for (int k = 0; k < 6; k++) nx[k] = fb_ld_scr(pn + (FG_W + k)*BLK);
+        nx[6] = fb_ld_scr(pn + FG_Q*BLK); nx[7] = fb_ld_scr(pn + FG_QD*BLK);
+        nx[8] = fb_ld_scr(pn + FG_TC*BLK); nx[9] = fb_ld_scr(pn + FG_TU*BLK);
       }
       const Quat q = {pb[(FB_QUAT)*BLK], pb[(FB_QUAT + 1)*BLK], pb[(FB_QUAT + 2)*BLK], pb[(FB_QUAT + 3)*BLK]};
       float R[9], v[6], fx[6];
@@ -609,8 +608,8 @@ FB_UNROLL
 FB_UNROLL
         for (int k = 0; k < 3; k++) pA[3 + k] += t0[k] + t1[k] + U[3 + k]*ud;
 FB_UNROLL
-        for (int k = 0; k < 6; k++) fb_st_scr(pg + (FG_W + k)*GS, U[k]);
-        fb_st_scr(pg + FG_U*GS, u); fb_st_scr(pg + FG_DINV*GS, dinv); fb_st_scr(pg + FG_TRQ*GS, trq);
+        for (int k = 0; k < 6; k++) fb_st_scr(pg + (FG_W + k)*BLK, U[k]);
+        fb_st_scr(pg + FG_U*BLK, u); fb_st_scr(pg + FG_DINV*BLK, dinv); fb_st_scr(pg + FG_TRQ*BLK, trq);
       }
       if (rc.parent == 0) continue;        /* fixed base: nothing above */
       /* move to the parent's anchor and hand over */
@@ -652,24 +651,24 @@ FB_UNROLL
     {
       const float *pn = gblock(1);
 FB_UNROLL
-      for (int k = 0; k < 9; k++) nx[k] = fb_ld_scr(pn + (FG_W + k)*GS);     /* W, U, DINV, TRQ are contiguous */
-      nx[9] = fb_ld_scr(pn + FG_Q*GS); nx[10] = fb_ld_scr(pn + FG_QD*GS);
+      for (int k = 0; k < 9; k++) nx[k] = fb_ld_scr(pn + (FG_W + k)*BLK);     /* W, U, DINV, TRQ are contiguous */
+      nx[9] = fb_ld_scr(pn + FG_Q*BLK); nx[10] = fb_ld_scr(pn + FG_QD*BLK);
     }
     float *pb = block(1) - FB_NF*BLK;
-    float *pg = gblock(1) - (size_t)FG_NF*GS;
+    float *pg = gblock(1) - FG_NF*BLK;
     for (int b = 1; b < nb; b++) {
       const FastRec &rc = rec[b];
       pb += FB_NF*BLK;
-      pg += (size_t)FG_NF*GS;
+      pg += FG_NF*BLK;
       const int jtype = rc.jtype, flags = rc.flags;
       float cx[11];
 FB_UNROLL
       for (int k = 0; k < 11; k++) cx[k] = nx[k];
       if (b + 1 < nb) {
-        const float *pn = pg + (size_t)FG_NF*GS;
+        const float *pn = pg + FG_NF*BLK;
 FB_UNROLL
-        for (int k = 0; k < 9; k++) nx[k] = fb_ld_scr(pn + (FG_W + k)*GS);
-        nx[9] = fb_ld_scr(pn + FG_Q*GS); nx[10] = fb_ld_scr(pn + FG_QD*GS);
+        for (int k = 0; k < 9; k++) nx[k] = fb_ld_scr(pn + (FG_W + k)*BLK);
+        nx[9] = fb_ld_scr(pn + FG_Q*BLK); nx[10] = fb_ld_scr(pn + FG_QD*BLK);
       }
       const Quat q = {pb[(FB_QUAT)*BLK], pb[(FB_QUAT + 1)*BLK], pb[(FB_QUAT + 2)*BLK], pb[(FB_QUAT + 3)*BLK]};
       float R[9], v[6], a[6];
@@ -738,8 +737,8 @@ FB_UNROLL
           if (jtype == FB_JNT_HINGE) { a[0] += ax[0]*qdd; a[1] += ax[1]*qdd; a[2] += ax[2]*qdd; }
           else { a[3] += ax[0]*qdd; a[4] += ax[1]*qdd; a[5] += ax[2]*qdd; }
           const float qdn = qd + hdt*qdd, qn = qj + hdt*qdn;
-          fb_st_scr(pg + FG_QD*GS, qdn);
-          fb_st_scr(pg + FG_Q*GS, qn);
+          fb_st_scr(pg + FG_QD*BLK, qdn);
+          fb_st_scr(pg + FG_Q*BLK, qn);
           bad |= !(fabsf(qn) < 1e30f);
           /* joints row: physics.py:481-524 (new position/velocity, forces of the old state) */
           if (rc.fj >= 0) {
@@ -802,12 +801,12 @@ FB_UNROLL
         float *row = row_xfrc + (long long)(3*rc.xr)*ev;
         fb_st2(row, F[0], F[1]); fb_st2(row + ev, F[2], Tq[0]); fb_st2(row + 2*ev, Tq[1], Tq[2]);
 FB_UNROLL
-        for (int k = 0; k < 3; k++) { fb_st_scr(pg + (FG_W + k)*GS, wf[k]); fb_st_scr(pg + (FG_W + 3 + k)*GS, wt[k]); }
+        for (int k = 0; k < 3; k++) { fb_st_scr(pg + (FG_W + k)*BLK, wf[k]); fb_st_scr(pg + (FG_W + 3 + k)*BLK, wt[k]); }
       } else {
         /* user-applied wrench: persistent, re-read (the slot held U during this step) */
         const float *gx = P.xfrc_applied + ((size_t)env*m.nbody + b)*6;
 FB_UNROLL
-        for (int k = 0; k < 6; k++) fb_st_scr(pg + (FG_W + k)*GS, gx[k]);
+        for (int k = 0; k < 6; k++) fb_st_scr(pg + (FG_W + k)*BLK, gx[k]);
       }
     }
     return bad;
