@@ -330,6 +330,9 @@ FB_UNROLL
     float nq = fb_ld_scr(gblock(1) + FG_Q*BLK), nqd = fb_ld_scr(gblock(1) + FG_QD*BLK);
     float *pb = block(1) - FB_NF*BLK;
     const float *pn = gblock(1);
+    Quat lastq = {1.f, 0.f, 0.f, 0.f};
+    float lasto[3] = {0.f, 0.f, 0.f}, lastv[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    float lastR[9] = {1.f, 0.f, 0.f, 0.f, 1.f, 0.f, 0.f, 0.f, 1.f};
     for (int b = 1; b < nb; b++) {
       const FastRec &rc = rec[b];
       pb += FB_NF*BLK;
@@ -339,6 +342,15 @@ FB_UNROLL
       const int jtype = rc.jtype;
       Quat q;
       float o[3], v[6], R[9];
+      /* pose / velocity / rotation of body b-1, still in registers for a chain child */
+      const Quat ql_ = lastq;
+      float lo_[3], lv_[6], lR_[9];
+FB_UNROLL
+      for (int k = 0; k < 3; k++) lo_[k] = lasto[k];
+FB_UNROLL
+      for (int k = 0; k < 6; k++) lv_[k] = lastv[k];
+FB_UNROLL
+      for (int k = 0; k < 9; k++) lR_[k] = lastR[k];
       if (jtype == FB_JNT_FREE) {
         Quat qq = {rt[3], rt[4], rt[5], rt[6]};
         q = q_normalize(qq);
@@ -350,16 +362,27 @@ FB_UNROLL
       } else {
         Quat qp = {1.f, 0.f, 0.f, 0.f};
         float op[3] = {0.f, 0.f, 0.f}, vp[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-        if (rc.parent > 0) {
-          const float *pp = (s + rc.pblk*BLK);
-          qp.w = pp[(FB_QUAT)*BLK]; qp.x = pp[(FB_QUAT + 1)*BLK]; qp.y = pp[(FB_QUAT + 2)*BLK]; qp.z = pp[(FB_QUAT + 3)*BLK];
-FB_UNROLL
-          for (int k = 0; k < 3; k++) op[k] = pp[(FB_ORG + k)*BLK];
-FB_UNROLL
-          for (int k = 0; k < 6; k++) vp[k] = pp[(FB_VEL + k)*BLK];
-        }
         float Rp[9], r[3], dq = 0.f, qd = 0.f;
-        q_mat(qp, Rp);
+        if (rc.flags & FT_TO_CARRY) {
+          /* the parent is the previous body: its pose is still in registers */
+          qp = ql_;
+FB_UNROLL
+          for (int k = 0; k < 3; k++) op[k] = lo_[k];
+FB_UNROLL
+          for (int k = 0; k < 6; k++) vp[k] = lv_[k];
+FB_UNROLL
+          for (int k = 0; k < 9; k++) Rp[k] = lR_[k];
+        } else {
+          if (rc.parent > 0) {
+            const float *pp = (s + rc.pblk*BLK);
+            qp.w = pp[(FB_QUAT)*BLK]; qp.x = pp[(FB_QUAT + 1)*BLK]; qp.y = pp[(FB_QUAT + 2)*BLK]; qp.z = pp[(FB_QUAT + 3)*BLK];
+FB_UNROLL
+            for (int k = 0; k < 3; k++) op[k] = pp[(FB_ORG + k)*BLK];
+FB_UNROLL
+            for (int k = 0; k < 6; k++) vp[k] = pp[(FB_VEL + k)*BLK];
+          }
+          q_mat(qp, Rp);
+        }
         m_rot(Rp, rc.dpos[0], rc.dpos[1], rc.dpos[2], r);
         Quat bq = {rc.bquat[0], rc.bquat[1], rc.bquat[2], rc.bquat[3]};
         q = q_mul(qp, bq);
@@ -399,6 +422,13 @@ FB_UNROLL
       for (int k = 0; k < 3; k++) pb[(FB_ORG + k)*BLK] = o[k];
 FB_UNROLL
       for (int k = 0; k < 6; k++) pb[(FB_VEL + k)*BLK] = v[k];
+      lastq = q;
+FB_UNROLL
+      for (int k = 0; k < 3; k++) lasto[k] = o[k];
+FB_UNROLL
+      for (int k = 0; k < 6; k++) lastv[k] = v[k];
+FB_UNROLL
+      for (int k = 0; k < 9; k++) lastR[k] = R[k];
       float xpos[3] = {rootpos[0] + o[0], rootpos[1] + o[1], rootpos[2] + o[2]};
       if (rc.flags & FT_HAS_JPOS) {
         float t[3];
