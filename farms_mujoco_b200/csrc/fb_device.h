@@ -921,13 +921,21 @@ FB_UNROLL
       }
       sync();
       md_times(qacc, tmp1);                      /* tmp1 = M a */
-      for (int v = lane; v < nv; v += TEAM) { tmp1[v] -= fsm[v]; grad[v] = tmp1[v]; }
+      float gref = 0.f;                          /* magnitude of the terms the gradient is the difference of */
+      for (int v = lane; v < nv; v += TEAM) {
+        gref += tmp1[v]*tmp1[v] + fsm[v]*fsm[v];
+        tmp1[v] -= fsm[v]; grad[v] = tmp1[v];
+      }
+      gref = T::sum(mask, gref);
       sync();
       rows_tapply(frc, grad, 1);                 /* grad = M a - fsm + J' y */
       float gn = 0.f;
       for (int v = lane; v < nv; v += TEAM) gn += grad[v]*grad[v];
       gn = T::sum(mask, gn);
-      if (sqrtf(gn)*m.solver_scale < m.tolerance) break;
+      /* MuJoCo's test (scaled gradient < tolerance, 1e-8 by default) is out of reach of fp32:
+       * once the active set is right the gradient is rounding noise, ~5e-6 of the terms it is
+       * the difference of.  Stop at whichever floor comes first. */
+      if (sqrtf(gn)*m.solver_scale < fmaxf(m.tolerance, 2e-5f*sqrtf(gref)*m.solver_scale)) break;
       /* H = M + sum_active D J'J (packed lower) */
       for (int e = lane; e < m.npack; e += TEAM) {
         int u = (int)((sqrtf(8.f*(float)e + 1.f) - 1.f)*0.5f);
@@ -1041,6 +1049,7 @@ FB_UNROLL
       sync();
       if (st <= 1e-14f*a2) break;
     }
+
     /* constraint forces */
     rows_apply(qacc, res);
     for (int r = lane; r < nrow; r += TEAM) {

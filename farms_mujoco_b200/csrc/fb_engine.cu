@@ -516,6 +516,21 @@ int fb_set_wave_controller(FbHandle *h, const FbWaveController *c) {
   return upload_model(h);
 }
 
+int fb_set_actuator_forcerange(FbHandle *h, int n, const int32_t *actuator, const int32_t *limited,
+                               const double *range) {
+  if (!h || (n > 0 && (!actuator || !limited || !range))) return fail("null argument");
+  /* the handle owns deep copies of the model arrays (deep_copy_model): edit them, rebuild */
+  int32_t *fl = const_cast<int32_t *>(h->fm_shallow.actuator_forcelimited);
+  double *fr = const_cast<double *>(h->fm_shallow.actuator_forcerange);
+  for (int i = 0; i < n; i++) {
+    int a = actuator[i];
+    if (a < 0 || a >= h->fm_shallow.nu) return fail("fb_set_actuator_forcerange: bad actuator index");
+    fl[a] = limited[i] != 0;
+    fr[2*a] = range[2*i]; fr[2*a + 1] = range[2*i + 1];
+  }
+  return upload_model(h);
+}
+
 int fb_set_water_velocity(FbHandle *h, double vx, double vy, double vz) {
   if (!h) return fail("null handle");
   if (!h->has_farms) return fail("no farms tables");

@@ -266,7 +266,7 @@ FB_UNROLL
           if (rc.fj >= 0) { ap = MI(fj_actpos, rc.fj); av = MI(fj_actvel, rc.fj); at = MI(fj_acttrq, rc.fj); }
           for (int t = MI(jnt_actstart, rc.jid); t < MI(jnt_actstart, rc.jid + 1); t++) {
             int a = MI(act_sorted, t);
-            if (a == rc.wave_act) continue;
+            if (a == rc.wave_act || MI(ft_actoff, a)) continue;
             float f = MF(act_gain, a)*g_ctrl[a];
             tc += f;
             if (!(a == ap || a == av || a == at)) tu += f;

@@ -52,6 +52,7 @@ struct DevOffsets {
   int key_qpos, key_qvel;
   /* tables of the environment-per-thread path (fb_fast.h) */
   int ft_actwc;   /* int   [nu] wave index of an actuator, -1 */
+  int ft_actoff;  /* int   [nu] 1: force-limited to [0, 0] (contributes nothing) */
   int ft_chk;     /* float [nchk][4] conservative plane checks (normal, offset) */
 };
 
@@ -609,6 +610,7 @@ inline bool fb_build_model(const FbModel *fm, const FbFarms *ff, const FbWaveCon
     }
     /* actuation: one linear form per joint when nothing clamps, gears are 1 and the farms
      * joint_torque column sums exactly the joint's actuators (physics.py:510-524) */
+    std::vector<int32_t> is_off(nu > 0 ? nu : 1, 0);
     for (int b = 1; b < nb; b++) {
       FastRec &r = rec[b];
       if (r.jid < 0 || r.jtype == FB_JNT_FREE) continue;
@@ -617,6 +619,10 @@ inline bool fb_build_model(const FbModel *fm, const FbFarms *ff, const FbWaveCon
       double Kq = 0, Kqd = 0, T0 = 0, KqU = 0, KqdU = 0, T0U = 0;
       for (int a = 0; a < nu; a++) {
         if (fm->actuator_trnid[a] != r.jid) continue;
+        /* switched off by initialize_control (task.py:274-286): contributes exactly zero */
+        const bool off = fm->actuator_forcelimited[a] && fm->actuator_forcerange[2*a] == 0.0 &&
+                         fm->actuator_forcerange[2*a + 1] == 0.0;
+        if (off && actwc[a] < 0) { is_off[a] = 1; continue; }
         if (fm->actuator_ctrllimited[a] || fm->actuator_forcelimited[a] || fm->actuator_gear[a] != 1.0) simple = false;
         bool logged = r.fj >= 0 && (ff->joint_act_position[r.fj] == a || ff->joint_act_velocity[r.fj] == a ||
                                     ff->joint_act_torque[r.fj] == a);
@@ -672,6 +678,7 @@ inline bool fb_build_model(const FbModel *fm, const FbFarms *ff, const FbWaveCon
       }
     }
     o.ft_actwc = put_i(I, actwc);
+    o.ft_actoff = put_i(I, is_off);
     o.ft_chk = put_f(F, chk);
     X.body0 = 0;
     X.slots = FB_NF*(nb - 1);

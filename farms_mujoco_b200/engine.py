@@ -36,6 +36,7 @@ ABI_SYMBOLS = {
     'fb_set_qpos_spring': (ct.c_int, [_H, cabi.c_double_p]),
     'fb_set_env_phase': (ct.c_int, [_H, cabi.c_double_p]),
     'fb_set_wave_controller': (ct.c_int, [_H, ct.POINTER(cabi.FbWaveController)]),
+    'fb_set_actuator_forcerange': (ct.c_int, [_H, ct.c_int, ct.POINTER(ct.c_int32), ct.POINTER(ct.c_int32), cabi.c_double_p]),
     'fb_set_water_velocity': (ct.c_int, [_H, ct.c_double, ct.c_double, ct.c_double]),
     'fb_set_swimming': (ct.c_int, [_H, ct.c_int, ct.c_int]),
     'fb_step': (ct.c_int, [_H, ct.c_int, ct.c_int, ct.c_int]),
@@ -238,6 +239,20 @@ class BatchedPhysics:
         keep.set_double('phase_lag', phase_lag)
         keep.set_double('offset', np.zeros(n) if offset is None else offset)
         self._check(self.lib.fb_set_wave_controller(self._handle, keep.byref()))
+
+    def set_actuator_forcerange(self, actuators, limited, forcerange):
+        """``physics.named.model.actuator_forcelimited / actuator_forcerange`` edits of
+        ``initialize_control`` (task.py:274-286); also applied to ``self.model``."""
+        acts = np.ascontiguousarray(actuators, dtype=np.int32)
+        lim = np.ascontiguousarray(np.broadcast_to(limited, acts.shape), dtype=np.int32)
+        rng = np.ascontiguousarray(np.broadcast_to(forcerange, acts.shape + (2,)), dtype=np.float64)
+        self._check(self.lib.fb_set_actuator_forcerange(
+            self._handle, len(acts), acts.ctypes.data_as(ct.POINTER(ct.c_int32)),
+            lim.ctypes.data_as(ct.POINTER(ct.c_int32)), rng.ctypes.data_as(cabi.c_double_p)))
+        self.model.actuator_forcelimited = np.array(self.model.actuator_forcelimited).copy()
+        self.model.actuator_forcerange = np.array(self.model.actuator_forcerange, dtype=float).reshape(-1, 2).copy()
+        self.model.actuator_forcelimited[acts] = lim
+        self.model.actuator_forcerange[acts] = rng
 
     def set_water_velocity(self, velocity):
         self._check(self.lib.fb_set_water_velocity(self._handle, *[float(v) for v in velocity]))

@@ -157,9 +157,23 @@ class ExperimentTask:
         self.maps['ctrl']['springref'] = {
             joint: int(model.jnt_qposadr[model.jnt_id(joint)])
             for joint in model.jnt_names if model.jnt_type[model.jnt_id(joint)] != 0}
-        # the reference also force-limits to [0, 0] the position/velocity actuators of joints
-        # whose motor has no 'position' control type (task.py:262-286); that edit is a model
-        # edit: models.py applies it when it emits the MJCF (models._emit_mjcf)
+        # Actuator limits (task.py:252-286): position / velocity actuators of joints whose motor
+        # has no 'position' control type are force-limited to [0, 0] -- a model edit
+        jntname2actid = {name: {} for name in model.jnt_names}
+        biasprm = np.asarray(model.actuator_biasprm).reshape(model.nu, -1)
+        trnid = np.asarray(model.actuator_trnid).reshape(model.nu, -1)[:, 0]
+        for act_i in range(model.nu):
+            act_type = 'pos' if biasprm[act_i, 1] != 0 else 'vel' if biasprm[act_i, 2] != 0 else 'trq'
+            jntname2actid[model.jnt_names[trnid[act_i]]][act_type] = act_i
+        if self.animat_options is not None:
+            disabled = []
+            for mtr_opts in self.animat_options.control.motors:
+                jnt_name = mtr_opts['joint_name']
+                if 'position' not in mtr_opts.control_types:
+                    disabled += [jntname2actid[jnt_name][t] for t in ('pos', 'vel')
+                                 if t in jntname2actid[jnt_name]]
+            if disabled:
+                physics.set_actuator_forcerange(disabled, True, [0.0, 0.0])
         if hasattr(self._controller, 'device_parameters') and not self._callbacks_need_ctrl():
             params = self._controller.device_parameters()
             acts = [ctrl_names.index(f'actuator_position_{j}') for j in params['joints']]

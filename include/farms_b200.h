@@ -179,6 +179,11 @@ int fb_set_ctrl(FbHandle *h, const double *ctrl);                 /* [n_envs][nu
 int fb_set_qpos_spring(FbHandle *h, const double *qpos_spring);   /* [n_envs][nq] */
 int fb_set_env_phase(FbHandle *h, const double *phase);           /* [n_envs] */
 int fb_set_wave_controller(FbHandle *h, const FbWaveController *c); /* NULL -> off */
+/* Model edit of ExperimentTask.initialize_control (task.py:262-286): the reference sets
+ * actuator_forcelimited / actuator_forcerange ([0, 0]) on the position and velocity
+ * actuators of joints whose motor has no 'position' control type.  limited[n], range[n][2]. */
+int fb_set_actuator_forcerange(FbHandle *h, int n, const int32_t *actuator, const int32_t *limited,
+                               const double *range);
 /* Water velocity (drag.pyx:417-419 set_water_velocity). */
 int fb_set_water_velocity(FbHandle *h, double vx, double vy, double vz);
 /* Drag on/off overrides for the fused swimming step (drag.pyx:393-395). */

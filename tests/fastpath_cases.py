@@ -86,3 +86,24 @@ def check_paths_agree(library, name, n_envs, n_steps=10, tol=1e-4):
     assert scaled_error(outs[True][3], outs[False][3]) < tol
     for kind in ('links', 'joints', 'contacts', 'xfrc'):
         assert scaled_error(outs[True][2][kind], outs[False][2][kind]) < tol, kind
+
+
+def check_variant(library, spec, n_envs=3, n_steps=15, tol=1e-5, free_base=True):
+    """Per-thread kernel on a hand-edited model (tests/variant_models.py) vs the oracle."""
+    from farms_mujoco_b200 import mjcf_subset
+    from farms_mujoco_b200.engine import BatchedPhysics
+    model = mjcf_subset.parse_mjcf(spec.mjcf)
+    rng = np.random.default_rng(1)
+    qpos0 = np.tile(model.key_qpos, (n_envs, 1))
+    first = 7 if free_base else 0
+    qpos0[:, first:] += rng.uniform(-0.1, 0.1, (n_envs, model.nq - first))
+    qvel0 = rng.uniform(-0.3, 0.3, (n_envs, model.nv))
+    ctrl = rng.uniform(-0.3, 0.3, (n_envs, model.nu))
+    physics = BatchedPhysics.from_spec(spec, n_envs, buffer_size=n_steps + 1, library=library)
+    assert physics.fast_path
+    physics.reset(qpos0, qvel0)
+    physics.set_ctrl(ctrl)
+    physics.step(n_steps)
+    assert physics.last_pending == 0
+    envs = sorted({0, n_envs//2, n_envs - 1})
+    return compare_with_oracle(spec, model, physics, qpos0, qvel0, ctrl, envs, n_steps, tol)

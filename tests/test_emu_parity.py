@@ -64,6 +64,20 @@ def test_fast_and_team_paths_agree(emu_library):
     fastpath_cases.check_paths_agree(emu_library, 'salamander_swim', n_envs=2)
 
 
+def test_fast_path_joint_and_actuator_variants(emu_library):
+    """Slide joint, off-origin anchors, tilted axes, stiffness + springref, rotated body
+    frame, general inertia, ctrl / force clamps, geared motor: 15 steps within 1e-5."""
+    import fastpath_cases
+    import variant_models
+    fastpath_cases.check_variant(emu_library, variant_models.swimmer8_features())
+
+
+def test_fast_path_fixed_base(emu_library):
+    import fastpath_cases
+    import variant_models
+    fastpath_cases.check_variant(emu_library, variant_models.swimmer8_fixed_base(), free_base=False)
+
+
 def test_log_layout_is_reference_layout(emu_library):
     """Row k: links/contacts of state k-1 (k=0: state 0), joints qpos/qvel of state k
     (SURVEY.md Appendix D-1); quaternions xyzw; unwritten joint columns stay zero."""

@@ -87,6 +87,14 @@ def test_hand_over_mid_launch(cuda_library, name):
     fastpath_cases.check_hand_over(cuda_library, name, n_envs=70)
 
 
+@pytest.mark.parametrize('variant,free_base', [('swimmer8_features', True), ('swimmer8_fixed_base', False)])
+def test_model_variants(cuda_library, variant, free_base):
+    import fastpath_cases
+    import variant_models
+    fastpath_cases.check_variant(cuda_library, getattr(variant_models, variant)(), n_envs=70,
+                                 free_base=free_base)
+
+
 def test_paths_agree(cuda_library):
     import fastpath_cases
     fastpath_cases.check_paths_agree(cuda_library, 'salamander_swim', n_envs=96)

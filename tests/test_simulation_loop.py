@@ -146,3 +146,59 @@ def test_physics_error_is_raised_or_handled(emu_library):
         sim.run()
     sim = Simulation.from_spec(spec, n_envs=1, qvel0=bad, handle_exceptions=True, library=emu_library)
     sim.run()     # swallowed, as simulation.py:157-161 does with handle_exceptions
+
+
+class HostTorque(AnimatController):
+    """Torque control + spring references, evaluated on the host (task.py:323-346)."""
+
+    def __init__(self, joints, n_envs):
+        super().__init__(joints_names=[[], [], list(joints)])
+        self.n_envs = n_envs
+
+    def torques(self, iteration, time, timestep):
+        return {j: 0.002*np.sin(40*time + i + np.arange(self.n_envs))
+                for i, j in enumerate(self.joints_names[ControlType.TORQUE])}
+
+    def springrefs(self, iteration, time, timestep):
+        return {self.joints_names[ControlType.TORQUE][0]: 0.1}
+
+
+def test_torque_control_disables_position_actuators(emu_library):
+    """initialize_control (task.py:262-286): motors without the 'position' control type get
+    their position / velocity actuators force-limited to [0, 0]; torques reach ctrl scaled by
+    units.torques; springrefs land in qpos_spring."""
+    import copy
+    import dataclasses
+    from oracle.oracle import OraclePhysics
+    from oracle import farms_oracle as fo
+    n_it, n_envs = 8, 2
+    spec = models.swimmer8(n_iterations=n_it)
+    animat = copy.deepcopy(spec.animat_options)
+    for motor in animat.control.motors:
+        motor.control_types = ['torque']
+    spec = dataclasses.replace(spec, animat_options=animat)
+    sim = Simulation.from_spec(spec, n_envs=n_envs, controller=HostTorque(spec.joints_names, n_envs),
+                               library=emu_library)
+    sim.run()
+    model = sim.physics.model
+    pos = [model.actuator_id(f'actuator_position_{j}') for j in spec.joints_names]
+    vel = [model.actuator_id(f'actuator_velocity_{j}') for j in spec.joints_names]
+    trq = [model.actuator_id(f'actuator_torque_{j}') for j in spec.joints_names]
+    assert np.asarray(model.actuator_forcelimited)[pos + vel].all()
+    assert not np.asarray(model.actuator_forcerange).reshape(-1, 2)[pos + vel].any()
+    assert not np.asarray(model.actuator_forcelimited)[trq].any()
+    assert sim.physics.qpos_spring[:, 7].tolist() == [np.float32(0.1)]*n_envs
+    controller = HostTorque(spec.joints_names, n_envs)
+    for env in range(n_envs):
+        def ctrl_of(iteration, time, env=env):
+            ctrl = np.zeros(model.nu)
+            values = controller.torques(iteration, time, model.timestep)
+            for act, joint in zip(trq, spec.joints_names):
+                ctrl[act] = values[joint][env]
+            return ctrl
+        oracle = OraclePhysics(model)          # the edited model
+        oracle.model.qpos_spring[7] = 0.1
+        data, _ = fo.reference_rollout(oracle, spec, sim.physics.tables, n_it, controller=ctrl_of)
+        for kind in ('links', 'joints', 'xfrc'):
+            ours = getattr(sim.task.data.sensors, kind).array[env]
+            assert scaled_error(ours, getattr(data.sensors, kind).array) < 2e-5, kind

@@ -1,0 +1,70 @@
+"""Hand-edited variants of the SWIMMER8 MJCF that leave the synthetic models' comfort zone:
+slide joint, joint anchors off the body origin, tilted axes, joint stiffness + springref,
+rotated body frame, general (non-axisymmetric) inertia with off-diagonals, ctrl / force
+clamps, a geared motor, and a fixed base.  Used by the emulation and GPU parity tests."""
+
+import copy
+import dataclasses
+import re
+
+from farms_mujoco_b200 import models
+
+
+def swimmer8_features():
+    spec = models.swimmer8()
+    x = spec.mjcf
+    edits = [
+        ('<joint name="joint_1" type="hinge" axis="0.0 0.0 1.0" pos="0.0 0.0 0.0"',
+         '<joint name="joint_1" type="slide" axis="0.0 1.0 0.0" pos="0.01 0.0 0.0"'),
+        ('<joint name="joint_2" type="hinge" axis="0.0 0.0 1.0" pos="0.0 0.0 0.0"',
+         '<joint name="joint_2" type="hinge" axis="0.0 0.6 0.8" pos="0.02 0.01 -0.01"'),
+        ('<joint name="joint_3" type="hinge" axis="0.0 0.0 1.0" pos="0.0 0.0 0.0" damping="0.001" '
+         'stiffness="0.0" springref="0.0"',
+         '<joint name="joint_3" type="hinge" axis="0.0 0.0 1.0" pos="0.0 0.0 0.0" damping="0.002" '
+         'stiffness="0.05" springref="0.2"'),
+        ('<body name="link_4" pos="0.1 0.0 0.0" quat="1.0 0.0 0.0 0.0">',
+         '<body name="link_4" pos="0.1 0.0 0.0" quat="0.9689124217106447 0.1 0.2 0.1">'),
+        ('<position name="actuator_position_joint_4" joint="joint_4" kp="1.0" ctrllimited="false" '
+         'ctrlrange="-1000000.0 1000000.0"',
+         '<position name="actuator_position_joint_4" joint="joint_4" kp="1.0" ctrllimited="true" '
+         'ctrlrange="-0.05 0.05"'),
+        ('<motor name="actuator_torque_joint_5" joint="joint_5"/>',
+         '<motor name="actuator_torque_joint_5" joint="joint_5" forcelimited="true" '
+         'forcerange="-0.01 0.01" gear="2.0"/>'),
+    ]
+    for old, new in edits:
+        assert old in x, old
+        x = x.replace(old, new)
+    count = [0]
+
+    def inertial(match):
+        count[0] += 1
+        if count[0] == 6:
+            return ('<inertial pos="0.05 0.01 0.0" mass="0.2" '
+                    'fullinertia="4e-05 0.00021 0.00025 1e-05 -2e-05 1.5e-05"/>')
+        return match.group(0)
+
+    x = re.sub(r'<inertial [^>]*/>', inertial, x)
+    return dataclasses.replace(spec, name='swimmer8_features', mjcf=x)
+
+
+def swimmer8_fixed_base():
+    """farms 'fixed_base' (mjcf.py:751-756): no free joint; the base links fuse into the world."""
+    spec = models.swimmer8()
+    x = spec.mjcf
+    assert '<freejoint name="root_swimmer"/>' in x
+    x = x.replace('      <freejoint name="root_swimmer"/>\n', '')
+
+    def trim(match):
+        values = match.group(2).split()
+        drop = 7 if match.group(1) == 'qpos' else 6
+        return f'{match.group(1)}="{" ".join(values[drop:])}"'
+
+    x = re.sub(r'(qpos|qvel)="([^"]*)"', trim, x)
+    links = spec.links_names[1:]        # link_0 is welded to the world now: not a moving body
+    animat = copy.deepcopy(spec.animat_options)
+    animat.morphology.links = [link for link in animat.morphology.links if link.name in links]
+    return dataclasses.replace(spec, name='swimmer8_fixed', mjcf=x, links_names=links,
+                               animat_options=animat,
+                               xfrc_names=links, contacts_names=[c for c in spec.contacts_names
+                                                                 if c[0] in links])
