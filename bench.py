@@ -304,7 +304,9 @@ def run_b200(args, rank, world, local_rank):
     # ---- optional end-of-rollout gather of per-env statistics (NCCL)
     stats = torch.as_tensor(physics.qpos[:, :3].astype(np.float32), device='cuda')
     stats = gather_env_statistics(stats, world)
-    flags = int(np.count_nonzero(physics.flags))
+    all_flags = physics.flags
+    flags = int(np.count_nonzero(all_flags & 1))
+    solver_flags = int(np.count_nonzero(all_flags & 4))
 
     if rank == 0:
         b_log = physics.log_bytes_per_env_step
@@ -341,7 +343,7 @@ def run_b200(args, rank, world, local_rank):
                 'team_lanes': physics.team_lanes, 'team_smem_bytes_per_env': physics.smem_bytes_per_env,
                 'l2_policy': (f'no flush: each step appends {n_local*args.inner*b_log/1e6:.0f} MB of new '
                               f'log rows to a {n_local*args.ring*b_log/1e9:.1f} GB ring (> 126 MB L2)'),
-                'diverged_envs': flags,
+                'diverged_envs': flags, 'solver_pivot_clamped_envs': solver_flags,
             },
             'clocks': clocks,
             'e2e': e2e,

@@ -965,14 +965,17 @@ FB_UNROLL
           if (res[r+2] < 0.f) h += d*(nu_ + t2u)*(nv_ + t2v);
           if (res[r+3] < 0.f) h += d*(nu_ - t2u)*(nv_ - t2v);
         }
-        H[e] = h;
+        /* stored with the dof order reversed: the dense factorisation below then eliminates
+         * leaves before roots, the order that keeps the Schur complements physical (composite
+         * inertias) and the fp32 pivots positive -- the order MuJoCo's sparse L'DL uses */
+        H[pack_idx(nv - 1 - v, nv - 1 - u)] = h;
       }
       sync();
-      /* in-place packed Cholesky H = L L' */
+      /* in-place packed Cholesky H = L L' (reversed dof order) */
       int bad = 0;
       for (int j = 0; j < nv; j++) {
         float djj = H[pack_idx(j, j)];
-        if (!(djj > 0.f)) { bad = 1; break; }
+        if (!(djj > FB_MINVAL)) { bad = 1; djj = FB_MINVAL; }   /* mju_cholFactor: clamp, go on */
         float dj = sqrtf(djj), idj = 1.0f/dj;
         sync();
         for (int i = j + 1 + lane; i < nv; i += TEAM) H[pack_idx(i, j)] *= idj;
@@ -985,12 +988,13 @@ FB_UNROLL
         }
         sync();
       }
-      if (bad) { if (lane == 0) FB_FLAG_OR(g.flags, FB_FLAG_SOLVER); break; }
-      /* p = -H^-1 grad : forward (into tmp2), backward (into p) */
+      if (bad && lane == 0) FB_FLAG_OR(g.flags, FB_FLAG_SOLVER);
+      /* p = -H^-1 grad : forward (into tmp2), backward (into p); index j of the factor is
+       * dof nv-1-j */
       for (int j = 0; j < nv; j++) {
-        float yj = -grad[j]/H[pack_idx(j, j)];
+        float yj = -grad[nv - 1 - j]/H[pack_idx(j, j)];
         sync();
-        for (int i = j + 1 + lane; i < nv; i += TEAM) grad[i] += H[pack_idx(i, j)]*yj;
+        for (int i = j + 1 + lane; i < nv; i += TEAM) grad[nv - 1 - i] += H[pack_idx(i, j)]*yj;
         if (lane == 0) tmp2[j] = yj;
         sync();
       }
@@ -998,7 +1002,7 @@ FB_UNROLL
         float xj = tmp2[j]/H[pack_idx(j, j)];
         sync();
         for (int i = lane; i < j; i += TEAM) tmp2[i] -= H[pack_idx(j, i)]*xj;
-        if (lane == 0) p[j] = xj;
+        if (lane == 0) p[nv - 1 - j] = xj;
         sync();
       }
       /* exact line search on phi'(alpha) = g0 + alpha pMp + sum D jp min(0, res + alpha jp) */
