@@ -27,6 +27,8 @@ import time
 
 import numpy as np
 
+_JSON_OUT = sys.stdout
+
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
@@ -191,7 +193,7 @@ def run_reference(args, rank, world):
                 'd2h_bytes_per_step': 0},
         'gpu_launches': 0,
     }
-    print(json.dumps(out), flush=True)
+    print(json.dumps(out), file=_JSON_OUT, flush=True)
 
 
 # ---------------------------------------------------------------- GPU arm
@@ -363,13 +365,19 @@ def run_b200(args, rank, world, local_rank):
         }
         if not args.no_cpu_baseline and world == 1:
             out['cpu_baseline'] = cpu_baseline(args.model, args.cpu_seconds)
-        print(json.dumps(out), flush=True)
+        print(json.dumps(out), file=_JSON_OUT, flush=True)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
 
 
 def main():
+    # The contract is ONE JSON line on stdout.  Libraries (NCCL prints its version banner) write
+    # to fd 1 too: everything but our line goes to stderr.
+    global _JSON_OUT  # pylint: disable=global-statement
+    sys.stdout.flush()
+    _JSON_OUT = os.fdopen(os.dup(1), 'w')
+    os.dup2(2, 1)
     args = parse_args()
     rank = int(os.environ.get('RANK', 0))
     world = int(os.environ.get('WORLD_SIZE', 1))
