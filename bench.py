@@ -269,38 +269,55 @@ def run_b200(args, rank, world, local_rank):
     e2e = None
     if not args.no_e2e:
         nl, njf = len(spec.links_names), len(spec.joints_names)
-        ctrl_host = torch.zeros((n_local, model.nu), dtype=torch.float32).pin_memory()
-        links_host = torch.empty((n_local, nl, 20), dtype=torch.float32).pin_memory()
-        joints_host = torch.empty((n_local, njf, 18), dtype=torch.float32).pin_memory()
+        # two sets of pinned host buffers: the engine's pipelined step_host overlaps the
+        # download of launch i with the kernels of launch i+1 (include/farms_b200.h)
+        ctrl_host = [torch.zeros((n_local, model.nu), dtype=torch.float32).pin_memory() for _ in range(2)]
+        links_host = [torch.empty((n_local, nl, 20), dtype=torch.float32).pin_memory() for _ in range(2)]
+        joints_host = [torch.empty((n_local, njf, 18), dtype=torch.float32).pin_memory() for _ in range(2)]
         physics.set_wave_controller(None, None, None, None)   # ctrl now comes from the host
         acts, amp, freq, lag = wave_controller(spec, model)
         acts_t = torch.as_tensor(np.array(acts))
         amp_t, freq_t = torch.as_tensor(amp, dtype=torch.float32), torch.as_tensor(freq, dtype=torch.float32)
         lag_t = torch.as_tensor(lag, dtype=torch.float32)
         phase_t = torch.as_tensor(phase, dtype=torch.float32)[:, None]
+        checksum = [0.0]
+        calls = [0]
 
         def one_host():
             # host-side controller of this outer iteration (task.py:288-321 analogue):
             # the same travelling wave, evaluated on the host and uploaded
+            k = calls[0] % 2
+            calls[0] += 1
+            if calls[0] > 2:
+                # the buffers of two calls ago are complete once this call is allowed to reuse
+                # them: consume the result (every step's rows are read on the host)
+                physics.host_wait_slot(k)
+                checksum[0] += float(links_host[k][0, 0, 0]) + float(joints_host[k][-1, 0, 0])
             t = physics.iteration*model.timestep
-            ctrl_host[:, acts_t] = amp_t*torch.sin(2*np.pi*freq_t*t - lag_t + phase_t)
-            physics.step_host(args.inner, ctrl=ctrl_host, links_row=links_host, joints_row=joints_host)
+            ctrl_host[k][:, acts_t] = amp_t*torch.sin(2*np.pi*freq_t*t - lag_t + phase_t)
+            physics.step_host(args.inner, ctrl=ctrl_host[k], links_row=links_host[k],
+                              joints_row=joints_host[k], pipelined=True)
 
-        for _ in range(max(1, args.warmup)):
+        for _ in range(max(2, args.warmup)):
             one_host()
+        physics.host_wait()
         barrier()
         t0 = time.perf_counter()
         for _ in range(args.steps):
             one_host()
+        physics.host_wait()
         barrier()
         wall = torch.tensor([time.perf_counter() - t0], device='cuda')
         if world > 1:
             dist.all_reduce(wall, op=dist.ReduceOp.MAX)
+        links_host = links_host[(calls[0] - 1) % 2]
+        ctrl_host, joints_host = ctrl_host[0], joints_host[0]
         e2e = {
             'value': env_steps/float(wall.item()), 'unit': 'env-steps/s',
             'h2d_bytes_per_step': int(ctrl_host.numel()*4*world),
             'd2h_bytes_per_step': int((links_host.numel() + joints_host.numel())*4*world),
-            'checksum': float(links_host[:, 0, 0].double().sum()),
+            'checksum': float(links_host[:, 0, 0].double().sum()) + checksum[0],
+            'pipelined': 'device->host copy of launch i overlaps the kernels of launch i+1 (fb_step_host_async)',
         }
 
     # ---- optional end-of-rollout gather of per-env statistics (NCCL)

@@ -161,6 +161,9 @@ struct FbHandle {
   std::vector<std::vector<double>> keep_d;
 #ifndef FB_HOST_EMU
   cudaEvent_t ev0, ev1;
+  cudaStream_t copy_stream;          /* device->host copies of fb_step_host_async */
+  cudaEvent_t ev_gather, ev_copy[2];  /* copy-done events of the last two pipelined calls */
+  long long host_calls;
 #endif
 };
 
@@ -325,6 +328,9 @@ void fb_destroy(FbHandle *h) {
   if (h->F_dev) dev_free(h->F_dev);
 #ifndef FB_HOST_EMU
   cudaEventDestroy(h->ev0); cudaEventDestroy(h->ev1);
+  cudaStreamSynchronize(h->copy_stream);
+  cudaEventDestroy(h->ev_gather); cudaEventDestroy(h->ev_copy[0]); cudaEventDestroy(h->ev_copy[1]);
+  cudaStreamDestroy(h->copy_stream);
   cudaStreamDestroy(h->stream);
   delete h->fastQ;
 #endif
@@ -359,6 +365,11 @@ int fb_create(const FbModel *model, const FbFarms *farms, int n_envs, int device
   cudaSetDevice(device);
   cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking);
   cudaEventCreate(&h->ev0); cudaEventCreate(&h->ev1);
+  cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking);
+  cudaEventCreateWithFlags(&h->ev_gather, cudaEventDisableTiming);
+  cudaEventCreateWithFlags(&h->ev_copy[0], cudaEventDisableTiming);
+  cudaEventCreateWithFlags(&h->ev_copy[1], cudaEventDisableTiming);
+  h->host_calls = 0;
   if (team_lanes != 0 && team_lanes != 8 && team_lanes != 16 && team_lanes != 32) {
     fb_destroy(h);
     return fail("fb_create: team_lanes must be 0, 8, 16 or 32");
@@ -653,8 +664,12 @@ int fb_export_farms(FbHandle *h, int env, double *links, double *joints, double 
   return 0;
 }
 
-int fb_step_host(FbHandle *h, const float *ctrl, const float *qpos, const float *qvel,
-                 int n_steps, float *links_row, float *joints_row) {
+/* Shared body of fb_step_host / fb_step_host_async.  Asynchronous form: the row gathers run on
+ * the handle's stream after the step kernels, the two device->host copies on a second (copy)
+ * stream, so the transfer of launch i overlaps the kernels of launch i+1; the single pair of
+ * gather buffers is protected by the copy-done event, waited for right before the next gathers. */
+static int step_host_impl(FbHandle *h, const float *ctrl, const float *qpos, const float *qvel,
+                          int n_steps, float *links_row, float *joints_row, bool wait) {
   if (!h) return fail("null handle");
   FbParams &P = h->P;
   const DevModel &m = h->hm.m;
@@ -666,6 +681,7 @@ int fb_step_host(FbHandle *h, const float *ctrl, const float *qpos, const float 
   long long row = h->it % P.ring;
   const int lf = m.n_links*20, jf = m.n_joints*m.joint_cols;
 #ifdef FB_HOST_EMU
+  (void)wait;
   for (size_t e = 0; e < n; e++) {
     for (int i = 0; links_row && i < lf; i++) {
       long long g = i/FB_VEC_LINKS;
@@ -677,23 +693,66 @@ int fb_step_host(FbHandle *h, const float *ctrl, const float *qpos, const float 
     }
   }
 #else
-  if (links_row && lf) {
-    long long total = (long long)n*(lf/FB_VEC_LINKS);
-    fb_gather_rows_kernel<<<(unsigned)((total + 255)/256), 256, 0, h->stream>>>(
-        P.log_links, row, lf, FB_VEC_LINKS, P.env_pad, P.n_envs, h->gather_links);
-    h->launches++;
-    if (d2h(links_row, h->gather_links, (size_t)n*lf*sizeof(float), h->stream)) return fail(dev_error());
+  const bool want_links = links_row && lf, want_joints = joints_row && jf;
+  if (want_links || want_joints) {
+    /* the previous call's copies must have left the gather buffers */
+    const int slot = (int)(h->host_calls & 1);
+    if (h->host_calls > 0 && cudaStreamWaitEvent(h->stream, h->ev_copy[slot ^ 1], 0) != cudaSuccess)
+      return fail(dev_error());
+    h->host_calls++;
+    if (want_links) {
+      long long total = (long long)n*(lf/FB_VEC_LINKS);
+      fb_gather_rows_kernel<<<(unsigned)((total + 255)/256), 256, 0, h->stream>>>(
+          P.log_links, row, lf, FB_VEC_LINKS, P.env_pad, P.n_envs, h->gather_links);
+      h->launches++;
+    }
+    if (want_joints) {
+      long long total = (long long)n*(jf/FB_VEC_JOINTS);
+      fb_gather_rows_kernel<<<(unsigned)((total + 255)/256), 256, 0, h->stream>>>(
+          P.log_joints, row, jf, FB_VEC_JOINTS, P.env_pad, P.n_envs, h->gather_joints);
+      h->launches++;
+    }
+    if (cudaEventRecord(h->ev_gather, h->stream) != cudaSuccess ||
+        cudaStreamWaitEvent(h->copy_stream, h->ev_gather, 0) != cudaSuccess) return fail(dev_error());
+    if (want_links && d2h(links_row, h->gather_links, (size_t)n*lf*sizeof(float), h->copy_stream)) return fail(dev_error());
+    if (want_joints && d2h(joints_row, h->gather_joints, (size_t)n*jf*sizeof(float), h->copy_stream)) return fail(dev_error());
+    if (cudaEventRecord(h->ev_copy[slot], h->copy_stream) != cudaSuccess) return fail(dev_error());
   }
-  if (joints_row && jf) {
-    long long total = (long long)n*(jf/FB_VEC_JOINTS);
-    fb_gather_rows_kernel<<<(unsigned)((total + 255)/256), 256, 0, h->stream>>>(
-        P.log_joints, row, jf, FB_VEC_JOINTS, P.env_pad, P.n_envs, h->gather_joints);
-    h->launches++;
-    if (d2h(joints_row, h->gather_joints, (size_t)n*jf*sizeof(float), h->stream)) return fail(dev_error());
+  if (wait) {
+    if (cudaStreamSynchronize(h->copy_stream) != cudaSuccess) return fail(dev_error());
   }
 #endif
-  if (dev_sync(h->stream)) return fail(std::string("fb_step_host: ") + dev_error());
+  if (wait && dev_sync(h->stream)) return fail(std::string("fb_step_host: ") + dev_error());
   return 0;
+}
+
+int fb_step_host(FbHandle *h, const float *ctrl, const float *qpos, const float *qvel,
+                 int n_steps, float *links_row, float *joints_row) {
+  return step_host_impl(h, ctrl, qpos, qvel, n_steps, links_row, joints_row, true);
+}
+
+int fb_step_host_async(FbHandle *h, const float *ctrl, const float *qpos, const float *qvel,
+                       int n_steps, float *links_row, float *joints_row) {
+  return step_host_impl(h, ctrl, qpos, qvel, n_steps, links_row, joints_row, false);
+}
+
+/* Wait for the copies of the latest pipelined call with (call index % 2) == slot. */
+int fb_host_wait_slot(FbHandle *h, int slot) {
+  if (!h) return fail("null handle");
+#ifndef FB_HOST_EMU
+  if (cudaEventSynchronize(h->ev_copy[slot & 1]) != cudaSuccess) return fail(dev_error());
+#else
+  (void)slot;
+#endif
+  return 0;
+}
+
+int fb_host_wait(FbHandle *h) {
+  if (!h) return fail("null handle");
+#ifndef FB_HOST_EMU
+  if (cudaStreamSynchronize(h->copy_stream) != cudaSuccess) return fail(dev_error());
+#endif
+  return dev_sync(h->stream) ? fail(std::string("fb_host_wait: ") + dev_error()) : 0;
 }
 
 int fb_set_fast_path(FbHandle *h, int enable) {

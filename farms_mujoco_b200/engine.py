@@ -48,8 +48,12 @@ ABI_SYMBOLS = {
     'fb_derived_view': (ct.c_int, [_H, ct.POINTER(cabi.FbDerivedView)]),
     'fb_export_farms': (ct.c_int, [_H, ct.c_int, cabi.c_double_p, cabi.c_double_p,
                                    cabi.c_double_p, cabi.c_double_p]),
+    'fb_host_wait': (ct.c_int, [_H]),
+    'fb_host_wait_slot': (ct.c_int, [_H, ct.c_int]),
     'fb_step_host': (ct.c_int, [_H, ct.c_void_p, ct.c_void_p, ct.c_void_p, ct.c_int, ct.c_void_p,
                                 ct.c_void_p]),
+    'fb_step_host_async': (ct.c_int, [_H, ct.c_void_p, ct.c_void_p, ct.c_void_p, ct.c_int, ct.c_void_p,
+                                      ct.c_void_p]),
     'fb_copy_to_host': (ct.c_int, [_H, ct.c_void_p, ct.c_void_p, ct.c_int64]),
     'fb_copy_to_device': (ct.c_int, [_H, ct.c_void_p, ct.c_void_p, ct.c_int64]),
     'fb_set_fast_path': (ct.c_int, [_H, ct.c_int]),
@@ -377,19 +381,30 @@ class BatchedPhysics:
         self._check(self.lib.fb_export_farms(self._handle, int(env), *ptrs))
         return data
 
-    def step_host(self, n_steps, ctrl=None, qpos=None, qvel=None, links_row=None, joints_row=None):
+    def step_host(self, n_steps, ctrl=None, qpos=None, qvel=None, links_row=None, joints_row=None,
+                  pipelined=False):
         """End-to-end call on HOST float32 buffers (pinned recommended): upload
         ctrl/qpos/qvel (each optional), step, download the last links/joints log
-        row of every environment."""
+        row of every environment.  ``pipelined``: return once enqueued; the download overlaps
+        the next call's kernels (alternate two buffer sets, ``host_wait()`` at the end)."""
         def addr(arr):
             if arr is None:
                 return None
             if hasattr(arr, 'data_ptr'):
                 return arr.data_ptr()
             return arr.ctypes.data
-        self._check(self.lib.fb_step_host(self._handle, addr(ctrl), addr(qpos), addr(qvel),
-                                          int(n_steps), addr(links_row), addr(joints_row)))
+        fn = self.lib.fb_step_host_async if pipelined else self.lib.fb_step_host
+        self._check(fn(self._handle, addr(ctrl), addr(qpos), addr(qvel),
+                       int(n_steps), addr(links_row), addr(joints_row)))
         self.iteration += int(n_steps)
+
+    def host_wait_slot(self, slot):
+        """Completion of the copies of the latest pipelined call with index % 2 == slot."""
+        self._check(self.lib.fb_host_wait_slot(self._handle, int(slot)))
+
+    def host_wait(self):
+        """Completion of every pipelined ``step_host`` issued so far (fb_host_wait)."""
+        self._check(self.lib.fb_host_wait(self._handle))
 
     # ---------------------------------------------------------- introspection
     @property

@@ -218,6 +218,16 @@ int fb_export_farms(FbHandle *h, int env, double *links, double *joints,
  *       float32 host, the last log row of every environment (NULL -> skipped) */
 int fb_step_host(FbHandle *h, const float *ctrl, const float *qpos, const float *qvel,
                  int n_steps, float *links_row, float *joints_row);
+/* Pipelined form: returns once everything is enqueued.  The device->host copies run on a
+ * second stream, so the transfer of call i overlaps the kernels of call i+1; links_row /
+ * joints_row (pinned) are complete after fb_host_wait() or after the NEXT-but-one call
+ * returns -- alternate two host buffer pairs.  Inputs are consumed in stream order: `ctrl`
+ * must stay untouched until the following call or fb_host_wait(). */
+int fb_step_host_async(FbHandle *h, const float *ctrl, const float *qpos, const float *qvel,
+                       int n_steps, float *links_row, float *joints_row);
+int fb_host_wait(FbHandle *h);
+/* completion of the copies of the latest pipelined call whose index (0, 1, 2, ...) % 2 == slot */
+int fb_host_wait_slot(FbHandle *h, int slot);
 
 /* Raw copies between host memory and the engine's device buffers (pointers
  * taken from the views above); for hosts without torch (plain ctypes). */

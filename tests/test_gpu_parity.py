@@ -212,3 +212,38 @@ def test_simulation_layer(cuda_library):
         for kind in ('links', 'joints', 'contacts', 'xfrc'):
             ours = getattr(sim.task.data.sensors, kind).array[env]
             assert scaled_error(ours, getattr(data.sensors, kind).array) < 5e-5, kind
+
+
+def test_step_host_pipelined_equals_synchronous(cuda_library):
+    """fb_step_host_async (download of call i overlapping the kernels of call i+1, two host
+    buffer sets) returns the rows fb_step_host returns."""
+    import torch
+    from farms_mujoco_b200.engine import BatchedPhysics
+    spec, model, qpos0, qvel0, ctrl = make_case('salamander_swim', 64)
+    nl, nj = len(spec.links_names), len(spec.joints_names)
+    rows = {}
+    for mode in ('sync', 'pipelined'):
+        physics = BatchedPhysics.from_spec(spec, 64, buffer_size=8, library=cuda_library)
+        physics.reset(qpos0, qvel0)
+        ctrl_host = [torch.as_tensor(ctrl, dtype=torch.float32).pin_memory() for _ in range(2)]
+        links = [torch.zeros((64, nl, 20), dtype=torch.float32).pin_memory() for _ in range(2)]
+        joints = [torch.zeros((64, nj, 18), dtype=torch.float32).pin_memory() for _ in range(2)]
+        got = []
+        for call in range(5):
+            k = call % 2
+            if mode == 'pipelined' and call >= 2:
+                physics.host_wait_slot(k)
+                got.append((links[k].clone(), joints[k].clone()))
+            physics.step_host(3, ctrl=ctrl_host[k], links_row=links[k], joints_row=joints[k],
+                              pipelined=mode == 'pipelined')
+            if mode == 'sync':
+                got.append((links[k].clone(), joints[k].clone()))
+        if mode == 'pipelined':
+            physics.host_wait()
+            got.append((links[1].clone(), joints[1].clone()))
+            got.append((links[0].clone(), joints[0].clone()))
+        rows[mode] = got
+    assert len(rows['sync']) == len(rows['pipelined']) == 5
+    for (la, ja), (lb, jb) in zip(rows['sync'], rows['pipelined']):
+        assert torch.equal(la, lb) and torch.equal(ja, jb)
+    assert rows['sync'][-1][0].abs().sum() > 0
