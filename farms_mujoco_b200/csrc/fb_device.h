@@ -1301,6 +1301,13 @@ FB_UNROLL
     sync();
   }
 
+  /* ctrl of this step from the uploaded sequence (environment-minor) */
+  FB_MEM void seq_control(const float *seq_env, long long env_pad) {
+    float *ctrl = s + m.L.ctrl;
+    for (int i = lane; i < m.nu; i += TEAM) ctrl[i] = seq_env[(long long)i*env_pad];
+    sync();
+  }
+
   FB_MEM void load_state() {
     float *qpos = s + m.L.qpos, *qvel = s + m.L.qvel, *ctrl = s + m.L.ctrl, *xf = s + m.L.xfrc;
     const int nb = m.nbody;
@@ -1311,12 +1318,12 @@ FB_UNROLL
     sync();
   }
 
-  FB_MEM void store_state() {
+  FB_MEM void store_state(int ctrl_changed) {
     const float *qpos = s + m.L.qpos, *qvel = s + m.L.qvel, *ctrl = s + m.L.ctrl, *xf = s + m.L.xfrc;
     const int nb = m.nbody;
     for (int i = lane; i < m.nq; i += TEAM) g.qpos[i] = qpos[i];
     for (int i = lane; i < m.nv; i += TEAM) g.qvel[i] = qvel[i];
-    if (m.n_wc > 0) for (int i = lane; i < m.nu; i += TEAM) g.ctrl[i] = ctrl[i];
+    if (m.n_wc > 0 || ctrl_changed) for (int i = lane; i < m.nu; i += TEAM) g.ctrl[i] = ctrl[i];
     for (int i = lane; i < 6*nb; i += TEAM) { int b = i/6, k = i - 6*b; g.xfrc_applied[i] = xf[k*nb + b]; }
   }
 };
@@ -1346,6 +1353,10 @@ struct FbParams {
    * from step 0. */
   int *pending, *pending_count, *steps_done;
   int use_pending, parity;
+  /* control sequence (fb_set_ctrl_sequence): ctrl of step k of this launch is
+   * ctrl_seq[((seq_pos + k)*nu + a)*env_pad + env]; NULL -> ctrl is held */
+  const float *ctrl_seq;
+  int seq_pos;
   float *fast_scratch;            /* [n_scratch][fast_scratch_stride]: second half of the per-thread state */
   long long fast_scratch_stride;
 };
@@ -1398,6 +1409,7 @@ FB_DEV void fb_run_env(const FbParams &P, int env, int k0, float *s, int *si, in
       st.forward(1);
       row = 0;
     } else {
+      if (P.ctrl_seq) st.seq_control(P.ctrl_seq + ((size_t)(P.seq_pos + k)*m.nu)*P.env_pad + e, P.env_pad);
       if (m.n_wc > 0) st.wave_control((float)(P.it0 + k)*m.timestep);
       int wd = P.want_derived && k == n - 1;
       st.forward(wd);
@@ -1412,7 +1424,7 @@ FB_DEV void fb_run_env(const FbParams &P, int env, int k0, float *s, int *si, in
     st.write_log();
     if (P.mode == FB_MODE_RESET) st.write_derived();
   }
-  st.store_state();
+  st.store_state(P.ctrl_seq != 0 && P.mode != FB_MODE_RESET);
   if (lane == 0) P.iteration[env] = P.mode == FB_MODE_RESET ? 0 : P.it0 + P.n_steps;
 }
 

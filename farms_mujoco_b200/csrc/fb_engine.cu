@@ -120,6 +120,16 @@ __global__ void fb_gather_rows_kernel(const float *__restrict__ log, long long r
   for (int k = 0; k < vec; k++) dst[k] = src[k];
 }
 
+/* control sequence [K][n_envs][nu] (host order) -> [K][nu][env_pad] (environment-minor) */
+__global__ void fb_transpose_ctrl_kernel(const float *__restrict__ in, int K, int n_envs, int nu,
+                                         long long env_pad, float *__restrict__ out) {
+  long long i = (long long)blockIdx.x*blockDim.x + threadIdx.x;
+  if (i >= (long long)K*nu*n_envs) return;
+  const long long env = i % n_envs, ka = i/n_envs;          /* ka = k*nu + a */
+  const long long k = ka/nu, a = ka - k*nu;
+  out[ka*env_pad + env] = in[(k*n_envs + env)*nu + a];
+}
+
 /* the whole ring of one environment -> dense [ring][row_floats] */
 __global__ void fb_gather_env_kernel(const float *__restrict__ log, int ring, int row_floats, int vec,
                                      long long env_pad, int env, float *__restrict__ out) {
@@ -151,6 +161,8 @@ struct FbHandle {
   float last_ms;
   float *gather_links, *gather_joints;   /* fb_step_host staging */
   float *gather_env;                     /* fb_export_farms staging: one environment's ring of one kind */
+  float *seq_dev, *seq_stage;            /* control sequence, environment-minor + upload staging */
+  int seq_len, seq_pos, seq_cap;
   /* wave-controller copies (owned) */
   std::vector<int32_t> wc_act;
   std::vector<double> wc_amp, wc_freq, wc_lag, wc_off;
@@ -269,6 +281,14 @@ static int launch(FbHandle *h, int mode, int n_steps, int want_derived) {
   /* The per-thread kernel advances every environment while it is unconstrained; the
    * team kernel finishes the ones it handed over.  Reset and derived-view requests go
    * to the team kernel alone (it is the one that produces mjData-like quantities). */
+  P.ctrl_seq = nullptr; P.seq_pos = 0;
+  if (mode == FB_MODE_STEP && h->seq_len > 0) {
+    if (h->seq_pos + n_steps > h->seq_len)
+      return fail("fb_step: the control sequence holds fewer steps than requested");
+    P.ctrl_seq = h->seq_dev; P.seq_pos = h->seq_pos;
+    h->seq_pos += n_steps;
+    if (h->seq_pos == h->seq_len) h->seq_len = h->seq_pos = 0;     /* consumed: ctrl is held again */
+  }
   const int use_fast = h->fast_enabled && P.m.X.ok && mode == FB_MODE_STEP && !want_derived;
   P.use_pending = use_fast;
   P.parity = (int)(h->launch_parity & 1);
@@ -324,6 +344,7 @@ void fb_destroy(FbHandle *h) {
   if (!h) return;
   dev_sync(h->stream);
   for (void *p : h->allocs) dev_free(p);
+  if (h->seq_dev) { dev_free(h->seq_dev); dev_free(h->seq_stage); }
   if (h->I_dev) dev_free(h->I_dev);
   if (h->F_dev) dev_free(h->F_dev);
 #ifndef FB_HOST_EMU
@@ -345,6 +366,7 @@ int fb_create(const FbModel *model, const FbFarms *farms, int n_envs, int device
   if (!h) return fail("out of host memory");
   h->device = device; h->I_dev = nullptr; h->F_dev = nullptr; h->launches = 0; h->it = 0;
   h->last_ms = 0.f; h->has_wc = false; h->gather_links = h->gather_joints = h->gather_env = nullptr;
+  h->seq_dev = h->seq_stage = nullptr; h->seq_len = h->seq_pos = h->seq_cap = 0;
   h->fast_enabled = 1; h->fast_block = 1; h->fast_smem_bytes = 0; h->launch_parity = 0;
 #ifndef FB_HOST_EMU
   h->fastQ = nullptr;
@@ -489,6 +511,7 @@ int fb_reset(FbHandle *h, const double *qpos0, const double *qvel0) {
   bad |= dev_sync(h->stream);   /* q, v are stack-owned */
   if (bad) return fail(std::string("fb_reset: ") + dev_error());
   h->it = 0;
+  h->seq_len = h->seq_pos = 0;
   if (launch(h, FB_MODE_RESET, 1, 1)) return -1;
   return dev_sync(h->stream) ? fail(std::string("fb_reset: ") + dev_error()) : 0;
 }
@@ -505,6 +528,39 @@ static int upload_doubles(FbHandle *h, float *dst, const double *src, size_t cou
 int fb_set_ctrl(FbHandle *h, const double *ctrl) {
   return upload_doubles(h, h->P.ctrl, ctrl, (size_t)h->P.n_envs*h->hm.m.nu, "fb_set_ctrl");
 }
+int fb_set_ctrl_sequence(FbHandle *h, const float *ctrl, int n_steps) {
+  if (!h) return fail("null handle");
+  h->seq_len = h->seq_pos = 0;
+  if (!ctrl || n_steps <= 0) return 0;              /* sequence off */
+  const DevModel &m = h->hm.m;
+  if (m.nu <= 0) return fail("fb_set_ctrl_sequence: the model has no actuators");
+  const size_t n = (size_t)h->P.n_envs, per_step = (size_t)m.nu*h->P.env_pad;
+  if (n_steps > h->seq_cap) {
+    dev_sync(h->stream);
+    if (h->seq_dev) { dev_free(h->seq_dev); dev_free(h->seq_stage); }
+    void *a = nullptr, *b = nullptr;
+    if (dev_alloc(&a, per_step*n_steps*sizeof(float)) || dev_alloc(&b, n*m.nu*n_steps*sizeof(float)))
+      return fail("fb_set_ctrl_sequence: device allocation failed");
+    h->seq_dev = static_cast<float *>(a); h->seq_stage = static_cast<float *>(b);
+    h->seq_cap = n_steps;
+  }
+#ifdef FB_HOST_EMU
+  for (int k = 0; k < n_steps; k++)
+    for (size_t e = 0; e < n; e++)
+      for (int a = 0; a < m.nu; a++)
+        h->seq_dev[((size_t)k*m.nu + a)*h->P.env_pad + e] = ctrl[((size_t)k*n + e)*m.nu + a];
+#else
+  if (h2d(h->seq_stage, ctrl, n*m.nu*n_steps*sizeof(float), h->stream)) return fail(dev_error());
+  long long total = (long long)n_steps*m.nu*(long long)n;
+  fb_transpose_ctrl_kernel<<<(unsigned)((total + 255)/256), 256, 0, h->stream>>>(
+      h->seq_stage, n_steps, (int)n, m.nu, h->P.env_pad, h->seq_dev);
+  h->launches++;
+  if (dev_sync(h->stream)) return fail(std::string("fb_set_ctrl_sequence: ") + dev_error());   /* ctrl is the caller's */
+#endif
+  h->seq_len = n_steps;
+  return 0;
+}
+
 int fb_set_qpos_spring(FbHandle *h, const double *qs) {
   return upload_doubles(h, h->P.qpos_spring, qs, (size_t)h->P.n_envs*h->hm.m.nq, "fb_set_qpos_spring");
 }

@@ -181,11 +181,13 @@ template <int BLK> struct FbFast {
   float env_phase;
   float rt[13];       /* floating root: qpos[7], qvel[6] (registers) */
   float rootpos[3];   /* world position the anchors are measured from (the floating root) */
+  float rqn[4];       /* normalised root quaternion of the current step */
 
   FB_MEM FbFast(const FbParams &P_, const FastRec *rec_, float *s_, float *gs_, int env_)
       : P(P_), m(P_.m), rec(rec_), s(s_), env(env_), gs(gs_) {
     env_phase = P.env_phase[env];
     rootpos[0] = rootpos[1] = rootpos[2] = 0.f;
+    rqn[0] = 1.f; rqn[1] = rqn[2] = rqn[3] = 0.f;
 FB_UNROLL
     for (int k = 0; k < 13; k++) rt[k] = 0.f;
   }
@@ -195,10 +197,29 @@ FB_UNROLL
   FB_MEM float *slot(int i) const { return s + (m.X.slots + 27*i)*BLK; }
 
   /* generic actuation (clamps, gears, partial logging): force sum and farms joint_torque */
+  /* ctrl of actuator a at this step: the uploaded sequence when there is one, else the held value */
+  FB_MEM float ctrl_of(int a, const float *seqk) const {
+    return seqk ? seqk[(long long)a*P.env_pad] : P.ctrl[(size_t)env*m.nu + a];
+  }
+
+  /* per-step constants of a joint's linear actuation form (load_state does this once when ctrl is held) */
+  FB_MEM void seq_constants(const FastRec &rc, const float *seqk, float *tc, float *tu) const {
+    float c = rc.T0, u = rc.T0U;
+    int ap = -1, av = -1, at = -1;
+    if (rc.fj >= 0) { ap = MI(fj_actpos, rc.fj); av = MI(fj_actvel, rc.fj); at = MI(fj_acttrq, rc.fj); }
+    for (int t = MI(jnt_actstart, rc.jid); t < MI(jnt_actstart, rc.jid + 1); t++) {
+      int a = MI(act_sorted, t);
+      if (a == rc.wave_act || MI(ft_actoff, a)) continue;
+      float f = MF(act_gain, a)*seqk[(long long)a*P.env_pad];
+      c += f;
+      if (!(a == ap || a == av || a == at)) u += f;
+    }
+    *tc = c; *tu = u;
+  }
+
   FB_MEM void actuation_generic(const FastRec &rc, float q, float qd, float time, int store_ctrl,
-                                float *tau, float *trq_log) const {
+                                const float *seqk, float *tau, float *trq_log) const {
     const int jid = rc.jid, fj = rc.fj;
-    const float *g_ctrl = P.ctrl + (size_t)env*(m.nu > 0 ? m.nu : 1);
     int a0 = MI(jnt_actstart, jid), a1 = MI(jnt_actstart, jid + 1);
     int ap = -1, av = -1, at = -1;
     if (fj >= 0) { ap = MI(fj_actpos, fj); av = MI(fj_actvel, fj); at = MI(fj_acttrq, fj); }
@@ -213,7 +234,7 @@ FB_UNROLL
         c = MF(wc_off, w) + MF(wc_amp, w)*sinf(ph);
         if (store_ctrl) P.ctrl[(size_t)env*m.nu + a] = c;
       } else {
-        c = g_ctrl[a];
+        c = ctrl_of(a, seqk);
       }
       if (MI(act_ctrllimited, a)) c = fminf(MF(act_ctrlrange, 2*a+1), fmaxf(MF(act_ctrlrange, 2*a), c));
       float f = MF(act_gain, a)*c + MF(act_bias, 3*a) + MF(act_bias, 3*a+1)*(gear*q) + MF(act_bias, 3*a+2)*(gear*qd);
@@ -354,7 +375,10 @@ FB_UNROLL
       if (jtype == FB_JNT_FREE) {
         Quat qq = {rt[3], rt[4], rt[5], rt[6]};
         q = q_normalize(qq);
-        rt[3] = q.w; rt[4] = q.x; rt[5] = q.y; rt[6] = q.z;
+        /* qpos takes the normalised quaternion (mj_kinematics does it in place) only once the
+         * step is known to be taken here: a handed-over environment must reach the team kernel
+         * with its state bit-for-bit untouched */
+        rqn[0] = q.w; rqn[1] = q.x; rqn[2] = q.y; rqn[3] = q.z;
         q_mat(q, R);
 FB_UNROLL
         for (int k = 0; k < 3; k++) { rootpos[k] = rt[k]; o[k] = 0.f; v[3 + k] = rt[7 + k]; }
@@ -458,7 +482,7 @@ FB_UNROLL
   }
 
   /* ---- pass 2: leaves -> root, articulated inertias and bias forces */
-  FB_MEM void pass_inertia(float time, float *aroot, int store_ctrl) {
+  FB_MEM void pass_inertia(float time, float *aroot, int store_ctrl, const float *seqk) {
     const int nb = m.nbody;
     const float hdt = m.timestep;
     ArtInertia C;        /* carry from child b+1 */
@@ -587,16 +611,18 @@ FB_UNROLL
         float ax[3], U[6], c[6], tau, trq;
         m_rot(R, rc.axis[0], rc.axis[1], rc.axis[2], ax);
         if (flags & FT_ACT_SIMPLE) {
-          tau = cx[8] + rc.Kq*qj + rc.Kqd*qd;
+          float tc = cx[8], tu = cx[9];
+          if (seqk) seq_constants(rc, seqk, &tc, &tu);
+          tau = tc + rc.Kq*qj + rc.Kqd*qd;
           if (flags & FT_HAS_WAVE) {
             float ph = 6.283185307179586f*rc.wfreq*time - rc.wlag + env_phase;
             float cw = rc.woff + rc.wamp*sinf(ph);
             tau += rc.wgain*cw;
             if (store_ctrl) P.ctrl[(size_t)env*m.nu + rc.wave_act] = cw;
           }
-          trq = tau - (cx[9] + rc.KqU*qj + rc.KqdU*qd);
+          trq = tau - (tu + rc.KqU*qj + rc.KqdU*qd);
         } else {
-          actuation_generic(rc, qj, qd, time, store_ctrl, &tau, &trq);
+          actuation_generic(rc, qj, qd, time, store_ctrl, seqk, &tau, &trq);
         }
         if (rc.stiffness != 0.f) tau -= rc.stiffness*(qj - P.qpos_spring[(size_t)env*m.nq + rc.qa]);
         tau -= rc.damping*qd;
@@ -856,12 +882,20 @@ FB_UNROLL
       float *row_xfrc = fb_log_row(P.log_xfrc, row, m.n_xfrc*6, P.env_pad, FB_VEC_XFRC, e);
       const float time = (float)(P.it0 + k)*m.timestep;
       if (pass_poses(row_links)) break;
+      if (rec[1].jtype == FB_JNT_FREE) { rt[3] = rqn[0]; rt[4] = rqn[1]; rt[5] = rqn[2]; rt[6] = rqn[3]; }
       float aroot[6] = {0.f, 0.f, 0.f, -m.grav[0], -m.grav[1], -m.grav[2]};
-      pass_inertia(time, aroot, k == n - 1 && m.n_wc > 0);   /* ctrl is left as the team path leaves it */
+      const float *seqk = P.ctrl_seq ? P.ctrl_seq + ((size_t)(P.seq_pos + k)*m.nu)*P.env_pad + e : 0;
+      pass_inertia(time, aroot, k == n - 1 && m.n_wc > 0, seqk);   /* ctrl is left as the team path leaves it */
       int bad = pass_accel(aroot, row_joints, row_xfrc);
       /* no contact is active on this path: the contacts rows are zero (sensors.pyx:140-190) */
       for (int i = 0; i < m.n_contacts*3; i++) fb_st4(row_contacts + i*(P.env_pad*FB_VEC_CONTACTS), 0.f, 0.f, 0.f, 0.f);
       if (bad) FB_FLAG_OR(P.flags + env, FB_FLAG_NONFINITE);
+    }
+    if (P.ctrl_seq && k == n) {
+      /* ctrl ends as the last entry used, as if the host had set it step by step */
+      const float *last = P.ctrl_seq + ((size_t)(P.seq_pos + n - 1)*m.nu)*P.env_pad + e;
+      for (int a = 0; a < m.nu; a++)
+        if (MI(ft_actwc, a) < 0) P.ctrl[e*m.nu + a] = last[(long long)a*P.env_pad];
     }
     store_state(P.it0 + k, coop, lane);
     return k;

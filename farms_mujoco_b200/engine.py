@@ -34,6 +34,7 @@ ABI_SYMBOLS = {
     'fb_reset': (ct.c_int, [_H, cabi.c_double_p, cabi.c_double_p]),
     'fb_set_ctrl': (ct.c_int, [_H, cabi.c_double_p]),
     'fb_set_qpos_spring': (ct.c_int, [_H, cabi.c_double_p]),
+    'fb_set_ctrl_sequence': (ct.c_int, [_H, ct.c_void_p, ct.c_int]),
     'fb_set_env_phase': (ct.c_int, [_H, cabi.c_double_p]),
     'fb_set_wave_controller': (ct.c_int, [_H, ct.POINTER(cabi.FbWaveController)]),
     'fb_set_actuator_forcerange': (ct.c_int, [_H, ct.c_int, ct.POINTER(ct.c_int32), ct.POINTER(ct.c_int32), cabi.c_double_p]),
@@ -218,6 +219,15 @@ class BatchedPhysics:
         arr = np.ascontiguousarray(ctrl, dtype=np.float64)
         assert arr.shape == (self.n_envs, self.model.nu), arr.shape
         self._check(self.lib.fb_set_ctrl(self._handle, arr.ctypes.data_as(cabi.c_double_p)))
+
+    def set_ctrl_sequence(self, ctrl):
+        """Open-loop control of the next ``K`` steps: ``ctrl[K, n_envs, nu]`` (``None``: off)."""
+        if ctrl is None:
+            self._check(self.lib.fb_set_ctrl_sequence(self._handle, None, 0))
+            return
+        arr = np.ascontiguousarray(ctrl, dtype=np.float32)
+        assert arr.ndim == 3 and arr.shape[1:] == (self.n_envs, self.model.nu), arr.shape
+        self._check(self.lib.fb_set_ctrl_sequence(self._handle, arr.ctypes.data, arr.shape[0]))
 
     def set_qpos_spring(self, qpos_spring):
         arr = np.ascontiguousarray(qpos_spring, dtype=np.float64)

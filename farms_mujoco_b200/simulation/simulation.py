@@ -11,8 +11,10 @@ resets (``initialize_episode``, no physics step), every later call is
 ``PhysicsError`` (simulation.py:157-161).
 
 Fused stepping: when no callback and no host-side controller needs to see every
-iteration (``task.device_controller`` or no controller, no callbacks) ``run`` advances
-``chunk`` iterations per kernel launch (``fb_step(h, K)``); the device log then holds
+iteration (no callbacks; no controller, a controller that runs on the device, or a host
+controller that declares ``open_loop = True`` and whose next K outputs are uploaded as one
+sequence, ``fb_set_ctrl_sequence``) ``run`` advances ``chunk`` iterations per kernel launch
+(``fb_step(h, K)``); the device log then holds
 exactly the rows the per-iteration loop would have produced, and ``postprocess`` reads
 them back.  ``chunk=1`` is the reference's ordering step for step.
 """
@@ -131,7 +133,8 @@ class Simulation:
 
     def _can_fuse(self):
         task = self.task
-        return (not task.callbacks and (task.controller is None or task.device_controller)
+        open_loop = getattr(task.controller, 'open_loop', False)
+        return (not task.callbacks and (task.controller is None or task.device_controller or open_loop)
                 and task.substeps == 1 and self.n_sub_steps == 1)
 
     def run(self):
@@ -147,6 +150,9 @@ class Simulation:
                     # K iterations in one launch: the device writes the K log rows itself
                     k = min(chunk, n_calls - done, self.task.n_iterations - self.task.iteration)
                     assert self.task.iteration + k <= self.task.n_iterations
+                    if self.task.controller is not None and not self.task.device_controller:
+                        # open-loop host controller: its next k outputs travel as one sequence
+                        self.physics.set_ctrl_sequence(self.task.control_sequence(k))
                     self.physics.step(k)
                     self._check_physics()
                     self.task.sim_iteration += k

@@ -198,6 +198,30 @@ class ExperimentTask:
             self.step_joints_control_torque(physics, current_time)
         physics.set_ctrl(self._ctrl)
 
+    def control_sequence(self, n_steps):
+        """``ctrl`` of the next ``n_steps`` iterations, ``[n_steps, n_envs, nu]``, for a controller
+        whose output depends on (iteration, time) only (``controller.open_loop``): what
+        ``step_control`` would write before each of those steps (task.py:288-346), computed
+        ahead so that the engine can fuse the steps into one launch (fb_set_ctrl_sequence)."""
+        sequence = np.empty((n_steps,) + self._ctrl.shape, dtype=np.float32)
+        for k in range(n_steps):
+            iteration = self.iteration + k
+            current_time = iteration*self.timestep
+            index = iteration % self.buffer_size
+            self._controller.step(iteration=index, time=current_time, timestep=self.timestep)
+            if self._controller.joints_names[ControlType.POSITION]:
+                positions = self._controller.positions(iteration=index, time=current_time, timestep=self.timestep)
+                for act, joint in zip(self.maps['ctrl']['pos'], self._controller.joints_names[ControlType.POSITION]):
+                    self._ctrl[:, act] = positions[joint]
+            if self._controller.joints_names[ControlType.TORQUE]:
+                torques = self._controller.torques(iteration=index, time=current_time, timestep=self.timestep)
+                for act, joint in zip(self.maps['ctrl']['trq'], self._controller.joints_names[ControlType.TORQUE]):
+                    self._ctrl[:, act] = np.asarray(torques[joint])*self.units.torques
+                assert not self._controller.springrefs(iteration=index, time=current_time, timestep=self.timestep), (
+                    'spring references change qpos_spring: not expressible as a ctrl sequence')
+            sequence[k] = self._ctrl
+        return sequence
+
     def step_joints_control_position(self, physics, time):
         """Step position control (task.py:309-321)"""
         del physics

@@ -177,6 +177,12 @@ int fb_reset(FbHandle *h, const double *qpos0, const double *qvel0);
 /* Control inputs (task.py:307,317,332,343-346). */
 int fb_set_ctrl(FbHandle *h, const double *ctrl);                 /* [n_envs][nu] */
 int fb_set_qpos_spring(FbHandle *h, const double *qpos_spring);   /* [n_envs][nq] */
+/* Open-loop control for the next n_steps physics steps: ctrl[n_steps][n_envs][nu] float32 host
+ * (what step_joints_control_* would write before each step, task.py:309-346).  Following
+ * fb_step calls consume it in order (a call may not ask for more steps than remain); when it
+ * is used up ctrl is held at its last entry.  NULL or n_steps = 0 switches it off; fb_reset
+ * clears it.  Actuators driven by the on-device wave controller keep the wave. */
+int fb_set_ctrl_sequence(FbHandle *h, const float *ctrl, int n_steps);
 int fb_set_env_phase(FbHandle *h, const double *phase);           /* [n_envs] */
 int fb_set_wave_controller(FbHandle *h, const FbWaveController *c); /* NULL -> off */
 /* Model edit of ExperimentTask.initialize_control (task.py:262-286): the reference sets

@@ -107,3 +107,40 @@ def check_variant(library, spec, n_envs=3, n_steps=15, tol=1e-5, free_base=True)
     assert physics.last_pending == 0
     envs = sorted({0, n_envs//2, n_envs - 1})
     return compare_with_oracle(spec, model, physics, qpos0, qvel0, ctrl, envs, n_steps, tol)
+
+
+def check_ctrl_sequence(library, spec, n_envs=4, n_steps=9, free_base=True):
+    """fb_set_ctrl_sequence: K steps in fused launches == K launches with set_ctrl before each."""
+    from farms_mujoco_b200 import mjcf_subset
+    from farms_mujoco_b200.engine import BatchedPhysics, EngineError
+    model = mjcf_subset.parse_mjcf(spec.mjcf)
+    rng = np.random.default_rng(7)
+    qpos0 = np.tile(model.key_qpos, (n_envs, 1))
+    first = 7 if free_base else 0
+    qpos0[:, first:] += rng.uniform(-0.1, 0.1, (n_envs, model.nq - first))
+    qvel0 = rng.uniform(-0.2, 0.2, (n_envs, model.nv))
+    seq = rng.uniform(-0.3, 0.3, (n_steps, n_envs, model.nu)).astype(np.float32)
+    outs = []
+    for mode in ('stepwise', 'fused'):
+        physics = BatchedPhysics.from_spec(spec, n_envs, buffer_size=n_steps + 1, library=library)
+        physics.reset(qpos0, qvel0)
+        if mode == 'stepwise':
+            for k in range(n_steps):
+                physics.set_ctrl(seq[k])
+                physics.step(1)
+        else:
+            physics.set_ctrl_sequence(seq)
+            physics.step(4)
+            physics.step(n_steps - 4)
+            try:
+                physics.set_ctrl_sequence(seq[:2])
+                physics.step(3)
+                raise AssertionError('a launch longer than the sequence must fail')
+            except EngineError as err:
+                assert 'sequence' in str(err)
+            physics.set_ctrl_sequence(None)
+        outs.append((physics.qpos, physics.qvel, physics.ctrl, physics.log_arrays()))
+    assert np.array_equal(outs[0][0], outs[1][0]) and np.array_equal(outs[0][1], outs[1][1])
+    assert np.array_equal(outs[0][2], outs[1][2])          # ctrl ends at the last entry
+    for kind in ('links', 'joints', 'contacts', 'xfrc'):
+        assert np.array_equal(outs[0][3][kind], outs[1][3][kind]), kind

@@ -78,6 +78,16 @@ def test_fast_path_fixed_base(emu_library):
     fastpath_cases.check_variant(emu_library, variant_models.swimmer8_fixed_base(), free_base=False)
 
 
+@pytest.mark.parametrize('which', ['swimmer8', 'features', 'salamander'])
+def test_ctrl_sequence(emu_library, which):
+    import fastpath_cases
+    import variant_models
+    from farms_mujoco_b200 import models
+    spec = {'swimmer8': models.swimmer8, 'features': variant_models.swimmer8_features,
+            'salamander': models.salamander}[which]()
+    fastpath_cases.check_ctrl_sequence(emu_library, spec)
+
+
 def test_log_layout_is_reference_layout(emu_library):
     """Row k: links/contacts of state k-1 (k=0: state 0), joints qpos/qvel of state k
     (SURVEY.md Appendix D-1); quaternions xyzw; unwritten joint columns stay zero."""

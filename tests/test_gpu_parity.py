@@ -95,6 +95,16 @@ def test_model_variants(cuda_library, variant, free_base):
                                  free_base=free_base)
 
 
+@pytest.mark.parametrize('which', ['swimmer8', 'features', 'salamander'])
+def test_ctrl_sequence(cuda_library, which):
+    import fastpath_cases
+    import variant_models
+    from farms_mujoco_b200 import models
+    spec = {'swimmer8': models.swimmer8, 'features': variant_models.swimmer8_features,
+            'salamander': models.salamander}[which]()
+    fastpath_cases.check_ctrl_sequence(cuda_library, spec, n_envs=70)
+
+
 def test_paths_agree(cuda_library):
     import fastpath_cases
     fastpath_cases.check_paths_agree(cuda_library, 'salamander_swim', n_envs=96)

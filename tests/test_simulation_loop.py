@@ -202,3 +202,23 @@ def test_torque_control_disables_position_actuators(emu_library):
         for kind in ('links', 'joints', 'xfrc'):
             ours = getattr(sim.task.data.sensors, kind).array[env]
             assert scaled_error(ours, getattr(data.sensors, kind).array) < 2e-5, kind
+
+
+def test_open_loop_host_controller_is_fused(emu_library):
+    """A host controller that declares ``open_loop`` runs in fused launches (its outputs travel as
+    a ctrl sequence) and produces exactly the per-iteration loop's log."""
+    spec = models.swimmer8(n_iterations=30)
+    joints, amp, freq, lag = travelling_wave_parameters(spec)
+    logs = []
+    for open_loop in (False, True):
+        ctl = HostWave(joints, amp, freq, lag, [0.2, 0.9])
+        ctl.open_loop = open_loop
+        sim = Simulation.from_spec(spec, n_envs=2, controller=ctl, chunk=8, library=emu_library)
+        sim.run()
+        assert not sim.task.device_controller and sim.iteration == 29
+        launches = sim.physics.launch_count()
+        logs.append(({k: getattr(sim.task.data.sensors, k).array.copy() for k in ('links', 'joints', 'xfrc')},
+                     launches))
+    assert logs[1][1] < logs[0][1]            # fewer launches when fused
+    for kind, arr in logs[0][0].items():
+        assert np.array_equal(arr, logs[1][0][kind]), kind
