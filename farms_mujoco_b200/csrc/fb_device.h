@@ -633,7 +633,7 @@ FB_UNROLL
    * fb_build_model (deepest pivots first, one lane per destination word). */
   FB_MEM void factor(float hdamp) {
     const float *qM = s + m.L.qM;
-    float *qLD = s + m.L.qLD, *dinv = s + m.L.dinv;
+    float *qLD = s + m.L.qLD;
     for (int e = lane; e < m.nM; e += TEAM) {
       int i = MI(ent_i, e);
       float v = qM[e];
@@ -641,6 +641,12 @@ FB_UNROLL
       qLD[e] = v;
     }
     sync();
+    eliminate();
+  }
+
+  /* in-place scheduled L'DL of the tree-sparse matrix held in qLD */
+  FB_MEM void eliminate() {
+    float *qLD = s + m.L.qLD, *dinv = s + m.L.dinv;
     const int NS = m.nstage;
     for (int st = 0; st < NS; st++) {
       int p0 = MI(st_pivstart, st), p1 = MI(st_pivstart, st + 1);
@@ -659,9 +665,9 @@ FB_UNROLL
   }
 
   /* x <- inv(L'DL) x, x in shared memory */
-  FB_MEM void solve_ld(float *x) {
+  FB_MEM void solve_ld(float *x) { solve_ld(x, s + m.L.tmp1); }
+  FB_MEM void solve_ld(float *x, float *y) {
     const float *qLD = s + m.L.qLD, *dinv = s + m.L.dinv;
-    float *y = s + m.L.tmp1;
     const int NS = m.nstage;
     /* y = D^-1 L^-T x: leaves to root */
     for (int st = 0; st < NS; st++) {
@@ -883,15 +889,17 @@ FB_UNROLL
     sync();
   }
 
-  /* dense packed symmetric matvec: out = Md x */
-  FB_MEM void md_times(const float *x, float *out) {
+  /* out = M x on the tree-sparse layout: ancestors from the dof's own row, descendants from
+   * the column lists */
+  FB_MEM void mul_m(const float *x, float *out) {
     const int nv = m.nv;
-    const float *Md = s + m.L.Md;
-    for (int u = lane; u < nv; u += TEAM) {
+    const float *qM = s + m.L.qM;
+    for (int i = lane; i < nv; i += TEAM) {
+      const int adr = MI(dof_Madr, i), nk = MI(dof_nanc, i);
       float acc = 0.f;
-      for (int v = 0; v <= u; v++) acc += Md[pack_idx(u, v)]*x[v];
-      for (int v = u + 1; v < nv; v++) acc += Md[pack_idx(v, u)]*x[v];
-      out[u] = acc;
+      for (int k = 0; k < nk; k++) acc += qM[adr + k]*x[MI(ent_j, adr + k)];
+      for (int t = MI(col_start, i); t < MI(col_start, i + 1); t++) acc += qM[MI(col_ent, t)]*x[MI(col_dof, t)];
+      out[i] = acc;
     }
     sync();
   }
@@ -902,15 +910,10 @@ FB_UNROLL
     const int nrow = 2*nj + 4*ncon;
     const int *con_cand = si + m.L.con_cand;
     float *qacc = s + m.L.qacc, *fsm = s + m.L.fsm, *fcon = s + m.L.fcon;
-    float *grad = s + m.L.grad, *p = s + m.L.pvec, *Md = s + m.L.Md, *H = s + m.L.H;
+    float *grad = s + m.L.grad, *p = s + m.L.pvec, *qLD = s + m.L.qLD;
     const float *qM = s + m.L.qM;
     float *aref = g.efc, *D = g.efc + m.maxefc, *res = g.efc + 2*m.maxefc,
           *jp = g.efc + 3*m.maxefc, *frc = g.efc + 4*m.maxefc;
-    /* dense packed copy of M */
-    for (int e = lane; e < m.npack; e += TEAM) Md[e] = 0.f;
-    sync();
-    for (int e = lane; e < m.nM; e += TEAM) Md[pack_idx(MI(ent_i, e), MI(ent_j, e))] = qM[e];
-    sync();
     int maxit = m.solver_iterations < 50 ? m.solver_iterations : 50;
     for (int it = 0; it < maxit; it++) {
       rows_apply(qacc, res);
@@ -920,7 +923,7 @@ FB_UNROLL
         frc[r] = (rr < 0.f) ? D[r]*rr : 0.f;   /* y = D min(0, res) */
       }
       sync();
-      md_times(qacc, tmp1);                      /* tmp1 = M a */
+      mul_m(qacc, tmp1);                         /* tmp1 = M a */
       float gref = 0.f;                          /* magnitude of the terms the gradient is the difference of */
       for (int v = lane; v < nv; v += TEAM) {
         gref += tmp1[v]*tmp1[v] + fsm[v]*fsm[v];
@@ -936,13 +939,13 @@ FB_UNROLL
        * once the active set is right the gradient is rounding noise, ~5e-6 of the terms it is
        * the difference of.  Stop at whichever floor comes first. */
       if (sqrtf(gn)*m.solver_scale < fmaxf(m.tolerance, 2e-5f*sqrtf(gref)*m.solver_scale)) break;
-      /* H = M + sum_active D J'J (packed lower) */
-      for (int e = lane; e < m.npack; e += TEAM) {
-        int u = (int)((sqrtf(8.f*(float)e + 1.f) - 1.f)*0.5f);
-        while (pack_idx(u + 1, 0) <= e) u++;
-        while (pack_idx(u, 0) > e) u--;
-        int v = e - pack_idx(u, 0);
-        float h = Md[e];
+      /* H = M + sum_active D J'J.  Every row of J is supported on the ancestors of ONE body
+       * (limits: one dof; plane contacts: the chain of the touching body), so H has exactly the
+       * tree sparsity of M: it is assembled in M's layout and factored by the same scheduled
+       * sparse L'DL (leaves first), no dense 33x33 matrix. */
+      for (int e = lane; e < m.nM; e += TEAM) {
+        const int u = MI(ent_i, e), v = MI(ent_j, e);      /* v is u or an ancestor of u */
+        float h = qM[e];
         if (u == v) {
           int j = MI(dof_jnt, u);
           if (MI(jnt_type, j) != FB_JNT_FREE) {
@@ -952,9 +955,8 @@ FB_UNROLL
         }
         for (int i = 0; i < ncon; i++) {
           int c = con_cand[i], b = MI(cand_body, c);
-          unsigned wu = (unsigned)MI(body_ancmask, b*m.nmaskw + (u >> 5));
-          unsigned wv = (unsigned)MI(body_ancmask, b*m.nmaskw + (v >> 5));
-          if (!((wu >> (u & 31)) & (wv >> (v & 31)) & 1u)) continue;
+          /* u on the chain of b implies v on it too */
+          if (!(((unsigned)MI(body_ancmask, b*m.nmaskw + (u >> 5)) >> (u & 31)) & 1u)) continue;
           int r = 2*nj + 4*i;
           float d = D[r], mu = MF(cand_friction, c);
           float nu_ = g.J3[(3*i)*nv + u], nv_ = g.J3[(3*i)*nv + v];
@@ -965,49 +967,17 @@ FB_UNROLL
           if (res[r+2] < 0.f) h += d*(nu_ + t2u)*(nv_ + t2v);
           if (res[r+3] < 0.f) h += d*(nu_ - t2u)*(nv_ - t2v);
         }
-        /* stored with the dof order reversed: the dense factorisation below then eliminates
-         * leaves before roots, the order that keeps the Schur complements physical (composite
-         * inertias) and the fp32 pivots positive -- the order MuJoCo's sparse L'DL uses */
-        H[pack_idx(nv - 1 - v, nv - 1 - u)] = h;
+        qLD[e] = h;
       }
       sync();
-      /* in-place packed Cholesky H = L L' (reversed dof order) */
-      int bad = 0;
-      for (int j = 0; j < nv; j++) {
-        float djj = H[pack_idx(j, j)];
-        if (!(djj > FB_MINVAL)) { bad = 1; djj = FB_MINVAL; }   /* mju_cholFactor: clamp, go on */
-        float dj = sqrtf(djj), idj = 1.0f/dj;
-        sync();
-        for (int i = j + 1 + lane; i < nv; i += TEAM) H[pack_idx(i, j)] *= idj;
-        if (lane == 0) H[pack_idx(j, j)] = dj;
-        sync();
-        for (int i = j + 1 + lane; i < nv; i += TEAM) {
-          float lij = H[pack_idx(i, j)];
-          int rowi = pack_idx(i, 0);
-          for (int k = j + 1; k <= i; k++) H[rowi + k] -= lij*H[pack_idx(k, j)];
-        }
-        sync();
-      }
-      if (bad && lane == 0) FB_FLAG_OR(g.flags, FB_FLAG_SOLVER);
-      /* p = -H^-1 grad : forward (into tmp2), backward (into p); index j of the factor is
-       * dof nv-1-j */
-      for (int j = 0; j < nv; j++) {
-        float yj = -grad[nv - 1 - j]/H[pack_idx(j, j)];
-        sync();
-        for (int i = j + 1 + lane; i < nv; i += TEAM) grad[nv - 1 - i] += H[pack_idx(i, j)]*yj;
-        if (lane == 0) tmp2[j] = yj;
-        sync();
-      }
-      for (int j = nv - 1; j >= 0; j--) {
-        float xj = tmp2[j]/H[pack_idx(j, j)];
-        sync();
-        for (int i = lane; i < j; i += TEAM) tmp2[i] -= H[pack_idx(j, i)]*xj;
-        if (lane == 0) p[nv - 1 - j] = xj;
-        sync();
-      }
+      eliminate();
+      /* p = -H^-1 grad */
+      for (int v = lane; v < nv; v += TEAM) p[v] = -grad[v];
+      sync();
+      solve_ld(p, tmp2);
       /* exact line search on phi'(alpha) = g0 + alpha pMp + sum D jp min(0, res + alpha jp) */
       rows_apply(p, jp);
-      md_times(p, tmp2);
+      mul_m(p, tmp2);
       float pMp = 0.f, g0 = 0.f;
       for (int v = lane; v < nv; v += TEAM) { pMp += p[v]*tmp2[v]; g0 += p[v]*tmp1[v]; }
       pMp = T::sum(mask, pMp);

@@ -35,6 +35,7 @@ struct DevOffsets {
   int jnt_type, jnt_body, jnt_qposadr, jnt_dofadr, jnt_limited, jnt_actstart, act_sorted;
   int dof_body, dof_jnt, dof_parent, dof_Madr, dof_nanc;
   int ent_i, ent_j;
+  int col_start, col_ent, col_dof;   /* per dof: entries (e, d) of descendants d whose row holds it */
   int st_pivstart, st_piv, fop_start, fop, sop_start, sop;   /* elimination schedule */
   int cand_body, cand_iscapsule, cand_sensor;
   int act_jnt, act_ctrllimited, act_forcelimited;
@@ -307,6 +308,20 @@ inline bool fb_build_model(const FbModel *fm, const FbFarms *ff, const FbWaveCon
   o.dof_nanc = put_i(I, nanc);
   o.ent_i = put_i(I, ent_i);
   o.ent_j = put_i(I, ent_j);
+  {
+    /* column view of the tree-sparse matrix: M x needs, for dof j, the entries M[d][j] of its
+     * descendants d (the row view gives the ancestors) */
+    std::vector<int32_t> cstart(nv + 1, 0), cent, cdof_;
+    for (int j = 0; j < nv; j++) {
+      cstart[j] = (int)cent.size();
+      for (int e = 0; e < fm->nM; e++)
+        if (ent_j[e] == j && ent_i[e] != j) { cent.push_back(e); cdof_.push_back(ent_i[e]); }
+    }
+    cstart[nv] = (int)cent.size();
+    o.col_start = put_i(I, cstart);
+    o.col_ent = put_i(I, cent);
+    o.col_dof = put_i(I, cdof_);
+  }
 
   /* Scheduled sparse L'DL and back-substitution.  Pivots are grouped into stages by
    * tree depth (deepest first): every pivot of a stage has all its descendants
@@ -735,7 +750,7 @@ inline bool fb_build_model(const FbModel *fm, const FbFarms *ff, const FbWaveCon
     L.cacc = L.altB;
     L.buf = L.altB;
     int natural = pad4(16*nb) + pad4(16*nb > 6*nv ? 16*nb : 6*nv);
-    int need = nc > 0 || m.any_limit ? 2*pad4(m.npack) : 0;
+    int need = 0;   /* the Newton step factors H in M's tree-sparse layout (qLD): no dense scratch */
     L.Md = L.scratch;
     L.H = L.scratch + pad4(m.npack);
     off += natural > need ? natural : need;
