@@ -171,6 +171,17 @@ FB_DEV void fb_sincos_half(float x, float *sn, float *cs) {
   }
 }
 
+/* Pin a constant-bank value into a register at this point of the program: ptxas otherwise
+ * issues the indexed LDC right before the first use and the lone warp of the scheduler waits
+ * out its latency every time. */
+#ifdef FB_HOST_EMU
+#define FB_PIN_F(x) (void)(x)
+#define FB_PIN_I(x) (void)(x)
+#else
+#define FB_PIN_F(x) asm volatile("" :: "f"(x))
+#define FB_PIN_I(x) asm volatile("" :: "r"(x))
+#endif
+
 template <int BLK> struct FbFast {
   const FbParams &P;
   const DevModel &m;
@@ -355,7 +366,20 @@ FB_UNROLL
     float lasto[3] = {0.f, 0.f, 0.f}, lastv[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
     float lastR[9] = {1.f, 0.f, 0.f, 0.f, 1.f, 0.f, 0.f, 0.f, 1.f};
     for (int b = 1; b < nb; b++) {
-      const FastRec &rc = rec[b];
+      const FastRec &rc0 = rec[b];
+      struct { int parent, jtype, flags, pblk, link, chk0, chk1; float dpos[3], bquat[4], axis[3], qpos0, lo, hi, margin, hloc[3], chk[4], jpos[3]; } rc;
+      rc.parent = rc0.parent; rc.jtype = rc0.jtype; rc.flags = rc0.flags; rc.pblk = rc0.pblk; rc.link = rc0.link;
+      rc.chk0 = rc0.chk0; rc.chk1 = rc0.chk1; rc.qpos0 = rc0.qpos0; rc.lo = rc0.lo; rc.hi = rc0.hi; rc.margin = rc0.margin;
+FB_UNROLL
+      for (int k = 0; k < 3; k++) { rc.dpos[k] = rc0.dpos[k]; rc.axis[k] = rc0.axis[k]; rc.hloc[k] = rc0.hloc[k]; rc.jpos[k] = rc0.jpos[k]; }
+FB_UNROLL
+      for (int k = 0; k < 4; k++) { rc.bquat[k] = rc0.bquat[k]; rc.chk[k] = rc0.chk[k]; }
+      FB_PIN_I(rc.parent); FB_PIN_I(rc.jtype); FB_PIN_I(rc.flags); FB_PIN_I(rc.pblk); FB_PIN_I(rc.link);
+      FB_PIN_F(rc.qpos0); FB_PIN_F(rc.lo); FB_PIN_F(rc.hi); FB_PIN_F(rc.margin);
+FB_UNROLL
+      for (int k = 0; k < 3; k++) { FB_PIN_F(rc.dpos[k]); FB_PIN_F(rc.axis[k]); FB_PIN_F(rc.hloc[k]); }
+FB_UNROLL
+      for (int k = 0; k < 4; k++) { FB_PIN_F(rc.bquat[k]); FB_PIN_F(rc.chk[k]); }
       pb += FB_NF*BLK;
       pn += FG_NF*BLK;
       const float cq = nq, cqd = nqd;
@@ -503,6 +527,15 @@ FB_UNROLL
     float *pg = gblock(nb - 1) + FG_NF*BLK;
     for (int b = nb - 1; b >= 1; b--) {
       const FastRec &rc = rec[b];
+      /* issue the record loads of this body now (see FB_PIN_F) */
+      FB_PIN_I(rc.jtype); FB_PIN_I(rc.flags); FB_PIN_I(rc.pblk); FB_PIN_I(rc.parent);
+      FB_PIN_F(rc.mass); FB_PIN_F(rc.Kq); FB_PIN_F(rc.Kqd); FB_PIN_F(rc.KqU); FB_PIN_F(rc.KqdU);
+      FB_PIN_F(rc.wfreq); FB_PIN_F(rc.wlag); FB_PIN_F(rc.woff); FB_PIN_F(rc.wamp); FB_PIN_F(rc.wgain);
+      FB_PIN_F(rc.stiffness); FB_PIN_F(rc.damping); FB_PIN_F(rc.armature);
+FB_UNROLL
+      for (int k = 0; k < 3; k++) { FB_PIN_F(rc.hloc[k]); FB_PIN_F(rc.axis[k]); }
+FB_UNROLL
+      for (int k = 0; k < 5; k++) FB_PIN_F(rc.Ib[k]);
       pb -= FB_NF*BLK;
       pg -= FG_NF*BLK;
       const int jtype = rc.jtype, flags = rc.flags;
@@ -714,6 +747,13 @@ FB_UNROLL
     float *pg = gblock(1) - FG_NF*BLK;
     for (int b = 1; b < nb; b++) {
       const FastRec &rc = rec[b];
+      FB_PIN_I(rc.jtype); FB_PIN_I(rc.flags); FB_PIN_I(rc.pblk); FB_PIN_I(rc.parent); FB_PIN_I(rc.fj);
+      FB_PIN_I(rc.xr); FB_PIN_I(rc.swim);
+      FB_PIN_F(rc.lift); FB_PIN_F(rc.height);
+FB_UNROLL
+      for (int k = 0; k < 3; k++) { FB_PIN_F(rc.hloc[k]); FB_PIN_F(rc.axis[k]); }
+FB_UNROLL
+      for (int k = 0; k < 6; k++) FB_PIN_F(rc.coef[k]);
       pb += FB_NF*BLK;
       pg += FG_NF*BLK;
       const int jtype = rc.jtype, flags = rc.flags;
