@@ -51,6 +51,9 @@ def parse_args():
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-e2e', action='store_true')
     ap.add_argument('--no-fast', action='store_true', help='team kernel only (comparison runs)')
+    ap.add_argument('--team-constraints', action='store_true',
+                    help='hand-overs (limits / contacts) go to the team kernel instead of the per-thread '
+                         'constrained kernel (comparison runs)')
     return ap.parse_args()
 
 
@@ -218,6 +221,8 @@ def run_b200(args, rank, world, local_rank):
     physics.set_wave_controller(*wave_controller(spec, model))
     if args.no_fast:
         physics.set_fast_path(False)
+    if args.team_constraints:
+        physics.set_constraint_path(False)
     physics.reset(qpos0, qvel0)
 
     stream_ptr = __import__('ctypes').c_void_p()
@@ -353,8 +358,10 @@ def run_b200(args, rank, world, local_rank):
                              'links/joints/contacts/xfrc log, on-device travelling-wave control'),
                 'n_envs': n_local*world, 'physics_steps_per_step': args.inner, 'timestep': model.timestep,
                 'nv': model.nv, 'nbody': model.nbody,
-                'kernels': ('fb_fast_kernel (1 thread = 1 env, articulated-body recursion) then '
-                            'fb_step_kernel (lane team = 1 env, constraint solver) on the hand-overs'
+                'kernels': (('fb_fast_kernel (1 thread = 1 env, articulated-body recursion) then '
+                             + ('fb_fastc_kernel (1 thread = 1 env, matrix-free Newton on the same recursion) '
+                                'on the environments with an active limit / contact' if physics.constraint_path
+                                else 'fb_step_kernel (lane team = 1 env, constraint solver) on the hand-overs'))
                             if physics.fast_path else 'fb_step_kernel only'),
                 'fast_envs_per_block': physics.fast_path,
                 'fast_smem_bytes_per_env': physics.fast_smem_bytes_per_env,
@@ -370,7 +377,9 @@ def run_b200(args, rank, world, local_rank):
             'roofline': {
                 'bound': 'hbm', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s',
                 'frac': achieved/peak, 'traffic': traffic,
-                'kernel': (f'fb_fast_kernel<{physics.fast_path}>' if physics.fast_path
+                'kernel': ((f'fb_fastc_kernel<{physics.fast_path}>' if physics.constraint_path and 2*handed_over > n_local
+                            else f'fb_fast_kernel<{physics.fast_path}>') if physics.fast_path and
+                           (physics.constraint_path or 2*handed_over <= n_local)
                            else f'fb_step_kernel<{physics.team_lanes}>'),
                 'kernel_ms': k_ms,
                 'algorithmic_bytes_per_env_step': b_log,

@@ -1329,6 +1329,7 @@ struct FbParams {
   int seq_pos;
   float *fast_scratch;            /* [n_scratch][fast_scratch_stride]: second half of the per-thread state */
   long long fast_scratch_stride;
+  float *con_scratch;             /* per-thread constrained step (fb_fastc.h): [warp][X.n_con][lane] */
 };
 
 /* start of ring row `it` for one environment: floats_per_row = N*C of the kind */

@@ -19,7 +19,7 @@
 #include <string>
 #include <vector>
 
-#include "fb_fast.h"
+#include "fb_fastc.h"
 
 #ifndef FB_HOST_EMU
 #include <cuda_runtime.h>
@@ -107,6 +107,33 @@ fb_fast_kernel(const __grid_constant__ FbFastParams Q) {
   }
 }
 
+/* per-thread constrained step (fb_fastc.h) over the environments the kernel above handed over:
+ * thread i of the launch takes pending[i] from the step it stopped at */
+struct FbFastConParams {
+  FbParams P;
+  FastRec rec[FB_FAST_MAXBODY];
+  CandRec cand[FB_FAST_MAXCAND];  /* collision candidates in body order, constant bank */
+};
+static_assert(sizeof(FbFastConParams) <= 32764, "kernel parameters of fb_fastc_kernel exceed 32 KB");
+
+template <int BLK>
+__global__ void __launch_bounds__(BLK)
+fb_fastc_kernel(const __grid_constant__ FbFastConParams Q) {
+  extern __shared__ __align__(16) float fb_smem[];
+  const FbParams &P = Q.P;
+  const int i = blockIdx.x*BLK + threadIdx.x;
+  const int count = P.use_pending ? P.pending_count[P.parity] : P.n_envs;
+  if (i >= count) return;
+  const int identity = !P.use_pending || count == P.n_envs;
+  const int env = identity ? i : P.pending[i];
+  const int k0 = P.use_pending ? P.steps_done[env] : 0;
+  const size_t t0 = (size_t)blockIdx.x*BLK;
+  FbFastCon<BLK> st(P, Q.rec, Q.cand, fb_smem + threadIdx.x, P.fast_scratch + t0*P.m.X.n_scratch + threadIdx.x,
+                    P.con_scratch + t0*P.m.X.n_con + threadIdx.x, env);
+  const int coop = BLK == 32 && identity && P.m.X.coop_io && (blockIdx.x + 1)*BLK <= count;
+  st.run_con(k0, coop, threadIdx.x);
+}
+
 /* ring row `row` of every environment -> dense [n_envs][row_floats] (the reference's row
  * layout); threads run over (vector, env) with env fastest: coalesced reads */
 __global__ void fb_gather_rows_kernel(const float *__restrict__ log, long long row, int row_floats,
@@ -147,10 +174,12 @@ struct FbHandle {
   int device, team, envs_per_block, threads;
   size_t smem_bytes;
   int fast_enabled, fast_block;     /* environment-per-thread kernel: on/off, threads per block */
+  int con_thread;                   /* 1: hand-overs go to the per-thread constrained kernel, 0: to the team kernel */
   size_t fast_smem_bytes;
   long long launch_parity;
 #ifndef FB_HOST_EMU
   FbFastParams *fastQ;               /* host staging of the per-thread kernel's parameters */
+  FbFastConParams *conQ;             /* ... and of the per-thread constrained kernel's */
 #endif
   fbStream stream;
   std::vector<void *> allocs;
@@ -270,6 +299,10 @@ static int upload_model(FbHandle *h) {
     if (!h->fastQ) h->fastQ = new FbFastParams();
     memset(h->fastQ->rec, 0, sizeof(h->fastQ->rec));
     memcpy(h->fastQ->rec, h->hm.rec.data(), sizeof(FastRec)*h->hm.rec.size());
+    if (!h->conQ) h->conQ = new FbFastConParams();
+    memcpy(h->conQ->rec, h->fastQ->rec, sizeof(h->conQ->rec));
+    memset(h->conQ->cand, 0, sizeof(h->conQ->cand));
+    if (h->hm.m.X.con_ok) memcpy(h->conQ->cand, h->hm.crec.data(), sizeof(CandRec)*h->hm.crec.size());
   }
 #endif
   return 0;
@@ -290,6 +323,7 @@ static int launch(FbHandle *h, int mode, int n_steps, int want_derived) {
     if (h->seq_pos == h->seq_len) h->seq_len = h->seq_pos = 0;     /* consumed: ctrl is held again */
   }
   const int use_fast = h->fast_enabled && P.m.X.ok && mode == FB_MODE_STEP && !want_derived;
+  const int con_thread = use_fast && h->con_thread && P.m.X.con_ok;
   P.use_pending = use_fast;
   P.parity = (int)(h->launch_parity & 1);
   if (use_fast) h->launch_parity++;
@@ -303,10 +337,18 @@ static int launch(FbHandle *h, int mode, int n_steps, int want_derived) {
       int done = st.run(0, 0);
       if (done < n_steps) { P.steps_done[env] = done; P.pending[P.pending_count[P.parity]++] = env; }
     }
+    if (con_thread) {
+      std::vector<float> fc((size_t)m.X.n_con + 8, 0.f);
+      for (int i = 0; i < P.pending_count[P.parity]; i++) {
+        const int env = P.pending[i];
+        FbFastCon<1> st(P, h->hm.rec.data(), h->hm.crec.data(), fs.data(), fg.data(), fc.data(), env);
+        st.run_con(P.steps_done[env], 0, 0);
+      }
+    }
   }
   std::vector<float> s((size_t)m.L.n_float + 8, 0.f);
   std::vector<int> si((size_t)m.L.n_int + 8, 0);
-  const int count = use_fast ? P.pending_count[P.parity] : P.n_envs;
+  const int count = use_fast ? (con_thread ? 0 : P.pending_count[P.parity]) : P.n_envs;
   for (int i = 0; i < count; i++) {
     int env = use_fast ? P.pending[i] : i;
     fb_run_env<1>(P, env, use_fast ? P.steps_done[env] : 0, s.data(), si.data(), 0, 0, 1u);
@@ -320,8 +362,12 @@ static int launch(FbHandle *h, int mode, int n_steps, int want_derived) {
     h->fastQ->P = P;
     fb_fast_kernel<32><<<fblocks, 32, h->fast_smem_bytes, h->stream>>>(*h->fastQ);
     h->launches++;
+    if (con_thread) {
+      h->conQ->P = P;
+      fb_fastc_kernel<32><<<fblocks, 32, h->fast_smem_bytes, h->stream>>>(*h->conQ);
+    }
   }
-  switch (h->team) {
+  if (!con_thread) switch (h->team) {
     case 8: fb_step_kernel<8><<<blocks, h->threads, h->smem_bytes, h->stream>>>(P); break;
     case 16: fb_step_kernel<16><<<blocks, h->threads, h->smem_bytes, h->stream>>>(P); break;
     default: fb_step_kernel<32><<<blocks, h->threads, h->smem_bytes, h->stream>>>(P); break;
@@ -354,6 +400,7 @@ void fb_destroy(FbHandle *h) {
   cudaStreamDestroy(h->copy_stream);
   cudaStreamDestroy(h->stream);
   delete h->fastQ;
+  delete h->conQ;
 #endif
   delete h;
 }
@@ -368,8 +415,10 @@ int fb_create(const FbModel *model, const FbFarms *farms, int n_envs, int device
   h->last_ms = 0.f; h->has_wc = false; h->gather_links = h->gather_joints = h->gather_env = nullptr;
   h->seq_dev = h->seq_stage = nullptr; h->seq_len = h->seq_pos = h->seq_cap = 0;
   h->fast_enabled = 1; h->fast_block = 1; h->fast_smem_bytes = 0; h->launch_parity = 0;
+  h->con_thread = 1;
+  if (const char *ev = getenv("FARMS_B200_CON_THREAD")) h->con_thread = atoi(ev) != 0;
 #ifndef FB_HOST_EMU
-  h->fastQ = nullptr;
+  h->fastQ = nullptr; h->conQ = nullptr;
 #endif
   if (const char *ev = getenv("FARMS_B200_FAST")) h->fast_enabled = atoi(ev) != 0;
   memset(&h->P, 0, sizeof(h->P));
@@ -434,6 +483,10 @@ int fb_create(const FbModel *model, const FbFarms *farms, int n_envs, int device
       ce = cudaFuncSetAttribute(fb_fast_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->fast_smem_bytes);
       if (ce == cudaSuccess)
         ce = cudaFuncSetAttribute(fb_fast_kernel<32>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+      if (ce == cudaSuccess)
+        ce = cudaFuncSetAttribute(fb_fastc_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->fast_smem_bytes);
+      if (ce == cudaSuccess)
+        ce = cudaFuncSetAttribute(fb_fastc_kernel<32>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
       if (ce != cudaSuccess) { fb_destroy(h); return fail(std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(ce)); }
     }
   }
@@ -455,6 +508,8 @@ int fb_create(const FbModel *model, const FbFarms *farms, int n_envs, int device
   P.fast_scratch_stride = (long long)((n + 31) & ~(size_t)31);
   P.fast_scratch = nullptr;
   if (m.X.ok) bad |= alloc_arr(h, &P.fast_scratch, (size_t)P.fast_scratch_stride*(m.X.n_scratch > 0 ? m.X.n_scratch : 1));
+  P.con_scratch = nullptr;
+  if (m.X.ok) bad |= alloc_arr(h, &P.con_scratch, (size_t)P.fast_scratch_stride*(m.X.n_con > 0 ? m.X.n_con : 1));
   bad |= alloc_arr(h, &P.d_xpos, n*3*nb); bad |= alloc_arr(h, &P.d_xquat, n*4*nb);
   bad |= alloc_arr(h, &P.d_xipos, n*3*nb); bad |= alloc_arr(h, &P.d_linvel, n*3*nb);
   bad |= alloc_arr(h, &P.d_angvel, n*3*nb); bad |= alloc_arr(h, &P.d_actf, n*nu);
@@ -816,6 +871,12 @@ int fb_set_fast_path(FbHandle *h, int enable) {
   h->fast_enabled = enable != 0;
   return 0;
 }
+int fb_set_constraint_path(FbHandle *h, int per_thread) {
+  if (!h) return fail("null handle");
+  h->con_thread = per_thread != 0;
+  return 0;
+}
+int fb_constraint_path(FbHandle *h) { return h && h->fast_enabled && h->hm.m.X.con_ok ? h->con_thread : 0; }
 /* 0: team kernel only; otherwise the environments per block of the per-thread kernel */
 int fb_fast_path(FbHandle *h) {
   if (!h) return 0;
@@ -830,6 +891,11 @@ int fb_last_pending(FbHandle *h, int *count) {
   *count = h->P.use_pending ? both[h->P.parity] : h->P.n_envs;
   return 0;
 }
+
+#ifdef FB_HOST_EMU
+/* emulation harness only: counters of the per-thread constrained solver */
+void fb_emu_solver_stats(double *stats3) { fb_emu_stats = stats3; }
+#endif
 
 int fb_team_lanes(FbHandle *h) { return h ? h->team : 0; }
 int fb_smem_bytes_per_env(FbHandle *h) {

@@ -50,6 +50,11 @@ FB_DEV void fb_st4(float *p, float a, float b, float c, float d) {
 FB_DEV void fb_st2(float *p, float a, float b) { __stcs(reinterpret_cast<float2 *>(p), make_float2(a, b)); }
 #endif
 
+/* word w (0..3) of a four-word mask held in registers */
+FB_DEV unsigned fb_sel4(const unsigned *m4, int w) {
+  return w == 0 ? m4[0] : (w == 1 ? m4[1] : (w == 2 ? m4[2] : m4[3]));
+}
+
 /* articulated inertia about a point, world axes:  [ A  H ] [w]   A, M symmetric
  *                                                 [ H' M ] [v]   (xx yy zz xy xz yz) */
 struct ArtInertia {
@@ -177,7 +182,10 @@ FB_DEV void fb_sincos_half(float x, float *sn, float *cs) {
 #ifdef FB_HOST_EMU
 #define FB_PIN_F(x) (void)(x)
 #define FB_PIN_I(x) (void)(x)
+#define FB_ANY(p) (p)
 #else
+/* warp vote at a point every live lane of the warp reaches together */
+#define FB_ANY(p) __any_sync(__activemask(), (p))
 #define FB_PIN_F(x) asm volatile("" :: "f"(x))
 #define FB_PIN_I(x) asm volatile("" :: "r"(x))
 #endif
@@ -193,9 +201,14 @@ template <int BLK> struct FbFast {
   float rt[13];       /* floating root: qpos[7], qvel[6] (registers) */
   float rootpos[3];   /* world position the anchors are measured from (the floating root) */
   float rqn[4];       /* normalised root quaternion of the current step */
+  /* constrained step (fb_fastc.h; unused on the unconstrained kernel): scratch like gs, the
+   * candidate records, and the masks of the candidates that touch in this lane / in any lane */
+  float *cs, *csc;
+  const CandRec *crec;
+  unsigned hm[4], hany[4];
 
   FB_MEM FbFast(const FbParams &P_, const FastRec *rec_, float *s_, float *gs_, int env_)
-      : P(P_), m(P_.m), rec(rec_), s(s_), env(env_), gs(gs_) {
+      : P(P_), m(P_.m), rec(rec_), s(s_), env(env_), gs(gs_), cs(0), csc(0), crec(0) {
     env_phase = P.env_phase[env];
     rootpos[0] = rootpos[1] = rootpos[2] = 0.f;
     rqn[0] = 1.f; rqn[1] = rqn[2] = rqn[3] = 0.f;
@@ -206,6 +219,9 @@ FB_UNROLL
   FB_MEM float *block(int b) const { return s + (m.X.body0 + FB_NF*(b - 1))*BLK; }
   FB_MEM float *gblock(int b) const { return gs + FG_NF*(b - 1)*BLK; }
   FB_MEM float *slot(int i) const { return s + (m.X.slots + 27*i)*BLK; }
+  FB_MEM float *nblock(int b) const { return cs + NB_NF*(b - 1)*BLK; }
+  FB_MEM float *nroot() const { return cs + NB_NF*(m.nbody - 1)*BLK; }
+  FB_MEM float *ncand(int fc) const { return csc + NC_NF*BLK*fc; }
 
   /* generic actuation (clamps, gears, partial logging): force sum and farms joint_torque */
   /* ctrl of actuator a at this step: the uploaded sequence when there is one, else the held value */
@@ -505,8 +521,16 @@ FB_UNROLL
     return active;
   }
 
-  /* ---- pass 2: leaves -> root, articulated inertias and bias forces */
+  /* ---- pass 2: leaves -> root, articulated inertias and bias forces.
+   * MODE 0: the step, (M + h D) x = f.  MODE 1 (constrained step): M a0 = f, the unconstrained
+   * acceleration; U, u, 1/d go to the constraint scratch and the applied wrench stays where it is.
+   * MODE 2 (constrained step): MODE 0 with the constraint forces applied (contact forces as body
+   * wrenches, limit forces as joint torques). */
   FB_MEM void pass_inertia(float time, float *aroot, int store_ctrl, const float *seqk) {
+    pass_inertia_m<0>(time, aroot, store_ctrl, seqk);
+  }
+  template <int MODE>
+  FB_MEM void pass_inertia_m(float time, float *aroot, int store_ctrl, const float *seqk) {
     const int nb = m.nbody;
     const float hdt = m.timestep;
     ArtInertia C;        /* carry from child b+1 */
@@ -558,6 +582,23 @@ FB_UNROLL
       const float mass = rc.mass;
       float h[3], Iw[6];
       m_rot(R, rc.hloc[0], rc.hloc[1], rc.hloc[2], h);
+      if (MODE == 2) {
+        /* contact forces of this body's candidates: world force at the contact point */
+        for (int fc = rc.bc0; fc < rc.bc1; fc++) {
+          if (!((fb_sel4(hany, fc >> 5) >> (fc & 31)) & 1u)) continue;
+          const float *pc_ = ncand(fc);
+          const int on = (fb_sel4(hm, fc >> 5) >> (fc & 31)) & 1u;
+          float Fw[3], rr[3], cr[3];
+FB_UNROLL
+          for (int k = 0; k < 3; k++) {
+            Fw[k] = on ? fb_ld_scr(pc_ + (NC_RES + k)*BLK) : 0.f;
+            rr[k] = on ? fb_ld_scr(pc_ + (NC_R + k)*BLK) - h[k] : 0.f;
+          }
+          v_cross(rr, Fw, cr);
+FB_UNROLL
+          for (int k = 0; k < 3; k++) { fx[k] += Fw[k]; fx[3 + k] += cr[k]; }
+        }
+      }
       if (flags & FT_AXISYM) {
         /* Iw = Ia 1 + dI n n', n = R n_body */
         float n[3];
@@ -659,6 +700,7 @@ FB_UNROLL
         }
         if (rc.stiffness != 0.f) tau -= rc.stiffness*(qj - P.qpos_spring[(size_t)env*m.nq + rc.qa]);
         tau -= rc.damping*qd;
+        if (MODE == 2) tau += fb_ld_scr(nblock(b) + NB_TAUC*BLK);
         float d, u;
         float aq[3] = {ax[0]*qd, ax[1]*qd, ax[2]*qd};
         if (jtype == FB_JNT_HINGE) {
@@ -676,7 +718,7 @@ FB_UNROLL
           c[0] = c[1] = c[2] = 0.f;
           v_cross(v, aq, c + 3);
         }
-        d += rc.armature + hdt*rc.damping;
+        d += MODE == 1 ? rc.armature : rc.armature + hdt*rc.damping;
         const float dinv = fb_rcp(d);
         /* Ia = I - U U'/d */
         sym_rank1(I.A, U, dinv);
@@ -696,9 +738,16 @@ FB_UNROLL
         ht_mul(I.H, c, t0); sym_mul(I.M, c + 3, t1);
 FB_UNROLL
         for (int k = 0; k < 3; k++) pA[3 + k] += t0[k] + t1[k] + U[3 + k]*ud;
+        if (MODE == 1) {
+          float *pn_ = nblock(b);
 FB_UNROLL
-        for (int k = 0; k < 6; k++) fb_st_scr(pg + (FG_W + k)*BLK, U[k]);
-        fb_st_scr(pg + FG_U*BLK, u); fb_st_scr(pg + FG_DINV*BLK, dinv); fb_st_scr(pg + FG_TRQ*BLK, trq);
+          for (int k = 0; k < 6; k++) fb_st_scr(pn_ + (NB_U + k)*BLK, U[k]);
+          fb_st_scr(pn_ + NB_UU*BLK, u); fb_st_scr(pn_ + NB_DINV*BLK, dinv);
+        } else {
+FB_UNROLL
+          for (int k = 0; k < 6; k++) fb_st_scr(pg + (FG_W + k)*BLK, U[k]);
+          fb_st_scr(pg + FG_U*BLK, u); fb_st_scr(pg + FG_DINV*BLK, dinv); fb_st_scr(pg + FG_TRQ*BLK, trq);
+        }
       }
       if (rc.parent == 0) continue;        /* fixed base: nothing above */
       /* move to the parent's anchor and hand over */
@@ -732,6 +781,11 @@ FB_UNROLL
 
   /* ---- pass 3: root -> leaves, accelerations, Euler, joints / xfrc rows, drag */
   FB_MEM int pass_accel(const float *aroot, float *row_joints, float *row_xfrc) {
+    return pass_accel_m<0>(aroot, row_joints, row_xfrc);
+  }
+  /* CON = 1: the joints rows carry the limit forces of the constrained step */
+  template <int CON>
+  FB_MEM int pass_accel_m(const float *aroot, float *row_joints, float *row_xfrc) {
     const int nb = m.nbody;
     const float hdt = m.timestep;
     float ac[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};   /* carry: acceleration of body b-1 */
@@ -842,13 +896,15 @@ FB_UNROLL
             const int cp = m.col_jpos, cv = m.col_jvel, ct = m.col_jtrq, cols = m.joint_cols;
             float *row = row_joints + (long long)((cols/2)*rc.fj)*ev;   /* 8-byte vectors, coalesced across the warp */
             const float trq = cx[8]*m.inv_torques, jv = qdn*m.inv_angvel;
+            const float lf = CON ? fb_ld_scr(nblock(b) + NB_LIMF*BLK)*m.inv_torques : 0.f;
+            const int cl = CON ? m.col_jlim : -1;
             if (m.X.jrow_std) {
-              /* farms layout: 18 columns, position 0, velocity 1, torque 11 */
+              /* farms layout: 18 columns, position 0, velocity 1, torque 11, limit force 16 */
               fb_st2(row, qn, jv);
 FB_UNROLL
-              for (int g = 1; g < 9; g++) fb_st2(row + g*ev, 0.f, g == 5 ? trq : 0.f);
+              for (int g = 1; g < 9; g++) fb_st2(row + g*ev, g == 8 ? lf : 0.f, g == 5 ? trq : 0.f);
             } else {
-#define FB_JCOL(c_) ((c_) == cp ? qn : ((c_) == cv ? jv : ((c_) == ct ? trq : 0.f)))
+#define FB_JCOL(c_) ((c_) == cp ? qn : ((c_) == cv ? jv : ((c_) == ct ? trq : ((c_) == cl ? lf : 0.f))))
               for (int c = 0; c < cols; c += 2) fb_st2(row + (c/2)*ev, FB_JCOL(c), FB_JCOL(c + 1));
 #undef FB_JCOL
             }

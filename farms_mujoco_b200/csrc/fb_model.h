@@ -55,6 +55,10 @@ struct DevOffsets {
   int ft_actwc;   /* int   [nu] wave index of an actuator, -1 */
   int ft_actoff;  /* int   [nu] 1: force-limited to [0, 0] (contributes nothing) */
   int ft_chk;     /* float [nchk][4] conservative plane checks (normal, offset) */
+  /* tables of the per-thread constrained step (fb_fastc.h) */
+  int ft_sstart;  /* int   [n_contacts+1] contact sensor -> entries (CandRec index, sign) it sums (sensors.pyx:140-190) */
+  int ft_scand;   /* int   [...] */
+  int ft_ssign;   /* float [...] */
 };
 
 /* ---- environment-per-thread path (fb_fast.h) ------------------------------------ */
@@ -88,8 +92,20 @@ struct FastRec {
   float Ib[6], wfreq, wlag;               /* inertia about the com, body axes (xx yy zz xy xz yz) */
   float wamp, woff, lift, height;         /* lift = 1000*9.81*mass/density (drag.pyx:142-145) */
   float coef[6], KqU, KqdU;               /* KqU/KqdU/T0U: the part of the actuation that the */
-  float T0U, nchk_pad[3];                 /* farms joint_torque column does not log */
+  float T0U;                              /* farms joint_torque column does not log */
+  int32_t bc0, bc1, pad0;                 /* candidates of the body: CandRec[bc0 .. bc1) (fb_fastc.h) */
   float chk[4];                           /* first conservative plane check (normal, offset) */
+};
+
+/* One collision candidate (world plane vs sphere / capsule end) of the per-thread constrained
+ * step (fb_fastc.h), in body order; travels in the kernel parameters like FastRec.  16 words. */
+#define FB_FAST_MAXCAND 112
+struct CandRec {
+  int32_t body, cid, iscapsule, pblk;     /* cid: index into the cand_* tables; pblk = FB_NF*(body-1) */
+  float pn[3], mu;                        /* plane normal (world), friction */
+  float lpos[3], radius;                  /* centre relative to the body's joint anchor (body axes) */
+  float laxis[3], pd;                     /* capsule axis (body axes); plane offset */
+  float includemargin, invw, pad[2];
 };
 
 /* per-environment shared-memory layout, in floats; element i of an environment lives at
@@ -107,7 +123,16 @@ struct DevFastLayout {
   int n_scratch;        /* global scratch floats per environment */
   int jrow_std;         /* farms joint row = 18 columns, position 0, velocity 1, torque 11 */
   int coop_io;          /* [32][nq + nv + nu + 6 nbody] fits the warp's shared memory: tiled state I/O */
+  int n_con;            /* global scratch floats per environment of the constrained step (fb_fastc.h) */
+  int con_ok;           /* 1 when the per-thread constrained step covers the model (else: team kernel) */
 };
+
+/* scratch of the per-thread constrained step (fb_fastc.h), element i of thread t at i*BLK + t:
+ * one block per moving body, one for the floating root, one per collision candidate */
+enum { NB_U = 0, NB_DINV = 6, NB_UU = 7, NB_AP = 8, NB_A = 14, NB_MD = 15, NB_P = 16, NB_MP = 17,
+       NB_DLO = 18, NB_DHI = 19, NB_ARLO = 20, NB_ARHI = 21, NB_LIMF = 22, NB_TAUC = 23, NB_NF = 24 };
+enum { NR_A = 0, NR_MD = 6, NR_P = 12, NR_MP = 18, NR_NF = 24 };
+enum { NC_R = 0, NC_T1 = 3, NC_D = 6, NC_RES = 7, NC_JP = 10, NC_POS = 13, NC_NF = 16 };
 
 /* per-environment shared-memory layout (float offsets; component-major SoA:
  * element (k, i) of an array with N items lives at off + k*N + i) */
@@ -149,6 +174,7 @@ struct FbHostModel {
   std::vector<float> F;
   DevModel m;  /* I/F pointers left null; the caller patches them */
   std::vector<FastRec> rec;   /* [nbody] when m.X.ok */
+  std::vector<CandRec> crec;  /* [ncand] in body order when m.X.con_ok */
   std::string error;
 };
 
@@ -695,12 +721,53 @@ inline bool fb_build_model(const FbModel *fm, const FbFarms *ff, const FbWaveCon
     o.ft_actwc = put_i(I, actwc);
     o.ft_actoff = put_i(I, is_off);
     o.ft_chk = put_f(F, chk);
+    /* per-thread constrained step: candidates in body order (CandRec), contact sensors as
+     * lists of (candidate in that order, sign) */
+    {
+      std::vector<CandRec> &crec = out.crec;
+      crec.clear();
+      X.con_ok = X.ok && nc <= FB_FAST_MAXCAND;
+      std::vector<int32_t> fc_of(nc > 0 ? nc : 1, -1), sstart(m.n_contacts + 1, 0), scand;
+      std::vector<double> ssign;
+      for (int b = 0; b < nb; b++) {
+        rec[b].bc0 = (int32_t)crec.size();
+        for (int c = 0; c < nc; c++) {
+          if (cbody[c] != b) continue;
+          if (b < 1) { X.con_ok = 0; continue; }
+          CandRec r;
+          std::memset(&r, 0, sizeof(r));
+          r.body = b; r.cid = c; r.iscapsule = ccaps[c]; r.pblk = FB_NF*(b - 1);
+          for (int k = 0; k < 3; k++) {
+            r.pn[k] = (float)pn[3*c + k];
+            r.lpos[k] = (float)(lpos[3*c + k] - (double)rec[b].jpos[k]);
+            r.laxis[k] = (float)laxis[3*c + k];
+          }
+          r.mu = (float)fm->cand_friction[c]; r.radius = (float)rad[c]; r.pd = (float)pd[c];
+          r.includemargin = (float)(fm->cand_margin[c] - fm->cand_gap[c]);
+          r.invw = (float)cinvw[c];
+          fc_of[c] = (int)crec.size();
+          crec.push_back(r);
+        }
+        rec[b].bc1 = (int32_t)crec.size();
+      }
+      for (int sx = 0; sx < m.n_contacts; sx++) {
+        sstart[sx] = (int)scand.size();
+        for (int c = 0; c < nc; c++)
+          for (int key = 0; key < 4; key++)
+            if (ff->cand_sensor[4*c + key] == sx && fc_of[c] >= 0) { scand.push_back(fc_of[c]); ssign.push_back((key & 1) ? 1.0 : -1.0); }
+      }
+      sstart[m.n_contacts] = (int)scand.size();
+      o.ft_sstart = put_i(I, sstart);
+      o.ft_scand = put_i(I, scand);
+      o.ft_ssign = put_f(F, ssign);
+      X.n_con = NB_NF*(nb - 1) + NR_NF + NC_NF*nc;
+    }
     X.body0 = 0;
     X.slots = FB_NF*(nb - 1);
     X.nslot = nslot;
     X.n_float = X.slots + 27*nslot;
     X.n_scratch = FG_NF*(nb - 1);
-    X.jrow_std = m.joint_cols == 18 && m.col_jpos == 0 && m.col_jvel == 1 && m.col_jtrq == 11;
+    X.jrow_std = m.joint_cols == 18 && m.col_jpos == 0 && m.col_jvel == 1 && m.col_jtrq == 11 && m.col_jlim == 16;
     X.coop_io = fm->nq + nv + (nu > 0 ? nu : 1) + 6*nb <= X.n_float;
   }
 

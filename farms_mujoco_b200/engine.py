@@ -59,6 +59,8 @@ ABI_SYMBOLS = {
     'fb_copy_to_device': (ct.c_int, [_H, ct.c_void_p, ct.c_void_p, ct.c_int64]),
     'fb_set_fast_path': (ct.c_int, [_H, ct.c_int]),
     'fb_fast_path': (ct.c_int, [_H]),
+    'fb_set_constraint_path': (ct.c_int, [_H, ct.c_int]),
+    'fb_constraint_path': (ct.c_int, [_H]),
     'fb_fast_smem_bytes_per_env': (ct.c_int, [_H]),
     'fb_last_pending': (ct.c_int, [_H, ct.POINTER(ct.c_int)]),
     'fb_team_lanes': (ct.c_int, [_H]),
@@ -430,6 +432,16 @@ class BatchedPhysics:
     def fast_path(self):
         """0 = team kernel only, else environments per block of the per-thread kernel."""
         return int(self.lib.fb_fast_path(self._handle))
+
+    def set_constraint_path(self, per_thread):
+        """Who finishes environments with an active joint limit / plane contact: ``True``
+        (default) the per-thread constrained kernel, ``False`` the team kernel."""
+        self._check(self.lib.fb_set_constraint_path(self._handle, int(bool(per_thread))))
+
+    @property
+    def constraint_path(self):
+        """1 = per-thread constrained kernel, 0 = team kernel."""
+        return int(self.lib.fb_constraint_path(self._handle))
 
     @property
     def fast_smem_bytes_per_env(self):

@@ -249,6 +249,11 @@ int fb_copy_to_device(FbHandle *h, void *dev_ptr, const void *host_ptr, int64_t 
  * fb_last_pending: environments the team kernel had to finish in the last fb_step. */
 int fb_set_fast_path(FbHandle *h, int enable);
 int fb_fast_path(FbHandle *h);
+/* Who finishes the environments the per-thread kernel hands over (a joint limit or a plane
+ * contact became active): 1 (default) = the per-thread constrained kernel (csrc/fb_fastc.h,
+ * matrix-free Newton on the articulated-body recursion), 0 = the team kernel. */
+int fb_set_constraint_path(FbHandle *h, int per_thread);
+int fb_constraint_path(FbHandle *h);
 int fb_fast_smem_bytes_per_env(FbHandle *h);
 int fb_last_pending(FbHandle *h, int *count);
 
