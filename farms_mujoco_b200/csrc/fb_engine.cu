@@ -360,11 +360,17 @@ static int launch(FbHandle *h, int mode, int n_steps, int want_derived) {
   if (use_fast) {
     int fblocks = (P.n_envs + h->fast_block - 1)/h->fast_block;
     h->fastQ->P = P;
-    fb_fast_kernel<32><<<fblocks, 32, h->fast_smem_bytes, h->stream>>>(*h->fastQ);
+    switch (h->fast_block) {
+      case 16: fb_fast_kernel<16><<<fblocks, 16, h->fast_smem_bytes, h->stream>>>(*h->fastQ); break;
+      default: fb_fast_kernel<32><<<fblocks, 32, h->fast_smem_bytes, h->stream>>>(*h->fastQ); break;
+    }
     h->launches++;
     if (con_thread) {
       h->conQ->P = P;
-      fb_fastc_kernel<32><<<fblocks, 32, h->fast_smem_bytes, h->stream>>>(*h->conQ);
+      switch (h->fast_block) {
+        case 16: fb_fastc_kernel<16><<<fblocks, 16, h->fast_smem_bytes, h->stream>>>(*h->conQ); break;
+        default: fb_fastc_kernel<32><<<fblocks, 32, h->fast_smem_bytes, h->stream>>>(*h->conQ); break;
+      }
     }
   }
   if (!con_thread) switch (h->team) {
@@ -472,21 +478,33 @@ int fb_create(const FbModel *model, const FbFarms *farms, int n_envs, int device
     default: ce = cudaFuncSetAttribute(fb_step_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_bytes); break;
   }
   if (ce != cudaSuccess) { fb_destroy(h); return fail(std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(ce)); }
-  /* environment-per-thread kernel: one warp (32 environments) per block, as many blocks per
-   * SM as their shared-memory working sets allow; models beyond that run on the team kernel */
+  /* environment-per-thread kernels: one warp per block, as many blocks per SM as their
+   * shared-memory working sets allow; models beyond that run on the team kernel.  A warp holds 32
+   * environments.  Exception: a model with many collision candidates on a batch that leaves
+   * schedulers idle anyway runs 16 per warp -- the constrained step visits the UNION of the
+   * candidates its lanes touch and iterates until its slowest lane has converged, so half-filled
+   * warps finish sooner (CENTIPEDE x 8,192: 60.5 -> 42.6 ms per 16 steps; slower everywhere else). */
   {
     size_t per_thread = (size_t)m.X.n_float*sizeof(float);
-    h->fast_block = 32;
-    if (!m.X.ok || per_thread*32 > (size_t)max_smem) h->fast_enabled = 0;
+    int sms = 148;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
+    h->fast_block = (m.ncand > 48 && n_envs/16 <= 4*sms) ? 16 : 32;
+    if (const char *ev = getenv("FARMS_B200_FAST_BLOCK")) {
+      const int v = atoi(ev);
+      if (v == 16 || v == 32) h->fast_block = v;
+    }
+    if (!m.X.ok || per_thread*h->fast_block > (size_t)max_smem) h->fast_enabled = 0;
     if (h->fast_enabled) {
       h->fast_smem_bytes = per_thread*h->fast_block;
-      ce = cudaFuncSetAttribute(fb_fast_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->fast_smem_bytes);
-      if (ce == cudaSuccess)
-        ce = cudaFuncSetAttribute(fb_fast_kernel<32>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-      if (ce == cudaSuccess)
-        ce = cudaFuncSetAttribute(fb_fastc_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->fast_smem_bytes);
-      if (ce == cudaSuccess)
-        ce = cudaFuncSetAttribute(fb_fastc_kernel<32>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+      const int bytes = (int)h->fast_smem_bytes;
+#define FB_SET_SMEM(K_) \
+      if (ce == cudaSuccess) ce = cudaFuncSetAttribute(K_, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes); \
+      if (ce == cudaSuccess) ce = cudaFuncSetAttribute(K_, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+      switch (h->fast_block) {
+        case 16: FB_SET_SMEM(fb_fast_kernel<16>) FB_SET_SMEM(fb_fastc_kernel<16>) break;
+        default: FB_SET_SMEM(fb_fast_kernel<32>) FB_SET_SMEM(fb_fastc_kernel<32>) break;
+      }
+#undef FB_SET_SMEM
       if (ce != cudaSuccess) { fb_destroy(h); return fail(std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(ce)); }
     }
   }

@@ -50,9 +50,9 @@ FB_DEV void fb_st4(float *p, float a, float b, float c, float d) {
 FB_DEV void fb_st2(float *p, float a, float b) { __stcs(reinterpret_cast<float2 *>(p), make_float2(a, b)); }
 #endif
 
-/* word w (0..3) of a four-word mask held in registers */
-FB_DEV unsigned fb_sel4(const unsigned *m4, int w) {
-  return w == 0 ? m4[0] : (w == 1 ? m4[1] : (w == 2 ? m4[2] : m4[3]));
+/* bit i (0..127) of a two-word mask held in registers */
+FB_DEV int fb_bit128(const unsigned long long *m2, int i) {
+  return (int)(((i < 64 ? m2[0] : m2[1]) >> (i & 63)) & 1ull);
 }
 
 /* articulated inertia about a point, world axes:  [ A  H ] [w]   A, M symmetric
@@ -205,7 +205,7 @@ template <int BLK> struct FbFast {
    * candidate records, and the masks of the candidates that touch in this lane / in any lane */
   float *cs, *csc;
   const CandRec *crec;
-  unsigned hm[4], hany[4];
+  unsigned long long hm[2], hany[2];
 
   FB_MEM FbFast(const FbParams &P_, const FastRec *rec_, float *s_, float *gs_, int env_)
       : P(P_), m(P_.m), rec(rec_), s(s_), env(env_), gs(gs_), cs(0), csc(0), crec(0) {
@@ -585,9 +585,9 @@ FB_UNROLL
       if (MODE == 2) {
         /* contact forces of this body's candidates: world force at the contact point */
         for (int fc = rc.bc0; fc < rc.bc1; fc++) {
-          if (!((fb_sel4(hany, fc >> 5) >> (fc & 31)) & 1u)) continue;
+          if (!fb_bit128(hany, fc)) continue;
           const float *pc_ = ncand(fc);
-          const int on = (fb_sel4(hm, fc >> 5) >> (fc & 31)) & 1u;
+          const int on = fb_bit128(hm, fc);
           float Fw[3], rr[3], cr[3];
 FB_UNROLL
           for (int k = 0; k < 3; k++) {

@@ -12,17 +12,20 @@
  * and a joint's armature gains D.  H is therefore the joint-space inertia of a tree
  * with augmented bodies, and  H p = -g  is solved WITHOUT forming any matrix by the
  * articulated-body recursion the unconstrained kernel already runs (fb_fast.h):
- * three O(nbody) sweeps per Newton iteration,
- *     A  leaves -> root   articulated inertias with the K_c, bias = -contact wrenches,
- *                         joint torques = -(M (a - a0)) + limit forces
- *     B  root -> leaves   p, J p per row
- *     C  leaves -> root   M p  (composite force of the rigid bodies)
+ * two O(nbody) sweeps per Newton iteration,
+ *     A  leaves -> root   the gradient g (see below), articulated inertias with the K_c,
+ *                         joint torques = -g
+ *     B  root -> leaves   p, J p per row, p . g
  * followed by MuJoCo's exact line search on the piecewise-quadratic cost along p
- * (a safeguarded 1-D Newton iteration over the rows).  M (a - a0) and J a - aref
- * are carried from iteration to iteration (both are linear in a), so neither the
- * mass matrix, nor J, nor a factorisation ever exists: the working set is a few
- * floats per body and per collision candidate, laid out [field][lane] in an
- * L2-resident scratch like the rest of the per-thread state.
+ * (a safeguarded 1-D Newton iteration over the rows).  The gradient is never
+ * assembled from M: with H p = -g, a step a <- a + alpha p changes it to
+ *     g' = (1 - alpha) g - J' Delta,   Delta_r = D_r res'_r ([r was active] - [r is active]),
+ * i.e. only the rows that SWITCHED contribute, as contact-point forces summed over
+ * subtrees by a second (plain) carry of sweep A; p'Mp and p'M(a - a0) of the line search
+ * follow from p.g and the row sums at alpha = 0.  J a - aref is carried per row (linear
+ * in a).  Neither the mass matrix, nor J, nor a factorisation ever exists: the working
+ * set is a few floats per body and per collision candidate, laid out [field][lane] in
+ * an L2-resident scratch like the rest of the per-thread state.
  *
  * All environments of a warp walk the same bodies and the same collision
  * CANDIDATES (plane vs sphere / capsule end, fixed by the model; CandRec, in the
@@ -49,8 +52,10 @@
 /* test harness only: Newton iterations, line-search evaluations, solves (tests/emu) */
 static double *fb_emu_stats = 0;
 #define FB_FFS(x) __builtin_ffs((int)(x))
+#define FB_FFSLL(x) __builtin_ffsll((long long)(x))
 #else
 #define FB_FFS(x) __ffs((int)(x))
+#define FB_FFSLL(x) __ffsll((long long)(x))
 #endif
 
 template <int BLK> struct FbFastCon : FbFast<BLK> {
@@ -61,28 +66,30 @@ template <int BLK> struct FbFastCon : FbFast<BLK> {
   using Base::block; using Base::gblock; using Base::slot; using Base::nblock; using Base::nroot;
   using Base::ncand;
   unsigned lany[2];      /* bodies whose joint has an active limit row in some lane */
+  float *csw;            /* plain-wrench accumulation slots of the branching bodies: 6 floats per slot */
+  FB_MEM float *wslot(int i) const { return csw + 6*BLK*i; }
 
   FB_MEM FbFastCon(const FbParams &P_, const FastRec *rec_, const CandRec *crec_, float *s_, float *gs_,
                    float *cs_, int env_)
       : Base(P_, rec_, s_, gs_, env_) {
     cs = cs_; crec = crec_;
     csc = cs_ + (NB_NF*(P_.m.nbody - 1) + NR_NF)*BLK;
-FB_UNROLL
-    for (int w = 0; w < 4; w++) hm[w] = hany[w] = 0u;
+    csw = csc + NC_NF*P_.m.ncand*BLK;
+    hm[0] = hm[1] = hany[0] = hany[1] = 0ull;
     lany[0] = lany[1] = 0u;
   }
 
-  FB_MEM int lane_on(int fc) const { return (fb_sel4(hm, fc >> 5) >> (fc & 31)) & 1u; }
-  FB_MEM int any_on(int fc) const { return (fb_sel4(hany, fc >> 5) >> (fc & 31)) & 1u; }
+  FB_MEM int lane_on(int fc) const { return fb_bit128(hm, fc); }
+  FB_MEM int any_on(int fc) const { return fb_bit128(hany, fc); }
   FB_MEM int lim_on(int b) const { return ((b < 32 ? lany[0] : lany[1]) >> (b & 31)) & 1u; }
 
   /* walk over the set bits of hany in ascending order */
-  struct CandIter { int w; unsigned mw; };
+  struct CandIter { int w; unsigned long long mw; };
   FB_MEM CandIter cand_begin() const { CandIter it = {0, hany[0]}; return it; }
   FB_MEM int cand_next(CandIter &it) const {
-    while (!it.mw && it.w < 3) { it.w++; it.mw = fb_sel4(hany, it.w); }
+    if (!it.mw && it.w == 0) { it.w = 1; it.mw = hany[1]; }
     if (!it.mw) return -1;
-    const int fc = 32*it.w + FB_FFS(it.mw) - 1;
+    const int fc = 64*it.w + FB_FFSLL(it.mw) - 1;
     it.mw &= it.mw - 1;
     return fc;
   }
@@ -152,10 +159,10 @@ FB_UNROLL
     }
     const float impratio = fmaxf(FB_MINVAL, m.impratio);
 FB_UNROLL
-    for (int w = 0; w < 4; w++) {
-      unsigned mine_w = 0u, any_w = 0u;
-      const int c1 = m.ncand < 32*w + 32 ? m.ncand : 32*w + 32;
-      for (int fc = 32*w; fc < c1; fc++) {
+    for (int w = 0; w < 2; w++) {
+      unsigned long long mine_w = 0ull, any_w = 0ull;
+      const int c1 = m.ncand < 64*w + 64 ? m.ncand : 64*w + 64;
+      for (int fc = 64*w; fc < c1; fc++) {
         const CandRec &cr_ = crec[fc];
         const float *pb = s + cr_.pblk*BLK;
         const Quat q = {pb[(FB_QUAT)*BLK], pb[(FB_QUAT + 1)*BLK], pb[(FB_QUAT + 2)*BLK], pb[(FB_QUAT + 3)*BLK]};
@@ -170,8 +177,8 @@ FB_UNROLL
                            + (n[0]*(o[0] + t[0]) + n[1]*(o[1] + t[1]) + n[2]*(o[2] + t[2])) - radius;
         const int hit = dist < includemargin;
         if (!FB_ANY(hit)) continue;
-        any_w |= 1u << (fc & 31);
-        if (hit) mine_w |= 1u << (fc & 31);
+        any_w |= 1ull << (fc & 63);
+        if (hit) mine_w |= 1ull << (fc & 63);
         float *pc = ncand(fc);
         float r[3], f[9];
 FB_UNROLL
@@ -322,9 +329,13 @@ FB_UNROLL
           }
           const float ua = U[0]*a[0] + U[1]*a[1] + U[2]*a[2] + U[3]*a[3] + U[4]*a[4] + U[5]*a[5];
           const float qdd = (cx[7] - ua)*cx[6];
-          const int o3 = jtype == FB_JNT_HINGE ? 0 : 3;
+          if (jtype == FB_JNT_HINGE) {
 FB_UNROLL
-          for (int k = 0; k < 3; k++) { a[o3 + k] += ax[k]*qdd; al[o3 + k] += ax[k]*qdd; }
+            for (int k = 0; k < 3; k++) { a[k] += ax[k]*qdd; al[k] += ax[k]*qdd; }
+          } else {
+FB_UNROLL
+            for (int k = 0; k < 3; k++) { a[3 + k] += ax[k]*qdd; al[3 + k] += ax[k]*qdd; }
+          }
           fb_st_scr(pn + NB_A*BLK, qdd);
           fb_st_scr(pn + NB_MD*BLK, 0.f);
         }
@@ -349,30 +360,37 @@ FB_UNROLL
 
   /* ---- Newton sweep A: leaves -> root.  Articulated inertias of the augmented tree, U, u, 1/d
    * per joint; the floating root's p */
-  FB_MEM void newton_a() {
+  FB_MEM void newton_a(float keep) {
     const int nb = m.nbody;
     ArtInertia C;
-    float pc6[6];
+    float pc6[6], wc[6];     /* carries from child b+1: articulated bias, plain wrench of the switched rows */
 FB_UNROLL
-    for (int k = 0; k < 6; k++) { C.A[k] = 0.f; C.M[k] = 0.f; pc6[k] = 0.f; }
+    for (int k = 0; k < 6; k++) { C.A[k] = 0.f; C.M[k] = 0.f; pc6[k] = 0.f; wc[k] = 0.f; }
 FB_UNROLL
     for (int k = 0; k < 9; k++) C.H[k] = 0.f;
-    float nx[2];      /* M(a - a0), a of the next joint to visit */
+    float nx[2];      /* previous gradient entry, a of the next joint to visit */
     nx[0] = fb_ld_scr(nblock(nb - 1) + NB_MD*BLK); nx[1] = fb_ld_scr(nblock(nb - 1) + NB_A*BLK);
     for (int b = nb - 1; b >= 1; b--) {
       const FastRec &rc = rec[b];
+      FB_PIN_I(rc.jtype); FB_PIN_I(rc.flags); FB_PIN_I(rc.pblk); FB_PIN_I(rc.parent); FB_PIN_I(rc.bc0); FB_PIN_I(rc.bc1);
+      FB_PIN_F(rc.mass); FB_PIN_F(rc.armature);
+FB_UNROLL
+      for (int k = 0; k < 3; k++) { FB_PIN_F(rc.hloc[k]); FB_PIN_F(rc.axis[k]); }
+FB_UNROLL
+      for (int k = 0; k < 5; k++) FB_PIN_F(rc.Ib[k]);
       const float *pb = block(b);
       float *pn = nblock(b);
       const int jtype = rc.jtype, flags = rc.flags;
       const float md = nx[0], aj = nx[1];
       if (b > 1) { nx[0] = fb_ld_scr(pn - NB_NF*BLK + NB_MD*BLK); nx[1] = fb_ld_scr(pn - NB_NF*BLK + NB_A*BLK); }
-      float lim4[4] = {0.f, 0.f, 0.f, 0.f};
+      float lim4[4] = {0.f, 0.f, 0.f, 0.f}, dtau = 0.f;
       const int limited = (flags & FT_LIMITED) && lim_on(b);
       if (limited) {
 FB_UNROLL
         for (int k = 0; k < 4; k++) lim4[k] = fb_ld_scr(pn + (NB_DLO + k)*BLK);
+        dtau = fb_ld_scr(pn + NB_MP*BLK);
       }
-      float R[9], h[3], Iw[6], pA[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+      float R[9], h[3], Iw[6], pA[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f}, W[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
       body_frame(rc, pb, R, h, Iw);
       const float mass = rc.mass;
       ArtInertia I;
@@ -384,12 +402,15 @@ FB_UNROLL
       I.H[3] = mass*h[2]; I.H[4] = 0.f; I.H[5] = -mass*h[0];
       I.H[6] = -mass*h[1]; I.H[7] = mass*h[0]; I.H[8] = 0.f;
       I.M[0] = mass; I.M[1] = mass; I.M[2] = mass; I.M[3] = 0.f; I.M[4] = 0.f; I.M[5] = 0.f;
-      /* active contact rows of this body: K_c and the contact force */
+      /* active contact rows of this body: K_c; switched rows: their force */
       for (int fc = rc.bc0; fc < rc.bc1; fc++) {
         if (!any_on(fc)) continue;
         const CandRec &cr_ = crec[fc];
         const float *pc = ncand(fc);
-        const float D = lane_on(fc) ? fb_ld_scr(pc + NC_D*BLK) : 0.f;
+        const int on = lane_on(fc);
+        const float D = on ? fb_ld_scr(pc + NC_D*BLK) : 0.f;
+        const float dn = on ? fb_ld_scr(pc + NC_JP*BLK) : 0.f, d1 = on ? fb_ld_scr(pc + (NC_JP + 1)*BLK) : 0.f,
+                    d2 = on ? fb_ld_scr(pc + (NC_JP + 2)*BLK) : 0.f;
         const float rn = fb_ld_scr(pc + NC_RES*BLK), r1 = fb_ld_scr(pc + (NC_RES + 1)*BLK), r2 = fb_ld_scr(pc + (NC_RES + 2)*BLK);
         float n[3] = {cr_.pn[0], cr_.pn[1], cr_.pn[2]}, t1[3], t2[3], r[3];
 FB_UNROLL
@@ -410,28 +431,38 @@ FB_UNROLL
           const float e0 = n[0] + sg*mu*(row < 2 ? t1[0] : t2[0]);
           const float e1 = n[1] + sg*mu*(row < 2 ? t1[1] : t2[1]);
           const float e2 = n[2] + sg*mu*(row < 2 ? t1[2] : t2[2]);
-          const float f = -w*res;
           const float w0 = w*e0, w1 = w*e1, w2 = w*e2;
           Kc.M[0] += w0*e0; Kc.M[1] += w1*e1; Kc.M[2] += w2*e2;
           Kc.M[3] += w0*e1; Kc.M[4] += w0*e2; Kc.M[5] += w1*e2;
-          p6[3] -= f*e0; p6[4] -= f*e1; p6[5] -= f*e2;
         }
         art_shift(Kc, p6, r);
 FB_UNROLL
-        for (int k = 0; k < 6; k++) { I.A[k] += Kc.A[k]; I.M[k] += Kc.M[k]; pA[k] += p6[k]; }
+        for (int k = 0; k < 6; k++) { I.A[k] += Kc.A[k]; I.M[k] += Kc.M[k]; }
 FB_UNROLL
         for (int k = 0; k < 9; k++) I.H[k] += Kc.H[k];
+        {
+          const float Fd[3] = {dn*n[0] + d1*t1[0] + d2*t2[0], dn*n[1] + d1*t1[1] + d2*t2[1],
+                               dn*n[2] + d1*t1[2] + d2*t2[2]};
+          float cr[3];
+          v_cross(r, Fd, cr);
+FB_UNROLL
+          for (int k = 0; k < 3; k++) { W[k] += cr[k]; W[3 + k] += Fd[k]; }
+        }
       }
       if (flags & FT_ADD_CARRY) {
 FB_UNROLL
-        for (int k = 0; k < 6; k++) { I.A[k] += C.A[k]; I.M[k] += C.M[k]; pA[k] += pc6[k]; }
+        for (int k = 0; k < 6; k++) { I.A[k] += C.A[k]; I.M[k] += C.M[k]; pA[k] += pc6[k]; W[k] += wc[k]; }
 FB_UNROLL
         for (int k = 0; k < 9; k++) I.H[k] += C.H[k];
       }
       if (flags & FT_HAS_SLOT) {
         const float *so = slot(rc.slot);
+        const float *sw = wslot(rc.slot);
 FB_UNROLL
-        for (int k = 0; k < 6; k++) { I.A[k] += so[k*BLK]; I.M[k] += so[(15 + k)*BLK]; pA[k] += so[(21 + k)*BLK]; }
+        for (int k = 0; k < 6; k++) {
+          I.A[k] += so[k*BLK]; I.M[k] += so[(15 + k)*BLK]; pA[k] += so[(21 + k)*BLK];
+          W[k] += fb_ld_scr(sw + k*BLK);
+        }
 FB_UNROLL
         for (int k = 0; k < 9; k++) I.H[k] += so[(6 + k)*BLK];
       }
@@ -447,7 +478,11 @@ FB_UNROLL
 FB_UNROLL
           for (int j = 0; j < 3; j++) K[3 + j][i] = I.H[3*i + j];
 FB_UNROLL
-        for (int k = 0; k < 6; k++) rhs[k] = -pA[k] - fb_ld_scr(pr + (NR_MD + k)*BLK);
+        for (int k = 0; k < 6; k++) {
+          const float g = keep*fb_ld_scr(pr + (NR_MD + k)*BLK) - W[k];
+          fb_st_scr(pr + (NR_MD + k)*BLK, g);
+          rhs[k] = -pA[k] - g;
+        }
         solve6(K, rhs, x);
 FB_UNROLL
         for (int k = 0; k < 6; k++) fb_st_scr(pr + (NR_P + k)*BLK, x[k]);
@@ -456,12 +491,16 @@ FB_UNROLL
       if (jtype >= 0) {
         float ax[3], U[6], d, u;
         m_rot(R, rc.axis[0], rc.axis[1], rc.axis[2], ax);
-        float tau = -md;
+        /* gradient entry of this joint: what is left of the previous one, minus the switched rows */
+        const float g = keep*md - dtau - (jtype == FB_JNT_HINGE ? ax[0]*W[0] + ax[1]*W[1] + ax[2]*W[2]
+                                                                 : ax[0]*W[3] + ax[1]*W[4] + ax[2]*W[5]);
+        fb_st_scr(pn + NB_MD*BLK, g);
+        const float tau = -g;
         float dl = 0.f;
         if (limited) {
           const float rlo = aj - lim4[2], rhi = -aj - lim4[3];
-          if (lim4[0] > 0.f && rlo < 0.f) { dl += lim4[0]; tau -= lim4[0]*rlo; }
-          if (lim4[1] > 0.f && rhi < 0.f) { dl += lim4[1]; tau += lim4[1]*rhi; }
+          if (lim4[0] > 0.f && rlo < 0.f) dl += lim4[0];
+          if (lim4[1] > 0.f && rhi < 0.f) dl += lim4[1];
         }
         if (jtype == FB_JNT_HINGE) {
           sym_mul(I.A, ax, U);
@@ -496,21 +535,31 @@ FB_UNROLL
 FB_UNROLL
         for (int k = 0; k < 3; k++) r[k] = pb[(FB_ORG + k)*BLK] - pp[(FB_ORG + k)*BLK];
         art_shift(I, pA, r);
+        float cr[3];
+        v_cross(r, W + 3, cr);
+        W[0] += cr[0]; W[1] += cr[1]; W[2] += cr[2];
       }
       if (flags & FT_TO_CARRY) {
         C = I;
 FB_UNROLL
-        for (int k = 0; k < 6; k++) pc6[k] = pA[k];
+        for (int k = 0; k < 6; k++) { pc6[k] = pA[k]; wc[k] = W[k]; }
       } else {
         float *so = slot(rc.pslot);
+        float *sw = wslot(rc.pslot);
         if (flags & FT_FIRST_WRITER) {
 FB_UNROLL
-          for (int k = 0; k < 6; k++) { so[k*BLK] = I.A[k]; so[(15 + k)*BLK] = I.M[k]; so[(21 + k)*BLK] = pA[k]; }
+          for (int k = 0; k < 6; k++) {
+            so[k*BLK] = I.A[k]; so[(15 + k)*BLK] = I.M[k]; so[(21 + k)*BLK] = pA[k];
+            fb_st_scr(sw + k*BLK, W[k]);
+          }
 FB_UNROLL
           for (int k = 0; k < 9; k++) so[(6 + k)*BLK] = I.H[k];
         } else {
 FB_UNROLL
-          for (int k = 0; k < 6; k++) { so[k*BLK] += I.A[k]; so[(15 + k)*BLK] += I.M[k]; so[(21 + k)*BLK] += pA[k]; }
+          for (int k = 0; k < 6; k++) {
+            so[k*BLK] += I.A[k]; so[(15 + k)*BLK] += I.M[k]; so[(21 + k)*BLK] += pA[k];
+            fb_st_scr(sw + k*BLK, fb_ld_scr(sw + k*BLK) + W[k]);
+          }
 FB_UNROLL
           for (int k = 0; k < 9; k++) so[(6 + k)*BLK] += I.H[k];
         }
@@ -519,12 +568,12 @@ FB_UNROLL
   }
 
   /* ---- Newton sweep B: root -> leaves.  p per joint, the bodies' pure accelerations, J p per
-   * candidate row; g0 = p . M(a - a0), pp = |p|^2 */
-  FB_MEM void newton_b(float *g0_out, float *pp_out) {
+   * candidate row; g0 = p . g, pp = |p|^2 */
+  FB_MEM void newton_b(float *g0_out, float *pp_out, int store_ap) {
     const int nb = m.nbody;
     float lc[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
     float g0 = 0.f, pp = 0.f;
-    float nx[9];      /* U[6], 1/d, u, M(a - a0) of the next body to visit */
+    float nx[9];      /* U[6], 1/d, u, gradient entry of the next body to visit */
     {
       const float *pn = nblock(1);
 FB_UNROLL
@@ -533,6 +582,9 @@ FB_UNROLL
     }
     for (int b = 1; b < nb; b++) {
       const FastRec &rc = rec[b];
+      FB_PIN_I(rc.jtype); FB_PIN_I(rc.flags); FB_PIN_I(rc.pblk); FB_PIN_I(rc.parent); FB_PIN_I(rc.bc0); FB_PIN_I(rc.bc1);
+FB_UNROLL
+      for (int k = 0; k < 3; k++) FB_PIN_F(rc.axis[k]);
       const float *pb = block(b);
       float *pn = nblock(b);
       const int jtype = rc.jtype, flags = rc.flags;
@@ -580,16 +632,19 @@ FB_UNROLL
           const float *U = cx;
           const float ua = U[0]*al[0] + U[1]*al[1] + U[2]*al[2] + U[3]*al[3] + U[4]*al[4] + U[5]*al[5];
           const float pj = (cx[7] - ua)*cx[6];
-          const int o3 = jtype == FB_JNT_HINGE ? 0 : 3;
-FB_UNROLL
-          for (int k = 0; k < 3; k++) al[o3 + k] += ax[k]*pj;
+          if (jtype == FB_JNT_HINGE) { al[0] += ax[0]*pj; al[1] += ax[1]*pj; al[2] += ax[2]*pj; }
+          else { al[3] += ax[0]*pj; al[4] += ax[1]*pj; al[5] += ax[2]*pj; }
           fb_st_scr(pn + NB_P*BLK, pj);
           g0 += pj*cx[8];
           pp += pj*pj;
         }
       }
 FB_UNROLL
-      for (int k = 0; k < 6; k++) { lc[k] = al[k]; fb_st_scr(pn + (NB_AP + k)*BLK, al[k]); }
+      for (int k = 0; k < 6; k++) lc[k] = al[k];
+      if (store_ap) {
+FB_UNROLL
+        for (int k = 0; k < 6; k++) fb_st_scr(pn + (NB_AP + k)*BLK, al[k]);
+      }
       if (flags & FT_HAS_SLOT) {
         float *so = slot(rc.slot);
 FB_UNROLL
@@ -607,7 +662,10 @@ FB_UNROLL
     *g0_out = g0; *pp_out = pp;
   }
 
-  /* ---- Newton sweep C: leaves -> root.  M p from the rigid bodies' forces; returns p' M p */
+  /* ---- sweep C (first Newton iteration only): leaves -> root, M p from the rigid bodies'
+   * forces, written where the next sweep A expects the previous gradient; returns p'Mp.  The
+   * first step is the large one (|p| ~ 60 |a|): taking M(a1 - a0) = alpha M p from the bodies
+   * instead of from H p = -g makes the second iteration refine its rounding error. */
   FB_MEM float newton_c() {
     const int nb = m.nbody;
     float fc6[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
@@ -621,6 +679,12 @@ FB_UNROLL
     }
     for (int b = nb - 1; b >= 1; b--) {
       const FastRec &rc = rec[b];
+      FB_PIN_I(rc.jtype); FB_PIN_I(rc.flags); FB_PIN_I(rc.pblk); FB_PIN_I(rc.parent);
+      FB_PIN_F(rc.mass); FB_PIN_F(rc.armature);
+FB_UNROLL
+      for (int k = 0; k < 3; k++) { FB_PIN_F(rc.hloc[k]); FB_PIN_F(rc.axis[k]); }
+FB_UNROLL
+      for (int k = 0; k < 5; k++) FB_PIN_F(rc.Ib[k]);
       const float *pb = block(b);
       float *pn = nblock(b);
       const int jtype = rc.jtype, flags = rc.flags;
@@ -660,7 +724,7 @@ FB_UNROLL
         float *pr = nroot();
 FB_UNROLL
         for (int k = 0; k < 6; k++) {
-          fb_st_scr(pr + (NR_MP + k)*BLK, F[k]);
+          fb_st_scr(pr + (NR_MD + k)*BLK, F[k]);
           pMp += F[k]*fb_ld_scr(pr + (NR_P + k)*BLK);
         }
         continue;
@@ -668,9 +732,9 @@ FB_UNROLL
       if (jtype >= 0) {
         float ax[3];
         m_rot(R, rc.axis[0], rc.axis[1], rc.axis[2], ax);
-        const int o3 = jtype == FB_JNT_HINGE ? 0 : 3;
-        const float mp = ax[0]*F[o3] + ax[1]*F[o3 + 1] + ax[2]*F[o3 + 2] + rc.armature*pj;
-        fb_st_scr(pn + NB_MP*BLK, mp);
+        const float mp = (jtype == FB_JNT_HINGE ? ax[0]*F[0] + ax[1]*F[1] + ax[2]*F[2]
+                                                : ax[0]*F[3] + ax[1]*F[4] + ax[2]*F[5]) + rc.armature*pj;
+        fb_st_scr(pn + NB_MD*BLK, mp);
         pMp += pj*mp;
       }
       if (rc.parent == 0) continue;
@@ -701,8 +765,9 @@ FB_UNROLL
 
   /* derivative of the cost along p at step a, and its slope there, over the rows some lane
    * holds active.  The loads of a row block are issued one visit ahead. */
-  FB_MEM void line_eval(float a, float g0, float pMp, float *gv_out, float *sl_out) const {
+  FB_MEM void line_eval(float a, float g0, float pMp, float *gv_out, float *sl_out, unsigned *hash_out) const {
     float gv = g0 + a*pMp, sl = pMp;
+    unsigned hash = 0u;       /* of the set of active rows at a */
 FB_UNROLL
     for (int w = 0; w < 2; w++) {
       for (unsigned mw = lany[w]; mw; mw &= mw - 1) {
@@ -712,8 +777,10 @@ FB_UNROLL
         const float arlo = fb_ld_scr(pn + NB_ARLO*BLK), arhi = fb_ld_scr(pn + NB_ARHI*BLK);
         const float aj = fb_ld_scr(pn + NB_A*BLK), pj = fb_ld_scr(pn + NB_P*BLK);
         const float xl = (aj - arlo) + a*pj, xh = (-aj - arhi) - a*pj;
-        if (dlo > 0.f && xl < 0.f) { gv += dlo*pj*xl; sl += dlo*pj*pj; }
-        if (dhi > 0.f && xh < 0.f) { gv -= dhi*pj*xh; sl += dhi*pj*pj; }
+        const int al_ = dlo > 0.f && xl < 0.f, ah_ = dhi > 0.f && xh < 0.f;
+        if (al_) { gv += dlo*pj*xl; sl += dlo*pj*pj; }
+        if (ah_) { gv -= dhi*pj*xh; sl += dhi*pj*pj; }
+        hash = (hash + (unsigned)(al_ + 2*ah_))*0x9E3779B1u;
       }
     }
     CandIter it = cand_begin();
@@ -738,44 +805,77 @@ FB_UNROLL
         const float sg = (row & 1) ? -1.f : 1.f;
         const float res = rn + sg*(row < 2 ? r1 : r2), jp = jn + sg*(row < 2 ? j1 : j2);
         const float x = res + a*jp;
-        if (D > 0.f && x < 0.f) { gv += D*jp*x; sl += D*jp*jp; }
+        const int act = D > 0.f && x < 0.f;
+        if (act) { gv += D*jp*x; sl += D*jp*jp; }
+        hash = (hash + (unsigned)act)*0x9E3779B1u;
       }
     }
-    *gv_out = gv; *sl_out = sl;
+    *gv_out = gv; *sl_out = sl; *hash_out = hash;
   }
 
-  /* a <- a + alpha p for everything that is carried; returns |a|^2 */
-  FB_MEM float newton_update(float alpha) {
+  /* a <- a + alpha p for everything that is carried, and the forces of the rows that switched,
+   * Delta = D res' ([was active] - [is active]), for the next sweep A.  mode 1: before the first
+   * iteration -- nothing moves, nothing was active (Delta = the constraint forces at a0).  mode 2:
+   * after the first iteration -- the next gradient starts from M(a1 - a0) (sweep C), so Delta is
+   * the whole constraint force at a1.  Returns |a|^2. */
+  FB_MEM float newton_update(float alpha, int mode) {
     const int nb = m.nbody;
+    const int first = mode == 1, fresh = mode != 0;
     float a2 = 0.f;
     for (int b = 1; b < nb; b++) {
       const FastRec &rc = rec[b];
       float *pn = nblock(b);
       if (rc.jtype == FB_JNT_FREE) {
+        if (first) continue;
         float *pr = nroot();
 FB_UNROLL
         for (int k = 0; k < 6; k++) {
           const float an = fb_ld_scr(pr + (NR_A + k)*BLK) + alpha*fb_ld_scr(pr + (NR_P + k)*BLK);
           fb_st_scr(pr + (NR_A + k)*BLK, an);
-          fb_st_scr(pr + (NR_MD + k)*BLK, fb_ld_scr(pr + (NR_MD + k)*BLK) + alpha*fb_ld_scr(pr + (NR_MP + k)*BLK));
           a2 += an*an;
         }
       } else if (rc.jtype >= 0) {
-        const float an = fb_ld_scr(pn + NB_A*BLK) + alpha*fb_ld_scr(pn + NB_P*BLK);
-        const float mdn = fb_ld_scr(pn + NB_MD*BLK) + alpha*fb_ld_scr(pn + NB_MP*BLK);
-        fb_st_scr(pn + NB_A*BLK, an);
-        fb_st_scr(pn + NB_MD*BLK, mdn);
+        const float ao = fb_ld_scr(pn + NB_A*BLK);
+        const float an = first ? ao : ao + alpha*fb_ld_scr(pn + NB_P*BLK);
+        if (!first) fb_st_scr(pn + NB_A*BLK, an);
         a2 += an*an;
+        if ((rc.flags & FT_LIMITED) && lim_on(b)) {
+          const float dlo = fb_ld_scr(pn + NB_DLO*BLK), dhi = fb_ld_scr(pn + NB_DHI*BLK);
+          const float arlo = fb_ld_scr(pn + NB_ARLO*BLK), arhi = fb_ld_scr(pn + NB_ARHI*BLK);
+          const float rlo = an - arlo, rhi = -an - arhi;
+          const int wl = !fresh && dlo > 0.f && ao - arlo < 0.f, il = dlo > 0.f && rlo < 0.f;
+          const int wh = !fresh && dhi > 0.f && -ao - arhi < 0.f, ih = dhi > 0.f && rhi < 0.f;
+          /* row Jacobians +1 / -1 */
+          fb_st_scr(pn + NB_MP*BLK, dlo*rlo*(float)(wl - il) - dhi*rhi*(float)(wh - ih));
+        }
       }
     }
     CandIter it = cand_begin();
     for (int fc = cand_next(it); fc >= 0; fc = cand_next(it)) {
       float *pc = ncand(fc);
-      float v[6];
+      const float mu = crec[fc].mu;
+      float v[7];
 FB_UNROLL
-      for (int k = 0; k < 6; k++) v[k] = fb_ld_scr(pc + (NC_RES + k)*BLK);
+      for (int k = 0; k < 7; k++) v[k] = fb_ld_scr(pc + (NC_D + k)*BLK);     /* D, res[3], jp[3] */
+      const float D = lane_on(fc) ? v[0] : 0.f;
+      float rn[3];
 FB_UNROLL
-      for (int k = 0; k < 3; k++) fb_st_scr(pc + (NC_RES + k)*BLK, v[k] + alpha*v[3 + k]);
+      for (int k = 0; k < 3; k++) rn[k] = first ? v[1 + k] : v[1 + k] + alpha*v[4 + k];
+      float d4[4];
+FB_UNROLL
+      for (int row = 0; row < 4; row++) {
+        const float sg = (row & 1) ? -1.f : 1.f;
+        const float ro = v[1] + sg*(row < 2 ? v[2] : v[3]), rw = rn[0] + sg*(row < 2 ? rn[1] : rn[2]);
+        const int was = !fresh && D > 0.f && ro < 0.f, is = D > 0.f && rw < 0.f;
+        d4[row] = D*rw*(float)(was - is);
+      }
+      if (!first) {
+FB_UNROLL
+        for (int k = 0; k < 3; k++) fb_st_scr(pc + (NC_RES + k)*BLK, rn[k]);
+      }
+      fb_st_scr(pc + NC_JP*BLK, d4[0] + d4[1] + d4[2] + d4[3]);
+      fb_st_scr(pc + (NC_JP + 1)*BLK, mu*(d4[0] - d4[1]));
+      fb_st_scr(pc + (NC_JP + 2)*BLK, mu*(d4[2] - d4[3]));
     }
     return a2;
   }
@@ -785,23 +885,34 @@ FB_UNROLL
     int done = !mine;
     const int maxit = m.solver_iterations < 50 ? m.solver_iterations : 50;
     int it = 0;
-    float prev_ratio = 3.0e38f;
+    float prev_ratio = 3.0e38f, keep = 1.f;
+    newton_update(0.f, 1);                       /* Delta = the constraint forces at a0: g = -J' f(a0) */
     for (; it < maxit && FB_ANY(!done); it++) {
-      float g0, pp, gv, sl;
-      newton_a();
-      newton_b(&g0, &pp);
-      const float pMp = newton_c();
-      /* exact line search: zero of the piecewise-linear derivative, safeguarded Newton */
-      float a = 0.f, lo = 0.f, hi = 3.0e38f, gv0 = 0.f;
-      int ls_done = done || !(pMp > 0.f), nls = 0;
-      for (int ls = 0; ls < 16 && FB_ANY(!ls_done); ls++) {
+      float pg, pp, gv, sl;
+      unsigned hash = 0u, hash0 = 0u;
+      newton_a(keep);
+      newton_b(&pg, &pp, it == 0);
+      /* Line search on phi'(a) = p'M(a - a0) + a p'Mp + sum_active(a) D jp (res + a jp).  With
+       * H p = -g:  p'M(a - a0) = p.g - S0,  p'Mp = -p.g - Q0,  S0 / Q0 = the row sums at a = 0.
+       * First iteration: a = a0 and p'Mp comes from sweep C. */
+      line_eval(0.f, 0.f, 0.f, &gv, &sl, &hash0);
+      float g0 = pg - gv, pMp = fmaxf(-pg - sl, 1e-7f*fabsf(pg));
+      if (it == 0) { g0 = 0.f; pMp = newton_c(); }
+      /* zero of the piecewise-linear derivative by safeguarded Newton steps; phi'(0) = p.g,
+       * phi''(0) = -p.g, so the first step is the full Newton step */
+      int ls_done = done || !(pg < 0.f), nls = 1, exact = 0;
+      float a = ls_done ? 0.f : 1.f, lo = 0.f, hi = 3.0e38f;
+      for (int ls = 1; ls < 16 && FB_ANY(!ls_done); ls++) {
         nls++;
-        line_eval(a, g0, pMp, &gv, &sl);
+        line_eval(a, g0, pMp, &gv, &sl, &hash);
         if (ls_done) continue;
-        if (ls == 0) {
-          if (!(gv < 0.f)) { ls_done = 1; continue; }              /* not a descent direction: rounding */
-          gv0 = gv;
-        } else if (fabsf(gv) <= 1e-5f*fabsf(gv0)) { ls_done = 1; continue; }
+        if (fabsf(gv) <= 1e-5f*fabsf(pg)) {
+          /* The derivative vanishes at a with the rows that were active at 0: H was built from
+           * the final active set, the Newton step is the exact minimiser, nothing is left to do. */
+          exact = hash == hash0;
+          ls_done = 1;
+          continue;
+        }
         if (gv < 0.f) lo = a; else hi = a;
         float an = a - gv/sl;
         if (!(an > lo) || !(an < hi)) {
@@ -814,7 +925,8 @@ FB_UNROLL
         a = an;
       }
       if (done) a = 0.f;
-      const float a2 = newton_update(a);
+      const float a2 = newton_update(a, it == 0 ? 2 : 0);
+      keep = it == 0 ? a : 1.f - a;
       /* Stop on a relative step below 3e-5 (|alpha p|^2 <= 1e-9 |a|^2).  Convergence is quadratic
        * once the active set is right -- measured relative steps 6e1, 4e-1, 1e-2, then the fp32
        * floor of 1e-6 .. 4e-6 -- so the step after a 1e-2 one is already rounding noise; MuJoCo's
@@ -822,7 +934,9 @@ FB_UNROLL
        * when the step has stopped shrinking below 1e-3: that is the floor of a worse-conditioned
        * model. */
       const float ratio = a*a*pp, lim = 1e-9f*a2 + 1e-30f;
-      if (!done && (ratio <= lim || (it > 0 && ratio <= 1e-6f*a2 && ratio >= 0.25f*prev_ratio))) done = 1;
+      if (!done && (exact || ratio <= lim || (it > 0 && ratio <= 1e-6f*a2 && ratio >= 0.25f*prev_ratio))) done = 1;
+      /* a diverged environment (non-finite state) must not hold its warp in the loop */
+      if (!(a2 < 3.0e38f) || !(ratio < 3.0e38f)) done = 1;
       prev_ratio = ratio;
 #ifdef FB_HOST_EMU
       if (fb_emu_stats) { fb_emu_stats[0] += 1; fb_emu_stats[1] += nls; }

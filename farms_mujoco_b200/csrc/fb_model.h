@@ -760,7 +760,7 @@ inline bool fb_build_model(const FbModel *fm, const FbFarms *ff, const FbWaveCon
       o.ft_sstart = put_i(I, sstart);
       o.ft_scand = put_i(I, scand);
       o.ft_ssign = put_f(F, ssign);
-      X.n_con = NB_NF*(nb - 1) + NR_NF + NC_NF*nc;
+      X.n_con = NB_NF*(nb - 1) + NR_NF + NC_NF*nc + 6*nslot;
     }
     X.body0 = 0;
     X.slots = FB_NF*(nb - 1);

@@ -37,7 +37,7 @@ def _run(cuda_library, name, n_envs, n_steps, team=0, seed=0, path='team', **kw)
     physics.reset(qpos0, qvel0)
     physics.set_ctrl(ctrl)
     if path != 'team':
-        assert physics.fast_path in (32, 64) and physics.constraint_path == (path == 'fast')
+        assert physics.fast_path in (16, 32) and physics.constraint_path == (path == 'fast')
         physics.step(n_steps)
         # swimming models stay unconstrained here; ground models are handed over at step 0
         assert physics.last_pending == (0 if name in SWIMMING else n_envs)
@@ -100,6 +100,27 @@ def test_hand_over_mid_launch(cuda_library, name, per_thread):
 def test_constraint_paths_agree(cuda_library, name):
     import fastpath_cases
     fastpath_cases.check_constraint_paths_agree(cuda_library, name, n_envs=70, tol=5e-4)
+
+
+@pytest.mark.parametrize('name', ['salamander_swim', 'salamander'])
+def test_block_sizes_agree(cuda_library, name, monkeypatch):
+    """16 or 32 environments per warp (fb_create picks 16 for candidate-rich models on small
+    batches) run the same per-thread arithmetic: bit-identical results."""
+    from farms_mujoco_b200.engine import BatchedPhysics
+    spec, model, qpos0, qvel0, ctrl = make_case(name, 75)
+    outs = []
+    for blk in (16, 32):
+        monkeypatch.setenv('FARMS_B200_FAST_BLOCK', str(blk))
+        physics = BatchedPhysics.from_spec(spec, 75, buffer_size=7, library=cuda_library)
+        assert physics.fast_path == blk
+        physics.reset(qpos0, qvel0)
+        physics.set_ctrl(ctrl)
+        physics.step(6)
+        outs.append((physics.qpos, physics.qvel, physics.log_arrays()))
+    for other in outs[1:]:
+        assert np.array_equal(outs[0][0], other[0]) and np.array_equal(outs[0][1], other[1])
+        for kind in ('links', 'joints', 'contacts', 'xfrc'):
+            assert np.array_equal(outs[0][2][kind], other[2][kind]), kind
 
 
 def test_constrained_launch_split_is_invariant(cuda_library):
