@@ -763,11 +763,13 @@ FB_UNROLL
     return pMp;
   }
 
-  /* derivative of the cost along p at step a, and its slope there, over the rows some lane
-   * holds active.  The loads of a row block are issued one visit ahead. */
-  FB_MEM void line_eval(float a, float g0, float pMp, float *gv_out, float *sl_out, unsigned *hash_out) const {
-    float gv = g0 + a*pMp, sl = pMp;
-    unsigned hash = 0u;       /* of the set of active rows at a */
+  /* Row sums of the line search at N step lengths a[i] in one pass over the rows some lane holds
+   * active: S = sum_active D jp (res + a jp), Q = sum_active D jp^2, and a hash of the active set.
+   * The loads of a row block are issued one visit ahead. */
+  template <int N>
+  FB_MEM void line_eval(const float *a, float *S, float *Q, unsigned *hash) const {
+FB_UNROLL
+    for (int i = 0; i < N; i++) { S[i] = 0.f; Q[i] = 0.f; hash[i] = 0u; }
 FB_UNROLL
     for (int w = 0; w < 2; w++) {
       for (unsigned mw = lany[w]; mw; mw &= mw - 1) {
@@ -776,11 +778,14 @@ FB_UNROLL
         const float dlo = fb_ld_scr(pn + NB_DLO*BLK), dhi = fb_ld_scr(pn + NB_DHI*BLK);
         const float arlo = fb_ld_scr(pn + NB_ARLO*BLK), arhi = fb_ld_scr(pn + NB_ARHI*BLK);
         const float aj = fb_ld_scr(pn + NB_A*BLK), pj = fb_ld_scr(pn + NB_P*BLK);
-        const float xl = (aj - arlo) + a*pj, xh = (-aj - arhi) - a*pj;
-        const int al_ = dlo > 0.f && xl < 0.f, ah_ = dhi > 0.f && xh < 0.f;
-        if (al_) { gv += dlo*pj*xl; sl += dlo*pj*pj; }
-        if (ah_) { gv -= dhi*pj*xh; sl += dhi*pj*pj; }
-        hash = (hash + (unsigned)(al_ + 2*ah_))*0x9E3779B1u;
+FB_UNROLL
+        for (int i = 0; i < N; i++) {
+          const float xl = (aj - arlo) + a[i]*pj, xh = (-aj - arhi) - a[i]*pj;
+          const int al_ = dlo > 0.f && xl < 0.f, ah_ = dhi > 0.f && xh < 0.f;
+          if (al_) { S[i] += dlo*pj*xl; Q[i] += dlo*pj*pj; }
+          if (ah_) { S[i] -= dhi*pj*xh; Q[i] += dhi*pj*pj; }
+          hash[i] = (hash[i] + (unsigned)(al_ + 2*ah_))*0x9E3779B1u;
+        }
       }
     }
     CandIter it = cand_begin();
@@ -804,13 +809,16 @@ FB_UNROLL
       for (int row = 0; row < 4; row++) {
         const float sg = (row & 1) ? -1.f : 1.f;
         const float res = rn + sg*(row < 2 ? r1 : r2), jp = jn + sg*(row < 2 ? j1 : j2);
-        const float x = res + a*jp;
-        const int act = D > 0.f && x < 0.f;
-        if (act) { gv += D*jp*x; sl += D*jp*jp; }
-        hash = (hash + (unsigned)act)*0x9E3779B1u;
+        const float djp = D*jp;
+FB_UNROLL
+        for (int i = 0; i < N; i++) {
+          const float x = res + a[i]*jp;
+          const int act = D > 0.f && x < 0.f;
+          if (act) { S[i] += djp*x; Q[i] += djp*jp; }
+          hash[i] = (hash[i] + (unsigned)act)*0x9E3779B1u;
+        }
       }
     }
-    *gv_out = gv; *sl_out = sl; *hash_out = hash;
   }
 
   /* a <- a + alpha p for everything that is carried, and the forces of the rows that switched,
@@ -822,31 +830,51 @@ FB_UNROLL
     const int nb = m.nbody;
     const int first = mode == 1, fresh = mode != 0;
     float a2 = 0.f;
-    for (int b = 1; b < nb; b++) {
-      const FastRec &rc = rec[b];
-      float *pn = nblock(b);
-      if (rc.jtype == FB_JNT_FREE) {
-        if (first) continue;
-        float *pr = nroot();
+    /* four joints per round: their loads are in flight together */
+    for (int b0 = 1; b0 < nb; b0 += 4) {
+      float av[4], pv[4];
 FB_UNROLL
-        for (int k = 0; k < 6; k++) {
-          const float an = fb_ld_scr(pr + (NR_A + k)*BLK) + alpha*fb_ld_scr(pr + (NR_P + k)*BLK);
-          fb_st_scr(pr + (NR_A + k)*BLK, an);
-          a2 += an*an;
+      for (int i = 0; i < 4; i++) {
+        const int b = b0 + i;
+        av[i] = 0.f; pv[i] = 0.f;
+        if (b < nb) {
+          const float *pn = nblock(b);
+          av[i] = fb_ld_scr(pn + NB_A*BLK);
+          if (!first) pv[i] = fb_ld_scr(pn + NB_P*BLK);
         }
-      } else if (rc.jtype >= 0) {
-        const float ao = fb_ld_scr(pn + NB_A*BLK);
-        const float an = first ? ao : ao + alpha*fb_ld_scr(pn + NB_P*BLK);
-        if (!first) fb_st_scr(pn + NB_A*BLK, an);
-        a2 += an*an;
-        if ((rc.flags & FT_LIMITED) && lim_on(b)) {
-          const float dlo = fb_ld_scr(pn + NB_DLO*BLK), dhi = fb_ld_scr(pn + NB_DHI*BLK);
-          const float arlo = fb_ld_scr(pn + NB_ARLO*BLK), arhi = fb_ld_scr(pn + NB_ARHI*BLK);
-          const float rlo = an - arlo, rhi = -an - arhi;
-          const int wl = !fresh && dlo > 0.f && ao - arlo < 0.f, il = dlo > 0.f && rlo < 0.f;
-          const int wh = !fresh && dhi > 0.f && -ao - arhi < 0.f, ih = dhi > 0.f && rhi < 0.f;
-          /* row Jacobians +1 / -1 */
-          fb_st_scr(pn + NB_MP*BLK, dlo*rlo*(float)(wl - il) - dhi*rhi*(float)(wh - ih));
+      }
+FB_UNROLL
+      for (int i = 0; i < 4; i++) {
+        const int b = b0 + i;
+        if (b >= nb) continue;
+        const FastRec &rc = rec[b];
+        float *pn = nblock(b);
+        if (rc.jtype == FB_JNT_FREE) {
+          if (first) continue;
+          float *pr = nroot();
+          float ra[6], rp[6];
+FB_UNROLL
+          for (int k = 0; k < 6; k++) { ra[k] = fb_ld_scr(pr + (NR_A + k)*BLK); rp[k] = fb_ld_scr(pr + (NR_P + k)*BLK); }
+FB_UNROLL
+          for (int k = 0; k < 6; k++) {
+            const float an = ra[k] + alpha*rp[k];
+            fb_st_scr(pr + (NR_A + k)*BLK, an);
+            a2 += an*an;
+          }
+        } else if (rc.jtype >= 0) {
+          const float ao = av[i];
+          const float an = first ? ao : ao + alpha*pv[i];
+          if (!first) fb_st_scr(pn + NB_A*BLK, an);
+          a2 += an*an;
+          if ((rc.flags & FT_LIMITED) && lim_on(b)) {
+            const float dlo = fb_ld_scr(pn + NB_DLO*BLK), dhi = fb_ld_scr(pn + NB_DHI*BLK);
+            const float arlo = fb_ld_scr(pn + NB_ARLO*BLK), arhi = fb_ld_scr(pn + NB_ARHI*BLK);
+            const float rlo = an - arlo, rhi = -an - arhi;
+            const int wl = !fresh && dlo > 0.f && ao - arlo < 0.f, il = dlo > 0.f && rlo < 0.f;
+            const int wh = !fresh && dhi > 0.f && -ao - arhi < 0.f, ih = dhi > 0.f && rhi < 0.f;
+            /* row Jacobians +1 / -1 */
+            fb_st_scr(pn + NB_MP*BLK, dlo*rlo*(float)(wl - il) - dhi*rhi*(float)(wh - ih));
+          }
         }
       }
     }
@@ -889,40 +917,50 @@ FB_UNROLL
     newton_update(0.f, 1);                       /* Delta = the constraint forces at a0: g = -J' f(a0) */
     for (; it < maxit && FB_ANY(!done); it++) {
       float pg, pp, gv, sl;
-      unsigned hash = 0u, hash0 = 0u;
+      unsigned hash, hash0;
       newton_a(keep);
       newton_b(&pg, &pp, it == 0);
       /* Line search on phi'(a) = p'M(a - a0) + a p'Mp + sum_active(a) D jp (res + a jp).  With
-       * H p = -g:  p'M(a - a0) = p.g - S0,  p'Mp = -p.g - Q0,  S0 / Q0 = the row sums at a = 0.
-       * First iteration: a = a0 and p'Mp comes from sweep C. */
-      line_eval(0.f, 0.f, 0.f, &gv, &sl, &hash0);
-      float g0 = pg - gv, pMp = fmaxf(-pg - sl, 1e-7f*fabsf(pg));
+       * H p = -g:  p'M(a - a0) = p.g - S(0),  p'Mp = -p.g - Q(0).  First iteration: a = a0 and
+       * p'Mp comes from sweep C.  phi'(0) = p.g and phi''(0) = -p.g, so the first trial step is
+       * the full Newton step: the rows are evaluated at 0 and 1 in the same pass. */
+      const float a01[2] = {0.f, 1.f};
+      float S2[2], Q2[2];
+      unsigned h2[2];
+      line_eval<2>(a01, S2, Q2, h2);
+      float g0 = pg - S2[0], pMp = fmaxf(-pg - Q2[0], 1e-7f*fabsf(pg));
       if (it == 0) { g0 = 0.f; pMp = newton_c(); }
-      /* zero of the piecewise-linear derivative by safeguarded Newton steps; phi'(0) = p.g,
-       * phi''(0) = -p.g, so the first step is the full Newton step */
+      /* zero of the piecewise-linear derivative by safeguarded Newton steps */
       int ls_done = done || !(pg < 0.f), nls = 1, exact = 0;
       float a = ls_done ? 0.f : 1.f, lo = 0.f, hi = 3.0e38f;
+      gv = g0 + pMp + S2[1]; sl = pMp + Q2[1];
+      hash0 = h2[0]; hash = h2[1];
       for (int ls = 1; ls < 16 && FB_ANY(!ls_done); ls++) {
+        /* here gv, sl, hash belong to a */
+        if (!ls_done) {
+          if (fabsf(gv) <= 1e-5f*fabsf(pg)) {
+            /* The derivative vanishes at a with the rows that were active at 0: H was built from
+             * the final active set, the Newton step is the exact minimiser, nothing is left to do. */
+            exact = hash == hash0;
+            ls_done = 1;
+          } else {
+            if (gv < 0.f) lo = a; else hi = a;
+            float an = a - gv/sl;
+            if (!(an > lo) || !(an < hi)) {
+              if (hi < 1.0e38f) an = 0.5f*(lo + hi);
+              else an = 2.f*a + 1.f;
+            }
+            /* the derivative is piecewise linear: a Newton step inside one piece is exact, and the
+             * outer iteration absorbs what is left (MuJoCo's own search stops at 1e-2) */
+            if (fabsf(an - a) <= 1e-4f*fabsf(an)) ls_done = 1;
+            a = an;
+          }
+        }
+        if (!FB_ANY(!ls_done)) break;
         nls++;
-        line_eval(a, g0, pMp, &gv, &sl, &hash);
-        if (ls_done) continue;
-        if (fabsf(gv) <= 1e-5f*fabsf(pg)) {
-          /* The derivative vanishes at a with the rows that were active at 0: H was built from
-           * the final active set, the Newton step is the exact minimiser, nothing is left to do. */
-          exact = hash == hash0;
-          ls_done = 1;
-          continue;
-        }
-        if (gv < 0.f) lo = a; else hi = a;
-        float an = a - gv/sl;
-        if (!(an > lo) || !(an < hi)) {
-          if (hi < 1.0e38f) an = 0.5f*(lo + hi);
-          else an = 2.f*a + 1.f;
-        }
-        /* the derivative is piecewise linear: a Newton step inside one piece is exact, and the
-         * outer iteration absorbs what is left (MuJoCo's own search stops at 1e-2) */
-        if (fabsf(an - a) <= 1e-4f*fabsf(an)) ls_done = 1;
-        a = an;
+        float S1, Q1;
+        line_eval<1>(&a, &S1, &Q1, &hash);
+        gv = g0 + a*pMp + S1; sl = pMp + Q1;
       }
       if (done) a = 0.f;
       const float a2 = newton_update(a, it == 0 ? 2 : 0);
