@@ -347,7 +347,10 @@ def run_b200(args, rank, world, local_rank):
         tpath = os.path.join(ROOT, 'profiles', 'traffic.json')
         if os.path.exists(tpath):
             with open(tpath) as f:
-                traffic = json.load(f).get('dram_bytes_per_launch')
+                tj = json.load(f)
+            # measured DRAM bytes per launch exist for the profiled (workload, batch, steps) only
+            traffic = tj.get('by_workload', {}).get(f'{args.model}:{n_local}:{args.inner}', {}).get(
+                'dram_bytes_per_launch')
         out = {
             'metric': METRIC, 'value': value, 'unit': 'env-steps/s', 'n_gpus': world,
             'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': total_ms/args.steps,
