@@ -278,7 +278,12 @@ def run_b200(args, rank, world, local_rank):
         # download of launch i with the kernels of launch i+1 (include/farms_b200.h)
         ctrl_host = [torch.zeros((n_local, model.nu), dtype=torch.float32).pin_memory() for _ in range(2)]
         links_host = [torch.empty((n_local, nl, 20), dtype=torch.float32).pin_memory() for _ in range(2)]
-        joints_host = [torch.empty((n_local, njf, 18), dtype=torch.float32).pin_memory() for _ in range(2)]
+        # the joints row comes down as the four columns the path writes (position, velocity,
+        # torque, limit force); physics.py:481-524 leaves the other 14 of the 18 zero
+        from farms_mujoco_b200.layout import sc
+        jcols = [sc.joint_position, sc.joint_velocity, sc.joint_torque, sc.joint_limit_force]
+        physics.set_host_joint_columns(jcols)
+        joints_host = [torch.empty((n_local, njf, len(jcols)), dtype=torch.float32).pin_memory() for _ in range(2)]
         physics.set_wave_controller(None, None, None, None)   # ctrl now comes from the host
         acts, amp, freq, lag = wave_controller(spec, model)
         acts_t = torch.as_tensor(np.array(acts))
@@ -323,6 +328,7 @@ def run_b200(args, rank, world, local_rank):
             'd2h_bytes_per_step': int((links_host.numel() + joints_host.numel())*4*world),
             'checksum': float(links_host[:, 0, 0].double().sum()) + checksum[0],
             'pipelined': 'device->host copy of launch i overlaps the kernels of launch i+1 (fb_step_host_async)',
+            'rows_down': 'last links row [n_envs, n_links, 20] + joints row [n_envs, n_joints, 4 written columns]',
         }
 
     # ---- optional end-of-rollout gather of per-env statistics (NCCL)
@@ -367,6 +373,7 @@ def run_b200(args, rank, world, local_rank):
                                 else 'fb_step_kernel (lane team = 1 env, constraint solver) on the hand-overs'))
                             if physics.fast_path else 'fb_step_kernel only'),
                 'fast_envs_per_block': physics.fast_path,
+                'fast_slim_layout': bool(physics.fast_slim),
                 'fast_smem_bytes_per_env': physics.fast_smem_bytes_per_env,
                 'handed_over_envs_last_launch': handed_over,
                 'team_lanes': physics.team_lanes, 'team_smem_bytes_per_env': physics.smem_bytes_per_env,
@@ -381,7 +388,7 @@ def run_b200(args, rank, world, local_rank):
                 'bound': 'hbm', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s',
                 'frac': achieved/peak, 'traffic': traffic,
                 'kernel': ((f'fb_fastc_kernel<{physics.fast_path}>' if physics.constraint_path and 2*handed_over > n_local
-                            else f'fb_fast_kernel<{physics.fast_path}>') if physics.fast_path and
+                            else f'fb_fast_kernel<{physics.fast_path},{physics.fast_slim}>') if physics.fast_path and
                            (physics.constraint_path or 2*handed_over <= n_local)
                            else f'fb_step_kernel<{physics.team_lanes}>'),
                 'kernel_ms': k_ms,

@@ -86,7 +86,7 @@ struct FbFastParams {
   FastRec rec[FB_FAST_MAXBODY];   /* per-body records, read from the constant bank */
 };
 
-template <int BLK>
+template <int BLK, int SLIM>
 __global__ void __launch_bounds__(BLK)
 fb_fast_kernel(const __grid_constant__ FbFastParams Q) {
   extern __shared__ __align__(16) float fb_smem[];
@@ -95,11 +95,12 @@ fb_fast_kernel(const __grid_constant__ FbFastParams Q) {
   if (blockIdx.x == 0 && threadIdx.x == 0) P.pending_count[P.parity ^ 1] = 0;   /* for the next launch */
   if (env >= P.n_envs) return;
   /* L2-resident scratch [block][field][lane]: compile-time strides, coalesced */
-  FbFast<BLK> st(P, Q.rec, fb_smem + threadIdx.x,
-                 P.fast_scratch + (size_t)blockIdx.x*P.m.X.n_scratch*BLK + threadIdx.x, env);
+  FbFast<BLK, SLIM> st(P, Q.rec, fb_smem + threadIdx.x,
+                       P.fast_scratch + (size_t)blockIdx.x*(SLIM ? P.m.X.n_scratch_slim : P.m.X.n_scratch)*BLK + threadIdx.x, env);
   /* full warps move their state through a shared-memory tile (coalesced); a partial last
-   * block, or a model whose state rows do not fit the tile, uses per-thread accesses */
-  const int coop = BLK == 32 && P.m.X.coop_io && (blockIdx.x + 1)*BLK <= P.n_envs;
+   * block, or a model whose state rows do not fit the tile (always so in the SLIM layout), uses
+   * per-thread accesses */
+  const int coop = !SLIM && BLK == 32 && P.m.X.coop_io && (blockIdx.x + 1)*BLK <= P.n_envs;
   const int done = st.run(coop, threadIdx.x);
   if (done < P.n_steps) {
     P.steps_done[env] = done;
@@ -147,6 +148,20 @@ __global__ void fb_gather_rows_kernel(const float *__restrict__ log, long long r
   for (int k = 0; k < vec; k++) dst[k] = src[k];
 }
 
+/* selected columns of ring row `row` of every environment -> dense [n_envs][n_items][n_sel] */
+struct FbColSel { int n; int col[32]; };
+__global__ void fb_gather_cols_kernel(const float *__restrict__ log, long long row, int n_items, int n_cols,
+                                      int vec, long long env_pad, int n_envs, FbColSel sel,
+                                      float *__restrict__ out) {
+  long long i = (long long)blockIdx.x*blockDim.x + threadIdx.x;
+  const long long per_env = (long long)n_items*sel.n;
+  if (i >= per_env*n_envs) return;
+  const long long k = i/n_envs, env = i - k*n_envs;            /* env fastest: coalesced reads */
+  const int item = (int)(k/sel.n), c = sel.col[k - (long long)item*sel.n];
+  const long long f = (long long)item*n_cols + c, nvec = (long long)n_items*n_cols/vec;
+  out[env*per_env + k] = log[((row*nvec + f/vec)*env_pad + env)*vec + f % vec];
+}
+
 /* control sequence [K][n_envs][nu] (host order) -> [K][nu][env_pad] (environment-minor) */
 __global__ void fb_transpose_ctrl_kernel(const float *__restrict__ in, int K, int n_envs, int nu,
                                          long long env_pad, float *__restrict__ out) {
@@ -175,6 +190,8 @@ struct FbHandle {
   size_t smem_bytes;
   int fast_enabled, fast_block;     /* environment-per-thread kernel: on/off, threads per block */
   int con_thread;                   /* 1: hand-overs go to the per-thread constrained kernel, 0: to the team kernel */
+  int fast_slim;                    /* 1: SLIM layout of the unconstrained kernel (8 warps per SM; large batches) */
+  size_t fast_slim_smem_bytes;
   size_t fast_smem_bytes;
   long long launch_parity;
 #ifndef FB_HOST_EMU
@@ -189,6 +206,7 @@ struct FbHandle {
   long long it;            /* physics steps since reset */
   float last_ms;
   float *gather_links, *gather_joints;   /* fb_step_host staging */
+  int joint_sel_n, joint_sel[32];        /* fb_set_host_joint_columns: columns of the joints row fb_step_host returns (0 = all) */
   float *gather_env;                     /* fb_export_farms staging: one environment's ring of one kind */
   float *seq_dev, *seq_stage;            /* control sequence, environment-minor + upload staging */
   int seq_len, seq_pos, seq_cap;
@@ -331,10 +349,12 @@ static int launch(FbHandle *h, int mode, int n_steps, int want_derived) {
   const DevModel &m = P.m;
   if (use_fast) {
     P.pending_count[P.parity ^ 1] = 0;
-    std::vector<float> fs((size_t)m.X.n_float + 8, 0.f), fg((size_t)m.X.n_scratch + 8, 0.f);
+    std::vector<float> fs((size_t)m.X.n_float + 8, 0.f);
+    std::vector<float> fg((size_t)(m.X.n_scratch > m.X.n_scratch_slim ? m.X.n_scratch : m.X.n_scratch_slim) + 8, 0.f);
     for (int env = 0; env < P.n_envs; env++) {
-      FbFast<1> st(P, h->hm.rec.data(), fs.data(), fg.data(), env);
-      int done = st.run(0, 0);
+      int done;
+      if (h->fast_slim) { FbFast<1, 1> st(P, h->hm.rec.data(), fs.data(), fg.data(), env); done = st.run(0, 0); }
+      else { FbFast<1> st(P, h->hm.rec.data(), fs.data(), fg.data(), env); done = st.run(0, 0); }
       if (done < n_steps) { P.steps_done[env] = done; P.pending[P.pending_count[P.parity]++] = env; }
     }
     if (con_thread) {
@@ -360,9 +380,11 @@ static int launch(FbHandle *h, int mode, int n_steps, int want_derived) {
   if (use_fast) {
     int fblocks = (P.n_envs + h->fast_block - 1)/h->fast_block;
     h->fastQ->P = P;
-    switch (h->fast_block) {
-      case 16: fb_fast_kernel<16><<<fblocks, 16, h->fast_smem_bytes, h->stream>>>(*h->fastQ); break;
-      default: fb_fast_kernel<32><<<fblocks, 32, h->fast_smem_bytes, h->stream>>>(*h->fastQ); break;
+    if (h->fast_slim) {
+      fb_fast_kernel<32, 1><<<(P.n_envs + 31)/32, 32, h->fast_slim_smem_bytes, h->stream>>>(*h->fastQ);
+    } else switch (h->fast_block) {
+      case 16: fb_fast_kernel<16, 0><<<fblocks, 16, h->fast_smem_bytes, h->stream>>>(*h->fastQ); break;
+      default: fb_fast_kernel<32, 0><<<fblocks, 32, h->fast_smem_bytes, h->stream>>>(*h->fastQ); break;
     }
     h->launches++;
     if (con_thread) {
@@ -420,9 +442,12 @@ int fb_create(const FbModel *model, const FbFarms *farms, int n_envs, int device
   h->device = device; h->I_dev = nullptr; h->F_dev = nullptr; h->launches = 0; h->it = 0;
   h->last_ms = 0.f; h->has_wc = false; h->gather_links = h->gather_joints = h->gather_env = nullptr;
   h->seq_dev = h->seq_stage = nullptr; h->seq_len = h->seq_pos = h->seq_cap = 0;
+  h->joint_sel_n = 0;
   h->fast_enabled = 1; h->fast_block = 1; h->fast_smem_bytes = 0; h->launch_parity = 0;
   h->con_thread = 1;
   if (const char *ev = getenv("FARMS_B200_CON_THREAD")) h->con_thread = atoi(ev) != 0;
+  h->fast_slim = 0; h->fast_slim_smem_bytes = 0;
+  if (const char *ev = getenv("FARMS_B200_FAST_SLIM")) h->fast_slim = atoi(ev) != 0;
 #ifndef FB_HOST_EMU
   h->fastQ = nullptr; h->conQ = nullptr;
 #endif
@@ -501,10 +526,19 @@ int fb_create(const FbModel *model, const FbFarms *farms, int n_envs, int device
       if (ce == cudaSuccess) ce = cudaFuncSetAttribute(K_, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes); \
       if (ce == cudaSuccess) ce = cudaFuncSetAttribute(K_, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
       switch (h->fast_block) {
-        case 16: FB_SET_SMEM(fb_fast_kernel<16>) FB_SET_SMEM(fb_fastc_kernel<16>) break;
-        default: FB_SET_SMEM(fb_fast_kernel<32>) FB_SET_SMEM(fb_fastc_kernel<32>) break;
+        case 16: FB_SET_SMEM((fb_fast_kernel<16, 0>)) FB_SET_SMEM(fb_fastc_kernel<16>) break;
+        default: FB_SET_SMEM((fb_fast_kernel<32, 0>)) FB_SET_SMEM(fb_fastc_kernel<32>) break;
       }
 #undef FB_SET_SMEM
+      /* SLIM layout: pays when the batch has more warps than the regular layout keeps resident
+       * (4 per SM), i.e. when a second warp per scheduler exists to hide latencies behind */
+      if (!getenv("FARMS_B200_FAST_SLIM")) h->fast_slim = h->fast_block == 32 && n_envs/32 > 4*sms;
+      if (h->fast_block != 32) h->fast_slim = 0;
+      if (h->fast_slim) {
+        h->fast_slim_smem_bytes = (size_t)m.X.n_float_slim*sizeof(float)*32;
+        if (ce == cudaSuccess) ce = cudaFuncSetAttribute(fb_fast_kernel<32, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->fast_slim_smem_bytes);
+        if (ce == cudaSuccess) ce = cudaFuncSetAttribute(fb_fast_kernel<32, 1>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+      }
       if (ce != cudaSuccess) { fb_destroy(h); return fail(std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(ce)); }
     }
   }
@@ -525,7 +559,10 @@ int fb_create(const FbModel *model, const FbFarms *farms, int n_envs, int device
   bad |= alloc_arr(h, &P.pending, n); bad |= alloc_arr(h, &P.pending_count, 2); bad |= alloc_arr(h, &P.steps_done, n);
   P.fast_scratch_stride = (long long)((n + 31) & ~(size_t)31);
   P.fast_scratch = nullptr;
-  if (m.X.ok) bad |= alloc_arr(h, &P.fast_scratch, (size_t)P.fast_scratch_stride*(m.X.n_scratch > 0 ? m.X.n_scratch : 1));
+  if (m.X.ok) {
+    const int ns = m.X.n_scratch > m.X.n_scratch_slim ? m.X.n_scratch : m.X.n_scratch_slim;
+    bad |= alloc_arr(h, &P.fast_scratch, (size_t)P.fast_scratch_stride*(ns > 0 ? ns : 1));
+  }
   P.con_scratch = nullptr;
   if (m.X.ok) bad |= alloc_arr(h, &P.con_scratch, (size_t)P.fast_scratch_stride*(m.X.n_con > 0 ? m.X.n_con : 1));
   bad |= alloc_arr(h, &P.d_xpos, n*3*nb); bad |= alloc_arr(h, &P.d_xquat, n*4*nb);
@@ -808,7 +845,7 @@ static int step_host_impl(FbHandle *h, const float *ctrl, const float *qpos, con
   if (qvel && h2d(P.qvel, qvel, n*m.nv*sizeof(float), h->stream)) return fail(dev_error());
   if (launch(h, FB_MODE_STEP, n_steps, 0)) return -1;
   long long row = h->it % P.ring;
-  const int lf = m.n_links*20, jf = m.n_joints*m.joint_cols;
+  const int lf = m.n_links*20, jf = m.n_joints*(h->joint_sel_n > 0 ? h->joint_sel_n : m.joint_cols);
 #ifdef FB_HOST_EMU
   (void)wait;
   for (size_t e = 0; e < n; e++) {
@@ -816,9 +853,11 @@ static int step_host_impl(FbHandle *h, const float *ctrl, const float *qpos, con
       long long g = i/FB_VEC_LINKS;
       links_row[e*lf + i] = P.log_links[((row*(lf/FB_VEC_LINKS) + g)*P.env_pad + e)*FB_VEC_LINKS + i % FB_VEC_LINKS];
     }
+    const int nsel = h->joint_sel_n > 0 ? h->joint_sel_n : m.joint_cols, jfull = m.n_joints*m.joint_cols;
     for (int i = 0; joints_row && i < jf; i++) {
-      long long g = i/FB_VEC_JOINTS;
-      joints_row[e*jf + i] = P.log_joints[((row*(jf/FB_VEC_JOINTS) + g)*P.env_pad + e)*FB_VEC_JOINTS + i % FB_VEC_JOINTS];
+      const int item = i/nsel, c = h->joint_sel_n > 0 ? h->joint_sel[i - item*nsel] : i - item*nsel;
+      const long long f = (long long)item*m.joint_cols + c, g = f/FB_VEC_JOINTS;
+      joints_row[e*jf + i] = P.log_joints[((row*(jfull/FB_VEC_JOINTS) + g)*P.env_pad + e)*FB_VEC_JOINTS + f % FB_VEC_JOINTS];
     }
   }
 #else
@@ -835,7 +874,15 @@ static int step_host_impl(FbHandle *h, const float *ctrl, const float *qpos, con
           P.log_links, row, lf, FB_VEC_LINKS, P.env_pad, P.n_envs, h->gather_links);
       h->launches++;
     }
-    if (want_joints) {
+    if (want_joints && h->joint_sel_n > 0) {
+      FbColSel sel;
+      sel.n = h->joint_sel_n;
+      for (int k = 0; k < 32; k++) sel.col[k] = k < sel.n ? h->joint_sel[k] : 0;
+      long long total = (long long)n*jf;
+      fb_gather_cols_kernel<<<(unsigned)((total + 255)/256), 256, 0, h->stream>>>(
+          P.log_joints, row, m.n_joints, m.joint_cols, FB_VEC_JOINTS, P.env_pad, P.n_envs, sel, h->gather_joints);
+      h->launches++;
+    } else if (want_joints) {
       long long total = (long long)n*(jf/FB_VEC_JOINTS);
       fb_gather_rows_kernel<<<(unsigned)((total + 255)/256), 256, 0, h->stream>>>(
           P.log_joints, row, jf, FB_VEC_JOINTS, P.env_pad, P.n_envs, h->gather_joints);
@@ -884,6 +931,18 @@ int fb_host_wait(FbHandle *h) {
   return dev_sync(h->stream) ? fail(std::string("fb_host_wait: ") + dev_error()) : 0;
 }
 
+int fb_set_host_joint_columns(FbHandle *h, int n, const int32_t *cols) {
+  if (!h) return fail("null handle");
+  if (n < 0 || n > 32 || (n > 0 && !cols)) return fail("fb_set_host_joint_columns: 0..32 columns");
+  for (int k = 0; k < n; k++)
+    if (cols[k] < 0 || cols[k] >= h->hm.m.joint_cols) return fail("fb_set_host_joint_columns: column out of range");
+  /* the pipelined copies of earlier calls used the previous row width */
+  if (fb_host_wait(h)) return -1;
+  h->joint_sel_n = n;
+  for (int k = 0; k < n; k++) h->joint_sel[k] = cols[k];
+  return 0;
+}
+
 int fb_set_fast_path(FbHandle *h, int enable) {
   if (!h) return fail("null handle");
   h->fast_enabled = enable != 0;
@@ -900,7 +959,25 @@ int fb_fast_path(FbHandle *h) {
   if (!h) return 0;
   return h->fast_enabled && h->hm.m.X.ok ? h->fast_block : 0;
 }
-int fb_fast_smem_bytes_per_env(FbHandle *h) { return h ? (int)(h->hm.m.X.n_float*sizeof(float)) : 0; }
+int fb_fast_smem_bytes_per_env(FbHandle *h) {
+  return h ? (int)((h->fast_slim ? h->hm.m.X.n_float_slim : h->hm.m.X.n_float)*sizeof(float)) : 0;
+}
+/* 1: the unconstrained kernel runs its large-batch (SLIM) layout */
+int fb_fast_slim(FbHandle *h) { return h && h->fast_enabled && h->hm.m.X.ok ? h->fast_slim : 0; }
+int fb_set_fast_slim(FbHandle *h, int enable) {
+  if (!h) return fail("null handle");
+#ifndef FB_HOST_EMU
+  if (enable && h->fast_block != 32) return fail("fb_set_fast_slim: needs 32 environments per warp");
+  if (enable && !h->fast_slim_smem_bytes) {
+    h->fast_slim_smem_bytes = (size_t)h->hm.m.X.n_float_slim*sizeof(float)*32;
+    cudaError_t ce = cudaFuncSetAttribute(fb_fast_kernel<32, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->fast_slim_smem_bytes);
+    if (ce == cudaSuccess) ce = cudaFuncSetAttribute(fb_fast_kernel<32, 1>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    if (ce != cudaSuccess) return fail(std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(ce));
+  }
+#endif
+  h->fast_slim = enable != 0;
+  return 0;
+}
 /* environments the team kernel had to finish in the last fb_step (synchronises) */
 int fb_last_pending(FbHandle *h, int *count) {
   if (!h || !count) return fail("null argument");

@@ -190,7 +190,13 @@ FB_DEV void fb_sincos_half(float x, float *sn, float *cs) {
 #define FB_PIN_I(x) asm volatile("" :: "r"(x))
 #endif
 
-template <int BLK> struct FbFast {
+/* SLIM = 1 (large batches, unconstrained kernel only): the shared-memory block of a body holds
+ * its pose only (7 floats); velocities and the accumulation slots of the branching bodies move to
+ * the L2 scratch, fetched one body ahead like the rest of it.  203 instead of 431 floats of
+ * shared memory per SALAMANDER: 8 warps of environments per SM instead of 4, i.e. two warps per
+ * scheduler to hide each other's latencies, which pays once the batch has that many warps. */
+template <int BLK, int SLIM = 0> struct FbFast {
+  enum { NF = SLIM ? 7 : FB_NF, GNF = SLIM ? FG_NF + 6 : FG_NF, FG_V = FG_NF };
   const FbParams &P;
   const DevModel &m;
   const FastRec *rec; /* [nbody], constant bank (kernel parameters) */
@@ -216,9 +222,17 @@ FB_UNROLL
     for (int k = 0; k < 13; k++) rt[k] = 0.f;
   }
 
-  FB_MEM float *block(int b) const { return s + (m.X.body0 + FB_NF*(b - 1))*BLK; }
-  FB_MEM float *gblock(int b) const { return gs + FG_NF*(b - 1)*BLK; }
-  FB_MEM float *slot(int i) const { return s + (m.X.slots + 27*i)*BLK; }
+  FB_MEM float *block(int b) const { return s + (m.X.body0 + NF*(b - 1))*BLK; }
+  FB_MEM float *gblock(int b) const { return gs + GNF*(b - 1)*BLK; }
+  /* accumulation slot i: shared memory, or (SLIM) the scratch behind the body blocks */
+  FB_MEM float *slot(int i) const {
+    return SLIM ? gs + (GNF*(m.nbody - 1) + 27*i)*BLK : s + (m.X.slots + 27*i)*BLK;
+  }
+  FB_MEM float sl_ld(const float *so, int k) const { return SLIM ? fb_ld_scr(so + k*BLK) : so[k*BLK]; }
+  FB_MEM void sl_st(float *so, int k, float v) const { if (SLIM) fb_st_scr(so + k*BLK, v); else so[k*BLK] = v; }
+  FB_MEM void sl_add(float *so, int k, float v) const { sl_st(so, k, sl_ld(so, k) + v); }
+  /* shared-memory block of the parent */
+  FB_MEM const float *pblock(const FastRec &rc) const { return s + (SLIM ? rc.pblk7 : rc.pblk)*BLK; }
   FB_MEM float *nblock(int b) const { return cs + NB_NF*(b - 1)*BLK; }
   FB_MEM float *nroot() const { return cs + NB_NF*(m.nbody - 1)*BLK; }
   FB_MEM float *ncand(int fc) const { return csc + NC_NF*BLK*fc; }
@@ -376,15 +390,15 @@ FB_UNROLL
     int active = 0;
     /* scratch values are fetched one body ahead: the L2 round trip overlaps the arithmetic */
     float nq = fb_ld_scr(gblock(1) + FG_Q*BLK), nqd = fb_ld_scr(gblock(1) + FG_QD*BLK);
-    float *pb = block(1) - FB_NF*BLK;
-    const float *pn = gblock(1);
+    float *pb = block(1) - NF*BLK;
+    float *pn = gblock(1);
     Quat lastq = {1.f, 0.f, 0.f, 0.f};
     float lasto[3] = {0.f, 0.f, 0.f}, lastv[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
     float lastR[9] = {1.f, 0.f, 0.f, 0.f, 1.f, 0.f, 0.f, 0.f, 1.f};
     for (int b = 1; b < nb; b++) {
       const FastRec &rc0 = rec[b];
       struct { int parent, jtype, flags, pblk, link, chk0, chk1; float dpos[3], bquat[4], axis[3], qpos0, lo, hi, margin, hloc[3], chk[4], jpos[3]; } rc;
-      rc.parent = rc0.parent; rc.jtype = rc0.jtype; rc.flags = rc0.flags; rc.pblk = rc0.pblk; rc.link = rc0.link;
+      rc.parent = rc0.parent; rc.jtype = rc0.jtype; rc.flags = rc0.flags; rc.pblk = SLIM ? rc0.pblk7 : rc0.pblk; rc.link = rc0.link;
       rc.chk0 = rc0.chk0; rc.chk1 = rc0.chk1; rc.qpos0 = rc0.qpos0; rc.lo = rc0.lo; rc.hi = rc0.hi; rc.margin = rc0.margin;
 FB_UNROLL
       for (int k = 0; k < 3; k++) { rc.dpos[k] = rc0.dpos[k]; rc.axis[k] = rc0.axis[k]; rc.hloc[k] = rc0.hloc[k]; rc.jpos[k] = rc0.jpos[k]; }
@@ -396,10 +410,11 @@ FB_UNROLL
       for (int k = 0; k < 3; k++) { FB_PIN_F(rc.dpos[k]); FB_PIN_F(rc.axis[k]); FB_PIN_F(rc.hloc[k]); }
 FB_UNROLL
       for (int k = 0; k < 4; k++) { FB_PIN_F(rc.bquat[k]); FB_PIN_F(rc.chk[k]); }
-      pb += FB_NF*BLK;
-      pn += FG_NF*BLK;
+      pb += NF*BLK;
+      pn += GNF*BLK;
       const float cq = nq, cqd = nqd;
       if (b + 1 < nb) { nq = fb_ld_scr(pn + FG_Q*BLK); nqd = fb_ld_scr(pn + FG_QD*BLK); }
+      float *pgv = pn - GNF*BLK;       /* scratch block of this body (pn runs one ahead) */
       const int jtype = rc.jtype;
       Quat q;
       float o[3], v[6], R[9];
@@ -442,8 +457,14 @@ FB_UNROLL
             qp.w = pp[(FB_QUAT)*BLK]; qp.x = pp[(FB_QUAT + 1)*BLK]; qp.y = pp[(FB_QUAT + 2)*BLK]; qp.z = pp[(FB_QUAT + 3)*BLK];
 FB_UNROLL
             for (int k = 0; k < 3; k++) op[k] = pp[(FB_ORG + k)*BLK];
+            if (SLIM) {
+              const float *pgp = gs + GNF*(rc.parent - 1)*BLK;
 FB_UNROLL
-            for (int k = 0; k < 6; k++) vp[k] = pp[(FB_VEL + k)*BLK];
+              for (int k = 0; k < 6; k++) vp[k] = fb_ld_scr(pgp + (FG_V + k)*BLK);
+            } else {
+FB_UNROLL
+              for (int k = 0; k < 6; k++) vp[k] = pp[(FB_VEL + k)*BLK];
+            }
           }
           q_mat(qp, Rp);
         }
@@ -484,8 +505,13 @@ FB_UNROLL
       pb[(FB_QUAT)*BLK] = q.w; pb[(FB_QUAT + 1)*BLK] = q.x; pb[(FB_QUAT + 2)*BLK] = q.y; pb[(FB_QUAT + 3)*BLK] = q.z;
 FB_UNROLL
       for (int k = 0; k < 3; k++) pb[(FB_ORG + k)*BLK] = o[k];
+      if (SLIM) {
 FB_UNROLL
-      for (int k = 0; k < 6; k++) pb[(FB_VEL + k)*BLK] = v[k];
+        for (int k = 0; k < 6; k++) fb_st_scr(pgv + (FG_V + k)*BLK, v[k]);
+      } else {
+FB_UNROLL
+        for (int k = 0; k < 6; k++) pb[(FB_VEL + k)*BLK] = v[k];
+      }
       lastq = q;
 FB_UNROLL
       for (int k = 0; k < 3; k++) lasto[k] = o[k];
@@ -540,19 +566,24 @@ FB_UNROLL
 FB_UNROLL
     for (int k = 0; k < 9; k++) C.H[k] = 0.f;
     float nx[10];        /* W[6], q, qd, tc, tu of the next body to visit */
+    float nxv[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};     /* SLIM: its velocity */
     {
       const float *pn = gblock(nb - 1);
 FB_UNROLL
       for (int k = 0; k < 6; k++) nx[k] = fb_ld_scr(pn + (FG_W + k)*BLK);
       nx[6] = fb_ld_scr(pn + FG_Q*BLK); nx[7] = fb_ld_scr(pn + FG_QD*BLK);
       nx[8] = fb_ld_scr(pn + FG_TC*BLK); nx[9] = fb_ld_scr(pn + FG_TU*BLK);
+      if (SLIM) {
+FB_UNROLL
+        for (int k = 0; k < 6; k++) nxv[k] = fb_ld_scr(pn + (FG_V + k)*BLK);
+      }
     }
-    float *pb = block(nb - 1) + FB_NF*BLK;
-    float *pg = gblock(nb - 1) + FG_NF*BLK;
+    float *pb = block(nb - 1) + NF*BLK;
+    float *pg = gblock(nb - 1) + GNF*BLK;
     for (int b = nb - 1; b >= 1; b--) {
       const FastRec &rc = rec[b];
       /* issue the record loads of this body now (see FB_PIN_F) */
-      FB_PIN_I(rc.jtype); FB_PIN_I(rc.flags); FB_PIN_I(rc.pblk); FB_PIN_I(rc.parent);
+      FB_PIN_I(rc.jtype); FB_PIN_I(rc.flags); FB_PIN_I(SLIM ? rc.pblk7 : rc.pblk); FB_PIN_I(rc.parent);
       FB_PIN_F(rc.mass); FB_PIN_F(rc.Kq); FB_PIN_F(rc.Kqd); FB_PIN_F(rc.KqU); FB_PIN_F(rc.KqdU);
       FB_PIN_F(rc.wfreq); FB_PIN_F(rc.wlag); FB_PIN_F(rc.woff); FB_PIN_F(rc.wamp); FB_PIN_F(rc.wgain);
       FB_PIN_F(rc.stiffness); FB_PIN_F(rc.damping); FB_PIN_F(rc.armature);
@@ -560,24 +591,30 @@ FB_UNROLL
       for (int k = 0; k < 3; k++) { FB_PIN_F(rc.hloc[k]); FB_PIN_F(rc.axis[k]); }
 FB_UNROLL
       for (int k = 0; k < 5; k++) FB_PIN_F(rc.Ib[k]);
-      pb -= FB_NF*BLK;
-      pg -= FG_NF*BLK;
+      pb -= NF*BLK;
+      pg -= GNF*BLK;
       const int jtype = rc.jtype, flags = rc.flags;
-      float cx[10];
+      float cx[10], cxv[6];
 FB_UNROLL
       for (int k = 0; k < 10; k++) cx[k] = nx[k];
+FB_UNROLL
+      for (int k = 0; k < 6; k++) cxv[k] = nxv[k];
       if (b > 1) {
-        const float *pn = pg - FG_NF*BLK;
+        const float *pn = pg - GNF*BLK;
 FB_UNROLL
         for (int k = 0; k < 6; k++) nx[k] = fb_ld_scr(pn + (FG_W + k)*BLK);
         nx[6] = fb_ld_scr(pn + FG_Q*BLK); nx[7] = fb_ld_scr(pn + FG_QD*BLK);
         nx[8] = fb_ld_scr(pn + FG_TC*BLK); nx[9] = fb_ld_scr(pn + FG_TU*BLK);
+        if (SLIM) {
+FB_UNROLL
+          for (int k = 0; k < 6; k++) nxv[k] = fb_ld_scr(pn + (FG_V + k)*BLK);
+        }
       }
       const Quat q = {pb[(FB_QUAT)*BLK], pb[(FB_QUAT + 1)*BLK], pb[(FB_QUAT + 2)*BLK], pb[(FB_QUAT + 3)*BLK]};
       float R[9], v[6], fx[6];
       q_mat(q, R);
 FB_UNROLL
-      for (int k = 0; k < 6; k++) { v[k] = pb[(FB_VEL + k)*BLK]; fx[k] = cx[k]; }
+      for (int k = 0; k < 6; k++) { v[k] = SLIM ? cxv[k] : pb[(FB_VEL + k)*BLK]; fx[k] = cx[k]; }
       /* rigid-body inertia about the anchor */
       const float mass = rc.mass;
       float h[3], Iw[6];
@@ -660,9 +697,9 @@ FB_UNROLL
       if (flags & FT_HAS_SLOT) {
         const float *so = slot(rc.slot);
 FB_UNROLL
-        for (int k = 0; k < 6; k++) { I.A[k] += so[k*BLK]; I.M[k] += so[(15 + k)*BLK]; pA[k] += so[(21 + k)*BLK]; }
+        for (int k = 0; k < 6; k++) { I.A[k] += sl_ld(so, k); I.M[k] += sl_ld(so, 15 + k); pA[k] += sl_ld(so, 21 + k); }
 FB_UNROLL
-        for (int k = 0; k < 9; k++) I.H[k] += so[(6 + k)*BLK];
+        for (int k = 0; k < 9; k++) I.H[k] += sl_ld(so, 6 + k);
       }
       if (jtype == FB_JNT_FREE) {
         /* floating root: I a + pA = 0 for the (gravity-free frame) acceleration */
@@ -752,7 +789,7 @@ FB_UNROLL
       if (rc.parent == 0) continue;        /* fixed base: nothing above */
       /* move to the parent's anchor and hand over */
       {
-        const float *pp = (s + rc.pblk*BLK);
+        const float *pp = pblock(rc);
         float r[3];
 FB_UNROLL
         for (int k = 0; k < 3; k++) r[k] = pb[(FB_ORG + k)*BLK] - pp[(FB_ORG + k)*BLK];
@@ -766,14 +803,14 @@ FB_UNROLL
         float *so = slot(rc.pslot);
         if (flags & FT_FIRST_WRITER) {
 FB_UNROLL
-          for (int k = 0; k < 6; k++) { so[k*BLK] = I.A[k]; so[(15 + k)*BLK] = I.M[k]; so[(21 + k)*BLK] = pA[k]; }
+          for (int k = 0; k < 6; k++) { sl_st(so, k, I.A[k]); sl_st(so, 15 + k, I.M[k]); sl_st(so, 21 + k, pA[k]); }
 FB_UNROLL
-          for (int k = 0; k < 9; k++) so[(6 + k)*BLK] = I.H[k];
+          for (int k = 0; k < 9; k++) sl_st(so, 6 + k, I.H[k]);
         } else {
 FB_UNROLL
-          for (int k = 0; k < 6; k++) { so[k*BLK] += I.A[k]; so[(15 + k)*BLK] += I.M[k]; so[(21 + k)*BLK] += pA[k]; }
+          for (int k = 0; k < 6; k++) { sl_add(so, k, I.A[k]); sl_add(so, 15 + k, I.M[k]); sl_add(so, 21 + k, pA[k]); }
 FB_UNROLL
-          for (int k = 0; k < 9; k++) so[(6 + k)*BLK] += I.H[k];
+          for (int k = 0; k < 9; k++) sl_add(so, 6 + k, I.H[k]);
         }
       }
     }
@@ -791,40 +828,51 @@ FB_UNROLL
     float ac[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};   /* carry: acceleration of body b-1 */
     int bad = 0;
     float nx[11];        /* U[6], u, 1/d, trq, q, qd of the next body to visit */
+    float nxv[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};     /* SLIM: its velocity */
     {
       const float *pn = gblock(1);
 FB_UNROLL
       for (int k = 0; k < 9; k++) nx[k] = fb_ld_scr(pn + (FG_W + k)*BLK);     /* W, U, DINV, TRQ are contiguous */
       nx[9] = fb_ld_scr(pn + FG_Q*BLK); nx[10] = fb_ld_scr(pn + FG_QD*BLK);
+      if (SLIM) {
+FB_UNROLL
+        for (int k = 0; k < 6; k++) nxv[k] = fb_ld_scr(pn + (FG_V + k)*BLK);
+      }
     }
-    float *pb = block(1) - FB_NF*BLK;
-    float *pg = gblock(1) - FG_NF*BLK;
+    float *pb = block(1) - NF*BLK;
+    float *pg = gblock(1) - GNF*BLK;
     for (int b = 1; b < nb; b++) {
       const FastRec &rc = rec[b];
-      FB_PIN_I(rc.jtype); FB_PIN_I(rc.flags); FB_PIN_I(rc.pblk); FB_PIN_I(rc.parent); FB_PIN_I(rc.fj);
+      FB_PIN_I(rc.jtype); FB_PIN_I(rc.flags); FB_PIN_I(SLIM ? rc.pblk7 : rc.pblk); FB_PIN_I(rc.parent); FB_PIN_I(rc.fj);
       FB_PIN_I(rc.xr); FB_PIN_I(rc.swim);
       FB_PIN_F(rc.lift); FB_PIN_F(rc.height);
 FB_UNROLL
       for (int k = 0; k < 3; k++) { FB_PIN_F(rc.hloc[k]); FB_PIN_F(rc.axis[k]); }
 FB_UNROLL
       for (int k = 0; k < 6; k++) FB_PIN_F(rc.coef[k]);
-      pb += FB_NF*BLK;
-      pg += FG_NF*BLK;
+      pb += NF*BLK;
+      pg += GNF*BLK;
       const int jtype = rc.jtype, flags = rc.flags;
-      float cx[11];
+      float cx[11], cxv[6];
 FB_UNROLL
       for (int k = 0; k < 11; k++) cx[k] = nx[k];
+FB_UNROLL
+      for (int k = 0; k < 6; k++) cxv[k] = nxv[k];
       if (b + 1 < nb) {
-        const float *pn = pg + FG_NF*BLK;
+        const float *pn = pg + GNF*BLK;
 FB_UNROLL
         for (int k = 0; k < 9; k++) nx[k] = fb_ld_scr(pn + (FG_W + k)*BLK);
         nx[9] = fb_ld_scr(pn + FG_Q*BLK); nx[10] = fb_ld_scr(pn + FG_QD*BLK);
+        if (SLIM) {
+FB_UNROLL
+          for (int k = 0; k < 6; k++) nxv[k] = fb_ld_scr(pn + (FG_V + k)*BLK);
+        }
       }
       const Quat q = {pb[(FB_QUAT)*BLK], pb[(FB_QUAT + 1)*BLK], pb[(FB_QUAT + 2)*BLK], pb[(FB_QUAT + 3)*BLK]};
       float R[9], v[6], a[6];
       q_mat(q, R);
 FB_UNROLL
-      for (int k = 0; k < 6; k++) v[k] = pb[(FB_VEL + k)*BLK];
+      for (int k = 0; k < 6; k++) v[k] = SLIM ? cxv[k] : pb[(FB_VEL + k)*BLK];
       if (jtype == FB_JNT_FREE) {
 FB_UNROLL
         for (int k = 0; k < 6; k++) a[k] = aroot[k];
@@ -851,7 +899,7 @@ FB_UNROLL
         float ap[6] = {0.f, 0.f, 0.f, -m.grav[0], -m.grav[1], -m.grav[2]};
         float r[3] = {0.f, 0.f, 0.f}, cr[3];
         if (rc.parent > 0) {
-          const float *pp = (s + rc.pblk*BLK);
+          const float *pp = pblock(rc);
 FB_UNROLL
           for (int k = 0; k < 3; k++) r[k] = pb[(FB_ORG + k)*BLK] - pp[(FB_ORG + k)*BLK];
           if (flags & FT_TO_CARRY) {
@@ -860,7 +908,7 @@ FB_UNROLL
           } else {
             const float *so = slot(rc.pslot);
 FB_UNROLL
-            for (int k = 0; k < 6; k++) ap[k] = so[k*BLK];
+            for (int k = 0; k < 6; k++) ap[k] = sl_ld(so, k);
           }
         }
         v_cross(ap, r, cr);
@@ -916,7 +964,7 @@ FB_UNROLL
       if (flags & FT_HAS_SLOT) {
         float *so = slot(rc.slot);
 FB_UNROLL
-        for (int k = 0; k < 6; k++) so[k*BLK] = a[k];
+        for (int k = 0; k < 6; k++) sl_st(so, k, a[k]);
       }
       /* xfrc row + the wrench applied during the next step (drag.pyx:152-268, 3.4) */
       if (rc.xr >= 0) {

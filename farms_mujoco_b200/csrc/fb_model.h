@@ -93,7 +93,7 @@ struct FastRec {
   float wamp, woff, lift, height;         /* lift = 1000*9.81*mass/density (drag.pyx:142-145) */
   float coef[6], KqU, KqdU;               /* KqU/KqdU/T0U: the part of the actuation that the */
   float T0U;                              /* farms joint_torque column does not log */
-  int32_t bc0, bc1, pad0;                 /* candidates of the body: CandRec[bc0 .. bc1) (fb_fastc.h) */
+  int32_t bc0, bc1, pblk7;                /* candidates of the body: CandRec[bc0 .. bc1) (fb_fastc.h); 7*(parent-1) (SLIM blocks) */
   float chk[4];                           /* first conservative plane check (normal, offset) */
 };
 
@@ -123,6 +123,7 @@ struct DevFastLayout {
   int n_scratch;        /* global scratch floats per environment */
   int jrow_std;         /* farms joint row = 18 columns, position 0, velocity 1, torque 11 */
   int coop_io;          /* [32][nq + nv + nu + 6 nbody] fits the warp's shared memory: tiled state I/O */
+  int n_float_slim, n_scratch_slim;   /* SLIM variant of the unconstrained kernel (fb_fast.h) */
   int n_con;            /* global scratch floats per environment of the constrained step (fb_fastc.h) */
   int con_ok;           /* 1 when the per-thread constrained step covers the model (else: team kernel) */
 };
@@ -569,6 +570,7 @@ inline bool fb_build_model(const FbModel *fm, const FbFarms *ff, const FbWaveCon
       if (dn == 0) jid = -1, jt = -1;
       r.parent = p; r.jtype = jt; r.jid = jid;
       r.pblk = FB_NF*(p - 1);
+      r.pblk7 = 7*(p - 1);
       r.qa = jid >= 0 ? fm->jnt_qposadr[jid] : 0;
       r.da = jid >= 0 ? fm->jnt_dofadr[jid] : 0;
       if (jt == FB_JNT_FREE)
@@ -767,6 +769,8 @@ inline bool fb_build_model(const FbModel *fm, const FbFarms *ff, const FbWaveCon
     X.nslot = nslot;
     X.n_float = X.slots + 27*nslot;
     X.n_scratch = FG_NF*(nb - 1);
+    X.n_float_slim = 7*(nb - 1);
+    X.n_scratch_slim = (FG_NF + 6)*(nb - 1) + 27*nslot;
     X.jrow_std = m.joint_cols == 18 && m.col_jpos == 0 && m.col_jvel == 1 && m.col_jtrq == 11 && m.col_jlim == 16;
     X.coop_io = fm->nq + nv + (nu > 0 ? nu : 1) + 6*nb <= X.n_float;
   }

@@ -50,6 +50,7 @@ ABI_SYMBOLS = {
     'fb_export_farms': (ct.c_int, [_H, ct.c_int, cabi.c_double_p, cabi.c_double_p,
                                    cabi.c_double_p, cabi.c_double_p]),
     'fb_host_wait': (ct.c_int, [_H]),
+    'fb_set_host_joint_columns': (ct.c_int, [_H, ct.c_int, ct.POINTER(ct.c_int32)]),
     'fb_host_wait_slot': (ct.c_int, [_H, ct.c_int]),
     'fb_step_host': (ct.c_int, [_H, ct.c_void_p, ct.c_void_p, ct.c_void_p, ct.c_int, ct.c_void_p,
                                 ct.c_void_p]),
@@ -62,6 +63,8 @@ ABI_SYMBOLS = {
     'fb_set_constraint_path': (ct.c_int, [_H, ct.c_int]),
     'fb_constraint_path': (ct.c_int, [_H]),
     'fb_fast_smem_bytes_per_env': (ct.c_int, [_H]),
+    'fb_set_fast_slim': (ct.c_int, [_H, ct.c_int]),
+    'fb_fast_slim': (ct.c_int, [_H]),
     'fb_last_pending': (ct.c_int, [_H, ct.POINTER(ct.c_int)]),
     'fb_team_lanes': (ct.c_int, [_H]),
     'fb_smem_bytes_per_env': (ct.c_int, [_H]),
@@ -410,6 +413,13 @@ class BatchedPhysics:
                        int(n_steps), addr(links_row), addr(joints_row)))
         self.iteration += int(n_steps)
 
+    def set_host_joint_columns(self, columns=None):
+        """Columns of the joints row ``step_host`` downloads (``joints_row`` is then
+        ``[n_envs, n_joints, len(columns)]``); ``None`` = the reference's full row."""
+        cols = [] if columns is None else [int(c) for c in columns]
+        arr = (ct.c_int32*max(1, len(cols)))(*cols)
+        self._check(self.lib.fb_set_host_joint_columns(self._handle, len(cols), arr))
+
     def host_wait_slot(self, slot):
         """Completion of the copies of the latest pipelined call with index % 2 == slot."""
         self._check(self.lib.fb_host_wait_slot(self._handle, int(slot)))
@@ -432,6 +442,14 @@ class BatchedPhysics:
     def fast_path(self):
         """0 = team kernel only, else environments per block of the per-thread kernel."""
         return int(self.lib.fb_fast_path(self._handle))
+
+    def set_fast_slim(self, enable):
+        """Large-batch layout of the unconstrained kernel (include/farms_b200.h)."""
+        self._check(self.lib.fb_set_fast_slim(self._handle, int(bool(enable))))
+
+    @property
+    def fast_slim(self):
+        return int(self.lib.fb_fast_slim(self._handle))
 
     def set_constraint_path(self, per_thread):
         """Who finishes environments with an active joint limit / plane contact: ``True``

@@ -232,6 +232,11 @@ int fb_step_host(FbHandle *h, const float *ctrl, const float *qpos, const float 
 int fb_step_host_async(FbHandle *h, const float *ctrl, const float *qpos, const float *qvel,
                        int n_steps, float *links_row, float *joints_row);
 int fb_host_wait(FbHandle *h);
+/* Columns of the joints row fb_step_host / fb_step_host_async return: joints_row becomes
+ * [n_envs][n_joints][n] with the listed columns (e.g. the four the path writes: position,
+ * velocity, torque, limit force; physics.py:481-524 leaves the other 14 zero).  n = 0: all
+ * joint_cols columns, the reference's row (default). */
+int fb_set_host_joint_columns(FbHandle *h, int n, const int32_t *cols);
 /* completion of the copies of the latest pipelined call whose index (0, 1, 2, ...) % 2 == slot */
 int fb_host_wait_slot(FbHandle *h, int slot);
 
@@ -255,6 +260,12 @@ int fb_fast_path(FbHandle *h);
 int fb_set_constraint_path(FbHandle *h, int per_thread);
 int fb_constraint_path(FbHandle *h);
 int fb_fast_smem_bytes_per_env(FbHandle *h);
+/* Large-batch (SLIM) layout of the unconstrained per-thread kernel: pose in shared memory,
+ * velocities and accumulation slots in the L2 scratch -> 8 instead of 4 warps of environments per
+ * SM.  fb_create switches it on when the batch has more warps than the regular layout keeps
+ * resident (n_envs/32 > 4 x SMs); results agree with the regular layout to fp32 rounding. */
+int fb_set_fast_slim(FbHandle *h, int enable);
+int fb_fast_slim(FbHandle *h);
 int fb_last_pending(FbHandle *h, int *count);
 
 /* introspection */

@@ -216,3 +216,47 @@ def test_errors_are_reported(emu_library):
         physics.step(0)
     with pytest.raises(EngineError, match='actuator'):
         physics.set_wave_controller([999], [1.0], [1.0], [0.0])
+
+
+def test_step_host_joint_columns(emu_library):
+    """fb_set_host_joint_columns: the joints row comes down as the selected columns."""
+    from farms_mujoco_b200.engine import BatchedPhysics
+    from farms_mujoco_b200.layout import sc
+    spec, model, qpos0, qvel0, ctrl = make_case('salamander', 3)
+    nl, nj = len(spec.links_names), len(spec.joints_names)
+    cols = [sc.joint_position, sc.joint_velocity, sc.joint_torque, sc.joint_limit_force]
+    rows = {}
+    for compact in (False, True):
+        physics = BatchedPhysics.from_spec(spec, 3, buffer_size=8, library=emu_library)
+        physics.reset(qpos0, qvel0)
+        links = np.zeros((3, nl, 20), dtype=np.float32)
+        joints = np.zeros((3, nj, len(cols) if compact else sc.joint_size), dtype=np.float32)
+        if compact:
+            physics.set_host_joint_columns(cols)
+        physics.step_host(4, ctrl=ctrl.astype(np.float32), links_row=links, joints_row=joints)
+        rows[compact] = (links, joints)
+    assert np.array_equal(rows[True][0], rows[False][0])
+    assert np.array_equal(rows[True][1], rows[False][1][:, :, cols])
+    assert rows[True][1][:, :, :3].any()
+
+
+@pytest.mark.parametrize('name', ['swimmer8', 'salamander_swim', 'salamander'])
+def test_slim_layout_is_bit_identical(emu_library, name):
+    """The large-batch (SLIM) layout of the unconstrained kernel keeps velocities and slots in the
+    scratch instead of shared memory: same arithmetic, bit-identical results (hand-overs too)."""
+    from farms_mujoco_b200.engine import BatchedPhysics
+    spec, model, qpos0, qvel0, ctrl = make_case(name, 3)
+    outs = []
+    for slim in (False, True):
+        physics = BatchedPhysics.from_spec(spec, 3, buffer_size=9, library=emu_library)
+        physics.set_fast_slim(slim)
+        assert physics.fast_slim == int(slim)
+        physics.reset(qpos0, qvel0)
+        physics.set_ctrl(ctrl)
+        physics.step(5)
+        physics.step(3)
+        outs.append((physics.qpos, physics.qvel, physics.xfrc_applied, physics.log_arrays()))
+    assert np.array_equal(outs[0][0], outs[1][0]) and np.array_equal(outs[0][1], outs[1][1])
+    assert np.array_equal(outs[0][2], outs[1][2])
+    for kind in ('links', 'joints', 'contacts', 'xfrc'):
+        assert np.array_equal(outs[0][3][kind], outs[1][3][kind]), kind

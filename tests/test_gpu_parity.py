@@ -125,6 +125,29 @@ def test_block_sizes_agree(cuda_library, name, monkeypatch):
             assert np.array_equal(outs[0][2][kind], other[2][kind]), kind
 
 
+@pytest.mark.parametrize('name', ['swimmer8', 'salamander_swim', 'salamander'])
+def test_slim_layout_is_bit_identical(cuda_library, name):
+    """Large-batch (SLIM) layout of the unconstrained kernel vs the regular one."""
+    from farms_mujoco_b200.engine import BatchedPhysics
+    spec, model, qpos0, qvel0, ctrl = make_case(name, 75)
+    outs = []
+    for slim in (False, True):
+        physics = BatchedPhysics.from_spec(spec, 75, buffer_size=9, library=cuda_library)
+        if physics.fast_path != 32:
+            pytest.skip('SLIM needs 32 environments per warp')
+        physics.set_fast_slim(slim)
+        assert physics.fast_slim == int(slim)
+        physics.reset(qpos0, qvel0)
+        physics.set_ctrl(ctrl)
+        physics.step(5)
+        physics.step(3)
+        outs.append((physics.qpos, physics.qvel, physics.xfrc_applied, physics.log_arrays()))
+    assert np.array_equal(outs[0][0], outs[1][0]) and np.array_equal(outs[0][1], outs[1][1])
+    assert np.array_equal(outs[0][2], outs[1][2])
+    for kind in ('links', 'joints', 'contacts', 'xfrc'):
+        assert np.array_equal(outs[0][3][kind], outs[1][3][kind]), kind
+
+
 def test_constrained_launch_split_is_invariant(cuda_library):
     """Ground contact on the per-thread constrained kernel: 12 steps == 3 launches of 4."""
     from farms_mujoco_b200.engine import BatchedPhysics
@@ -336,6 +359,30 @@ def test_simulation_layer(cuda_library):
         for kind in ('links', 'joints', 'contacts', 'xfrc'):
             ours = getattr(sim.task.data.sensors, kind).array[env]
             assert scaled_error(ours, getattr(data.sensors, kind).array) < 5e-5, kind
+
+
+def test_step_host_joint_columns(cuda_library):
+    """fb_set_host_joint_columns: the joints row comes down as the selected columns."""
+    import torch
+    from farms_mujoco_b200.engine import BatchedPhysics
+    from farms_mujoco_b200.layout import sc
+    spec, model, qpos0, qvel0, ctrl = make_case('salamander', 70)
+    nl, nj = len(spec.links_names), len(spec.joints_names)
+    cols = [sc.joint_position, sc.joint_velocity, sc.joint_torque, sc.joint_limit_force]
+    rows = {}
+    for compact in (False, True):
+        physics = BatchedPhysics.from_spec(spec, 70, buffer_size=8, library=cuda_library)
+        physics.reset(qpos0, qvel0)
+        links = torch.zeros((70, nl, 20), dtype=torch.float32).pin_memory()
+        joints = torch.zeros((70, nj, len(cols) if compact else sc.joint_size), dtype=torch.float32).pin_memory()
+        if compact:
+            physics.set_host_joint_columns(cols)
+        physics.step_host(4, ctrl=torch.as_tensor(ctrl, dtype=torch.float32).pin_memory(), links_row=links,
+                          joints_row=joints)
+        rows[compact] = (links.clone(), joints.clone())
+    assert torch.equal(rows[True][0], rows[False][0])
+    assert torch.equal(rows[True][1], rows[False][1][:, :, cols])
+    assert rows[True][1][:, :, :3].abs().sum() > 0
 
 
 def test_step_host_pipelined_equals_synchronous(cuda_library):
