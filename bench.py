@@ -7,10 +7,11 @@ Contract (one JSON line on stdout, rank 0):
 
 Workload (config.workload): swimming salamander (28 links, nv=33) with
 hydrodynamic drag + buoyancy and full sensor logging (links/joints/contacts/
-xfrc), BASELINE.json configs[2]: 16,384 environments per GPU; N GPUs step
-N x 16,384 independent environments (weak scaling; N=4 is the 65,536-env sweep
-of configs[4]).  One bench "step" = one launch of the fused kernel advancing
-every environment by ``--inner`` physics steps.
+xfrc), the 65,536-environment sweep BASELINE.json's metric is quoted on
+(configs[4]): 65,536 environments per GPU, N GPUs step N x 65,536 independent
+environments (weak scaling, no data-path collective).  ``--envs-per-gpu 16384`` is
+configs[2].  One bench "step" = one launch of the fused kernels advancing every
+environment by ``--inner`` physics steps.
 
 value  : device-timed (CUDA events on the engine's stream, max over ranks),
          state resident in HBM.
@@ -42,7 +43,9 @@ def parse_args():
     ap.add_argument('--steps', type=int, default=20)
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
-    ap.add_argument('--envs-per-gpu', type=int, default=16384)
+    ap.add_argument('--envs-per-gpu', type=int, default=65536,
+                    help='BASELINE.json config 5 at N = 1: 65,536 swimming salamanders on one B200 (config 3 is '
+                         '--envs-per-gpu 16384)')
     ap.add_argument('--inner', type=int, default=16, help='physics steps per launch')
     ap.add_argument('--ring', type=int, default=64, help='log ring rows per env')
     ap.add_argument('--model', default=WORKLOAD)

@@ -86,30 +86,35 @@ struct FbFastParams {
   FastRec rec[FB_FAST_MAXBODY];   /* per-body records, read from the constant bank */
 };
 
-template <int BLK, int SLIM>
-__global__ void __launch_bounds__(BLK)
+/* BLK environments per warp (32, or 16 in a half-filled warp), WPB warps per block.  WPB > 1:
+ * the warps of a block are kept in step by a barrier per physics step (FbFast::run_t). */
+template <int BLK, int SLIM, int WPB>
+__global__ void __launch_bounds__(32*WPB)
 fb_fast_kernel(const __grid_constant__ FbFastParams Q) {
   extern __shared__ __align__(16) float fb_smem[];
   const FbParams &P = Q.P;
-  const int env = blockIdx.x*BLK + threadIdx.x;
+  const int warp = WPB > 1 ? threadIdx.x >> 5 : 0, lane = WPB > 1 ? threadIdx.x & 31 : threadIdx.x;
+  const int wid = blockIdx.x*WPB + warp;              /* warp index of the launch */
+  const int env = wid*BLK + lane;
   if (blockIdx.x == 0 && threadIdx.x == 0) P.pending_count[P.parity ^ 1] = 0;   /* for the next launch */
-  if (env >= P.n_envs) return;
-  /* L2-resident scratch [block][field][lane]: compile-time strides, coalesced */
-  FbFast<BLK, SLIM> st(P, Q.rec, fb_smem + threadIdx.x,
-                       P.fast_scratch + (size_t)blockIdx.x*(SLIM ? P.m.X.n_scratch_slim : P.m.X.n_scratch)*BLK + threadIdx.x, env);
+  const int valid = env < P.n_envs;
+  if (WPB == 1 && !valid) return;
+  const int n_float = SLIM ? P.m.X.n_float_slim : P.m.X.n_float;
+  /* L2-resident scratch [warp][field][lane]: compile-time strides, coalesced */
+  FbFast<BLK, SLIM> st(P, Q.rec, fb_smem + (size_t)warp*n_float*BLK + lane,
+                       P.fast_scratch + (size_t)wid*(SLIM ? P.m.X.n_scratch_slim : P.m.X.n_scratch)*BLK + lane,
+                       valid ? env : 0);
   /* full warps move their state through a shared-memory tile (coalesced); a partial last
-   * block, or a model whose state rows do not fit the tile (always so in the SLIM layout), uses
+   * warp, or a model whose state rows do not fit the tile (always so in the SLIM layout), uses
    * per-thread accesses */
-  const int coop = !SLIM && BLK == 32 && P.m.X.coop_io && (blockIdx.x + 1)*BLK <= P.n_envs;
-  const int done = st.run(coop, threadIdx.x);
-  if (done < P.n_steps) {
+  const int coop = !SLIM && BLK == 32 && P.m.X.coop_io && (wid + 1)*BLK <= P.n_envs;
+  const int done = st.template run_t<(WPB > 1)>(coop, lane, valid);
+  if (valid && done < P.n_steps) {
     P.steps_done[env] = done;
     P.pending[atomicAdd(P.pending_count + P.parity, 1)] = env;
   }
 }
 
-/* per-thread constrained step (fb_fastc.h) over the environments the kernel above handed over:
- * thread i of the launch takes pending[i] from the step it stopped at */
 struct FbFastConParams {
   FbParams P;
   FastRec rec[FB_FAST_MAXBODY];
@@ -191,6 +196,7 @@ struct FbHandle {
   int fast_enabled, fast_block;     /* environment-per-thread kernel: on/off, threads per block */
   int con_thread;                   /* 1: hand-overs go to the per-thread constrained kernel, 0: to the team kernel */
   int fast_slim;                    /* 1: SLIM layout of the unconstrained kernel (8 warps per SM; large batches) */
+  int fast_wpb;                     /* warps per block of the unconstrained kernel (> 1: barrier per step) */
   size_t fast_slim_smem_bytes;
   size_t fast_smem_bytes;
   long long launch_parity;
@@ -380,11 +386,19 @@ static int launch(FbHandle *h, int mode, int n_steps, int want_derived) {
   if (use_fast) {
     int fblocks = (P.n_envs + h->fast_block - 1)/h->fast_block;
     h->fastQ->P = P;
-    if (h->fast_slim) {
-      fb_fast_kernel<32, 1><<<(P.n_envs + 31)/32, 32, h->fast_slim_smem_bytes, h->stream>>>(*h->fastQ);
-    } else switch (h->fast_block) {
-      case 16: fb_fast_kernel<16, 0><<<fblocks, 16, h->fast_smem_bytes, h->stream>>>(*h->fastQ); break;
-      default: fb_fast_kernel<32, 0><<<fblocks, 32, h->fast_smem_bytes, h->stream>>>(*h->fastQ); break;
+    {
+      int wpb = h->fast_block == 32 ? h->fast_wpb : 1;
+      if (h->fast_slim ? (wpb != 4 && wpb != 8) : (wpb != 2 && wpb != 4)) wpb = 1;
+      const int warps = (P.n_envs + 31)/32;
+      const int wblocks = (warps + wpb - 1)/wpb;
+      const size_t bytes = (h->fast_slim ? h->fast_slim_smem_bytes : h->fast_smem_bytes)*(h->fast_block == 32 ? wpb : 1);
+      if (h->fast_block == 16) fb_fast_kernel<16, 0, 1><<<fblocks, 16, bytes, h->stream>>>(*h->fastQ);
+      else if (h->fast_slim && wpb == 8) fb_fast_kernel<32, 1, 8><<<wblocks, 256, bytes, h->stream>>>(*h->fastQ);
+      else if (h->fast_slim && wpb == 4) fb_fast_kernel<32, 1, 4><<<wblocks, 128, bytes, h->stream>>>(*h->fastQ);
+      else if (h->fast_slim) fb_fast_kernel<32, 1, 1><<<warps, 32, bytes, h->stream>>>(*h->fastQ);
+      else if (wpb == 4) fb_fast_kernel<32, 0, 4><<<wblocks, 128, bytes, h->stream>>>(*h->fastQ);
+      else if (wpb == 2) fb_fast_kernel<32, 0, 2><<<wblocks, 64, bytes, h->stream>>>(*h->fastQ);
+      else fb_fast_kernel<32, 0, 1><<<warps, 32, bytes, h->stream>>>(*h->fastQ);
     }
     h->launches++;
     if (con_thread) {
@@ -407,6 +421,23 @@ static int launch(FbHandle *h, int mode, int n_steps, int want_derived) {
   if (mode == FB_MODE_RESET) h->it = 0; else h->it += n_steps;
   return 0;
 }
+
+#ifndef FB_HOST_EMU
+/* shared-memory attributes of the SLIM variants (1, 4 or 8 warps per block) */
+static int fb_slim_attributes(FbHandle *h, int max_smem) {
+  h->fast_slim_smem_bytes = (size_t)h->hm.m.X.n_float_slim*sizeof(float)*32;
+  const int b1 = (int)h->fast_slim_smem_bytes;
+  cudaError_t ce = cudaFuncSetAttribute(fb_fast_kernel<32, 1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, b1);
+  if (ce == cudaSuccess) ce = cudaFuncSetAttribute(fb_fast_kernel<32, 1, 1>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+  if (ce == cudaSuccess && 4*b1 <= max_smem) ce = cudaFuncSetAttribute(fb_fast_kernel<32, 1, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 4*b1);
+  if (ce == cudaSuccess) ce = cudaFuncSetAttribute(fb_fast_kernel<32, 1, 4>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+  if (ce == cudaSuccess && 8*b1 <= max_smem) ce = cudaFuncSetAttribute(fb_fast_kernel<32, 1, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 8*b1);
+  if (ce == cudaSuccess) ce = cudaFuncSetAttribute(fb_fast_kernel<32, 1, 8>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+  if (ce != cudaSuccess) return fail(std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(ce));
+  if ((h->fast_wpb == 8 && 8*b1 > max_smem) || (h->fast_wpb == 4 && 4*b1 > max_smem)) h->fast_wpb = 1;
+  return 0;
+}
+#endif
 
 /* ------------------------------------------------------------------ ABI */
 extern "C" {
@@ -446,7 +477,7 @@ int fb_create(const FbModel *model, const FbFarms *farms, int n_envs, int device
   h->fast_enabled = 1; h->fast_block = 1; h->fast_smem_bytes = 0; h->launch_parity = 0;
   h->con_thread = 1;
   if (const char *ev = getenv("FARMS_B200_CON_THREAD")) h->con_thread = atoi(ev) != 0;
-  h->fast_slim = 0; h->fast_slim_smem_bytes = 0;
+  h->fast_slim = 0; h->fast_slim_smem_bytes = 0; h->fast_wpb = 1;
   if (const char *ev = getenv("FARMS_B200_FAST_SLIM")) h->fast_slim = atoi(ev) != 0;
 #ifndef FB_HOST_EMU
   h->fastQ = nullptr; h->conQ = nullptr;
@@ -526,19 +557,27 @@ int fb_create(const FbModel *model, const FbFarms *farms, int n_envs, int device
       if (ce == cudaSuccess) ce = cudaFuncSetAttribute(K_, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes); \
       if (ce == cudaSuccess) ce = cudaFuncSetAttribute(K_, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
       switch (h->fast_block) {
-        case 16: FB_SET_SMEM((fb_fast_kernel<16, 0>)) FB_SET_SMEM(fb_fastc_kernel<16>) break;
-        default: FB_SET_SMEM((fb_fast_kernel<32, 0>)) FB_SET_SMEM(fb_fastc_kernel<32>) break;
+        case 16: FB_SET_SMEM((fb_fast_kernel<16, 0, 1>)) FB_SET_SMEM(fb_fastc_kernel<16>) break;
+        default: FB_SET_SMEM((fb_fast_kernel<32, 0, 1>)) FB_SET_SMEM(fb_fastc_kernel<32>) break;
       }
 #undef FB_SET_SMEM
+      if (const char *ev = getenv("FARMS_B200_FAST_WPB")) h->fast_wpb = atoi(ev);
+      if (h->fast_block == 32) {
+        /* multi-warp variants: one block's shared memory is wpb warps' worth */
+        const int b4 = (int)(4*per_thread*32), b2 = (int)(2*per_thread*32);
+        if (ce == cudaSuccess && b4 <= max_smem) ce = cudaFuncSetAttribute(fb_fast_kernel<32, 0, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, b4);
+        if (ce == cudaSuccess) ce = cudaFuncSetAttribute(fb_fast_kernel<32, 0, 4>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        if (ce == cudaSuccess && b2 <= max_smem) ce = cudaFuncSetAttribute(fb_fast_kernel<32, 0, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, b2);
+        if (ce == cudaSuccess) ce = cudaFuncSetAttribute(fb_fast_kernel<32, 0, 2>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        if ((h->fast_wpb == 4 && b4 > max_smem) || (h->fast_wpb == 2 && b2 > max_smem)) h->fast_wpb = 1;
+      }
       /* SLIM layout: pays when the batch has more warps than the regular layout keeps resident
        * (4 per SM), i.e. when a second warp per scheduler exists to hide latencies behind */
       if (!getenv("FARMS_B200_FAST_SLIM")) h->fast_slim = h->fast_block == 32 && n_envs/32 > 4*sms;
       if (h->fast_block != 32) h->fast_slim = 0;
-      if (h->fast_slim) {
-        h->fast_slim_smem_bytes = (size_t)m.X.n_float_slim*sizeof(float)*32;
-        if (ce == cudaSuccess) ce = cudaFuncSetAttribute(fb_fast_kernel<32, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->fast_slim_smem_bytes);
-        if (ce == cudaSuccess) ce = cudaFuncSetAttribute(fb_fast_kernel<32, 1>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-      }
+      /* ... in blocks of 8 warps kept in step (4 while that still leaves SMs without a block) */
+      if (h->fast_slim && !getenv("FARMS_B200_FAST_WPB")) h->fast_wpb = n_envs/32 >= 8*sms ? 8 : 4;
+      if (h->fast_slim && fb_slim_attributes(h, max_smem)) { fb_destroy(h); return -1; }
       if (ce != cudaSuccess) { fb_destroy(h); return fail(std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(ce)); }
     }
   }
@@ -962,17 +1001,21 @@ int fb_fast_path(FbHandle *h) {
 int fb_fast_smem_bytes_per_env(FbHandle *h) {
   return h ? (int)((h->fast_slim ? h->hm.m.X.n_float_slim : h->hm.m.X.n_float)*sizeof(float)) : 0;
 }
-/* 1: the unconstrained kernel runs its large-batch (SLIM) layout */
-int fb_fast_slim(FbHandle *h) { return h && h->fast_enabled && h->hm.m.X.ok ? h->fast_slim : 0; }
+/* 0: regular layout; else the warps per block of the large-batch (SLIM) layout (1, 4 or 8) */
+int fb_fast_slim(FbHandle *h) {
+  if (!h || !h->fast_enabled || !h->hm.m.X.ok || !h->fast_slim) return 0;
+  return h->fast_wpb == 4 || h->fast_wpb == 8 ? h->fast_wpb : 1;
+}
 int fb_set_fast_slim(FbHandle *h, int enable) {
   if (!h) return fail("null handle");
+  if (enable != 0 && enable != 1 && enable != 4 && enable != 8) return fail("fb_set_fast_slim: 0, 1, 4 or 8");
+  h->fast_wpb = enable > 1 ? enable : 1;
 #ifndef FB_HOST_EMU
   if (enable && h->fast_block != 32) return fail("fb_set_fast_slim: needs 32 environments per warp");
   if (enable && !h->fast_slim_smem_bytes) {
-    h->fast_slim_smem_bytes = (size_t)h->hm.m.X.n_float_slim*sizeof(float)*32;
-    cudaError_t ce = cudaFuncSetAttribute(fb_fast_kernel<32, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->fast_slim_smem_bytes);
-    if (ce == cudaSuccess) ce = cudaFuncSetAttribute(fb_fast_kernel<32, 1>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-    if (ce != cudaSuccess) return fail(std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(ce));
+    int max_smem = 0;
+    cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, h->device);
+    if (fb_slim_attributes(h, max_smem)) return -1;
   }
 #endif
   h->fast_slim = enable != 0;

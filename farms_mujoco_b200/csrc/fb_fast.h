@@ -195,6 +195,12 @@ FB_DEV void fb_sincos_half(float x, float *sn, float *cs) {
  * the L2 scratch, fetched one body ahead like the rest of it.  203 instead of 431 floats of
  * shared memory per SALAMANDER: 8 warps of environments per SM instead of 4, i.e. two warps per
  * scheduler to hide each other's latencies, which pays once the batch has that many warps. */
+template <int SYNC> FB_DEV void fb_block_sync() {
+#ifndef FB_HOST_EMU
+  if (SYNC) __syncthreads();
+#endif
+}
+
 template <int BLK, int SLIM = 0> struct FbFast {
   enum { NF = SLIM ? 7 : FB_NF, GNF = SLIM ? FG_NF + 6 : FG_NF, FG_V = FG_NF };
   const FbParams &P;
@@ -1013,36 +1019,50 @@ FB_UNROLL
   }
 
   /* Returns the number of steps taken here (n_steps unless a constraint appeared). */
-  FB_MEM int run(int coop, int lane) {
-    load_state(coop, lane);
+  FB_MEM int run(int coop, int lane) { return run_t<0>(coop, lane, 1); }
+  /* SYNC = 1: the warps of a block meet at a barrier before every pass.  They run the same
+   * instruction stream, so they then walk the same loop bodies at the same time and share their
+   * instruction-cache lines (the three body loops are ~30 KB each, the L1.5 I-cache 32 KB: warps at
+   * unrelated program positions miss in it all the time -- 20 % of the stall samples with eight
+   * resident warps).  Every thread of the block takes every iteration: an environment that hands
+   * over (or a thread beyond the batch, valid = 0) idles through the rest instead of leaving. */
+  template <int SYNC>
+  FB_MEM int run_t(int coop, int lane, int valid) {
+    if (valid) load_state(coop, lane);
     const size_t e = (size_t)env;
     const int n = P.n_steps;
-    int k = 0;
-    for (; k < n; k++) {
+    int kdone = n, dead = !valid;
+    for (int k = 0; k < n; k++) {
       const long long row = (P.it0 + k + 1) % P.ring;
       float *row_links = fb_log_row(P.log_links, row, m.n_links*20, P.env_pad, FB_VEC_LINKS, e);
       float *row_joints = fb_log_row(P.log_joints, row, m.n_joints*m.joint_cols, P.env_pad, FB_VEC_JOINTS, e);
       float *row_contacts = fb_log_row(P.log_contacts, row, m.n_contacts*12, P.env_pad, FB_VEC_CONTACTS, e);
       float *row_xfrc = fb_log_row(P.log_xfrc, row, m.n_xfrc*6, P.env_pad, FB_VEC_XFRC, e);
       const float time = (float)(P.it0 + k)*m.timestep;
-      if (pass_poses(row_links)) break;
-      if (rec[1].jtype == FB_JNT_FREE) { rt[3] = rqn[0]; rt[4] = rqn[1]; rt[5] = rqn[2]; rt[6] = rqn[3]; }
+      fb_block_sync<SYNC>();
+      if (!dead && pass_poses(row_links)) { kdone = k; dead = 1; }
+      if (!SYNC && dead) break;
+      if (!dead && rec[1].jtype == FB_JNT_FREE) { rt[3] = rqn[0]; rt[4] = rqn[1]; rt[5] = rqn[2]; rt[6] = rqn[3]; }
       float aroot[6] = {0.f, 0.f, 0.f, -m.grav[0], -m.grav[1], -m.grav[2]};
       const float *seqk = P.ctrl_seq ? P.ctrl_seq + ((size_t)(P.seq_pos + k)*m.nu)*P.env_pad + e : 0;
-      pass_inertia(time, aroot, k == n - 1 && m.n_wc > 0, seqk);   /* ctrl is left as the team path leaves it */
+      fb_block_sync<SYNC>();
+      if (!dead) pass_inertia(time, aroot, k == n - 1 && m.n_wc > 0, seqk);   /* ctrl is left as the team path leaves it */
+      fb_block_sync<SYNC>();
+      if (dead) continue;
       int bad = pass_accel(aroot, row_joints, row_xfrc);
       /* no contact is active on this path: the contacts rows are zero (sensors.pyx:140-190) */
       for (int i = 0; i < m.n_contacts*3; i++) fb_st4(row_contacts + i*(P.env_pad*FB_VEC_CONTACTS), 0.f, 0.f, 0.f, 0.f);
       if (bad) FB_FLAG_OR(P.flags + env, FB_FLAG_NONFINITE);
     }
-    if (P.ctrl_seq && k == n) {
+    if (!valid) return n;
+    if (P.ctrl_seq && kdone == n) {
       /* ctrl ends as the last entry used, as if the host had set it step by step */
       const float *last = P.ctrl_seq + ((size_t)(P.seq_pos + n - 1)*m.nu)*P.env_pad + e;
       for (int a = 0; a < m.nu; a++)
         if (MI(ft_actwc, a) < 0) P.ctrl[e*m.nu + a] = last[(long long)a*P.env_pad];
     }
-    store_state(P.it0 + k, coop, lane);
-    return k;
+    store_state(P.it0 + kdone, coop, lane);
+    return kdone;
   }
 };
 

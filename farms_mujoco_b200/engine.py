@@ -444,8 +444,9 @@ class BatchedPhysics:
         return int(self.lib.fb_fast_path(self._handle))
 
     def set_fast_slim(self, enable):
-        """Large-batch layout of the unconstrained kernel (include/farms_b200.h)."""
-        self._check(self.lib.fb_set_fast_slim(self._handle, int(bool(enable))))
+        """Large-batch layout of the unconstrained kernel (include/farms_b200.h): 0 / False =
+        regular, else 1, 4 or 8 warps per block."""
+        self._check(self.lib.fb_set_fast_slim(self._handle, int(enable)))
 
     @property
     def fast_slim(self):

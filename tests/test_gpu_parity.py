@@ -126,26 +126,29 @@ def test_block_sizes_agree(cuda_library, name, monkeypatch):
 
 
 @pytest.mark.parametrize('name', ['swimmer8', 'salamander_swim', 'salamander'])
-def test_slim_layout_is_bit_identical(cuda_library, name):
-    """Large-batch (SLIM) layout of the unconstrained kernel vs the regular one."""
+def test_slim_layout_is_bit_identical(cuda_library, name, monkeypatch):
+    """Large-batch (SLIM) layout of the unconstrained kernel (1, 4, 8 warps per block) vs the
+    regular one; the ground model exercises the hand-over out of multi-warp blocks."""
     from farms_mujoco_b200.engine import BatchedPhysics
+    monkeypatch.setenv('FARMS_B200_FAST_BLOCK', '32')
     spec, model, qpos0, qvel0, ctrl = make_case(name, 75)
     outs = []
-    for slim in (False, True):
+    for slim in (0, 1, 4, 8):
         physics = BatchedPhysics.from_spec(spec, 75, buffer_size=9, library=cuda_library)
         if physics.fast_path != 32:
             pytest.skip('SLIM needs 32 environments per warp')
         physics.set_fast_slim(slim)
-        assert physics.fast_slim == int(slim)
+        assert physics.fast_slim == slim
         physics.reset(qpos0, qvel0)
         physics.set_ctrl(ctrl)
         physics.step(5)
         physics.step(3)
         outs.append((physics.qpos, physics.qvel, physics.xfrc_applied, physics.log_arrays()))
-    assert np.array_equal(outs[0][0], outs[1][0]) and np.array_equal(outs[0][1], outs[1][1])
-    assert np.array_equal(outs[0][2], outs[1][2])
-    for kind in ('links', 'joints', 'contacts', 'xfrc'):
-        assert np.array_equal(outs[0][3][kind], outs[1][3][kind]), kind
+    for other in outs[1:]:
+        assert np.array_equal(outs[0][0], other[0]) and np.array_equal(outs[0][1], other[1])
+        assert np.array_equal(outs[0][2], other[2])
+        for kind in ('links', 'joints', 'contacts', 'xfrc'):
+            assert np.array_equal(outs[0][3][kind], other[3][kind]), kind
 
 
 def test_constrained_launch_split_is_invariant(cuda_library):
