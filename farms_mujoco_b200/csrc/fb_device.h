@@ -748,6 +748,15 @@ FB_UNROLL
         float cdist = centre[0]*nrm[0] + centre[1]*nrm[1] + centre[2]*nrm[2] - MF(cand_pd, c);
         dist = cdist - radius;
         hit = dist < MF(cand_margin, c) - MF(cand_gap, c);
+        if (MI(cand_iscapsule, c) >= 2) {
+          /* box corner (mjc_PlaneBox): only while it is below the box centre along the normal.
+           * (MuJoCo's cap of 4 corners per box only binds in degenerate poses and is not applied
+           * here; the per-thread kernel and the oracle apply it.) */
+          float u[3];
+          m_rot(R, MF(cand_lpos, 3*c) - MF(cand_laxis, 3*c), MF(cand_lpos, 3*c+1) - MF(cand_laxis, 3*c+1),
+                MF(cand_lpos, 3*c+2) - MF(cand_laxis, 3*c+2), u);
+          if (u[0]*nrm[0] + u[1]*nrm[1] + u[2]*nrm[2] > 0.f) hit = 0;
+        }
       }
       unsigned bits = T::ballot(mask, base, hit);
       if (hit) {
@@ -760,7 +769,7 @@ FB_UNROLL
           g.d_con_pos[3*i + k] = centre[k] - nrm[k]*(radius + 0.5f*dist);
           f[k] = nrm[k];
         }
-        if (MI(cand_iscapsule, c)) {
+        if (MI(cand_iscapsule, c) == 1) {
           m_rot(R, MF(cand_laxis, 3*c), MF(cand_laxis, 3*c+1), MF(cand_laxis, 3*c+2), f + 3);
         } else {
           f[3] = f[4] = f[5] = 0.f;

@@ -158,6 +158,7 @@ FB_UNROLL
       fb_st_scr(pn + NB_ARLO*BLK, ar2[0]); fb_st_scr(pn + NB_ARHI*BLK, ar2[1]);
     }
     const float impratio = fmaxf(FB_MINVAL, m.impratio);
+    int box_count = 0;           /* corners of the current box that touch (mjc_PlaneBox keeps 4) */
 FB_UNROLL
     for (int w = 0; w < 2; w++) {
       unsigned long long mine_w = 0ull, any_w = 0ull;
@@ -175,7 +176,15 @@ FB_UNROLL
         /* plane offset first: both terms are small near the plane */
         const float dist = ((n[0]*rootpos[0] + n[1]*rootpos[1] + n[2]*rootpos[2]) - cr_.pd)
                            + (n[0]*(o[0] + t[0]) + n[1]*(o[1] + t[1]) + n[2]*(o[2] + t[2])) - radius;
-        const int hit = dist < includemargin;
+        int hit = dist < includemargin;
+        if (cr_.iscapsule >= 2) {
+          /* box corner: only while it is below the box centre along the normal, at most 4 per box */
+          float u[3];
+          m_rot(R, cr_.lpos[0] - cr_.laxis[0], cr_.lpos[1] - cr_.laxis[1], cr_.lpos[2] - cr_.laxis[2], u);
+          if (cr_.iscapsule == 3) box_count = 0;
+          if (n[0]*u[0] + n[1]*u[1] + n[2]*u[2] > 0.f || box_count >= 4) hit = 0;
+          box_count += hit;
+        }
         if (!FB_ANY(hit)) continue;
         any_w |= 1ull << (fc & 63);
         if (hit) mine_w |= 1ull << (fc & 63);
@@ -183,7 +192,7 @@ FB_UNROLL
         float r[3], f[9];
 FB_UNROLL
         for (int k = 0; k < 3; k++) { r[k] = t[k] - n[k]*(radius + 0.5f*dist); f[k] = n[k]; }
-        if (cr_.iscapsule) m_rot(R, cr_.laxis[0], cr_.laxis[1], cr_.laxis[2], f + 3);
+        if (cr_.iscapsule == 1) m_rot(R, cr_.laxis[0], cr_.laxis[1], cr_.laxis[2], f + 3);
         else f[3] = f[4] = f[5] = 0.f;
         /* mju_makeFrame */
         v_normalize3(f);

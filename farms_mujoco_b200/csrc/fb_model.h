@@ -101,10 +101,11 @@ struct FastRec {
  * step (fb_fastc.h), in body order; travels in the kernel parameters like FastRec.  16 words. */
 #define FB_FAST_MAXCAND 112
 struct CandRec {
-  int32_t body, cid, iscapsule, pblk;     /* cid: index into the cand_* tables; pblk = FB_NF*(body-1) */
+  int32_t body, cid, iscapsule, pblk;     /* cid: index into the cand_* tables; pblk = FB_NF*(body-1);
+                                           * iscapsule: 0 sphere, 1 capsule end, 2 box corner, 3 first corner of a box */
   float pn[3], mu;                        /* plane normal (world), friction */
   float lpos[3], radius;                  /* centre relative to the body's joint anchor (body axes) */
-  float laxis[3], pd;                     /* capsule axis (body axes); plane offset */
+  float laxis[3], pd;                     /* capsule axis (body axes) / box centre relative to the anchor; plane offset */
   float includemargin, invw, pad[2];
 };
 
@@ -437,15 +438,37 @@ inline bool fb_build_model(const FbModel *fm, const FbFarms *ff, const FbWaveCon
     quat2mat(fm->geom_quat + 4*g1, pm);
     quat2mat(fm->geom_quat + 4*g2, gm);
     double n[3] = { pm[2], pm[5], pm[8] }, ax[3] = { gm[2], gm[5], gm[8] };
-    double off = fm->cand_end[c]*fm->geom_size[3*g2+1];
+    const int end = fm->cand_end[c];
     cbody[c] = fm->geom_bodyid[g2];
-    ccaps[c] = fm->cand_end[c] != 0;
-    for (int k = 0; k < 3; k++) {
-      lpos[3*c+k] = fm->geom_pos[3*g2+k] + off*ax[k];
-      laxis[3*c+k] = ax[k];
-      pn[3*c+k] = n[k];
+    if (end >= 2) {
+      /* box corner end-2 (mjc_PlaneBox): a point of radius 0; kind 2, or 3 for the first corner
+       * of its (plane, box) pair; laxis holds the box centre (the corner counts only while it is
+       * below the centre along the plane normal) */
+      if (fm->geom_type[g2] != FB_GEOM_BOX) { out.error = "cand_end >= 2 on a geom that is not a box"; return false; }
+      const int i8 = end - 2;
+      const double vec[3] = { (i8 & 1 ? 1 : -1)*fm->geom_size[3*g2], (i8 & 2 ? 1 : -1)*fm->geom_size[3*g2+1],
+                              (i8 & 4 ? 1 : -1)*fm->geom_size[3*g2+2] };
+      const bool first = c == 0 || fm->cand_geom2[c-1] != g2 || fm->cand_geom1[c-1] != g1;
+      ccaps[c] = first ? 3 : 2;
+      for (int k = 0; k < 3; k++) {
+        lpos[3*c+k] = fm->geom_pos[3*g2+k] + gm[3*k]*vec[0] + gm[3*k+1]*vec[1] + gm[3*k+2]*vec[2];
+        laxis[3*c+k] = fm->geom_pos[3*g2+k];
+        pn[3*c+k] = n[k];
+      }
+      rad[c] = 0.0;
+    } else {
+      if (fm->geom_type[g2] != FB_GEOM_SPHERE && fm->geom_type[g2] != FB_GEOM_CAPSULE) {
+        out.error = "collision candidates must be spheres, capsules or boxes"; return false;
+      }
+      const double off = end*fm->geom_size[3*g2+1];
+      ccaps[c] = end != 0;
+      for (int k = 0; k < 3; k++) {
+        lpos[3*c+k] = fm->geom_pos[3*g2+k] + off*ax[k];
+        laxis[3*c+k] = ax[k];
+        pn[3*c+k] = n[k];
+      }
+      rad[c] = fm->geom_size[3*g2];
     }
-    rad[c] = fm->geom_size[3*g2];
     pd[c] = n[0]*fm->geom_pos[3*g1] + n[1]*fm->geom_pos[3*g1+1] + n[2]*fm->geom_pos[3*g1+2];
     cinvw[c] = fm->body_invweight0[2*0] + fm->body_invweight0[2*cbody[c]];
   }
@@ -742,7 +765,7 @@ inline bool fb_build_model(const FbModel *fm, const FbFarms *ff, const FbWaveCon
           for (int k = 0; k < 3; k++) {
             r.pn[k] = (float)pn[3*c + k];
             r.lpos[k] = (float)(lpos[3*c + k] - (double)rec[b].jpos[k]);
-            r.laxis[k] = (float)laxis[3*c + k];
+            r.laxis[k] = (float)(ccaps[c] >= 2 ? laxis[3*c + k] - (double)rec[b].jpos[k] : laxis[3*c + k]);
           }
           r.mu = (float)fm->cand_friction[c]; r.radius = (float)rad[c]; r.pd = (float)pd[c];
           r.includemargin = (float)(fm->cand_margin[c] - fm->cand_gap[c]);

@@ -359,11 +359,36 @@ static void make_frame(double *f) {
 
 void orc_collision(const FbModel *m, OrcData *d) {
   d->ncon = 0;
+  int box_geom = -1, box_count = 0;
   for (int c = 0; c < m->ncand; c++) {
     int g1 = m->cand_geom1[c], g2 = m->cand_geom2[c], end = m->cand_end[c];
     const double *pm = d->geom_xmat + 9*g1, *pp = d->geom_xpos + 3*g1;
     const double *gm = d->geom_xmat + 9*g2, *gp = d->geom_xpos + 3*g2;
     double n[3] = { pm[2], pm[5], pm[8] };
+    if (end >= 2) {
+      /* plane-box (mjc_PlaneBox): corner end-2 (bit 0: x, 1: y, 2: z) of the half-sizes; kept when
+       * it is below the box centre along the normal and inside the margin; at most 4 per pair */
+      if (g2 != box_geom || (c > 0 && m->cand_geom1[c-1] != g1)) { box_geom = g2; box_count = 0; }
+      int i8 = end - 2;
+      double vec[3] = { (i8 & 1 ? 1 : -1)*m->geom_size[3*g2], (i8 & 2 ? 1 : -1)*m->geom_size[3*g2+1],
+                        (i8 & 4 ? 1 : -1)*m->geom_size[3*g2+2] };
+      double corner[3];
+      for (int k = 0; k < 3; k++) corner[k] = gm[3*k]*vec[0] + gm[3*k+1]*vec[1] + gm[3*k+2]*vec[2];
+      double dif[3] = { gp[0]-pp[0], gp[1]-pp[1], gp[2]-pp[2] };
+      double ldist = dot3(n, corner), bdist = dot3(dif, n) + ldist;
+      if (bdist > m->cand_margin[c] || ldist > 0 || box_count >= 4) continue;
+      box_count++;
+      int i = d->ncon++;
+      d->con_cand[i] = c;
+      d->con_dist[i] = bdist;
+      for (int k = 0; k < 3; k++) d->con_pos[3*i+k] = gp[k] + corner[k] - n[k]*0.5*bdist;
+      double *f = d->con_frame + 9*i;
+      memcpy(f, n, sizeof(n));
+      f[3] = f[4] = f[5] = 0;
+      make_frame(f);
+      d->con_efc_address[i] = -1;
+      continue;
+    }
     double axis[3] = { gm[2], gm[5], gm[8] };
     double centre[3], radius = m->geom_size[3*g2];
     double margin = m->cand_margin[c];

@@ -261,3 +261,30 @@ def test_slim_layout_is_bit_identical(emu_library, name):
         assert np.array_equal(outs[0][2], other[2])
         for kind in ('links', 'joints', 'contacts', 'xfrc'):
             assert np.array_equal(outs[0][3][kind], other[3][kind]), kind
+
+
+@pytest.mark.parametrize('per_thread,tol', [(True, 2e-5), (False, 5e-4)])
+def test_box_plane_contacts(emu_library, per_thread, tol):
+    """Plane-box contacts (mjc_PlaneBox corners): SALAMANDER with box feet and a
+    box trunk segment, both constraint paths vs the oracle."""
+    import fastpath_cases
+    import variant_models
+    from farms_mujoco_b200 import mjcf_subset
+    from farms_mujoco_b200.engine import BatchedPhysics
+    spec = variant_models.salamander_box_feet()
+    model = mjcf_subset.parse_mjcf(spec.mjcf)
+    assert set(range(2, 10)) <= set(model.cand_end.tolist())
+    n, n_steps = 4, 10
+    rng = np.random.default_rng(3)
+    qpos0 = np.tile(model.key_qpos, (n, 1))
+    qpos0[:, 7:] += rng.uniform(-0.1, 0.1, (n, model.nq - 7))
+    qvel0 = rng.uniform(-0.2, 0.2, (n, model.nv))
+    ctrl = rng.uniform(-0.3, 0.3, (n, model.nu))
+    physics = BatchedPhysics.from_spec(spec, n, buffer_size=n_steps + 1, library=emu_library)
+    physics.set_constraint_path(per_thread)
+    physics.reset(qpos0, qvel0)
+    physics.set_ctrl(ctrl)
+    physics.step(n_steps)
+    assert physics.last_pending == n and physics.log_arrays()['contacts'].any()
+    fastpath_cases.compare_with_oracle(spec, model, physics, qpos0, qvel0, ctrl, range(n), n_steps, tol,
+                                       tol_contacts=max(tol, 2e-4))

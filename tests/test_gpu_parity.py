@@ -151,6 +151,31 @@ def test_slim_layout_is_bit_identical(cuda_library, name, monkeypatch):
             assert np.array_equal(outs[0][3][kind], other[3][kind]), kind
 
 
+@pytest.mark.parametrize('path,tol', [('fast', 2e-5), ('team', 5e-4)])
+def test_box_plane_contacts(cuda_library, path, tol):
+    """Plane-box contacts (mjc_PlaneBox corners): SALAMANDER with box feet and a box trunk segment."""
+    import fastpath_cases
+    import variant_models
+    from farms_mujoco_b200 import mjcf_subset
+    from farms_mujoco_b200.engine import BatchedPhysics
+    spec = variant_models.salamander_box_feet()
+    model = mjcf_subset.parse_mjcf(spec.mjcf)
+    n, n_steps = 70, 10
+    rng = np.random.default_rng(3)
+    qpos0 = np.tile(model.key_qpos, (n, 1))
+    qpos0[:, 7:] += rng.uniform(-0.1, 0.1, (n, model.nq - 7))
+    qvel0 = rng.uniform(-0.2, 0.2, (n, model.nv))
+    ctrl = rng.uniform(-0.3, 0.3, (n, model.nu))
+    physics = BatchedPhysics.from_spec(spec, n, buffer_size=n_steps + 1, library=cuda_library)
+    physics.set_fast_path(path != 'team')
+    physics.reset(qpos0, qvel0)
+    physics.set_ctrl(ctrl)
+    physics.step(n_steps)
+    assert physics.log_arrays()['contacts'].any()
+    fastpath_cases.compare_with_oracle(spec, model, physics, qpos0, qvel0, ctrl, [0, 1, 35, n - 1], n_steps, tol,
+                                       tol_contacts=max(tol, 5e-4))
+
+
 def test_constrained_launch_split_is_invariant(cuda_library):
     """Ground contact on the per-thread constrained kernel: 12 steps == 3 launches of 4."""
     from farms_mujoco_b200.engine import BatchedPhysics

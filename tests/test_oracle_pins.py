@@ -189,3 +189,38 @@ def test_buoyancy_matches_formula():
     assert not fo.drag_forces(0, links, 0, xfrc, 0, np.zeros((2, 3)), water, mass=0.2, height=0.01,
                               density=800.0, gravity=-9.81, use_buoyancy=True)
     assert (xfrc == 7.0).all()
+
+
+def test_plane_box_corners():
+    """Plane-box collision (mjc_PlaneBox): a box foot flat on the floor touches with exactly its
+    four lower corners, at the corners, with the corner height as distance; at rest the contact
+    sensors carry the animat's weight."""
+    import variant_models
+    from farms_mujoco_b200 import mjcf_subset
+    from oracle.oracle import OraclePhysics
+    spec = variant_models.salamander_box_feet()
+    model = mjcf_subset.parse_mjcf(spec.mjcf)
+    orc = OraclePhysics(model)
+    orc.reset(keyframe_id=0)
+    qpos = np.array(model.key_qpos)
+    qpos[2] -= 0.004                       # feet 2 mm into the floor
+    orc.data.qpos[:] = qpos
+    orc.forward()
+    n = orc.ncon
+    cand = orc.arrays['con_cand'][:n]
+    ends = np.asarray(model.cand_end)[cand]
+    geoms = np.asarray(model.cand_geom2)[cand]
+    pos = orc.arrays['con_pos'].reshape(-1, 3)[:n]
+    dist = orc.arrays['con_dist'][:n]
+    feet = [g for g in range(model.ngeom) if model.geom_names[g].endswith('_foot')]
+    assert len(feet) == 4
+    for g in feet:
+        sel = geoms == g
+        assert sel.sum() == 4, (model.geom_names[g], sel.sum())
+        assert np.all(ends[sel] >= 2) and np.all((ends[sel] - 2) & 4 == 0)      # the four z- corners
+        assert np.allclose(dist[sel], dist[sel][0], atol=1e-12) and dist[sel][0] < 0
+        assert np.allclose(pos[sel][:, 2], 0.5*dist[sel][0], atol=1e-12)        # halfway into the floor
+        # the corners are those of the foot's 28 x 18 mm rectangle, turned by 0.3 rad about z
+        span = pos[sel][:, :2].max(axis=0) - pos[sel][:, :2].min(axis=0)
+        cs, sn = np.cos(0.3), np.sin(0.3)
+        assert np.allclose(span, [0.028*cs + 0.018*sn, 0.028*sn + 0.018*cs], atol=1e-9)

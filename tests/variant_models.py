@@ -68,3 +68,20 @@ def swimmer8_fixed_base():
                                animat_options=animat,
                                xfrc_names=links, contacts_names=[c for c in spec.contacts_names
                                                                  if c[0] in links])
+
+
+def salamander_box_feet():
+    """SALAMANDER on the ground with box feet (rotated about z by 0.3 rad) and a box trunk segment:
+    plane-box contacts, the eight corners of mjc_PlaneBox."""
+    spec = models.salamander()
+    x = spec.mjcf
+    n_feet = x.count('type="sphere" size="0.01 0.01 0.01" pos="0.0 0.0 -0.04" quat="1.0 0.0 0.0 0.0" friction=')
+    assert n_feet == 4, n_feet
+    x = x.replace('type="sphere" size="0.01 0.01 0.01" pos="0.0 0.0 -0.04" quat="1.0 0.0 0.0 0.0"',
+                  'type="box" size="0.014 0.009 0.01" pos="0.0 0.0 -0.04" '
+                  'quat="0.9887710779360422 0.0 0.0 0.14943813247359922"')
+    old = ('type="capsule" size="0.020000000000000004 0.04 0.0" pos="0.04 0.0 0.0" '
+           'quat="0.7071067811865476 0.0 0.7071067811865475 0.0"')
+    assert x.count(old) == 2, x.count(old)
+    x = x.replace(old, 'type="box" size="0.05 0.02 0.018" pos="0.04 0.0 0.0" quat="1.0 0.0 0.0 0.0"')
+    return dataclasses.replace(spec, name='salamander_box', mjcf=x)
