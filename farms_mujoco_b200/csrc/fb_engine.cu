@@ -105,9 +105,9 @@ fb_fast_kernel(const __grid_constant__ FbFastParams Q) {
                        P.fast_scratch + (size_t)wid*(SLIM ? P.m.X.n_scratch_slim : P.m.X.n_scratch)*BLK + lane,
                        valid ? env : 0);
   /* full warps move their state through a shared-memory tile (coalesced); a partial last
-   * warp, or a model whose state rows do not fit the tile (always so in the SLIM layout), uses
-   * per-thread accesses */
-  const int coop = !SLIM && BLK == 32 && P.m.X.coop_io && (wid + 1)*BLK <= P.n_envs;
+   * warp, or a model whose state rows do not fit the tile, uses per-thread accesses (the SLIM
+   * layout's smaller blocks take the rows in two phases) */
+  const int coop = BLK == 32 && (wid + 1)*BLK <= P.n_envs ? (SLIM ? 2*P.m.X.coop_io2 : P.m.X.coop_io) : 0;
   const int done = st.template run_t<(WPB > 1)>(coop, lane, valid);
   if (valid && done < P.n_steps) {
     P.steps_done[env] = done;

@@ -293,28 +293,9 @@ FB_UNROLL
     *trq_log = lsum;
   }
 
-  /* State enters and leaves through a shared-memory tile when the block is a full warp: the
-   * warp copies the contiguous [32 envs][n] blocks of qpos / qvel / ctrl / xfrc_applied with
-   * coalesced accesses and every thread then picks its own row from the tile (the body blocks
-   * are not live outside the step loop).  coop = 0: plain per-thread global accesses. */
-  FB_MEM void load_state(int coop, int lane) {
-    const int nq = m.nq, nv = m.nv, nu = m.nu > 0 ? m.nu : 1, nx = 6*m.nbody;
-    const float *gq = P.qpos + (size_t)env*nq, *gv = P.qvel + (size_t)env*nv;
-    const float *gx = P.xfrc_applied + (size_t)env*nx;
-    const float *g_ctrl = P.ctrl + (size_t)env*nu;
-#ifndef FB_HOST_EMU
-    if (coop) {
-      float *tile = s - lane;
-      const size_t e0 = (size_t)(env - lane);
-      for (int i = lane; i < 32*nq; i += 32) tile[i] = P.qpos[e0*nq + i];
-      for (int i = lane; i < 32*nv; i += 32) tile[32*nq + i] = P.qvel[e0*nv + i];
-      for (int i = lane; i < 32*nu; i += 32) tile[32*(nq + nv) + i] = P.ctrl[e0*nu + i];
-      for (int i = lane; i < 32*nx; i += 32) tile[32*(nq + nv + nu) + i] = P.xfrc_applied[e0*nx + i];
-      __syncwarp();
-      gq = tile + lane*nq; gv = tile + 32*nq + lane*nv;
-      g_ctrl = tile + 32*(nq + nv) + lane*nu; gx = tile + 32*(nq + nv + nu) + lane*nx;
-    }
-#endif
+  /* joint half of load_state: root state into registers, q / qd and the constant part of the
+   * actuation of every joint into the scratch */
+  FB_MEM void load_joints(const float *gq, const float *gv, const float *g_ctrl) {
     for (int b = 1; b < m.nbody; b++) {
       const FastRec &rc = rec[b];
       float *pg = gblock(b);
@@ -343,25 +324,55 @@ FB_UNROLL
         fb_st_scr(pg + FG_TC*BLK, tc);
         fb_st_scr(pg + FG_TU*BLK, tu);
       }
+    }
+  }
+  FB_MEM void load_wrenches(const float *gx) {
+    for (int b = 1; b < m.nbody; b++) {
+      float *pg = gblock(b);
       for (int k = 0; k < 6; k++) fb_st_scr(pg + (FG_W + k)*BLK, gx[6*b + k]);
     }
+  }
+
+  /* State enters and leaves through a shared-memory tile when the warp is full: the
+   * warp copies the contiguous [32 envs][n] blocks of qpos / qvel / ctrl / xfrc_applied with
+   * coalesced accesses and every thread then picks its own row from the tile (the body blocks
+   * are not live outside the step loop).  coop = 1: one tile holds everything; coop = 2 (SLIM
+   * layout, smaller blocks): joints first, wrenches second; coop = 0: plain per-thread accesses. */
+  FB_MEM void load_state(int coop, int lane) {
+    const int nq = m.nq, nv = m.nv, nu = m.nu > 0 ? m.nu : 1, nx = 6*m.nbody;
+    const float *gq = P.qpos + (size_t)env*nq, *gv = P.qvel + (size_t)env*nv;
+    const float *gx = P.xfrc_applied + (size_t)env*nx;
+    const float *g_ctrl = P.ctrl + (size_t)env*nu;
+#ifndef FB_HOST_EMU
+    if (coop) {
+      float *tile = s - lane;
+      const size_t e0 = (size_t)(env - lane);
+      for (int i = lane; i < 32*nq; i += 32) tile[i] = P.qpos[e0*nq + i];
+      for (int i = lane; i < 32*nv; i += 32) tile[32*nq + i] = P.qvel[e0*nv + i];
+      for (int i = lane; i < 32*nu; i += 32) tile[32*(nq + nv) + i] = P.ctrl[e0*nu + i];
+      if (coop == 1) for (int i = lane; i < 32*nx; i += 32) tile[32*(nq + nv + nu) + i] = P.xfrc_applied[e0*nx + i];
+      __syncwarp();
+      gq = tile + lane*nq; gv = tile + 32*nq + lane*nv;
+      g_ctrl = tile + 32*(nq + nv) + lane*nu; gx = tile + 32*(nq + nv + nu) + lane*nx;
+      if (coop == 2) {
+        load_joints(gq, gv, g_ctrl);
+        __syncwarp();
+        for (int i = lane; i < 32*nx; i += 32) tile[i] = P.xfrc_applied[e0*nx + i];
+        __syncwarp();
+        load_wrenches(tile + lane*nx);
+        __syncwarp();
+        return;
+      }
+    }
+#endif
+    load_joints(gq, gv, g_ctrl);
+    load_wrenches(gx);
 #ifndef FB_HOST_EMU
     if (coop) __syncwarp();      /* the tile becomes the body blocks */
 #endif
   }
 
-  FB_MEM void store_state(long long iteration, int coop, int lane) {
-    const int nq = m.nq, nv = m.nv, nx = 6*m.nbody;
-    float *gq = P.qpos + (size_t)env*nq, *gv = P.qvel + (size_t)env*nv;
-    float *gx = P.xfrc_applied + (size_t)env*nx;
-#ifndef FB_HOST_EMU
-    if (coop) {
-      __syncwarp();              /* every lane is done with its body blocks */
-      float *tile = s - lane;
-      gq = tile + lane*nq; gv = tile + 32*nq + lane*nv; gx = tile + 32*(nq + nv) + lane*nx;
-      for (int k = 0; k < 6; k++) gx[k] = 0.f;      /* the world body carries no wrench */
-    }
-#endif
+  FB_MEM void store_joints(float *gq, float *gv) const {
     for (int b = 1; b < m.nbody; b++) {
       const FastRec &rc = rec[b];
       const float *pg = gblock(b);
@@ -374,8 +385,46 @@ FB_UNROLL
         gq[rc.qa] = fb_ld_scr(pg + FG_Q*BLK);
         gv[rc.da] = fb_ld_scr(pg + FG_QD*BLK);
       }
+    }
+  }
+  FB_MEM void store_wrenches(float *gx) const {
+    for (int b = 1; b < m.nbody; b++) {
+      const float *pg = gblock(b);
       for (int k = 0; k < 6; k++) gx[6*b + k] = fb_ld_scr(pg + (FG_W + k)*BLK);
     }
+  }
+
+  FB_MEM void store_state(long long iteration, int coop, int lane) {
+    const int nq = m.nq, nv = m.nv, nx = 6*m.nbody;
+    float *gq = P.qpos + (size_t)env*nq, *gv = P.qvel + (size_t)env*nv;
+    float *gx = P.xfrc_applied + (size_t)env*nx;
+#ifndef FB_HOST_EMU
+    if (coop == 2) {
+      __syncwarp();              /* every lane is done with its body blocks */
+      float *tile = s - lane;
+      const size_t e0 = (size_t)(env - lane);
+      store_joints(tile + lane*nq, tile + 32*nq + lane*nv);
+      __syncwarp();
+      for (int i = lane; i < 32*nq; i += 32) P.qpos[e0*nq + i] = tile[i];
+      for (int i = lane; i < 32*nv; i += 32) P.qvel[e0*nv + i] = tile[32*nq + i];
+      __syncwarp();
+      gx = tile + lane*nx;
+      for (int k = 0; k < 6; k++) gx[k] = 0.f;      /* the world body carries no wrench */
+      store_wrenches(gx);
+      __syncwarp();
+      for (int i = lane; i < 32*nx; i += 32) P.xfrc_applied[e0*nx + i] = tile[i];
+      P.iteration[env] = iteration;
+      return;
+    }
+    if (coop) {
+      __syncwarp();              /* every lane is done with its body blocks */
+      float *tile = s - lane;
+      gq = tile + lane*nq; gv = tile + 32*nq + lane*nv; gx = tile + 32*(nq + nv) + lane*nx;
+      for (int k = 0; k < 6; k++) gx[k] = 0.f;      /* the world body carries no wrench */
+    }
+#endif
+    store_joints(gq, gv);
+    store_wrenches(gx);
 #ifndef FB_HOST_EMU
     if (coop) {
       __syncwarp();

@@ -124,6 +124,7 @@ struct DevFastLayout {
   int n_scratch;        /* global scratch floats per environment */
   int jrow_std;         /* farms joint row = 18 columns, position 0, velocity 1, torque 11 */
   int coop_io;          /* [32][nq + nv + nu + 6 nbody] fits the warp's shared memory: tiled state I/O */
+  int coop_io2;         /* SLIM layout: [32][nq + nv + nu] and [32][6 nbody] each fit: two-phase tiled state I/O */
   int n_float_slim, n_scratch_slim;   /* SLIM variant of the unconstrained kernel (fb_fast.h) */
   int n_con;            /* global scratch floats per environment of the constrained step (fb_fastc.h) */
   int con_ok;           /* 1 when the per-thread constrained step covers the model (else: team kernel) */
@@ -796,6 +797,7 @@ inline bool fb_build_model(const FbModel *fm, const FbFarms *ff, const FbWaveCon
     X.n_scratch_slim = (FG_NF + 6)*(nb - 1) + 27*nslot;
     X.jrow_std = m.joint_cols == 18 && m.col_jpos == 0 && m.col_jvel == 1 && m.col_jtrq == 11 && m.col_jlim == 16;
     X.coop_io = fm->nq + nv + (nu > 0 ? nu : 1) + 6*nb <= X.n_float;
+    X.coop_io2 = fm->nq + nv + (nu > 0 ? nu : 1) <= X.n_float_slim && 6*nb <= X.n_float_slim;
   }
 
   /* water + units */
