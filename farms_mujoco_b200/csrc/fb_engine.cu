@@ -388,7 +388,7 @@ static int launch(FbHandle *h, int mode, int n_steps, int want_derived) {
     h->fastQ->P = P;
     {
       int wpb = h->fast_block == 32 ? h->fast_wpb : 1;
-      if (h->fast_slim ? (wpb != 4 && wpb != 8) : (wpb != 2 && wpb != 4)) wpb = 1;
+      if (!h->fast_slim || (wpb != 4 && wpb != 8)) wpb = 1;      /* multi-warp blocks: SLIM layout only (measured 3-5 % slower on the regular one) */
       const int warps = (P.n_envs + 31)/32;
       const int wblocks = (warps + wpb - 1)/wpb;
       const size_t bytes = (h->fast_slim ? h->fast_slim_smem_bytes : h->fast_smem_bytes)*(h->fast_block == 32 ? wpb : 1);
@@ -396,8 +396,6 @@ static int launch(FbHandle *h, int mode, int n_steps, int want_derived) {
       else if (h->fast_slim && wpb == 8) fb_fast_kernel<32, 1, 8><<<wblocks, 256, bytes, h->stream>>>(*h->fastQ);
       else if (h->fast_slim && wpb == 4) fb_fast_kernel<32, 1, 4><<<wblocks, 128, bytes, h->stream>>>(*h->fastQ);
       else if (h->fast_slim) fb_fast_kernel<32, 1, 1><<<warps, 32, bytes, h->stream>>>(*h->fastQ);
-      else if (wpb == 4) fb_fast_kernel<32, 0, 4><<<wblocks, 128, bytes, h->stream>>>(*h->fastQ);
-      else if (wpb == 2) fb_fast_kernel<32, 0, 2><<<wblocks, 64, bytes, h->stream>>>(*h->fastQ);
       else fb_fast_kernel<32, 0, 1><<<warps, 32, bytes, h->stream>>>(*h->fastQ);
     }
     h->launches++;
@@ -562,15 +560,7 @@ int fb_create(const FbModel *model, const FbFarms *farms, int n_envs, int device
       }
 #undef FB_SET_SMEM
       if (const char *ev = getenv("FARMS_B200_FAST_WPB")) h->fast_wpb = atoi(ev);
-      if (h->fast_block == 32) {
-        /* multi-warp variants: one block's shared memory is wpb warps' worth */
-        const int b4 = (int)(4*per_thread*32), b2 = (int)(2*per_thread*32);
-        if (ce == cudaSuccess && b4 <= max_smem) ce = cudaFuncSetAttribute(fb_fast_kernel<32, 0, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, b4);
-        if (ce == cudaSuccess) ce = cudaFuncSetAttribute(fb_fast_kernel<32, 0, 4>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-        if (ce == cudaSuccess && b2 <= max_smem) ce = cudaFuncSetAttribute(fb_fast_kernel<32, 0, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, b2);
-        if (ce == cudaSuccess) ce = cudaFuncSetAttribute(fb_fast_kernel<32, 0, 2>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-        if ((h->fast_wpb == 4 && b4 > max_smem) || (h->fast_wpb == 2 && b2 > max_smem)) h->fast_wpb = 1;
-      }
+
       /* SLIM layout: pays when the batch has more warps than the regular layout keeps resident
        * (4 per SM), i.e. when a second warp per scheduler exists to hide latencies behind */
       if (!getenv("FARMS_B200_FAST_SLIM")) h->fast_slim = h->fast_block == 32 && n_envs/32 > 4*sms;
