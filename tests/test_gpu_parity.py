@@ -446,3 +446,36 @@ def test_step_host_pipelined_equals_synchronous(cuda_library):
     for (la, ja), (lb, jb) in zip(rows['sync'], rows['pipelined']):
         assert torch.equal(la, lb) and torch.equal(ja, jb)
     assert rows['sync'][-1][0].abs().sum() > 0
+
+
+@pytest.mark.parametrize('which', ['features', 'fixed_base'])
+def test_slim_layout_variants_and_ctrl_sequence(cuda_library, which, monkeypatch):
+    """SLIM layout on the hand-edited models (slide joint, off-origin anchors, clamps, fixed base)
+    with an uploaded control sequence: bit-identical to the regular layout."""
+    import variant_models
+    from farms_mujoco_b200 import mjcf_subset
+    from farms_mujoco_b200.engine import BatchedPhysics
+    monkeypatch.setenv('FARMS_B200_FAST_BLOCK', '32')
+    spec = variant_models.swimmer8_features() if which == 'features' else variant_models.swimmer8_fixed_base()
+    model = mjcf_subset.parse_mjcf(spec.mjcf)
+    n, n_steps = 75, 7
+    rng = np.random.default_rng(2)
+    first = 7 if which == 'features' else 0
+    qpos0 = np.tile(model.key_qpos, (n, 1))
+    qpos0[:, first:] += rng.uniform(-0.1, 0.1, (n, model.nq - first))
+    qvel0 = rng.uniform(-0.3, 0.3, (n, model.nv))
+    seq = rng.uniform(-0.3, 0.3, (n_steps, n, model.nu)).astype(np.float32)
+    outs = []
+    for slim in (0, 1, 8):
+        physics = BatchedPhysics.from_spec(spec, n, buffer_size=n_steps + 1, library=cuda_library)
+        physics.set_fast_slim(slim)
+        physics.reset(qpos0, qvel0)
+        physics.set_ctrl_sequence(seq)
+        physics.step(3)
+        physics.step(n_steps - 3)
+        outs.append((physics.qpos, physics.qvel, physics.ctrl, physics.log_arrays()))
+    for other in outs[1:]:
+        assert np.array_equal(outs[0][0], other[0]) and np.array_equal(outs[0][1], other[1])
+        assert np.array_equal(outs[0][2], other[2])
+        for kind in ('links', 'joints', 'contacts', 'xfrc'):
+            assert np.array_equal(outs[0][3][kind], other[3][kind]), kind
