@@ -563,7 +563,8 @@ int fb_create(const FbModel *model, const FbFarms *farms, int n_envs, int device
 
       /* SLIM layout: pays when the batch has more warps than the regular layout keeps resident
        * (4 per SM), i.e. when a second warp per scheduler exists to hide latencies behind */
-      if (!getenv("FARMS_B200_FAST_SLIM")) h->fast_slim = h->fast_block == 32 && n_envs/32 > 4*sms;
+      if (!getenv("FARMS_B200_FAST_SLIM"))
+        h->fast_slim = h->fast_block == 32 && n_envs/32 > 4*sms && 8*per_thread*32 > (size_t)max_smem;   /* regular layout: < 8 warps per SM */
       if (h->fast_block != 32) h->fast_slim = 0;
       /* ... in blocks of 8 warps kept in step (4 while that still leaves SMs without a block) */
       if (h->fast_slim && !getenv("FARMS_B200_FAST_WPB")) h->fast_wpb = n_envs/32 >= 8*sms ? 8 : 4;
