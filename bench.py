@@ -397,6 +397,7 @@ def run_b200(args, rank, world, local_rank):
                             if physics.fast_path else 'fb_step_kernel only'),
                 'fast_envs_per_block': physics.fast_path,
                 'fast_slim_layout': bool(physics.fast_slim),
+                'fast_warps_per_block': max(1, int(physics.fast_slim)),
                 'fast_smem_bytes_per_env': physics.fast_smem_bytes_per_env,
                 'handed_over_envs_last_launch': handed_over,
                 'team_lanes': physics.team_lanes, 'team_smem_bytes_per_env': physics.smem_bytes_per_env,
@@ -411,7 +412,7 @@ def run_b200(args, rank, world, local_rank):
                 'bound': 'hbm', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s',
                 'frac': achieved/peak, 'traffic': traffic,
                 'kernel': ((f'fb_fastc_kernel<{physics.fast_path}>' if physics.constraint_path and 2*handed_over > n_local
-                            else f'fb_fast_kernel<{physics.fast_path},{physics.fast_slim}>') if physics.fast_path and
+                            else f'fb_fast_kernel<{physics.fast_path},{int(physics.fast_slim > 0)},{int(physics.fast_slim > 1)}>') if physics.fast_path and
                            (physics.constraint_path or 2*handed_over <= n_local)
                            else f'fb_step_kernel<{physics.team_lanes}>'),
                 'kernel_ms': k_ms,

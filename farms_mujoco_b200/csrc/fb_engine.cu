@@ -86,19 +86,19 @@ struct FbFastParams {
   FastRec rec[FB_FAST_MAXBODY];   /* per-body records, read from the constant bank */
 };
 
-/* BLK environments per warp (32, or 16 in a half-filled warp), WPB warps per block.  WPB > 1:
- * the warps of a block are kept in step by a barrier per physics step (FbFast::run_t). */
-template <int BLK, int SLIM, int WPB>
-__global__ void __launch_bounds__(32*WPB)
+/* BLK environments per warp (32, or 16 in a half-filled warp).  MULTI: blocks of 2..8 warps
+ * (blockDim.x/32) kept in step by a barrier per physics step (FbFast::run_t). */
+template <int BLK, int SLIM, int MULTI>
+__global__ void __launch_bounds__(MULTI ? 256 : 32)
 fb_fast_kernel(const __grid_constant__ FbFastParams Q) {
   extern __shared__ __align__(16) float fb_smem[];
   const FbParams &P = Q.P;
-  const int warp = WPB > 1 ? threadIdx.x >> 5 : 0, lane = WPB > 1 ? threadIdx.x & 31 : threadIdx.x;
-  const int wid = blockIdx.x*WPB + warp;              /* warp index of the launch */
+  const int warp = MULTI ? threadIdx.x >> 5 : 0, lane = MULTI ? threadIdx.x & 31 : threadIdx.x;
+  const int wid = MULTI ? blockIdx.x*(blockDim.x >> 5) + warp : blockIdx.x;   /* warp index of the launch */
   const int env = wid*BLK + lane;
   if (blockIdx.x == 0 && threadIdx.x == 0) P.pending_count[P.parity ^ 1] = 0;   /* for the next launch */
   const int valid = env < P.n_envs;
-  if (WPB == 1 && !valid) return;
+  if (!MULTI && !valid) return;
   const int n_float = SLIM ? P.m.X.n_float_slim : P.m.X.n_float;
   /* L2-resident scratch [warp][field][lane]: compile-time strides, coalesced */
   FbFast<BLK, SLIM> st(P, Q.rec, fb_smem + (size_t)warp*n_float*BLK + lane,
@@ -108,7 +108,7 @@ fb_fast_kernel(const __grid_constant__ FbFastParams Q) {
    * warp, or a model whose state rows do not fit the tile, uses per-thread accesses (the SLIM
    * layout's smaller blocks take the rows in two phases) */
   const int coop = BLK == 32 && (wid + 1)*BLK <= P.n_envs ? (SLIM ? 2*P.m.X.coop_io2 : P.m.X.coop_io) : 0;
-  const int done = st.template run_t<(WPB > 1)>(coop, lane, valid);
+  const int done = st.template run_t<MULTI>(coop, lane, valid);
   if (valid && done < P.n_steps) {
     P.steps_done[env] = done;
     P.pending[atomicAdd(P.pending_count + P.parity, 1)] = env;
@@ -388,15 +388,14 @@ static int launch(FbHandle *h, int mode, int n_steps, int want_derived) {
     h->fastQ->P = P;
     {
       int wpb = h->fast_block == 32 ? h->fast_wpb : 1;
-      if (!h->fast_slim || (wpb != 4 && wpb != 8)) wpb = 1;      /* multi-warp blocks: SLIM layout only (measured 3-5 % slower on the regular one) */
+      if (!h->fast_slim || wpb < 2 || wpb > 8) wpb = 1;      /* multi-warp blocks: SLIM layout only (measured 3-5 % slower on the regular one) */
       const int warps = (P.n_envs + 31)/32;
       const int wblocks = (warps + wpb - 1)/wpb;
       const size_t bytes = (h->fast_slim ? h->fast_slim_smem_bytes : h->fast_smem_bytes)*(h->fast_block == 32 ? wpb : 1);
-      if (h->fast_block == 16) fb_fast_kernel<16, 0, 1><<<fblocks, 16, bytes, h->stream>>>(*h->fastQ);
-      else if (h->fast_slim && wpb == 8) fb_fast_kernel<32, 1, 8><<<wblocks, 256, bytes, h->stream>>>(*h->fastQ);
-      else if (h->fast_slim && wpb == 4) fb_fast_kernel<32, 1, 4><<<wblocks, 128, bytes, h->stream>>>(*h->fastQ);
-      else if (h->fast_slim) fb_fast_kernel<32, 1, 1><<<warps, 32, bytes, h->stream>>>(*h->fastQ);
-      else fb_fast_kernel<32, 0, 1><<<warps, 32, bytes, h->stream>>>(*h->fastQ);
+      if (h->fast_block == 16) fb_fast_kernel<16, 0, 0><<<fblocks, 16, bytes, h->stream>>>(*h->fastQ);
+      else if (h->fast_slim && wpb > 1) fb_fast_kernel<32, 1, 1><<<wblocks, 32*wpb, bytes, h->stream>>>(*h->fastQ);
+      else if (h->fast_slim) fb_fast_kernel<32, 1, 0><<<warps, 32, bytes, h->stream>>>(*h->fastQ);
+      else fb_fast_kernel<32, 0, 0><<<warps, 32, bytes, h->stream>>>(*h->fastQ);
     }
     h->launches++;
     if (con_thread) {
@@ -421,18 +420,19 @@ static int launch(FbHandle *h, int mode, int n_steps, int want_derived) {
 }
 
 #ifndef FB_HOST_EMU
-/* shared-memory attributes of the SLIM variants (1, 4 or 8 warps per block) */
+/* shared-memory attributes of the SLIM variants (one warp per block, or 2..8 kept in step) */
 static int fb_slim_attributes(FbHandle *h, int max_smem) {
   h->fast_slim_smem_bytes = (size_t)h->hm.m.X.n_float_slim*sizeof(float)*32;
   const int b1 = (int)h->fast_slim_smem_bytes;
-  cudaError_t ce = cudaFuncSetAttribute(fb_fast_kernel<32, 1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, b1);
+  int fit = max_smem/b1;                       /* warps of one block that fit an SM's shared memory */
+  if (fit > 8) fit = 8;
+  cudaError_t ce = cudaFuncSetAttribute(fb_fast_kernel<32, 1, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, b1);
+  if (ce == cudaSuccess) ce = cudaFuncSetAttribute(fb_fast_kernel<32, 1, 0>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+  if (ce == cudaSuccess && fit >= 2) ce = cudaFuncSetAttribute(fb_fast_kernel<32, 1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, fit*b1);
   if (ce == cudaSuccess) ce = cudaFuncSetAttribute(fb_fast_kernel<32, 1, 1>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-  if (ce == cudaSuccess && 4*b1 <= max_smem) ce = cudaFuncSetAttribute(fb_fast_kernel<32, 1, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 4*b1);
-  if (ce == cudaSuccess) ce = cudaFuncSetAttribute(fb_fast_kernel<32, 1, 4>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-  if (ce == cudaSuccess && 8*b1 <= max_smem) ce = cudaFuncSetAttribute(fb_fast_kernel<32, 1, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 8*b1);
-  if (ce == cudaSuccess) ce = cudaFuncSetAttribute(fb_fast_kernel<32, 1, 8>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
   if (ce != cudaSuccess) return fail(std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(ce));
-  if ((h->fast_wpb == 8 && 8*b1 > max_smem) || (h->fast_wpb == 4 && 4*b1 > max_smem)) h->fast_wpb = 1;
+  if (h->fast_wpb > fit) h->fast_wpb = fit;
+  if (h->fast_wpb < 2) h->fast_wpb = 1;
   return 0;
 }
 #endif
@@ -555,8 +555,8 @@ int fb_create(const FbModel *model, const FbFarms *farms, int n_envs, int device
       if (ce == cudaSuccess) ce = cudaFuncSetAttribute(K_, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes); \
       if (ce == cudaSuccess) ce = cudaFuncSetAttribute(K_, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
       switch (h->fast_block) {
-        case 16: FB_SET_SMEM((fb_fast_kernel<16, 0, 1>)) FB_SET_SMEM(fb_fastc_kernel<16>) break;
-        default: FB_SET_SMEM((fb_fast_kernel<32, 0, 1>)) FB_SET_SMEM(fb_fastc_kernel<32>) break;
+        case 16: FB_SET_SMEM((fb_fast_kernel<16, 0, 0>)) FB_SET_SMEM(fb_fastc_kernel<16>) break;
+        default: FB_SET_SMEM((fb_fast_kernel<32, 0, 0>)) FB_SET_SMEM(fb_fastc_kernel<32>) break;
       }
 #undef FB_SET_SMEM
       if (const char *ev = getenv("FARMS_B200_FAST_WPB")) h->fast_wpb = atoi(ev);
@@ -566,8 +566,15 @@ int fb_create(const FbModel *model, const FbFarms *farms, int n_envs, int device
       if (!getenv("FARMS_B200_FAST_SLIM"))
         h->fast_slim = h->fast_block == 32 && n_envs/32 > 4*sms && 8*per_thread*32 > (size_t)max_smem;   /* regular layout: < 8 warps per SM */
       if (h->fast_block != 32) h->fast_slim = 0;
-      /* ... in blocks of 8 warps kept in step (4 while that still leaves SMs without a block) */
-      if (h->fast_slim && !getenv("FARMS_B200_FAST_WPB")) h->fast_wpb = n_envs/32 >= 8*sms ? 8 : 4;
+      /* ... in blocks of up to 8 warps kept in step, one block per SM at a time: the launch takes
+       * `rounds` blocks per SM one after the other, and the block size is the smallest that covers
+       * the batch in that many rounds (65,536 environments on 148 SMs: 2 rounds of 7 warps, not
+       * a round of 8 on every SM and a second one on 108 of them) */
+      if (h->fast_slim && !getenv("FARMS_B200_FAST_WPB")) {
+        const int warps = (n_envs + 31)/32, rounds = (warps + 8*sms - 1)/(8*sms);
+        h->fast_wpb = (warps + sms*rounds - 1)/(sms*rounds);
+        if (h->fast_wpb < 4) h->fast_wpb = 4;
+      }
       if (h->fast_slim && fb_slim_attributes(h, max_smem)) { fb_destroy(h); return -1; }
       if (ce != cudaSuccess) { fb_destroy(h); return fail(std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(ce)); }
     }
@@ -992,18 +999,18 @@ int fb_fast_path(FbHandle *h) {
 int fb_fast_smem_bytes_per_env(FbHandle *h) {
   return h ? (int)((h->fast_slim ? h->hm.m.X.n_float_slim : h->hm.m.X.n_float)*sizeof(float)) : 0;
 }
-/* 0: regular layout; else the warps per block of the large-batch (SLIM) layout (1, 4 or 8) */
+/* 0: regular layout; else the warps per block of the large-batch (SLIM) layout (1 .. 8) */
 int fb_fast_slim(FbHandle *h) {
   if (!h || !h->fast_enabled || !h->hm.m.X.ok || !h->fast_slim) return 0;
-  return h->fast_wpb == 4 || h->fast_wpb == 8 ? h->fast_wpb : 1;
+  return h->fast_wpb >= 2 && h->fast_wpb <= 8 ? h->fast_wpb : 1;
 }
 int fb_set_fast_slim(FbHandle *h, int enable) {
   if (!h) return fail("null handle");
-  if (enable != 0 && enable != 1 && enable != 4 && enable != 8) return fail("fb_set_fast_slim: 0, 1, 4 or 8");
+  if (enable < 0 || enable > 8) return fail("fb_set_fast_slim: 0 (regular layout) or 1 .. 8 warps per block");
   h->fast_wpb = enable > 1 ? enable : 1;
 #ifndef FB_HOST_EMU
   if (enable && h->fast_block != 32) return fail("fb_set_fast_slim: needs 32 environments per warp");
-  if (enable && !h->fast_slim_smem_bytes) {
+  if (enable) {
     int max_smem = 0;
     cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, h->device);
     if (fb_slim_attributes(h, max_smem)) return -1;

@@ -445,7 +445,7 @@ class BatchedPhysics:
 
     def set_fast_slim(self, enable):
         """Large-batch layout of the unconstrained kernel (include/farms_b200.h): 0 / False =
-        regular, else 1, 4 or 8 warps per block."""
+        regular, else 1 .. 8 warps per block."""
         self._check(self.lib.fb_set_fast_slim(self._handle, int(enable)))
 
     @property

@@ -262,7 +262,7 @@ int fb_constraint_path(FbHandle *h);
 int fb_fast_smem_bytes_per_env(FbHandle *h);
 /* Large-batch (SLIM) layout of the unconstrained per-thread kernel: pose in shared memory,
  * velocities and accumulation slots in the L2 scratch -> 8 instead of 4 warps of environments per
- * SM, in blocks of `enable` = 1, 4 or 8 warps (4 / 8: kept in step by a barrier per pass so that
+ * SM, in blocks of `enable` = 1 .. 8 warps (2 .. 8: kept in step by a barrier per pass so that
  * they share instruction-cache lines).  fb_create switches it on when the batch has more warps than
  * the regular layout keeps resident (n_envs/32 > 4 x SMs); results are bit-identical to the regular
  * layout.  fb_fast_slim: 0 or the warps per block. */
