@@ -277,16 +277,18 @@ def run_b200(args, rank, world, local_rank):
     e2e = None
     if not args.no_e2e:
         nl, njf = len(spec.links_names), len(spec.joints_names)
-        # two sets of pinned host buffers: the engine's pipelined step_host overlaps the
-        # download of launch i with the kernels of launch i+1 (include/farms_b200.h)
-        ctrl_host = [torch.zeros((n_local, model.nu), dtype=torch.float32).pin_memory() for _ in range(2)]
-        links_host = [torch.empty((n_local, nl, 20), dtype=torch.float32).pin_memory() for _ in range(2)]
+        # three sets of pinned host buffers: the engine's pipelined step_host overlaps the
+        # download of launch i with the kernels of launch i+1 (include/farms_b200.h); the third
+        # set lets the host enqueue launch i+1 (and its ctrl upload) while launch i still runs
+        NSETS = 3
+        ctrl_host = [torch.zeros((n_local, model.nu), dtype=torch.float32).pin_memory() for _ in range(NSETS)]
+        links_host = [torch.empty((n_local, nl, 20), dtype=torch.float32).pin_memory() for _ in range(NSETS)]
         # the joints row comes down as the four columns the path writes (position, velocity,
         # torque, limit force); physics.py:481-524 leaves the other 14 of the 18 zero
         from farms_mujoco_b200.layout import sc
         jcols = [sc.joint_position, sc.joint_velocity, sc.joint_torque, sc.joint_limit_force]
         physics.set_host_joint_columns(jcols)
-        joints_host = [torch.empty((n_local, njf, len(jcols)), dtype=torch.float32).pin_memory() for _ in range(2)]
+        joints_host = [torch.empty((n_local, njf, len(jcols)), dtype=torch.float32).pin_memory() for _ in range(NSETS)]
         physics.set_wave_controller(None, None, None, None)   # ctrl now comes from the host
         acts, amp, freq, lag = wave_controller(spec, model)
         acts_t = torch.as_tensor(np.array(acts))
@@ -309,16 +311,17 @@ def run_b200(args, rank, world, local_rank):
             torch.set_num_threads(max(1, (os.cpu_count() or world)//world))
         checksum = [0.0]
         calls = [0]
+        pending = [None]*NSETS
 
         def one_host():
             # host-side controller of this outer iteration (task.py:288-321 analogue):
             # the same travelling wave, evaluated on the host and uploaded
-            k = calls[0] % 2
+            k = calls[0] % NSETS
             calls[0] += 1
-            if calls[0] > 2:
-                # the buffers of two calls ago are complete once this call is allowed to reuse
+            if pending[k] is not None:
+                # the buffers of NSETS calls ago are complete once this call is allowed to reuse
                 # them: consume the result (every step's rows are read on the host)
-                physics.host_wait_slot(k)
+                physics.host_wait_call(pending[k])
                 checksum[0] += float(links_host[k][0, 0, 0]) + float(joints_host[k][-1, 0, 0])
             t = physics.iteration*model.timestep
             arg = 2*np.pi*freq_t*t - lag_t
@@ -328,10 +331,10 @@ def run_b200(args, rank, world, local_rank):
                 ctrl_view[k].copy_(wave_buf)
             else:
                 ctrl_host[k].index_copy_(1, acts_t, wave_buf)
-            physics.step_host(args.inner, ctrl=ctrl_host[k], links_row=links_host[k],
-                              joints_row=joints_host[k], pipelined=True)
+            pending[k] = physics.step_host(args.inner, ctrl=ctrl_host[k], links_row=links_host[k],
+                                           joints_row=joints_host[k], pipelined=True)
 
-        for _ in range(max(2, args.warmup)):
+        for _ in range(max(NSETS, args.warmup)):
             one_host()
         physics.host_wait()
         barrier()
@@ -343,14 +346,14 @@ def run_b200(args, rank, world, local_rank):
         wall = torch.tensor([time.perf_counter() - t0], device='cuda')
         if world > 1:
             dist.all_reduce(wall, op=dist.ReduceOp.MAX)
-        links_host = links_host[(calls[0] - 1) % 2]
+        links_host = links_host[(calls[0] - 1) % NSETS]
         ctrl_host, joints_host = ctrl_host[0], joints_host[0]
         e2e = {
             'value': env_steps/float(wall.item()), 'unit': 'env-steps/s',
             'h2d_bytes_per_step': int(ctrl_host.numel()*4*world),
             'd2h_bytes_per_step': int((links_host.numel() + joints_host.numel())*4*world),
             'checksum': float(links_host[:, 0, 0].double().sum()) + checksum[0],
-            'pipelined': 'device->host copy of launch i overlaps the kernels of launch i+1 (fb_step_host_async)',
+            'pipelined': 'device->host copy of launch i overlaps the kernels of launch i+1 (fb_step_host_async, three host buffer sets); ctrl is fetched from pinned host memory by the SMs on an upload stream',
             'rows_down': 'last links row [n_envs, n_links, 20] + joints row [n_envs, n_joints, 4 written columns]',
         }
 
@@ -380,6 +383,32 @@ def run_b200(args, rank, world, local_rank):
             # measured DRAM bytes per launch exist for the profiled (workload, batch, steps) only
             traffic = tj.get('by_workload', {}).get(f'{args.model}:{n_local}:{args.inner}', {}).get(
                 'dram_bytes_per_launch')
+        # FP32 side of the roofline ("report both"): arithmetic of the step against the
+        # FFMA throughput measured on this device by the library's own micro-benchmark.  Two
+        # numerators: the oracle's instrumented op count of one mj_step (profiles/oracle_opcount.json,
+        # MuJoCo's CRB + L'DL pipeline in fp64 -- the shared "algorithmic" figure) and the FADD / FMUL /
+        # FFMA the kernel executes (ncu, profiles/; the articulated-body recursion needs fewer).
+        fp32 = None
+        try:
+            from farms_mujoco_b200.engine import measure_fp32_peak
+            fp32_peak = measure_fp32_peak(local_rank)
+            with open(os.path.join(ROOT, 'profiles', 'oracle_opcount.json')) as f:
+                oc = json.load(f)
+            rec = oc['models'].get(args.model)
+            if rec:
+                per_gpu = value/world
+                fp32 = {
+                    'peak_tflops': fp32_peak, 'peak_source': 'fb_measure_fp32_peak (FFMA micro-benchmark, this run)',
+                    'oracle_flop_per_env_step': rec['flop'],
+                    'oracle_equivalent_tflops': per_gpu*rec['flop']*1e-12,
+                    'oracle_equivalent_frac': per_gpu*rec['flop']*1e-12/fp32_peak,
+                    'executed_flop_per_env_step': oc.get('executed_flop_per_env_step', {}).get(args.model),
+                }
+                if fp32['executed_flop_per_env_step']:
+                    fp32['executed_tflops'] = per_gpu*fp32['executed_flop_per_env_step']*1e-12
+                    fp32['executed_frac'] = fp32['executed_tflops']/fp32_peak
+        except (OSError, KeyError, ValueError) as exc:
+            fp32 = {'error': str(exc)}
         out = {
             'metric': METRIC, 'value': value, 'unit': 'env-steps/s', 'n_gpus': world,
             'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': total_ms/args.steps,
@@ -408,6 +437,7 @@ def run_b200(args, rank, world, local_rank):
             'clocks': clocks,
             'e2e': e2e,
             'gpu_launches': int(launches),
+            'fp32': fp32,
             'roofline': {
                 'bound': 'hbm', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s',
                 'frac': achieved/peak, 'traffic': traffic,

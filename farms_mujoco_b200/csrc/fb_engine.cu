@@ -12,9 +12,11 @@
  * so the arithmetic can be checked on the GPU-less development box.  The
  * product never loads that library.
  */
+#include <cstdint>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <ctime>
 #include <new>
 #include <string>
 #include <vector>
@@ -153,6 +155,44 @@ __global__ void fb_gather_rows_kernel(const float *__restrict__ log, long long r
   for (int k = 0; k < vec; k++) dst[k] = src[k];
 }
 
+/* Plain copy by the SMs, 16 bytes per access when both ends allow it.  fb_step_host uses it to
+ * read ctrl straight out of PINNED host memory (mapped under unified addressing): a
+ * cudaMemcpyAsync upload shares the copy-engine queue with the row download of the previous
+ * launch and was measured to wait for it (up + down 7.1 ms per launch against 3.7 either way). */
+__global__ void __launch_bounds__(256) fb_copy_kernel(const float *__restrict__ src, float *__restrict__ dst,
+                                                      long long n, int vec4) {
+  const long long stride = (long long)gridDim.x*blockDim.x, t = (long long)blockIdx.x*blockDim.x + threadIdx.x;
+  if (vec4) {
+    const float4 *s4 = reinterpret_cast<const float4 *>(src);
+    float4 *d4 = reinterpret_cast<float4 *>(dst);
+    const long long n4 = n >> 2;
+    long long i = t;
+    for (; i + 3*stride < n4; i += 4*stride) {          /* four loads in flight per thread */
+      const float4 a = s4[i], b = s4[i + stride], c = s4[i + 2*stride], d = s4[i + 3*stride];
+      d4[i] = a; d4[i + stride] = b; d4[i + 2*stride] = c; d4[i + 3*stride] = d;
+    }
+    for (; i < n4; i += stride) d4[i] = s4[i];
+    for (long long k = (n4 << 2) + t; k < n; k += stride) dst[k] = src[k];
+  } else {
+    for (long long i = t; i < n; i += stride) dst[i] = src[i];
+  }
+}
+
+/* The same for 4-float vectors (the links log) through a shared-memory tile of 32 environments x
+ * 32 vectors: reads run along the environments (512 contiguous bytes per warp, as the log is
+ * laid out), writes along the row (512 contiguous bytes of one environment's dense row). */
+__global__ void __launch_bounds__(256) fb_gather_rows4_kernel(const float4 *__restrict__ log4, long long row, int nvec,
+                                                              long long env_pad, int n_envs, float4 *__restrict__ out4) {
+  __shared__ float4 tile[32][33];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int env0 = blockIdx.x*32, g0 = blockIdx.y*32;
+  for (int g = w; g < 32; g += 8)
+    if (g0 + g < nvec && env0 + lane < n_envs) tile[g][lane] = log4[(row*nvec + g0 + g)*env_pad + env0 + lane];
+  __syncthreads();
+  for (int e = w; e < 32; e += 8)
+    if (env0 + e < n_envs && g0 + lane < nvec) out4[(long long)(env0 + e)*nvec + g0 + lane] = tile[lane][e];
+}
+
 /* selected columns of ring row `row` of every environment -> dense [n_envs][n_items][n_sel] */
 struct FbColSel { int n; int col[32]; };
 __global__ void fb_gather_cols_kernel(const float *__restrict__ log, long long row, int n_items, int n_cols,
@@ -227,7 +267,11 @@ struct FbHandle {
 #ifndef FB_HOST_EMU
   cudaEvent_t ev0, ev1;
   cudaStream_t copy_stream;          /* device->host copies of fb_step_host_async */
-  cudaEvent_t ev_gather, ev_copy[2];  /* copy-done events of the last two pipelined calls */
+  cudaStream_t up_stream;            /* ctrl upload of fb_step_host (SM reads of pinned host memory) */
+  cudaEvent_t ev_up, ev_stage_free;
+  float *ctrl_stage;                 /* [n_envs][nu] landing buffer of the upload, copied to ctrl in stream order */
+  int sms;
+  cudaEvent_t ev_gather, ev_gathered[4], ev_copy[4];  /* copy-done events of the last four pipelined calls (ring) */
   long long host_calls;
 #endif
 };
@@ -382,6 +426,14 @@ static int launch(FbHandle *h, int mode, int n_steps, int want_derived) {
   h->last_ms = 0.f;
 #else
   int blocks = (P.n_envs + h->envs_per_block - 1)/h->envs_per_block;
+  if (h->host_calls > 0) {
+    /* fb_step_host's row gathers run on the copy stream: this launch may overwrite ring rows, so
+     * it waits for the gathers that could still read them -- the latest one when this launch
+     * (or a reset) wraps the ring onto its row, else the one before it */
+    const bool wraps = mode != FB_MODE_STEP || 2LL*n_steps >= (long long)P.ring;
+    const long long dep = h->host_calls - (wraps ? 1 : 2);
+    if (dep >= 0 && cudaStreamWaitEvent(h->stream, h->ev_gathered[dep & 3], 0) != cudaSuccess) return fail(dev_error());
+  }
   cudaEventRecord(h->ev0, h->stream);
   if (use_fast) {
     int fblocks = (P.n_envs + h->fast_block - 1)/h->fast_block;
@@ -437,6 +489,26 @@ static int fb_slim_attributes(FbHandle *h, int max_smem) {
 }
 #endif
 
+#ifndef FB_HOST_EMU
+/* FP32 roof of the device as this path could use it at best: every lane of every scheduler issuing
+ * independent FFMAs from registers (8 chains per thread, 32 warps per SM).  bench.py quotes the
+ * step kernels' arithmetic against this MEASURED figure (BASELINE.md section 2 asks the build for
+ * it; the driver's MEASURED_PEAKS.json holds HBM and bf16 GEMM only). */
+__global__ void __launch_bounds__(256) fb_ffma_peak_kernel(float *out, int iters, float a, float b) {
+  float x0 = threadIdx.x*1e-3f, x1 = x0 + 1.f, x2 = x0 + 2.f, x3 = x0 + 3.f;
+  float x4 = x0 + 4.f, x5 = x0 + 5.f, x6 = x0 + 6.f, x7 = x0 + 7.f;
+  for (int i = 0; i < iters; i++) {
+#pragma unroll
+    for (int u = 0; u < 16; u++) {
+      x0 = fmaf(x0, a, b); x1 = fmaf(x1, a, b); x2 = fmaf(x2, a, b); x3 = fmaf(x3, a, b);
+      x4 = fmaf(x4, a, b); x5 = fmaf(x5, a, b); x6 = fmaf(x6, a, b); x7 = fmaf(x7, a, b);
+    }
+  }
+  const float r = ((x0 + x1) + (x2 + x3)) + ((x4 + x5) + (x6 + x7));
+  if (r == 123.456f) out[0] = r;       /* keeps the chains alive; never true for a = 1, b = 1e-9 */
+}
+#endif
+
 /* ------------------------------------------------------------------ ABI */
 extern "C" {
 
@@ -453,7 +525,12 @@ void fb_destroy(FbHandle *h) {
 #ifndef FB_HOST_EMU
   cudaEventDestroy(h->ev0); cudaEventDestroy(h->ev1);
   cudaStreamSynchronize(h->copy_stream);
-  cudaEventDestroy(h->ev_gather); cudaEventDestroy(h->ev_copy[0]); cudaEventDestroy(h->ev_copy[1]);
+  cudaStreamSynchronize(h->up_stream);
+  cudaEventDestroy(h->ev_up); cudaEventDestroy(h->ev_stage_free);
+  cudaStreamDestroy(h->up_stream);
+  cudaEventDestroy(h->ev_gather);
+  for (auto &e : h->ev_copy) cudaEventDestroy(e);
+  for (auto &e : h->ev_gathered) cudaEventDestroy(e);
   cudaStreamDestroy(h->copy_stream);
   cudaStreamDestroy(h->stream);
   delete h->fastQ;
@@ -496,10 +573,22 @@ int fb_create(const FbModel *model, const FbFarms *farms, int n_envs, int device
   cudaSetDevice(device);
   cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking);
   cudaEventCreate(&h->ev0); cudaEventCreate(&h->ev1);
-  cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking);
+  {
+    /* the small kernels of these two streams (ctrl upload, row gathers) must be dispatched while a
+     * step kernel still has blocks waiting, so they outrank it: highest stream priority */
+    int prio_lo = 0, prio_hi = 0;
+    cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
+    cudaStreamCreateWithPriority(&h->copy_stream, cudaStreamNonBlocking, prio_hi);
+    cudaStreamCreateWithPriority(&h->up_stream, cudaStreamNonBlocking, prio_hi);
+  }
+  cudaEventCreateWithFlags(&h->ev_up, cudaEventDisableTiming);
+  cudaEventCreateWithFlags(&h->ev_stage_free, cudaEventDisableTiming);
+  h->ctrl_stage = nullptr;
+  h->sms = 148;
+  cudaDeviceGetAttribute(&h->sms, cudaDevAttrMultiProcessorCount, device);
   cudaEventCreateWithFlags(&h->ev_gather, cudaEventDisableTiming);
-  cudaEventCreateWithFlags(&h->ev_copy[0], cudaEventDisableTiming);
-  cudaEventCreateWithFlags(&h->ev_copy[1], cudaEventDisableTiming);
+  for (auto &e : h->ev_copy) cudaEventCreateWithFlags(&e, cudaEventDisableTiming);
+  for (auto &e : h->ev_gathered) cudaEventCreateWithFlags(&e, cudaEventDisableTiming);
   h->host_calls = 0;
   if (team_lanes != 0 && team_lanes != 8 && team_lanes != 16 && team_lanes != 32) {
     fb_destroy(h);
@@ -867,20 +956,79 @@ int fb_export_farms(FbHandle *h, int env, double *links, double *joints, double 
   return 0;
 }
 
-/* Shared body of fb_step_host / fb_step_host_async.  Asynchronous form: the row gathers run on
- * the handle's stream after the step kernels, the two device->host copies on a second (copy)
- * stream, so the transfer of launch i overlaps the kernels of launch i+1; the single pair of
- * gather buffers is protected by the copy-done event, waited for right before the next gathers. */
+#ifndef FB_HOST_EMU
+/* FARMS_B200_TRACE=1: device timeline of the pipelined host step (timing events on the three
+ * streams of each call, printed by fb_host_wait); a debugging aid, off by default */
+struct FbTraceCall { cudaEvent_t e[6]; double host_ms; };
+static std::vector<FbTraceCall> g_trace;
+static cudaEvent_t g_trace_t0;
+static int g_trace_on = -1;
+static double host_now_ms() {
+  timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts);
+  return ts.tv_sec*1e3 + ts.tv_nsec*1e-6;
+}
+static void trace_mark(int slot, cudaStream_t st) {
+  if (g_trace_on != 1) return;
+  cudaEventCreate(&g_trace.back().e[slot]);
+  cudaEventRecord(g_trace.back().e[slot], st);
+}
+#endif
+
+/* Shared body of fb_step_host / fb_step_host_async.  Asynchronous form: ctrl comes in on the upload
+ * stream (SM reads of pinned host memory), the step kernels run on the handle's stream, the row
+ * gathers and the two device->host copies on the copy stream, so the upload of launch i+1 and
+ * the transfer of launch i overlap the kernels of launch i+1. */
 static int step_host_impl(FbHandle *h, const float *ctrl, const float *qpos, const float *qvel,
                           int n_steps, float *links_row, float *joints_row, bool wait) {
   if (!h) return fail("null handle");
   FbParams &P = h->P;
   const DevModel &m = h->hm.m;
   const size_t n = (size_t)P.n_envs;
+#ifndef FB_HOST_EMU
+  if (g_trace_on < 0) g_trace_on = getenv("FARMS_B200_TRACE") ? 1 : 0;
+  if (g_trace_on == 1) {
+    if (g_trace.empty()) { cudaEventCreate(&g_trace_t0); cudaEventRecord(g_trace_t0, h->stream); }
+    g_trace.push_back(FbTraceCall());
+    for (auto &e : g_trace.back().e) e = nullptr;
+    g_trace.back().host_ms = host_now_ms();
+    trace_mark(0, h->stream);
+  }
+  bool ctrl_done = false;
+  if (ctrl && m.nu > 0) {
+    /* pinned (registered) host memory: the SMs fetch it on the upload stream while the previous
+     * launch is still running; the launch stream then takes it over with a device copy */
+    cudaPointerAttributes pa;
+    if (cudaPointerGetAttributes(&pa, ctrl) == cudaSuccess && pa.type == cudaMemoryTypeHost && pa.devicePointer) {
+      const long long nf = (long long)n*m.nu;
+      if (!h->ctrl_stage && alloc_arr(h, &h->ctrl_stage, (size_t)nf)) return fail("out of device memory (ctrl staging)");
+      const float *src = static_cast<const float *>(pa.devicePointer);
+      const int v4 = ((reinterpret_cast<uintptr_t>(src) | reinterpret_cast<uintptr_t>(h->ctrl_stage) |
+                       reinterpret_cast<uintptr_t>(P.ctrl)) & 15) == 0;
+      if (cudaStreamWaitEvent(h->up_stream, h->ev_stage_free, 0) != cudaSuccess) return fail(dev_error());
+      fb_copy_kernel<<<h->sms*2, 256, 0, h->up_stream>>>(src, h->ctrl_stage, nf, v4);
+      if (cudaEventRecord(h->ev_up, h->up_stream) != cudaSuccess ||
+          cudaStreamWaitEvent(h->stream, h->ev_up, 0) != cudaSuccess) return fail(dev_error());
+      fb_copy_kernel<<<h->sms*4, 256, 0, h->stream>>>(h->ctrl_stage, P.ctrl, nf, v4);
+      if (cudaEventRecord(h->ev_stage_free, h->stream) != cudaSuccess) return fail(dev_error());
+      h->launches += 2;
+      ctrl_done = true;
+    } else {
+      cudaGetLastError();               /* pageable memory: cudaPointerGetAttributes may flag it */
+    }
+  }
+  if (ctrl && m.nu > 0 && !ctrl_done && h2d(P.ctrl, ctrl, n*m.nu*sizeof(float), h->stream)) return fail(dev_error());
+#else
   if (ctrl && m.nu > 0 && h2d(P.ctrl, ctrl, n*m.nu*sizeof(float), h->stream)) return fail(dev_error());
+#endif
   if (qpos && h2d(P.qpos, qpos, n*m.nq*sizeof(float), h->stream)) return fail(dev_error());
   if (qvel && h2d(P.qvel, qvel, n*m.nv*sizeof(float), h->stream)) return fail(dev_error());
+#ifndef FB_HOST_EMU
+  trace_mark(1, h->stream);
+#endif
   if (launch(h, FB_MODE_STEP, n_steps, 0)) return -1;
+#ifndef FB_HOST_EMU
+  trace_mark(2, h->stream);
+#endif
   long long row = h->it % P.ring;
   const int lf = m.n_links*20, jf = m.n_joints*(h->joint_sel_n > 0 ? h->joint_sel_n : m.joint_cols);
 #ifdef FB_HOST_EMU
@@ -900,15 +1048,21 @@ static int step_host_impl(FbHandle *h, const float *ctrl, const float *qpos, con
 #else
   const bool want_links = links_row && lf, want_joints = joints_row && jf;
   if (want_links || want_joints) {
-    /* the previous call's copies must have left the gather buffers */
-    const int slot = (int)(h->host_calls & 1);
-    if (h->host_calls > 0 && cudaStreamWaitEvent(h->stream, h->ev_copy[slot ^ 1], 0) != cudaSuccess)
-      return fail(dev_error());
+    /* gathers and copies on the copy stream, behind this call's kernels: the launch stream goes
+     * straight on to the next call's kernels (launch() orders them against these gathers); the
+     * single pair of gather buffers is safe because the copy stream runs call by call */
+    const int slot = (int)(h->host_calls & 3);
     h->host_calls++;
+    cudaStream_t cs = h->copy_stream;
+    if (cudaEventRecord(h->ev_gather, h->stream) != cudaSuccess ||
+        cudaStreamWaitEvent(cs, h->ev_gather, 0) != cudaSuccess) return fail(dev_error());
+    trace_mark(4, cs);
     if (want_links) {
-      long long total = (long long)n*(lf/FB_VEC_LINKS);
-      fb_gather_rows_kernel<<<(unsigned)((total + 255)/256), 256, 0, h->stream>>>(
-          P.log_links, row, lf, FB_VEC_LINKS, P.env_pad, P.n_envs, h->gather_links);
+      const int nvec = lf/FB_VEC_LINKS;
+      static_assert(FB_VEC_LINKS == 4, "fb_gather_rows4_kernel moves float4 vectors");
+      fb_gather_rows4_kernel<<<dim3((unsigned)((n + 31)/32), (unsigned)((nvec + 31)/32)), 256, 0, cs>>>(
+          reinterpret_cast<const float4 *>(P.log_links), row, nvec, P.env_pad, P.n_envs,
+          reinterpret_cast<float4 *>(h->gather_links));
       h->launches++;
     }
     if (want_joints && h->joint_sel_n > 0) {
@@ -916,20 +1070,21 @@ static int step_host_impl(FbHandle *h, const float *ctrl, const float *qpos, con
       sel.n = h->joint_sel_n;
       for (int k = 0; k < 32; k++) sel.col[k] = k < sel.n ? h->joint_sel[k] : 0;
       long long total = (long long)n*jf;
-      fb_gather_cols_kernel<<<(unsigned)((total + 255)/256), 256, 0, h->stream>>>(
+      fb_gather_cols_kernel<<<(unsigned)((total + 255)/256), 256, 0, cs>>>(
           P.log_joints, row, m.n_joints, m.joint_cols, FB_VEC_JOINTS, P.env_pad, P.n_envs, sel, h->gather_joints);
       h->launches++;
     } else if (want_joints) {
       long long total = (long long)n*(jf/FB_VEC_JOINTS);
-      fb_gather_rows_kernel<<<(unsigned)((total + 255)/256), 256, 0, h->stream>>>(
+      fb_gather_rows_kernel<<<(unsigned)((total + 255)/256), 256, 0, cs>>>(
           P.log_joints, row, jf, FB_VEC_JOINTS, P.env_pad, P.n_envs, h->gather_joints);
       h->launches++;
     }
-    if (cudaEventRecord(h->ev_gather, h->stream) != cudaSuccess ||
-        cudaStreamWaitEvent(h->copy_stream, h->ev_gather, 0) != cudaSuccess) return fail(dev_error());
-    if (want_links && d2h(links_row, h->gather_links, (size_t)n*lf*sizeof(float), h->copy_stream)) return fail(dev_error());
-    if (want_joints && d2h(joints_row, h->gather_joints, (size_t)n*jf*sizeof(float), h->copy_stream)) return fail(dev_error());
-    if (cudaEventRecord(h->ev_copy[slot], h->copy_stream) != cudaSuccess) return fail(dev_error());
+    if (cudaEventRecord(h->ev_gathered[slot], cs) != cudaSuccess) return fail(dev_error());
+    trace_mark(3, cs);
+    if (want_links && d2h(links_row, h->gather_links, (size_t)n*lf*sizeof(float), cs)) return fail(dev_error());
+    if (want_joints && d2h(joints_row, h->gather_joints, (size_t)n*jf*sizeof(float), cs)) return fail(dev_error());
+    if (cudaEventRecord(h->ev_copy[slot], cs) != cudaSuccess) return fail(dev_error());
+    trace_mark(5, cs);
   }
   if (wait) {
     if (cudaStreamSynchronize(h->copy_stream) != cudaSuccess) return fail(dev_error());
@@ -953,9 +1108,34 @@ int fb_step_host_async(FbHandle *h, const float *ctrl, const float *qpos, const 
 int fb_host_wait_slot(FbHandle *h, int slot) {
   if (!h) return fail("null handle");
 #ifndef FB_HOST_EMU
-  if (cudaEventSynchronize(h->ev_copy[slot & 1]) != cudaSuccess) return fail(dev_error());
+  long long call = h->host_calls - 1;
+  if ((call & 1) != (slot & 1)) call--;
+  if (call >= 0 && cudaEventSynchronize(h->ev_copy[call & 3]) != cudaSuccess) return fail(dev_error());
 #else
   (void)slot;
+#endif
+  return 0;
+}
+
+/* Calls of fb_step_host / fb_step_host_async that asked for rows so far: the next one has this index. */
+long long fb_host_call_count(FbHandle *h) {
+#ifndef FB_HOST_EMU
+  return h ? h->host_calls : 0;
+#else
+  (void)h; return 0;
+#endif
+}
+
+/* Wait for the copies of pipelined call `call` (index as counted by fb_host_call_count).  The
+ * copies complete in call order, so an index older than the four-event ring waits on a later
+ * call's event, which implies its own. */
+int fb_host_wait_call(FbHandle *h, long long call) {
+  if (!h) return fail("null handle");
+#ifndef FB_HOST_EMU
+  if (call >= h->host_calls) return fail("fb_host_wait_call: no such call yet");
+  if (call >= 0 && cudaEventSynchronize(h->ev_copy[call & 3]) != cudaSuccess) return fail(dev_error());
+#else
+  (void)call;
 #endif
   return 0;
 }
@@ -964,6 +1144,22 @@ int fb_host_wait(FbHandle *h) {
   if (!h) return fail("null handle");
 #ifndef FB_HOST_EMU
   if (cudaStreamSynchronize(h->copy_stream) != cudaSuccess) return fail(dev_error());
+  if (g_trace_on == 1 && !g_trace.empty()) {
+    cudaStreamSynchronize(h->stream);
+    const double h0 = g_trace[0].host_ms;
+    fprintf(stderr, "call  host_enq | main: begin  ctrl_in  kernels | copy: gathered | start  done   (ms)\n");
+    for (size_t c = 0; c < g_trace.size(); c++) {
+      fprintf(stderr, "%4zu  %8.3f |", c, g_trace[c].host_ms - h0);
+      for (int k = 0; k < 6; k++) {
+        float ms = -1.f;
+        if (g_trace[c].e[k]) { cudaEventElapsedTime(&ms, g_trace_t0, g_trace[c].e[k]); cudaEventDestroy(g_trace[c].e[k]); }
+        fprintf(stderr, " %8.3f%s", ms, k == 3 ? " |" : "");
+      }
+      fprintf(stderr, "\n");
+    }
+    cudaEventDestroy(g_trace_t0);
+    g_trace.clear();
+  }
 #endif
   return dev_sync(h->stream) ? fail(std::string("fb_host_wait: ") + dev_error()) : 0;
 }
@@ -1032,6 +1228,38 @@ int fb_last_pending(FbHandle *h, int *count) {
 /* emulation harness only: counters of the per-thread constrained solver */
 void fb_emu_solver_stats(double *stats3) { fb_emu_stats = stats3; }
 #endif
+
+/* measured FFMA throughput of `device` in TFLOP/s (2 flops per FFMA), best of 5 launches */
+int fb_measure_fp32_peak(int device, double *tflops_out) {
+  if (!tflops_out) return fail("null argument");
+#ifdef FB_HOST_EMU
+  (void)device; *tflops_out = 0.0;
+  return fail("fb_measure_fp32_peak: needs a CUDA device");
+#else
+  int sms = 0;
+  if (cudaSetDevice(device) != cudaSuccess ||
+      cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device) != cudaSuccess) return fail(dev_error());
+  float *out = nullptr;
+  cudaEvent_t e0, e1;
+  if (cudaMalloc(&out, sizeof(float)) != cudaSuccess) return fail(dev_error());
+  cudaEventCreate(&e0); cudaEventCreate(&e1);
+  const int blocks = sms*8, iters = 2048;         /* 8 x 256 threads = 64 warps per SM in flight */
+  double best = 0.0;
+  for (int rep = 0; rep < 6; rep++) {
+    cudaEventRecord(e0, 0);
+    fb_ffma_peak_kernel<<<blocks, 256>>>(out, iters, 1.0f, 1e-9f);
+    cudaEventRecord(e1, 0);
+    if (cudaEventSynchronize(e1) != cudaSuccess) { cudaFree(out); return fail(dev_error()); }
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, e0, e1);
+    const double tf = 2.0*8*16*(double)iters*256.0*blocks/(ms*1e-3)*1e-12;
+    if (rep && tf > best) best = tf;              /* first launch: warm-up */
+  }
+  cudaEventDestroy(e0); cudaEventDestroy(e1); cudaFree(out);
+  *tflops_out = best;
+  return 0;
+#endif
+}
 
 int fb_team_lanes(FbHandle *h) { return h ? h->team : 0; }
 int fb_smem_bytes_per_env(FbHandle *h) {

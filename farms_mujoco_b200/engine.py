@@ -52,6 +52,8 @@ ABI_SYMBOLS = {
     'fb_host_wait': (ct.c_int, [_H]),
     'fb_set_host_joint_columns': (ct.c_int, [_H, ct.c_int, ct.POINTER(ct.c_int32)]),
     'fb_host_wait_slot': (ct.c_int, [_H, ct.c_int]),
+    'fb_host_call_count': (ct.c_longlong, [_H]),
+    'fb_host_wait_call': (ct.c_int, [_H, ct.c_longlong]),
     'fb_step_host': (ct.c_int, [_H, ct.c_void_p, ct.c_void_p, ct.c_void_p, ct.c_int, ct.c_void_p,
                                 ct.c_void_p]),
     'fb_step_host_async': (ct.c_int, [_H, ct.c_void_p, ct.c_void_p, ct.c_void_p, ct.c_int, ct.c_void_p,
@@ -66,6 +68,7 @@ ABI_SYMBOLS = {
     'fb_set_fast_slim': (ct.c_int, [_H, ct.c_int]),
     'fb_fast_slim': (ct.c_int, [_H]),
     'fb_last_pending': (ct.c_int, [_H, ct.POINTER(ct.c_int)]),
+    'fb_measure_fp32_peak': (ct.c_int, [ct.c_int, ct.POINTER(ct.c_double)]),
     'fb_team_lanes': (ct.c_int, [_H]),
     'fb_smem_bytes_per_env': (ct.c_int, [_H]),
     'fb_device_ptr_stream': (ct.c_int, [_H, ct.POINTER(ct.c_void_p)]),
@@ -96,6 +99,15 @@ def load_library(path=None):
         raise EngineError('ABI version mismatch')
     _LIBS[path] = lib
     return lib
+
+
+def measure_fp32_peak(device=0, library=None):
+    """Measured FFMA throughput of ``device`` in TFLOP/s (``fb_measure_fp32_peak``)."""
+    lib = load_library(library)
+    out = ct.c_double()
+    if lib.fb_measure_fp32_peak(int(device), ct.byref(out)) != 0:
+        raise EngineError(lib.fb_last_error().decode())
+    return float(out.value)
 
 
 class _DeviceArray:
@@ -401,7 +413,8 @@ class BatchedPhysics:
         """End-to-end call on HOST float32 buffers (pinned recommended): upload
         ctrl/qpos/qvel (each optional), step, download the last links/joints log
         row of every environment.  ``pipelined``: return once enqueued; the download overlaps
-        the next call's kernels (alternate two buffer sets, ``host_wait()`` at the end)."""
+        the next call's kernels (alternate two or more buffer sets, ``host_wait()`` at the end).
+        Returns the call's index for ``host_wait_call`` when rows were asked for."""
         def addr(arr):
             if arr is None:
                 return None
@@ -409,9 +422,11 @@ class BatchedPhysics:
                 return arr.data_ptr()
             return arr.ctypes.data
         fn = self.lib.fb_step_host_async if pipelined else self.lib.fb_step_host
+        call = int(self.lib.fb_host_call_count(self._handle))
         self._check(fn(self._handle, addr(ctrl), addr(qpos), addr(qvel),
                        int(n_steps), addr(links_row), addr(joints_row)))
         self.iteration += int(n_steps)
+        return call if (links_row is not None or joints_row is not None) else None
 
     def set_host_joint_columns(self, columns=None):
         """Columns of the joints row ``step_host`` downloads (``joints_row`` is then
@@ -423,6 +438,10 @@ class BatchedPhysics:
     def host_wait_slot(self, slot):
         """Completion of the copies of the latest pipelined call with index % 2 == slot."""
         self._check(self.lib.fb_host_wait_slot(self._handle, int(slot)))
+
+    def host_wait_call(self, call):
+        """Completion of the copies of the pipelined ``step_host`` that returned ``call``."""
+        self._check(self.lib.fb_host_wait_call(self._handle, int(call)))
 
     def host_wait(self):
         """Completion of every pipelined ``step_host`` issued so far (fb_host_wait)."""

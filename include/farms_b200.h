@@ -239,6 +239,12 @@ int fb_host_wait(FbHandle *h);
 int fb_set_host_joint_columns(FbHandle *h, int n, const int32_t *cols);
 /* completion of the copies of the latest pipelined call whose index (0, 1, 2, ...) % 2 == slot */
 int fb_host_wait_slot(FbHandle *h, int slot);
+/* Deeper pipelines (three or more host buffer sets): fb_host_call_count = the index the next
+ * call that asks for rows will get; fb_host_wait_call = completion of the copies of that call
+ * (copies complete in call order).  Nothing comparable in the reference (its loop is synchronous,
+ * simulation.py:149-161). */
+long long fb_host_call_count(FbHandle *h);
+int fb_host_wait_call(FbHandle *h, long long call);
 
 /* Raw copies between host memory and the engine's device buffers (pointers
  * taken from the views above); for hosts without torch (plain ctypes). */
@@ -271,6 +277,9 @@ int fb_fast_slim(FbHandle *h);
 int fb_last_pending(FbHandle *h, int *count);
 
 /* introspection */
+/* Measured FP32 (FFMA, non-tensor) throughput of `device` in TFLOP/s: the denominator bench.py
+ * quotes the step kernels' arithmetic against (nothing in the reference). */
+int fb_measure_fp32_peak(int device, double *tflops_out);
 int fb_team_lanes(FbHandle *h);
 int fb_smem_bytes_per_env(FbHandle *h);
 int fb_device_ptr_stream(FbHandle *h, void **stream_out);

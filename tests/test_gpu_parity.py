@@ -421,31 +421,46 @@ def test_step_host_pipelined_equals_synchronous(cuda_library):
     spec, model, qpos0, qvel0, ctrl = make_case('salamander_swim', 64)
     nl, nj = len(spec.links_names), len(spec.joints_names)
     rows = {}
-    for mode in ('sync', 'pipelined'):
+    base = torch.as_tensor(ctrl, dtype=torch.float32)
+    for mode, nsets in (('sync', 2), ('pipelined', 2), ('pipelined3', 3)):
         physics = BatchedPhysics.from_spec(spec, 64, buffer_size=8, library=cuda_library)
         physics.reset(qpos0, qvel0)
-        ctrl_host = [torch.as_tensor(ctrl, dtype=torch.float32).pin_memory() for _ in range(2)]
-        links = [torch.zeros((64, nl, 20), dtype=torch.float32).pin_memory() for _ in range(2)]
-        joints = [torch.zeros((64, nj, 18), dtype=torch.float32).pin_memory() for _ in range(2)]
-        got = []
-        for call in range(5):
-            k = call % 2
-            if mode == 'pipelined' and call >= 2:
-                physics.host_wait_slot(k)
+        ctrl_host = [base.clone().pin_memory() for _ in range(nsets)]
+        links = [torch.zeros((64, nl, 20), dtype=torch.float32).pin_memory() for _ in range(nsets)]
+        joints = [torch.zeros((64, nj, 18), dtype=torch.float32).pin_memory() for _ in range(nsets)]
+        got, pending = [], [None]*nsets
+        for call in range(7):
+            k = call % nsets
+            if mode != 'sync' and pending[k] is not None:
+                if nsets == 2:
+                    physics.host_wait_slot(k)
+                else:
+                    physics.host_wait_call(pending[k])
                 got.append((links[k].clone(), joints[k].clone()))
-            physics.step_host(3, ctrl=ctrl_host[k], links_row=links[k], joints_row=joints[k],
-                              pipelined=mode == 'pipelined')
+            ctrl_host[k].copy_(base*(1.0 - 0.1*call))          # a new ctrl per call (pinned: SM upload path)
+            pending[k] = physics.step_host(3, ctrl=ctrl_host[k], links_row=links[k], joints_row=joints[k],
+                                           pipelined=mode != 'sync')
+            assert pending[k] == call
             if mode == 'sync':
                 got.append((links[k].clone(), joints[k].clone()))
-        if mode == 'pipelined':
+        if mode != 'sync':
             physics.host_wait()
-            got.append((links[1].clone(), joints[1].clone()))
-            got.append((links[0].clone(), joints[0].clone()))
+            for call in range(7 - nsets, 7):
+                got.append((links[call % nsets].clone(), joints[call % nsets].clone()))
         rows[mode] = got
-    assert len(rows['sync']) == len(rows['pipelined']) == 5
-    for (la, ja), (lb, jb) in zip(rows['sync'], rows['pipelined']):
-        assert torch.equal(la, lb) and torch.equal(ja, jb)
+    assert len(rows['sync']) == len(rows['pipelined']) == len(rows['pipelined3']) == 7
+    for other in ('pipelined', 'pipelined3'):
+        for (la, ja), (lb, jb) in zip(rows['sync'], rows[other]):
+            assert torch.equal(la, lb) and torch.equal(ja, jb)
     assert rows['sync'][-1][0].abs().sum() > 0
+    assert not torch.equal(rows['sync'][-1][1], rows['sync'][-2][1])
+    # pageable ctrl (plain numpy): the cudaMemcpyAsync path gives the same rows
+    physics = BatchedPhysics.from_spec(spec, 64, buffer_size=8, library=cuda_library)
+    physics.reset(qpos0, qvel0)
+    lrow, jrow = np.zeros((64, nl, 20), np.float32), np.zeros((64, nj, 18), np.float32)
+    for call in range(7):
+        physics.step_host(3, ctrl=np.ascontiguousarray((base*(1.0 - 0.1*call)).numpy()), links_row=lrow, joints_row=jrow)
+    assert np.array_equal(lrow, rows['sync'][-1][0].numpy()) and np.array_equal(jrow, rows['sync'][-1][1].numpy())
 
 
 @pytest.mark.parametrize('which', ['features', 'fixed_base'])
