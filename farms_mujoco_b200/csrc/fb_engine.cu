@@ -267,6 +267,8 @@ struct FbHandle {
 #ifndef FB_HOST_EMU
   cudaEvent_t ev0, ev1;
   cudaStream_t copy_stream;          /* device->host copies of fb_step_host_async */
+  cudaStream_t gather_stream;        /* row gathers of fb_step_host (two buffer pairs: gathers of call i+1 overlap the copies of call i) */
+  float *gather_links2, *gather_joints2;
   cudaStream_t up_stream;            /* ctrl upload of fb_step_host (SM reads of pinned host memory) */
   cudaEvent_t ev_up, ev_stage_free;
   float *ctrl_stage;                 /* [n_envs][nu] landing buffer of the upload, copied to ctrl in stream order */
@@ -526,6 +528,8 @@ void fb_destroy(FbHandle *h) {
   cudaEventDestroy(h->ev0); cudaEventDestroy(h->ev1);
   cudaStreamSynchronize(h->copy_stream);
   cudaStreamSynchronize(h->up_stream);
+  cudaStreamSynchronize(h->gather_stream);
+  cudaStreamDestroy(h->gather_stream);
   cudaEventDestroy(h->ev_up); cudaEventDestroy(h->ev_stage_free);
   cudaStreamDestroy(h->up_stream);
   cudaEventDestroy(h->ev_gather);
@@ -574,12 +578,17 @@ int fb_create(const FbModel *model, const FbFarms *farms, int n_envs, int device
   cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking);
   cudaEventCreate(&h->ev0); cudaEventCreate(&h->ev1);
   {
-    /* the small kernels of these two streams (ctrl upload, row gathers) must be dispatched while a
-     * step kernel still has blocks waiting, so they outrank it: highest stream priority */
+    /* the row gathers must be dispatched while the next step kernel still has blocks waiting, so
+     * their streams outrank it (measured: 3.3 ms behind the step kernel's second round, 0.13 ms
+     * with priority).  The ctrl upload stays at normal priority: it is enqueued a launch ahead and
+     * slips into the tail of the running step kernel; with priority it delays the first round of
+     * the next one (e2e 2.67e8 -> 2.80e8 env-steps/s). */
     int prio_lo = 0, prio_hi = 0;
     cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
     cudaStreamCreateWithPriority(&h->copy_stream, cudaStreamNonBlocking, prio_hi);
-    cudaStreamCreateWithPriority(&h->up_stream, cudaStreamNonBlocking, prio_hi);
+    cudaStreamCreateWithPriority(&h->up_stream, cudaStreamNonBlocking, prio_lo);
+    cudaStreamCreateWithPriority(&h->gather_stream, cudaStreamNonBlocking, prio_hi);
+    h->gather_links2 = h->gather_joints2 = nullptr;
   }
   cudaEventCreateWithFlags(&h->ev_up, cudaEventDisableTiming);
   cudaEventCreateWithFlags(&h->ev_stage_free, cudaEventDisableTiming);
@@ -1048,12 +1057,20 @@ static int step_host_impl(FbHandle *h, const float *ctrl, const float *qpos, con
 #else
   const bool want_links = links_row && lf, want_joints = joints_row && jf;
   if (want_links || want_joints) {
-    /* gathers and copies on the copy stream, behind this call's kernels: the launch stream goes
-     * straight on to the next call's kernels (launch() orders them against these gathers); the
-     * single pair of gather buffers is safe because the copy stream runs call by call */
-    const int slot = (int)(h->host_calls & 3);
+    /* gathers on the gather stream behind this call's kernels, copies on the copy stream behind
+     * the gathers: the launch stream goes straight on to the next call's kernels (launch() orders
+     * them against these gathers), and two pairs of gather buffers let the gathers of this call
+     * run while the copies of the previous one are still on the bus */
+    const int slot = (int)(h->host_calls & 3), pair = (int)(h->host_calls & 1);
+    if (pair && !h->gather_links2) {
+      if (alloc_arr(h, &h->gather_links2, n*m.n_links*20) || alloc_arr(h, &h->gather_joints2, n*m.n_joints*m.joint_cols))
+        return fail("out of device memory (second pair of gather buffers)");
+    }
+    float *g_links = pair ? h->gather_links2 : h->gather_links, *g_joints = pair ? h->gather_joints2 : h->gather_joints;
+    cudaStream_t cs = h->gather_stream;
+    /* this pair of gather buffers was last used two calls ago: its copies must have left */
+    if (h->host_calls >= 2 && cudaStreamWaitEvent(cs, h->ev_copy[(slot + 2) & 3], 0) != cudaSuccess) return fail(dev_error());
     h->host_calls++;
-    cudaStream_t cs = h->copy_stream;
     if (cudaEventRecord(h->ev_gather, h->stream) != cudaSuccess ||
         cudaStreamWaitEvent(cs, h->ev_gather, 0) != cudaSuccess) return fail(dev_error());
     trace_mark(4, cs);
@@ -1062,7 +1079,7 @@ static int step_host_impl(FbHandle *h, const float *ctrl, const float *qpos, con
       static_assert(FB_VEC_LINKS == 4, "fb_gather_rows4_kernel moves float4 vectors");
       fb_gather_rows4_kernel<<<dim3((unsigned)((n + 31)/32), (unsigned)((nvec + 31)/32)), 256, 0, cs>>>(
           reinterpret_cast<const float4 *>(P.log_links), row, nvec, P.env_pad, P.n_envs,
-          reinterpret_cast<float4 *>(h->gather_links));
+          reinterpret_cast<float4 *>(g_links));
       h->launches++;
     }
     if (want_joints && h->joint_sel_n > 0) {
@@ -1071,18 +1088,20 @@ static int step_host_impl(FbHandle *h, const float *ctrl, const float *qpos, con
       for (int k = 0; k < 32; k++) sel.col[k] = k < sel.n ? h->joint_sel[k] : 0;
       long long total = (long long)n*jf;
       fb_gather_cols_kernel<<<(unsigned)((total + 255)/256), 256, 0, cs>>>(
-          P.log_joints, row, m.n_joints, m.joint_cols, FB_VEC_JOINTS, P.env_pad, P.n_envs, sel, h->gather_joints);
+          P.log_joints, row, m.n_joints, m.joint_cols, FB_VEC_JOINTS, P.env_pad, P.n_envs, sel, g_joints);
       h->launches++;
     } else if (want_joints) {
       long long total = (long long)n*(jf/FB_VEC_JOINTS);
       fb_gather_rows_kernel<<<(unsigned)((total + 255)/256), 256, 0, cs>>>(
-          P.log_joints, row, jf, FB_VEC_JOINTS, P.env_pad, P.n_envs, h->gather_joints);
+          P.log_joints, row, jf, FB_VEC_JOINTS, P.env_pad, P.n_envs, g_joints);
       h->launches++;
     }
     if (cudaEventRecord(h->ev_gathered[slot], cs) != cudaSuccess) return fail(dev_error());
     trace_mark(3, cs);
-    if (want_links && d2h(links_row, h->gather_links, (size_t)n*lf*sizeof(float), cs)) return fail(dev_error());
-    if (want_joints && d2h(joints_row, h->gather_joints, (size_t)n*jf*sizeof(float), cs)) return fail(dev_error());
+    cs = h->copy_stream;
+    if (cudaStreamWaitEvent(cs, h->ev_gathered[slot], 0) != cudaSuccess) return fail(dev_error());
+    if (want_links && d2h(links_row, g_links, (size_t)n*lf*sizeof(float), cs)) return fail(dev_error());
+    if (want_joints && d2h(joints_row, g_joints, (size_t)n*jf*sizeof(float), cs)) return fail(dev_error());
     if (cudaEventRecord(h->ev_copy[slot], cs) != cudaSuccess) return fail(dev_error());
     trace_mark(5, cs);
   }
