@@ -224,3 +224,25 @@ def test_plane_box_corners():
         span = pos[sel][:, :2].max(axis=0) - pos[sel][:, :2].min(axis=0)
         cs, sn = np.cos(0.3), np.sin(0.3)
         assert np.allclose(span, [0.028*cs + 0.018*sn, 0.028*sn + 0.018*cs], atol=1e-9)
+
+
+def test_instrumented_op_count_matches_stock_oracle(tmp_path):
+    """oracle/opcount: the oracle compiled with the counting scalar reproduces the stock oracle's
+    bits and reports the committed per-step operation counts (profiles/oracle_opcount.json,
+    BASELINE.md section 3) for the contact-free models, whose count does not depend on the state."""
+    import json
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, os.path.join(root, 'oracle', 'opcount', 'count_ops.py'),
+                          '--steps', '6', '--warm', '2', '--envs', '1'], check=True, capture_output=True, text=True)
+    got = json.loads(out.stdout)['models']
+    with open(os.path.join(root, 'profiles', 'oracle_opcount.json')) as f:
+        committed = json.load(f)['models']
+    for name, rec in got.items():
+        assert rec['same_bits_as_stock_oracle'], name
+    for name in ('swimmer8', 'salamander_swim'):
+        for key in ('add', 'mul', 'div', 'sqrt', 'flop'):
+            assert got[name][key] == committed[name][key], (name, key, got[name][key], committed[name][key])
+    assert got['centipede']['flop'] > got['salamander']['flop'] > got['swimmer8']['flop']
