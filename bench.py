@@ -61,7 +61,7 @@ def parse_args():
 
 
 # ------------------------------------------------------------------ inputs
-from farms_mujoco_b200.sharding import synthetic_inputs, gather_env_statistics  # noqa: E402
+from farms_mujoco_b200.sharding import synthetic_inputs, gather_env_statistics, bind_host_to_device  # noqa: E402
 
 
 def wave_controller(spec, model):
@@ -211,6 +211,8 @@ def run_b200(args, rank, world, local_rank):
     if not torch.cuda.is_available():
         raise SystemExit('bench.py: no CUDA device (the engine has no CPU fallback)')
     torch.cuda.set_device(local_rank)
+    # host side of the e2e arm on the GPU's own NUMA node (pinned buffers, controller threads)
+    bound = None if os.environ.get('FARMS_B200_NO_BIND') else bind_host_to_device(local_rank)
     if world > 1:
         dist.init_process_group('nccl', device_id=torch.device('cuda', local_rank))
     spec = models.MODELS[args.model]()
@@ -308,7 +310,7 @@ def run_b200(args, rank, world, local_rank):
                      for c in ctrl_host]
         if world > 1:
             # torchrun pins every rank to one OpenMP thread; the host-side controller may use its share
-            torch.set_num_threads(max(1, (os.cpu_count() or world)//world))
+            torch.set_num_threads(max(1, min(len(bound) if bound else 1 << 30, (os.cpu_count() or world)//world)))
         checksum = [0.0]
         calls = [0]
         pending = [None]*NSETS
@@ -354,6 +356,7 @@ def run_b200(args, rank, world, local_rank):
             'd2h_bytes_per_step': int((links_host.numel() + joints_host.numel())*4*world),
             'checksum': float(links_host[:, 0, 0].double().sum()) + checksum[0],
             'pipelined': 'device->host copy of launch i overlaps the kernels of launch i+1 (fb_step_host_async, three host buffer sets); ctrl is fetched from pinned host memory by the SMs on an upload stream',
+            'host_cpus_bound': len(bound) if bound else None,
             'rows_down': 'last links row [n_envs, n_links, 20] + joints row [n_envs, n_joints, 4 written columns]',
         }
 

@@ -37,6 +37,30 @@ def synthetic_inputs(model, env_ids, seed=1234):
     return qpos, qvel, phase[env_ids]
 
 
+def bind_host_to_device(device):
+    """Pin this process to the CPUs NVML lists as local to GPU ``device`` (its NUMA node), so that
+    the pinned host buffers of ``step_host`` -- allocated after this call, first-touch -- and the
+    host-side controller sit on the socket the GPU's PCIe root hangs off.  On a two-socket box with
+    eight ranks the sensor download otherwise crosses the socket interconnect for half of them.
+    Returns the CPU list it bound to, or None when NVML / the affinity call is unavailable (a
+    single-socket host, a container without the permission): nothing else changes then."""
+    import os
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        handle = pynvml.nvmlDeviceGetHandleByIndex(int(device))
+        ncpu = os.cpu_count() or 1
+        words = pynvml.nvmlDeviceGetCpuAffinity(handle, (ncpu + 63)//64)
+        cpus = {64*w + b for w, word in enumerate(words) for b in range(64) if (int(word) >> b) & 1}
+        cpus &= os.sched_getaffinity(0)
+        if not cpus:
+            return None
+        os.sched_setaffinity(0, cpus)
+        return sorted(cpus)
+    except Exception:  # pylint: disable=broad-except
+        return None
+
+
 def gather_env_statistics(local, world_size):
     """all_gather of a per-env statistics tensor ``[n_local, k]`` -> ``[n_total, k]``.
 
