@@ -60,3 +60,14 @@ def test_two_rank_shards_reproduce_single_process_inputs():
         p.join(timeout=180)
         assert p.exitcode == 0
     assert dict(out) == {0: True, 1: True}
+
+
+def test_bind_host_to_device_is_harmless_without_a_gpu():
+    """No NVML device here: the helper reports None and leaves the affinity alone."""
+    import os
+    from farms_mujoco_b200.sharding import bind_host_to_device
+    before = os.sched_getaffinity(0)
+    bound = bind_host_to_device(0)
+    assert bound is None or set(bound) <= before
+    if bound is None:
+        assert os.sched_getaffinity(0) == before
