@@ -1339,7 +1339,15 @@ struct FbParams {
   float *fast_scratch;            /* [n_scratch][fast_scratch_stride]: second half of the per-thread state */
   long long fast_scratch_stride;
   float *con_scratch;             /* per-thread constrained step (fb_fastc.h): [warp][X.n_con][lane] */
+  /* Last iteration (row index before the ring modulus) at which a constraint-capable kernel wrote
+   * this environment's log row, i.e. at which the contacts row / the joint_limit_force column may
+   * be non-zero.  The unconstrained kernel zero-fills those columns only when the row it
+   * overwrites was last written at or before that iteration (fb_fast.h: log_row_dirty); the
+   * log starts zeroed (fb_create, fb_reset) and nothing else writes it. */
+  long long *con_dirty;
 };
+
+#define FB_NEVER_DIRTY (-(1LL << 60))
 
 /* start of ring row `it` for one environment: floats_per_row = N*C of the kind */
 FB_DEV float *fb_log_row(float *base, long long it, long long floats_per_row, long long env_pad, int vec,
@@ -1405,7 +1413,10 @@ FB_DEV void fb_run_env(const FbParams &P, int env, int k0, float *s, int *si, in
     if (P.mode == FB_MODE_RESET) st.write_derived();
   }
   st.store_state(P.ctrl_seq != 0 && P.mode != FB_MODE_RESET);
-  if (lane == 0) P.iteration[env] = P.mode == FB_MODE_RESET ? 0 : P.it0 + P.n_steps;
+  if (lane == 0) {
+    P.iteration[env] = P.mode == FB_MODE_RESET ? 0 : P.it0 + P.n_steps;
+    if (k0 < n) P.con_dirty[env] = P.mode == FB_MODE_RESET ? 0 : P.it0 + P.n_steps;   /* full rows, constraint columns included */
+  }
 }
 
 #endif /* FB_DEVICE_H_ */

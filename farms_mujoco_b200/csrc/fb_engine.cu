@@ -240,6 +240,7 @@ struct FbHandle {
   size_t fast_slim_smem_bytes;
   size_t fast_smem_bytes;
   long long launch_parity;
+  int log_used;                     /* 0 until the first reset: the log is as fb_create zeroed it */
 #ifndef FB_HOST_EMU
   FbFastParams *fastQ;               /* host staging of the per-thread kernel's parameters */
   FbFastConParams *conQ;             /* ... and of the per-thread constrained kernel's */
@@ -554,7 +555,7 @@ int fb_create(const FbModel *model, const FbFarms *farms, int n_envs, int device
   h->seq_dev = h->seq_stage = nullptr; h->seq_len = h->seq_pos = h->seq_cap = 0;
   h->joint_sel_n = 0;
   h->fast_enabled = 1; h->fast_block = 1; h->fast_smem_bytes = 0; h->launch_parity = 0;
-  h->con_thread = 1;
+  h->con_thread = 1; h->log_used = 0;
   if (const char *ev = getenv("FARMS_B200_CON_THREAD")) h->con_thread = atoi(ev) != 0;
   h->fast_slim = 0; h->fast_slim_smem_bytes = 0; h->fast_wpb = 1;
   if (const char *ev = getenv("FARMS_B200_FAST_SLIM")) h->fast_slim = atoi(ev) != 0;
@@ -692,6 +693,7 @@ int fb_create(const FbModel *model, const FbFarms *farms, int n_envs, int device
   bad |= alloc_arr(h, &P.qpos_spring, n*m.nq); bad |= alloc_arr(h, &P.env_phase, n);
   bad |= alloc_arr(h, &P.flags, n); bad |= alloc_arr(h, &P.iteration, n);
   bad |= alloc_arr(h, &P.pending, n); bad |= alloc_arr(h, &P.pending_count, 2); bad |= alloc_arr(h, &P.steps_done, n);
+  bad |= alloc_arr(h, &P.con_dirty, n);
   P.fast_scratch_stride = (long long)((n + 31) & ~(size_t)31);
   P.fast_scratch = nullptr;
   if (m.X.ok) {
@@ -748,7 +750,18 @@ int fb_reset(FbHandle *h, const double *qpos0, const double *qvel0) {
       v[e*m.nv + i] = qvel0 ? (float)qvel0[e*m.nv + i] : h->hm.F[h->hm.m.o.key_qvel + i];
   }
   FbParams &P = h->P;
-  int bad = h2d(P.qpos, q.data(), q.size()*sizeof(float), h->stream);
+  /* The unconstrained kernel relies on a log whose constraint-only columns start as zeros
+   * (FbParams::con_dirty): fresh from fb_create they are; a later reset clears what the previous
+   * episode left in the contacts and joints rows. */
+  std::vector<long long> never(n, FB_NEVER_DIRTY);
+  int bad = h2d(P.con_dirty, never.data(), n*sizeof(long long), h->stream);
+  if (h->log_used) {
+    const size_t ep = (size_t)P.env_pad*P.ring;
+    bad |= dev_zero(P.log_contacts, ep*m.n_contacts*12*sizeof(float), h->stream);
+    bad |= dev_zero(P.log_joints, ep*m.n_joints*m.joint_cols*sizeof(float), h->stream);
+  }
+  h->log_used = 1;
+  bad |= h2d(P.qpos, q.data(), q.size()*sizeof(float), h->stream);
   bad |= h2d(P.qvel, v.data(), v.size()*sizeof(float), h->stream);
   bad |= dev_zero(P.ctrl, n*(m.nu > 0 ? m.nu : 1)*sizeof(float), h->stream);
   bad |= dev_zero(P.xfrc_applied, n*6*m.nbody*sizeof(float), h->stream);

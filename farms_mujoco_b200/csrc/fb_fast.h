@@ -218,16 +218,29 @@ template <int BLK, int SLIM = 0> struct FbFast {
   float *cs, *csc;
   const CandRec *crec;
   unsigned long long hm[2], hany[2];
+  /* log columns only a constrained step can make non-zero (contacts rows, joint_limit_force) are
+   * zero-filled by an unconstrained step only when the ring row it overwrites may hold such a
+   * value: dirty_c = last iteration a constraint-capable kernel wrote a row of this environment
+   * (FbParams::con_dirty), zfill = verdict for the current step */
+  long long dirty_c;
+  int zfill;
 
   FB_MEM FbFast(const FbParams &P_, const FastRec *rec_, float *s_, float *gs_, int env_)
       : P(P_), m(P_.m), rec(rec_), s(s_), env(env_), gs(gs_), cs(0), csc(0), crec(0) {
     env_phase = P.env_phase[env];
+    dirty_c = P.con_dirty[env];
+    zfill = 1;
     rootpos[0] = rootpos[1] = rootpos[2] = 0.f;
     rqn[0] = 1.f; rqn[1] = rqn[2] = rqn[3] = 0.f;
 FB_UNROLL
     for (int k = 0; k < 13; k++) rt[k] = 0.f;
   }
 
+  /* row of iteration `itr` (before the ring modulus): was it last written at or before dirty_c? */
+  FB_MEM int log_row_dirty(long long itr) const {
+    const long long prev = itr - P.ring;
+    return prev >= 0 && prev <= dirty_c;
+  }
   FB_MEM float *block(int b) const { return s + (m.X.body0 + NF*(b - 1))*BLK; }
   FB_MEM float *gblock(int b) const { return gs + GNF*(b - 1)*BLK; }
   /* accumulation slot i: shared memory, or (SLIM) the scratch behind the body blocks */
@@ -450,6 +463,10 @@ FB_UNROLL
     Quat lastq = {1.f, 0.f, 0.f, 0.f};
     float lasto[3] = {0.f, 0.f, 0.f}, lastv[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
     float lastR[9] = {1.f, 0.f, 0.f, 0.f, 1.f, 0.f, 0.f, 0.f, 1.f};
+    /* SLIM: velocity of the parent of a branch child (its parent is not the previous body), fetched
+     * from the scratch while the previous body is computed -- issued at its use it cost a full L2
+     * round trip per branch (r1aq: 6 % of the stall samples together with its pass-3 twin) */
+    float nvp[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
     for (int b = 1; b < nb; b++) {
       const FastRec &rc0 = rec[b];
       struct { int parent, jtype, flags, pblk, link, chk0, chk1; float dpos[3], bquat[4], axis[3], qpos0, lo, hi, margin, hloc[3], chk[4], jpos[3]; } rc;
@@ -513,9 +530,8 @@ FB_UNROLL
 FB_UNROLL
             for (int k = 0; k < 3; k++) op[k] = pp[(FB_ORG + k)*BLK];
             if (SLIM) {
-              const float *pgp = gs + GNF*(rc.parent - 1)*BLK;
 FB_UNROLL
-              for (int k = 0; k < 6; k++) vp[k] = fb_ld_scr(pgp + (FG_V + k)*BLK);
+              for (int k = 0; k < 6; k++) vp[k] = nvp[k];
             } else {
 FB_UNROLL
               for (int k = 0; k < 6; k++) vp[k] = pp[(FB_VEL + k)*BLK];
@@ -555,6 +571,14 @@ FB_UNROLL
           o[k] = op[k] + r[k];
           v[k] = vp[k] + (jtype == FB_JNT_HINGE ? ax[k]*qd : 0.f);
           v[3 + k] = vp[3 + k] + cr[k] + (jtype == FB_JNT_SLIDE ? ax[k]*qd : 0.f);
+        }
+      }
+      if (SLIM && b + 1 < nb) {
+        const FastRec &rn = rec[b + 1];
+        if (!(rn.flags & FT_TO_CARRY) && rn.parent > 0) {      /* parent <= b - 1: its velocity is stored */
+          const float *pgp = gs + GNF*(rn.parent - 1)*BLK;
+FB_UNROLL
+          for (int k = 0; k < 6; k++) nvp[k] = fb_ld_scr(pgp + (FG_V + k)*BLK);
         }
       }
       pb[(FB_QUAT)*BLK] = q.w; pb[(FB_QUAT + 1)*BLK] = q.x; pb[(FB_QUAT + 2)*BLK] = q.y; pb[(FB_QUAT + 3)*BLK] = q.z;
@@ -896,6 +920,7 @@ FB_UNROLL
     }
     float *pb = block(1) - NF*BLK;
     float *pg = gblock(1) - GNF*BLK;
+    float nap[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};     /* SLIM: acceleration of the parent of the next body when that is a branch child */
     for (int b = 1; b < nb; b++) {
       const FastRec &rc = rec[b];
       FB_PIN_I(rc.jtype); FB_PIN_I(rc.flags); FB_PIN_I(SLIM ? rc.pblk7 : rc.pblk); FB_PIN_I(rc.parent); FB_PIN_I(rc.fj);
@@ -922,6 +947,14 @@ FB_UNROLL
 FB_UNROLL
           for (int k = 0; k < 6; k++) nxv[k] = fb_ld_scr(pn + (FG_V + k)*BLK);
         }
+      }
+      /* a body without an xfrc row keeps the user's wrench: fetched now, stored at the end of the
+       * iteration (the slot held U during this step) */
+      float uwr[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+      if (rc.xr < 0) {
+        const float *gx = P.xfrc_applied + ((size_t)env*m.nbody + b)*6;
+FB_UNROLL
+        for (int k = 0; k < 6; k++) uwr[k] = gx[k];
       }
       const Quat q = {pb[(FB_QUAT)*BLK], pb[(FB_QUAT + 1)*BLK], pb[(FB_QUAT + 2)*BLK], pb[(FB_QUAT + 3)*BLK]};
       float R[9], v[6], a[6];
@@ -960,6 +993,9 @@ FB_UNROLL
           if (flags & FT_TO_CARRY) {
 FB_UNROLL
             for (int k = 0; k < 6; k++) ap[k] = ac[k];
+          } else if (SLIM) {
+FB_UNROLL
+            for (int k = 0; k < 6; k++) ap[k] = nap[k];
           } else {
             const float *so = slot(rc.pslot);
 FB_UNROLL
@@ -1001,14 +1037,21 @@ FB_UNROLL
             const float trq = cx[8]*m.inv_torques, jv = qdn*m.inv_angvel;
             const float lf = CON ? fb_ld_scr(nblock(b) + NB_LIMF*BLK)*m.inv_torques : 0.f;
             const int cl = CON ? m.col_jlim : -1;
+            /* The other columns of the row (physics.py:481-524 leaves 14 of the 18 untouched) are
+             * zero in the log from its allocation on and no kernel writes them; the limit-force pair
+             * is written by constrained steps, and here only over a row that may hold one. */
             if (m.X.jrow_std) {
               /* farms layout: 18 columns, position 0, velocity 1, torque 11, limit force 16 */
               fb_st2(row, qn, jv);
-FB_UNROLL
-              for (int g = 1; g < 9; g++) fb_st2(row + g*ev, g == 8 ? lf : 0.f, g == 5 ? trq : 0.f);
+              fb_st2(row + 5*ev, 0.f, trq);
+              if (CON || zfill) fb_st2(row + 8*ev, lf, 0.f);
             } else {
+              const int cz = CON || zfill ? m.col_jlim : -1;
 #define FB_JCOL(c_) ((c_) == cp ? qn : ((c_) == cv ? jv : ((c_) == ct ? trq : ((c_) == cl ? lf : 0.f))))
-              for (int c = 0; c < cols; c += 2) fb_st2(row + (c/2)*ev, FB_JCOL(c), FB_JCOL(c + 1));
+#define FB_JHAS(c_) ((c_) == cp || (c_) == cv || (c_) == ct || (c_) == cz)
+              for (int c = 0; c < cols; c += 2)
+                if (FB_JHAS(c) || FB_JHAS(c + 1)) fb_st2(row + (c/2)*ev, FB_JCOL(c), FB_JCOL(c + 1));
+#undef FB_JHAS
 #undef FB_JCOL
             }
           }
@@ -1020,6 +1063,19 @@ FB_UNROLL
         float *so = slot(rc.slot);
 FB_UNROLL
         for (int k = 0; k < 6; k++) sl_st(so, k, a[k]);
+      }
+      if (SLIM && b + 1 < nb) {
+        const FastRec &rn = rec[b + 1];
+        if (!(rn.flags & FT_TO_CARRY) && rn.parent > 0) {
+          if (rn.parent == b) {             /* (cannot happen: a child of b that follows it is a carry child) */
+FB_UNROLL
+            for (int k = 0; k < 6; k++) nap[k] = a[k];
+          } else {
+            const float *so = slot(rn.pslot);
+FB_UNROLL
+            for (int k = 0; k < 6; k++) nap[k] = sl_ld(so, k);
+          }
+        }
       }
       /* xfrc row + the wrench applied during the next step (drag.pyx:152-268, 3.4) */
       if (rc.xr >= 0) {
@@ -1059,9 +1115,8 @@ FB_UNROLL
         for (int k = 0; k < 3; k++) { fb_st_scr(pg + (FG_W + k)*BLK, wf[k]); fb_st_scr(pg + (FG_W + 3 + k)*BLK, wt[k]); }
       } else {
         /* user-applied wrench: persistent, re-read (the slot held U during this step) */
-        const float *gx = P.xfrc_applied + ((size_t)env*m.nbody + b)*6;
 FB_UNROLL
-        for (int k = 0; k < 6; k++) fb_st_scr(pg + (FG_W + k)*BLK, gx[k]);
+        for (int k = 0; k < 6; k++) fb_st_scr(pg + (FG_W + k)*BLK, uwr[k]);
       }
     }
     return bad;
@@ -1088,6 +1143,7 @@ FB_UNROLL
       float *row_contacts = fb_log_row(P.log_contacts, row, m.n_contacts*12, P.env_pad, FB_VEC_CONTACTS, e);
       float *row_xfrc = fb_log_row(P.log_xfrc, row, m.n_xfrc*6, P.env_pad, FB_VEC_XFRC, e);
       const float time = (float)(P.it0 + k)*m.timestep;
+      zfill = log_row_dirty(P.it0 + k + 1);
       fb_block_sync<SYNC>();
       if (!dead && pass_poses(row_links)) { kdone = k; dead = 1; }
       if (!SYNC && dead) break;
@@ -1099,8 +1155,10 @@ FB_UNROLL
       fb_block_sync<SYNC>();
       if (dead) continue;
       int bad = pass_accel(aroot, row_joints, row_xfrc);
-      /* no contact is active on this path: the contacts rows are zero (sensors.pyx:140-190) */
-      for (int i = 0; i < m.n_contacts*3; i++) fb_st4(row_contacts + i*(P.env_pad*FB_VEC_CONTACTS), 0.f, 0.f, 0.f, 0.f);
+      /* no contact is active on this path: the contacts rows are zero (sensors.pyx:140-190), which
+       * is what the log holds already unless a constrained step wrote this ring row before */
+      if (zfill)
+        for (int i = 0; i < m.n_contacts*3; i++) fb_st4(row_contacts + i*(P.env_pad*FB_VEC_CONTACTS), 0.f, 0.f, 0.f, 0.f);
       if (bad) FB_FLAG_OR(P.flags + env, FB_FLAG_NONFINITE);
     }
     if (!valid) return n;

@@ -1101,7 +1101,9 @@ FB_UNROLL
       const int store_ctrl = k == n - 1 && m.n_wc > 0;
       int mine = 0, bad;
       if (FB_ANY(maybe)) mine = detect();
+      this->zfill = this->log_row_dirty(P.it0 + k + 1);
       if (FB_ANY(mine)) {
+        this->dirty_c = P.it0 + k + 1;       /* every lane of the warp writes the constraint columns of this row */
         this->template pass_inertia_m<1>(time, aroot, 0, seqk);
         smooth_accel(aroot);
         solve(mine);
@@ -1114,7 +1116,8 @@ FB_UNROLL
       } else {
         this->template pass_inertia_m<0>(time, aroot, store_ctrl, seqk);
         bad = this->template pass_accel_m<0>(aroot, row_joints, row_xfrc);
-        for (int i = 0; i < m.n_contacts*3; i++) fb_st4(row_contacts + i*(P.env_pad*FB_VEC_CONTACTS), 0.f, 0.f, 0.f, 0.f);
+        if (this->zfill)
+          for (int i = 0; i < m.n_contacts*3; i++) fb_st4(row_contacts + i*(P.env_pad*FB_VEC_CONTACTS), 0.f, 0.f, 0.f, 0.f);
       }
       if (bad) FB_FLAG_OR(P.flags + env, FB_FLAG_NONFINITE);
     }
@@ -1123,6 +1126,7 @@ FB_UNROLL
       for (int a = 0; a < m.nu; a++)
         if (MI(ft_actwc, a) < 0) P.ctrl[e*m.nu + a] = last[(long long)a*P.env_pad];
     }
+    P.con_dirty[env] = this->dirty_c;
     this->store_state(P.it0 + n, coop, lane);
   }
 };

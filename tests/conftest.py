@@ -69,9 +69,86 @@ def oracle_rollout(spec, model, tables, n_rows, qpos0, qvel0, ctrl):
     return physics, data, states
 
 
-def scaled_error(a, b):
-    """max |a-b| / max(1, max|b|): absolute below 1, relative above."""
+def scaled_error(a, b, floor=1.0):
+    """max |a - b| / max(max |b|, floor): error relative to the largest magnitude of the array,
+    absolute in units of `floor` when the whole array is smaller than that."""
     a, b = np.asarray(a, dtype=np.float64), np.asarray(b, dtype=np.float64)
     if a.size == 0:
         return 0.0
-    return float(np.abs(a - b).max()/max(1.0, np.abs(b).max()))
+    return float(np.abs(a - b).max()/max(floor, np.abs(b).max()))
+
+
+# ---- parity metric of the oracle comparisons ---------------------------------------------
+# Every array is split into groups of ONE physical quantity (joint angles, root position, link
+# linear velocities, contact forces ...) and each group is measured relative to the largest
+# magnitude that quantity takes in the reference array:
+#       err(group) = max |ours - ref| / max(max |ref|, PARITY_FLOOR),
+# the error of the array being the worst of its groups.  It is a relative error throughout (a
+# 0.1 rad joint angle is held to tol * 0.1 rad, not to tol * 1); the absolute floor only keeps
+# groups that are identically zero in the reference (a limit force while no limit is active)
+# from dividing by zero: there the error is absolute, in units of 1e-2 SI (0.01 rad, 1 cm, 0.01 rad/s, 0.01 N).
+PARITY_FLOOR = 1e-2
+
+
+def _log_groups(kind, n_cols):
+    from farms_mujoco_b200.layout import sc
+    if kind == 'links':
+        return {'com_position': slice(0, 3), 'com_orientation': slice(3, 7), 'urdf_position': slice(7, 10),
+                'urdf_orientation': slice(10, 14), 'velocity_lin': slice(14, 17), 'velocity_ang': slice(17, 20)}
+    if kind == 'joints':
+        named = {'position': sc.joint_position, 'velocity': sc.joint_velocity, 'torque': sc.joint_torque,
+                 'limit_force': sc.joint_limit_force}
+        groups = {k: slice(c, c + 1) for k, c in named.items() if c < n_cols}
+        rest = [c for c in range(n_cols) if c not in named.values()]
+        if rest:
+            groups['unwritten'] = rest           # columns physics.py:481-524 leaves zero
+        return groups
+    if kind == 'contacts':
+        return {'reaction': slice(0, 3), 'friction': slice(3, 6), 'total': slice(6, 9), 'position': slice(9, 12)}
+    if kind == 'xfrc':
+        return {'force': slice(0, 3), 'torque': slice(3, 6)}
+    raise KeyError(kind)
+
+
+def log_errors(kind, ours, ref):
+    """Group-wise relative errors of one log array [..., n_items, n_cols] (see PARITY_FLOOR)."""
+    ours, ref = np.asarray(ours), np.asarray(ref)
+    assert ours.shape == ref.shape, (kind, ours.shape, ref.shape)
+    return {name: scaled_error(ours[..., cols], ref[..., cols], PARITY_FLOOR)
+            for name, cols in _log_groups(kind, ref.shape[-1]).items()}
+
+
+def log_error(kind, ours, ref):
+    return max(log_errors(kind, ours, ref).values(), default=0.0)
+
+
+def state_errors(qpos, qvel, ref_qpos, ref_qvel):
+    """Group-wise relative errors of a state: root position / root quaternion / joint positions and
+    root linear / root angular / joint velocities (free base: nq == nv + 1), else one group each."""
+    qpos, qvel, ref_qpos, ref_qvel = (np.asarray(x, dtype=np.float64) for x in (qpos, qvel, ref_qpos, ref_qvel))
+    if qpos.shape[-1] == qvel.shape[-1] + 1:
+        groups = {'root_position': (qpos[..., :3], ref_qpos[..., :3]), 'root_quaternion': (qpos[..., 3:7], ref_qpos[..., 3:7]),
+                  'joint_position': (qpos[..., 7:], ref_qpos[..., 7:]), 'root_velocity_lin': (qvel[..., :3], ref_qvel[..., :3]),
+                  'root_velocity_ang': (qvel[..., 3:6], ref_qvel[..., 3:6]), 'joint_velocity': (qvel[..., 6:], ref_qvel[..., 6:])}
+    else:
+        groups = {'joint_position': (qpos, ref_qpos), 'joint_velocity': (qvel, ref_qvel)}
+    return {name: scaled_error(a, b, PARITY_FLOOR) for name, (a, b) in groups.items()}
+
+
+def parity_errors(qpos, qvel, logs, ref_qpos, ref_qvel, ref_data, rows=None):
+    """{'qpos': e, 'qvel': e, 'links': e, ...} -- worst group of each array, plus the per-group
+    detail under 'detail'.  `logs[kind]` is [n_rows, n_items, n_cols] of ONE environment."""
+    st = state_errors(qpos, qvel, ref_qpos, ref_qvel)
+    out = {'qpos': max(v for k, v in st.items() if 'velocity' not in k),
+           'qvel': max(v for k, v in st.items() if 'velocity' in k)}
+    detail = dict(st)
+    for kind in ('links', 'joints', 'contacts', 'xfrc'):
+        ref = getattr(ref_data.sensors, kind).array
+        ours = logs[kind]
+        if rows is not None:
+            ref, ours = ref[rows], ours[rows]
+        errs = log_errors(kind, ours, ref)
+        out[kind] = max(errs.values(), default=0.0)
+        detail.update({f'{kind}.{k}': v for k, v in errs.items()})
+    out['detail'] = detail
+    return out

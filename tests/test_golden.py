@@ -7,7 +7,7 @@ import os
 import numpy as np
 import pytest
 
-from conftest import make_case, oracle_rollout, scaled_error
+from conftest import make_case, oracle_rollout, scaled_error, log_error, state_errors
 
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden')
 CASES = [('swimmer8', 5e-4), ('salamander_swim', 5e-4), ('salamander', 5e-3), ('centipede', 5e-3)]
@@ -51,10 +51,10 @@ def _engine_vs_golden(library, name, tol, **kw):
     physics.step(n_rows - 1)
     logs = physics.log_arrays()
     for env in range(2):
-        assert scaled_error(physics.qpos[env], gold[f'qpos_{env}']) < tol
-        assert scaled_error(physics.qvel[env], gold[f'qvel_{env}']) < tol
+        errs = state_errors(physics.qpos[env], physics.qvel[env], gold[f'qpos_{env}'], gold[f'qvel_{env}'])
+        assert max(errs.values()) < tol, errs
         for kind in ('links', 'joints', 'contacts', 'xfrc'):
-            assert scaled_error(logs[kind][env], gold[f'{kind}_{env}']) < tol, kind
+            assert log_error(kind, logs[kind][env], gold[f'{kind}_{env}']) < tol, kind
 
 
 @pytest.mark.parametrize('name,tol', CASES)

@@ -17,7 +17,7 @@ Scaled error = max|a-b| / max(1, max|b|).  Measured values in DESIGN.md.
 import numpy as np
 import pytest
 
-from conftest import make_case, oracle_rollout, scaled_error
+from conftest import make_case, oracle_rollout, scaled_error, parity_errors, log_error
 
 pytestmark = pytest.mark.gpu
 
@@ -51,19 +51,20 @@ def _run(cuda_library, name, n_envs, n_steps, team=0, seed=0, path='team', check
 def _compare(spec, model, physics, qpos0, qvel0, ctrl, envs, n_steps, tol, tol_contacts=None):
     qpos, qvel, logs = physics.qpos, physics.qvel, physics.log_arrays()
     assert not physics.flags.any(), physics.flags
-    worst = {}
+    worst, detail = {}, {}
     for env in envs:
         _, data, states = oracle_rollout(spec, model, physics.tables, n_steps + 1, qpos0[env],
                                          qvel0[env], ctrl[env])
         ref_q, ref_v = states[-1]
-        errs = {'qpos': scaled_error(qpos[env], ref_q), 'qvel': scaled_error(qvel[env], ref_v)}
-        for kind in ('links', 'joints', 'contacts', 'xfrc'):
-            errs[kind] = scaled_error(logs[kind][env], getattr(data.sensors, kind).array)
+        errs = parity_errors(qpos[env], qvel[env], {k: v[env] for k, v in logs.items()}, ref_q, ref_v, data)
+        for key, val in errs.pop('detail').items():
+            detail[key] = max(detail.get(key, 0.0), val)
         for key, val in errs.items():
             worst[key] = max(worst.get(key, 0.0), val)
-    print(spec.name, n_steps, 'steps:', {k: f'{v:.2e}' for k, v in worst.items()})
+    print(spec.name, n_steps, 'steps:', {k: f'{v:.2e}' for k, v in worst.items()},
+          'worst group:', max(detail, key=detail.get))
     for key, val in worst.items():
-        assert val < (tol_contacts if key == 'contacts' and tol_contacts else tol), (key, val, worst)
+        assert val < (tol_contacts if key == 'contacts' and tol_contacts else tol), (key, val, worst, detail)
 
 
 @pytest.mark.parametrize('path', ['fast', 'fast_team', 'team'])
@@ -182,13 +183,13 @@ def test_block_sizes_agree(cuda_library, name, monkeypatch):
 
 @pytest.mark.parametrize('name', ['swimmer8', 'salamander_swim', 'salamander'])
 def test_slim_layout_is_bit_identical(cuda_library, name, monkeypatch):
-    """Large-batch (SLIM) layout of the unconstrained kernel (1, 4, 8 warps per block) vs the
-    regular one; the ground model exercises the hand-over out of multi-warp blocks."""
+    """Large-batch (SLIM) layout of the unconstrained kernel (1, 4, 7, 8 warps per block; 7 is what
+    fb_create picks for 65,536 environments) vs the regular one; the ground model exercises the hand-over out of multi-warp blocks."""
     from farms_mujoco_b200.engine import BatchedPhysics
     monkeypatch.setenv('FARMS_B200_FAST_BLOCK', '32')
     spec, model, qpos0, qvel0, ctrl = make_case(name, 75)
     outs = []
-    for slim in (0, 1, 4, 8):
+    for slim in (0, 1, 4, 7, 8):
         physics = BatchedPhysics.from_spec(spec, 75, buffer_size=9, library=cuda_library)
         if physics.fast_path != 32:
             pytest.skip('SLIM needs 32 environments per warp')
@@ -441,7 +442,7 @@ def test_simulation_layer(cuda_library):
                                        controller=controller)
         for kind in ('links', 'joints', 'contacts', 'xfrc'):
             ours = getattr(sim.task.data.sensors, kind).array[env]
-            assert scaled_error(ours, getattr(data.sensors, kind).array) < 5e-5, kind
+            assert log_error(kind, ours, getattr(data.sensors, kind).array) < 5e-5, kind
 
 
 def test_step_host_joint_columns(cuda_library):
@@ -549,3 +550,91 @@ def test_slim_layout_variants_and_ctrl_sequence(cuda_library, which, monkeypatch
         assert np.array_equal(outs[0][2], other[2])
         for kind in ('links', 'joints', 'contacts', 'xfrc'):
             assert np.array_equal(outs[0][3][kind], other[3][kind]), kind
+
+
+# ---- the BASELINE.json configurations themselves (batch size, layout and block size fb_create
+# picks for them, a ring that wraps), sampled environments against the oracle -------------------
+BENCH_CONFIGS = [
+    # name, envs, ring, launches of 16 steps, tol (state, links / joints / xfrc rows), tol contacts
+    ('salamander_swim', 65536, 64, 6, 2e-5, 2e-5),      # configs[4] at N = 1: SLIM layout, 7 warps per block, ring wraps
+    ('salamander_swim', 16384, 64, 6, 2e-5, 2e-5),      # configs[2]: regular layout
+    ('salamander_swim', 8192, 64, 6, 2e-5, 2e-5),       # configs[4] at N = 8 (65,536 / 8 per GPU)
+    ('swimmer8', 65536, 64, 6, 2e-5, 2e-5),
+    ('salamander', 4096, 16, 2, 1e-4, 5e-4),            # configs[1]: ground contact in every step
+    ('centipede', 8192, 16, 2, 1e-4, 5e-4),             # configs[3]
+]
+
+
+@pytest.mark.parametrize('name,n_envs,ring,launches,tol,tol_contacts', BENCH_CONFIGS)
+def test_bench_configuration_against_oracle(cuda_library, name, n_envs, ring, launches, tol, tol_contacts):
+    """bench.py's own setup (synthetic_inputs, on-device travelling wave, 16 steps per launch, the
+    kernel variant fb_create selects for the batch) at BASELINE.json's sizes: 16 sampled
+    environments -- first / last of the first / last block and warp, plus random ones -- agree with
+    the fp64 oracle over a rollout that wraps the ring."""
+    from farms_mujoco_b200 import models, mjcf_subset
+    from farms_mujoco_b200.engine import BatchedPhysics
+    from farms_mujoco_b200.models import travelling_wave_parameters
+    from farms_mujoco_b200.sharding import synthetic_inputs
+    from oracle.oracle import OraclePhysics
+    from oracle import farms_oracle as fo
+    from conftest import log_errors, state_errors
+    inner = 16
+    spec = models.MODELS[name]()
+    model = mjcf_subset.parse_mjcf(spec.mjcf)
+    qpos0, qvel0, phase = synthetic_inputs(model, np.arange(n_envs))
+    joints, amp, freq, lag = travelling_wave_parameters(spec)
+    acts = [model.actuator_id(f'actuator_position_{j}') for j in joints]
+    physics = BatchedPhysics.from_spec(spec, n_envs, buffer_size=ring, library=cuda_library)
+    physics.set_env_phase(phase)
+    physics.set_wave_controller(acts, amp, freq, lag)
+    physics.reset(qpos0, qvel0)
+    if name == 'salamander_swim' and n_envs == 65536:
+        assert physics.fast_slim == 7, physics.fast_slim      # the variant the bench line is measured on
+    if name == 'salamander_swim' and n_envs <= 16384:
+        assert physics.fast_slim == 0
+    for _ in range(launches):
+        physics.step(inner, sync=False)
+    physics.synchronize()
+    n_steps = inner*launches
+    assert n_steps > ring
+    swimming = name in SWIMMING
+    assert physics.last_pending == (0 if swimming else n_envs)
+    assert not physics.flags.any()
+    rng = np.random.default_rng(5)
+    wpb = max(1, physics.fast_slim)*32
+    sample = {0, 31, 32, wpb - 1, wpb, n_envs - wpb, n_envs - 33, n_envs - 32, n_envs - 1, n_envs//2}
+    sample |= set(int(e) for e in rng.integers(0, n_envs, size=16 - len(sample)))
+    qpos, qvel = physics.qpos, physics.qvel
+    worst = {}
+    for env in sorted(sample):
+        def controller(iteration, time, env=env):
+            ctrl = np.zeros(model.nu)
+            ctrl[acts] = amp*np.sin(2*np.pi*freq*time - lag + phase[env])
+            return ctrl
+        data, states = fo.reference_rollout(OraclePhysics(model), spec, physics.tables, n_steps + 1,
+                                            controller=controller, qpos0=qpos0[env], qvel0=qvel0[env])
+        ours = physics.export_farms(env)
+        for key, val in state_errors(qpos[env], qvel[env], *states[-1]).items():
+            worst[key] = max(worst.get(key, 0.0), val)
+        for kind in ('links', 'joints', 'contacts', 'xfrc'):
+            ref = getattr(data.sensors, kind).array
+            want = np.zeros((ring,) + ref.shape[1:])
+            for it in range(n_steps + 1):
+                want[it % ring] = ref[it]
+            for key, val in log_errors(kind, getattr(ours.sensors, kind).array, want).items():
+                worst[f'{kind}.{key}'] = max(worst.get(f'{kind}.{key}', 0.0), val)
+    print(name, n_envs, 'envs,', n_steps, 'steps:', {k: f'{v:.1e}' for k, v in worst.items() if v > 0})
+    for key, val in worst.items():
+        assert val < (tol_contacts if key.startswith('contacts') else tol), (key, val, worst)
+
+
+@pytest.mark.parametrize('kind', ['limits', 'contacts'])
+def test_ring_wrap(cuda_library, kind):
+    """buffer_size < n_steps, constraint columns dirtied early and clean later."""
+    import fastpath_cases
+    fastpath_cases.check_ring_wrap(cuda_library, kind, n_envs=70)
+
+
+def test_reset_clears_constraint_columns(cuda_library):
+    import fastpath_cases
+    fastpath_cases.check_reset_clears_log(cuda_library, n_envs=70)

@@ -7,7 +7,7 @@ import os
 
 import numpy as np
 
-from conftest import scaled_error
+from conftest import scaled_error, log_error
 from farms_mujoco_b200 import models, mjcf_subset
 from farms_mujoco_b200.control import AnimatController, ControlType, TravellingWaveController
 from farms_mujoco_b200.models import travelling_wave_parameters
@@ -82,7 +82,7 @@ def test_per_iteration_loop_matches_reference_replay(emu_library):
                                             controller=controller)
         for kind in ('links', 'joints', 'contacts', 'xfrc'):
             ours = getattr(sim.task.data.sensors, kind).array[env]
-            assert scaled_error(ours, getattr(data.sensors, kind).array) < 2e-5, kind
+            assert log_error(kind, ours, getattr(data.sensors, kind).array) < 2e-5, kind
         assert scaled_error(sim.physics.qpos[env], states[-1][0]) < 2e-5
 
 
@@ -201,7 +201,7 @@ def test_torque_control_disables_position_actuators(emu_library):
         data, _ = fo.reference_rollout(oracle, spec, sim.physics.tables, n_it, controller=ctrl_of)
         for kind in ('links', 'joints', 'xfrc'):
             ours = getattr(sim.task.data.sensors, kind).array[env]
-            assert scaled_error(ours, getattr(data.sensors, kind).array) < 2e-5, kind
+            assert log_error(kind, ours, getattr(data.sensors, kind).array) < 2e-5, kind
 
 
 def test_open_loop_host_controller_is_fused(emu_library):
