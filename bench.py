@@ -46,6 +46,13 @@ def parse_args():
     ap.add_argument('--envs-per-gpu', type=int, default=65536,
                     help='BASELINE.json config 5 at N = 1: 65,536 swimming salamanders on one B200 (config 3 is '
                          '--envs-per-gpu 16384)')
+    ap.add_argument('--total-envs', type=int, default=0,
+                    help='strong-scaling mode: this many environments in total, sharded evenly over the '
+                         'GPUs (BASELINE.json north_star: 65,536 in total, 8,192 per GPU at N = 8); 0 = weak '
+                         'scaling with --envs-per-gpu on every GPU')
+    ap.add_argument('--no-other-configs', action='store_true',
+                    help="skip the short device-timed runs of BASELINE.json's other configurations "
+                         "(reported under 'extra' at N = 1)")
     ap.add_argument('--inner', type=int, default=16, help='physics steps per launch')
     ap.add_argument('--ring', type=int, default=64, help='log ring rows per env')
     ap.add_argument('--model', default=WORKLOAD)
@@ -123,10 +130,17 @@ class ClockSampler(threading.Thread):
 
 
 # ---------------------------------------------------------------- CPU arm
+CPU_ENVS_PER_CORE = 64
+
+
 def _cpu_worker(args):
-    """One process = one environment of the workload on the oracle port, full
-    reference order per step (sensors -> swimming -> control -> mj_step)."""
-    model_name, seconds, seed = args
+    """One process = one host core advancing ``envs`` environments of the workload by ``inner``
+    physics steps per bench step, on the oracle port: the fp64 C restatement of mj_step plus the
+    farms glue in C (oracle/farms_loop.c: physics2data, cycontacts2data, drag_forces / the swimming
+    callback, the travelling-wave controller), one C call per environment and bench step -- the
+    reference's order per iteration (task.py:168-186, simulation.py:156), no interpreter inside.
+    Returns the wall time of every bench step and the per-stage seconds."""
+    model_name, envs, inner, steps, warmup, ring, first_env = args
     sys.path.insert(0, ROOT)
     from farms_mujoco_b200 import models, mjcf_subset
     from farms_mujoco_b200.data import AnimatData
@@ -135,71 +149,244 @@ def _cpu_worker(args):
     from oracle import farms_oracle as fo
     spec = models.MODELS[model_name]()
     model = mjcf_subset.parse_mjcf(spec.mjcf)
-    physics = OraclePhysics(model)
-    n_rows = 256
-    data = AnimatData.from_sensors_names(model.timestep, n_rows, spec.links_names,
-                                         spec.joints_names, spec.contacts_names, spec.xfrc_names)
+    data = AnimatData.from_sensors_names(model.timestep, 2, spec.links_names, spec.joints_names,
+                                         spec.contacts_names, spec.xfrc_names)
     maps = fo.make_maps(model, data)
     tables = FarmsTables(model, data.sensors, maps['sensors'], spec.animat_options,
                          spec.arena_options, spec.simulation_options.units)
-    handler = fo.SwimmingHandlerOracle(data, tables)
-    units = spec.simulation_options.units
-    qpos, qvel, phase = synthetic_inputs(model, np.array([seed]))
+    qpos, qvel, phase = synthetic_inputs(model, np.arange(first_env, first_env + envs))
     joints, amp, freq, lag = wave_controller(spec, model)
-    acts = np.array(joints)
-    physics.reset(keyframe_id=0)
-    physics.data.qpos[:] = qpos[0]
-    physics.forward()
-    steps, t0 = 0, time.perf_counter()
-    while True:
-        row = steps % n_rows
-        data.sensors.contacts.array[row] = 0
-        data.sensors.joints.array[row] = 0
-        fo.physics2data(physics, row, data, maps, units)
-        if len(tables.swim_links_index):
-            handler.step(row)
-            fo.apply_xfrc(physics, data, row, maps['sensors'], units)
-        t = steps*model.timestep
-        physics.data.ctrl[acts] = amp*np.sin(2*np.pi*freq*t - lag + phase[0])
-        physics.step()
-        steps += 1
-        if steps % 16 == 0 and time.perf_counter() - t0 > seconds:
-            break
-    return steps, time.perf_counter() - t0
+    loops = []
+    for e in range(envs):
+        physics = OraclePhysics(model)
+        physics.reset(keyframe_id=0)
+        physics.data.qpos[:] = qpos[e]
+        physics.data.qvel[:] = qvel[e]
+        physics.forward()
+        loops.append(fo.CompiledRollout(physics, spec, tables, ring, wave=(np.array(joints), amp, freq, lag),
+                                        env_phase=phase[e]))
+    times = []
+    for k in range(warmup + steps):
+        t0 = time.perf_counter()
+        for loop in loops:
+            loop.run(inner, timed=k >= warmup)
+        times.append(time.perf_counter() - t0)
+    stage = np.sum([loop.stage_seconds for loop in loops], axis=0)
+    return times[warmup:], stage.tolist()
 
 
-def cpu_baseline(model_name, seconds, cores=None):
+def cpu_reference_run(model_name, inner, steps, warmup, ring=64, cores=None, envs_per_core=CPU_ENVS_PER_CORE):
+    """The CPU arm: ``cores`` processes x ``envs_per_core`` environments, every bench step advances
+    all of them by ``inner`` physics steps (the same per-environment work as one GPU bench step,
+    on a bounded number of environments)."""
     import multiprocessing as mp
     cores = cores or os.cpu_count() or 1
     ctx = mp.get_context('spawn')
     with ctx.Pool(cores) as pool:
-        res = pool.map(_cpu_worker, [(model_name, seconds, i) for i in range(cores)])
-    rate = sum(s/t for s, t in res)
+        res = pool.map(_cpu_worker, [(model_name, envs_per_core, inner, steps, warmup, ring, i*envs_per_core)
+                                     for i in range(cores)])
+    # the processes run side by side without a barrier between steps: the job is done when the
+    # slowest core is, so a bench step costs the largest per-core total divided by the step count
+    total_s = max(sum(t) for t, _ in res)
+    env_steps = cores*envs_per_core*inner*steps
+    stage = np.sum([st for _, st in res], axis=0)
+    names = ('physics2data+contacts', 'swimming drag + xfrc', 'control', 'mj_step')
     return {
-        'value': rate, 'unit': 'env-steps/s', 'cores': cores, 'kind': 'port',
-        'sample': (f'{cores} processes x 1 env of {model_name}, ~{seconds:.0f} s each, fp64 C oracle '
-                   'step + NumPy physics2data/contacts/drag port (CPU restatement, not MuJoCo)'),
+        'value': env_steps/total_s, 'unit': 'env-steps/s', 'cores': cores, 'kind': 'port',
+        'per_core': env_steps/total_s/cores,
+        'ms_per_step': 1e3*total_s/steps,
+        'stage_share': {n: float(v/stage.sum()) for n, v in zip(names, stage)},
+        'sample': (f'{cores} processes x {envs_per_core} envs of {model_name} x {steps} steps of {inner} physics '
+                   f'steps ({env_steps} env-steps, {float(stage.sum()):.1f} s of CPU work): fp64 C restatement of '
+                   'mj_step + the farms glue in C (oracle/farms_loop.c; CPU port, not MuJoCo)'),
     }
 
 
+def cpu_baseline(model_name, seconds, inner=16, cores=None):
+    """Bounded sample for the GPU line's ``cpu_baseline`` object: about ``seconds`` of wall time."""
+    cores = cores or os.cpu_count() or 1
+    probe = cpu_reference_run(model_name, inner, steps=2, warmup=1, cores=cores, envs_per_core=4)
+    per_step = probe['ms_per_step']*1e-3*CPU_ENVS_PER_CORE/4
+    steps = int(max(3, min(200, seconds/max(per_step, 1e-6))))
+    return cpu_reference_run(model_name, inner, steps=steps, warmup=1, cores=cores)
+
+
 def run_reference(args, rank, world):
+    """``--impl reference``: the reference's CPU path for this metric, timed on the host cores.
+    The reference itself (MuJoCo + dm_control + farms_core) cannot be installed here (DESIGN.md
+    section 2), so this is the oracle port, all host threads, on a bounded sample of the same
+    workload: every bench step advances cores x 64 environments by --inner physics steps."""
     if rank != 0:
         return
-    base = cpu_baseline(args.model, max(2.0, args.cpu_seconds))
-    n_envs = args.envs_per_gpu*args.gpus
+    base = cpu_reference_run(args.model, args.inner, args.steps, max(1, args.warmup), ring=args.ring)
+    n_envs = base['cores']*CPU_ENVS_PER_CORE
     out = {
         'impl': 'reference', 'metric': METRIC, 'value': base['value'], 'unit': 'env-steps/s',
         'n_gpus': args.gpus, 'steps': args.steps, 'warmup': args.warmup,
-        'ms_per_step': 1e3*n_envs*args.inner/base['value'], 'higher_is_better': True,
+        'ms_per_step': base['ms_per_step'], 'higher_is_better': True,
         'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
-        'config': {'workload': f'{args.model} x {n_envs} envs (bounded sample: {base["sample"]})',
-                   'physics_steps_per_step': args.inner},
+        'config': {'workload': (f'{args.model}: bounded sample of {n_envs} envs ({base["cores"]} host cores x '
+                                f'{CPU_ENVS_PER_CORE}), drag+buoyancy, full links/joints/contacts/xfrc log, '
+                                'travelling-wave control'),
+                   'n_envs': n_envs, 'physics_steps_per_step': args.inner},
         'cpu_baseline': base,
         'e2e': {'value': base['value'], 'unit': 'env-steps/s', 'h2d_bytes_per_step': 0,
                 'd2h_bytes_per_step': 0},
         'gpu_launches': 0,
     }
     print(json.dumps(out), file=_JSON_OUT, flush=True)
+
+
+# ---------------------------------------------------------------- roofline helpers
+def csrc_sha():
+    """Hash of the kernel sources: the committed ncu traffic figures are only quoted while the
+    kernels they were captured on are the ones being benchmarked."""
+    import hashlib
+    h = hashlib.sha256()
+    csrc = os.path.join(ROOT, 'farms_mujoco_b200', 'csrc')
+    for name in sorted(os.listdir(csrc)):
+        if name.endswith(('.h', '.cu')):
+            with open(os.path.join(csrc, name), 'rb') as f:
+                h.update(f.read())
+    return h.hexdigest()[:16]
+
+
+def measured_traffic(model_name, n_envs, inner):
+    """DRAM bytes per launch of the dominant kernel from the committed ``ncu --set full`` capture
+    (profiles/traffic.json), or None when there is none for this (workload, batch, steps) or when
+    it was captured on other kernel sources than the ones in the tree."""
+    tpath = os.path.join(ROOT, 'profiles', 'traffic.json')
+    if not os.path.exists(tpath):
+        return None, 'no profiles/traffic.json'
+    with open(tpath) as f:
+        tj = json.load(f)
+    rec = tj.get('by_workload', {}).get(f'{model_name}:{n_envs}:{inner}')
+    if not rec:
+        return None, 'no ncu capture for this (workload, batch, steps)'
+    if rec.get('csrc_sha') != csrc_sha():
+        return None, f'stale: captured on csrc {rec.get("csrc_sha")}, tree is {csrc_sha()}'
+    return rec['dram_bytes_per_launch'], rec.get('source')
+
+
+def written_bytes_per_env_step(spec, constrained):
+    """Bytes the step kernels actually store per env-step (fp32): the columns that carry values.
+    The farms joints row is 18 columns of which physics.py:481-524 writes 4 (two 8-byte pairs here,
+    a third when a limit may be active); contacts rows only exist while a contact is possible.  The
+    other columns are zeros the log holds from its allocation on."""
+    nl, nj = len(spec.links_names), len(spec.joints_names)
+    nc, nx = len(spec.contacts_names), len(spec.xfrc_names)
+    return 80*nl + (24 if constrained else 16)*nj + (48*nc if constrained else 0) + 24*nx
+
+
+def kernel_name(physics, handed_over, n_local):
+    if not physics.fast_path:
+        return f'fb_step_kernel<{physics.team_lanes}>'
+    if 2*handed_over > n_local:
+        return f'fb_fastc_kernel<{physics.fast_path}>' if physics.constraint_path else f'fb_step_kernel<{physics.team_lanes}>'
+    return f'fb_fast_kernel<{physics.fast_path},{int(physics.fast_slim > 0)},{int(physics.fast_slim > 1)}>'
+
+
+def roofline_objects(args_model, spec, physics, n_local, inner, k_ms, per_gpu_rate, handed_over, peaks, device):
+    """The ``roofline`` and ``fp32`` objects of a bench line.  HBM side: algorithmic log bytes per
+    launch / CUDA-event time of the launch against the measured copy bandwidth.  FP32 side
+    ("report both"): the oracle's instrumented op count of one mj_step
+    (profiles/oracle_opcount.json) and the FADD / FMUL / FFMA the kernel executes (ncu) against the
+    FFMA throughput the library measures on this device.  ``bound`` names the roof the kernel
+    sits closer to."""
+    b_log = physics.log_bytes_per_env_step
+    peak = float(peaks.get('hbm_gbs', 6650.0))
+    achieved = n_local*inner*b_log/(k_ms*1e-3)/1e9
+    constrained = 2*handed_over > n_local
+    b_written = written_bytes_per_env_step(spec, constrained)
+    traffic, traffic_source = measured_traffic(args_model, n_local, inner)
+    fp32 = None
+    try:
+        from farms_mujoco_b200.engine import measure_fp32_peak
+        fp32_peak = measure_fp32_peak(device)
+        with open(os.path.join(ROOT, 'profiles', 'oracle_opcount.json')) as f:
+            oc = json.load(f)
+        rec = oc['models'].get(args_model)
+        if rec:
+            fp32 = {
+                'peak_tflops': fp32_peak, 'peak_source': 'fb_measure_fp32_peak (FFMA micro-benchmark, this run)',
+                'oracle_flop_per_env_step': rec['flop'],
+                'oracle_equivalent_tflops': per_gpu_rate*rec['flop']*1e-12,
+                'oracle_equivalent_frac': per_gpu_rate*rec['flop']*1e-12/fp32_peak,
+                'executed_flop_per_env_step': oc.get('executed_flop_per_env_step', {}).get(args_model),
+            }
+            if fp32['executed_flop_per_env_step'] and not constrained:
+                fp32['executed_tflops'] = per_gpu_rate*fp32['executed_flop_per_env_step']*1e-12
+                fp32['executed_frac'] = fp32['executed_tflops']/fp32_peak
+    except (OSError, KeyError, ValueError) as exc:
+        fp32 = {'error': str(exc)}
+    hbm_frac = achieved/peak
+    fp32_frac = (fp32 or {}).get('oracle_equivalent_frac') or 0.0
+    roofline = {
+        'bound': 'hbm' if hbm_frac >= fp32_frac else 'fp32',
+        'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': hbm_frac,
+        'traffic': traffic, 'traffic_source': traffic_source,
+        'kernel': kernel_name(physics, handed_over, n_local),
+        'kernel_ms': k_ms,
+        'algorithmic_bytes_per_env_step': b_log,
+        'written_bytes_per_env_step': b_written,
+        'frac_written_bytes': n_local*inner*b_written/(k_ms*1e-3)/1e9/peak,
+        'fp32_frac_oracle_equivalent': fp32_frac,
+        'peak_source': 'MEASURED_PEAKS.json hbm_gbs (of measured)' if peaks else 'fallback 6650',
+        'note': ('achieved = algorithmic log bytes (B_log, SURVEY 8d: every column of every row) per launch / '
+                 'mean CUDA-event time of a launch on the engine stream; written_bytes counts only the columns '
+                 'that carry values (the constant-zero columns are not stored again); the kernels are '
+                 'issue/latency bound, below both roofs: see profiles/ for issue-slot utilisation'),
+    }
+    return roofline, fp32
+
+
+def short_device_run(name, n_envs, inner, ring, steps, warmup, device, peaks):
+    """Device-timed run of another BASELINE.json configuration on this GPU (no e2e, no CPU arm)."""
+    import ctypes
+    import torch
+    from farms_mujoco_b200 import models, mjcf_subset
+    from farms_mujoco_b200.engine import BatchedPhysics
+    spec = models.MODELS[name]()
+    model = mjcf_subset.parse_mjcf(spec.mjcf)
+    qpos0, qvel0, phase = synthetic_inputs(model, np.arange(n_envs))
+    physics = BatchedPhysics.from_spec(spec, n_envs, buffer_size=ring, device=device)
+    physics.set_env_phase(phase)
+    physics.set_wave_controller(*wave_controller(spec, model))
+    physics.reset(qpos0, qvel0)
+    stream_ptr = ctypes.c_void_p()
+    physics._check(physics.lib.fb_device_ptr_stream(physics._handle, ctypes.byref(stream_ptr)))
+    stream = torch.cuda.ExternalStream(stream_ptr.value, device=device)
+    for _ in range(warmup):
+        physics.step(inner, sync=False)
+    physics.synchronize()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    launches0 = physics.launch_count()
+    with torch.cuda.stream(stream):
+        ev0.record()
+        for _ in range(steps):
+            physics.step(inner, sync=False)
+        ev1.record()
+    physics.synchronize()
+    ms = ev0.elapsed_time(ev1)
+    launches = physics.launch_count() - launches0
+    k_ms = []
+    for _ in range(3):
+        physics.step(inner, sync=True)
+        k_ms.append(physics.last_step_ms())
+    handed_over = physics.last_pending if physics.fast_path else n_envs
+    value = n_envs*inner*steps/(ms*1e-3)
+    roofline, fp32 = roofline_objects(name, spec, physics, n_envs, inner, float(np.mean(k_ms)), value,
+                                      handed_over, peaks, device)
+    flags = physics.flags
+    out = {
+        'workload': f'{name}: {n_envs} envs on 1 GPU, full log, on-device travelling-wave control',
+        'value': value, 'unit': 'env-steps/s', 'ms_per_step': ms/steps, 'steps': steps, 'warmup': warmup,
+        'physics_steps_per_step': inner, 'gpu_launches': int(launches),
+        'handed_over_envs_last_launch': int(handed_over), 'diverged_envs': int(np.count_nonzero(flags & 1)),
+        'roofline': roofline, 'fp32': fp32,
+    }
+    physics.close()
+    return out
 
 
 # ---------------------------------------------------------------- GPU arm
@@ -217,7 +404,12 @@ def run_b200(args, rank, world, local_rank):
         dist.init_process_group('nccl', device_id=torch.device('cuda', local_rank))
     spec = models.MODELS[args.model]()
     model = mjcf_subset.parse_mjcf(spec.mjcf)
-    n_local = args.envs_per_gpu
+    if args.total_envs:
+        if args.total_envs % world:
+            raise SystemExit('--total-envs must be a multiple of the number of GPUs')
+        n_local = args.total_envs//world
+    else:
+        n_local = args.envs_per_gpu
     env_ids = np.arange(rank*n_local, (rank + 1)*n_local)
     qpos0, qvel0, phase = synthetic_inputs(model, env_ids)
     physics = BatchedPhysics.from_spec(spec, n_local, buffer_size=args.ring, device=local_rank,
@@ -267,12 +459,15 @@ def run_b200(args, rank, world, local_rank):
         physics.step(args.inner, sync=False)
 
     total_ms = timed(one, args.steps)
-    # per-launch kernel time from the engine's own events (last launch)
-    kernel_ms.append(physics.last_step_ms())
     clocks = sampler.summary()
+    launches = physics.launch_count() - launches0
+    # per-launch kernel time from the engine's own CUDA events (recorded on the engine's stream
+    # around the launch pair): mean over a few more launches, each read back before the next
+    for _ in range(5):
+        physics.step(args.inner, sync=True)
+        kernel_ms.append(physics.last_step_ms())
     env_steps = n_local*world*args.inner*args.steps
     value = env_steps/(total_ms*1e-3)
-    launches = physics.launch_count() - launches0
     handed_over = physics.last_pending if physics.fast_path else n_local
 
     # ---- end-to-end arm on pinned host buffers
@@ -375,47 +570,14 @@ def run_b200(args, rank, world, local_rank):
                 peaks = json.load(f)
         except OSError:
             pass
-        peak = float(peaks.get('hbm_gbs', 6650.0))
-        k_ms = kernel_ms[-1]
-        achieved = n_local*args.inner*b_log/(k_ms*1e-3)/1e9
-        traffic = None
-        tpath = os.path.join(ROOT, 'profiles', 'traffic.json')
-        if os.path.exists(tpath):
-            with open(tpath) as f:
-                tj = json.load(f)
-            # measured DRAM bytes per launch exist for the profiled (workload, batch, steps) only
-            traffic = tj.get('by_workload', {}).get(f'{args.model}:{n_local}:{args.inner}', {}).get(
-                'dram_bytes_per_launch')
-        # FP32 side of the roofline ("report both"): arithmetic of the step against the
-        # FFMA throughput measured on this device by the library's own micro-benchmark.  Two
-        # numerators: the oracle's instrumented op count of one mj_step (profiles/oracle_opcount.json,
-        # MuJoCo's CRB + L'DL pipeline in fp64 -- the shared "algorithmic" figure) and the FADD / FMUL /
-        # FFMA the kernel executes (ncu, profiles/; the articulated-body recursion needs fewer).
-        fp32 = None
-        try:
-            from farms_mujoco_b200.engine import measure_fp32_peak
-            fp32_peak = measure_fp32_peak(local_rank)
-            with open(os.path.join(ROOT, 'profiles', 'oracle_opcount.json')) as f:
-                oc = json.load(f)
-            rec = oc['models'].get(args.model)
-            if rec:
-                per_gpu = value/world
-                fp32 = {
-                    'peak_tflops': fp32_peak, 'peak_source': 'fb_measure_fp32_peak (FFMA micro-benchmark, this run)',
-                    'oracle_flop_per_env_step': rec['flop'],
-                    'oracle_equivalent_tflops': per_gpu*rec['flop']*1e-12,
-                    'oracle_equivalent_frac': per_gpu*rec['flop']*1e-12/fp32_peak,
-                    'executed_flop_per_env_step': oc.get('executed_flop_per_env_step', {}).get(args.model),
-                }
-                if fp32['executed_flop_per_env_step']:
-                    fp32['executed_tflops'] = per_gpu*fp32['executed_flop_per_env_step']*1e-12
-                    fp32['executed_frac'] = fp32['executed_tflops']/fp32_peak
-        except (OSError, KeyError, ValueError) as exc:
-            fp32 = {'error': str(exc)}
+        k_ms = float(np.mean(kernel_ms))
+        roofline, fp32 = roofline_objects(args.model, spec, physics, n_local, args.inner, k_ms, value/world,
+                                          handed_over, peaks, local_rank)
         out = {
             'metric': METRIC, 'value': value, 'unit': 'env-steps/s', 'n_gpus': world,
             'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': total_ms/args.steps,
-            'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32',
+            'higher_is_better': True, 'scaling': 'strong' if args.total_envs else 'weak',
+            'vs_baseline': None, 'dtype': 'f32',
             'data': 'synthetic',
             'config': {
                 'workload': (f'{args.model}: {n_local} envs/GPU x {world} GPU, drag+buoyancy, full '
@@ -441,23 +603,24 @@ def run_b200(args, rank, world, local_rank):
             'e2e': e2e,
             'gpu_launches': int(launches),
             'fp32': fp32,
-            'roofline': {
-                'bound': 'hbm', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s',
-                'frac': achieved/peak, 'traffic': traffic,
-                'kernel': ((f'fb_fastc_kernel<{physics.fast_path}>' if physics.constraint_path and 2*handed_over > n_local
-                            else f'fb_fast_kernel<{physics.fast_path},{int(physics.fast_slim > 0)},{int(physics.fast_slim > 1)}>') if physics.fast_path and
-                           (physics.constraint_path or 2*handed_over <= n_local)
-                           else f'fb_step_kernel<{physics.team_lanes}>'),
-                'kernel_ms': k_ms,
-                'algorithmic_bytes_per_env_step': b_log,
-                'peak_source': 'MEASURED_PEAKS.json hbm_gbs (of measured)' if peaks else 'fallback 6650',
-                'note': ('log-write bytes only (the one HBM stream of the step); kernel_ms is the CUDA-event '
-                         'time of one fb_step launch pair on the engine stream; the step is FP32-issue/'
-                         'latency bound, see profiles/ for issue-slot utilisation'),
-            },
+            'roofline': roofline,
         }
         if not args.no_cpu_baseline and world == 1:
-            out['cpu_baseline'] = cpu_baseline(args.model, args.cpu_seconds)
+            out['cpu_baseline'] = cpu_baseline(args.model, args.cpu_seconds, inner=args.inner)
+        if world == 1 and not args.no_other_configs and args.model == WORKLOAD:
+            # BASELINE.json's other configurations, device-timed on this GPU (parity cases with a
+            # number attached; the headline stays the line's own value)
+            physics.close()
+            extra = []
+            for name, n_envs in (('salamander', 4096), ('salamander_swim', 16384), ('centipede', 8192),
+                                 ('salamander_swim', 8192)):
+                if name == args.model and n_envs == n_local:
+                    continue
+                try:
+                    extra.append(short_device_run(name, n_envs, args.inner, 64, 10, 3, local_rank, peaks))
+                except Exception as exc:  # pylint: disable=broad-except
+                    extra.append({'workload': f'{name}: {n_envs} envs', 'error': str(exc)})
+            out['extra'] = {'other_configs': extra}
         print(json.dumps(out), file=_JSON_OUT, flush=True)
     if world > 1:
         dist.barrier()

@@ -53,6 +53,15 @@ class Simulation:
             'device', 'team_lanes', 'library', 'qpos0', 'qvel0'))
         env_kwargs = extract_sub_dict(kwargs, ('control_timestep', 'n_sub_steps', 'flat_observation'))
         self.n_sub_steps = int(env_kwargs.get('n_sub_steps', 1) or 1)
+        # The device writes log row (physics step count) % ring after EVERY physics step
+        # (fb_device.h: fb_run_env); the reference logs on full steps only (task.py:168-186,
+        # row = iteration % buffer_size with iteration advancing once per `substeps` physics
+        # steps).  Until the row index is decoupled from the step count the two only agree for
+        # one physics step per iteration, so anything else is refused rather than logged wrongly.
+        if self.n_sub_steps != 1 or int(self.options.num_sub_steps or 1) != 1:
+            raise NotImplementedError(
+                'num_sub_steps / n_sub_steps > 1: the batched engine logs one row per physics step; '
+                'run with num_sub_steps=1 and the sub-step as timestep')
         self.chunk = int(kwargs.pop('chunk', 0))
         assert self.options.headless, 'the viewer is outside the batched path'
         self._qpos0, self._qvel0 = engine_kwargs.pop('qpos0', None), engine_kwargs.pop('qvel0', None)

@@ -268,3 +268,68 @@ def reference_rollout(physics, spec, tables, n_iterations, controller=None, unit
         physics.step()
         states.append((physics.data.qpos.copy(), physics.data.qvel.copy()))
     return data, states
+
+
+# --------------------------------------------------------------------------
+# the same loop without the interpreter (oracle/farms_loop.c) -- the CPU baseline
+# --------------------------------------------------------------------------
+
+class CompiledRollout:
+    """``reference_rollout`` on oracle/farms_loop.c: physics2data, cycontacts2data, the swimming
+    callback, a travelling-wave controller and ``mj_step`` in one C call per K iterations, as the
+    reference's compiled glue (Cython -O3, NumPy kernels) would run them.  The NumPy functions
+    above remain the checker (tests/test_oracle_farms_loop.py compares the two)."""
+    # pylint: disable=too-many-instance-attributes
+
+    def __init__(self, physics, spec, tables, buffer_size, wave=None, env_phase=0.0, swimming=True):
+        import ctypes as ct
+        from farms_mujoco_b200 import cabi
+        from oracle import oracle as orc
+        self.ct, self.lib = ct, orc.lib()
+        self.physics, self.tables = physics, tables
+        self.buffer_size = int(buffer_size)
+        self.data = AnimatData.from_sensors_names(
+            timestep=physics.model.timestep, buffer_size=self.buffer_size, links=spec.links_names,
+            joints=spec.joints_names, contacts=spec.contacts_names, xfrc=spec.xfrc_names)
+        self._farms = cabi.farms_to_c(tables)
+        self._wave, self._keep = None, []
+        if wave is not None:
+            acts, amp, freq, lag = wave
+            wc = cabi.FbWaveController()
+            arrays = [np.ascontiguousarray(acts, dtype=np.int32)] + [
+                np.ascontiguousarray(a, dtype=np.float64) for a in (amp, freq, lag, np.zeros(len(acts)))]
+            self._keep = arrays
+            wc.n = len(arrays[0])
+            wc.actuator = arrays[0].ctypes.data_as(ct.POINTER(ct.c_int32))
+            for name, arr in zip(('amplitude', 'frequency', 'phase_lag', 'offset'), arrays[1:]):
+                setattr(wc, name, arr.ctypes.data_as(orc.c_double_p))
+            self._wave = wc
+        self.env_phase = float(env_phase)
+        self.swimming = bool(swimming and len(tables.swim_links_index))
+        self._norm = np.zeros(max(1, tables.n_contacts))
+        self.stage_seconds = np.zeros(4)          # physics2data, swimming, control, mj_step
+        self.iteration = 0
+
+    def _arrays(self):
+        orc_p = self.ct.POINTER(self.ct.c_double)
+        s = self.data.sensors
+        return [np.ascontiguousarray(a).ctypes.data_as(orc_p) if a.size else None
+                for a in (s.links.array, s.joints.array, s.contacts.array, s.xfrc.array)] + [
+                    self._norm.ctypes.data_as(orc_p)]
+
+    def run(self, n_iterations, timed=False):
+        """``n_iterations`` x (sensors, swimming, control, mj_step) from the current iteration."""
+        ct = self.ct
+        stage = self.stage_seconds.ctypes.data_as(ct.POINTER(ct.c_double)) if timed else None
+        self.lib.orc_farms_run(
+            self.physics._cmodel.byref(), ct.byref(self.physics._d), self._farms.byref(),
+            ct.byref(self._wave) if self._wave is not None else None, self.env_phase,
+            self.iteration, int(n_iterations), self.buffer_size, *self._arrays(), int(self.swimming), stage)
+        self.iteration += int(n_iterations)
+
+    def sensors(self):
+        """The before_step of the current iteration alone (the last row of a rollout)."""
+        ct = self.ct
+        self.lib.orc_farms_sensors(
+            self.physics._cmodel.byref(), ct.byref(self.physics._d), self._farms.byref(), self.iteration,
+            self.buffer_size, *self._arrays(), int(self.swimming), None)

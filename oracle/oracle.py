@@ -58,9 +58,9 @@ class OrcData(ct.Structure):
 def build(force=False):
     """Compile liboracle.so with the committed Makefile (gcc only)."""
     so = os.path.join(_HERE, 'liboracle.so')
-    src = os.path.join(_HERE, 'mjstep_oracle.c')
-    if force or not os.path.exists(so) or (
-            os.path.exists(src) and os.path.getmtime(so) < os.path.getmtime(src)):
+    srcs = [os.path.join(_HERE, name) for name in ('mjstep_oracle.c', 'farms_loop.c', 'oracle.h', 'Makefile')]
+    if force or not os.path.exists(so) or any(
+            os.path.exists(src) and os.path.getmtime(so) < os.path.getmtime(src) for src in srcs):
         subprocess.run(['make', '-C', _HERE, '-B' if force else '-s'], check=True,
                        stdout=subprocess.DEVNULL)
     return so
@@ -77,6 +77,18 @@ def lib():
             getattr(_LIB, name).restype = None
         _LIB.orc_step_n.argtypes = [ct.c_void_p, ct.c_void_p, ct.c_int]
         _LIB.orc_step_n.restype = None
+        # farms_loop.c: (model, data, farms, iteration, buffer_size, links, joints, contacts, xfrc,
+        #                norm_scratch, swimming, stage_seconds[4] or NULL)
+        _LIB.orc_farms_sensors.argtypes = [ct.c_void_p, ct.c_void_p, ct.c_void_p, ct.c_longlong, ct.c_int,
+                                           c_double_p, c_double_p, c_double_p, c_double_p, c_double_p,
+                                           ct.c_int, c_double_p]
+        _LIB.orc_farms_sensors.restype = None
+        # (model, data, farms, wave controller or NULL, env_phase, it0, n_iterations, buffer_size, ...)
+        _LIB.orc_farms_run.argtypes = [ct.c_void_p, ct.c_void_p, ct.c_void_p, ct.c_void_p, ct.c_double,
+                                       ct.c_longlong, ct.c_int, ct.c_int,
+                                       c_double_p, c_double_p, c_double_p, c_double_p, c_double_p,
+                                       ct.c_int, c_double_p]
+        _LIB.orc_farms_run.restype = None
     return _LIB
 
 

@@ -222,3 +222,20 @@ def test_open_loop_host_controller_is_fused(emu_library):
     assert logs[1][1] < logs[0][1]            # fewer launches when fused
     for kind, arr in logs[0][0].items():
         assert np.array_equal(arr, logs[1][0][kind]), kind
+
+
+def test_sub_steps_are_refused_not_mislogged(emu_library):
+    """num_sub_steps / n_sub_steps > 1: the device ring is indexed by the physics step count, the
+    reference's by the iteration (task.py:156-186); the layer refuses instead of logging rows the
+    reference would not."""
+    import dataclasses
+    import pytest
+    spec = models.swimmer8(n_iterations=6)
+    with pytest.raises(NotImplementedError):
+        Simulation.from_spec(spec, n_envs=2, library=emu_library, n_sub_steps=2)
+    opts = dataclasses.replace(spec.simulation_options, num_sub_steps=2)
+    with pytest.raises(NotImplementedError):
+        Simulation(mjcf_model=spec.mjcf, base_link=spec.base_link, simulation_options=opts,
+                   animat_options=spec.animat_options, arena_options=spec.arena_options, n_envs=2,
+                   links_names=spec.links_names, joints_names=spec.joints_names,
+                   contacts_names=spec.contacts_names, xfrc_names=spec.xfrc_names, library=emu_library)
