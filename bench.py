@@ -50,6 +50,9 @@ def parse_args():
                     help='strong-scaling mode: this many environments in total, sharded evenly over the '
                          'GPUs (BASELINE.json north_star: 65,536 in total, 8,192 per GPU at N = 8); 0 = weak '
                          'scaling with --envs-per-gpu on every GPU')
+    ap.add_argument('--e2e-full-links', action='store_true',
+                    help='e2e arm: download all 20 columns of the links row (default: CoM position + orientation)')
+    ap.add_argument('--no-export', action='store_true', help='skip the full-log export measurement')
     ap.add_argument('--no-other-configs', action='store_true',
                     help="skip the short device-timed runs of BASELINE.json's other configurations "
                          "(reported under 'extra' at N = 1)")
@@ -479,7 +482,12 @@ def run_b200(args, rank, world, local_rank):
         # set lets the host enqueue launch i+1 (and its ctrl upload) while launch i still runs
         NSETS = 3
         ctrl_host = [torch.zeros((n_local, model.nu), dtype=torch.float32).pin_memory() for _ in range(NSETS)]
-        links_host = [torch.empty((n_local, nl, 20), dtype=torch.float32).pin_memory() for _ in range(NSETS)]
+        # the links row comes down as CoM position + orientation (7 of the 20 columns: what a host
+        # controller steering by pose reads; the velocities stay in the device log) unless
+        # --e2e-full-links asks for the whole row
+        lcols = list(range(20)) if args.e2e_full_links else list(range(7))
+        physics.set_host_link_columns(None if args.e2e_full_links else lcols)
+        links_host = [torch.empty((n_local, nl, len(lcols)), dtype=torch.float32).pin_memory() for _ in range(NSETS)]
         # the joints row comes down as the four columns the path writes (position, velocity,
         # torque, limit force); physics.py:481-524 leaves the other 14 of the 18 zero
         from farms_mujoco_b200.layout import sc
@@ -552,8 +560,32 @@ def run_b200(args, rank, world, local_rank):
             'checksum': float(links_host[:, 0, 0].double().sum()) + checksum[0],
             'pipelined': 'device->host copy of launch i overlaps the kernels of launch i+1 (fb_step_host_async, three host buffer sets); ctrl is fetched from pinned host memory by the SMs on an upload stream',
             'host_cpus_bound': len(bound) if bound else None,
-            'rows_down': 'last links row [n_envs, n_links, 20] + joints row [n_envs, n_joints, 4 written columns]',
+            'rows_down': (f'last links row [n_envs, n_links, {len(lcols)} columns'
+                          + ('' if args.e2e_full_links else ': CoM position + orientation')
+                          + '] + joints row [n_envs, n_joints, 4 written columns: position, velocity, torque, '
+                          'limit force] of every launch'),
         }
+        if world == 1 and not args.no_export:
+            # streamed export of the FULL log (every column of every kind, the arrays the
+            # reference saves, simulation.py:198-209): 4 ring rows of every environment
+            rows = 4
+            bufs = {k: torch.empty((rows, n_local, n_items, cols), dtype=torch.float32).pin_memory()
+                    for k, n_items, cols in (('links', nl, 20), ('joints', njf, 18),
+                                             ('contacts', len(spec.contacts_names), 12), ('xfrc', len(spec.xfrc_names), 6))}
+            for k, buf in bufs.items():
+                physics.export_rows(k, 0, 1, out=buf)            # warm-up (staging allocation)
+            t0 = time.perf_counter()
+            for k, buf in bufs.items():
+                physics.export_rows(k, 0, rows, out=buf)
+            dt = time.perf_counter() - t0
+            nbytes = sum(b.numel()*4 for b in bufs.values())
+            e2e['full_log_export'] = {
+                'GB_per_s': nbytes/dt/1e9, 'bytes': nbytes, 'rows': rows,
+                'env_steps_per_s_exportable': rows*n_local/dt,
+                'note': 'fb_export_rows: ring rows -> dense pinned host arrays [rows, n_envs, n_items, n_cols], '
+                        'gathers double-buffered against the device->host copies',
+            }
+            del bufs
 
     # ---- optional end-of-rollout gather of per-env statistics (NCCL)
     stats = torch.as_tensor(physics.qpos[:, :3].astype(np.float32), device='cuda')

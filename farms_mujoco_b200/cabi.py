@@ -81,6 +81,17 @@ class FbWaveController(ct.Structure):
     ]
 
 
+class FbCpgNetwork(ct.Structure):
+    _fields_ = [
+        ('n_osc', ct.c_int32), ('n_coupling', ct.c_int32), ('n_out', ct.c_int32),
+        ('frequency', c_double_p), ('amplitude', c_double_p), ('rate', c_double_p),
+        ('coupling_from', c_int_p), ('coupling_to', c_int_p),
+        ('coupling_weight', c_double_p), ('coupling_bias', c_double_p),
+        ('out_actuator', c_int_p), ('out_osc_a', c_int_p), ('out_osc_b', c_int_p),
+        ('out_gain', c_double_p), ('out_offset', c_double_p),
+    ]
+
+
 class FbLogView(ct.Structure):
     _fields_ = [
         ('links_dev', c_float_p), ('joints_dev', c_float_p), ('contacts_dev', c_float_p),

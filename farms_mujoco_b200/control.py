@@ -11,6 +11,12 @@ farms_core satisfy this protocol unchanged.
 benchmark workloads.  It can be evaluated on the host (reference ordering, one
 ``ctrl`` upload per iteration) or handed to the engine, which then evaluates it
 inside the step kernel (``device_parameters``).
+
+``CPGController`` is a network of coupled phase oscillators with amplitude dynamics (the
+salamander-type CPG FARMS controllers implement in farms_core / farms_amphibious) driving
+position and/or torque actuators.  On the host it is the NumPy reference, stepped through
+``ExperimentTask.step_control`` exactly like any farms_core controller; ``device_cpg`` hands the
+same network to the engine (``fb_set_cpg``), which integrates it inside every launch.
 """
 
 import enum
@@ -73,3 +79,81 @@ class TravellingWaveController(AnimatController):
         return dict(joints=self.joints_names[ControlType.POSITION], amplitude=self.amplitude,
                     frequency=self.frequency, phase_lag=self.phase_lag, offset=self.offset,
                     env_phase=self.env_phase)
+
+
+class CPGController(AnimatController):
+    """Coupled phase oscillators (explicit Euler at the physics time step):
+
+        theta_i' = 2 pi f_i + sum_j w_ij r_j sin(theta_j - theta_i - phi_ij)
+        r_i''    = a_i (a_i/4 (R_i - r_i) - r_i')
+
+    ``outputs``: list of ``(joint, ControlType, osc_a, osc_b, gain, offset)``; the command of the
+    joint is ``offset + gain (r_a (1 + cos theta_a) - r_b (1 + cos theta_b))`` (``osc_b = -1``:
+    ``offset + gain r_a cos theta_a``), a position target or a torque in SI units.
+    ``couplings``: list of ``(from_j, to_i, w_ij, phi_ij)``.  State arrays are ``[n_envs, n_osc]``.
+    The command of iteration k is the output after k Euler steps: ``step`` advances the state
+    when the task moves to a new iteration (task.py:292-296)."""
+    # pylint: disable=too-many-instance-attributes,too-many-arguments
+
+    def __init__(self, frequency, amplitude, rate, couplings, outputs, phase0, amplitude0=None, device=True):
+        pos = [o[0] for o in outputs if ControlType(o[1]) == ControlType.POSITION]
+        trq = [o[0] for o in outputs if ControlType(o[1]) == ControlType.TORQUE]
+        super().__init__(joints_names=[pos, [], trq])
+        self.frequency = np.asarray(frequency, dtype=float)
+        self.amplitude = np.asarray(amplitude, dtype=float)
+        self.rate = np.asarray(rate, dtype=float)
+        self.couplings = [(int(j), int(i), float(w), float(phi)) for j, i, w, phi in couplings]
+        self.outputs = [(str(j), ControlType(t), int(a), int(b), float(g), float(o)) for j, t, a, b, g, o in outputs]
+        self.theta = np.array(np.atleast_2d(phase0), dtype=float)
+        self.r = np.zeros_like(self.theta) if amplitude0 is None else np.array(
+            np.broadcast_to(amplitude0, self.theta.shape), dtype=float)
+        self.rd = np.zeros_like(self.theta)
+        self._state0 = (self.theta.copy(), self.r.copy())
+        self._last = None
+        self._device = bool(device)
+        if not device:
+            # instance attribute shadowing the method: the task then evaluates it on the host
+            self.device_cpg = None
+
+    def _advance(self, timestep):
+        dth = np.tile(2*np.pi*self.frequency, (self.theta.shape[0], 1))
+        for j, i, w, phi in self.couplings:
+            dth[:, i] += w*self.r[:, j]*np.sin(self.theta[:, j] - self.theta[:, i] - phi)
+        rdd = self.rate*(0.25*self.rate*(self.amplitude - self.r) - self.rd)
+        self.theta = self.theta + timestep*dth
+        self.r, self.rd = self.r + timestep*self.rd, self.rd + timestep*rdd
+
+    def step(self, iteration, time, timestep):
+        key = int(round(time/timestep)) if timestep else iteration
+        if self._last is not None and key != self._last:
+            for _ in range(key - self._last):
+                self._advance(timestep)
+        self._last = key
+
+    def _command(self, out):
+        _, _, a, b, gain, offset = out
+        if b >= 0:
+            val = self.r[:, a]*(1 + np.cos(self.theta[:, a])) - self.r[:, b]*(1 + np.cos(self.theta[:, b]))
+        else:
+            val = self.r[:, a]*np.cos(self.theta[:, a])
+        return offset + gain*val
+
+    def positions(self, iteration, time, timestep):
+        return {o[0]: self._command(o) for o in self.outputs if o[1] == ControlType.POSITION}
+
+    def torques(self, iteration, time, timestep):
+        return {o[0]: self._command(o) for o in self.outputs if o[1] == ControlType.TORQUE}
+
+    def device_cpg(self, actuator_index, torque_unit=1.0):  # pylint: disable=method-hidden
+        """The network as ``fb_set_cpg`` takes it.  ``actuator_index(joint, ControlType)`` maps
+        an output to its ctrl index; torque commands are scaled by ``units.torques`` (task.py:332)."""
+        theta0, r0 = self._state0
+        return dict(
+            frequency=self.frequency, amplitude=self.amplitude, rate=self.rate,
+            coupling_from=[c[0] for c in self.couplings], coupling_to=[c[1] for c in self.couplings],
+            coupling_weight=[c[2] for c in self.couplings], coupling_bias=[c[3] for c in self.couplings],
+            out_actuator=[actuator_index(o[0], o[1]) for o in self.outputs],
+            out_osc_a=[o[2] for o in self.outputs], out_osc_b=[o[3] for o in self.outputs],
+            out_gain=[o[4]*(torque_unit if o[1] == ControlType.TORQUE else 1.0) for o in self.outputs],
+            out_offset=[o[5]*(torque_unit if o[1] == ControlType.TORQUE else 1.0) for o in self.outputs],
+            phase0=theta0, amplitude0=r0)

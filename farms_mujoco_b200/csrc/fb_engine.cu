@@ -22,6 +22,7 @@
 #include <vector>
 
 #include "fb_fastc.h"
+#include "fb_cpg.h"
 
 #ifndef FB_HOST_EMU
 #include <cuda_runtime.h>
@@ -217,6 +218,13 @@ __global__ void fb_transpose_ctrl_kernel(const float *__restrict__ in, int K, in
   out[ka*env_pad + env] = in[(k*n_envs + env)*nu + a];
 }
 
+/* on-device CPG (fb_cpg.h): the control vectors of the launch's n_steps, one thread per environment */
+__global__ void __launch_bounds__(128) fb_cpg_kernel(CpgDev c, int n_envs, long long env_pad, int n_steps, int nu,
+                                                      float dt, const float *__restrict__ ctrl, float *__restrict__ seq) {
+  const int env = blockIdx.x*blockDim.x + threadIdx.x;
+  if (env < n_envs) fb_cpg_env(c, env, env_pad, n_steps, nu, dt, ctrl, seq);
+}
+
 /* the whole ring of one environment -> dense [ring][row_floats] */
 __global__ void fb_gather_env_kernel(const float *__restrict__ log, int ring, int row_floats, int vec,
                                      long long env_pad, int env, float *__restrict__ out) {
@@ -254,9 +262,16 @@ struct FbHandle {
   float last_ms;
   float *gather_links, *gather_joints;   /* fb_step_host staging */
   int joint_sel_n, joint_sel[32];        /* fb_set_host_joint_columns: columns of the joints row fb_step_host returns (0 = all) */
+  int link_sel_n, link_sel[32];          /* fb_set_host_link_columns: the same for the links row */
+  float *export_stage[2];                /* fb_export_rows: dense row staging, double-buffered */
+  size_t export_stage_floats;
   float *gather_env;                     /* fb_export_farms staging: one environment's ring of one kind */
   float *seq_dev, *seq_stage;            /* control sequence, environment-minor + upload staging */
   int seq_len, seq_pos, seq_cap;
+  /* on-device CPG (fb_set_cpg): device tables + per-environment oscillator state */
+  bool cpg_on;
+  CpgDev cpg;
+  std::vector<void *> cpg_allocs;
   /* wave-controller copies (owned) */
   std::vector<int32_t> wc_act;
   std::vector<double> wc_amp, wc_freq, wc_lag, wc_off;
@@ -379,6 +394,21 @@ static int upload_model(FbHandle *h) {
   return 0;
 }
 
+/* capacity of the device control sequence ([n_steps][nu][env_pad] + the upload staging) */
+static int ensure_sequence(FbHandle *h, int n_steps) {
+  if (n_steps <= h->seq_cap) return 0;
+  const DevModel &m = h->hm.m;
+  const size_t n = (size_t)h->P.n_envs, per_step = (size_t)m.nu*h->P.env_pad;
+  dev_sync(h->stream);
+  if (h->seq_dev) { dev_free(h->seq_dev); dev_free(h->seq_stage); h->seq_dev = h->seq_stage = nullptr; h->seq_cap = 0; }
+  void *a = nullptr, *b = nullptr;
+  if (dev_alloc(&a, per_step*n_steps*sizeof(float)) || dev_alloc(&b, n*m.nu*n_steps*sizeof(float)))
+    return fail("control sequence: device allocation failed");
+  h->seq_dev = static_cast<float *>(a); h->seq_stage = static_cast<float *>(b);
+  h->seq_cap = n_steps;
+  return 0;
+}
+
 static int launch(FbHandle *h, int mode, int n_steps, int want_derived) {
   FbParams &P = h->P;
   P.mode = mode; P.n_steps = n_steps; P.want_derived = want_derived; P.it0 = h->it;
@@ -386,7 +416,19 @@ static int launch(FbHandle *h, int mode, int n_steps, int want_derived) {
    * team kernel finishes the ones it handed over.  Reset and derived-view requests go
    * to the team kernel alone (it is the one that produces mjData-like quantities). */
   P.ctrl_seq = nullptr; P.seq_pos = 0;
-  if (mode == FB_MODE_STEP && h->seq_len > 0) {
+  if (mode == FB_MODE_STEP && h->cpg_on) {
+    if (ensure_sequence(h, n_steps)) return -1;
+    const DevModel &dm = h->hm.m;
+#ifdef FB_HOST_EMU
+    for (int env = 0; env < P.n_envs; env++)
+      fb_cpg_env(h->cpg, env, P.env_pad, n_steps, dm.nu, dm.timestep, P.ctrl, h->seq_dev);
+#else
+    fb_cpg_kernel<<<(P.n_envs + 127)/128, 128, 0, h->stream>>>(h->cpg, P.n_envs, P.env_pad, n_steps, dm.nu,
+                                                                dm.timestep, P.ctrl, h->seq_dev);
+    h->launches++;
+#endif
+    P.ctrl_seq = h->seq_dev; P.seq_pos = 0;
+  } else if (mode == FB_MODE_STEP && h->seq_len > 0) {
     if (h->seq_pos + n_steps > h->seq_len)
       return fail("fb_step: the control sequence holds fewer steps than requested");
     P.ctrl_seq = h->seq_dev; P.seq_pos = h->seq_pos;
@@ -512,6 +554,18 @@ __global__ void __launch_bounds__(256) fb_ffma_peak_kernel(float *out, int iters
 }
 #endif
 
+template <typename Tsrc, typename Tdst>
+static int cpg_upload(FbHandle *h, const Tsrc *src, size_t count, const Tdst **out) {
+  std::vector<Tdst> tmp(count > 0 ? count : 1, Tdst(0));
+  for (size_t i = 0; i < count; i++) tmp[i] = (Tdst)src[i];
+  void *p = nullptr;
+  if (dev_alloc(&p, tmp.size()*sizeof(Tdst))) return -1;
+  h->cpg_allocs.push_back(p);
+  if (h2d(p, tmp.data(), tmp.size()*sizeof(Tdst), h->stream) || dev_sync(h->stream)) return -1;
+  *out = static_cast<const Tdst *>(p);
+  return 0;
+}
+
 /* ------------------------------------------------------------------ ABI */
 extern "C" {
 
@@ -522,6 +576,8 @@ void fb_destroy(FbHandle *h) {
   if (!h) return;
   dev_sync(h->stream);
   for (void *p : h->allocs) dev_free(p);
+  for (int k = 0; k < 2; k++) if (h->export_stage[k]) dev_free(h->export_stage[k]);
+  for (void *p : h->cpg_allocs) dev_free(p);
   if (h->seq_dev) { dev_free(h->seq_dev); dev_free(h->seq_stage); }
   if (h->I_dev) dev_free(h->I_dev);
   if (h->F_dev) dev_free(h->F_dev);
@@ -553,7 +609,9 @@ int fb_create(const FbModel *model, const FbFarms *farms, int n_envs, int device
   h->device = device; h->I_dev = nullptr; h->F_dev = nullptr; h->launches = 0; h->it = 0;
   h->last_ms = 0.f; h->has_wc = false; h->gather_links = h->gather_joints = h->gather_env = nullptr;
   h->seq_dev = h->seq_stage = nullptr; h->seq_len = h->seq_pos = h->seq_cap = 0;
-  h->joint_sel_n = 0;
+  h->cpg_on = false; memset(&h->cpg, 0, sizeof(h->cpg));
+  h->joint_sel_n = 0; h->link_sel_n = 0;
+  h->export_stage[0] = h->export_stage[1] = nullptr; h->export_stage_floats = 0;
   h->fast_enabled = 1; h->fast_block = 1; h->fast_smem_bytes = 0; h->launch_parity = 0;
   h->con_thread = 1; h->log_used = 0;
   if (const char *ev = getenv("FARMS_B200_CON_THREAD")) h->con_thread = atoi(ev) != 0;
@@ -792,16 +850,9 @@ int fb_set_ctrl_sequence(FbHandle *h, const float *ctrl, int n_steps) {
   if (!ctrl || n_steps <= 0) return 0;              /* sequence off */
   const DevModel &m = h->hm.m;
   if (m.nu <= 0) return fail("fb_set_ctrl_sequence: the model has no actuators");
-  const size_t n = (size_t)h->P.n_envs, per_step = (size_t)m.nu*h->P.env_pad;
-  if (n_steps > h->seq_cap) {
-    dev_sync(h->stream);
-    if (h->seq_dev) { dev_free(h->seq_dev); dev_free(h->seq_stage); }
-    void *a = nullptr, *b = nullptr;
-    if (dev_alloc(&a, per_step*n_steps*sizeof(float)) || dev_alloc(&b, n*m.nu*n_steps*sizeof(float)))
-      return fail("fb_set_ctrl_sequence: device allocation failed");
-    h->seq_dev = static_cast<float *>(a); h->seq_stage = static_cast<float *>(b);
-    h->seq_cap = n_steps;
-  }
+  if (h->cpg_on) return fail("fb_set_ctrl_sequence: the on-device CPG owns the control sequence (fb_set_cpg(h, NULL) first)");
+  const size_t n = (size_t)h->P.n_envs;
+  if (ensure_sequence(h, n_steps)) return -1;
 #ifdef FB_HOST_EMU
   for (int k = 0; k < n_steps; k++)
     for (size_t e = 0; e < n; e++)
@@ -839,6 +890,83 @@ int fb_set_wave_controller(FbHandle *h, const FbWaveController *c) {
     }
   }
   return upload_model(h);
+}
+
+int fb_set_cpg(FbHandle *h, const FbCpgNetwork *net) {
+  if (!h) return fail("null handle");
+  dev_sync(h->stream);
+  for (void *p : h->cpg_allocs) dev_free(p);
+  h->cpg_allocs.clear();
+  h->cpg_on = false;
+  memset(&h->cpg, 0, sizeof(h->cpg));
+  if (!net || net->n_osc <= 0) return 0;
+  const DevModel &m = h->hm.m;
+  if (net->n_osc > FB_CPG_MAXOSC) return fail("fb_set_cpg: at most 64 oscillators");
+  if (m.nu <= 0) return fail("fb_set_cpg: the model has no actuators");
+  for (int e = 0; e < net->n_coupling; e++)
+    if (net->coupling_from[e] < 0 || net->coupling_from[e] >= net->n_osc || net->coupling_to[e] < 0 ||
+        net->coupling_to[e] >= net->n_osc) return fail("fb_set_cpg: coupling index out of range");
+  for (int o = 0; o < net->n_out; o++)
+    if (net->out_actuator[o] < 0 || net->out_actuator[o] >= m.nu || net->out_osc_a[o] < 0 ||
+        net->out_osc_a[o] >= net->n_osc || net->out_osc_b[o] >= net->n_osc)
+      return fail("fb_set_cpg: output index out of range");
+  CpgDev &c = h->cpg;
+  c.n_osc = net->n_osc; c.n_coupling = net->n_coupling; c.n_out = net->n_out;
+  int bad = 0;
+  bad |= cpg_upload(h, net->frequency, net->n_osc, &c.freq);
+  bad |= cpg_upload(h, net->amplitude, net->n_osc, &c.amp);
+  bad |= cpg_upload(h, net->rate, net->n_osc, &c.rate);
+  bad |= cpg_upload(h, net->coupling_from, net->n_coupling, &c.c_from);
+  bad |= cpg_upload(h, net->coupling_to, net->n_coupling, &c.c_to);
+  bad |= cpg_upload(h, net->coupling_weight, net->n_coupling, &c.c_w);
+  bad |= cpg_upload(h, net->coupling_bias, net->n_coupling, &c.c_phi);
+  bad |= cpg_upload(h, net->out_actuator, net->n_out, &c.o_act);
+  bad |= cpg_upload(h, net->out_osc_a, net->n_out, &c.o_a);
+  bad |= cpg_upload(h, net->out_osc_b, net->n_out, &c.o_b);
+  bad |= cpg_upload(h, net->out_gain, net->n_out, &c.o_gain);
+  bad |= cpg_upload(h, net->out_offset, net->n_out, &c.o_off);
+  const size_t st = (size_t)net->n_osc*h->P.env_pad;
+  void *pt = nullptr, *pr = nullptr, *pd = nullptr;
+  bad |= dev_alloc(&pt, st*sizeof(float)); bad |= dev_alloc(&pr, st*sizeof(float)); bad |= dev_alloc(&pd, st*sizeof(float));
+  if (bad) return fail("fb_set_cpg: device allocation / upload failed");
+  h->cpg_allocs.push_back(pt); h->cpg_allocs.push_back(pr); h->cpg_allocs.push_back(pd);
+  c.theta = static_cast<float *>(pt); c.r = static_cast<float *>(pr); c.rd = static_cast<float *>(pd);
+  h->cpg_on = true;
+  h->seq_len = h->seq_pos = 0;
+  return 0;
+}
+
+int fb_set_cpg_state(FbHandle *h, const double *phase, const double *amplitude) {
+  if (!h || !phase) return fail("null argument");
+  if (!h->cpg_on) return fail("fb_set_cpg_state: no CPG set");
+  const size_t n = (size_t)h->P.n_envs, pad = (size_t)h->P.env_pad, no = (size_t)h->cpg.n_osc;
+  std::vector<float> th(no*pad, 0.f), r(no*pad, 0.f), rd(no*pad, 0.f);
+  for (size_t e = 0; e < n; e++)
+    for (size_t i = 0; i < no; i++) {
+      th[i*pad + e] = (float)phase[e*no + i];
+      if (amplitude) r[i*pad + e] = (float)amplitude[e*no + i];
+    }
+  if (h2d(h->cpg.theta, th.data(), th.size()*sizeof(float), h->stream) ||
+      h2d(h->cpg.r, r.data(), r.size()*sizeof(float), h->stream) ||
+      h2d(h->cpg.rd, rd.data(), rd.size()*sizeof(float), h->stream) || dev_sync(h->stream))
+    return fail(std::string("fb_set_cpg_state: ") + dev_error());
+  return 0;
+}
+
+int fb_get_cpg_state(FbHandle *h, double *phase, double *amplitude) {
+  if (!h || !phase) return fail("null argument");
+  if (!h->cpg_on) return fail("fb_get_cpg_state: no CPG set");
+  const size_t n = (size_t)h->P.n_envs, pad = (size_t)h->P.env_pad, no = (size_t)h->cpg.n_osc;
+  std::vector<float> th(no*pad), r(no*pad);
+  if (d2h(th.data(), h->cpg.theta, th.size()*sizeof(float), h->stream) ||
+      d2h(r.data(), h->cpg.r, r.size()*sizeof(float), h->stream) || dev_sync(h->stream))
+    return fail(std::string("fb_get_cpg_state: ") + dev_error());
+  for (size_t e = 0; e < n; e++)
+    for (size_t i = 0; i < no; i++) {
+      phase[e*no + i] = th[i*pad + e];
+      if (amplitude) amplitude[e*no + i] = r[i*pad + e];
+    }
+  return 0;
 }
 
 int fb_set_actuator_forcerange(FbHandle *h, int n, const int32_t *actuator, const int32_t *limited,
@@ -1052,13 +1180,16 @@ static int step_host_impl(FbHandle *h, const float *ctrl, const float *qpos, con
   trace_mark(2, h->stream);
 #endif
   long long row = h->it % P.ring;
-  const int lf = m.n_links*20, jf = m.n_joints*(h->joint_sel_n > 0 ? h->joint_sel_n : m.joint_cols);
+  const int lf = m.n_links*(h->link_sel_n > 0 ? h->link_sel_n : 20);
+  const int jf = m.n_joints*(h->joint_sel_n > 0 ? h->joint_sel_n : m.joint_cols);
 #ifdef FB_HOST_EMU
   (void)wait;
   for (size_t e = 0; e < n; e++) {
+    const int lsel = h->link_sel_n > 0 ? h->link_sel_n : 20, lfull = m.n_links*20;
     for (int i = 0; links_row && i < lf; i++) {
-      long long g = i/FB_VEC_LINKS;
-      links_row[e*lf + i] = P.log_links[((row*(lf/FB_VEC_LINKS) + g)*P.env_pad + e)*FB_VEC_LINKS + i % FB_VEC_LINKS];
+      const int item = i/lsel, c = h->link_sel_n > 0 ? h->link_sel[i - item*lsel] : i - item*lsel;
+      const long long f = (long long)item*20 + c, g = f/FB_VEC_LINKS;
+      links_row[e*lf + i] = P.log_links[((row*(lfull/FB_VEC_LINKS) + g)*P.env_pad + e)*FB_VEC_LINKS + f % FB_VEC_LINKS];
     }
     const int nsel = h->joint_sel_n > 0 ? h->joint_sel_n : m.joint_cols, jfull = m.n_joints*m.joint_cols;
     for (int i = 0; joints_row && i < jf; i++) {
@@ -1087,7 +1218,15 @@ static int step_host_impl(FbHandle *h, const float *ctrl, const float *qpos, con
     if (cudaEventRecord(h->ev_gather, h->stream) != cudaSuccess ||
         cudaStreamWaitEvent(cs, h->ev_gather, 0) != cudaSuccess) return fail(dev_error());
     trace_mark(4, cs);
-    if (want_links) {
+    if (want_links && h->link_sel_n > 0) {
+      FbColSel sel;
+      sel.n = h->link_sel_n;
+      for (int k = 0; k < 32; k++) sel.col[k] = k < sel.n ? h->link_sel[k] : 0;
+      long long total = (long long)n*lf;
+      fb_gather_cols_kernel<<<(unsigned)((total + 255)/256), 256, 0, cs>>>(
+          P.log_links, row, m.n_links, 20, FB_VEC_LINKS, P.env_pad, P.n_envs, sel, g_links);
+      h->launches++;
+    } else if (want_links) {
       const int nvec = lf/FB_VEC_LINKS;
       static_assert(FB_VEC_LINKS == 4, "fb_gather_rows4_kernel moves float4 vectors");
       fb_gather_rows4_kernel<<<dim3((unsigned)((n + 31)/32), (unsigned)((nvec + 31)/32)), 256, 0, cs>>>(
@@ -1206,6 +1345,88 @@ int fb_set_host_joint_columns(FbHandle *h, int n, const int32_t *cols) {
   h->joint_sel_n = n;
   for (int k = 0; k < n; k++) h->joint_sel[k] = cols[k];
   return 0;
+}
+
+int fb_set_host_link_columns(FbHandle *h, int n, const int32_t *cols) {
+  if (!h) return fail("null handle");
+  if (n < 0 || n > 20 || (n > 0 && !cols)) return fail("fb_set_host_link_columns: 0..20 columns");
+  for (int k = 0; k < n; k++)
+    if (cols[k] < 0 || cols[k] >= 20) return fail("fb_set_host_link_columns: column out of range");
+  if (fb_host_wait(h)) return -1;
+  h->link_sel_n = n;
+  for (int k = 0; k < n; k++) h->link_sel[k] = cols[k];
+  return 0;
+}
+
+/* Streamed export of whole ring rows: rows row0 .. row0+n_rows-1 (ring indices, modulo the ring)
+ * of one log kind for EVERY environment, as dense float32 [n_rows][n_envs][n_items*n_cols] on the
+ * host -- per environment and row exactly data.sensors.<kind>.array[row] (task.py:158).  Each row
+ * is transposed out of the environment-minor log by a gather kernel into one of two staging
+ * buffers and copied down on the copy stream while the next row is gathered. */
+int fb_export_rows(FbHandle *h, int kind, int row0, int n_rows, float *host) {
+  if (!h || !host) return fail("null argument");
+  const FbParams &P = h->P;
+  const DevModel &m = h->hm.m;
+  if (kind < 0 || kind > 3) return fail("fb_export_rows: kind 0 links, 1 joints, 2 contacts, 3 xfrc");
+  if (n_rows < 1 || n_rows > P.ring || row0 < 0) return fail("fb_export_rows: bad row range");
+  const float *src[4] = {P.log_links, P.log_joints, P.log_contacts, P.log_xfrc};
+  const int floats[4] = {m.n_links*20, m.n_joints*m.joint_cols, m.n_contacts*12, m.n_xfrc*6};
+  const int vec[4] = {FB_VEC_LINKS, FB_VEC_JOINTS, FB_VEC_CONTACTS, FB_VEC_XFRC};
+  const int rf = floats[kind];
+  if (rf == 0) return 0;
+  const size_t n = (size_t)P.n_envs, per_row = n*rf;
+#ifdef FB_HOST_EMU
+  for (int r = 0; r < n_rows; r++) {
+    const long long row = (row0 + r) % P.ring;
+    for (size_t e = 0; e < n; e++)
+      for (int i = 0; i < rf; i++) {
+        const long long g = i/vec[kind];
+        host[(size_t)r*per_row + e*rf + i] = src[kind][((row*(rf/vec[kind]) + g)*P.env_pad + e)*vec[kind] + i % vec[kind]];
+      }
+  }
+  return 0;
+#else
+  if (dev_sync(h->stream)) return fail(dev_error());       /* the rows are complete */
+  if (h->export_stage_floats < per_row) {
+    for (int k = 0; k < 2; k++) {
+      if (h->export_stage[k]) cudaFree(h->export_stage[k]);
+      if (cudaMalloc(&h->export_stage[k], per_row*sizeof(float)) != cudaSuccess) {
+        h->export_stage[k] = nullptr; h->export_stage_floats = 0;
+        return fail("fb_export_rows: out of device memory (staging)");
+      }
+    }
+    h->export_stage_floats = per_row;
+  }
+  cudaEvent_t gathered[2], copied[2];
+  for (int k = 0; k < 2; k++) {
+    cudaEventCreateWithFlags(&gathered[k], cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&copied[k], cudaEventDisableTiming);
+  }
+  int rc = 0;
+  for (int r = 0; r < n_rows && !rc; r++) {
+    const int b = r & 1;
+    const long long row = (row0 + r) % P.ring;
+    if (r >= 2) cudaStreamWaitEvent(h->gather_stream, copied[b], 0);   /* the staging buffer is free again */
+    if (vec[kind] == 4) {
+      const int nvec = rf/4;
+      fb_gather_rows4_kernel<<<dim3((unsigned)((n + 31)/32), (unsigned)((nvec + 31)/32)), 256, 0, h->gather_stream>>>(
+          reinterpret_cast<const float4 *>(src[kind]), row, nvec, P.env_pad, P.n_envs,
+          reinterpret_cast<float4 *>(h->export_stage[b]));
+    } else {
+      const long long total = (long long)n*(rf/vec[kind]);
+      fb_gather_rows_kernel<<<(unsigned)((total + 255)/256), 256, 0, h->gather_stream>>>(
+          src[kind], row, rf, vec[kind], P.env_pad, P.n_envs, h->export_stage[b]);
+    }
+    h->launches++;
+    cudaEventRecord(gathered[b], h->gather_stream);
+    cudaStreamWaitEvent(h->copy_stream, gathered[b], 0);
+    if (d2h(host + (size_t)r*per_row, h->export_stage[b], per_row*sizeof(float), h->copy_stream)) rc = -1;
+    cudaEventRecord(copied[b], h->copy_stream);
+  }
+  if (cudaStreamSynchronize(h->copy_stream) != cudaSuccess || cudaGetLastError() != cudaSuccess) rc = -1;
+  for (int k = 0; k < 2; k++) { cudaEventDestroy(gathered[k]); cudaEventDestroy(copied[k]); }
+  return rc ? fail(std::string("fb_export_rows: ") + dev_error()) : 0;
+#endif
 }
 
 int fb_set_fast_path(FbHandle *h, int enable) {

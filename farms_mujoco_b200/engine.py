@@ -37,6 +37,9 @@ ABI_SYMBOLS = {
     'fb_set_ctrl_sequence': (ct.c_int, [_H, ct.c_void_p, ct.c_int]),
     'fb_set_env_phase': (ct.c_int, [_H, cabi.c_double_p]),
     'fb_set_wave_controller': (ct.c_int, [_H, ct.POINTER(cabi.FbWaveController)]),
+    'fb_set_cpg': (ct.c_int, [_H, ct.POINTER(cabi.FbCpgNetwork)]),
+    'fb_set_cpg_state': (ct.c_int, [_H, cabi.c_double_p, cabi.c_double_p]),
+    'fb_get_cpg_state': (ct.c_int, [_H, cabi.c_double_p, cabi.c_double_p]),
     'fb_set_actuator_forcerange': (ct.c_int, [_H, ct.c_int, ct.POINTER(ct.c_int32), ct.POINTER(ct.c_int32), cabi.c_double_p]),
     'fb_set_water_velocity': (ct.c_int, [_H, ct.c_double, ct.c_double, ct.c_double]),
     'fb_set_swimming': (ct.c_int, [_H, ct.c_int, ct.c_int]),
@@ -51,6 +54,8 @@ ABI_SYMBOLS = {
                                    cabi.c_double_p, cabi.c_double_p]),
     'fb_host_wait': (ct.c_int, [_H]),
     'fb_set_host_joint_columns': (ct.c_int, [_H, ct.c_int, ct.POINTER(ct.c_int32)]),
+    'fb_set_host_link_columns': (ct.c_int, [_H, ct.c_int, ct.POINTER(ct.c_int32)]),
+    'fb_export_rows': (ct.c_int, [_H, ct.c_int, ct.c_int, ct.c_int, ct.c_void_p]),
     'fb_host_wait_slot': (ct.c_int, [_H, ct.c_int]),
     'fb_host_call_count': (ct.c_longlong, [_H]),
     'fb_host_wait_call': (ct.c_int, [_H, ct.c_longlong]),
@@ -154,6 +159,7 @@ class BatchedPhysics:
                                        int(device), self.buffer_size, int(team_lanes),
                                        ct.byref(handle)))
         self._handle = handle
+        self._cpg_n_osc = 0
         self._log = cabi.FbLogView()
         self._state = cabi.FbStateView()
         self._derived = cabi.FbDerivedView()
@@ -270,6 +276,43 @@ class BatchedPhysics:
         keep.set_double('phase_lag', phase_lag)
         keep.set_double('offset', np.zeros(n) if offset is None else offset)
         self._check(self.lib.fb_set_wave_controller(self._handle, keep.byref()))
+
+    def set_cpg(self, network):
+        """On-device CPG (include/farms_b200.h FbCpgNetwork): ``network`` is a dict with the
+        struct's array fields (``frequency, amplitude, rate, coupling_from, coupling_to,
+        coupling_weight, coupling_bias, out_actuator, out_osc_a, out_osc_b, out_gain,
+        out_offset``), or None to switch it off."""
+        if network is None:
+            self._check(self.lib.fb_set_cpg(self._handle, None))
+            self._cpg_n_osc = 0
+            return
+        keep = cabi.Marshalled(cabi.FbCpgNetwork())
+        s = keep.struct
+        s.n_osc, s.n_coupling, s.n_out = (len(network['frequency']), len(network['coupling_from']),
+                                          len(network['out_actuator']))
+        for name in ('frequency', 'amplitude', 'rate', 'coupling_weight', 'coupling_bias', 'out_gain', 'out_offset'):
+            keep.set_double(name, network[name])
+        for name in ('coupling_from', 'coupling_to', 'out_actuator', 'out_osc_a', 'out_osc_b'):
+            keep.set_int(name, network[name])
+        self._check(self.lib.fb_set_cpg(self._handle, keep.byref()))
+        self._cpg_n_osc = int(s.n_osc)
+
+    def set_cpg_state(self, phase, amplitude=None):
+        """Oscillator phases (and amplitudes) ``[n_envs, n_osc]`` of the on-device CPG."""
+        ph = np.ascontiguousarray(np.broadcast_to(phase, (self.n_envs, self._cpg_n_osc)), dtype=np.float64)
+        am = None if amplitude is None else np.ascontiguousarray(
+            np.broadcast_to(amplitude, (self.n_envs, self._cpg_n_osc)), dtype=np.float64)
+        self._check(self.lib.fb_set_cpg_state(
+            self._handle, ph.ctypes.data_as(cabi.c_double_p),
+            am.ctypes.data_as(cabi.c_double_p) if am is not None else None))
+
+    def cpg_state(self):
+        """(phase, amplitude) ``[n_envs, n_osc]`` float64 host copies."""
+        ph = np.zeros((self.n_envs, self._cpg_n_osc))
+        am = np.zeros_like(ph)
+        self._check(self.lib.fb_get_cpg_state(self._handle, ph.ctypes.data_as(cabi.c_double_p),
+                                              am.ctypes.data_as(cabi.c_double_p)))
+        return ph, am
 
     def set_actuator_forcerange(self, actuators, limited, forcerange):
         """``physics.named.model.actuator_forcelimited / actuator_forcerange`` edits of
@@ -434,6 +477,31 @@ class BatchedPhysics:
         cols = [] if columns is None else [int(c) for c in columns]
         arr = (ct.c_int32*max(1, len(cols)))(*cols)
         self._check(self.lib.fb_set_host_joint_columns(self._handle, len(cols), arr))
+
+    def set_host_link_columns(self, columns=None):
+        """Columns of the links row ``step_host`` downloads (``links_row`` is then
+        ``[n_envs, n_links, len(columns)]``); ``None`` = the full 20-column row."""
+        cols = [] if columns is None else [int(c) for c in columns]
+        arr = (ct.c_int32*max(1, len(cols)))(*cols)
+        self._check(self.lib.fb_set_host_link_columns(self._handle, len(cols), arr))
+
+    def export_rows(self, kind, row0, n_rows, out=None):
+        """Ring rows ``row0 .. row0+n_rows-1`` (modulo the ring) of one log kind for EVERY
+        environment as float32 ``[n_rows, n_envs, n_items, n_cols]`` on the host: the streamed
+        full-log export (fb_export_rows).  ``out``: a preallocated (pinned) torch tensor / array
+        of that many float32 to fill.  ``out[r, e]`` is the reference's
+        ``data.sensors.<kind>.array[row0 + r]`` of environment ``e`` (task.py:158)."""
+        names = self.names
+        n_items, cols, code = dict(
+            links=(len(names.links.names), sc.link_size, 0), joints=(len(names.joints.names), sc.joint_size, 1),
+            contacts=(len(names.contacts.names), sc.contact_size, 2), xfrc=(len(names.xfrc.names), sc.xfrc_size, 3))[kind]
+        shape = (int(n_rows), self.n_envs, n_items, cols)
+        if out is None:
+            out = np.empty(shape, dtype=np.float32)
+        ptr = out.data_ptr() if hasattr(out, 'data_ptr') else out.ctypes.data
+        if n_items:
+            self._check(self.lib.fb_export_rows(self._handle, code, int(row0), int(n_rows), ptr))
+        return out
 
     def host_wait_slot(self, slot):
         """Completion of the copies of the latest pipelined call with index % 2 == slot."""

@@ -182,6 +182,16 @@ class ExperimentTask:
             physics.set_wave_controller(acts, params['amplitude'], params['frequency'],
                                         params['phase_lag'], params.get('offset'))
             self.device_controller = True
+        if callable(getattr(self._controller, 'device_cpg', None)) and not self._callbacks_need_ctrl():
+            # coupled-oscillator network integrated on the device (fb_set_cpg): position targets and
+            # torque commands (x units.torques, task.py:332) written inside every launch
+            names = {ControlType.POSITION: 'actuator_position_{}', ControlType.TORQUE: 'actuator_torque_{}'}
+            net = self._controller.device_cpg(
+                lambda joint, kind: ctrl_names.index(names[ControlType(kind)].format(joint)),
+                torque_unit=self.units.torques)
+            physics.set_cpg(net)
+            physics.set_cpg_state(net['phase0'], net['amplitude0'])
+            self.device_controller = True
         self._ctrl = np.zeros((physics.n_envs, model.nu))
 
     def _callbacks_need_ctrl(self):

@@ -110,6 +110,25 @@ typedef struct FbWaveController {
   const double *amplitude, *frequency, *phase_lag, *offset; /* [n] */
 } FbWaveController;
 
+/* On-device central pattern generator (coupled phase oscillators with amplitude dynamics), the
+ * batched stand-in for a farms_core network controller driven through step_control
+ * (task.py:288-346).  Per environment and physics step (explicit Euler, dt = timestep):
+ *   theta_i' = 2 pi frequency_i + sum_c weight_c r_from(c) sin(theta_from(c) - theta_i - bias_c)
+ *   r_i''    = rate_i (rate_i/4 (amplitude_i - r_i) - r_i')
+ *   ctrl[out_actuator_o] = out_offset_o + out_gain_o (r_a (1 + cos theta_a) - r_b (1 + cos theta_b))
+ *                          (out_osc_b < 0: out_gain_o r_a cos theta_a)
+ * ctrl of iteration k is the output after k Euler steps.  A position target writes the joint's
+ * position actuator; a torque command writes its motor actuator with out_gain = units.torques
+ * (task.py:332).  At most 64 oscillators.  All arrays are host pointers. */
+typedef struct FbCpgNetwork {
+  int32_t n_osc, n_coupling, n_out;
+  const double *frequency, *amplitude, *rate;        /* [n_osc] Hz, nominal amplitude, convergence rate 1/s */
+  const int32_t *coupling_from, *coupling_to;        /* [n_coupling] oscillator j acts on oscillator i */
+  const double *coupling_weight, *coupling_bias;     /* [n_coupling] w_ij, phi_ij */
+  const int32_t *out_actuator, *out_osc_a, *out_osc_b; /* [n_out] */
+  const double *out_gain, *out_offset;               /* [n_out] */
+} FbCpgNetwork;
+
 typedef struct FbHandle FbHandle;
 
 /* Device log, float32, environment-minor so that the 32 environments of a warp write one
@@ -185,6 +204,14 @@ int fb_set_qpos_spring(FbHandle *h, const double *qpos_spring);   /* [n_envs][nq
 int fb_set_ctrl_sequence(FbHandle *h, const float *ctrl, int n_steps);
 int fb_set_env_phase(FbHandle *h, const double *phase);           /* [n_envs] */
 int fb_set_wave_controller(FbHandle *h, const FbWaveController *c); /* NULL -> off */
+/* On-device CPG (NULL -> off).  While it is on, every fb_step first integrates the network for
+ * the steps of the launch and writes their ctrl into the control sequence (the actuators it does
+ * not drive keep their held ctrl); a sequence uploaded with fb_set_ctrl_sequence is refused.
+ * fb_set_cpg_state: phase [n_envs][n_osc] (and amplitude, NULL -> 0; rates of change start at 0);
+ * fb_reset keeps the state (set it again for a new episode). */
+int fb_set_cpg(FbHandle *h, const FbCpgNetwork *net);
+int fb_set_cpg_state(FbHandle *h, const double *phase, const double *amplitude);
+int fb_get_cpg_state(FbHandle *h, double *phase, double *amplitude);
 /* Model edit of ExperimentTask.initialize_control (task.py:262-286): the reference sets
  * actuator_forcelimited / actuator_forcerange ([0, 0]) on the position and velocity
  * actuators of joints whose motor has no 'position' control type.  limited[n], range[n][2]. */
@@ -237,6 +264,17 @@ int fb_host_wait(FbHandle *h);
  * velocity, torque, limit force; physics.py:481-524 leaves the other 14 zero).  n = 0: all
  * joint_cols columns, the reference's row (default). */
 int fb_set_host_joint_columns(FbHandle *h, int n, const int32_t *cols);
+/* The same for the links row: links_row becomes [n_envs][n_links][n] with the listed columns of
+ * the 20 physics.py:435-466 writes (e.g. CoM position + orientation, 7 columns = 35 % of the
+ * bytes, for a host controller that does not read velocities).  n = 0: the full row (default). */
+int fb_set_host_link_columns(FbHandle *h, int n, const int32_t *cols);
+/* Streamed export of whole ring rows of one log kind (0 links, 1 joints, 2 contacts, 3 xfrc) for
+ * EVERY environment: rows row0 .. row0+n_rows-1 (ring indices, taken modulo the ring) as dense
+ * float32 host memory [n_rows][n_envs][n_items*n_cols] (pinned recommended).  Row r of
+ * environment e is the reference's data.sensors.<kind>.array[row] of that environment
+ * (task.py:158, simulation.py:198-209 saves exactly these arrays).  Synchronises the step stream
+ * first; gathers and device->host copies are double-buffered against each other. */
+int fb_export_rows(FbHandle *h, int kind, int row0, int n_rows, float *host);
 /* completion of the copies of the latest pipelined call whose index (0, 1, 2, ...) % 2 == slot */
 int fb_host_wait_slot(FbHandle *h, int slot);
 /* Deeper pipelines (three or more host buffer sets): fb_host_call_count = the index the next

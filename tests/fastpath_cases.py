@@ -286,3 +286,59 @@ def check_reset_clears_log(library, n_envs=4, ring=8):
         # rows the second episode has not reached: the first episode's contacts / limit forces are gone
         assert not logs['contacts'][env][n_steps + 1:].any()
         assert not logs['joints'][env][n_steps + 1:].any()
+
+
+def swimmer_cpg(n_envs, device, torque_joints=()):
+    """A salamander-type CPG for SWIMMER8: two oscillators per joint (left / right, antiphase),
+    nearest-neighbour couplings with a head-to-tail phase lag, position targets = r_L (1 + cos) -
+    r_R (1 + cos); `torque_joints` are driven through their motor actuators instead."""
+    from farms_mujoco_b200.control import CPGController, ControlType
+    nj = 7
+    freq, amp, rate = np.full(2*nj, 1.5), np.full(2*nj, 0.15), np.full(2*nj, 20.0)
+    couplings = []
+    for j in range(nj):
+        couplings += [(2*j, 2*j + 1, 10.0, np.pi), (2*j + 1, 2*j, 10.0, np.pi)]
+        if j + 1 < nj:
+            lag = 2*np.pi/nj
+            for s in (0, 1):
+                couplings += [(2*j + s, 2*(j + 1) + s, 10.0, lag), (2*(j + 1) + s, 2*j + s, 10.0, -lag)]
+    outputs = []
+    for j in range(nj):
+        name = f'joint_{j}'
+        if name in torque_joints:
+            outputs.append((name, ControlType.TORQUE, 2*j, -1, 0.02, 0.0))
+        else:
+            outputs.append((name, ControlType.POSITION, 2*j, 2*j + 1, 1.0, 0.0))
+    rng = np.random.default_rng(4)
+    phase0 = rng.uniform(0, 2*np.pi, (n_envs, 2*nj))
+    return CPGController(freq, amp, rate, couplings, outputs, phase0, amplitude0=0.05, device=device)
+
+
+def check_device_cpg(library, n_envs=3, n_it=40, chunk=8, tol=2e-5):
+    """On-device CPG (fb_set_cpg; position targets + torque commands) vs the same network evaluated
+    on the host through ExperimentTask.step_control (task.py:288-346), iteration by iteration."""
+    from farms_mujoco_b200 import models
+    from farms_mujoco_b200.simulation.simulation import Simulation
+    torque_joints = ('joint_5', 'joint_6')
+    logs = {}
+    for device in (True, False):
+        spec = models.swimmer8(n_iterations=n_it)
+        # joints 5 and 6 are torque-controlled: their motors lose the 'position' control type, so
+        # initialize_control switches their position / velocity actuators off (task.py:274-286)
+        for motor in spec.animat_options.control.motors:
+            if motor['joint_name'] in torque_joints:
+                motor.control_types = ['torque']
+        sim = Simulation.from_spec(spec, n_envs=n_envs, chunk=chunk, library=library,
+                                   controller=swimmer_cpg(n_envs, device, torque_joints))
+        sim.run()
+        assert sim.task.device_controller == device and sim.iteration == n_it - 1
+        logs[device] = {k: getattr(sim.task.data.sensors, k).array.copy() for k in ('links', 'joints', 'xfrc')}
+        if device:
+            phase, amplitude = sim.physics.cpg_state()
+            assert np.isfinite(phase).all() and (amplitude > 0.05).all()
+    assert np.abs(logs[False]['joints'][..., 0]).max() > 0.02          # the swimmer moves
+    from farms_mujoco_b200.layout import sc
+    assert np.abs(logs[False]['joints'][:, :, 5:, sc.joint_torque]).max() == 0   # motors are not logged (D-4)
+    for kind in ('links', 'joints', 'xfrc'):
+        err = log_error(kind, logs[True][kind], logs[False][kind])
+        assert err < tol, (kind, err)

@@ -333,3 +333,40 @@ def test_ring_wrap(emu_library, kind):
 def test_reset_clears_constraint_columns(emu_library):
     import fastpath_cases
     fastpath_cases.check_reset_clears_log(emu_library)
+
+
+def test_host_link_columns_and_row_export(emu_library):
+    """fb_set_host_link_columns (links row as selected columns) and fb_export_rows (whole ring
+    rows of every environment, dense) against the per-environment log view."""
+    from farms_mujoco_b200.engine import BatchedPhysics
+    from farms_mujoco_b200.layout import sc
+    n, n_steps, ring = 5, 7, 4
+    spec, model, qpos0, qvel0, ctrl = make_case('salamander', n)
+    nl, nj = len(spec.links_names), len(spec.joints_names)
+    physics = BatchedPhysics.from_spec(spec, n, buffer_size=ring, library=emu_library)
+    physics.reset(qpos0, qvel0)
+    cols = list(range(sc.link_com_position_x, sc.link_com_orientation_w + 1))
+    physics.set_host_link_columns(cols)
+    links = np.zeros((n, nl, len(cols)), np.float32)
+    joints = np.zeros((n, nj, sc.joint_size), np.float32)
+    physics.step_host(n_steps, ctrl=np.ascontiguousarray(ctrl, dtype=np.float32), links_row=links, joints_row=joints)
+    logs = physics.log_arrays()
+    last = n_steps % ring
+    assert np.array_equal(links, logs['links'][:, last][:, :, cols])
+    assert np.array_equal(joints, logs['joints'][:, last])
+    physics.set_host_link_columns(None)
+    full = np.zeros((n, nl, 20), np.float32)
+    physics.step_host(1, links_row=full)
+    logs = physics.log_arrays()
+    assert np.array_equal(full, logs['links'][:, (n_steps + 1) % ring])
+    for kind in ('links', 'joints', 'contacts', 'xfrc'):
+        out = physics.export_rows(kind, 2, 4)           # rows 2, 3, 0, 1
+        want = logs[kind][:, [2, 3, 0, 1]].transpose(1, 0, 2, 3)
+        assert out.shape == want.shape and np.array_equal(out, want), kind
+    assert logs['contacts'].any()
+
+
+def test_device_cpg_matches_host_controller(emu_library):
+    """coupled-oscillator CPG + torque writer on the device == step_control on the host."""
+    import fastpath_cases
+    fastpath_cases.check_device_cpg(emu_library)

@@ -650,3 +650,10 @@ def test_ring_wrap(cuda_library, kind):
 def test_reset_clears_constraint_columns(cuda_library):
     import fastpath_cases
     fastpath_cases.check_reset_clears_log(cuda_library, n_envs=70)
+
+
+def test_device_cpg_matches_host_controller(cuda_library):
+    """the on-device CPG (fb_cpg_kernel feeding the control sequence of every launch)
+    against the same network stepped on the host through ExperimentTask.step_control."""
+    import fastpath_cases
+    fastpath_cases.check_device_cpg(cuda_library, n_envs=70, n_it=48, chunk=16)
