@@ -103,10 +103,14 @@ fb_fast_kernel(const __grid_constant__ FbFastParams Q) {
   const int valid = env < P.n_envs;
   if (!MULTI && !valid) return;
   const int n_float = SLIM ? P.m.X.n_float_slim : P.m.X.n_float;
+  /* multi-warp SLIM blocks stage the scratch through a TMA ring behind the warp's body blocks */
+  constexpr int TMA = FB_TMA_ENABLE && SLIM && MULTI;
+  const size_t warp_floats = (size_t)n_float*BLK + (TMA ? FB_RING_BYTES/sizeof(float) : 0);
   /* L2-resident scratch [warp][field][lane]: compile-time strides, coalesced */
-  FbFast<BLK, SLIM> st(P, Q.rec, fb_smem + (size_t)warp*n_float*BLK + lane,
-                       P.fast_scratch + (size_t)wid*(SLIM ? P.m.X.n_scratch_slim : P.m.X.n_scratch)*BLK + lane,
-                       valid ? env : 0);
+  FbFast<BLK, SLIM, TMA> st(P, Q.rec, fb_smem + warp*warp_floats + lane,
+                            P.fast_scratch + (size_t)wid*(SLIM ? P.m.X.n_scratch_slim : P.m.X.n_scratch)*BLK + lane,
+                            valid ? env : 0);
+  if (TMA) st.ring_setup(fb_smem + warp*warp_floats + (size_t)n_float*BLK, lane);
   /* full warps move their state through a shared-memory tile (coalesced); a partial last
    * warp, or a model whose state rows do not fit the tile, uses per-thread accesses (the SLIM
    * layout's smaller blocks take the rows in two phases) */
@@ -488,7 +492,8 @@ static int launch(FbHandle *h, int mode, int n_steps, int want_derived) {
       if (!h->fast_slim || wpb < 2 || wpb > 8) wpb = 1;      /* multi-warp blocks: SLIM layout only (measured 3-5 % slower on the regular one) */
       const int warps = (P.n_envs + 31)/32;
       const int wblocks = (warps + wpb - 1)/wpb;
-      const size_t bytes = (h->fast_slim ? h->fast_slim_smem_bytes : h->fast_smem_bytes)*(h->fast_block == 32 ? wpb : 1);
+      size_t bytes = (h->fast_slim ? h->fast_slim_smem_bytes : h->fast_smem_bytes)*(h->fast_block == 32 ? wpb : 1);
+      if (FB_TMA_ENABLE && h->fast_slim && wpb > 1) bytes += (size_t)wpb*FB_RING_BYTES;      /* TMA ring of every warp */
       if (h->fast_block == 16) fb_fast_kernel<16, 0, 0><<<fblocks, 16, bytes, h->stream>>>(*h->fastQ);
       else if (h->fast_slim && wpb > 1) fb_fast_kernel<32, 1, 1><<<wblocks, 32*wpb, bytes, h->stream>>>(*h->fastQ);
       else if (h->fast_slim) fb_fast_kernel<32, 1, 0><<<warps, 32, bytes, h->stream>>>(*h->fastQ);
@@ -521,11 +526,11 @@ static int launch(FbHandle *h, int mode, int n_steps, int want_derived) {
 static int fb_slim_attributes(FbHandle *h, int max_smem) {
   h->fast_slim_smem_bytes = (size_t)h->hm.m.X.n_float_slim*sizeof(float)*32;
   const int b1 = (int)h->fast_slim_smem_bytes;
-  int fit = max_smem/b1;                       /* warps of one block that fit an SM's shared memory */
+  int fit = max_smem/(b1 + (FB_TMA_ENABLE ? FB_RING_BYTES : 0));     /* warps of one block (body blocks + TMA ring each) that fit an SM's shared memory */
   if (fit > 8) fit = 8;
   cudaError_t ce = cudaFuncSetAttribute(fb_fast_kernel<32, 1, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, b1);
   if (ce == cudaSuccess) ce = cudaFuncSetAttribute(fb_fast_kernel<32, 1, 0>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-  if (ce == cudaSuccess && fit >= 2) ce = cudaFuncSetAttribute(fb_fast_kernel<32, 1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, fit*b1);
+  if (ce == cudaSuccess && fit >= 2) ce = cudaFuncSetAttribute(fb_fast_kernel<32, 1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, fit*(b1 + (FB_TMA_ENABLE ? FB_RING_BYTES : 0)));
   if (ce == cudaSuccess) ce = cudaFuncSetAttribute(fb_fast_kernel<32, 1, 1>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
   if (ce != cudaSuccess) return fail(std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(ce));
   if (h->fast_wpb > fit) h->fast_wpb = fit;

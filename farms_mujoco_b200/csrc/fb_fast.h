@@ -195,14 +195,77 @@ FB_DEV void fb_sincos_half(float x, float *sn, float *cs) {
  * the L2 scratch, fetched one body ahead like the rest of it.  203 instead of 431 floats of
  * shared memory per SALAMANDER: 8 warps of environments per SM instead of 4, i.e. two warps per
  * scheduler to hide each other's latencies, which pays once the batch has that many warps. */
+#ifndef FB_HOST_EMU
+/* ---- TMA bulk copies global -> shared memory with mbarrier completion (sm_90+ PTX; SASS UBLKCP /
+ * SYNCS).  One elected lane arms the barrier with the byte count and issues the copy; every lane
+ * of the warp waits on the barrier's phase and then reads the staged block with LDS. */
+FB_DEV unsigned fb_smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+FB_DEV void fb_mbar_init(unsigned bar, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(bar), "r"(count) : "memory");
+}
+FB_DEV void fb_mbar_expect_tx(unsigned bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(bar), "r"(bytes) : "memory");
+}
+FB_DEV void fb_bulk_g2s(unsigned dst, const void *src, unsigned bytes, unsigned bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               :: "r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+FB_DEV void fb_mbar_wait(unsigned bar, unsigned parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred P1;\n"
+      "LAB_WAIT:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+      "@P1 bra DONE;\n"
+      "bra LAB_WAIT;\n"
+      "DONE:\n"
+      "}" :: "r"(bar), "r"(parity) : "memory");
+}
+/* generic-proxy writes (st.global of the scratch) before async-proxy reads (the bulk copies) */
+#ifndef FB_TMA_FENCE
+#define FB_TMA_FENCE 1
+#endif
+FB_DEV void fb_fence_proxy_async() {
+#if FB_TMA_FENCE == 2
+  asm volatile("fence.proxy.async;" ::: "memory");            /* + MEMBAR.ALL.GPU: measured, not needed */
+#elif FB_TMA_FENCE == 1
+  asm volatile("fence.proxy.async.global;" ::: "memory");     /* FENCE.VIEW.ASYNC.G */
+#endif
+}
+#endif
+
+/* stages of the TMA scratch ring (FbFast<.., TMA = 1>): a body's block is requested RING - 1
+ * bodies before it is used */
+#ifndef FB_RING
+#define FB_RING 3
+#endif
+/* Off by default: measured r2d on B200, 65,536 SALAMANDERs, 7 warps per block -- 3.61 ms per launch
+ * with the ring (bit-identical results; RING 2 or 3, with or without the proxy fences: 3.58 .. 3.61)
+ * against 3.12 ms with the register prefetch.  A body's iteration then starts with
+ * __syncwarp -> one lane arms the barrier and issues UBLKCP -> every lane polls the mbarrier -> 17 LDS,
+ * a serial prefix of 100-200 cycles x 87 body visits per step that the register prefetch does not
+ * have, and the ring's 6.5 KB per warp cost the eighth warp of a block.  Build with
+ * -DFB_TMA_ENABLE=1 to reproduce (tools/variant_bench.sh). */
+#ifndef FB_TMA_ENABLE
+#define FB_TMA_ENABLE 0
+#endif
+#define FB_RING_FIELDS 17      /* W[6] U 1/d trq q qd V[6]: the fields the sweeps read, contiguous */
+/* shared memory of one warp's ring: the stages + one 8-byte mbarrier per stage, padded to 128 B */
+#define FB_RING_BYTES ((FB_RING*FB_RING_FIELDS*32*4 + 8*FB_RING + 127)/128*128)
+
 template <int SYNC> FB_DEV void fb_block_sync() {
 #ifndef FB_HOST_EMU
   if (SYNC) __syncthreads();
 #endif
 }
 
-template <int BLK, int SLIM = 0> struct FbFast {
-  enum { NF = SLIM ? 7 : FB_NF, GNF = SLIM ? FG_NF + 6 : FG_NF, FG_V = FG_NF };
+/* TMA = 1 (SLIM layout in multi-warp blocks): the per-body scratch block is not fetched into
+ * registers one body ahead (16-17 long-lived LDG results per thread that tie up a scoreboard:
+ * r2a's top stalls) but staged in a small shared-memory ring by bulk copies, two bodies ahead. */
+template <int BLK, int SLIM = 0, int TMA = 0> struct FbFast {
+  /* SLIM scratch block: W[6] U 1/d trq q qd V[6] tc tu -- the first 17 are one contiguous run */
+  enum { NF = SLIM ? 7 : FB_NF, GNF = SLIM ? FG_NF + 6 : FG_NF, FG_V = SLIM ? 11 : FG_NF,
+         FGTC = SLIM ? 17 : FG_TC, FGTU = SLIM ? 18 : FG_TU };
   const FbParams &P;
   const DevModel &m;
   const FastRec *rec; /* [nbody], constant bank (kernel parameters) */
@@ -224,18 +287,53 @@ template <int BLK, int SLIM = 0> struct FbFast {
    * (FbParams::con_dirty), zfill = verdict for the current step */
   long long dirty_c;
   int zfill;
+  /* TMA ring of this warp: shared-memory stages, their mbarriers, the parity each barrier
+   * completes next, and the lane */
+  float *ring;
+  unsigned ring_bar, ring_phase;
+  int ring_lane;
 
   FB_MEM FbFast(const FbParams &P_, const FastRec *rec_, float *s_, float *gs_, int env_)
       : P(P_), m(P_.m), rec(rec_), s(s_), env(env_), gs(gs_), cs(0), csc(0), crec(0) {
     env_phase = P.env_phase[env];
     dirty_c = P.con_dirty[env];
     zfill = 1;
+    ring = 0; ring_bar = 0; ring_phase = 0; ring_lane = 0;
     rootpos[0] = rootpos[1] = rootpos[2] = 0.f;
     rqn[0] = 1.f; rqn[1] = rqn[2] = rqn[3] = 0.f;
 FB_UNROLL
     for (int k = 0; k < 13; k++) rt[k] = 0.f;
   }
 
+#ifndef FB_HOST_EMU
+  /* ---- TMA ring.  ring_setup: once per kernel, by every lane of the warp. */
+  FB_MEM void ring_setup(float *ring_base, int lane) {
+    ring = ring_base; ring_lane = lane; ring_phase = 0;
+    ring_bar = fb_smem_u32(ring_base + FB_RING*FB_RING_FIELDS*32);
+    if (lane == 0) {
+FB_UNROLL
+      for (int k = 0; k < FB_RING; k++) fb_mbar_init(ring_bar + 8*k, 1);
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncwarp();
+  }
+  /* request the block of body b into stage st (the stage's previous content has been read:
+   * callers put a __syncwarp() between those reads and this call) */
+  FB_MEM void ring_issue(int leader, int b, int st, int f0, int nf) {
+    if (ring_lane == leader) {
+      const unsigned bar = ring_bar + 8*st, bytes = nf*32*sizeof(float);
+      fb_mbar_expect_tx(bar, bytes);
+      fb_bulk_g2s(fb_smem_u32(ring + (st*FB_RING_FIELDS + f0)*32),
+                  gs - ring_lane + ((size_t)GNF*(b - 1) + f0)*BLK, bytes, bar);
+    }
+  }
+  /* wait for stage st; returns this lane's view of it: field f at [f*32] */
+  FB_MEM const float *ring_wait(int st) {
+    fb_mbar_wait(ring_bar + 8*st, (ring_phase >> st) & 1u);
+    ring_phase ^= 1u << st;
+    return ring + st*FB_RING_FIELDS*32 + ring_lane;
+  }
+#endif
   /* row of iteration `itr` (before the ring modulus): was it last written at or before dirty_c? */
   FB_MEM int log_row_dirty(long long itr) const {
     const long long prev = itr - P.ring;
@@ -334,8 +432,8 @@ FB_UNROLL
             if (!(a == ap || a == av || a == at)) tu += f;
           }
         }
-        fb_st_scr(pg + FG_TC*BLK, tc);
-        fb_st_scr(pg + FG_TU*BLK, tu);
+        fb_st_scr(pg + FGTC*BLK, tc);
+        fb_st_scr(pg + FGTU*BLK, tu);
       }
     }
   }
@@ -457,7 +555,19 @@ FB_UNROLL
     const int nb = m.nbody;
     int active = 0;
     /* scratch values are fetched one body ahead: the L2 round trip overlaps the arithmetic */
-    float nq = fb_ld_scr(gblock(1) + FG_Q*BLK), nqd = fb_ld_scr(gblock(1) + FG_QD*BLK);
+    float nq = 0.f, nqd = 0.f;
+#ifndef FB_HOST_EMU
+    /* (TMA) the lanes that take this step: one of them issues the copies, all of them wait */
+    const unsigned live = TMA ? __activemask() : 0u;
+    const int leader = TMA ? __ffs(live) - 1 : 0;
+    int st = 0;
+    if (TMA) {
+FB_UNROLL
+      for (int d = 0; d < FB_RING - 1; d++)
+        if (1 + d < nb) ring_issue(leader, 1 + d, d, FG_Q, 2);
+    } else
+#endif
+    { nq = fb_ld_scr(gblock(1) + FG_Q*BLK); nqd = fb_ld_scr(gblock(1) + FG_QD*BLK); }
     float *pb = block(1) - NF*BLK;
     float *pn = gblock(1);
     Quat lastq = {1.f, 0.f, 0.f, 0.f};
@@ -484,7 +594,17 @@ FB_UNROLL
       for (int k = 0; k < 4; k++) { FB_PIN_F(rc.bquat[k]); FB_PIN_F(rc.chk[k]); }
       pb += NF*BLK;
       pn += GNF*BLK;
-      const float cq = nq, cqd = nqd;
+      float cq = nq, cqd = nqd;
+#ifndef FB_HOST_EMU
+      if (TMA) {
+        __syncwarp(live);                 /* the stage requested next was read in the previous iteration */
+        const int sn = st == 0 ? FB_RING - 1 : st - 1;
+        if (b + FB_RING - 1 < nb) ring_issue(leader, b + FB_RING - 1, sn, FG_Q, 2);
+        const float *sb = ring_wait(st);
+        cq = sb[FG_Q*32]; cqd = sb[FG_QD*32];
+        st = st + 1 == FB_RING ? 0 : st + 1;
+      } else
+#endif
       if (b + 1 < nb) { nq = fb_ld_scr(pn + FG_Q*BLK); nqd = fb_ld_scr(pn + FG_QD*BLK); }
       float *pgv = pn - GNF*BLK;       /* scratch block of this body (pn runs one ahead) */
       const int jtype = rc.jtype;
@@ -623,6 +743,9 @@ FB_UNROLL
         fb_st4(row + 4*ev, (v[5] + cr[2])*iv, v[0]*iw, v[1]*iw, v[2]*iw);
       }
     }
+#ifndef FB_HOST_EMU
+    if (TMA) fb_fence_proxy_async();      /* the velocities just stored are bulk-copied by pass 2 */
+#endif
     return active;
   }
 
@@ -644,15 +767,27 @@ FB_UNROLL
     for (int k = 0; k < 6; k++) { C.A[k] = 0.f; C.M[k] = 0.f; pc[k] = 0.f; }
 FB_UNROLL
     for (int k = 0; k < 9; k++) C.H[k] = 0.f;
-    float nx[10];        /* W[6], q, qd, tc, tu of the next body to visit */
+    float nx[10] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};        /* W[6], q, qd, tc, tu of the next body to visit */
     float nxv[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};     /* SLIM: its velocity */
+#ifndef FB_HOST_EMU
+    const unsigned live = TMA ? __activemask() : 0u;
+    const int leader = TMA ? __ffs(live) - 1 : 0;
+    int st = 0;
+    if (TMA) {
+FB_UNROLL
+      for (int d = 0; d < FB_RING - 1; d++)
+        if (nb - 1 - d >= 1) ring_issue(leader, nb - 1 - d, d, 0, FB_RING_FIELDS);
+    }
+#endif
     {
       const float *pn = gblock(nb - 1);
+      if (!TMA) {
 FB_UNROLL
-      for (int k = 0; k < 6; k++) nx[k] = fb_ld_scr(pn + (FG_W + k)*BLK);
-      nx[6] = fb_ld_scr(pn + FG_Q*BLK); nx[7] = fb_ld_scr(pn + FG_QD*BLK);
-      nx[8] = fb_ld_scr(pn + FG_TC*BLK); nx[9] = fb_ld_scr(pn + FG_TU*BLK);
-      if (SLIM) {
+        for (int k = 0; k < 6; k++) nx[k] = fb_ld_scr(pn + (FG_W + k)*BLK);
+        nx[6] = fb_ld_scr(pn + FG_Q*BLK); nx[7] = fb_ld_scr(pn + FG_QD*BLK);
+      }
+      nx[8] = fb_ld_scr(pn + FGTC*BLK); nx[9] = fb_ld_scr(pn + FGTU*BLK);
+      if (SLIM && !TMA) {
 FB_UNROLL
         for (int k = 0; k < 6; k++) nxv[k] = fb_ld_scr(pn + (FG_V + k)*BLK);
       }
@@ -680,15 +815,29 @@ FB_UNROLL
       for (int k = 0; k < 6; k++) cxv[k] = nxv[k];
       if (b > 1) {
         const float *pn = pg - GNF*BLK;
+        if (!TMA) {
 FB_UNROLL
-        for (int k = 0; k < 6; k++) nx[k] = fb_ld_scr(pn + (FG_W + k)*BLK);
-        nx[6] = fb_ld_scr(pn + FG_Q*BLK); nx[7] = fb_ld_scr(pn + FG_QD*BLK);
-        nx[8] = fb_ld_scr(pn + FG_TC*BLK); nx[9] = fb_ld_scr(pn + FG_TU*BLK);
-        if (SLIM) {
+          for (int k = 0; k < 6; k++) nx[k] = fb_ld_scr(pn + (FG_W + k)*BLK);
+          nx[6] = fb_ld_scr(pn + FG_Q*BLK); nx[7] = fb_ld_scr(pn + FG_QD*BLK);
+        }
+        nx[8] = fb_ld_scr(pn + FGTC*BLK); nx[9] = fb_ld_scr(pn + FGTU*BLK);
+        if (SLIM && !TMA) {
 FB_UNROLL
           for (int k = 0; k < 6; k++) nxv[k] = fb_ld_scr(pn + (FG_V + k)*BLK);
         }
       }
+#ifndef FB_HOST_EMU
+      if (TMA) {
+        __syncwarp(live);
+        const int sn = st == 0 ? FB_RING - 1 : st - 1;
+        if (b - (FB_RING - 1) >= 1) ring_issue(leader, b - (FB_RING - 1), sn, 0, FB_RING_FIELDS);
+        const float *sb = ring_wait(st);
+FB_UNROLL
+        for (int k = 0; k < 6; k++) { cx[k] = sb[(FG_W + k)*32]; cxv[k] = sb[(FG_V + k)*32]; }
+        cx[6] = sb[FG_Q*32]; cx[7] = sb[FG_QD*32];
+        st = st + 1 == FB_RING ? 0 : st + 1;
+      }
+#endif
       const Quat q = {pb[(FB_QUAT)*BLK], pb[(FB_QUAT + 1)*BLK], pb[(FB_QUAT + 2)*BLK], pb[(FB_QUAT + 3)*BLK]};
       float R[9], v[6], fx[6];
       q_mat(q, R);
@@ -893,6 +1042,9 @@ FB_UNROLL
         }
       }
     }
+#ifndef FB_HOST_EMU
+    if (TMA) fb_fence_proxy_async();      /* U, u, 1/d, trq just stored are bulk-copied by pass 3 */
+#endif
   }
 
   /* ---- pass 3: root -> leaves, accelerations, Euler, joints / xfrc rows, drag */
@@ -906,9 +1058,19 @@ FB_UNROLL
     const float hdt = m.timestep;
     float ac[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};   /* carry: acceleration of body b-1 */
     int bad = 0;
-    float nx[11];        /* U[6], u, 1/d, trq, q, qd of the next body to visit */
+    float nx[11] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};   /* U[6], u, 1/d, trq, q, qd of the next body to visit */
     float nxv[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};     /* SLIM: its velocity */
-    {
+#ifndef FB_HOST_EMU
+    const unsigned live = TMA ? __activemask() : 0u;
+    const int leader = TMA ? __ffs(live) - 1 : 0;
+    int st = 0;
+    if (TMA) {
+FB_UNROLL
+      for (int d = 0; d < FB_RING - 1; d++)
+        if (1 + d < nb) ring_issue(leader, 1 + d, d, 0, FB_RING_FIELDS);
+    }
+#endif
+    if (!TMA) {
       const float *pn = gblock(1);
 FB_UNROLL
       for (int k = 0; k < 9; k++) nx[k] = fb_ld_scr(pn + (FG_W + k)*BLK);     /* W, U, DINV, TRQ are contiguous */
@@ -938,7 +1100,7 @@ FB_UNROLL
       for (int k = 0; k < 11; k++) cx[k] = nx[k];
 FB_UNROLL
       for (int k = 0; k < 6; k++) cxv[k] = nxv[k];
-      if (b + 1 < nb) {
+      if (!TMA && b + 1 < nb) {
         const float *pn = pg + GNF*BLK;
 FB_UNROLL
         for (int k = 0; k < 9; k++) nx[k] = fb_ld_scr(pn + (FG_W + k)*BLK);
@@ -948,6 +1110,20 @@ FB_UNROLL
           for (int k = 0; k < 6; k++) nxv[k] = fb_ld_scr(pn + (FG_V + k)*BLK);
         }
       }
+#ifndef FB_HOST_EMU
+      if (TMA) {
+        __syncwarp(live);
+        const int sn = st == 0 ? FB_RING - 1 : st - 1;
+        if (b + FB_RING - 1 < nb) ring_issue(leader, b + FB_RING - 1, sn, 0, FB_RING_FIELDS);
+        const float *sb = ring_wait(st);
+FB_UNROLL
+        for (int k = 0; k < 9; k++) cx[k] = sb[(FG_W + k)*32];
+        cx[9] = sb[FG_Q*32]; cx[10] = sb[FG_QD*32];
+FB_UNROLL
+        for (int k = 0; k < 6; k++) cxv[k] = sb[(FG_V + k)*32];
+        st = st + 1 == FB_RING ? 0 : st + 1;
+      }
+#endif
       /* a body without an xfrc row keeps the user's wrench: fetched now, stored at the end of the
        * iteration (the slot held U during this step) */
       float uwr[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
@@ -1119,6 +1295,9 @@ FB_UNROLL
         for (int k = 0; k < 6; k++) fb_st_scr(pg + (FG_W + k)*BLK, uwr[k]);
       }
     }
+#ifndef FB_HOST_EMU
+    if (TMA) fb_fence_proxy_async();      /* q, qd, W just stored are bulk-copied by the next step's sweeps */
+#endif
     return bad;
   }
 
@@ -1133,6 +1312,9 @@ FB_UNROLL
   template <int SYNC>
   FB_MEM int run_t(int coop, int lane, int valid) {
     if (valid) load_state(coop, lane);
+#ifndef FB_HOST_EMU
+    if (TMA) fb_fence_proxy_async();      /* the scratch load_state filled is bulk-copied by the sweeps */
+#endif
     const size_t e = (size_t)env;
     const int n = P.n_steps;
     int kdone = n, dead = !valid;
