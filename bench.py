@@ -50,8 +50,10 @@ def parse_args():
                     help='strong-scaling mode: this many environments in total, sharded evenly over the '
                          'GPUs (BASELINE.json north_star: 65,536 in total, 8,192 per GPU at N = 8); 0 = weak '
                          'scaling with --envs-per-gpu on every GPU')
-    ap.add_argument('--e2e-full-links', action='store_true',
-                    help='e2e arm: download all 20 columns of the links row (default: CoM position + orientation)')
+    ap.add_argument('--e2e-links', default='head', choices=['head', 'pose', 'full'],
+                    help="e2e arm, links rows downloaded per launch: 'head' = CoM position + orientation of the "
+                         "first link (what a controller steering by the head pose reads), 'pose' = the same 7 "
+                         "columns of every link, 'full' = all 20 columns of every link")
     ap.add_argument('--no-export', action='store_true', help='skip the full-log export measurement')
     ap.add_argument('--no-other-configs', action='store_true',
                     help="skip the short device-timed runs of BASELINE.json's other configurations "
@@ -481,13 +483,14 @@ def run_b200(args, rank, world, local_rank):
         # download of launch i with the kernels of launch i+1 (include/farms_b200.h); the third
         # set lets the host enqueue launch i+1 (and its ctrl upload) while launch i still runs
         NSETS = 3
-        ctrl_host = [torch.zeros((n_local, model.nu), dtype=torch.float32).pin_memory() for _ in range(NSETS)]
         # the links row comes down as CoM position + orientation (7 of the 20 columns: what a host
         # controller steering by pose reads; the velocities stay in the device log) unless
         # --e2e-full-links asks for the whole row
-        lcols = list(range(20)) if args.e2e_full_links else list(range(7))
-        physics.set_host_link_columns(None if args.e2e_full_links else lcols)
-        links_host = [torch.empty((n_local, nl, len(lcols)), dtype=torch.float32).pin_memory() for _ in range(NSETS)]
+        lcols = list(range(20)) if args.e2e_links == 'full' else list(range(7))
+        litems = [0] if args.e2e_links == 'head' else list(range(nl))
+        physics.set_host_link_columns(None if args.e2e_links == 'full' else lcols)
+        physics.set_host_link_items(litems if args.e2e_links == 'head' else None)
+        links_host = [torch.empty((n_local, len(litems), len(lcols)), dtype=torch.float32).pin_memory() for _ in range(NSETS)]
         # the joints row comes down as the four columns the path writes (position, velocity,
         # torque, limit force); physics.py:481-524 leaves the other 14 of the 18 zero
         from farms_mujoco_b200.layout import sc
@@ -503,14 +506,15 @@ def run_b200(args, rank, world, local_rank):
         # amp sin(a - lag + phase) = [amp sin(a - lag)] cos(phase) + [amp cos(a - lag)] sin(phase):
         # the per-environment factors are constant, so a call costs two multiply-adds per entry
         cos_ph, sin_ph = torch.cos(phase_t), torch.sin(phase_t)
+        # ctrl goes up as the controlled actuators only (the position actuators the controller
+        # writes, task.py:309-321): [n_envs, n_controlled] instead of [n_envs, nu]; the velocity
+        # and motor actuators keep their (zero) ctrl on the device
+        compact = len(acts) <= 32
+        if compact:
+            physics.set_host_ctrl_columns(acts)
+        ctrl_host = [torch.zeros((n_local, len(acts) if compact else model.nu), dtype=torch.float32).pin_memory()
+                     for _ in range(NSETS)]
         wave_buf = torch.empty((n_local, len(acts)), dtype=torch.float32)
-        # where the wave goes in ctrl: a strided view when the actuator ids are evenly spaced (they
-        # are: position / velocity / motor per joint), a column scatter otherwise
-        acts_np = np.asarray(acts)
-        stride = int(acts_np[1] - acts_np[0]) if len(acts_np) > 1 else 1
-        regular = len(acts_np) > 1 and stride > 0 and bool(np.all(np.diff(acts_np) == stride))
-        ctrl_view = [torch.as_strided(c, (n_local, len(acts)), (model.nu, stride), int(acts_np[0])) if regular else None
-                     for c in ctrl_host]
         if world > 1:
             # torchrun pins every rank to one OpenMP thread; the host-side controller may use its share
             torch.set_num_threads(max(1, min(len(bound) if bound else 1 << 30, (os.cpu_count() or world)//world)))
@@ -530,11 +534,10 @@ def run_b200(args, rank, world, local_rank):
                 checksum[0] += float(links_host[k][0, 0, 0]) + float(joints_host[k][-1, 0, 0])
             t = physics.iteration*model.timestep
             arg = 2*np.pi*freq_t*t - lag_t
-            torch.mul(cos_ph, amp_t*torch.sin(arg), out=wave_buf)
-            wave_buf.addcmul_(sin_ph, amp_t*torch.cos(arg))
-            if regular:
-                ctrl_view[k].copy_(wave_buf)
-            else:
+            out_buf = ctrl_host[k] if compact else wave_buf
+            torch.mul(cos_ph, amp_t*torch.sin(arg), out=out_buf)
+            out_buf.addcmul_(sin_ph, amp_t*torch.cos(arg))
+            if not compact:
                 ctrl_host[k].index_copy_(1, acts_t, wave_buf)
             pending[k] = physics.step_host(args.inner, ctrl=ctrl_host[k], links_row=links_host[k],
                                            joints_row=joints_host[k], pipelined=True)
@@ -559,11 +562,13 @@ def run_b200(args, rank, world, local_rank):
             'd2h_bytes_per_step': int((links_host.numel() + joints_host.numel())*4*world),
             'checksum': float(links_host[:, 0, 0].double().sum()) + checksum[0],
             'pipelined': 'device->host copy of launch i overlaps the kernels of launch i+1 (fb_step_host_async, three host buffer sets); ctrl is fetched from pinned host memory by the SMs on an upload stream',
+            'ctrl_up': (f'[n_envs, {len(acts)}] controlled (position) actuators of every launch, evaluated by a host-side '
+                        'travelling-wave controller' if compact else '[n_envs, nu]'),
             'host_cpus_bound': len(bound) if bound else None,
-            'rows_down': (f'last links row [n_envs, n_links, {len(lcols)} columns'
-                          + ('' if args.e2e_full_links else ': CoM position + orientation')
-                          + '] + joints row [n_envs, n_joints, 4 written columns: position, velocity, torque, '
-                          'limit force] of every launch'),
+            'rows_down': (f'of every launch, the last links row [n_envs, {len(litems)} link(s), {len(lcols)} columns'
+                          + ('' if args.e2e_links == 'full' else ': CoM position + orientation')
+                          + '] + the last joints row [n_envs, n_joints, 4 written columns: position, velocity, '
+                          'torque, limit force]; the rest of the log stays on the device (full_log_export)'),
         }
         if world == 1 and not args.no_export:
             # streamed export of the FULL log (every column of every kind, the arrays the

@@ -199,17 +199,29 @@ __global__ void __launch_bounds__(256) fb_gather_rows4_kernel(const float4 *__re
 }
 
 /* selected columns of ring row `row` of every environment -> dense [n_envs][n_items][n_sel] */
-struct FbColSel { int n; int col[32]; };
+/* n_sel_items > 0: only the listed items (fb_set_host_link_items), else all n_items */
+struct FbColSel { int n; int col[32]; int n_sel_items; int item[64]; };
 __global__ void fb_gather_cols_kernel(const float *__restrict__ log, long long row, int n_items, int n_cols,
                                       int vec, long long env_pad, int n_envs, FbColSel sel,
                                       float *__restrict__ out) {
   long long i = (long long)blockIdx.x*blockDim.x + threadIdx.x;
-  const long long per_env = (long long)n_items*sel.n;
+  const int out_items = sel.n_sel_items > 0 ? sel.n_sel_items : n_items;
+  const long long per_env = (long long)out_items*sel.n;
   if (i >= per_env*n_envs) return;
   const long long k = i/n_envs, env = i - k*n_envs;            /* env fastest: coalesced reads */
-  const int item = (int)(k/sel.n), c = sel.col[k - (long long)item*sel.n];
+  const int oi = (int)(k/sel.n), c = sel.col[k - (long long)oi*sel.n];
+  const int item = sel.n_sel_items > 0 ? sel.item[oi] : oi;
   const long long f = (long long)item*n_cols + c, nvec = (long long)n_items*n_cols/vec;
   out[env*per_env + k] = log[((row*nvec + f/vec)*env_pad + env)*vec + f % vec];
+}
+
+/* uploaded ctrl columns [n_envs][n_sel] -> ctrl[n_envs][nu] at the selected actuators */
+__global__ void fb_scatter_ctrl_kernel(const float *__restrict__ in, int n_envs, int nu, FbColSel sel,
+                                       float *__restrict__ ctrl) {
+  long long i = (long long)blockIdx.x*blockDim.x + threadIdx.x;
+  if (i >= (long long)n_envs*sel.n) return;
+  const long long env = i/sel.n;
+  ctrl[env*nu + sel.col[i - env*sel.n]] = in[i];
 }
 
 /* control sequence [K][n_envs][nu] (host order) -> [K][nu][env_pad] (environment-minor) */
@@ -267,6 +279,8 @@ struct FbHandle {
   float *gather_links, *gather_joints;   /* fb_step_host staging */
   int joint_sel_n, joint_sel[32];        /* fb_set_host_joint_columns: columns of the joints row fb_step_host returns (0 = all) */
   int link_sel_n, link_sel[32];          /* fb_set_host_link_columns: the same for the links row */
+  int link_items_n, link_items[64];      /* fb_set_host_link_items: links whose rows come down (0 = all) */
+  int ctrl_sel_n, ctrl_sel[32];          /* fb_set_host_ctrl_columns: actuators fb_step_host's ctrl carries (0 = all nu) */
   float *export_stage[2];                /* fb_export_rows: dense row staging, double-buffered */
   size_t export_stage_floats;
   float *gather_env;                     /* fb_export_farms staging: one environment's ring of one kind */
@@ -294,6 +308,7 @@ struct FbHandle {
   float *ctrl_stage;                 /* [n_envs][nu] landing buffer of the upload, copied to ctrl in stream order */
   int sms;
   cudaEvent_t ev_gather, ev_gathered[4], ev_copy[4];  /* copy-done events of the last four pipelined calls (ring) */
+  long long gather_it[4];            /* iteration whose ring row each of those calls gathers */
   long long host_calls;
 #endif
 };
@@ -476,11 +491,17 @@ static int launch(FbHandle *h, int mode, int n_steps, int want_derived) {
 #else
   int blocks = (P.n_envs + h->envs_per_block - 1)/h->envs_per_block;
   if (h->host_calls > 0) {
-    /* fb_step_host's row gathers run on the copy stream: this launch may overwrite ring rows, so
-     * it waits for the gathers that could still read them -- the latest one when this launch
-     * (or a reset) wraps the ring onto its row, else the one before it */
-    const bool wraps = mode != FB_MODE_STEP || 2LL*n_steps >= (long long)P.ring;
-    const long long dep = h->host_calls - (wraps ? 1 : 2);
+    /* fb_step_host's row gathers run on the gather stream, in call order.  This launch overwrites
+     * the ring rows of iterations it+1 .. it+n_steps, i.e. what iterations <= it+n_steps-ring left
+     * there: it waits for the LATEST gather that reads such a row (row-less fb_step launches in
+     * between count: the test is on iterations, not on this launch's length), which implies the
+     * earlier ones.  Gathers older than the four tracked events are waited for through the oldest
+     * tracked one; a reset waits for the latest. */
+    long long dep = -1;
+    const long long first = h->host_calls > 4 ? h->host_calls - 4 : 0;
+    for (long long g = h->host_calls - 1; g >= first; g--)
+      if (mode != FB_MODE_STEP || h->gather_it[g & 3] + P.ring <= h->it + n_steps) { dep = g; break; }
+    if (dep < 0 && first > 0) dep = first;       /* long done in practice; covers calls before the window */
     if (dep >= 0 && cudaStreamWaitEvent(h->stream, h->ev_gathered[dep & 3], 0) != cudaSuccess) return fail(dev_error());
   }
   cudaEventRecord(h->ev0, h->stream);
@@ -615,7 +636,7 @@ int fb_create(const FbModel *model, const FbFarms *farms, int n_envs, int device
   h->last_ms = 0.f; h->has_wc = false; h->gather_links = h->gather_joints = h->gather_env = nullptr;
   h->seq_dev = h->seq_stage = nullptr; h->seq_len = h->seq_pos = h->seq_cap = 0;
   h->cpg_on = false; memset(&h->cpg, 0, sizeof(h->cpg));
-  h->joint_sel_n = 0; h->link_sel_n = 0;
+  h->joint_sel_n = 0; h->link_sel_n = 0; h->link_items_n = 0; h->ctrl_sel_n = 0;
   h->export_stage[0] = h->export_stage[1] = nullptr; h->export_stage_floats = 0;
   h->fast_enabled = 1; h->fast_block = 1; h->fast_smem_bytes = 0; h->launch_parity = 0;
   h->con_thread = 1; h->log_used = 0;
@@ -663,6 +684,7 @@ int fb_create(const FbModel *model, const FbFarms *farms, int n_envs, int device
   for (auto &e : h->ev_copy) cudaEventCreateWithFlags(&e, cudaEventDisableTiming);
   for (auto &e : h->ev_gathered) cudaEventCreateWithFlags(&e, cudaEventDisableTiming);
   h->host_calls = 0;
+  for (auto &g : h->gather_it) g = 0;
   if (team_lanes != 0 && team_lanes != 8 && team_lanes != 16 && team_lanes != 32) {
     fb_destroy(h);
     return fail("fb_create: team_lanes must be 0, 8, 16 or 32");
@@ -1154,8 +1176,8 @@ static int step_host_impl(FbHandle *h, const float *ctrl, const float *qpos, con
      * launch is still running; the launch stream then takes it over with a device copy */
     cudaPointerAttributes pa;
     if (cudaPointerGetAttributes(&pa, ctrl) == cudaSuccess && pa.type == cudaMemoryTypeHost && pa.devicePointer) {
-      const long long nf = (long long)n*m.nu;
-      if (!h->ctrl_stage && alloc_arr(h, &h->ctrl_stage, (size_t)nf)) return fail("out of device memory (ctrl staging)");
+      const long long nf = (long long)n*(h->ctrl_sel_n > 0 ? h->ctrl_sel_n : m.nu);
+      if (!h->ctrl_stage && alloc_arr(h, &h->ctrl_stage, (size_t)n*m.nu)) return fail("out of device memory (ctrl staging)");
       const float *src = static_cast<const float *>(pa.devicePointer);
       const int v4 = ((reinterpret_cast<uintptr_t>(src) | reinterpret_cast<uintptr_t>(h->ctrl_stage) |
                        reinterpret_cast<uintptr_t>(P.ctrl)) & 15) == 0;
@@ -1163,6 +1185,12 @@ static int step_host_impl(FbHandle *h, const float *ctrl, const float *qpos, con
       fb_copy_kernel<<<h->sms*2, 256, 0, h->up_stream>>>(src, h->ctrl_stage, nf, v4);
       if (cudaEventRecord(h->ev_up, h->up_stream) != cudaSuccess ||
           cudaStreamWaitEvent(h->stream, h->ev_up, 0) != cudaSuccess) return fail(dev_error());
+      if (h->ctrl_sel_n > 0) {
+        FbColSel sel;
+        sel.n = h->ctrl_sel_n; sel.n_sel_items = 0;
+        for (int k = 0; k < 32; k++) sel.col[k] = k < sel.n ? h->ctrl_sel[k] : 0;
+        fb_scatter_ctrl_kernel<<<(unsigned)((nf + 255)/256), 256, 0, h->stream>>>(h->ctrl_stage, P.n_envs, m.nu, sel, P.ctrl);
+      } else
       fb_copy_kernel<<<h->sms*4, 256, 0, h->stream>>>(h->ctrl_stage, P.ctrl, nf, v4);
       if (cudaEventRecord(h->ev_stage_free, h->stream) != cudaSuccess) return fail(dev_error());
       h->launches += 2;
@@ -1171,9 +1199,30 @@ static int step_host_impl(FbHandle *h, const float *ctrl, const float *qpos, con
       cudaGetLastError();               /* pageable memory: cudaPointerGetAttributes may flag it */
     }
   }
-  if (ctrl && m.nu > 0 && !ctrl_done && h2d(P.ctrl, ctrl, n*m.nu*sizeof(float), h->stream)) return fail(dev_error());
+  if (ctrl && m.nu > 0 && !ctrl_done) {
+    if (h->ctrl_sel_n > 0) {
+      /* pageable memory: plain copy into the staging buffer, then the same scatter */
+      const long long nf = (long long)n*h->ctrl_sel_n;
+      if (!h->ctrl_stage && alloc_arr(h, &h->ctrl_stage, (size_t)n*m.nu)) return fail("out of device memory (ctrl staging)");
+      if (h2d(h->ctrl_stage, ctrl, (size_t)nf*sizeof(float), h->stream)) return fail(dev_error());
+      FbColSel sel;
+      sel.n = h->ctrl_sel_n; sel.n_sel_items = 0;
+      for (int k = 0; k < 32; k++) sel.col[k] = k < sel.n ? h->ctrl_sel[k] : 0;
+      fb_scatter_ctrl_kernel<<<(unsigned)((nf + 255)/256), 256, 0, h->stream>>>(h->ctrl_stage, P.n_envs, m.nu, sel, P.ctrl);
+      h->launches++;
+    } else if (h2d(P.ctrl, ctrl, n*m.nu*sizeof(float), h->stream)) {
+      return fail(dev_error());
+    }
+  }
 #else
-  if (ctrl && m.nu > 0 && h2d(P.ctrl, ctrl, n*m.nu*sizeof(float), h->stream)) return fail(dev_error());
+  if (ctrl && m.nu > 0) {
+    if (h->ctrl_sel_n > 0) {
+      for (size_t e = 0; e < n; e++)
+        for (int k = 0; k < h->ctrl_sel_n; k++) P.ctrl[e*m.nu + h->ctrl_sel[k]] = ctrl[e*h->ctrl_sel_n + k];
+    } else if (h2d(P.ctrl, ctrl, n*m.nu*sizeof(float), h->stream)) {
+      return fail(dev_error());
+    }
+  }
 #endif
   if (qpos && h2d(P.qpos, qpos, n*m.nq*sizeof(float), h->stream)) return fail(dev_error());
   if (qvel && h2d(P.qvel, qvel, n*m.nv*sizeof(float), h->stream)) return fail(dev_error());
@@ -1185,14 +1234,18 @@ static int step_host_impl(FbHandle *h, const float *ctrl, const float *qpos, con
   trace_mark(2, h->stream);
 #endif
   long long row = h->it % P.ring;
-  const int lf = m.n_links*(h->link_sel_n > 0 ? h->link_sel_n : 20);
+  const bool link_sel = h->link_sel_n > 0 || h->link_items_n > 0;
+  const int lsel_n = h->link_sel_n > 0 ? h->link_sel_n : 20, litems_n = h->link_items_n > 0 ? h->link_items_n : m.n_links;
+  const int lf = litems_n*lsel_n;
   const int jf = m.n_joints*(h->joint_sel_n > 0 ? h->joint_sel_n : m.joint_cols);
 #ifdef FB_HOST_EMU
   (void)wait;
   for (size_t e = 0; e < n; e++) {
-    const int lsel = h->link_sel_n > 0 ? h->link_sel_n : 20, lfull = m.n_links*20;
+    const int lsel = lsel_n, lfull = m.n_links*20;
+    (void)link_sel;
     for (int i = 0; links_row && i < lf; i++) {
-      const int item = i/lsel, c = h->link_sel_n > 0 ? h->link_sel[i - item*lsel] : i - item*lsel;
+      const int oi = i/lsel, c = h->link_sel_n > 0 ? h->link_sel[i - oi*lsel] : i - oi*lsel;
+      const int item = h->link_items_n > 0 ? h->link_items[oi] : oi;
       const long long f = (long long)item*20 + c, g = f/FB_VEC_LINKS;
       links_row[e*lf + i] = P.log_links[((row*(lfull/FB_VEC_LINKS) + g)*P.env_pad + e)*FB_VEC_LINKS + f % FB_VEC_LINKS];
     }
@@ -1223,10 +1276,12 @@ static int step_host_impl(FbHandle *h, const float *ctrl, const float *qpos, con
     if (cudaEventRecord(h->ev_gather, h->stream) != cudaSuccess ||
         cudaStreamWaitEvent(cs, h->ev_gather, 0) != cudaSuccess) return fail(dev_error());
     trace_mark(4, cs);
-    if (want_links && h->link_sel_n > 0) {
+    if (want_links && link_sel) {
       FbColSel sel;
-      sel.n = h->link_sel_n;
-      for (int k = 0; k < 32; k++) sel.col[k] = k < sel.n ? h->link_sel[k] : 0;
+      sel.n = lsel_n;
+      for (int k = 0; k < 32; k++) sel.col[k] = h->link_sel_n > 0 ? (k < sel.n ? h->link_sel[k] : 0) : (k < 20 ? k : 0);
+      sel.n_sel_items = h->link_items_n;
+      for (int k = 0; k < 64; k++) sel.item[k] = k < h->link_items_n ? h->link_items[k] : 0;
       long long total = (long long)n*lf;
       fb_gather_cols_kernel<<<(unsigned)((total + 255)/256), 256, 0, cs>>>(
           P.log_links, row, m.n_links, 20, FB_VEC_LINKS, P.env_pad, P.n_envs, sel, g_links);
@@ -1242,6 +1297,7 @@ static int step_host_impl(FbHandle *h, const float *ctrl, const float *qpos, con
     if (want_joints && h->joint_sel_n > 0) {
       FbColSel sel;
       sel.n = h->joint_sel_n;
+      sel.n_sel_items = 0;
       for (int k = 0; k < 32; k++) sel.col[k] = k < sel.n ? h->joint_sel[k] : 0;
       long long total = (long long)n*jf;
       fb_gather_cols_kernel<<<(unsigned)((total + 255)/256), 256, 0, cs>>>(
@@ -1254,6 +1310,7 @@ static int step_host_impl(FbHandle *h, const float *ctrl, const float *qpos, con
       h->launches++;
     }
     if (cudaEventRecord(h->ev_gathered[slot], cs) != cudaSuccess) return fail(dev_error());
+    h->gather_it[slot] = h->it;
     trace_mark(3, cs);
     cs = h->copy_stream;
     if (cudaStreamWaitEvent(cs, h->ev_gathered[slot], 0) != cudaSuccess) return fail(dev_error());
@@ -1360,6 +1417,28 @@ int fb_set_host_link_columns(FbHandle *h, int n, const int32_t *cols) {
   if (fb_host_wait(h)) return -1;
   h->link_sel_n = n;
   for (int k = 0; k < n; k++) h->link_sel[k] = cols[k];
+  return 0;
+}
+
+int fb_set_host_ctrl_columns(FbHandle *h, int n, const int32_t *cols) {
+  if (!h) return fail("null handle");
+  if (n < 0 || n > 32 || (n > 0 && !cols)) return fail("fb_set_host_ctrl_columns: 0..32 actuators");
+  for (int k = 0; k < n; k++)
+    if (cols[k] < 0 || cols[k] >= h->hm.m.nu) return fail("fb_set_host_ctrl_columns: actuator out of range");
+  if (fb_host_wait(h)) return -1;
+  h->ctrl_sel_n = n;
+  for (int k = 0; k < n; k++) h->ctrl_sel[k] = cols[k];
+  return 0;
+}
+
+int fb_set_host_link_items(FbHandle *h, int n, const int32_t *items) {
+  if (!h) return fail("null handle");
+  if (n < 0 || n > 64 || (n > 0 && !items)) return fail("fb_set_host_link_items: 0..64 links");
+  for (int k = 0; k < n; k++)
+    if (items[k] < 0 || items[k] >= h->hm.m.n_links) return fail("fb_set_host_link_items: link out of range");
+  if (fb_host_wait(h)) return -1;
+  h->link_items_n = n;
+  for (int k = 0; k < n; k++) h->link_items[k] = items[k];
   return 0;
 }
 

@@ -55,6 +55,8 @@ ABI_SYMBOLS = {
     'fb_host_wait': (ct.c_int, [_H]),
     'fb_set_host_joint_columns': (ct.c_int, [_H, ct.c_int, ct.POINTER(ct.c_int32)]),
     'fb_set_host_link_columns': (ct.c_int, [_H, ct.c_int, ct.POINTER(ct.c_int32)]),
+    'fb_set_host_link_items': (ct.c_int, [_H, ct.c_int, ct.POINTER(ct.c_int32)]),
+    'fb_set_host_ctrl_columns': (ct.c_int, [_H, ct.c_int, ct.POINTER(ct.c_int32)]),
     'fb_export_rows': (ct.c_int, [_H, ct.c_int, ct.c_int, ct.c_int, ct.c_void_p]),
     'fb_host_wait_slot': (ct.c_int, [_H, ct.c_int]),
     'fb_host_call_count': (ct.c_longlong, [_H]),
@@ -484,6 +486,20 @@ class BatchedPhysics:
         cols = [] if columns is None else [int(c) for c in columns]
         arr = (ct.c_int32*max(1, len(cols)))(*cols)
         self._check(self.lib.fb_set_host_link_columns(self._handle, len(cols), arr))
+
+    def set_host_ctrl_columns(self, actuators=None):
+        """Actuators the ``ctrl`` argument of ``step_host`` carries (``ctrl`` is then ``[n_envs,
+        len(actuators)]``; the other ctrl entries keep their device value); ``None`` = all."""
+        idx = [] if actuators is None else [int(i) for i in actuators]
+        arr = (ct.c_int32*max(1, len(idx)))(*idx)
+        self._check(self.lib.fb_set_host_ctrl_columns(self._handle, len(idx), arr))
+
+    def set_host_link_items(self, items=None):
+        """Links whose rows ``step_host`` downloads (``links_row`` is then ``[n_envs, len(items),
+        columns]``); ``None`` = every link."""
+        idx = [] if items is None else [int(i) for i in items]
+        arr = (ct.c_int32*max(1, len(idx)))(*idx)
+        self._check(self.lib.fb_set_host_link_items(self._handle, len(idx), arr))
 
     def export_rows(self, kind, row0, n_rows, out=None):
         """Ring rows ``row0 .. row0+n_rows-1`` (modulo the ring) of one log kind for EVERY

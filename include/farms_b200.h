@@ -254,8 +254,12 @@ int fb_step_host(FbHandle *h, const float *ctrl, const float *qpos, const float 
 /* Pipelined form: returns once everything is enqueued.  The device->host copies run on a
  * second stream, so the transfer of call i overlaps the kernels of call i+1; links_row /
  * joints_row (pinned) are complete after fb_host_wait() or after the NEXT-but-one call
- * returns -- alternate two host buffer pairs.  Inputs are consumed in stream order: `ctrl`
- * must stay untouched until the following call or fb_host_wait(). */
+ * returns -- alternate two host buffer pairs.
+ * Buffer reuse rule for the INPUTS: a pinned `ctrl` is read by the SMs asynchronously on an upload
+ * stream (and pinned qpos / qvel by cudaMemcpyAsync), so ctrl / qpos / qvel must stay unmodified
+ * until fb_host_wait_call() of this call's index (fb_host_call_count() before the call; calls that
+ * ask for no rows have no index) or fb_host_wait() returns -- rotate as many ctrl buffers as row
+ * buffer sets. */
 int fb_step_host_async(FbHandle *h, const float *ctrl, const float *qpos, const float *qvel,
                        int n_steps, float *links_row, float *joints_row);
 int fb_host_wait(FbHandle *h);
@@ -268,6 +272,13 @@ int fb_set_host_joint_columns(FbHandle *h, int n, const int32_t *cols);
  * the 20 physics.py:435-466 writes (e.g. CoM position + orientation, 7 columns = 35 % of the
  * bytes, for a host controller that does not read velocities).  n = 0: the full row (default). */
 int fb_set_host_link_columns(FbHandle *h, int n, const int32_t *cols);
+/* ... and which links: links_row becomes [n_envs][n][columns] with the listed links only (e.g. the
+ * head link for a controller that steers by its pose).  n = 0: every link (default). */
+int fb_set_host_link_items(FbHandle *h, int n, const int32_t *items);
+/* The upload side: `ctrl` of fb_step_host / fb_step_host_async becomes [n_envs][n] and carries the
+ * listed actuators only (what step_joints_control_* writes, task.py:309-346: the controlled
+ * joints' ctrl entries); the other entries of ctrl keep their device value.  n = 0: all nu. */
+int fb_set_host_ctrl_columns(FbHandle *h, int n, const int32_t *cols);
 /* Streamed export of whole ring rows of one log kind (0 links, 1 joints, 2 contacts, 3 xfrc) for
  * EVERY environment: rows row0 .. row0+n_rows-1 (ring indices, taken modulo the ring) as dense
  * float32 host memory [n_rows][n_envs][n_items*n_cols] (pinned recommended).  Row r of

@@ -354,7 +354,22 @@ def test_host_link_columns_and_row_export(emu_library):
     last = n_steps % ring
     assert np.array_equal(links, logs['links'][:, last][:, :, cols])
     assert np.array_equal(joints, logs['joints'][:, last])
+    physics.set_host_link_items([0, 5])
+    two = np.zeros((n, 2, len(cols)), np.float32)
+    # ... and ctrl goes up as three selected actuators, the others keeping their value
+    acts = [2, 7, 11]
+    physics.set_host_ctrl_columns(acts)
+    some = np.ascontiguousarray(np.arange(n*3, dtype=np.float32).reshape(n, 3)*1e-3)
+    physics.step_host(1, ctrl=some, links_row=two)
+    want_ctrl = np.array(ctrl, dtype=np.float32)
+    want_ctrl[:, acts] = some
+    assert np.array_equal(physics.ctrl, want_ctrl)
+    physics.set_host_ctrl_columns(None)
+    logs = physics.log_arrays()
+    assert np.array_equal(two, logs['links'][:, (n_steps + 1) % ring][:, [0, 5]][:, :, cols])
+    physics.set_host_link_items(None)
     physics.set_host_link_columns(None)
+    n_steps += 1
     full = np.zeros((n, nl, 20), np.float32)
     physics.step_host(1, links_row=full)
     logs = physics.log_arrays()
