@@ -91,7 +91,7 @@ struct FbFastParams {
 
 /* BLK environments per warp (32, or 16 in a half-filled warp).  MULTI: blocks of 2..8 warps
  * (blockDim.x/32) kept in step by a barrier per physics step (FbFast::run_t). */
-template <int BLK, int SLIM, int MULTI>
+template <int BLK, int SLIM, int MULTI, int LEAN = 0>
 __global__ void __launch_bounds__(MULTI ? 256 : 32)
 fb_fast_kernel(const __grid_constant__ FbFastParams Q) {
   extern __shared__ __align__(16) float fb_smem[];
@@ -107,7 +107,7 @@ fb_fast_kernel(const __grid_constant__ FbFastParams Q) {
   constexpr int TMA = FB_TMA_ENABLE && SLIM && MULTI;
   const size_t warp_floats = (size_t)n_float*BLK + (TMA ? FB_RING_BYTES/sizeof(float) : 0);
   /* L2-resident scratch [warp][field][lane]: compile-time strides, coalesced */
-  FbFast<BLK, SLIM, TMA> st(P, Q.rec, fb_smem + warp*warp_floats + lane,
+  FbFast<BLK, SLIM, TMA, LEAN> st(P, Q.rec, fb_smem + warp*warp_floats + lane,
                             P.fast_scratch + (size_t)wid*(SLIM ? P.m.X.n_scratch_slim : P.m.X.n_scratch)*BLK + lane,
                             valid ? env : 0);
   if (TMA) st.ring_setup(fb_smem + warp*warp_floats + (size_t)n_float*BLK, lane);
@@ -129,7 +129,7 @@ struct FbFastConParams {
 };
 static_assert(sizeof(FbFastConParams) <= 32764, "kernel parameters of fb_fastc_kernel exceed 32 KB");
 
-template <int BLK>
+template <int BLK, int LEAN = 0>
 __global__ void __launch_bounds__(BLK)
 fb_fastc_kernel(const __grid_constant__ FbFastConParams Q) {
   extern __shared__ __align__(16) float fb_smem[];
@@ -141,7 +141,7 @@ fb_fastc_kernel(const __grid_constant__ FbFastConParams Q) {
   const int env = identity ? i : P.pending[i];
   const int k0 = P.use_pending ? P.steps_done[env] : 0;
   const size_t t0 = (size_t)blockIdx.x*BLK;
-  FbFastCon<BLK> st(P, Q.rec, Q.cand, fb_smem + threadIdx.x, P.fast_scratch + t0*P.m.X.n_scratch + threadIdx.x,
+  FbFastCon<BLK, LEAN> st(P, Q.rec, Q.cand, fb_smem + threadIdx.x, P.fast_scratch + t0*P.m.X.n_scratch + threadIdx.x,
                     P.con_scratch + t0*P.m.X.n_con + threadIdx.x, env);
   const int coop = BLK == 32 && identity && P.m.X.coop_io && (blockIdx.x + 1)*BLK <= count;
   st.run_con(k0, coop, threadIdx.x);
@@ -261,6 +261,7 @@ struct FbHandle {
   int con_thread;                   /* 1: hand-overs go to the per-thread constrained kernel, 0: to the team kernel */
   int fast_slim;                    /* 1: SLIM layout of the unconstrained kernel (8 warps per SM; large batches) */
   int fast_wpb;                     /* warps per block of the unconstrained kernel (> 1: barrier per step) */
+  int fast_lean;                    /* 1: use the LEAN variants when the model allows (FARMS_B200_FAST_LEAN=0 switches them off) */
   size_t fast_slim_smem_bytes;
   size_t fast_smem_bytes;
   long long launch_parity;
@@ -467,7 +468,10 @@ static int launch(FbHandle *h, int mode, int n_steps, int want_derived) {
     std::vector<float> fg((size_t)(m.X.n_scratch > m.X.n_scratch_slim ? m.X.n_scratch : m.X.n_scratch_slim) + 8, 0.f);
     for (int env = 0; env < P.n_envs; env++) {
       int done;
-      if (h->fast_slim) { FbFast<1, 1> st(P, h->hm.rec.data(), fs.data(), fg.data(), env); done = st.run(0, 0); }
+      const bool lean = h->fast_lean && m.X.lean && !P.ctrl_seq;
+      if (h->fast_slim && lean) { FbFast<1, 1, 0, 1> st(P, h->hm.rec.data(), fs.data(), fg.data(), env); done = st.run(0, 0); }
+      else if (h->fast_slim) { FbFast<1, 1> st(P, h->hm.rec.data(), fs.data(), fg.data(), env); done = st.run(0, 0); }
+      else if (lean) { FbFast<1, 0, 0, 1> st(P, h->hm.rec.data(), fs.data(), fg.data(), env); done = st.run(0, 0); }
       else { FbFast<1> st(P, h->hm.rec.data(), fs.data(), fg.data(), env); done = st.run(0, 0); }
       if (done < n_steps) { P.steps_done[env] = done; P.pending[P.pending_count[P.parity]++] = env; }
     }
@@ -475,8 +479,13 @@ static int launch(FbHandle *h, int mode, int n_steps, int want_derived) {
       std::vector<float> fc((size_t)m.X.n_con + 8, 0.f);
       for (int i = 0; i < P.pending_count[P.parity]; i++) {
         const int env = P.pending[i];
-        FbFastCon<1> st(P, h->hm.rec.data(), h->hm.crec.data(), fs.data(), fg.data(), fc.data(), env);
-        st.run_con(P.steps_done[env], 0, 0);
+        if (h->fast_lean && m.X.lean && !P.ctrl_seq) {
+          FbFastCon<1, 1> st(P, h->hm.rec.data(), h->hm.crec.data(), fs.data(), fg.data(), fc.data(), env);
+          st.run_con(P.steps_done[env], 0, 0);
+        } else {
+          FbFastCon<1> st(P, h->hm.rec.data(), h->hm.crec.data(), fs.data(), fg.data(), fc.data(), env);
+          st.run_con(P.steps_done[env], 0, 0);
+        }
       }
     }
   }
@@ -515,17 +524,32 @@ static int launch(FbHandle *h, int mode, int n_steps, int want_derived) {
       const int wblocks = (warps + wpb - 1)/wpb;
       size_t bytes = (h->fast_slim ? h->fast_slim_smem_bytes : h->fast_smem_bytes)*(h->fast_block == 32 ? wpb : 1);
       if (FB_TMA_ENABLE && h->fast_slim && wpb > 1) bytes += (size_t)wpb*FB_RING_BYTES;      /* TMA ring of every warp */
-      if (h->fast_block == 16) fb_fast_kernel<16, 0, 0><<<fblocks, 16, bytes, h->stream>>>(*h->fastQ);
-      else if (h->fast_slim && wpb > 1) fb_fast_kernel<32, 1, 1><<<wblocks, 32*wpb, bytes, h->stream>>>(*h->fastQ);
-      else if (h->fast_slim) fb_fast_kernel<32, 1, 0><<<warps, 32, bytes, h->stream>>>(*h->fastQ);
-      else fb_fast_kernel<32, 0, 0><<<warps, 32, bytes, h->stream>>>(*h->fastQ);
+      /* LEAN variants: same arithmetic with the model's unused paths compiled out (smaller loops) */
+      const bool lean = h->fast_lean && P.m.X.lean && !P.ctrl_seq;
+      if (h->fast_block == 16) {
+        if (lean) fb_fast_kernel<16, 0, 0, 1><<<fblocks, 16, bytes, h->stream>>>(*h->fastQ);
+        else fb_fast_kernel<16, 0, 0><<<fblocks, 16, bytes, h->stream>>>(*h->fastQ);
+      } else if (h->fast_slim && wpb > 1) {
+        if (lean) fb_fast_kernel<32, 1, 1, 1><<<wblocks, 32*wpb, bytes, h->stream>>>(*h->fastQ);
+        else fb_fast_kernel<32, 1, 1><<<wblocks, 32*wpb, bytes, h->stream>>>(*h->fastQ);
+      } else if (h->fast_slim) {
+        if (lean) fb_fast_kernel<32, 1, 0, 1><<<warps, 32, bytes, h->stream>>>(*h->fastQ);
+        else fb_fast_kernel<32, 1, 0><<<warps, 32, bytes, h->stream>>>(*h->fastQ);
+      } else {
+        if (lean) fb_fast_kernel<32, 0, 0, 1><<<warps, 32, bytes, h->stream>>>(*h->fastQ);
+        else fb_fast_kernel<32, 0, 0><<<warps, 32, bytes, h->stream>>>(*h->fastQ);
+      }
     }
     h->launches++;
     if (con_thread) {
       h->conQ->P = P;
-      switch (h->fast_block) {
-        case 16: fb_fastc_kernel<16><<<fblocks, 16, h->fast_smem_bytes, h->stream>>>(*h->conQ); break;
-        default: fb_fastc_kernel<32><<<fblocks, 32, h->fast_smem_bytes, h->stream>>>(*h->conQ); break;
+      const bool clean = h->fast_lean && P.m.X.lean && !P.ctrl_seq;
+      if (h->fast_block == 16) {
+        if (clean) fb_fastc_kernel<16, 1><<<fblocks, 16, h->fast_smem_bytes, h->stream>>>(*h->conQ);
+        else fb_fastc_kernel<16><<<fblocks, 16, h->fast_smem_bytes, h->stream>>>(*h->conQ);
+      } else {
+        if (clean) fb_fastc_kernel<32, 1><<<fblocks, 32, h->fast_smem_bytes, h->stream>>>(*h->conQ);
+        else fb_fastc_kernel<32><<<fblocks, 32, h->fast_smem_bytes, h->stream>>>(*h->conQ);
       }
     }
   }
@@ -551,8 +575,12 @@ static int fb_slim_attributes(FbHandle *h, int max_smem) {
   if (fit > 8) fit = 8;
   cudaError_t ce = cudaFuncSetAttribute(fb_fast_kernel<32, 1, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, b1);
   if (ce == cudaSuccess) ce = cudaFuncSetAttribute(fb_fast_kernel<32, 1, 0>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+  if (ce == cudaSuccess) ce = cudaFuncSetAttribute(fb_fast_kernel<32, 1, 0, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, b1);
+  if (ce == cudaSuccess) ce = cudaFuncSetAttribute(fb_fast_kernel<32, 1, 0, 1>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
   if (ce == cudaSuccess && fit >= 2) ce = cudaFuncSetAttribute(fb_fast_kernel<32, 1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, fit*(b1 + (FB_TMA_ENABLE ? FB_RING_BYTES : 0)));
   if (ce == cudaSuccess) ce = cudaFuncSetAttribute(fb_fast_kernel<32, 1, 1>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+  if (ce == cudaSuccess && fit >= 2) ce = cudaFuncSetAttribute(fb_fast_kernel<32, 1, 1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, fit*(b1 + (FB_TMA_ENABLE ? FB_RING_BYTES : 0)));
+  if (ce == cudaSuccess) ce = cudaFuncSetAttribute(fb_fast_kernel<32, 1, 1, 1>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
   if (ce != cudaSuccess) return fail(std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(ce));
   if (h->fast_wpb > fit) h->fast_wpb = fit;
   if (h->fast_wpb < 2) h->fast_wpb = 1;
@@ -642,6 +670,8 @@ int fb_create(const FbModel *model, const FbFarms *farms, int n_envs, int device
   h->con_thread = 1; h->log_used = 0;
   if (const char *ev = getenv("FARMS_B200_CON_THREAD")) h->con_thread = atoi(ev) != 0;
   h->fast_slim = 0; h->fast_slim_smem_bytes = 0; h->fast_wpb = 1;
+  h->fast_lean = 1;
+  if (const char *ev = getenv("FARMS_B200_FAST_LEAN")) h->fast_lean = atoi(ev) != 0;
   if (const char *ev = getenv("FARMS_B200_FAST_SLIM")) h->fast_slim = atoi(ev) != 0;
 #ifndef FB_HOST_EMU
   h->fastQ = nullptr; h->conQ = nullptr;
@@ -739,8 +769,8 @@ int fb_create(const FbModel *model, const FbFarms *farms, int n_envs, int device
       if (ce == cudaSuccess) ce = cudaFuncSetAttribute(K_, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes); \
       if (ce == cudaSuccess) ce = cudaFuncSetAttribute(K_, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
       switch (h->fast_block) {
-        case 16: FB_SET_SMEM((fb_fast_kernel<16, 0, 0>)) FB_SET_SMEM(fb_fastc_kernel<16>) break;
-        default: FB_SET_SMEM((fb_fast_kernel<32, 0, 0>)) FB_SET_SMEM(fb_fastc_kernel<32>) break;
+        case 16: FB_SET_SMEM((fb_fast_kernel<16, 0, 0>)) FB_SET_SMEM((fb_fast_kernel<16, 0, 0, 1>)) FB_SET_SMEM(fb_fastc_kernel<16>) FB_SET_SMEM((fb_fastc_kernel<16, 1>)) break;
+        default: FB_SET_SMEM((fb_fast_kernel<32, 0, 0>)) FB_SET_SMEM((fb_fast_kernel<32, 0, 0, 1>)) FB_SET_SMEM(fb_fastc_kernel<32>) FB_SET_SMEM((fb_fastc_kernel<32, 1>)) break;
       }
 #undef FB_SET_SMEM
       if (const char *ev = getenv("FARMS_B200_FAST_WPB")) h->fast_wpb = atoi(ev);
@@ -1552,6 +1582,14 @@ int fb_set_fast_slim(FbHandle *h, int enable) {
   h->fast_slim = enable != 0;
   return 0;
 }
+/* LEAN variants of the unconstrained kernel (fb_fast.h): on by default when the model allows */
+int fb_set_fast_lean(FbHandle *h, int enable) {
+  if (!h) return fail("null handle");
+  h->fast_lean = enable != 0;
+  return 0;
+}
+/* 1 when fb_step launches the LEAN variant for this model (a control sequence falls back) */
+int fb_fast_lean(FbHandle *h) { return h && h->fast_enabled && h->fast_lean && h->hm.m.X.ok && h->hm.m.X.lean ? 1 : 0; }
 /* environments the team kernel had to finish in the last fb_step (synchronises) */
 int fb_last_pending(FbHandle *h, int *count) {
   if (!h || !count) return fail("null argument");

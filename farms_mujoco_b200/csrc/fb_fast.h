@@ -253,6 +253,16 @@ FB_DEV void fb_fence_proxy_async() {
 /* shared memory of one warp's ring: the stages + one 8-byte mbarrier per stage, padded to 128 B */
 #define FB_RING_BYTES ((FB_RING*FB_RING_FIELDS*32*4 + 8*FB_RING + 127)/128*128)
 
+/* body loops of the three sweeps: -DFB_BODY_UNROLL=2 lets ptxas overlap the tail of one body with
+ * the head of the next (measured; default: not unrolled) */
+#if defined(FB_BODY_UNROLL) && !defined(FB_HOST_EMU)
+#define FB_STR_(x) #x
+#define FB_STR(x) FB_STR_(x)
+#define FB_BODY_LOOP _Pragma(FB_STR(unroll FB_BODY_UNROLL))
+#else
+#define FB_BODY_LOOP
+#endif
+
 template <int SYNC> FB_DEV void fb_block_sync() {
 #ifndef FB_HOST_EMU
   if (SYNC) __syncthreads();
@@ -262,7 +272,13 @@ template <int SYNC> FB_DEV void fb_block_sync() {
 /* TMA = 1 (SLIM layout in multi-warp blocks): the per-body scratch block is not fetched into
  * registers one body ahead (16-17 long-lived LDG results per thread that tie up a scoreboard:
  * r2a's top stalls) but staged in a small shared-memory ring by bulk copies, two bodies ahead. */
-template <int BLK, int SLIM = 0, int TMA = 0> struct FbFast {
+/* LEAN = 1: the model (DevFastLayout::lean) has hinge joints only, anchors at the body origins,
+ * axisymmetric inertias, the linear actuation form on every joint and the farms joints-row layout,
+ * and the launch reads no control sequence: the slide-joint, general-inertia, generic-actuation,
+ * anchor-offset and generic-column paths are compiled out.  Same arithmetic on the paths that
+ * remain (bit-identical results); the point is the SIZE of the three body loops -- they run out of
+ * a 32 KB instruction cache, and unrolling them by two (60 KB) was measured 10-25 % slower. */
+template <int BLK, int SLIM = 0, int TMA = 0, int LEAN = 0> struct FbFast {
   /* SLIM scratch block: W[6] U 1/d trq q qd V[6] tc tu -- the first 17 are one contiguous run */
   enum { NF = SLIM ? 7 : FB_NF, GNF = SLIM ? FG_NF + 6 : FG_NF, FG_V = SLIM ? 11 : FG_NF,
          FGTC = SLIM ? 17 : FG_TC, FGTU = SLIM ? 18 : FG_TU };
@@ -577,6 +593,7 @@ FB_UNROLL
      * from the scratch while the previous body is computed -- issued at its use it cost a full L2
      * round trip per branch (r1aq: 6 % of the stall samples together with its pass-3 twin) */
     float nvp[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+FB_BODY_LOOP
     for (int b = 1; b < nb; b++) {
       const FastRec &rc0 = rec[b];
       struct { int parent, jtype, flags, pblk, link, chk0, chk1; float dpos[3], bquat[4], axis[3], qpos0, lo, hi, margin, hloc[3], chk[4], jpos[3]; } rc;
@@ -662,7 +679,7 @@ FB_UNROLL
         m_rot(Rp, rc.dpos[0], rc.dpos[1], rc.dpos[2], r);
         Quat bq = {rc.bquat[0], rc.bquat[1], rc.bquat[2], rc.bquat[3]};
         q = q_mul(qp, bq);
-        if (rc.flags & FT_HAS_JPOS) {      /* the anchor is fixed in the frame before the joint rotation */
+        if (!LEAN && (rc.flags & FT_HAS_JPOS)) {      /* the anchor is fixed in the frame before the joint rotation */
           float Rpre[9], t[3];
           q_mat(q_normalize(q), Rpre);
           m_rot(Rpre, rc.jpos[0], rc.jpos[1], rc.jpos[2], t);
@@ -672,7 +689,7 @@ FB_UNROLL
           const float qj = cq;
           qd = cqd;
           dq = qj - rc.qpos0;
-          if (jtype == FB_JNT_HINGE) {
+          if (LEAN || jtype == FB_JNT_HINGE) {
             float sn, cs;
             fb_sincos_half(0.5f*dq, &sn, &cs);
             Quat ql = {cs, rc.axis[0]*sn, rc.axis[1]*sn, rc.axis[2]*sn};
@@ -684,13 +701,13 @@ FB_UNROLL
         q_mat(q, R);
         float ax[3] = {0.f, 0.f, 0.f}, cr[3];
         if (jtype >= 0) m_rot(R, rc.axis[0], rc.axis[1], rc.axis[2], ax);
-        if (jtype == FB_JNT_SLIDE) { r[0] += ax[0]*dq; r[1] += ax[1]*dq; r[2] += ax[2]*dq; }
+        if (!LEAN && jtype == FB_JNT_SLIDE) { r[0] += ax[0]*dq; r[1] += ax[1]*dq; r[2] += ax[2]*dq; }
         v_cross(vp, r, cr);                      /* w_parent x r */
 FB_UNROLL
         for (int k = 0; k < 3; k++) {
           o[k] = op[k] + r[k];
           v[k] = vp[k] + (jtype == FB_JNT_HINGE ? ax[k]*qd : 0.f);
-          v[3 + k] = vp[3 + k] + cr[k] + (jtype == FB_JNT_SLIDE ? ax[k]*qd : 0.f);
+          v[3 + k] = vp[3 + k] + cr[k] + (!LEAN && jtype == FB_JNT_SLIDE ? ax[k]*qd : 0.f);
         }
       }
       if (SLIM && b + 1 < nb) {
@@ -719,7 +736,7 @@ FB_UNROLL
 FB_UNROLL
       for (int k = 0; k < 9; k++) lastR[k] = R[k];
       float xpos[3] = {rootpos[0] + o[0], rootpos[1] + o[1], rootpos[2] + o[2]};
-      if (rc.flags & FT_HAS_JPOS) {
+      if (!LEAN && (rc.flags & FT_HAS_JPOS)) {
         float t[3];
         m_rot(R, rc.jpos[0], rc.jpos[1], rc.jpos[2], t);
         xpos[0] -= t[0]; xpos[1] -= t[1]; xpos[2] -= t[2];
@@ -794,6 +811,7 @@ FB_UNROLL
     }
     float *pb = block(nb - 1) + NF*BLK;
     float *pg = gblock(nb - 1) + GNF*BLK;
+FB_BODY_LOOP
     for (int b = nb - 1; b >= 1; b--) {
       const FastRec &rc = rec[b];
       /* issue the record loads of this body now (see FB_PIN_F) */
@@ -864,7 +882,7 @@ FB_UNROLL
           for (int k = 0; k < 3; k++) { fx[k] += Fw[k]; fx[3 + k] += cr[k]; }
         }
       }
-      if (flags & FT_AXISYM) {
+      if (LEAN || (flags & FT_AXISYM)) {
         /* Iw = Ia 1 + dI n n', n = R n_body */
         float n[3];
         m_rot(R, rc.Ib[2], rc.Ib[3], rc.Ib[4], n);
@@ -949,9 +967,9 @@ FB_UNROLL
         const float qj = cx[6], qd = cx[7];
         float ax[3], U[6], c[6], tau, trq;
         m_rot(R, rc.axis[0], rc.axis[1], rc.axis[2], ax);
-        if (flags & FT_ACT_SIMPLE) {
+        if (LEAN || (flags & FT_ACT_SIMPLE)) {
           float tc = cx[8], tu = cx[9];
-          if (seqk) seq_constants(rc, seqk, &tc, &tu);
+          if (!LEAN && seqk) seq_constants(rc, seqk, &tc, &tu);
           tau = tc + rc.Kq*qj + rc.Kqd*qd;
           if (flags & FT_HAS_WAVE) {
             float ph = 6.283185307179586f*rc.wfreq*time - rc.wlag + env_phase;
@@ -968,7 +986,7 @@ FB_UNROLL
         if (MODE == 2) tau += fb_ld_scr(nblock(b) + NB_TAUC*BLK);
         float d, u;
         float aq[3] = {ax[0]*qd, ax[1]*qd, ax[2]*qd};
-        if (jtype == FB_JNT_HINGE) {
+        if (LEAN || jtype == FB_JNT_HINGE) {
           sym_mul(I.A, ax, U);
           ht_mul(I.H, ax, U + 3);
           d = ax[0]*U[0] + ax[1]*U[1] + ax[2]*U[2];
@@ -1083,6 +1101,7 @@ FB_UNROLL
     float *pb = block(1) - NF*BLK;
     float *pg = gblock(1) - GNF*BLK;
     float nap[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};     /* SLIM: acceleration of the parent of the next body when that is a branch child */
+FB_BODY_LOOP
     for (int b = 1; b < nb; b++) {
       const FastRec &rc = rec[b];
       FB_PIN_I(rc.jtype); FB_PIN_I(rc.flags); FB_PIN_I(SLIM ? rc.pblk7 : rc.pblk); FB_PIN_I(rc.parent); FB_PIN_I(rc.fj);
@@ -1188,7 +1207,7 @@ FB_UNROLL
 FB_UNROLL
           for (int k = 0; k < 6; k++) U[k] = cx[k];
           float aq[3] = {ax[0]*qd, ax[1]*qd, ax[2]*qd}, c[3];
-          if (jtype == FB_JNT_HINGE) {
+          if (LEAN || jtype == FB_JNT_HINGE) {
             v_cross(v, aq, c);
             a[0] += c[0]; a[1] += c[1]; a[2] += c[2];
             v_cross(v + 3, aq, c);
@@ -1199,7 +1218,7 @@ FB_UNROLL
           }
           float ua = U[0]*a[0] + U[1]*a[1] + U[2]*a[2] + U[3]*a[3] + U[4]*a[4] + U[5]*a[5];
           const float qdd = (cx[6] - ua)*cx[7];
-          if (jtype == FB_JNT_HINGE) { a[0] += ax[0]*qdd; a[1] += ax[1]*qdd; a[2] += ax[2]*qdd; }
+          if (LEAN || jtype == FB_JNT_HINGE) { a[0] += ax[0]*qdd; a[1] += ax[1]*qdd; a[2] += ax[2]*qdd; }
           else { a[3] += ax[0]*qdd; a[4] += ax[1]*qdd; a[5] += ax[2]*qdd; }
           const float qdn = qd + hdt*qdd, qn = qj + hdt*qdn;
           fb_st_scr(pg + FG_QD*BLK, qdn);
@@ -1216,7 +1235,7 @@ FB_UNROLL
             /* The other columns of the row (physics.py:481-524 leaves 14 of the 18 untouched) are
              * zero in the log from its allocation on and no kernel writes them; the limit-force pair
              * is written by constrained steps, and here only over a row that may hold one. */
-            if (m.X.jrow_std) {
+            if (LEAN || m.X.jrow_std) {
               /* farms layout: 18 columns, position 0, velocity 1, torque 11, limit force 16 */
               fb_st2(row, qn, jv);
               fb_st2(row + 5*ev, 0.f, trq);

@@ -58,8 +58,9 @@ static double *fb_emu_stats = 0;
 #define FB_FFSLL(x) __ffsll((long long)(x))
 #endif
 
-template <int BLK> struct FbFastCon : FbFast<BLK> {
-  typedef FbFast<BLK> Base;
+/* LEAN: as in FbFast (hinge joints only, axisymmetric inertias, ...): the unused paths compiled out */
+template <int BLK, int LEAN = 0> struct FbFastCon : FbFast<BLK, 0, 0, LEAN> {
+  typedef FbFast<BLK, 0, 0, LEAN> Base;
   using Base::P; using Base::m; using Base::rec; using Base::s; using Base::env; using Base::gs;
   using Base::cs; using Base::csc; using Base::crec; using Base::hm; using Base::hany;
   using Base::rt; using Base::rootpos; using Base::rqn;
@@ -99,7 +100,7 @@ template <int BLK> struct FbFastCon : FbFast<BLK> {
     const Quat q = {pb[(FB_QUAT)*BLK], pb[(FB_QUAT + 1)*BLK], pb[(FB_QUAT + 2)*BLK], pb[(FB_QUAT + 3)*BLK]};
     q_mat(q, R);
     m_rot(R, rc.hloc[0], rc.hloc[1], rc.hloc[2], h);
-    if (rc.flags & FT_AXISYM) {
+    if (LEAN || (rc.flags & FT_AXISYM)) {
       float n[3];
       m_rot(R, rc.Ib[2], rc.Ib[3], rc.Ib[4], n);
       const float ia = rc.Ib[0], d0 = rc.Ib[1]*n[0], d1 = rc.Ib[1]*n[1], d2 = rc.Ib[1]*n[2];
@@ -327,7 +328,7 @@ FB_UNROLL
           m_rot(R, rc.axis[0], rc.axis[1], rc.axis[2], ax);
           const float *U = cx;
           float aq[3] = {ax[0]*qd, ax[1]*qd, ax[2]*qd}, c[3];
-          if (jtype == FB_JNT_HINGE) {
+          if (LEAN || jtype == FB_JNT_HINGE) {
             v_cross(v, aq, c);
             a[0] += c[0]; a[1] += c[1]; a[2] += c[2];
             v_cross(v + 3, aq, c);
@@ -338,7 +339,7 @@ FB_UNROLL
           }
           const float ua = U[0]*a[0] + U[1]*a[1] + U[2]*a[2] + U[3]*a[3] + U[4]*a[4] + U[5]*a[5];
           const float qdd = (cx[7] - ua)*cx[6];
-          if (jtype == FB_JNT_HINGE) {
+          if (LEAN || jtype == FB_JNT_HINGE) {
 FB_UNROLL
             for (int k = 0; k < 3; k++) { a[k] += ax[k]*qdd; al[k] += ax[k]*qdd; }
           } else {
@@ -501,7 +502,7 @@ FB_UNROLL
         float ax[3], U[6], d, u;
         m_rot(R, rc.axis[0], rc.axis[1], rc.axis[2], ax);
         /* gradient entry of this joint: what is left of the previous one, minus the switched rows */
-        const float g = keep*md - dtau - (jtype == FB_JNT_HINGE ? ax[0]*W[0] + ax[1]*W[1] + ax[2]*W[2]
+        const float g = keep*md - dtau - ((LEAN || jtype == FB_JNT_HINGE) ? ax[0]*W[0] + ax[1]*W[1] + ax[2]*W[2]
                                                                  : ax[0]*W[3] + ax[1]*W[4] + ax[2]*W[5]);
         fb_st_scr(pn + NB_MD*BLK, g);
         const float tau = -g;
@@ -511,7 +512,7 @@ FB_UNROLL
           if (lim4[0] > 0.f && rlo < 0.f) dl += lim4[0];
           if (lim4[1] > 0.f && rhi < 0.f) dl += lim4[1];
         }
-        if (jtype == FB_JNT_HINGE) {
+        if (LEAN || jtype == FB_JNT_HINGE) {
           sym_mul(I.A, ax, U);
           ht_mul(I.H, ax, U + 3);
           d = ax[0]*U[0] + ax[1]*U[1] + ax[2]*U[2];
@@ -641,7 +642,7 @@ FB_UNROLL
           const float *U = cx;
           const float ua = U[0]*al[0] + U[1]*al[1] + U[2]*al[2] + U[3]*al[3] + U[4]*al[4] + U[5]*al[5];
           const float pj = (cx[7] - ua)*cx[6];
-          if (jtype == FB_JNT_HINGE) { al[0] += ax[0]*pj; al[1] += ax[1]*pj; al[2] += ax[2]*pj; }
+          if (LEAN || jtype == FB_JNT_HINGE) { al[0] += ax[0]*pj; al[1] += ax[1]*pj; al[2] += ax[2]*pj; }
           else { al[3] += ax[0]*pj; al[4] += ax[1]*pj; al[5] += ax[2]*pj; }
           fb_st_scr(pn + NB_P*BLK, pj);
           g0 += pj*cx[8];
@@ -741,7 +742,7 @@ FB_UNROLL
       if (jtype >= 0) {
         float ax[3];
         m_rot(R, rc.axis[0], rc.axis[1], rc.axis[2], ax);
-        const float mp = (jtype == FB_JNT_HINGE ? ax[0]*F[0] + ax[1]*F[1] + ax[2]*F[2]
+        const float mp = ((LEAN || jtype == FB_JNT_HINGE) ? ax[0]*F[0] + ax[1]*F[1] + ax[2]*F[2]
                                                 : ax[0]*F[3] + ax[1]*F[4] + ax[2]*F[5]) + rc.armature*pj;
         fb_st_scr(pn + NB_MD*BLK, mp);
         pMp += pj*mp;

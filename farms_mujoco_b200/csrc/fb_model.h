@@ -128,6 +128,8 @@ struct DevFastLayout {
   int n_float_slim, n_scratch_slim;   /* SLIM variant of the unconstrained kernel (fb_fast.h) */
   int n_con;            /* global scratch floats per environment of the constrained step (fb_fastc.h) */
   int con_ok;           /* 1 when the per-thread constrained step covers the model (else: team kernel) */
+  int lean;             /* 1: hinge joints only, anchors at the body origins, axisymmetric inertias, the linear
+                         * actuation form on every joint, farms joints-row layout (FbFast<.., LEAN = 1>) */
 };
 
 /* scratch of the per-thread constrained step (fb_fastc.h), element i of thread t at i*BLK + t:
@@ -798,6 +800,14 @@ inline bool fb_build_model(const FbModel *fm, const FbFarms *ff, const FbWaveCon
     X.jrow_std = m.joint_cols == 18 && m.col_jpos == 0 && m.col_jvel == 1 && m.col_jtrq == 11 && m.col_jlim == 16;
     X.coop_io = fm->nq + nv + (nu > 0 ? nu : 1) + 6*nb <= X.n_float;
     X.coop_io2 = fm->nq + nv + (nu > 0 ? nu : 1) <= X.n_float_slim && 6*nb <= X.n_float_slim;
+    X.lean = X.ok && X.jrow_std;
+    for (int b = 1; b < nb; b++) {
+      const FastRec &r = rec[b];
+      if (r.flags & FT_HAS_JPOS) X.lean = 0;
+      if (!(r.flags & FT_AXISYM)) X.lean = 0;
+      if (r.jtype == FB_JNT_SLIDE) X.lean = 0;
+      if (r.jtype == FB_JNT_HINGE && !(r.flags & FT_ACT_SIMPLE)) X.lean = 0;
+    }
   }
 
   /* water + units */

@@ -74,6 +74,8 @@ ABI_SYMBOLS = {
     'fb_fast_smem_bytes_per_env': (ct.c_int, [_H]),
     'fb_set_fast_slim': (ct.c_int, [_H, ct.c_int]),
     'fb_fast_slim': (ct.c_int, [_H]),
+    'fb_set_fast_lean': (ct.c_int, [_H, ct.c_int]),
+    'fb_fast_lean': (ct.c_int, [_H]),
     'fb_last_pending': (ct.c_int, [_H, ct.POINTER(ct.c_int)]),
     'fb_measure_fp32_peak': (ct.c_int, [ct.c_int, ct.POINTER(ct.c_double)]),
     'fb_team_lanes': (ct.c_int, [_H]),
@@ -554,6 +556,15 @@ class BatchedPhysics:
     @property
     def fast_slim(self):
         return int(self.lib.fb_fast_slim(self._handle))
+
+    def set_fast_lean(self, enable):
+        """Use (default) or not the LEAN variants of the unconstrained kernel (fb_set_fast_lean)."""
+        self._check(self.lib.fb_set_fast_lean(self._handle, int(bool(enable))))
+
+    @property
+    def fast_lean(self):
+        """True when ``step`` launches the LEAN variant for this model."""
+        return bool(self.lib.fb_fast_lean(self._handle))
 
     def set_constraint_path(self, per_thread):
         """Who finishes environments with an active joint limit / plane contact: ``True``

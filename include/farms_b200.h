@@ -322,6 +322,13 @@ int fb_fast_smem_bytes_per_env(FbHandle *h);
  * the regular layout keeps resident (n_envs/32 > 4 x SMs); results are bit-identical to the regular
  * layout.  fb_fast_slim: 0 or the warps per block. */
 int fb_set_fast_slim(FbHandle *h, int enable);
+/* LEAN variants of the unconstrained kernel: when every joint is a hinge anchored at its body's
+ * origin, every inertia axisymmetric, every joint's actuation the unclamped linear form and the
+ * joints row the farms layout, fb_step launches a variant with the other paths compiled out (same
+ * arithmetic, smaller loops; launches that read a control sequence use the general one).
+ * fb_set_fast_lean(h, 0) forces the general variant; fb_fast_lean = 1 when the lean one applies. */
+int fb_set_fast_lean(FbHandle *h, int enable);
+int fb_fast_lean(FbHandle *h);
 int fb_fast_slim(FbHandle *h);
 int fb_last_pending(FbHandle *h, int *count);
 

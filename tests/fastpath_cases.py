@@ -154,6 +154,9 @@ def check_ctrl_sequence(library, spec, n_envs=4, n_steps=9, free_base=True):
     outs = []
     for mode in ('stepwise', 'fused'):
         physics = BatchedPhysics.from_spec(spec, n_envs, buffer_size=n_steps + 1, library=library)
+        # launches that read a control sequence use the general kernel variant; bit-identity with
+        # the step-by-step run holds within that variant (the LEAN one agrees to a few ulp)
+        physics.set_fast_lean(False)
         physics.reset(qpos0, qvel0)
         if mode == 'stepwise':
             for k in range(n_steps):
@@ -342,3 +345,53 @@ def check_device_cpg(library, n_envs=3, n_it=40, chunk=8, tol=2e-5):
     for kind in ('links', 'joints', 'xfrc'):
         err = log_error(kind, logs[True][kind], logs[False][kind])
         assert err < tol, (kind, err)
+
+
+LEAN_TOL = 1e-5
+
+
+def check_lean_variant(library, names=('swimmer8', 'salamander_swim', 'salamander'), n_envs=5, slims=(0,)):
+    """LEAN variants of the unconstrained kernel (the model's unused paths compiled out) against the
+    general one, in every layout: the same arithmetic -- the two are separate compilations, so the
+    compiler may contract a multiply-add in one and not in the other: agreement to a few ulp
+    (LEAN_TOL = 1e-5, group-wise relative, over 8 steps: drag forces square the velocity differences); the LAYOUTS of the general variant give the same
+    bits, those of the LEAN variant agree to the same tolerance.
+    Models outside the subset report fast_lean = False."""
+    import variant_models
+    from farms_mujoco_b200.engine import BatchedPhysics
+    for name in names:
+        spec, model, qpos0, qvel0, ctrl = make_case(name, n_envs)
+        outs = {}
+        for slim in slims:
+            for lean in (True, False):
+                physics = BatchedPhysics.from_spec(spec, n_envs, buffer_size=9, library=library)
+                if slim:
+                    physics.set_fast_slim(slim)
+                physics.set_fast_lean(lean)
+                assert physics.fast_lean == lean, name
+                physics.reset(qpos0, qvel0)
+                physics.set_ctrl(ctrl)
+                physics.step(5)
+                physics.step(3)
+                outs[slim, lean] = (physics.qpos, physics.qvel, physics.xfrc_applied, physics.log_arrays())
+        for slim in slims:
+            a, b = outs[slim, True], outs[slim, False]
+            for env in range(n_envs):
+                errs = state_errors(a[0][env], a[1][env], b[0][env], b[1][env])
+                assert max(errs.values()) < LEAN_TOL, (name, slim, errs)
+                for kind in ('links', 'joints', 'contacts', 'xfrc'):
+                    assert log_error(kind, a[3][kind][env], b[3][kind][env]) < LEAN_TOL, (name, slim, kind)
+            # layouts of the GENERAL variant: same bits (one source, same contraction); of the LEAN
+            # variant: the same to a few ulp
+            ref, other = outs[slims[0], False], outs[slim, False]
+            assert np.array_equal(ref[0], other[0]) and np.array_equal(ref[1], other[1]), (name, slim)
+            assert np.array_equal(ref[2], other[2])
+            for kind in ('links', 'joints', 'contacts', 'xfrc'):
+                assert np.array_equal(ref[3][kind], other[3][kind]), (name, slim, kind)
+            ref, other = outs[slims[0], True], outs[slim, True]
+            for env in range(n_envs):
+                assert max(state_errors(other[0][env], other[1][env], ref[0][env], ref[1][env]).values()) < LEAN_TOL
+                for kind in ('links', 'joints', 'contacts', 'xfrc'):
+                    assert log_error(kind, other[3][kind][env], ref[3][kind][env]) < LEAN_TOL, (name, slim, kind)
+    physics = BatchedPhysics.from_spec(variant_models.swimmer8_features(), 2, buffer_size=2, library=library)
+    assert not physics.fast_lean            # slide joint, clamps, off-origin anchors

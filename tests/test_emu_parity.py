@@ -385,3 +385,8 @@ def test_device_cpg_matches_host_controller(emu_library):
     """coupled-oscillator CPG + torque writer on the device == step_control on the host."""
     import fastpath_cases
     fastpath_cases.check_device_cpg(emu_library)
+
+
+def test_lean_variant(emu_library):
+    import fastpath_cases
+    fastpath_cases.check_lean_variant(emu_library, slims=(0, 1))

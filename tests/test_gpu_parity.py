@@ -207,6 +207,9 @@ def test_slim_layout_is_bit_identical(cuda_library, name, monkeypatch):
             pytest.skip('SLIM needs 32 environments per warp')
         physics.set_fast_slim(slim)
         assert physics.fast_slim == slim
+        # the general variant: one source for every layout, hence the same bits (the LEAN variants
+        # are separate compilations that agree to a few ulp, test_lean_variant)
+        physics.set_fast_lean(False)
         physics.reset(qpos0, qvel0)
         physics.set_ctrl(ctrl)
         physics.step(5)
@@ -657,3 +660,9 @@ def test_device_cpg_matches_host_controller(cuda_library):
     against the same network stepped on the host through ExperimentTask.step_control."""
     import fastpath_cases
     fastpath_cases.check_device_cpg(cuda_library, n_envs=70, n_it=48, chunk=16)
+
+
+def test_lean_variant(cuda_library, monkeypatch):
+    import fastpath_cases
+    monkeypatch.setenv('FARMS_B200_FAST_BLOCK', '32')
+    fastpath_cases.check_lean_variant(cuda_library, n_envs=75, slims=(0, 1, 7))
