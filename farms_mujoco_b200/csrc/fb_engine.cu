@@ -262,6 +262,9 @@ struct FbHandle {
   int fast_slim;                    /* 1: SLIM layout of the unconstrained kernel (8 warps per SM; large batches) */
   int fast_wpb;                     /* warps per block of the unconstrained kernel (> 1: barrier per step) */
   int fast_lean;                    /* 1: use the LEAN variants when the model allows (FARMS_B200_FAST_LEAN=0 switches them off) */
+  bool fast_block_auto;             /* 16 environments per warp chosen by the heuristic ... */
+  int block_review;                 /* ... and reviewed after the first launch of an episode */
+  int max_smem;
   size_t fast_slim_smem_bytes;
   size_t fast_smem_bytes;
   long long launch_parity;
@@ -414,6 +417,10 @@ static int upload_model(FbHandle *h) {
   return 0;
 }
 
+#ifndef FB_HOST_EMU
+static int fb_set_fast_block(FbHandle *h, int blk);
+#endif
+
 /* capacity of the device control sequence ([n_steps][nu][env_pad] + the upload staging) */
 static int ensure_sequence(FbHandle *h, int n_steps) {
   if (n_steps <= h->seq_cap) return 0;
@@ -563,10 +570,44 @@ static int launch(FbHandle *h, int mode, int n_steps, int want_derived) {
 #endif
   h->launches++;
   if (mode == FB_MODE_RESET) h->it = 0; else h->it += n_steps;
+#ifndef FB_HOST_EMU
+  /* Half-filled warps (16 environments each) pay for candidate-rich models only through the
+   * constrained step: a warp visits the union of its lanes' contacts.  Whether an episode is of
+   * that kind shows in its first launch: when fewer than half of the environments were handed
+   * over (a swimmer whose floor is far below), later launches use full warps, which is faster for
+   * the unconstrained kernel at every batch size (r2l: 1.14e8 against 1.08e8 env-steps/s at 8,192
+   * SALAMANDERs); ground-contact batches keep 16 (7.46e6 against 7.24e6 at 4,096).  The scratch
+   * layouts depend on the block size but hold nothing across launches. */
+  if (use_fast && h->block_review) {
+    h->block_review = 0;
+    int both[2] = {0, 0};
+    if (d2h(both, P.pending_count, sizeof(both), h->stream) || dev_sync(h->stream)) return fail(dev_error());
+    const int want = 2*both[P.parity] >= P.n_envs ? 16 : 32;
+    if (want != h->fast_block && (size_t)P.m.X.n_float*sizeof(float)*want <= (size_t)h->max_smem && fb_set_fast_block(h, want)) return -1;
+  }
+#endif
   return 0;
 }
 
 #ifndef FB_HOST_EMU
+/* environments per warp of the per-thread kernels (regular layout): shared-memory attributes */
+static int fb_set_fast_block(FbHandle *h, int blk) {
+  const size_t per_thread = (size_t)h->hm.m.X.n_float*sizeof(float);
+  h->fast_block = blk;
+  h->fast_smem_bytes = per_thread*blk;
+  const int bytes = (int)h->fast_smem_bytes;
+  cudaError_t ce = cudaSuccess;
+#define FB_SET_SMEM(K_) \
+  if (ce == cudaSuccess) ce = cudaFuncSetAttribute(K_, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes); \
+  if (ce == cudaSuccess) ce = cudaFuncSetAttribute(K_, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+  switch (blk) {
+    case 16: FB_SET_SMEM((fb_fast_kernel<16, 0, 0>)) FB_SET_SMEM((fb_fast_kernel<16, 0, 0, 1>)) FB_SET_SMEM(fb_fastc_kernel<16>) FB_SET_SMEM((fb_fastc_kernel<16, 1>)) break;
+    default: FB_SET_SMEM((fb_fast_kernel<32, 0, 0>)) FB_SET_SMEM((fb_fast_kernel<32, 0, 0, 1>)) FB_SET_SMEM(fb_fastc_kernel<32>) FB_SET_SMEM((fb_fastc_kernel<32, 1>)) break;
+  }
+#undef FB_SET_SMEM
+  return ce == cudaSuccess ? 0 : fail(std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(ce));
+}
+
 /* shared-memory attributes of the SLIM variants (one warp per block, or 2..8 kept in step) */
 static int fb_slim_attributes(FbHandle *h, int max_smem) {
   h->fast_slim_smem_bytes = (size_t)h->hm.m.X.n_float_slim*sizeof(float)*32;
@@ -670,7 +711,7 @@ int fb_create(const FbModel *model, const FbFarms *farms, int n_envs, int device
   h->con_thread = 1; h->log_used = 0;
   if (const char *ev = getenv("FARMS_B200_CON_THREAD")) h->con_thread = atoi(ev) != 0;
   h->fast_slim = 0; h->fast_slim_smem_bytes = 0; h->fast_wpb = 1;
-  h->fast_lean = 1;
+  h->fast_lean = 1; h->fast_block_auto = false; h->block_review = 0; h->max_smem = 0;
   if (const char *ev = getenv("FARMS_B200_FAST_LEAN")) h->fast_lean = atoi(ev) != 0;
   if (const char *ev = getenv("FARMS_B200_FAST_SLIM")) h->fast_slim = atoi(ev) != 0;
 #ifndef FB_HOST_EMU
@@ -761,18 +802,11 @@ int fb_create(const FbModel *model, const FbFarms *farms, int n_envs, int device
       const int v = atoi(ev);
       if (v == 16 || v == 32) h->fast_block = v;
     }
+    h->fast_block_auto = getenv("FARMS_B200_FAST_BLOCK") == nullptr && h->fast_block == 16;
+    h->max_smem = max_smem;
     if (!m.X.ok || per_thread*h->fast_block > (size_t)max_smem) h->fast_enabled = 0;
     if (h->fast_enabled) {
-      h->fast_smem_bytes = per_thread*h->fast_block;
-      const int bytes = (int)h->fast_smem_bytes;
-#define FB_SET_SMEM(K_) \
-      if (ce == cudaSuccess) ce = cudaFuncSetAttribute(K_, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes); \
-      if (ce == cudaSuccess) ce = cudaFuncSetAttribute(K_, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-      switch (h->fast_block) {
-        case 16: FB_SET_SMEM((fb_fast_kernel<16, 0, 0>)) FB_SET_SMEM((fb_fast_kernel<16, 0, 0, 1>)) FB_SET_SMEM(fb_fastc_kernel<16>) FB_SET_SMEM((fb_fastc_kernel<16, 1>)) break;
-        default: FB_SET_SMEM((fb_fast_kernel<32, 0, 0>)) FB_SET_SMEM((fb_fast_kernel<32, 0, 0, 1>)) FB_SET_SMEM(fb_fastc_kernel<32>) FB_SET_SMEM((fb_fastc_kernel<32, 1>)) break;
-      }
-#undef FB_SET_SMEM
+      if (fb_set_fast_block(h, h->fast_block)) { fb_destroy(h); return -1; }
       if (const char *ev = getenv("FARMS_B200_FAST_WPB")) h->fast_wpb = atoi(ev);
 
       /* SLIM layout: pays when the batch has more warps than the regular layout keeps resident
@@ -885,6 +919,12 @@ int fb_reset(FbHandle *h, const double *qpos0, const double *qvel0) {
   if (bad) return fail(std::string("fb_reset: ") + dev_error());
   h->it = 0;
   h->seq_len = h->seq_pos = 0;
+#ifndef FB_HOST_EMU
+  if (h->fast_enabled && h->fast_block_auto) {
+    if (h->fast_block != 16 && fb_set_fast_block(h, 16)) return -1;
+    h->block_review = 1;
+  }
+#endif
   if (launch(h, FB_MODE_RESET, 1, 1)) return -1;
   return dev_sync(h->stream) ? fail(std::string("fb_reset: ") + dev_error()) : 0;
 }

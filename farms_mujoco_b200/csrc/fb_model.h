@@ -624,9 +624,12 @@ inline bool fb_build_model(const FbModel *fm, const FbFarms *ff, const FbWaveCon
       /* two equal principal moments: Ia*1 + (Ic - Ia) n n', n the odd principal axis */
       for (int odd = 0; odd < 3; odd++) {
         int e1 = (odd + 1) % 3, e2 = (odd + 2) % 3;
-        if (I3[e1] == I3[e2]) {
+        /* equal up to the rounding of the model compiler (a rotated capsule's two transverse
+         * moments differ in the 16th digit), far below what fp32 resolves */
+        if (std::fabs(I3[e1] - I3[e2]) <= 1e-10*std::fmax(std::fabs(I3[e1]), std::fabs(I3[e2]))) {
+          const double Ia = 0.5*(I3[e1] + I3[e2]);
           r.flags |= FT_AXISYM;
-          r.Ib[0] = (float)I3[e1]; r.Ib[1] = (float)(I3[odd] - I3[e1]);
+          r.Ib[0] = (float)Ia; r.Ib[1] = (float)(I3[odd] - Ia);
           r.Ib[2] = (float)R[odd]; r.Ib[3] = (float)R[3 + odd]; r.Ib[4] = (float)R[6 + odd]; r.Ib[5] = 0.f;
           break;
         }
