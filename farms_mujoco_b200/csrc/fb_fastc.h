@@ -1088,8 +1088,9 @@ FB_UNROLL
     this->load_state(coop, lane);
     const size_t e = (size_t)env;
     const int n = P.n_steps;
+    long long row = (P.it0 + k0) % P.ring;
     for (int k = k0; k < n; k++) {
-      const long long row = (P.it0 + k + 1) % P.ring;
+      row = row + 1 == P.ring ? 0 : row + 1;
       float *row_links = fb_log_row(P.log_links, row, m.n_links*20, P.env_pad, FB_VEC_LINKS, e);
       float *row_joints = fb_log_row(P.log_joints, row, m.n_joints*m.joint_cols, P.env_pad, FB_VEC_JOINTS, e);
       float *row_contacts = fb_log_row(P.log_contacts, row, m.n_contacts*12, P.env_pad, FB_VEC_CONTACTS, e);
