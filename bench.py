@@ -286,9 +286,13 @@ def written_bytes_per_env_step(spec, constrained):
 def kernel_name(physics, handed_over, n_local):
     if not physics.fast_path:
         return f'fb_step_kernel<{physics.team_lanes}>'
+    lean = int(physics.fast_lean)
     if 2*handed_over > n_local:
-        return f'fb_fastc_kernel<{physics.fast_path}>' if physics.constraint_path else f'fb_step_kernel<{physics.team_lanes}>'
-    return f'fb_fast_kernel<{physics.fast_path},{int(physics.fast_slim > 0)},{int(physics.fast_slim > 1)}>'
+        return (f'fb_fastc_kernel<{physics.fast_path},{lean}>' if physics.constraint_path
+                else f'fb_step_kernel<{physics.team_lanes}>')
+    if physics.fast_split:
+        return f'fb_fast_split_kernel<{lean}> ({physics.fast_split} warps per 32 envs)'
+    return f'fb_fast_kernel<{physics.fast_path},{int(physics.fast_slim > 0)},{int(physics.fast_slim > 1)},{lean}>'
 
 
 def roofline_objects(args_model, spec, physics, n_local, inner, k_ms, per_gpu_rate, handed_over, peaks, device):
@@ -628,6 +632,8 @@ def run_b200(args, rank, world, local_rank):
                             if physics.fast_path else 'fb_step_kernel only'),
                 'fast_envs_per_block': physics.fast_path,
                 'fast_slim_layout': bool(physics.fast_slim),
+                'fast_lean_variant': bool(physics.fast_lean),
+                'fast_split_warps': int(physics.fast_split),
                 'fast_warps_per_block': max(1, int(physics.fast_slim)),
                 'fast_smem_bytes_per_env': physics.fast_smem_bytes_per_env,
                 'handed_over_envs_last_launch': handed_over,

@@ -122,6 +122,44 @@ fb_fast_kernel(const __grid_constant__ FbFastParams Q) {
   }
 }
 
+/* SPLIT variant (small batches): one block = 32 environments stepped by split.nwarps warps */
+struct FbFastSplitParams {
+  FbParams P;
+  FastRec rec[FB_FAST_MAXBODY];
+  FastSplit split;
+};
+#define FB_SPLIT_EXTRA_BYTES 512       /* root position [3][32] + hand-over flags [32] behind the body blocks */
+
+/* registers capped for 3 blocks of 128 threads per SM (168): with the 96-thread blocks of a
+ * three-way split four blocks are then resident (shared memory allows four), i.e. 592 blocks =
+ * 18,944 environments in one wave.  Measured r2t (SALAMANDER, 16 steps per launch): 12,288 envs
+ * 0.82 ms, 16,384 envs 0.83 ms; uncapped (197 registers, 2 blocks per SM) 1.42 ms beyond 9,472
+ * envs; capped for 4 blocks of 128 (128 registers, spills) 1.07 .. 1.13 ms. */
+#ifndef FB_SPLIT_MINBLOCKS
+#define FB_SPLIT_MINBLOCKS 3
+#endif
+template <int LEAN>
+__global__ void __launch_bounds__(32*FB_SPLIT_MAXW, FB_SPLIT_MINBLOCKS)
+fb_fast_split_kernel(const __grid_constant__ FbFastSplitParams Q) {
+  extern __shared__ __align__(16) float fb_smem[];
+  const FbParams &P = Q.P;
+  const int role = threadIdx.x >> 5, lane = threadIdx.x & 31, wid = blockIdx.x;
+  const int env = wid*32 + lane;
+  if (blockIdx.x == 0 && threadIdx.x == 0) P.pending_count[P.parity ^ 1] = 0;   /* for the next launch */
+  const int valid = env < P.n_envs;
+  const int n_float = P.m.X.n_float;
+  FbFast<32, 0, 0, LEAN, 1> st(P, Q.rec, fb_smem + lane, P.fast_scratch + (size_t)wid*P.m.X.n_scratch*32 + lane,
+                               valid ? env : 0);
+  float *extra = fb_smem + (size_t)n_float*32;
+  st.split_setup(Q.split, role, extra + lane, reinterpret_cast<int *>(extra + 3*32) + lane);
+  const int coop = (wid + 1)*32 <= P.n_envs ? P.m.X.coop_io : 0;
+  const int done = st.run_split(coop, lane, valid);
+  if (role == 0 && valid && done < P.n_steps) {
+    P.steps_done[env] = done;
+    P.pending[atomicAdd(P.pending_count + P.parity, 1)] = env;
+  }
+}
+
 struct FbFastConParams {
   FbParams P;
   FastRec rec[FB_FAST_MAXBODY];
@@ -262,6 +300,8 @@ struct FbHandle {
   int fast_slim;                    /* 1: SLIM layout of the unconstrained kernel (8 warps per SM; large batches) */
   int fast_wpb;                     /* warps per block of the unconstrained kernel (> 1: barrier per step) */
   int fast_lean;                    /* 1: use the LEAN variants when the model allows (FARMS_B200_FAST_LEAN=0 switches them off) */
+  int fast_split;                   /* 1: small batches run the SPLIT variant (several warps per 32 environments) */
+  long long split_capacity;         /* blocks of the SPLIT variant the device holds at once (0: not applicable) */
   bool fast_block_auto;             /* 16 environments per warp chosen by the heuristic ... */
   int block_review;                 /* ... and reviewed after the first launch of an episode */
   int max_smem;
@@ -271,6 +311,7 @@ struct FbHandle {
   int log_used;                     /* 0 until the first reset: the log is as fb_create zeroed it */
 #ifndef FB_HOST_EMU
   FbFastParams *fastQ;               /* host staging of the per-thread kernel's parameters */
+  FbFastSplitParams *splitQ;         /* ... of its SPLIT variant */
   FbFastConParams *conQ;             /* ... and of the per-thread constrained kernel's */
 #endif
   fbStream stream;
@@ -408,6 +449,9 @@ static int upload_model(FbHandle *h) {
     if (!h->fastQ) h->fastQ = new FbFastParams();
     memset(h->fastQ->rec, 0, sizeof(h->fastQ->rec));
     memcpy(h->fastQ->rec, h->hm.rec.data(), sizeof(FastRec)*h->hm.rec.size());
+    if (!h->splitQ) h->splitQ = new FbFastSplitParams();
+    memcpy(h->splitQ->rec, h->fastQ->rec, sizeof(h->splitQ->rec));
+    h->splitQ->split = h->hm.split;
     if (!h->conQ) h->conQ = new FbFastConParams();
     memcpy(h->conQ->rec, h->fastQ->rec, sizeof(h->conQ->rec));
     memset(h->conQ->cand, 0, sizeof(h->conQ->cand));
@@ -533,7 +577,14 @@ static int launch(FbHandle *h, int mode, int n_steps, int want_derived) {
       if (FB_TMA_ENABLE && h->fast_slim && wpb > 1) bytes += (size_t)wpb*FB_RING_BYTES;      /* TMA ring of every warp */
       /* LEAN variants: same arithmetic with the model's unused paths compiled out (smaller loops) */
       const bool lean = h->fast_lean && P.m.X.lean && !P.ctrl_seq;
-      if (h->fast_block == 16) {
+      if (h->fast_split && h->fast_block == 32 && !h->fast_slim && h->hm.split.nwarps > 1 && warps <= h->split_capacity) {
+        /* small batch: the tree of every 32 environments split over several warps */
+        h->splitQ->P = P;
+        const size_t sbytes = h->fast_smem_bytes + FB_SPLIT_EXTRA_BYTES;
+        const int threads = 32*h->hm.split.nwarps;
+        if (lean) fb_fast_split_kernel<1><<<warps, threads, sbytes, h->stream>>>(*h->splitQ);
+        else fb_fast_split_kernel<0><<<warps, threads, sbytes, h->stream>>>(*h->splitQ);
+      } else if (h->fast_block == 16) {
         if (lean) fb_fast_kernel<16, 0, 0, 1><<<fblocks, 16, bytes, h->stream>>>(*h->fastQ);
         else fb_fast_kernel<16, 0, 0><<<fblocks, 16, bytes, h->stream>>>(*h->fastQ);
       } else if (h->fast_slim && wpb > 1) {
@@ -605,6 +656,20 @@ static int fb_set_fast_block(FbHandle *h, int blk) {
     default: FB_SET_SMEM((fb_fast_kernel<32, 0, 0>)) FB_SET_SMEM((fb_fast_kernel<32, 0, 0, 1>)) FB_SET_SMEM(fb_fastc_kernel<32>) FB_SET_SMEM((fb_fastc_kernel<32, 1>)) break;
   }
 #undef FB_SET_SMEM
+  h->split_capacity = 0;
+  if (blk == 32 && h->hm.split.nwarps > 1 && (size_t)bytes + FB_SPLIT_EXTRA_BYTES <= (size_t)h->max_smem) {
+    int per_sm = 1 << 30;
+    for (int lean = 0; lean < 2 && ce == cudaSuccess; lean++) {
+      const void *k = lean ? (const void *)fb_fast_split_kernel<1> : (const void *)fb_fast_split_kernel<0>;
+      ce = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes + FB_SPLIT_EXTRA_BYTES);
+      if (ce == cudaSuccess) ce = cudaFuncSetAttribute(k, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+      int nb = 0;
+      if (ce == cudaSuccess) ce = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k, 32*h->hm.split.nwarps, (size_t)bytes + FB_SPLIT_EXTRA_BYTES);
+      if (nb < per_sm) per_sm = nb;
+    }
+    /* the SPLIT variant pays while ALL its blocks are resident at once (one wave) */
+    if (ce == cudaSuccess) h->split_capacity = (long long)per_sm*h->sms;
+  }
   return ce == cudaSuccess ? 0 : fail(std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(ce));
 }
 
@@ -691,6 +756,7 @@ void fb_destroy(FbHandle *h) {
   cudaStreamDestroy(h->stream);
   delete h->fastQ;
   delete h->conQ;
+  delete h->splitQ;
 #endif
   delete h;
 }
@@ -711,11 +777,12 @@ int fb_create(const FbModel *model, const FbFarms *farms, int n_envs, int device
   h->con_thread = 1; h->log_used = 0;
   if (const char *ev = getenv("FARMS_B200_CON_THREAD")) h->con_thread = atoi(ev) != 0;
   h->fast_slim = 0; h->fast_slim_smem_bytes = 0; h->fast_wpb = 1;
-  h->fast_lean = 1; h->fast_block_auto = false; h->block_review = 0; h->max_smem = 0;
+  h->fast_lean = 1; h->fast_block_auto = false; h->block_review = 0; h->max_smem = 0; h->fast_split = 0;
+  h->split_capacity = 0;
   if (const char *ev = getenv("FARMS_B200_FAST_LEAN")) h->fast_lean = atoi(ev) != 0;
   if (const char *ev = getenv("FARMS_B200_FAST_SLIM")) h->fast_slim = atoi(ev) != 0;
 #ifndef FB_HOST_EMU
-  h->fastQ = nullptr; h->conQ = nullptr;
+  h->fastQ = nullptr; h->conQ = nullptr; h->splitQ = nullptr;
 #endif
   if (const char *ev = getenv("FARMS_B200_FAST")) h->fast_enabled = atoi(ev) != 0;
   memset(&h->P, 0, sizeof(h->P));
@@ -824,6 +891,11 @@ int fb_create(const FbModel *model, const FbFarms *farms, int n_envs, int device
         if (h->fast_wpb < 4) h->fast_wpb = 4;
       }
       if (h->fast_slim && fb_slim_attributes(h, max_smem)) { fb_destroy(h); return -1; }
+      /* SPLIT variant: pays while the batch leaves schedulers idle (a launch is then one warp's
+       * latency, which the split shortens); beyond ~2 warps per scheduler the single-warp kernel
+       * does the same work with fewer instructions */
+      h->fast_split = !h->fast_slim && h->hm.split.nwarps > 1;     /* used while the batch fits one wave (launch) */
+      if (const char *ev = getenv("FARMS_B200_FAST_SPLIT")) h->fast_split = atoi(ev) != 0;
       if (ce != cudaSuccess) { fb_destroy(h); return fail(std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(ce)); }
     }
   }
@@ -1621,6 +1693,42 @@ int fb_set_fast_slim(FbHandle *h, int enable) {
 #endif
   h->fast_slim = enable != 0;
   return 0;
+}
+/* SPLIT variant of the unconstrained kernel (small batches): several warps per 32 environments */
+int fb_set_fast_split(FbHandle *h, int enable) {
+  if (!h) return fail("null handle");
+  h->fast_split = enable != 0;
+  return 0;
+}
+/* warps per 32 environments when fb_step launches the SPLIT variant, else 0 (the batch must fit one
+ * wave of its blocks; while fb_create's 16-per-warp guess stands -- until the first launch of an
+ * episode has been reviewed -- the single-warp kernels run) */
+int fb_fast_split(FbHandle *h) {
+  if (!h || !h->fast_enabled || !h->fast_split || h->fast_slim || !h->hm.m.X.ok) return 0;
+#ifndef FB_HOST_EMU
+  if (h->fast_block != 32 || (h->P.n_envs + 31)/32 > h->split_capacity) return 0;
+#endif
+  return h->hm.split.nwarps > 1 ? h->hm.split.nwarps : 0;
+}
+/* resident SPLIT blocks per SM as the runtime computes it (0: not applicable) */
+int fb_fast_split_blocks_per_sm(FbHandle *h) {
+#ifndef FB_HOST_EMU
+  if (!h || !h->hm.m.X.ok || h->hm.split.nwarps < 2) return 0;
+  int nb = 0;
+  const size_t sbytes = (size_t)h->hm.m.X.n_float*sizeof(float)*32 + FB_SPLIT_EXTRA_BYTES;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, fb_fast_split_kernel<1>, 32*h->hm.split.nwarps, sbytes) != cudaSuccess) return 0;
+  return nb;
+#else
+  (void)h; return 0;
+#endif
+}
+/* the schedule itself (tests): n[4], boundary[4], order[4][64]; returns the number of warps */
+int fb_fast_split_schedule(FbHandle *h, int32_t *n, int32_t *boundary, uint8_t *order) {
+  if (!h || !n || !boundary || !order) return 0;
+  const FastSplit &sp = h->hm.split;
+  for (int w = 0; w < FB_SPLIT_MAXW; w++) { n[w] = sp.n[w]; boundary[w] = sp.boundary[w]; }
+  memcpy(order, sp.order, sizeof(sp.order));
+  return sp.nwarps;
 }
 /* LEAN variants of the unconstrained kernel (fb_fast.h): on by default when the model allows */
 int fb_set_fast_lean(FbHandle *h, int enable) {

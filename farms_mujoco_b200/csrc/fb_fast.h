@@ -292,7 +292,11 @@ template <int SYNC> FB_DEV void fb_block_sync() {
  * anchor-offset and generic-column paths are compiled out.  Same arithmetic on the paths that
  * remain (bit-identical results); the point is the SIZE of the three body loops -- they run out of
  * a 32 KB instruction cache, and unrolling them by two (60 KB) was measured 10-25 % slower. */
-template <int BLK, int SLIM = 0, int TMA = 0, int LEAN = 0> struct FbFast {
+/* SPLIT = 1 (small batches, regular layout): the 32 environments of a block are stepped by several
+ * warps, each visiting its own bodies of the tree in two phases per sweep (FastSplit, fb_model.h);
+ * the per-body code is the one every other variant runs, in the same order along every chain, so
+ * the results are bit-identical to the single-warp kernel. */
+template <int BLK, int SLIM = 0, int TMA = 0, int LEAN = 0, int SPLIT = 0> struct FbFast {
   /* SLIM scratch block: W[6] U 1/d trq q qd V[6] tc tu -- the first 17 are one contiguous run */
   enum { NF = SLIM ? 7 : FB_NF, GNF = SLIM ? FG_NF + 6 : FG_NF, FG_V = SLIM ? 11 : FG_NF,
          FGTC = SLIM ? 17 : FG_TC, FGTU = SLIM ? 18 : FG_TU };
@@ -322,6 +326,14 @@ template <int BLK, int SLIM = 0, int TMA = 0, int LEAN = 0> struct FbFast {
   float *ring;
   unsigned ring_bar, ring_phase;
   int ring_lane;
+  /* SPLIT: this warp's body list (ascending; phase A = [0, ord_bnd)), its role (0 = the trunk warp,
+   * which also owns the root state and the state I/O), whether this lane's environment has left
+   * the kernel (it still takes every barrier), the root position as warp 0 publishes it and the
+   * per-lane hand-over flags the warps agree through */
+  const uint8_t *ord;
+  int ord_n, ord_bnd, role, idle;
+  float *sroot;
+  int *sflag;
 
   FB_MEM FbFast(const FbParams &P_, const FastRec *rec_, float *s_, float *gs_, int env_)
       : P(P_), m(P_.m), rec(rec_), s(s_), env(env_), gs(gs_), cs(0), csc(0), crec(0) {
@@ -329,6 +341,7 @@ template <int BLK, int SLIM = 0, int TMA = 0, int LEAN = 0> struct FbFast {
     dirty_c = P.con_dirty[env];
     zfill = 1;
     ring = 0; ring_bar = 0; ring_phase = 0; ring_lane = 0;
+    ord = 0; ord_n = 0; ord_bnd = 0; role = 0; idle = 0; sroot = 0; sflag = 0;
     rootpos[0] = rootpos[1] = rootpos[2] = 0.f;
     rqn[0] = 1.f; rqn[1] = rqn[2] = rqn[3] = 0.f;
 FB_UNROLL
@@ -364,6 +377,16 @@ FB_UNROLL
     return ring + st*FB_RING_FIELDS*32 + ring_lane;
   }
 #endif
+  FB_MEM void split_setup(const FastSplit &sp, int role_, float *sroot_, int *sflag_) {
+    role = role_; ord = sp.order[role_]; ord_n = sp.n[role_]; ord_bnd = sp.boundary[role_];
+    sroot = sroot_; sflag = sflag_;
+  }
+  /* phase barrier of a sweep (every thread of the block, idle or not) */
+  FB_MEM void split_barrier() const {
+#ifndef FB_HOST_EMU
+    __syncthreads();
+#endif
+  }
   /* row of iteration `itr` (before the ring modulus): was it last written at or before dirty_c? */
   FB_MEM int log_row_dirty(long long itr) const {
     const long long prev = itr - P.ring;
@@ -597,7 +620,11 @@ FB_UNROLL
         if (1 + d < nb) ring_issue(leader, 1 + d, d, FG_Q, 2);
     } else
 #endif
-    { nq = fb_ld_scr(gblock(1) + FG_Q*BLK); nqd = fb_ld_scr(gblock(1) + FG_QD*BLK); }
+    {
+      const int b0 = SPLIT ? (ord_n > 0 ? ord[0] : 1) : 1;
+      nq = fb_ld_scr(gblock(b0) + FG_Q*BLK); nqd = fb_ld_scr(gblock(b0) + FG_QD*BLK);
+    }
+    const int n_it = SPLIT ? ord_n : nb - 1;
     float *pb = block(1) - NF*BLK;
     float *pn = gblock(1);
     Quat lastq = {1.f, 0.f, 0.f, 0.f};
@@ -608,7 +635,18 @@ FB_UNROLL
      * round trip per branch (r1aq: 6 % of the stall samples together with its pass-3 twin) */
     float nvp[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
 FB_BODY_LOOP
-    for (int b = 1; b < nb; b++) {
+    for (int i = 0; i <= n_it; i++) {
+      if (SPLIT && i == ord_bnd) {
+        split_barrier();                 /* the trunk is placed: the subtrees hanging off it start */
+        if (role != 0) {
+FB_UNROLL
+          for (int k = 0; k < 3; k++) rootpos[k] = sroot[k*BLK];
+        }
+      }
+      if (i == n_it) break;
+      if (SPLIT && idle) continue;
+      const int b = SPLIT ? ord[i] : i + 1;
+      const int bn = SPLIT ? (i + 1 < n_it ? ord[i + 1] : 0) : (i + 2 < nb ? i + 2 : 0);   /* visited next; 0: none */
       const FastRec &rc0 = rec[b];
       struct { int parent, jtype, flags, pblk, link, chk0, chk1; float dpos[3], bquat[4], axis[3], qpos0, lo, hi, margin, hloc[3], chk[4], jpos[3]; } rc;
       rc.parent = rc0.parent; rc.jtype = rc0.jtype; rc.flags = rc0.flags; rc.pblk = SLIM ? rc0.pblk7 : rc0.pblk; rc.link = rc0.link;
@@ -623,9 +661,9 @@ FB_UNROLL
       for (int k = 0; k < 3; k++) { FB_PIN_F(rc.dpos[k]); FB_PIN_F(rc.axis[k]); FB_PIN_F(rc.hloc[k]); }
 FB_UNROLL
       for (int k = 0; k < 4; k++) { FB_PIN_F(rc.bquat[k]); FB_PIN_F(rc.chk[k]); }
-      if (b + 1 < nb) FB_TOUCH_REC(rec[b + 1]);
-      pb += NF*BLK;
-      pn += GNF*BLK;
+      if (bn) FB_TOUCH_REC(rec[bn]);
+      if (SPLIT) { pb = block(b); pn = gblock(bn ? bn : b); }
+      else { pb += NF*BLK; pn += GNF*BLK; }
       float cq = nq, cqd = nqd;
 #ifndef FB_HOST_EMU
       if (TMA) {
@@ -637,8 +675,8 @@ FB_UNROLL
         st = st + 1 == FB_RING ? 0 : st + 1;
       } else
 #endif
-      if (b + 1 < nb) { nq = fb_ld_scr(pn + FG_Q*BLK); nqd = fb_ld_scr(pn + FG_QD*BLK); }
-      float *pgv = pn - GNF*BLK;       /* scratch block of this body (pn runs one ahead) */
+      if (bn) { nq = fb_ld_scr(pn + FG_Q*BLK); nqd = fb_ld_scr(pn + FG_QD*BLK); }
+      float *pgv = SPLIT ? gblock(b) : pn - GNF*BLK;       /* scratch block of this body (pn runs one ahead) */
       const int jtype = rc.jtype;
       Quat q;
       float o[3], v[6], R[9];
@@ -661,6 +699,10 @@ FB_UNROLL
         q_mat(q, R);
 FB_UNROLL
         for (int k = 0; k < 3; k++) { rootpos[k] = rt[k]; o[k] = 0.f; v[3 + k] = rt[7 + k]; }
+        if (SPLIT) {
+FB_UNROLL
+          for (int k = 0; k < 3; k++) sroot[k*BLK] = rt[k];
+        }
         m_rot(R, rt[10], rt[11], rt[12], v);
       } else {
         Quat qp = {1.f, 0.f, 0.f, 0.f};
@@ -811,8 +853,9 @@ FB_UNROLL
         if (nb - 1 - d >= 1) ring_issue(leader, nb - 1 - d, d, 0, FB_RING_FIELDS);
     }
 #endif
+    const int n_it = SPLIT ? ord_n : nb - 1;
     {
-      const float *pn = gblock(nb - 1);
+      const float *pn = gblock(SPLIT ? (ord_n > 0 ? ord[ord_n - 1] : 1) : nb - 1);
       if (!TMA) {
 FB_UNROLL
         for (int k = 0; k < 6; k++) nx[k] = fb_ld_scr(pn + (FG_W + k)*BLK);
@@ -827,7 +870,12 @@ FB_UNROLL
     float *pb = block(nb - 1) + NF*BLK;
     float *pg = gblock(nb - 1) + GNF*BLK;
 FB_BODY_LOOP
-    for (int b = nb - 1; b >= 1; b--) {
+    for (int i = n_it; i >= 0; i--) {
+      if (SPLIT && i == ord_bnd) split_barrier();      /* the subtrees have handed over: the trunk goes on */
+      if (i == 0) break;
+      if (SPLIT && idle) continue;
+      const int b = SPLIT ? ord[i - 1] : i;
+      const int bn = SPLIT ? (i >= 2 ? ord[i - 2] : 0) : (i > 1 ? i - 1 : 0);
       const FastRec &rc = rec[b];
       /* issue the record loads of this body now (see FB_PIN_F) */
       FB_PIN_I(rc.jtype); FB_PIN_I(rc.flags); FB_PIN_I(SLIM ? rc.pblk7 : rc.pblk); FB_PIN_I(rc.parent);
@@ -838,17 +886,17 @@ FB_UNROLL
       for (int k = 0; k < 3; k++) { FB_PIN_F(rc.hloc[k]); FB_PIN_F(rc.axis[k]); }
 FB_UNROLL
       for (int k = 0; k < 5; k++) FB_PIN_F(rc.Ib[k]);
-      if (b > 1) FB_TOUCH_REC(rec[b - 1]);
-      pb -= NF*BLK;
-      pg -= GNF*BLK;
+      if (bn) FB_TOUCH_REC(rec[bn]);
+      if (SPLIT) { pb = block(b); pg = gblock(b); }
+      else { pb -= NF*BLK; pg -= GNF*BLK; }
       const int jtype = rc.jtype, flags = rc.flags;
       float cx[10], cxv[6];
 FB_UNROLL
       for (int k = 0; k < 10; k++) cx[k] = nx[k];
 FB_UNROLL
       for (int k = 0; k < 6; k++) cxv[k] = nxv[k];
-      if (b > 1) {
-        const float *pn = pg - GNF*BLK;
+      if (bn) {
+        const float *pn = SPLIT ? gblock(bn) : pg - GNF*BLK;
         if (!TMA) {
 FB_UNROLL
           for (int k = 0; k < 6; k++) nx[k] = fb_ld_scr(pn + (FG_W + k)*BLK);
@@ -1104,8 +1152,9 @@ FB_UNROLL
         if (1 + d < nb) ring_issue(leader, 1 + d, d, 0, FB_RING_FIELDS);
     }
 #endif
+    const int n_it = SPLIT ? ord_n : nb - 1;
     if (!TMA) {
-      const float *pn = gblock(1);
+      const float *pn = gblock(SPLIT ? (ord_n > 0 ? ord[0] : 1) : 1);
 FB_UNROLL
       for (int k = 0; k < 9; k++) nx[k] = fb_ld_scr(pn + (FG_W + k)*BLK);     /* W, U, DINV, TRQ are contiguous */
       nx[9] = fb_ld_scr(pn + FG_Q*BLK); nx[10] = fb_ld_scr(pn + FG_QD*BLK);
@@ -1118,7 +1167,12 @@ FB_UNROLL
     float *pg = gblock(1) - GNF*BLK;
     float nap[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};     /* SLIM: acceleration of the parent of the next body when that is a branch child */
 FB_BODY_LOOP
-    for (int b = 1; b < nb; b++) {
+    for (int i = 0; i <= n_it; i++) {
+      if (SPLIT && i == ord_bnd) split_barrier();      /* the trunk's accelerations are known */
+      if (i == n_it) break;
+      if (SPLIT && idle) continue;
+      const int b = SPLIT ? ord[i] : i + 1;
+      const int bn = SPLIT ? (i + 1 < n_it ? ord[i + 1] : 0) : (i + 2 < nb ? i + 2 : 0);
       const FastRec &rc = rec[b];
       FB_PIN_I(rc.jtype); FB_PIN_I(rc.flags); FB_PIN_I(SLIM ? rc.pblk7 : rc.pblk); FB_PIN_I(rc.parent); FB_PIN_I(rc.fj);
       FB_PIN_I(rc.xr); FB_PIN_I(rc.swim);
@@ -1127,17 +1181,17 @@ FB_UNROLL
       for (int k = 0; k < 3; k++) { FB_PIN_F(rc.hloc[k]); FB_PIN_F(rc.axis[k]); }
 FB_UNROLL
       for (int k = 0; k < 6; k++) FB_PIN_F(rc.coef[k]);
-      if (b + 1 < nb) FB_TOUCH_REC(rec[b + 1]);
-      pb += NF*BLK;
-      pg += GNF*BLK;
+      if (bn) FB_TOUCH_REC(rec[bn]);
+      if (SPLIT) { pb = block(b); pg = gblock(b); }
+      else { pb += NF*BLK; pg += GNF*BLK; }
       const int jtype = rc.jtype, flags = rc.flags;
       float cx[11], cxv[6];
 FB_UNROLL
       for (int k = 0; k < 11; k++) cx[k] = nx[k];
 FB_UNROLL
       for (int k = 0; k < 6; k++) cxv[k] = nxv[k];
-      if (!TMA && b + 1 < nb) {
-        const float *pn = pg + GNF*BLK;
+      if (!TMA && bn) {
+        const float *pn = SPLIT ? gblock(bn) : pg + GNF*BLK;
 FB_UNROLL
         for (int k = 0; k < 9; k++) nx[k] = fb_ld_scr(pn + (FG_W + k)*BLK);
         nx[9] = fb_ld_scr(pn + FG_Q*BLK); nx[10] = fb_ld_scr(pn + FG_QD*BLK);
@@ -1389,6 +1443,61 @@ FB_UNROLL
     }
     store_state(P.it0 + kdone, coop, lane);
     return kdone;
+  }
+
+  /* SPLIT: run_t's protocol for a block whose warps step the SAME 32 environments, each its own
+   * bodies (split_setup).  Every thread takes every barrier; warp 0 owns the root state, the state
+   * I/O and the hand-over bookkeeping; a lane leaves the step when ANY warp saw one of its bodies at
+   * a limit or inside a plane bound. */
+  FB_MEM int run_split(int coop, int lane, int valid) {
+#ifndef FB_HOST_EMU
+    if (role == 0 && valid) load_state(coop, lane);
+    __syncthreads();
+    const size_t e = (size_t)env;
+    const int n = P.n_steps;
+    int kdone = n, dead = !valid;
+    long long row = P.it0 % P.ring;
+    for (int k = 0; k < n; k++) {
+      row = row + 1 == P.ring ? 0 : row + 1;
+      float *row_links = fb_log_row(P.log_links, row, m.n_links*20, P.env_pad, FB_VEC_LINKS, e);
+      float *row_joints = fb_log_row(P.log_joints, row, m.n_joints*m.joint_cols, P.env_pad, FB_VEC_JOINTS, e);
+      float *row_contacts = fb_log_row(P.log_contacts, row, m.n_contacts*12, P.env_pad, FB_VEC_CONTACTS, e);
+      float *row_xfrc = fb_log_row(P.log_xfrc, row, m.n_xfrc*6, P.env_pad, FB_VEC_XFRC, e);
+      const float time = (float)(P.it0 + k)*m.timestep;
+      zfill = log_row_dirty(P.it0 + k + 1);
+      if (role == 0) sflag[0] = 0;
+      __syncthreads();
+      idle = dead;
+      const int act = pass_poses(row_links);
+      if (!dead && act) sflag[0] = 1;
+      __syncthreads();
+      if (!dead && sflag[0]) { kdone = k; dead = 1; }
+      idle = dead;
+      if (role == 0 && !dead && rec[1].jtype == FB_JNT_FREE) { rt[3] = rqn[0]; rt[4] = rqn[1]; rt[5] = rqn[2]; rt[6] = rqn[3]; }
+      float aroot[6] = {0.f, 0.f, 0.f, -m.grav[0], -m.grav[1], -m.grav[2]};
+      const float *seqk = P.ctrl_seq ? P.ctrl_seq + ((size_t)(P.seq_pos + k)*m.nu)*P.env_pad + e : 0;
+      pass_inertia(time, aroot, k == n - 1 && m.n_wc > 0, seqk);
+      __syncthreads();
+      const int bad = pass_accel(aroot, row_joints, row_xfrc);
+      if (!dead) {
+        if (zfill && role == 0)
+          for (int i = 0; i < m.n_contacts*3; i++) fb_st4(row_contacts + i*(P.env_pad*FB_VEC_CONTACTS), 0.f, 0.f, 0.f, 0.f);
+        if (bad) FB_FLAG_OR(P.flags + env, FB_FLAG_NONFINITE);
+      }
+    }
+    __syncthreads();
+    if (role != 0 || !valid) return n;
+    if (P.ctrl_seq && kdone == n) {
+      const float *last = P.ctrl_seq + ((size_t)(P.seq_pos + n - 1)*m.nu)*P.env_pad + e;
+      for (int a = 0; a < m.nu; a++)
+        if (MI(ft_actwc, a) < 0) P.ctrl[e*m.nu + a] = last[(long long)a*P.env_pad];
+    }
+    store_state(P.it0 + kdone, coop, lane);
+    return kdone;
+#else
+    (void)coop; (void)lane; (void)valid;
+    return 0;
+#endif
   }
 };
 

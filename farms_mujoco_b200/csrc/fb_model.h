@@ -14,6 +14,7 @@
 #ifndef FB_MODEL_H_
 #define FB_MODEL_H_
 
+#include <algorithm>
 #include <cmath>
 #include <cstdint>
 #include <cstring>
@@ -95,6 +96,19 @@ struct FastRec {
   float T0U;                              /* farms joint_torque column does not log */
   int32_t bc0, bc1, pblk7;                /* candidates of the body: CandRec[bc0 .. bc1) (fb_fastc.h); 7*(parent-1) (SLIM blocks) */
   float chk[4];                           /* first conservative plane check (normal, offset) */
+};
+
+/* Tree split of the unconstrained kernel for SMALL batches (fb_fast.h, FbFast<.., SPLIT = 1>): the 32
+ * environments of a warp are stepped by `nwarps` warps that share their shared-memory blocks, each
+ * visiting its own bodies -- the trunk up to the last branching body on warp 0 (phase A), then,
+ * after a block barrier, the subtrees hanging off it in parallel (phase B: the rest of the trunk
+ * stays on warp 0, subtrees with the same parent share a warp).  Leaves -> root sweeps run the lists
+ * backwards, phase B first.  A launch is then about one trunk + one subtree long instead of the whole
+ * tree.  order[w][0 .. n[w]) ascending, phase A = [0, boundary[w]). */
+#define FB_SPLIT_MAXW 4
+struct FastSplit {
+  int32_t nwarps, n[FB_SPLIT_MAXW], boundary[FB_SPLIT_MAXW];
+  uint8_t order[FB_SPLIT_MAXW][FB_FAST_MAXBODY];
 };
 
 /* One collision candidate (world plane vs sphere / capsule end) of the per-thread constrained
@@ -180,8 +194,66 @@ struct FbHostModel {
   DevModel m;  /* I/F pointers left null; the caller patches them */
   std::vector<FastRec> rec;   /* [nbody] when m.X.ok */
   std::vector<CandRec> crec;  /* [ncand] in body order when m.X.con_ok */
+  FastSplit split;            /* nwarps = 1: the tree does not branch (or the model is outside the path) */
   std::string error;
 };
+
+/* Phase schedule of FastSplit for a tree given by parent[] (parent[b] < b, body 0 = world). */
+inline void fb_build_split(const std::vector<int> &parent, int max_warps, FastSplit &sp) {
+  const int nb = (int)parent.size();
+  std::memset(&sp, 0, sizeof(sp));
+  sp.nwarps = 1;
+  for (int b = 1; b < nb; b++) sp.order[0][sp.n[0]++] = (uint8_t)b;
+  sp.boundary[0] = sp.n[0];
+  if (nb < 4 || nb > FB_FAST_MAXBODY || max_warps < 2) return;
+  /* the last body some other body branches off (a child that is not its successor) */
+  int split = 0;
+  for (int b = 2; b < nb; b++)
+    if (parent[b] >= 1 && parent[b] != b - 1 && parent[b] > split) split = parent[b];
+  if (split < 1 || split >= nb - 1) return;
+  /* phase B: the forest on the bodies after `split`; a component is named by its first body, and
+   * components whose roots share a parent are merged (their hand-overs accumulate in one slot) */
+  std::vector<int> comp(nb, -1);
+  std::vector<std::vector<int>> groups;
+  std::vector<int> group_parent;
+  for (int b = split + 1; b < nb; b++) {
+    const int p = parent[b];
+    if (p > split) { comp[b] = comp[p]; groups[comp[b]].push_back(b); continue; }
+    int g = -1;
+    /* the successor of `split` continues warp 0's chain in registers: a group of its own */
+    if (!(b == split + 1 && p == split))
+      for (size_t k = 0; k < groups.size(); k++) if (group_parent[k] == p) g = (int)k;
+    if (g < 0) { g = (int)groups.size(); groups.emplace_back(); group_parent.push_back(b == split + 1 && p == split ? -1 : p); }
+    comp[b] = g;
+    groups[g].push_back(b);
+  }
+  if (groups.size() < 2) return;
+  const int nw = (int)groups.size() < max_warps ? (int)groups.size() : max_warps;
+  std::vector<std::vector<int>> phase_b(nw);
+  std::vector<int> load(nw, 0);
+  std::vector<char> done(groups.size(), 0);
+  for (size_t k = 0; k < groups.size(); k++)
+    if (group_parent[k] == -1) { phase_b[0] = groups[k]; load[0] = (int)groups[k].size(); done[k] = 1; }
+  for (;;) {                                   /* largest remaining group to the least loaded warp */
+    int best = -1;
+    for (size_t k = 0; k < groups.size(); k++)
+      if (!done[k] && (best < 0 || groups[k].size() > groups[best].size())) best = (int)k;
+    if (best < 0) break;
+    int w = 0;
+    for (int k = 1; k < nw; k++) if (load[k] < load[w]) w = k;
+    phase_b[w].insert(phase_b[w].end(), groups[best].begin(), groups[best].end());
+    load[w] += (int)groups[best].size();
+    done[best] = 1;
+  }
+  std::memset(&sp, 0, sizeof(sp));
+  sp.nwarps = nw;
+  for (int b = 1; b <= split; b++) sp.order[0][sp.n[0]++] = (uint8_t)b;
+  sp.boundary[0] = sp.n[0];
+  for (int w = 0; w < nw; w++) {
+    std::sort(phase_b[w].begin(), phase_b[w].end());
+    for (int b : phase_b[w]) sp.order[w][sp.n[w]++] = (uint8_t)b;
+  }
+}
 
 namespace fbdetail {
 inline int put_i(std::vector<int32_t> &I, const std::vector<int32_t> &v) {
@@ -803,6 +875,11 @@ inline bool fb_build_model(const FbModel *fm, const FbFarms *ff, const FbWaveCon
     X.jrow_std = m.joint_cols == 18 && m.col_jpos == 0 && m.col_jvel == 1 && m.col_jtrq == 11 && m.col_jlim == 16;
     X.coop_io = fm->nq + nv + (nu > 0 ? nu : 1) + 6*nb <= X.n_float;
     X.coop_io2 = fm->nq + nv + (nu > 0 ? nu : 1) <= X.n_float_slim && 6*nb <= X.n_float_slim;
+    {
+      std::vector<int> parent(nb);
+      for (int b = 0; b < nb; b++) parent[b] = fm->body_parentid[b];
+      fb_build_split(parent, X.ok ? FB_SPLIT_MAXW : 1, out.split);
+    }
     X.lean = X.ok && X.jrow_std;
     for (int b = 1; b < nb; b++) {
       const FastRec &r = rec[b];

@@ -74,6 +74,10 @@ ABI_SYMBOLS = {
     'fb_fast_smem_bytes_per_env': (ct.c_int, [_H]),
     'fb_set_fast_slim': (ct.c_int, [_H, ct.c_int]),
     'fb_fast_slim': (ct.c_int, [_H]),
+    'fb_set_fast_split': (ct.c_int, [_H, ct.c_int]),
+    'fb_fast_split': (ct.c_int, [_H]),
+    'fb_fast_split_blocks_per_sm': (ct.c_int, [_H]),
+    'fb_fast_split_schedule': (ct.c_int, [_H, ct.POINTER(ct.c_int32), ct.POINTER(ct.c_int32), ct.POINTER(ct.c_uint8)]),
     'fb_set_fast_lean': (ct.c_int, [_H, ct.c_int]),
     'fb_fast_lean': (ct.c_int, [_H]),
     'fb_last_pending': (ct.c_int, [_H, ct.POINTER(ct.c_int)]),
@@ -556,6 +560,27 @@ class BatchedPhysics:
     @property
     def fast_slim(self):
         return int(self.lib.fb_fast_slim(self._handle))
+
+    def set_fast_split(self, enable):
+        """Use or not the SPLIT variant of the unconstrained kernel (several warps per 32
+        environments, small batches; fb_set_fast_split)."""
+        self._check(self.lib.fb_set_fast_split(self._handle, int(bool(enable))))
+
+    @property
+    def fast_split(self):
+        """Warps per 32 environments when ``step`` launches the SPLIT variant, else 0."""
+        return int(self.lib.fb_fast_split(self._handle))
+
+    def fast_split_schedule(self):
+        """The tree split: list (one entry per warp) of (phase A bodies, phase B bodies)."""
+        n, bnd = (ct.c_int32*4)(), (ct.c_int32*4)()
+        order = (ct.c_uint8*(4*64))()
+        nw = int(self.lib.fb_fast_split_schedule(self._handle, n, bnd, order))
+        out = []
+        for w in range(nw):
+            bodies = [int(order[64*w + i]) for i in range(n[w])]
+            out.append((bodies[:bnd[w]], bodies[bnd[w]:]))
+        return out
 
     def set_fast_lean(self, enable):
         """Use (default) or not the LEAN variants of the unconstrained kernel (fb_set_fast_lean)."""

@@ -329,6 +329,17 @@ int fb_set_fast_slim(FbHandle *h, int enable);
  * fb_set_fast_lean(h, 0) forces the general variant; fb_fast_lean = 1 when the lean one applies. */
 int fb_set_fast_lean(FbHandle *h, int enable);
 int fb_fast_lean(FbHandle *h);
+/* SPLIT variant of the unconstrained kernel for small batches: the tree of every 32 environments is
+ * stepped by several warps (the trunk up to the last branching body on one, the subtrees hanging
+ * off it in parallel on the others, two phases per sweep), so that a launch lasts about one trunk +
+ * one subtree instead of the whole tree; same per-body arithmetic in the same order along every
+ * chain (bit-identical results).  fb_create enables it while the batch leaves schedulers idle;
+ * fb_fast_split = warps per 32 environments when it is in use, else 0;
+ * fb_fast_split_schedule returns the body lists (n[4], boundary[4] = end of phase A, order[4][64]). */
+int fb_set_fast_split(FbHandle *h, int enable);
+int fb_fast_split(FbHandle *h);
+int fb_fast_split_schedule(FbHandle *h, int32_t *n, int32_t *boundary, uint8_t *order);
+int fb_fast_split_blocks_per_sm(FbHandle *h);   /* resident SPLIT blocks per SM (occupancy API), 0 if n/a */
 int fb_fast_slim(FbHandle *h);
 int fb_last_pending(FbHandle *h, int *count);
 

@@ -31,13 +31,9 @@ def compare_with_oracle(spec, model, physics, qpos0, qvel0, ctrl, envs, n_steps,
     return worst
 
 
-def check_hand_over(library, name, n_envs, n_steps=16, tol=2e-3, per_thread=True):
-    """Joints start just inside their upper limit and move into it: the per-thread kernel
-    takes the first steps, hands an environment over when its limit becomes active (a
-    different step in every environment, some never), and the team kernel finishes the
-    launch with the limit row in the solver.  The log must be the oracle's throughout."""
-    from farms_mujoco_b200.engine import BatchedPhysics
-    from farms_mujoco_b200.layout import sc
+def hand_over_case(name, n_envs):
+    """Joints start just inside their upper limit; the position actuator of a driven joint pulls it
+    through the limit after a few steps (a different number in every environment, some never)."""
     spec, model, qpos0, qvel0, ctrl = make_case(name, n_envs, qvel_scale=0.0, ctrl_scale=0.0)
     rng = np.random.default_rng(5)
     hi = np.asarray(model.jnt_range).reshape(-1, 2)[:, 1]
@@ -60,6 +56,17 @@ def check_hand_over(library, name, n_envs, n_steps=16, tol=2e-3, per_thread=True
     qpos0[rows, qadr] = hi[joint] - rng.uniform(0.0, 0.004, size=n_envs)
     for e in range(n_envs):
         ctrl[e, position_act[int(joint[e])]] = hi[joint[e]] + (0.6 if driven[e] else -0.2)
+    return spec, model, qpos0, qvel0, ctrl
+
+
+def check_hand_over(library, name, n_envs, n_steps=16, tol=2e-3, per_thread=True):
+    """Joints start just inside their upper limit and move into it: the per-thread kernel
+    takes the first steps, hands an environment over when its limit becomes active (a
+    different step in every environment, some never), and the team kernel finishes the
+    launch with the limit row in the solver.  The log must be the oracle's throughout."""
+    from farms_mujoco_b200.engine import BatchedPhysics
+    from farms_mujoco_b200.layout import sc
+    spec, model, qpos0, qvel0, ctrl = hand_over_case(name, n_envs)
     physics = BatchedPhysics.from_spec(spec, n_envs, buffer_size=n_steps + 1, library=library)
     assert physics.fast_path
     physics.set_constraint_path(per_thread)
@@ -398,3 +405,36 @@ def check_lean_variant(library, names=('swimmer8', 'salamander_swim', 'salamande
                     assert log_error(kind, other[3][kind][env], ref[3][kind][env]) < tol, (name, slim, kind)
     physics = BatchedPhysics.from_spec(variant_models.swimmer8_features(), 2, buffer_size=2, library=library)
     assert not physics.fast_lean            # slide joint, clamps, off-origin anchors
+
+
+def check_split_variant_is_bit_identical(library, n_envs=75):
+    """SPLIT variant (several warps per 32 environments, each its own bodies of the tree) against the
+    single-warp kernel: the same per-body code in the same order along every chain, hence the same
+    bits -- unconstrained rollouts, ground models (handed over at step 0) and hand-overs in the
+    middle of a launch."""
+    from farms_mujoco_b200.engine import BatchedPhysics
+    for name in ('salamander_swim', 'salamander', 'centipede'):
+        if name == 'salamander_swim':
+            # some environments reach a joint limit within the launch: mixed warps
+            spec, model, qpos0, qvel0, ctrl = hand_over_case(name, n_envs)
+        else:
+            spec, model, qpos0, qvel0, ctrl = make_case(name, n_envs)
+        outs = []
+        for split in (False, True):
+            physics = BatchedPhysics.from_spec(spec, n_envs, buffer_size=12, library=library)
+            physics.set_fast_split(split)
+            assert bool(physics.fast_split) == split and (not split or physics.fast_split >= 3), name
+            physics.reset(qpos0, qvel0)
+            physics.set_ctrl(ctrl)
+            physics.step(6)
+            pending = physics.last_pending
+            physics.step(5)
+            outs.append((physics.qpos, physics.qvel, physics.xfrc_applied, physics.log_arrays(), pending, physics.flags))
+        assert outs[0][4] == outs[1][4], (name, outs[0][4], outs[1][4])
+        if name == 'salamander_swim':
+            assert 0 < outs[0][4] < n_envs
+        assert np.array_equal(outs[0][5], outs[1][5])
+        assert np.array_equal(outs[0][0], outs[1][0]) and np.array_equal(outs[0][1], outs[1][1]), name
+        assert np.array_equal(outs[0][2], outs[1][2]), name
+        for kind in ('links', 'joints', 'contacts', 'xfrc'):
+            assert np.array_equal(outs[0][3][kind], outs[1][3][kind]), (name, kind)

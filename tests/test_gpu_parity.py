@@ -666,3 +666,10 @@ def test_lean_variant(cuda_library, monkeypatch):
     import fastpath_cases
     monkeypatch.setenv('FARMS_B200_FAST_BLOCK', '32')
     fastpath_cases.check_lean_variant(cuda_library, n_envs=75, slims=(0, 1, 7))
+
+
+def test_split_variant_is_bit_identical(cuda_library, monkeypatch):
+    """Small-batch SPLIT variant of the unconstrained kernel (fb_fast_split_kernel)."""
+    import fastpath_cases
+    monkeypatch.setenv('FARMS_B200_FAST_BLOCK', '32')
+    fastpath_cases.check_split_variant_is_bit_identical(cuda_library)

@@ -172,3 +172,42 @@ def test_no_cpu_fallback_without_library(tmp_path):
     from farms_mujoco_b200 import engine
     with pytest.raises(engine.EngineError, match='no CPU fallback'):
         engine.load_library(str(tmp_path/'missing.so'))
+
+
+def test_tree_split_schedule(emu_library):
+    """FastSplit (fb_model.h: fb_build_split): the trunk up to the last branching body on warp 0, the
+    subtrees behind it in parallel, subtrees of one parent on one warp, every body exactly once, and
+    every chain link (parent == body - 1) consecutive on its warp."""
+    from farms_mujoco_b200 import models, mjcf_subset
+    from farms_mujoco_b200.engine import BatchedPhysics
+    for name, want_warps in (('swimmer8', 1), ('salamander_swim', 3), ('centipede', 4)):
+        spec = models.MODELS[name]()
+        model = mjcf_subset.parse_mjcf(spec.mjcf)
+        physics = BatchedPhysics.from_spec(spec, 2, buffer_size=2, library=emu_library)
+        sched = physics.fast_split_schedule()
+        assert len(sched) == want_warps, (name, sched)
+        parent = [int(p) for p in model.body_parentid]
+        seen = sorted(b for a, bb in sched for b in a + bb)
+        assert seen == list(range(1, model.nbody)), name
+        if want_warps == 1:
+            continue
+        trunk = sched[0][0]
+        split = trunk[-1]
+        assert trunk == list(range(1, split + 1)) and all(not a for a, _ in sched[1:])
+        assert max(parent[b] for b in range(2, model.nbody) if parent[b] != b - 1 and parent[b] >= 1) == split
+        owner = {b: w for w, (a, bb) in enumerate(sched) for b in a + bb}
+        for w, (a, bb) in enumerate(sched):
+            order = a + bb
+            for i, b in enumerate(order):
+                p = parent[b]
+                if b > split and p > split:
+                    assert owner[p] == w and order.index(p) < i            # inside its subtree
+                if p == b - 1 and p >= 1:
+                    assert i > 0 and order[i - 1] == p, (name, b)          # register hand-over stays consecutive
+        roots = {}
+        for b in range(split + 1, model.nbody):
+            if parent[b] <= split and not (b == split + 1 and parent[b] == split):
+                roots.setdefault(parent[b], set()).add(owner[b])
+        assert all(len(ws) == 1 for ws in roots.values()), roots     # one slot, one warp
+    if name == 'salamander_swim':
+        pass
