@@ -9,14 +9,22 @@ Workload (config.workload): swimming salamander (28 links, nv=33) with
 hydrodynamic drag + buoyancy and full sensor logging (links/joints/contacts/
 xfrc), the 65,536-environment sweep BASELINE.json's metric is quoted on
 (configs[4]): 65,536 environments per GPU, N GPUs step N x 65,536 independent
-environments (weak scaling, no data-path collective).  ``--envs-per-gpu 16384`` is
-configs[2].  One bench "step" = one launch of the fused kernels advancing every
-environment by ``--inner`` physics steps.
+environments (weak scaling, no data-path collective).  ``--total-envs 65536`` is the
+same sweep with the environments sharded over the GPUs (strong scaling);
+``--envs-per-gpu 16384`` is configs[2].  One bench "step" = one launch of the fused
+kernels advancing every environment by ``--inner`` physics steps.
 
-value  : device-timed (CUDA events on the engine's stream, max over ranks),
-         state resident in HBM.
-e2e    : the same through BatchedPhysics.step_host on pinned HOST buffers:
-         ctrl uploaded, last links+joints log row of every env downloaded.
+value    : device-timed (CUDA events on the engine's stream, max over ranks),
+           state resident in HBM.
+e2e      : the same through BatchedPhysics.step_host on pinned HOST buffers, every launch:
+           ctrl of the controlled actuators uploaded (evaluated by a host-side controller),
+           the last joints row (4 written columns) and the head link's pose downloaded;
+           e2e.full_log_export = rate of the streamed export of the FULL log (fb_export_rows).
+roofline : algorithmic log bytes / launch time against measured HBM, plus the FP32 side
+           (``fp32``); ``bound`` is the larger of the two fractions.
+cpu_baseline / --impl reference: the oracle port on every host core (oracle/farms_loop.c: fp64 C
+           restatement of mj_step + the farms glue), a bounded sample of the same workload.
+extra    : (N = 1) device-timed lines of BASELINE.json's other configurations.
 """
 
 import argparse

@@ -5,13 +5,13 @@ fb_set_constraint_path):
   * 'fast': the default fb_step -- the environment-per-thread kernel (articulated-body
     recursion) plus the per-thread constrained kernel (matrix-free Newton, fb_fastc.h) on
     whatever it hands over.  Single step 1e-5 (BASELINE.json north_star) on every model, contact
-    forces 2e-4 (proportional to a penetration depth the fp32 state holds to 4e-9 m); 20 steps 5e-5.
+    forces included for the SALAMANDER (CENTIPEDE: 1e-4, see CONTACT_TOL); 20 steps 5e-5.
   * 'fast_team': the per-thread kernel plus the TEAM kernel on the hand-overs.
-  * 'team': the team kernel alone (CRB + L'DL + constraint solver, as MuJoCo does it).
-    fp32 solves of the ill-conditioned mass matrix reach 2e-5 .. 6e-5; tolerance 5e-4 for
-    a single step and for 20 swimming steps, 5e-3 for 20 steps of ground contact (the
-    active set of the soft-contact solver amplifies rounding).
-Scaled error = max|a-b| / max(1, max|b|).  Measured values in DESIGN.md.
+  * 'team': the team kernel alone (CRB + L'DL + constraint solver, as MuJoCo does it), a
+    secondary path: TEAM_TOL.
+Metric: group-wise relative error, conftest.py (PARITY_FLOOR).  Measured values in DESIGN.md 5.
+Kernel variants (layouts, LEAN, SPLIT, block sizes) are held to each other bit for bit where they
+share a compilation and to a few ulp where they do not.
 """
 
 import numpy as np
