@@ -84,9 +84,9 @@ def parse_args():
 from farms_mujoco_b200.sharding import synthetic_inputs, gather_env_statistics, bind_host_to_device  # noqa: E402
 
 
-def wave_controller(spec, model):
+def wave_controller(spec, model, amplitude=0.3):
     from farms_mujoco_b200.models import travelling_wave_parameters
-    joints, amp, freq, lag = travelling_wave_parameters(spec)
+    joints, amp, freq, lag = travelling_wave_parameters(spec, amplitude=amplitude)
     acts = [model.actuator_id(f'actuator_position_{j}') for j in joints]
     return acts, amp, freq, lag
 
@@ -357,8 +357,10 @@ def roofline_objects(args_model, spec, physics, n_local, inner, k_ms, per_gpu_ra
     return roofline, fp32
 
 
-def short_device_run(name, n_envs, inner, ring, steps, warmup, device, peaks):
-    """Device-timed run of another BASELINE.json configuration on this GPU (no e2e, no CPU arm)."""
+def short_device_run(name, n_envs, inner, ring, steps, warmup, device, peaks, amplitude=0.3):
+    """Device-timed run of another BASELINE.json configuration on this GPU (no e2e, no CPU arm).
+    ``amplitude`` > 1 drives the body joints into their +-1 rad limits: the mixed regime in which the
+    unconstrained kernel hands environments over to the constrained one in the middle of a launch."""
     import ctypes
     import torch
     from farms_mujoco_b200 import models, mjcf_subset
@@ -368,7 +370,7 @@ def short_device_run(name, n_envs, inner, ring, steps, warmup, device, peaks):
     qpos0, qvel0, phase = synthetic_inputs(model, np.arange(n_envs))
     physics = BatchedPhysics.from_spec(spec, n_envs, buffer_size=ring, device=device)
     physics.set_env_phase(phase)
-    physics.set_wave_controller(*wave_controller(spec, model))
+    physics.set_wave_controller(*wave_controller(spec, model, amplitude))
     physics.reset(qpos0, qvel0)
     stream_ptr = ctypes.c_void_p()
     physics._check(physics.lib.fb_device_ptr_stream(physics._handle, ctypes.byref(stream_ptr)))
@@ -396,7 +398,8 @@ def short_device_run(name, n_envs, inner, ring, steps, warmup, device, peaks):
                                       handed_over, peaks, device)
     flags = physics.flags
     out = {
-        'workload': f'{name}: {n_envs} envs on 1 GPU, full log, on-device travelling-wave control',
+        'workload': (f'{name}: {n_envs} envs on 1 GPU, full log, on-device travelling-wave control'
+                     + ('' if amplitude == 0.3 else f', wave amplitude {amplitude} rad (joint limits at +-1: mixed regime)')),
         'value': value, 'unit': 'env-steps/s', 'ms_per_step': ms/steps, 'steps': steps, 'warmup': warmup,
         'physics_steps_per_step': inner, 'gpu_launches': int(launches),
         'handed_over_envs_last_launch': int(handed_over), 'diverged_envs': int(np.count_nonzero(flags & 1)),
@@ -663,12 +666,13 @@ def run_b200(args, rank, world, local_rank):
             # number attached; the headline stays the line's own value)
             physics.close()
             extra = []
-            for name, n_envs in (('salamander', 4096), ('salamander_swim', 16384), ('centipede', 8192),
-                                 ('salamander_swim', 8192)):
-                if name == args.model and n_envs == n_local:
+            for name, n_envs, amplitude in (('salamander', 4096, 0.3), ('salamander_swim', 16384, 0.3),
+                                            ('centipede', 8192, 0.3), ('salamander_swim', 8192, 0.3),
+                                            ('salamander_swim', 16384, 1.3)):
+                if name == args.model and n_envs == n_local and amplitude == 0.3:
                     continue
                 try:
-                    extra.append(short_device_run(name, n_envs, args.inner, 64, 10, 3, local_rank, peaks))
+                    extra.append(short_device_run(name, n_envs, args.inner, 64, 10, 3, local_rank, peaks, amplitude))
                 except Exception as exc:  # pylint: disable=broad-except
                     extra.append({'workload': f'{name}: {n_envs} envs', 'error': str(exc)})
             out['extra'] = {'other_configs': extra}

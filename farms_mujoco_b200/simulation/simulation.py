@@ -197,8 +197,13 @@ class Simulation:
 
     def postprocess(self, iteration, log_path='', plot=False, **kwargs):
         """Postprocessing after simulation (simulation.py:181-213).  The reference writes
-        ``simulation.hdf5`` through farms_core; h5py is not in this image, so the same arrays
-        go to ``simulation.npz`` (keys ``<kind>`` and ``<kind>_names``); options as YAML."""
+        ``simulation.hdf5`` through farms_core's ``AnimatData.to_file`` (a nested dict -> HDF5
+        groups); h5py and farms_core are not in this image, so the same arrays go to
+        ``simulation.npz`` under the keys of that tree as farms_core lays it out to the best of
+        our knowledge (UNVERIFIED): ``timestep``, ``sensors/<kind>/array``
+        (here with a leading environment axis: ``[n_envs, iteration, n_items, n_cols]``) and
+        ``sensors/<kind>/names``; the flat ``<kind>`` / ``<kind>_names`` keys of round 1 are kept.
+        Options go to the two YAML files as in the reference."""
         del kwargs
         assert not plot, 'plotting is outside the batched path'
         times = np.arange(0, self.task.timestep*self.task.n_iterations, self.task.timestep)[:iteration]
@@ -209,8 +214,11 @@ class Simulation:
             payload = {'times': times, 'timestep': self.task.timestep}
             for kind in ('links', 'joints', 'contacts', 'xfrc'):
                 arr = getattr(sensors, kind)
+                names = np.array([str(n) for n in arr.names])
                 payload[kind] = arr.array[:, :iteration]
-                payload[f'{kind}_names'] = np.array([str(n) for n in arr.names])
+                payload[f'{kind}_names'] = names
+                payload[f'sensors/{kind}/array'] = arr.array[:, :iteration]
+                payload[f'sensors/{kind}/names'] = names
             np.savez_compressed(os.path.join(log_path, 'simulation.npz'), **payload)
             with open(os.path.join(log_path, 'simulation_options.yaml'), 'w', encoding='utf-8') as out:
                 yaml.safe_dump(_plain(self.options), out)
