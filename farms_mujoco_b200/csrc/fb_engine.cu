@@ -617,7 +617,10 @@ static int launch(FbHandle *h, int mode, int n_steps, int want_derived) {
     default: fb_step_kernel<32><<<blocks, h->threads, h->smem_bytes, h->stream>>>(P); break;
   }
   cudaEventRecord(h->ev1, h->stream);
-  if (cudaGetLastError() != cudaSuccess) return fail(std::string("kernel launch failed: ") + dev_error());
+  {
+    const cudaError_t le = cudaGetLastError();
+    if (le != cudaSuccess) return fail(std::string("kernel launch failed: ") + cudaGetErrorString(le));
+  }
 #endif
   h->launches++;
   if (mode == FB_MODE_RESET) h->it = 0; else h->it += n_steps;
