@@ -645,6 +645,7 @@ def run_b200(args, rank, world, local_rank):
                 'fast_slim_layout': bool(physics.fast_slim),
                 'fast_lean_variant': bool(physics.fast_lean),
                 'fast_split_warps': int(physics.fast_split),
+                'constrained_split': bool(physics.con_split),
                 'fast_warps_per_block': max(1, int(physics.fast_slim)),
                 'fast_smem_bytes_per_env': physics.fast_smem_bytes_per_env,
                 'handed_over_envs_last_launch': handed_over,

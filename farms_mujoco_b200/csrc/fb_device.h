@@ -44,11 +44,22 @@ __device__ __forceinline__ void fb_sincos(float x, float *s, float *c) { sincosf
 #endif
 
 #ifdef FB_HOST_EMU
+#include <pthread.h>
+#include <cstring>
 #define FB_POPC(x) __builtin_popcount(x)
-#define FB_FLAG_OR(ptr, bit) (*(ptr) |= (bit))
+#define FB_FLAG_OR(ptr, bit) __atomic_fetch_or((ptr), (bit), __ATOMIC_RELAXED)
+/* SPLIT variants under the test harness: the warps of a block are host threads (one lane each)
+ * that meet at this barrier; NULL outside such a run */
+static pthread_barrier_t *fb_emu_bar = 0;
+#define FB_BLOCK_BARRIER() do { if (fb_emu_bar) pthread_barrier_wait(fb_emu_bar); } while (0)
+static inline float fb_u2f(unsigned u) { float f; std::memcpy(&f, &u, 4); return f; }
+static inline unsigned fb_f2u(float f) { unsigned u; std::memcpy(&u, &f, 4); return u; }
 #else
 #define FB_POPC(x) __popc(x)
 #define FB_FLAG_OR(ptr, bit) atomicOr((ptr), (bit))
+#define FB_BLOCK_BARRIER() __syncthreads()
+__device__ __forceinline__ float fb_u2f(unsigned u) { return __uint_as_float(u); }
+__device__ __forceinline__ unsigned fb_f2u(float f) { return __float_as_uint(f); }
 #endif
 
 #define MI(name, i) FB_LDG(m.I + m.o.name + (i))
@@ -1345,6 +1356,10 @@ struct FbParams {
    * overwrites was last written at or before that iteration (fb_fast.h: log_row_dirty); the
    * log starts zeroed (fb_create, fb_reset) and nothing else writes it. */
   long long *con_dirty;
+  /* Groups of environments the SPLIT variant of the per-thread constrained kernel has stepped in
+   * this launch (fb_fastc_split_kernel writes 0 / 1 per group; the single-warp kernel launched
+   * behind it skips the groups marked 1).  NULL: the SPLIT variant was not launched. */
+  int *con_split_done;
 };
 
 #define FB_NEVER_DIRTY (-(1LL << 60))

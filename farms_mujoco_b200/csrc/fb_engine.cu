@@ -20,6 +20,9 @@
 #include <new>
 #include <string>
 #include <vector>
+#ifdef FB_HOST_EMU
+#include <thread>
+#endif
 
 #include "fb_fastc.h"
 #include "fb_cpg.h"
@@ -175,6 +178,7 @@ fb_fastc_kernel(const __grid_constant__ FbFastConParams Q) {
   const int i = blockIdx.x*BLK + threadIdx.x;
   const int count = P.use_pending ? P.pending_count[P.parity] : P.n_envs;
   if (i >= count) return;
+  if (P.con_split_done && P.con_split_done[blockIdx.x]) return;      /* stepped by the SPLIT variant */
   const int identity = !P.use_pending || count == P.n_envs;
   const int env = identity ? i : P.pending[i];
   const int k0 = P.use_pending ? P.steps_done[env] : 0;
@@ -183,6 +187,45 @@ fb_fastc_kernel(const __grid_constant__ FbFastConParams Q) {
                     P.con_scratch + t0*P.m.X.n_con + threadIdx.x, env);
   const int coop = BLK == 32 && identity && P.m.X.coop_io && (blockIdx.x + 1)*BLK <= count;
   st.run_con(k0, coop, threadIdx.x);
+}
+
+/* SPLIT variant of the constrained kernel: one block = the BLK environments of one group (the
+ * lanes of a warp; the upper half-warp leaves at once when BLK = 16) stepped by split.nwarps
+ * warps, each its own bodies of the tree.  It takes the groups in which EVERY environment was
+ * handed over before its first step (ground-contact batches: all of them, every launch) and marks
+ * them in con_split_done; everything else is left to fb_fastc_kernel, launched behind it. */
+struct FbFastConSplitParams {
+  FbParams P;
+  FastRec rec[FB_FAST_MAXBODY];
+  CandRec cand[FB_FAST_MAXCAND];
+  FastSplit split;
+};
+static_assert(sizeof(FbFastConSplitParams) <= 32764, "kernel parameters of fb_fastc_split_kernel exceed 32 KB");
+/* floats per lane behind the body blocks: root position [3], hand-over flag, reduction buffers */
+#define FB_CSPLIT_EXTRA (4 + 2*FB_SPLIT_MAXW*FB_RED_MAX)
+#ifndef FB_CSPLIT_MINBLOCKS
+#define FB_CSPLIT_MINBLOCKS 2
+#endif
+template <int BLK, int LEAN>
+__global__ void __launch_bounds__(32*FB_SPLIT_MAXW, FB_CSPLIT_MINBLOCKS)
+fb_fastc_split_kernel(const __grid_constant__ FbFastConSplitParams Q) {
+  extern __shared__ __align__(16) float fb_smem[];
+  const FbParams &P = Q.P;
+  const int role = threadIdx.x >> 5, lane = threadIdx.x & 31, grp = blockIdx.x;
+  const int env = grp*BLK + lane;
+  if (lane >= BLK || env >= P.n_envs) return;
+  /* block-uniform: every warp sees the same lanes */
+  const int all0 = P.pending_count[P.parity] == P.n_envs && __ballot_sync(__activemask(), P.steps_done[env] != 0) == 0u;
+  if (threadIdx.x == 0) P.con_split_done[grp] = all0;
+  if (!all0) return;
+  const size_t t0 = (size_t)grp*BLK;
+  FbFastCon<BLK, LEAN, 1> st(P, Q.rec, Q.cand, fb_smem + lane, P.fast_scratch + t0*P.m.X.n_scratch + lane,
+                             P.con_scratch + t0*P.m.X.n_con + lane, env);
+  float *extra = fb_smem + (size_t)P.m.X.n_float*BLK;
+  st.split_setup(Q.split, role, extra + lane, reinterpret_cast<int *>(extra + 3*BLK) + lane);
+  st.con_split_setup(Q.split, extra + 4*BLK + lane);
+  const int coop = BLK == 32 && P.m.X.coop_io && (grp + 1)*BLK <= P.n_envs;
+  st.run_con_split(coop, lane);
 }
 
 /* ring row `row` of every environment -> dense [n_envs][row_floats] (the reference's row
@@ -302,6 +345,9 @@ struct FbHandle {
   int fast_lean;                    /* 1: use the LEAN variants when the model allows (FARMS_B200_FAST_LEAN=0 switches them off) */
   int fast_split;                   /* 1: small batches run the SPLIT variant (several warps per 32 environments) */
   long long split_capacity;         /* blocks of the SPLIT variant the device holds at once (0: not applicable) */
+  int con_split;                    /* 1: ground-contact batches run the SPLIT variant of the constrained kernel */
+  long long con_split_capacity;     /* blocks of it the device holds at once, at the current environments per warp */
+  int *con_split_done;              /* device: FbParams::con_split_done */
   bool fast_block_auto;             /* 16 environments per warp chosen by the heuristic ... */
   int block_review;                 /* ... and reviewed after the first launch of an episode */
   int max_smem;
@@ -313,6 +359,7 @@ struct FbHandle {
   FbFastParams *fastQ;               /* host staging of the per-thread kernel's parameters */
   FbFastSplitParams *splitQ;         /* ... of its SPLIT variant */
   FbFastConParams *conQ;             /* ... and of the per-thread constrained kernel's */
+  FbFastConSplitParams *csplitQ;     /* ... and of its SPLIT variant */
 #endif
   fbStream stream;
   std::vector<void *> allocs;
@@ -456,6 +503,10 @@ static int upload_model(FbHandle *h) {
     memcpy(h->conQ->rec, h->fastQ->rec, sizeof(h->conQ->rec));
     memset(h->conQ->cand, 0, sizeof(h->conQ->cand));
     if (h->hm.m.X.con_ok) memcpy(h->conQ->cand, h->hm.crec.data(), sizeof(CandRec)*h->hm.crec.size());
+    if (!h->csplitQ) h->csplitQ = new FbFastConSplitParams();
+    memcpy(h->csplitQ->rec, h->conQ->rec, sizeof(h->csplitQ->rec));
+    memcpy(h->csplitQ->cand, h->conQ->cand, sizeof(h->csplitQ->cand));
+    h->csplitQ->split = h->hm.split;
   }
 #endif
   return 0;
@@ -463,6 +514,7 @@ static int upload_model(FbHandle *h) {
 
 #ifndef FB_HOST_EMU
 static int fb_set_fast_block(FbHandle *h, int blk);
+static long long fb_con_split_blocks(FbHandle *h, int blk, cudaError_t *ce);
 #endif
 
 /* capacity of the device control sequence ([n_steps][nu][env_pad] + the upload staging) */
@@ -479,6 +531,20 @@ static int ensure_sequence(FbHandle *h, int n_steps) {
   h->seq_cap = n_steps;
   return 0;
 }
+
+#ifdef FB_HOST_EMU
+/* test harness: the warps of a SPLIT block as host threads meeting at FB_BLOCK_BARRIER */
+template <class F> static void emu_split_run(int nw, F body) {
+  pthread_barrier_t bar;
+  pthread_barrier_init(&bar, nullptr, nw);
+  fb_emu_bar = &bar;
+  std::vector<std::thread> th;
+  for (int r = 0; r < nw; r++) th.emplace_back(body, r);
+  for (auto &t : th) t.join();
+  fb_emu_bar = nullptr;
+  pthread_barrier_destroy(&bar);
+}
+#endif
 
 static int launch(FbHandle *h, int mode, int n_steps, int want_derived) {
   FbParams &P = h->P;
@@ -517,9 +583,30 @@ static int launch(FbHandle *h, int mode, int n_steps, int want_derived) {
     P.pending_count[P.parity ^ 1] = 0;
     std::vector<float> fs((size_t)m.X.n_float + 8, 0.f);
     std::vector<float> fg((size_t)(m.X.n_scratch > m.X.n_scratch_slim ? m.X.n_scratch : m.X.n_scratch_slim) + 8, 0.f);
+    const FastSplit &sp = h->hm.split;
+    const int n_extra = 4 + 2*FB_SPLIT_MAXW*FB_RED_MAX;      /* root position, flag, reduction buffers (one lane) */
     for (int env = 0; env < P.n_envs; env++) {
       int done;
       const bool lean = h->fast_lean && m.X.lean && !P.ctrl_seq;
+      if (h->fast_split && !h->fast_slim && sp.nwarps > 1) {
+        /* SPLIT variant: the warps of the block are host threads */
+        std::vector<float> extra(n_extra, 0.f);
+        int done0 = 0;
+        emu_split_run(sp.nwarps, [&](int role) {
+          int d;
+          if (lean) {
+            FbFast<1, 0, 0, 1, 1> st(P, h->hm.rec.data(), fs.data(), fg.data(), env);
+            st.split_setup(sp, role, extra.data(), reinterpret_cast<int *>(extra.data() + 3));
+            d = st.run_split(0, 0, 1);
+          } else {
+            FbFast<1, 0, 0, 0, 1> st(P, h->hm.rec.data(), fs.data(), fg.data(), env);
+            st.split_setup(sp, role, extra.data(), reinterpret_cast<int *>(extra.data() + 3));
+            d = st.run_split(0, 0, 1);
+          }
+          if (role == 0) done0 = d;
+        });
+        done = done0;
+      } else
       if (h->fast_slim && lean) { FbFast<1, 1, 0, 1> st(P, h->hm.rec.data(), fs.data(), fg.data(), env); done = st.run(0, 0); }
       else if (h->fast_slim) { FbFast<1, 1> st(P, h->hm.rec.data(), fs.data(), fg.data(), env); done = st.run(0, 0); }
       else if (lean) { FbFast<1, 0, 0, 1> st(P, h->hm.rec.data(), fs.data(), fg.data(), env); done = st.run(0, 0); }
@@ -530,6 +617,25 @@ static int launch(FbHandle *h, int mode, int n_steps, int want_derived) {
       std::vector<float> fc((size_t)m.X.n_con + 8, 0.f);
       for (int i = 0; i < P.pending_count[P.parity]; i++) {
         const int env = P.pending[i];
+        if (h->con_split && !h->fast_slim && sp.nwarps > 1 && P.steps_done[env] == 0) {
+          /* SPLIT variant of the constrained kernel (a group = this environment) */
+          std::vector<float> extra(n_extra, 0.f);
+          const bool lean = h->fast_lean && m.X.lean && !P.ctrl_seq;
+          emu_split_run(sp.nwarps, [&](int role) {
+            if (lean) {
+              FbFastCon<1, 1, 1> st(P, h->hm.rec.data(), h->hm.crec.data(), fs.data(), fg.data(), fc.data(), env);
+              st.split_setup(sp, role, extra.data(), reinterpret_cast<int *>(extra.data() + 3));
+              st.con_split_setup(sp, extra.data() + 4);
+              st.run_con_split(0, 0);
+            } else {
+              FbFastCon<1, 0, 1> st(P, h->hm.rec.data(), h->hm.crec.data(), fs.data(), fg.data(), fc.data(), env);
+              st.split_setup(sp, role, extra.data(), reinterpret_cast<int *>(extra.data() + 3));
+              st.con_split_setup(sp, extra.data() + 4);
+              st.run_con_split(0, 0);
+            }
+          });
+          continue;
+        }
         if (h->fast_lean && m.X.lean && !P.ctrl_seq) {
           FbFastCon<1, 1> st(P, h->hm.rec.data(), h->hm.crec.data(), fs.data(), fg.data(), fc.data(), env);
           st.run_con(P.steps_done[env], 0, 0);
@@ -600,8 +706,24 @@ static int launch(FbHandle *h, int mode, int n_steps, int want_derived) {
     }
     h->launches++;
     if (con_thread) {
-      h->conQ->P = P;
       const bool clean = h->fast_lean && P.m.X.lean && !P.ctrl_seq;
+      P.con_split_done = nullptr;
+      if (h->con_split && P.use_pending && !h->fast_slim && h->hm.split.nwarps > 1 && fblocks <= h->con_split_capacity) {
+        /* small ground-contact batch: the tree of every group split over several warps */
+        P.con_split_done = h->con_split_done;
+        h->csplitQ->P = P;
+        const size_t sbytes = h->fast_smem_bytes + (size_t)FB_CSPLIT_EXTRA*h->fast_block*sizeof(float);
+        const int threads = 32*h->hm.split.nwarps;
+        if (h->fast_block == 16) {
+          if (clean) fb_fastc_split_kernel<16, 1><<<fblocks, threads, sbytes, h->stream>>>(*h->csplitQ);
+          else fb_fastc_split_kernel<16, 0><<<fblocks, threads, sbytes, h->stream>>>(*h->csplitQ);
+        } else {
+          if (clean) fb_fastc_split_kernel<32, 1><<<fblocks, threads, sbytes, h->stream>>>(*h->csplitQ);
+          else fb_fastc_split_kernel<32, 0><<<fblocks, threads, sbytes, h->stream>>>(*h->csplitQ);
+        }
+        h->launches++;
+      }
+      h->conQ->P = P;
       if (h->fast_block == 16) {
         if (clean) fb_fastc_kernel<16, 1><<<fblocks, 16, h->fast_smem_bytes, h->stream>>>(*h->conQ);
         else fb_fastc_kernel<16><<<fblocks, 16, h->fast_smem_bytes, h->stream>>>(*h->conQ);
@@ -636,7 +758,14 @@ static int launch(FbHandle *h, int mode, int n_steps, int want_derived) {
     h->block_review = 0;
     int both[2] = {0, 0};
     if (d2h(both, P.pending_count, sizeof(both), h->stream) || dev_sync(h->stream)) return fail(dev_error());
-    const int want = 2*both[P.parity] >= P.n_envs ? 16 : 32;
+    int want = 2*both[P.parity] >= P.n_envs ? 16 : 32;
+    if (want == 16 && con_thread && h->con_split && h->hm.split.nwarps > 1) {
+      /* with the constrained SPLIT variant a group is several warps: 16 per group pays only while
+       * every group has an SM to itself (r2x, SALAMANDER ground: 1,024 envs 3.47e6 against 3.31e6
+       * env-steps/s with 32; 4,096 envs 1.09e7 against 1.29e7) */
+      cudaError_t ce = cudaSuccess;
+      if ((P.n_envs + 15)/16 > h->sms && (P.n_envs + 31)/32 <= fb_con_split_blocks(h, 32, &ce)) want = 32;
+    }
     if (want != h->fast_block && (size_t)P.m.X.n_float*sizeof(float)*want <= (size_t)h->max_smem && fb_set_fast_block(h, want)) return -1;
   }
 #endif
@@ -644,6 +773,24 @@ static int launch(FbHandle *h, int mode, int n_steps, int want_derived) {
 }
 
 #ifndef FB_HOST_EMU
+/* blocks of the constrained SPLIT variant the device holds at once with `blk` environments per group
+ * (0: not applicable); sets the kernels' shared-memory attributes on the way */
+static long long fb_con_split_blocks(FbHandle *h, int blk, cudaError_t *ce) {
+  const size_t sbytes = ((size_t)h->hm.m.X.n_float + FB_CSPLIT_EXTRA)*blk*sizeof(float);
+  if (!h->hm.m.X.con_ok || h->hm.split.nwarps < 2 || sbytes > (size_t)h->max_smem) return 0;
+  int per_sm = 1 << 30;
+  for (int lean = 0; lean < 2 && *ce == cudaSuccess; lean++) {
+    const void *k = blk == 16 ? (lean ? (const void *)fb_fastc_split_kernel<16, 1> : (const void *)fb_fastc_split_kernel<16, 0>)
+                              : (lean ? (const void *)fb_fastc_split_kernel<32, 1> : (const void *)fb_fastc_split_kernel<32, 0>);
+    *ce = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sbytes);
+    if (*ce == cudaSuccess) *ce = cudaFuncSetAttribute(k, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    int nb = 0;
+    if (*ce == cudaSuccess) *ce = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k, 32*h->hm.split.nwarps, sbytes);
+    if (nb < per_sm) per_sm = nb;
+  }
+  return *ce == cudaSuccess ? (long long)per_sm*h->sms : 0;
+}
+
 /* environments per warp of the per-thread kernels (regular layout): shared-memory attributes */
 static int fb_set_fast_block(FbHandle *h, int blk) {
   const size_t per_thread = (size_t)h->hm.m.X.n_float*sizeof(float);
@@ -673,6 +820,7 @@ static int fb_set_fast_block(FbHandle *h, int blk) {
     /* the SPLIT variant pays while ALL its blocks are resident at once (one wave) */
     if (ce == cudaSuccess) h->split_capacity = (long long)per_sm*h->sms;
   }
+  if (ce == cudaSuccess) h->con_split_capacity = fb_con_split_blocks(h, blk, &ce);
   return ce == cudaSuccess ? 0 : fail(std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(ce));
 }
 
@@ -760,6 +908,7 @@ void fb_destroy(FbHandle *h) {
   delete h->fastQ;
   delete h->conQ;
   delete h->splitQ;
+  delete h->csplitQ;
 #endif
   delete h;
 }
@@ -781,11 +930,11 @@ int fb_create(const FbModel *model, const FbFarms *farms, int n_envs, int device
   if (const char *ev = getenv("FARMS_B200_CON_THREAD")) h->con_thread = atoi(ev) != 0;
   h->fast_slim = 0; h->fast_slim_smem_bytes = 0; h->fast_wpb = 1;
   h->fast_lean = 1; h->fast_block_auto = false; h->block_review = 0; h->max_smem = 0; h->fast_split = 0;
-  h->split_capacity = 0;
+  h->split_capacity = 0; h->con_split = 0; h->con_split_capacity = 0; h->con_split_done = nullptr;
   if (const char *ev = getenv("FARMS_B200_FAST_LEAN")) h->fast_lean = atoi(ev) != 0;
   if (const char *ev = getenv("FARMS_B200_FAST_SLIM")) h->fast_slim = atoi(ev) != 0;
 #ifndef FB_HOST_EMU
-  h->fastQ = nullptr; h->conQ = nullptr; h->splitQ = nullptr;
+  h->fastQ = nullptr; h->conQ = nullptr; h->splitQ = nullptr; h->csplitQ = nullptr;
 #endif
   if (const char *ev = getenv("FARMS_B200_FAST")) h->fast_enabled = atoi(ev) != 0;
   memset(&h->P, 0, sizeof(h->P));
@@ -899,6 +1048,8 @@ int fb_create(const FbModel *model, const FbFarms *farms, int n_envs, int device
        * does the same work with fewer instructions */
       h->fast_split = !h->fast_slim && h->hm.split.nwarps > 1;     /* used while the batch fits one wave (launch) */
       if (const char *ev = getenv("FARMS_B200_FAST_SPLIT")) h->fast_split = atoi(ev) != 0;
+      h->con_split = !h->fast_slim && h->hm.split.nwarps > 1 && m.X.con_ok;
+      if (const char *ev = getenv("FARMS_B200_CON_SPLIT")) h->con_split = atoi(ev) != 0;
       if (ce != cudaSuccess) { fb_destroy(h); return fail(std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(ce)); }
     }
   }
@@ -918,6 +1069,7 @@ int fb_create(const FbModel *model, const FbFarms *farms, int n_envs, int device
   bad |= alloc_arr(h, &P.flags, n); bad |= alloc_arr(h, &P.iteration, n);
   bad |= alloc_arr(h, &P.pending, n); bad |= alloc_arr(h, &P.pending_count, 2); bad |= alloc_arr(h, &P.steps_done, n);
   bad |= alloc_arr(h, &P.con_dirty, n);
+  bad |= alloc_arr(h, &h->con_split_done, (n + 15)/16);
   P.fast_scratch_stride = (long long)((n + 31) & ~(size_t)31);
   P.fast_scratch = nullptr;
   if (m.X.ok) {
@@ -1713,6 +1865,24 @@ int fb_fast_split(FbHandle *h) {
 #endif
   return h->hm.split.nwarps > 1 ? h->hm.split.nwarps : 0;
 }
+/* SPLIT variant of the constrained per-thread kernel (ground-contact batches) */
+int fb_set_con_split(FbHandle *h, int enable) {
+  if (!h) return fail("fb_set_con_split: null handle");
+  h->con_split = enable != 0;
+  return 0;
+}
+
+/* 1 when the next launch hands the fully handed-over groups to the SPLIT variant */
+int fb_con_split(FbHandle *h) {
+  if (!h || !h->fast_enabled || !h->con_thread || !h->con_split || h->fast_slim || !h->hm.m.X.con_ok) return 0;
+  if (h->hm.split.nwarps < 2) return 0;
+#ifdef FB_HOST_EMU
+  return 1;
+#else
+  return (h->P.n_envs + h->fast_block - 1)/h->fast_block <= h->con_split_capacity;
+#endif
+}
+
 /* resident SPLIT blocks per SM as the runtime computes it (0: not applicable) */
 int fb_fast_split_blocks_per_sm(FbHandle *h) {
 #ifndef FB_HOST_EMU

@@ -265,8 +265,8 @@ FB_DEV void fb_fence_proxy_async() {
 
 /* Touch the record of the body visited NEXT (one word per 64-byte line of its 288 bytes) so that the
  * indexed constant loads of the next iteration hit the constant cache: the table (8 KB for 29
- * bodies) is larger than its first level, and a lone warp waits out every miss.  -DFB_REC_PREFETCH=0
- * leaves it out; measured r2q: +0.2 .. 0.8 %, within noise, so off by default. */
+ * bodies) is larger than its first level, and a lone warp waits out every miss.  Off by default
+ * (-DFB_REC_PREFETCH=1 compiles it in): measured r2q +0.2 .. 0.8 %, within noise. */
 #ifndef FB_REC_PREFETCH
 #define FB_REC_PREFETCH 0
 #endif
@@ -382,11 +382,7 @@ FB_UNROLL
     sroot = sroot_; sflag = sflag_;
   }
   /* phase barrier of a sweep (every thread of the block, idle or not) */
-  FB_MEM void split_barrier() const {
-#ifndef FB_HOST_EMU
-    __syncthreads();
-#endif
-  }
+  FB_MEM void split_barrier() const { FB_BLOCK_BARRIER(); }
   /* row of iteration `itr` (before the ring modulus): was it last written at or before dirty_c? */
   FB_MEM int log_row_dirty(long long itr) const {
     const long long prev = itr - P.ring;
@@ -1450,9 +1446,8 @@ FB_UNROLL
    * I/O and the hand-over bookkeeping; a lane leaves the step when ANY warp saw one of its bodies at
    * a limit or inside a plane bound. */
   FB_MEM int run_split(int coop, int lane, int valid) {
-#ifndef FB_HOST_EMU
     if (role == 0 && valid) load_state(coop, lane);
-    __syncthreads();
+    FB_BLOCK_BARRIER();
     const size_t e = (size_t)env;
     const int n = P.n_steps;
     int kdone = n, dead = !valid;
@@ -1466,18 +1461,18 @@ FB_UNROLL
       const float time = (float)(P.it0 + k)*m.timestep;
       zfill = log_row_dirty(P.it0 + k + 1);
       if (role == 0) sflag[0] = 0;
-      __syncthreads();
+      FB_BLOCK_BARRIER();
       idle = dead;
       const int act = pass_poses(row_links);
       if (!dead && act) sflag[0] = 1;
-      __syncthreads();
+      FB_BLOCK_BARRIER();
       if (!dead && sflag[0]) { kdone = k; dead = 1; }
       idle = dead;
       if (role == 0 && !dead && rec[1].jtype == FB_JNT_FREE) { rt[3] = rqn[0]; rt[4] = rqn[1]; rt[5] = rqn[2]; rt[6] = rqn[3]; }
       float aroot[6] = {0.f, 0.f, 0.f, -m.grav[0], -m.grav[1], -m.grav[2]};
       const float *seqk = P.ctrl_seq ? P.ctrl_seq + ((size_t)(P.seq_pos + k)*m.nu)*P.env_pad + e : 0;
       pass_inertia(time, aroot, k == n - 1 && m.n_wc > 0, seqk);
-      __syncthreads();
+      FB_BLOCK_BARRIER();
       const int bad = pass_accel(aroot, row_joints, row_xfrc);
       if (!dead) {
         if (zfill && role == 0)
@@ -1485,7 +1480,7 @@ FB_UNROLL
         if (bad) FB_FLAG_OR(P.flags + env, FB_FLAG_NONFINITE);
       }
     }
-    __syncthreads();
+    FB_BLOCK_BARRIER();
     if (role != 0 || !valid) return n;
     if (P.ctrl_seq && kdone == n) {
       const float *last = P.ctrl_seq + ((size_t)(P.seq_pos + n - 1)*m.nu)*P.env_pad + e;
@@ -1494,10 +1489,6 @@ FB_UNROLL
     }
     store_state(P.it0 + kdone, coop, lane);
     return kdone;
-#else
-    (void)coop; (void)lane; (void)valid;
-    return 0;
-#endif
   }
 };
 

@@ -58,16 +58,80 @@ static double *fb_emu_stats = 0;
 #define FB_FFSLL(x) __ffsll((long long)(x))
 #endif
 
-/* LEAN: as in FbFast (hinge joints only, axisymmetric inertias, ...): the unused paths compiled out */
-template <int BLK, int LEAN = 0> struct FbFastCon : FbFast<BLK, 0, 0, LEAN> {
-  typedef FbFast<BLK, 0, 0, LEAN> Base;
+/* LEAN: as in FbFast (hinge joints only, axisymmetric inertias, ...): the unused paths compiled out.
+ * SPLIT: as in FbFast -- the 32 environments of a block are stepped by several warps, each owning
+ * part of the tree.  Every sweep of the constrained step is a tree sweep with the same two phases
+ * (trunk, then the subtrees behind it); a warp's limit rows and collision candidates are those of
+ * its own bodies, so its masks (hm, hany, lany) only ever hold its own rows, and the scalars of the
+ * line search (row sums, p.g, |p|^2, p'Mp, |a|^2) are summed over the warps through shared memory,
+ * in a fixed order, so that every warp of a block takes the same decisions.  The sums are taken in
+ * another order than on one warp: results agree with the single-warp kernel to rounding, not bit
+ * for bit. */
+#define FB_RED_MAX 8       /* values of one cross-warp reduction */
+template <int BLK, int LEAN = 0, int SPLIT = 0> struct FbFastCon : FbFast<BLK, 0, 0, LEAN, SPLIT> {
+  typedef FbFast<BLK, 0, 0, LEAN, SPLIT> Base;
   using Base::P; using Base::m; using Base::rec; using Base::s; using Base::env; using Base::gs;
   using Base::cs; using Base::csc; using Base::crec; using Base::hm; using Base::hany;
   using Base::rt; using Base::rootpos; using Base::rqn;
   using Base::block; using Base::gblock; using Base::slot; using Base::nblock; using Base::nroot;
   using Base::ncand;
+  using Base::role; using Base::idle; using Base::ord; using Base::ord_n; using Base::ord_bnd;
   unsigned lany[2];      /* bodies whose joint has an active limit row in some lane */
   float *csw;            /* plain-wrench accumulation slots of the branching bodies: 6 floats per slot */
+  /* SPLIT: bodies of this warp (bit b), the warps of the block, and the area the warps add their
+   * partial sums through: two buffers [warp][FB_RED_MAX][BLK] (lane-offset) used in turn, so that
+   * one barrier per reduction is enough */
+  unsigned long long own;
+  int nroles, red_par;
+  float *sred;
+  /* The active-set hash of line_eval is linear in the rows' bits, sum_k act_k C^(n-k): the plain sum
+   * of the warps' hashes would give rows at the same position of two warps (the two leg pairs of a
+   * walker) the same weight, and a foot that lands while its mirror image lifts would leave the sum
+   * unchanged.  Each warp's hash is therefore scaled by C^(1024 role) before the sum -- the hash of
+   * the warps' row lists laid end to end (a list is shorter than 1024 rows). */
+  unsigned hmul;
+  FB_MEM int owns(int b) const { return !SPLIT || (int)((own >> b) & 1ull); }
+  FB_MEM void con_split_setup(const FastSplit &sp, float *sred_) {
+    own = 0ull;
+    for (int i = 0; i < ord_n; i++) own |= 1ull << ord[i];
+    nroles = sp.nwarps;
+    sred = sred_;
+    red_par = 0;
+    unsigned c1024 = 0x9E3779B1u;
+    for (int k = 0; k < 10; k++) c1024 *= c1024;
+    hmul = 1u;
+    for (int r = 0; r < role; r++) hmul *= c1024;
+  }
+  /* f[0 .. NF) and u[0 .. NU) <- their sums over the warps of the block, added in warp order by
+   * every warp: all warps hold the same bits afterwards and take the same decisions.  Every thread
+   * of the block calls it. */
+  template <int NF, int NU> FB_MEM void rcombine(float *f, unsigned *u) {
+    if (!SPLIT) return;
+    float *buf = sred + red_par*(FB_SPLIT_MAXW*FB_RED_MAX*BLK);
+    red_par ^= 1;
+FB_UNROLL
+    for (int k = 0; k < NF; k++) buf[(role*FB_RED_MAX + k)*BLK] = f[k];
+FB_UNROLL
+    for (int k = 0; k < NU; k++) buf[(role*FB_RED_MAX + NF + k)*BLK] = fb_u2f(u[k]);
+    FB_BLOCK_BARRIER();
+FB_UNROLL
+    for (int k = 0; k < NF; k++) {
+      float t = buf[k*BLK];
+      for (int r = 1; r < nroles; r++) t += buf[(r*FB_RED_MAX + k)*BLK];
+      f[k] = t;
+    }
+FB_UNROLL
+    for (int k = 0; k < NU; k++) {
+      unsigned t = fb_f2u(buf[(NF + k)*BLK]);
+      for (int r = 1; r < nroles; r++) t += fb_f2u(buf[(r*FB_RED_MAX + NF + k)*BLK]);
+      u[k] = t;
+    }
+  }
+  FB_MEM int rany(int flag) {
+    unsigned u = flag ? 1u : 0u;
+    rcombine<0, 1>(0, &u);
+    return u != 0u;
+  }
   FB_MEM float *wslot(int i) const { return csw + 6*BLK*i; }
 
   FB_MEM FbFastCon(const FbParams &P_, const FastRec *rec_, const CandRec *crec_, float *s_, float *gs_,
@@ -78,6 +142,7 @@ template <int BLK, int LEAN = 0> struct FbFastCon : FbFast<BLK, 0, 0, LEAN> {
     csw = csc + NC_NF*P_.m.ncand*BLK;
     hm[0] = hm[1] = hany[0] = hany[1] = 0ull;
     lany[0] = lany[1] = 0u;
+    own = ~0ull; nroles = 1; red_par = 0; sred = 0; hmul = 1u;
   }
 
   FB_MEM int lane_on(int fc) const { return fb_bit128(hm, fc); }
@@ -132,6 +197,7 @@ FB_UNROLL
     lany[0] = lany[1] = 0u;
     for (int b = 1; b < nb; b++) {
       const FastRec &rc = rec[b];
+      if (!owns(b)) continue;
       if (!(rc.flags & FT_LIMITED) || rc.jtype < 0 || rc.jtype == FB_JNT_FREE) continue;
       const float *pg = gblock(b);
       float *pn = nblock(b);
@@ -166,6 +232,7 @@ FB_UNROLL
       const int c1 = m.ncand < 64*w + 64 ? m.ncand : 64*w + 64;
       for (int fc = 64*w; fc < c1; fc++) {
         const CandRec &cr_ = crec[fc];
+        if (!owns(cr_.body)) continue;
         const float *pb = s + cr_.pblk*BLK;
         const Quat q = {pb[(FB_QUAT)*BLK], pb[(FB_QUAT + 1)*BLK], pb[(FB_QUAT + 2)*BLK], pb[(FB_QUAT + 3)*BLK]};
         float R[9], t[3], n[3], o[3];
@@ -264,13 +331,19 @@ FB_UNROLL
     const int nb = m.nbody;
     float ac[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f}, lc[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
     float nx[9];      /* U[6], u, 1/d, qd of the next body to visit */
+    const int n_it = SPLIT ? ord_n : nb - 1;
     {
-      const float *pn = nblock(1);
+      const int b0 = SPLIT ? (ord_n > 0 ? ord[0] : 1) : 1;
+      const float *pn = nblock(b0);
 FB_UNROLL
       for (int k = 0; k < 8; k++) nx[k] = fb_ld_scr(pn + (NB_U + k)*BLK);
-      nx[8] = fb_ld_scr(gblock(1) + FG_QD*BLK);
+      nx[8] = fb_ld_scr(gblock(b0) + FG_QD*BLK);
     }
-    for (int b = 1; b < nb; b++) {
+    for (int i = 0; i <= n_it; i++) {
+      if (SPLIT && i == ord_bnd) this->split_barrier();      /* the trunk's accelerations are known */
+      if (i == n_it) break;
+      const int b = SPLIT ? ord[i] : i + 1;
+      const int bn = SPLIT ? (i + 1 < n_it ? ord[i + 1] : 0) : (i + 2 < nb ? i + 2 : 0);
       const FastRec &rc = rec[b];
       const float *pb = block(b);
       float *pn = nblock(b);
@@ -278,11 +351,11 @@ FB_UNROLL
       float cx[9];
 FB_UNROLL
       for (int k = 0; k < 9; k++) cx[k] = nx[k];
-      if (b + 1 < nb) {
-        const float *pn1 = nblock(b + 1);
+      if (bn) {
+        const float *pn1 = nblock(bn);
 FB_UNROLL
         for (int k = 0; k < 8; k++) nx[k] = fb_ld_scr(pn1 + (NB_U + k)*BLK);
-        nx[8] = fb_ld_scr(gblock(b + 1) + FG_QD*BLK);
+        nx[8] = fb_ld_scr(gblock(bn) + FG_QD*BLK);
       }
       const Quat q = {pb[(FB_QUAT)*BLK], pb[(FB_QUAT + 1)*BLK], pb[(FB_QUAT + 2)*BLK], pb[(FB_QUAT + 3)*BLK]};
       float R[9], v[6], a[6], al[6];
@@ -379,8 +452,16 @@ FB_UNROLL
 FB_UNROLL
     for (int k = 0; k < 9; k++) C.H[k] = 0.f;
     float nx[2];      /* previous gradient entry, a of the next joint to visit */
-    nx[0] = fb_ld_scr(nblock(nb - 1) + NB_MD*BLK); nx[1] = fb_ld_scr(nblock(nb - 1) + NB_A*BLK);
-    for (int b = nb - 1; b >= 1; b--) {
+    const int n_it = SPLIT ? ord_n : nb - 1;
+    {
+      const int b0 = SPLIT ? (ord_n > 0 ? ord[ord_n - 1] : 1) : nb - 1;
+      nx[0] = fb_ld_scr(nblock(b0) + NB_MD*BLK); nx[1] = fb_ld_scr(nblock(b0) + NB_A*BLK);
+    }
+    for (int i = n_it; i >= 0; i--) {
+      if (SPLIT && i == ord_bnd) this->split_barrier();      /* the subtrees have handed over: the trunk goes on */
+      if (i == 0) break;
+      const int b = SPLIT ? ord[i - 1] : i;
+      const int bn = SPLIT ? (i >= 2 ? ord[i - 2] : 0) : (i > 1 ? i - 1 : 0);
       const FastRec &rc = rec[b];
       FB_PIN_I(rc.jtype); FB_PIN_I(rc.flags); FB_PIN_I(rc.pblk); FB_PIN_I(rc.parent); FB_PIN_I(rc.bc0); FB_PIN_I(rc.bc1);
       FB_PIN_F(rc.mass); FB_PIN_F(rc.armature);
@@ -392,7 +473,7 @@ FB_UNROLL
       float *pn = nblock(b);
       const int jtype = rc.jtype, flags = rc.flags;
       const float md = nx[0], aj = nx[1];
-      if (b > 1) { nx[0] = fb_ld_scr(pn - NB_NF*BLK + NB_MD*BLK); nx[1] = fb_ld_scr(pn - NB_NF*BLK + NB_A*BLK); }
+      if (bn) { nx[0] = fb_ld_scr(nblock(bn) + NB_MD*BLK); nx[1] = fb_ld_scr(nblock(bn) + NB_A*BLK); }
       float lim4[4] = {0.f, 0.f, 0.f, 0.f}, dtau = 0.f;
       const int limited = (flags & FT_LIMITED) && lim_on(b);
       if (limited) {
@@ -584,13 +665,18 @@ FB_UNROLL
     float lc[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
     float g0 = 0.f, pp = 0.f;
     float nx[9];      /* U[6], 1/d, u, gradient entry of the next body to visit */
+    const int n_it = SPLIT ? ord_n : nb - 1;
     {
-      const float *pn = nblock(1);
+      const float *pn = nblock(SPLIT ? (ord_n > 0 ? ord[0] : 1) : 1);
 FB_UNROLL
       for (int k = 0; k < 8; k++) nx[k] = fb_ld_scr(pn + (NB_U + k)*BLK);
       nx[8] = fb_ld_scr(pn + NB_MD*BLK);
     }
-    for (int b = 1; b < nb; b++) {
+    for (int i = 0; i <= n_it; i++) {
+      if (SPLIT && i == ord_bnd) this->split_barrier();      /* the trunk's p is known */
+      if (i == n_it) break;
+      const int b = SPLIT ? ord[i] : i + 1;
+      const int bn = SPLIT ? (i + 1 < n_it ? ord[i + 1] : 0) : (i + 2 < nb ? i + 2 : 0);
       const FastRec &rc = rec[b];
       FB_PIN_I(rc.jtype); FB_PIN_I(rc.flags); FB_PIN_I(rc.pblk); FB_PIN_I(rc.parent); FB_PIN_I(rc.bc0); FB_PIN_I(rc.bc1);
 FB_UNROLL
@@ -601,8 +687,8 @@ FB_UNROLL
       float cx[9];
 FB_UNROLL
       for (int k = 0; k < 9; k++) cx[k] = nx[k];
-      if (b + 1 < nb) {
-        const float *pn1 = pn + NB_NF*BLK;
+      if (bn) {
+        const float *pn1 = nblock(bn);
 FB_UNROLL
         for (int k = 0; k < 8; k++) nx[k] = fb_ld_scr(pn1 + (NB_U + k)*BLK);
         nx[8] = fb_ld_scr(pn1 + NB_MD*BLK);
@@ -681,13 +767,18 @@ FB_UNROLL
     float fc6[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
     float pMp = 0.f;
     float nx[7];      /* pure acceleration[6], p of the next body to visit */
+    const int n_it = SPLIT ? ord_n : nb - 1;
     {
-      const float *pn = nblock(nb - 1);
+      const float *pn = nblock(SPLIT ? (ord_n > 0 ? ord[ord_n - 1] : 1) : nb - 1);
 FB_UNROLL
       for (int k = 0; k < 6; k++) nx[k] = fb_ld_scr(pn + (NB_AP + k)*BLK);
       nx[6] = fb_ld_scr(pn + NB_P*BLK);
     }
-    for (int b = nb - 1; b >= 1; b--) {
+    for (int i = n_it; i >= 0; i--) {
+      if (SPLIT && i == ord_bnd) this->split_barrier();
+      if (i == 0) break;
+      const int b = SPLIT ? ord[i - 1] : i;
+      const int bn = SPLIT ? (i >= 2 ? ord[i - 2] : 0) : (i > 1 ? i - 1 : 0);
       const FastRec &rc = rec[b];
       FB_PIN_I(rc.jtype); FB_PIN_I(rc.flags); FB_PIN_I(rc.pblk); FB_PIN_I(rc.parent);
       FB_PIN_F(rc.mass); FB_PIN_F(rc.armature);
@@ -702,8 +793,8 @@ FB_UNROLL
 FB_UNROLL
       for (int k = 0; k < 6; k++) al[k] = nx[k];
       const float pj = nx[6];
-      if (b > 1) {
-        const float *pn1 = pn - NB_NF*BLK;
+      if (bn) {
+        const float *pn1 = nblock(bn);
 FB_UNROLL
         for (int k = 0; k < 6; k++) nx[k] = fb_ld_scr(pn1 + (NB_AP + k)*BLK);
         nx[6] = fb_ld_scr(pn1 + NB_P*BLK);
@@ -847,7 +938,7 @@ FB_UNROLL
       for (int i = 0; i < 4; i++) {
         const int b = b0 + i;
         av[i] = 0.f; pv[i] = 0.f;
-        if (b < nb) {
+        if (b < nb && owns(b)) {
           const float *pn = nblock(b);
           av[i] = fb_ld_scr(pn + NB_A*BLK);
           if (!first) pv[i] = fb_ld_scr(pn + NB_P*BLK);
@@ -856,7 +947,7 @@ FB_UNROLL
 FB_UNROLL
       for (int i = 0; i < 4; i++) {
         const int b = b0 + i;
-        if (b >= nb) continue;
+        if (b >= nb || !owns(b)) continue;
         const FastRec &rc = rec[b];
         float *pn = nblock(b);
         if (rc.jtype == FB_JNT_FREE) {
@@ -919,7 +1010,7 @@ FB_UNROLL
   }
 
   /* ---- primal Newton with exact line search, matrix-free */
-  FB_MEM void solve(int mine) {
+  FB_MEM void solve(int mine) {      /* SPLIT: `mine` as combined over the warps */
     int done = !mine;
     const int maxit = m.solver_iterations < 50 ? m.solver_iterations : 50;
     int it = 0;
@@ -938,8 +1029,17 @@ FB_UNROLL
       float S2[2], Q2[2];
       unsigned h2[2];
       line_eval<2>(a01, S2, Q2, h2);
+      if (SPLIT) {
+        float f6[6] = {pg, pp, S2[0], S2[1], Q2[0], Q2[1]};
+        h2[0] *= hmul; h2[1] *= hmul;
+        rcombine<6, 2>(f6, h2);
+        pg = f6[0]; pp = f6[1]; S2[0] = f6[2]; S2[1] = f6[3]; Q2[0] = f6[4]; Q2[1] = f6[5];
+      }
       float g0 = pg - S2[0], pMp = fmaxf(-pg - Q2[0], 1e-7f*fabsf(pg));
-      if (it == 0) { g0 = 0.f; pMp = newton_c(); }
+      if (it == 0) {
+        g0 = 0.f; pMp = newton_c();
+        if (SPLIT) rcombine<1, 0>(&pMp, 0);
+      }
       /* zero of the piecewise-linear derivative by safeguarded Newton steps */
       int ls_done = done || !(pg < 0.f), nls = 1, exact = 0;
       float a = ls_done ? 0.f : 1.f, lo = 0.f, hi = 3.0e38f;
@@ -970,10 +1070,17 @@ FB_UNROLL
         nls++;
         float S1, Q1;
         line_eval<1>(&a, &S1, &Q1, &hash);
+        if (SPLIT) {
+          float f2[2] = {S1, Q1};
+          hash *= hmul;
+          rcombine<2, 1>(f2, &hash);
+          S1 = f2[0]; Q1 = f2[1];
+        }
         gv = g0 + a*pMp + S1; sl = pMp + Q1;
       }
       if (done) a = 0.f;
-      const float a2 = newton_update(a, it == 0 ? 2 : 0);
+      float a2 = newton_update(a, it == 0 ? 2 : 0);
+      if (SPLIT) rcombine<1, 0>(&a2, 0);
       keep = it == 0 ? a : 1.f - a;
       /* Stop on a relative step below 3e-5 (|alpha p|^2 <= 1e-9 |a|^2).  Convergence is quadratic
        * once the active set is right -- measured relative steps 6e1, 4e-1, 1e-2, then the fp32
@@ -987,11 +1094,11 @@ FB_UNROLL
       if (!(a2 < 3.0e38f) || !(ratio < 3.0e38f)) done = 1;
       prev_ratio = ratio;
 #ifdef FB_HOST_EMU
-      if (fb_emu_stats) { fb_emu_stats[0] += 1; fb_emu_stats[1] += nls; }
+      if (fb_emu_stats && role == 0) { fb_emu_stats[0] += 1; fb_emu_stats[1] += nls; }
 #endif
     }
 #ifdef FB_HOST_EMU
-    if (fb_emu_stats) fb_emu_stats[2] += 1;
+    if (fb_emu_stats && role == 0) fb_emu_stats[2] += 1;
 #endif
     if (!done) FB_FLAG_OR(P.flags + env, FB_FLAG_SOLVER);
   }
@@ -1002,7 +1109,7 @@ FB_UNROLL
     const int nb = m.nbody;
     for (int b = 1; b < nb; b++) {
       const FastRec &rc = rec[b];
-      if (rc.jtype < 0 || rc.jtype == FB_JNT_FREE) continue;
+      if (!owns(b) || rc.jtype < 0 || rc.jtype == FB_JNT_FREE) continue;
       float *pn = nblock(b);
       float tauc = 0.f, lf = 0.f;
       if ((rc.flags & FT_LIMITED) && lim_on(b)) {
@@ -1047,9 +1154,21 @@ FB_UNROLL
   }
 
   /* ---- contacts rows: sensors.pyx:140-190 over the active candidates */
-  FB_MEM void write_contacts(float *row_contacts) const {
+  FB_MEM void write_contacts(float *row_contacts) {
     const long long ev = P.env_pad*FB_VEC_CONTACTS;
-    for (int sx = 0; sx < m.n_contacts; sx++) {
+    /* SPLIT: a sensor may sum candidates of several warps' bodies.  The masks are disjoint over the
+     * warps: their sums are the masks of the whole tree (and the barrier of the reduction makes the
+     * other warps' forces visible); the sensors are then dealt over the warps. */
+    unsigned long long keep_m[4] = {hm[0], hm[1], hany[0], hany[1]};
+    if (SPLIT) {
+      unsigned u8[8];
+FB_UNROLL
+      for (int k = 0; k < 4; k++) { u8[2*k] = (unsigned)keep_m[k]; u8[2*k + 1] = (unsigned)(keep_m[k] >> 32); }
+      rcombine<0, 8>(0, u8);
+      hm[0] = u8[0] | ((unsigned long long)u8[1] << 32); hm[1] = u8[2] | ((unsigned long long)u8[3] << 32);
+      hany[0] = u8[4] | ((unsigned long long)u8[5] << 32); hany[1] = u8[6] | ((unsigned long long)u8[7] << 32);
+    }
+    for (int sx = SPLIT ? role : 0; sx < m.n_contacts; sx += SPLIT ? nroles : 1) {
       float acc[12], nsum = 0.f;
 FB_UNROLL
       for (int k = 0; k < 12; k++) acc[k] = 0.f;
@@ -1081,6 +1200,7 @@ FB_UNROLL
       fb_st4(row + ev, acc[4]*in, acc[5]*in, acc[6]*in, acc[7]*in);
       fb_st4(row + 2*ev, acc[8]*in, acc[9]*ip, acc[10]*ip, acc[11]*ip);
     }
+    if (SPLIT) { hm[0] = keep_m[0]; hm[1] = keep_m[1]; hany[0] = keep_m[2]; hany[1] = keep_m[3]; }
   }
 
   /* Steps k0 .. n_steps-1 of the launch, constraints included. */
@@ -1123,6 +1243,65 @@ FB_UNROLL
       }
       if (bad) FB_FLAG_OR(P.flags + env, FB_FLAG_NONFINITE);
     }
+    if (P.ctrl_seq) {
+      const float *last = P.ctrl_seq + ((size_t)(P.seq_pos + n - 1)*m.nu)*P.env_pad + e;
+      for (int a = 0; a < m.nu; a++)
+        if (MI(ft_actwc, a) < 0) P.ctrl[e*m.nu + a] = last[(long long)a*P.env_pad];
+    }
+    P.con_dirty[env] = this->dirty_c;
+    this->store_state(P.it0 + n, coop, lane);
+  }
+
+  /* SPLIT: run_con from step 0 for a block whose warps step the SAME environments, each its own
+   * bodies (split_setup + con_split_setup).  Warp 0 owns the root state and the state I/O; every
+   * thread of the block takes every barrier. */
+  FB_MEM void run_con_split(int coop, int lane) {
+    if (role == 0) this->load_state(coop, lane);
+    FB_BLOCK_BARRIER();
+    const size_t e = (size_t)env;
+    const int n = P.n_steps;
+    long long row = P.it0 % P.ring;
+    idle = 0;
+    for (int k = 0; k < n; k++) {
+      row = row + 1 == P.ring ? 0 : row + 1;
+      float *row_links = fb_log_row(P.log_links, row, m.n_links*20, P.env_pad, FB_VEC_LINKS, e);
+      float *row_joints = fb_log_row(P.log_joints, row, m.n_joints*m.joint_cols, P.env_pad, FB_VEC_JOINTS, e);
+      float *row_contacts = fb_log_row(P.log_contacts, row, m.n_contacts*12, P.env_pad, FB_VEC_CONTACTS, e);
+      float *row_xfrc = fb_log_row(P.log_xfrc, row, m.n_xfrc*6, P.env_pad, FB_VEC_XFRC, e);
+      const float time = (float)(P.it0 + k)*m.timestep;
+      const int maybe = rany(this->pass_poses(row_links));
+      if (role == 0 && rec[1].jtype == FB_JNT_FREE) { rt[3] = rqn[0]; rt[4] = rqn[1]; rt[5] = rqn[2]; rt[6] = rqn[3]; }
+      float aroot[6] = {0.f, 0.f, 0.f, -m.grav[0], -m.grav[1], -m.grav[2]};
+      const float *seqk = P.ctrl_seq ? P.ctrl_seq + ((size_t)(P.seq_pos + k)*m.nu)*P.env_pad + e : 0;
+      const int store_ctrl = k == n - 1 && m.n_wc > 0;
+      int mine = 0, bad;
+      if (FB_ANY(maybe)) mine = rany(detect());
+      this->zfill = this->log_row_dirty(P.it0 + k + 1);
+      if (FB_ANY(mine)) {
+        this->dirty_c = P.it0 + k + 1;
+        this->template pass_inertia_m<1>(time, aroot, 0, seqk);
+        FB_BLOCK_BARRIER();
+        smooth_accel(aroot);
+        solve(mine);
+        final_forces();
+FB_UNROLL
+        for (int i = 0; i < 3; i++) { aroot[i] = 0.f; aroot[3 + i] = -m.grav[i]; }
+        FB_BLOCK_BARRIER();
+        this->template pass_inertia_m<2>(time, aroot, store_ctrl, seqk);
+        FB_BLOCK_BARRIER();
+        bad = this->template pass_accel_m<1>(aroot, row_joints, row_xfrc);
+        write_contacts(row_contacts);
+      } else {
+        this->template pass_inertia_m<0>(time, aroot, store_ctrl, seqk);
+        FB_BLOCK_BARRIER();
+        bad = this->template pass_accel_m<0>(aroot, row_joints, row_xfrc);
+        if (this->zfill && role == 0)
+          for (int i = 0; i < m.n_contacts*3; i++) fb_st4(row_contacts + i*(P.env_pad*FB_VEC_CONTACTS), 0.f, 0.f, 0.f, 0.f);
+      }
+      if (bad) FB_FLAG_OR(P.flags + env, FB_FLAG_NONFINITE);
+      FB_BLOCK_BARRIER();
+    }
+    if (role != 0) return;
     if (P.ctrl_seq) {
       const float *last = P.ctrl_seq + ((size_t)(P.seq_pos + n - 1)*m.nu)*P.env_pad + e;
       for (int a = 0; a < m.nu; a++)

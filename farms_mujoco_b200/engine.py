@@ -77,6 +77,8 @@ ABI_SYMBOLS = {
     'fb_set_fast_split': (ct.c_int, [_H, ct.c_int]),
     'fb_fast_split': (ct.c_int, [_H]),
     'fb_fast_split_blocks_per_sm': (ct.c_int, [_H]),
+    'fb_set_con_split': (ct.c_int, [_H, ct.c_int]),
+    'fb_con_split': (ct.c_int, [_H]),
     'fb_fast_split_schedule': (ct.c_int, [_H, ct.POINTER(ct.c_int32), ct.POINTER(ct.c_int32), ct.POINTER(ct.c_uint8)]),
     'fb_set_fast_lean': (ct.c_int, [_H, ct.c_int]),
     'fb_fast_lean': (ct.c_int, [_H]),
@@ -570,6 +572,15 @@ class BatchedPhysics:
     def fast_split(self):
         """Warps per 32 environments when ``step`` launches the SPLIT variant, else 0."""
         return int(self.lib.fb_fast_split(self._handle))
+
+    def set_con_split(self, enable):
+        """Use or not the SPLIT variant of the constrained per-thread kernel (fb_set_con_split)."""
+        self._check(self.lib.fb_set_con_split(self._handle, int(bool(enable))))
+
+    @property
+    def con_split(self):
+        """True when the next launch hands fully handed-over groups to the SPLIT constrained kernel."""
+        return bool(self.lib.fb_con_split(self._handle))
 
     def fast_split_schedule(self):
         """The tree split: list (one entry per warp) of (phase A bodies, phase B bodies)."""

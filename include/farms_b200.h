@@ -340,6 +340,17 @@ int fb_set_fast_split(FbHandle *h, int enable);
 int fb_fast_split(FbHandle *h);
 int fb_fast_split_schedule(FbHandle *h, int32_t *n, int32_t *boundary, uint8_t *order);
 int fb_fast_split_blocks_per_sm(FbHandle *h);   /* resident SPLIT blocks per SM (occupancy API), 0 if n/a */
+/* SPLIT variant of the CONSTRAINED per-thread kernel (ground-contact batches): the same tree split
+ * applied to every sweep of the constrained step (smooth accelerations, the Newton sweeps, the
+ * force sweeps); each warp holds the limit rows and collision candidates of its own bodies and the
+ * line-search scalars are summed over the warps in a fixed order.  It takes the groups of
+ * environments that were ALL handed over before their first step of the launch (a walking batch:
+ * every group, every launch) while all its blocks are resident at once; every other group is
+ * stepped by the single-warp kernel as before.  Results agree with the single-warp kernel to
+ * rounding (the sums are taken in another order), not bit for bit.  fb_con_split = 1 when the
+ * next launch uses it. */
+int fb_set_con_split(FbHandle *h, int enable);
+int fb_con_split(FbHandle *h);
 int fb_fast_slim(FbHandle *h);
 int fb_last_pending(FbHandle *h, int *count);
 

@@ -3,7 +3,7 @@ environment-per-thread kernel first, team kernel on what it hands over."""
 
 import numpy as np
 
-from conftest import make_case, oracle_rollout, scaled_error, parity_errors, log_error, state_errors
+from conftest import log_errors, make_case, oracle_rollout, scaled_error, parity_errors, log_error, state_errors
 
 
 def compare_with_oracle(spec, model, physics, qpos0, qvel0, ctrl, envs, n_steps, tol, tol_contacts=None):
@@ -438,3 +438,46 @@ def check_split_variant_is_bit_identical(library, n_envs=75):
         assert np.array_equal(outs[0][2], outs[1][2]), name
         for kind in ('links', 'joints', 'contacts', 'xfrc'):
             assert np.array_equal(outs[0][3][kind], outs[1][3][kind]), (name, kind)
+
+
+def check_con_split_variant(library, n_envs=75, n_steps=(6, 5), names=('salamander', 'centipede'), tol=None):
+    """SPLIT variant of the constrained per-thread kernel (several warps per group of environments,
+    each its own bodies; fb_fastc_split_kernel) against the single-warp kernel on walking batches:
+    every environment is handed over before its first step, so every group is taken by the SPLIT
+    variant (the last one is partial).  The line-search sums are added over the warps in another
+    order than on one warp: agreement to rounding (the tolerance of the LEAN check on the salamander;
+    the centipede, whose fp32 floor against the oracle is 3e-5, to 1e-4), same flags."""
+    from farms_mujoco_b200.engine import BatchedPhysics
+    tol = tol or {'salamander': LEAN_TOL, 'centipede': 1e-4}
+    for name in names:
+        spec, model, qpos0, qvel0, ctrl = make_case(name, n_envs)
+        outs = []
+        for split in (False, True):
+            physics = BatchedPhysics.from_spec(spec, n_envs, buffer_size=sum(n_steps) + 1, library=library)
+            physics.set_con_split(split)
+            assert physics.con_split == split, name
+            physics.reset(qpos0, qvel0)
+            physics.set_ctrl(ctrl)
+            pending = []
+            for n in n_steps:
+                physics.step(n)
+                pending.append(physics.last_pending)
+            outs.append((physics.qpos, physics.qvel, physics.xfrc_applied, physics.log_arrays(), pending, physics.flags))
+        assert outs[0][4] == outs[1][4] == [n_envs]*len(n_steps), (name, outs[0][4], outs[1][4])
+        assert np.array_equal(outs[0][5], outs[1][5]), name
+        a, b = outs
+        worst = {}
+        for env in range(n_envs):
+            errs = state_errors(a[0][env], a[1][env], b[0][env], b[1][env])
+            for kind in ('links', 'joints', 'contacts', 'xfrc'):
+                for group, val in log_errors(kind, a[3][kind][env], b[3][kind][env]).items():
+                    errs[kind + '.' + group] = val
+            for key, val in errs.items():
+                worst[key] = max(worst.get(key, 0.0), val)
+        for key, val in worst.items():
+            # constraint forces (contacts rows, joint limit force): the solver may stop an iteration
+            # apart in the two variants, as in the LEAN check
+            force = key.startswith('contacts.') or key == 'joints.limit_force'
+            assert val < (5e-4 if force else tol[name]), (name, key, worst)
+        # the contacts rows are not all zero: the comparison above is about real forces
+        assert np.abs(a[3]['contacts']).max() > 0, name

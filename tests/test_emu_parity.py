@@ -390,3 +390,17 @@ def test_device_cpg_matches_host_controller(emu_library):
 def test_lean_variant(emu_library):
     import fastpath_cases
     fastpath_cases.check_lean_variant(emu_library, slims=(0, 1))
+
+
+def test_split_variant_is_bit_identical(emu_library):
+    """SPLIT variant of the unconstrained kernel: the warps of a block emulated by host threads that
+    meet at the kernel's barriers (one lane each) -- the schedule, the phase barriers and the
+    hand-over protocol are the device's."""
+    import fastpath_cases
+    fastpath_cases.check_split_variant_is_bit_identical(emu_library, n_envs=9)
+
+
+def test_con_split_variant(emu_library):
+    """SPLIT variant of the constrained kernel under the same emulation (cross-warp sums included)."""
+    import fastpath_cases
+    fastpath_cases.check_con_split_variant(emu_library, n_envs=75, n_steps=(3, 2))

@@ -673,3 +673,11 @@ def test_split_variant_is_bit_identical(cuda_library, monkeypatch):
     import fastpath_cases
     monkeypatch.setenv('FARMS_B200_FAST_BLOCK', '32')
     fastpath_cases.check_split_variant_is_bit_identical(cuda_library)
+
+
+@pytest.mark.parametrize('block', ['16', '32'])
+def test_con_split_variant(cuda_library, monkeypatch, block):
+    """SPLIT variant of the constrained kernel (fb_fastc_split_kernel), 16 and 32 environments per group."""
+    import fastpath_cases
+    monkeypatch.setenv('FARMS_B200_FAST_BLOCK', block)
+    fastpath_cases.check_con_split_variant(cuda_library)
