@@ -347,6 +347,7 @@ struct FbHandle {
   long long split_capacity;         /* blocks of the SPLIT variant the device holds at once (0: not applicable) */
   int con_split;                    /* 1: ground-contact batches run the SPLIT variant of the constrained kernel */
   long long con_split_capacity;     /* blocks of it the device holds at once, at the current environments per warp */
+  long long con_single_capacity;    /* ... and blocks (warps) of the single-warp constrained kernel */
   int *con_split_done;              /* device: FbParams::con_split_done */
   bool fast_block_auto;             /* 16 environments per warp chosen by the heuristic ... */
   int block_review;                 /* ... and reviewed after the first launch of an episode */
@@ -515,6 +516,8 @@ static int upload_model(FbHandle *h) {
 #ifndef FB_HOST_EMU
 static int fb_set_fast_block(FbHandle *h, int blk);
 static long long fb_con_split_blocks(FbHandle *h, int blk, cudaError_t *ce);
+static long long fb_con_cost(long long n_envs, int blk, long long capacity, int split);
+static bool fb_con_split_pays(FbHandle *h);
 #endif
 
 /* capacity of the device control sequence ([n_steps][nu][env_pad] + the upload staging) */
@@ -708,7 +711,7 @@ static int launch(FbHandle *h, int mode, int n_steps, int want_derived) {
     if (con_thread) {
       const bool clean = h->fast_lean && P.m.X.lean && !P.ctrl_seq;
       P.con_split_done = nullptr;
-      if (h->con_split && P.use_pending && !h->fast_slim && h->hm.split.nwarps > 1 && fblocks <= h->con_split_capacity) {
+      if (h->con_split && P.use_pending && !h->fast_slim && h->hm.split.nwarps > 1 && fb_con_split_pays(h)) {
         /* small ground-contact batch: the tree of every group split over several warps */
         P.con_split_done = h->con_split_done;
         h->csplitQ->P = P;
@@ -762,9 +765,12 @@ static int launch(FbHandle *h, int mode, int n_steps, int want_derived) {
     if (want == 16 && con_thread && h->con_split && h->hm.split.nwarps > 1) {
       /* with the constrained SPLIT variant a group is several warps: 16 per group pays only while
        * every group has an SM to itself (r2x, SALAMANDER ground: 1,024 envs 3.47e6 against 3.31e6
-       * env-steps/s with 32; 4,096 envs 1.09e7 against 1.29e7) */
+       * env-steps/s with 32; 4,096 envs 1.09e7 against 1.29e7); beyond that, whichever group size
+       * needs fewer waves */
       cudaError_t ce = cudaSuccess;
-      if ((P.n_envs + 15)/16 > h->sms && (P.n_envs + 31)/32 <= fb_con_split_blocks(h, 32, &ce)) want = 32;
+      const long long c16 = fb_con_cost(P.n_envs, 16, fb_con_split_blocks(h, 16, &ce), 1);
+      const long long c32 = fb_con_cost(P.n_envs, 32, fb_con_split_blocks(h, 32, &ce), 1);
+      if (c32 > 0 && (c16 == 0 || c32 < c16 || (c32 == c16 && (P.n_envs + 15)/16 > h->sms))) want = 32;
     }
     if (want != h->fast_block && (size_t)P.m.X.n_float*sizeof(float)*want <= (size_t)h->max_smem && fb_set_fast_block(h, want)) return -1;
   }
@@ -789,6 +795,39 @@ static long long fb_con_split_blocks(FbHandle *h, int blk, cudaError_t *ce) {
     if (nb < per_sm) per_sm = nb;
   }
   return *ce == cudaSuccess ? (long long)per_sm*h->sms : 0;
+}
+
+/* blocks (= warps) of the single-warp constrained kernel the device holds at once */
+static long long fb_con_single_blocks(FbHandle *h, int blk, cudaError_t *ce) {
+  const size_t sbytes = (size_t)h->hm.m.X.n_float*blk*sizeof(float);
+  if (!h->hm.m.X.con_ok || sbytes > (size_t)h->max_smem) return 0;
+  int per_sm = 1 << 30;
+  for (int lean = 0; lean < 2 && *ce == cudaSuccess; lean++) {
+    const void *k = blk == 16 ? (lean ? (const void *)fb_fastc_kernel<16, 1> : (const void *)fb_fastc_kernel<16, 0>)
+                              : (lean ? (const void *)fb_fastc_kernel<32, 1> : (const void *)fb_fastc_kernel<32, 0>);
+    *ce = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sbytes);
+    if (*ce == cudaSuccess) *ce = cudaFuncSetAttribute(k, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    int nb = 0;
+    if (*ce == cudaSuccess) *ce = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k, blk, sbytes);
+    if (nb < per_sm) per_sm = nb;
+  }
+  return *ce == cudaSuccess ? (long long)per_sm*h->sms : 0;
+}
+
+/* A ground-contact launch is as long as one group's step sequence times the number of waves its
+ * blocks take: the SPLIT variant shortens the sequence (x FB_CSPLIT_GAIN, measured r2y: 1.7 .. 2.0
+ * faster per wave) and holds fewer groups per wave.  Cost of stepping n_envs environments in
+ * groups of blk, in units of a single-warp wave x 100; 0 = not available. */
+#define FB_CSPLIT_GAIN 55
+static long long fb_con_cost(long long n_envs, int blk, long long capacity, int split) {
+  if (capacity <= 0) return 0;
+  const long long groups = (n_envs + blk - 1)/blk, waves = (groups + capacity - 1)/capacity;
+  return waves*(split ? FB_CSPLIT_GAIN : 100);
+}
+static bool fb_con_split_pays(FbHandle *h) {
+  const long long cs = fb_con_cost(h->P.n_envs, h->fast_block, h->con_split_capacity, 1);
+  const long long c1 = fb_con_cost(h->P.n_envs, h->fast_block, h->con_single_capacity, 0);
+  return cs > 0 && (c1 == 0 || cs < c1);
 }
 
 /* environments per warp of the per-thread kernels (regular layout): shared-memory attributes */
@@ -821,6 +860,7 @@ static int fb_set_fast_block(FbHandle *h, int blk) {
     if (ce == cudaSuccess) h->split_capacity = (long long)per_sm*h->sms;
   }
   if (ce == cudaSuccess) h->con_split_capacity = fb_con_split_blocks(h, blk, &ce);
+  if (ce == cudaSuccess) h->con_single_capacity = fb_con_single_blocks(h, blk, &ce);
   return ce == cudaSuccess ? 0 : fail(std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(ce));
 }
 
@@ -930,7 +970,7 @@ int fb_create(const FbModel *model, const FbFarms *farms, int n_envs, int device
   if (const char *ev = getenv("FARMS_B200_CON_THREAD")) h->con_thread = atoi(ev) != 0;
   h->fast_slim = 0; h->fast_slim_smem_bytes = 0; h->fast_wpb = 1;
   h->fast_lean = 1; h->fast_block_auto = false; h->block_review = 0; h->max_smem = 0; h->fast_split = 0;
-  h->split_capacity = 0; h->con_split = 0; h->con_split_capacity = 0; h->con_split_done = nullptr;
+  h->split_capacity = 0; h->con_split = 0; h->con_split_capacity = 0; h->con_single_capacity = 0; h->con_split_done = nullptr;
   if (const char *ev = getenv("FARMS_B200_FAST_LEAN")) h->fast_lean = atoi(ev) != 0;
   if (const char *ev = getenv("FARMS_B200_FAST_SLIM")) h->fast_slim = atoi(ev) != 0;
 #ifndef FB_HOST_EMU
@@ -1879,7 +1919,7 @@ int fb_con_split(FbHandle *h) {
 #ifdef FB_HOST_EMU
   return 1;
 #else
-  return (h->P.n_envs + h->fast_block - 1)/h->fast_block <= h->con_split_capacity;
+  return fb_con_split_pays(h);
 #endif
 }
 

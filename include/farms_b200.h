@@ -345,8 +345,9 @@ int fb_fast_split_blocks_per_sm(FbHandle *h);   /* resident SPLIT blocks per SM 
  * force sweeps); each warp holds the limit rows and collision candidates of its own bodies and the
  * line-search scalars are summed over the warps in a fixed order.  It takes the groups of
  * environments that were ALL handed over before their first step of the launch (a walking batch:
- * every group, every launch) while all its blocks are resident at once; every other group is
- * stepped by the single-warp kernel as before.  Results agree with the single-warp kernel to
+ * every group, every launch) whenever that needs less time by the engine's estimate -- waves of
+ * resident blocks x the measured gain per wave; every other group is stepped by the single-warp
+ * kernel as before.  Results agree with the single-warp kernel to
  * rounding (the sums are taken in another order), not bit for bit.  fb_con_split = 1 when the
  * next launch uses it. */
 int fb_set_con_split(FbHandle *h, int enable);

@@ -210,6 +210,9 @@ def test_slim_layout_is_bit_identical(cuda_library, name, monkeypatch):
         # the general variant: one source for every layout, hence the same bits (the LEAN variants
         # are separate compilations that agree to a few ulp, test_lean_variant)
         physics.set_fast_lean(False)
+        # ... and one constrained kernel for the hand-overs (its SPLIT variant only exists beside the
+        # regular layout and agrees with the single-warp kernel to rounding, test_con_split_variant)
+        physics.set_con_split(False)
         physics.reset(qpos0, qvel0)
         physics.set_ctrl(ctrl)
         physics.step(5)
@@ -416,6 +419,9 @@ def test_lanes_are_independent(cuda_library):
     outs = {}
     for key, q in (('ground', qpos0), ('air', high), ('mixed', mixed)):
         physics = BatchedPhysics.from_spec(spec, 64, buffer_size=9, library=cuda_library)
+        # the single-warp constrained kernel in all three batches: the all-ground one would otherwise
+        # run its SPLIT variant, which agrees to rounding only (test_con_split_variant)
+        physics.set_con_split(False)
         physics.reset(q, qvel0)
         physics.set_ctrl(ctrl)
         physics.step(8)

@@ -14,7 +14,7 @@ try:
 except Exception as e:
     print('$1 $2 con_split=$3', 'FAILED', e)" >> $out
 }
-for cfg in "salamander 512" "salamander 2048" "salamander 4096" "salamander 8192" "centipede 1024" "centipede 4096" "centipede 8192"; do
-  for sp in 0 1; do run $cfg $sp; done
+for cfg in ${CONSPLIT_CFGS:-salamander:512 salamander:2048 salamander:4096 salamander:8192 centipede:1024 centipede:4096 centipede:8192}; do
+  for sp in 0 1; do run ${cfg%%:*} ${cfg##*:} $sp; done
 done
 cat $out
