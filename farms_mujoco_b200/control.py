@@ -91,11 +91,14 @@ class CPGController(AnimatController):
     joint is ``offset + gain (r_a (1 + cos theta_a) - r_b (1 + cos theta_b))`` (``osc_b = -1``:
     ``offset + gain r_a cos theta_a``), a position target or a torque in SI units.
     ``couplings``: list of ``(from_j, to_i, w_ij, phi_ij)``.  State arrays are ``[n_envs, n_osc]``.
+    ``springs``: list of ``(joint, osc_a, osc_b, gain, offset)``: spring references of passive
+    joints driven by the same expression (``springrefs``; the reference applies them together with the
+    torque commands, task.py:338-346).
     The command of iteration k is the output after k Euler steps: ``step`` advances the state
     when the task moves to a new iteration (task.py:292-296)."""
     # pylint: disable=too-many-instance-attributes,too-many-arguments
 
-    def __init__(self, frequency, amplitude, rate, couplings, outputs, phase0, amplitude0=None, device=True):
+    def __init__(self, frequency, amplitude, rate, couplings, outputs, phase0, amplitude0=None, device=True, springs=()):
         pos = [o[0] for o in outputs if ControlType(o[1]) == ControlType.POSITION]
         trq = [o[0] for o in outputs if ControlType(o[1]) == ControlType.TORQUE]
         super().__init__(joints_names=[pos, [], trq])
@@ -104,6 +107,7 @@ class CPGController(AnimatController):
         self.rate = np.asarray(rate, dtype=float)
         self.couplings = [(int(j), int(i), float(w), float(phi)) for j, i, w, phi in couplings]
         self.outputs = [(str(j), ControlType(t), int(a), int(b), float(g), float(o)) for j, t, a, b, g, o in outputs]
+        self.springs = [(str(j), None, int(a), int(b), float(g), float(o)) for j, a, b, g, o in springs]
         self.theta = np.array(np.atleast_2d(phase0), dtype=float)
         self.r = np.zeros_like(self.theta) if amplitude0 is None else np.array(
             np.broadcast_to(amplitude0, self.theta.shape), dtype=float)
@@ -144,11 +148,19 @@ class CPGController(AnimatController):
     def torques(self, iteration, time, timestep):
         return {o[0]: self._command(o) for o in self.outputs if o[1] == ControlType.TORQUE}
 
-    def device_cpg(self, actuator_index, torque_unit=1.0):  # pylint: disable=method-hidden
+    def springrefs(self, iteration, time, timestep):
+        return {s[0]: self._command(s) for s in self.springs}
+
+    def device_cpg(self, actuator_index, torque_unit=1.0, spring_index=None):  # pylint: disable=method-hidden
         """The network as ``fb_set_cpg`` takes it.  ``actuator_index(joint, ControlType)`` maps
-        an output to its ctrl index; torque commands are scaled by ``units.torques`` (task.py:332)."""
+        an output to its ctrl index; torque commands are scaled by ``units.torques`` (task.py:332);
+        ``spring_index(joint)`` maps a spring reference to its qpos address."""
         theta0, r0 = self._state0
+        springs = self.springs if spring_index is not None else []
         return dict(
+            spring_qpos_adr=[spring_index(s[0]) for s in springs],
+            spring_osc_a=[s[2] for s in springs], spring_osc_b=[s[3] for s in springs],
+            spring_gain=[s[4] for s in springs], spring_offset=[s[5] for s in springs],
             frequency=self.frequency, amplitude=self.amplitude, rate=self.rate,
             coupling_from=[c[0] for c in self.couplings], coupling_to=[c[1] for c in self.couplings],
             coupling_weight=[c[2] for c in self.couplings], coupling_bias=[c[3] for c in self.couplings],

@@ -31,24 +31,35 @@ struct CpgDev {
   const int *o_act, *o_a, *o_b;             /* [n_out] */
   const float *o_gain, *o_off;              /* [n_out] */
   float *theta, *r, *rd;                    /* state [n_osc][env_pad] */
+  /* spring references (task.py:338-346: model.qpos_spring[joint] = springrefs[joint]): output s
+   * goes to row nu + s of the sequence step */
+  int n_spring;
+  const int *s_a, *s_b;                     /* [n_spring] */
+  const float *s_gain, *s_off;              /* [n_spring] */
 };
 
-/* n_steps control vectors of one environment into seq[(k*nu + a)*env_pad + env]; actuators the
- * network does not drive keep ctrl[env][a] */
+/* n_steps control vectors of one environment into seq[(k*stride + a)*env_pad + env] (stride = nu +
+ * n_spring rows per step); actuators the network does not drive keep ctrl[env][a] */
 FB_DEV void fb_cpg_env(const CpgDev &c, int env, long long env_pad, int n_steps, int nu, float dt,
                        const float *ctrl, float *seq) {
+  const int stride = nu + c.n_spring;
   float th[FB_CPG_MAXOSC], r[FB_CPG_MAXOSC], rd[FB_CPG_MAXOSC], dth[FB_CPG_MAXOSC];
   for (int i = 0; i < c.n_osc; i++) {
     th[i] = c.theta[(long long)i*env_pad + env]; r[i] = c.r[(long long)i*env_pad + env];
     rd[i] = c.rd[(long long)i*env_pad + env];
   }
   for (int k = 0; k < n_steps; k++) {
-    float *row = seq + (long long)k*nu*env_pad + env;
+    float *row = seq + (long long)k*stride*env_pad + env;
     for (int a = 0; a < nu; a++) row[(long long)a*env_pad] = ctrl[(size_t)env*nu + a];
     for (int o = 0; o < c.n_out; o++) {
       const int a = c.o_a[o], b = c.o_b[o];
       const float v = b >= 0 ? r[a]*(1.f + cosf(th[a])) - r[b]*(1.f + cosf(th[b])) : r[a]*cosf(th[a]);
       row[(long long)c.o_act[o]*env_pad] = c.o_off[o] + c.o_gain[o]*v;
+    }
+    for (int o = 0; o < c.n_spring; o++) {
+      const int a = c.s_a[o], b = c.s_b[o];
+      const float v = b >= 0 ? r[a]*(1.f + cosf(th[a])) - r[b]*(1.f + cosf(th[b])) : r[a]*cosf(th[a]);
+      row[(long long)(nu + o)*env_pad] = c.s_off[o] + c.s_gain[o]*v;
     }
     /* explicit Euler to the next iteration */
     for (int i = 0; i < c.n_osc; i++) dth[i] = 6.283185307179586f*c.freq[i];

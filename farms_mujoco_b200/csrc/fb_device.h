@@ -1347,6 +1347,10 @@ struct FbParams {
    * ctrl_seq[((seq_pos + k)*nu + a)*env_pad + env]; NULL -> ctrl is held */
   const float *ctrl_seq;
   int seq_pos;
+  /* rows of one sequence step: the nu ctrl values, then n_spring spring references (on-device CPG,
+   * fb_set_cpg_springrefs: qpos_spring[spring_qadr[s]] of step k is row nu + s) */
+  int seq_stride, n_spring;
+  const int *spring_qadr;
   float *fast_scratch;            /* [n_scratch][fast_scratch_stride]: second half of the per-thread state */
   long long fast_scratch_stride;
   float *con_scratch;             /* per-thread constrained step (fb_fastc.h): [warp][X.n_con][lane] */
@@ -1412,7 +1416,12 @@ FB_DEV void fb_run_env(const FbParams &P, int env, int k0, float *s, int *si, in
       st.forward(1);
       row = 0;
     } else {
-      if (P.ctrl_seq) st.seq_control(P.ctrl_seq + ((size_t)(P.seq_pos + k)*m.nu)*P.env_pad + e, P.env_pad);
+      if (P.ctrl_seq) {
+        const float *seqk = P.ctrl_seq + ((size_t)(P.seq_pos + k)*P.seq_stride)*P.env_pad + e;
+        /* model.qpos_spring of this step (task.py:338-346), before forward() reads it */
+        for (int i = lane; i < P.n_spring; i += TEAM) st.g.qpos_spring[P.spring_qadr[i]] = seqk[(long long)(m.nu + i)*P.env_pad];
+        st.seq_control(seqk, P.env_pad);
+      }
       if (m.n_wc > 0) st.wave_control((float)(P.it0 + k)*m.timestep);
       int wd = P.want_derived && k == n - 1;
       st.forward(wd);

@@ -378,11 +378,13 @@ struct FbHandle {
   size_t export_stage_floats;
   float *gather_env;                     /* fb_export_farms staging: one environment's ring of one kind */
   float *seq_dev, *seq_stage;            /* control sequence, environment-minor + upload staging */
-  int seq_len, seq_pos, seq_cap;
+  int seq_len, seq_pos, seq_cap, seq_rows;
   /* on-device CPG (fb_set_cpg): device tables + per-environment oscillator state */
   bool cpg_on;
   CpgDev cpg;
   std::vector<void *> cpg_allocs;
+  std::vector<int> spring_qadr_host;   /* qpos addresses of the CPG's spring-reference outputs */
+  const int *cpg_spring_qadr;          /* the same on the device */
   /* wave-controller copies (owned) */
   std::vector<int32_t> wc_act;
   std::vector<double> wc_amp, wc_freq, wc_lag, wc_off;
@@ -492,6 +494,11 @@ static int upload_model(FbHandle *h) {
   h->P.m = h->hm.m;
   h->P.m.I = h->I_dev;
   h->P.m.F = h->F_dev;
+  /* spring-reference rows of the on-device CPG (the records were just rebuilt) */
+  for (size_t sx = 0; sx < h->spring_qadr_host.size(); sx++)
+    for (size_t b = 1; b < h->hm.rec.size(); b++)
+      if (h->hm.rec[b].jtype >= 0 && h->hm.rec[b].jtype != FB_JNT_FREE && h->hm.rec[b].qa == h->spring_qadr_host[sx])
+        h->hm.rec[b].sref = (int32_t)sx;
 #ifndef FB_HOST_EMU
   if (h->hm.m.X.ok) {
     if (!h->fastQ) h->fastQ = new FbFastParams();
@@ -522,9 +529,11 @@ static bool fb_con_split_pays(FbHandle *h);
 
 /* capacity of the device control sequence ([n_steps][nu][env_pad] + the upload staging) */
 static int ensure_sequence(FbHandle *h, int n_steps) {
-  if (n_steps <= h->seq_cap) return 0;
   const DevModel &m = h->hm.m;
-  const size_t n = (size_t)h->P.n_envs, per_step = (size_t)m.nu*h->P.env_pad;
+  const int rows = m.nu + h->cpg.n_spring;          /* ctrl rows + spring-reference rows per step */
+  if (n_steps <= h->seq_cap && rows <= h->seq_rows) return 0;
+  const size_t n = (size_t)h->P.n_envs, per_step = (size_t)rows*h->P.env_pad;
+  h->seq_rows = rows;
   dev_sync(h->stream);
   if (h->seq_dev) { dev_free(h->seq_dev); dev_free(h->seq_stage); h->seq_dev = h->seq_stage = nullptr; h->seq_cap = 0; }
   void *a = nullptr, *b = nullptr;
@@ -556,6 +565,7 @@ static int launch(FbHandle *h, int mode, int n_steps, int want_derived) {
    * team kernel finishes the ones it handed over.  Reset and derived-view requests go
    * to the team kernel alone (it is the one that produces mjData-like quantities). */
   P.ctrl_seq = nullptr; P.seq_pos = 0;
+  P.seq_stride = h->hm.m.nu; P.n_spring = 0; P.spring_qadr = nullptr;
   if (mode == FB_MODE_STEP && h->cpg_on) {
     if (ensure_sequence(h, n_steps)) return -1;
     const DevModel &dm = h->hm.m;
@@ -568,6 +578,7 @@ static int launch(FbHandle *h, int mode, int n_steps, int want_derived) {
     h->launches++;
 #endif
     P.ctrl_seq = h->seq_dev; P.seq_pos = 0;
+    P.n_spring = h->cpg.n_spring; P.seq_stride = dm.nu + h->cpg.n_spring; P.spring_qadr = h->cpg_spring_qadr;
   } else if (mode == FB_MODE_STEP && h->seq_len > 0) {
     if (h->seq_pos + n_steps > h->seq_len)
       return fail("fb_step: the control sequence holds fewer steps than requested");
@@ -961,7 +972,7 @@ int fb_create(const FbModel *model, const FbFarms *farms, int n_envs, int device
   if (!h) return fail("out of host memory");
   h->device = device; h->I_dev = nullptr; h->F_dev = nullptr; h->launches = 0; h->it = 0;
   h->last_ms = 0.f; h->has_wc = false; h->gather_links = h->gather_joints = h->gather_env = nullptr;
-  h->seq_dev = h->seq_stage = nullptr; h->seq_len = h->seq_pos = h->seq_cap = 0;
+  h->seq_dev = h->seq_stage = nullptr; h->seq_len = h->seq_pos = h->seq_cap = h->seq_rows = 0;
   h->cpg_on = false; memset(&h->cpg, 0, sizeof(h->cpg));
   h->joint_sel_n = 0; h->link_sel_n = 0; h->link_items_n = 0; h->ctrl_sel_n = 0;
   h->export_stage[0] = h->export_stage[1] = nullptr; h->export_stage_floats = 0;
@@ -1263,6 +1274,11 @@ int fb_set_cpg(FbHandle *h, const FbCpgNetwork *net) {
   h->cpg_allocs.clear();
   h->cpg_on = false;
   memset(&h->cpg, 0, sizeof(h->cpg));
+  h->cpg_spring_qadr = nullptr;
+  if (!h->spring_qadr_host.empty()) {
+    h->spring_qadr_host.clear();
+    if (upload_model(h)) return -1;              /* records without spring rows */
+  }
   if (!net || net->n_osc <= 0) return 0;
   const DevModel &m = h->hm.m;
   if (net->n_osc > FB_CPG_MAXOSC) return fail("fb_set_cpg: at most 64 oscillators");
@@ -1297,6 +1313,39 @@ int fb_set_cpg(FbHandle *h, const FbCpgNetwork *net) {
   c.theta = static_cast<float *>(pt); c.r = static_cast<float *>(pr); c.rd = static_cast<float *>(pd);
   h->cpg_on = true;
   h->seq_len = h->seq_pos = 0;
+  return 0;
+}
+
+int fb_set_cpg_springrefs(FbHandle *h, int n, const int32_t *qpos_adr, const int32_t *osc_a, const int32_t *osc_b,
+                          const double *gain, const double *offset) {
+  if (!h) return fail("null handle");
+  if (!h->cpg_on) return fail("fb_set_cpg_springrefs: no CPG set (fb_set_cpg first)");
+  if (n < 0 || (n > 0 && (!qpos_adr || !osc_a || !osc_b || !gain || !offset))) return fail("fb_set_cpg_springrefs: null argument");
+  dev_sync(h->stream);
+  const DevModel &m = h->hm.m;
+  std::vector<int> adr;
+  for (int i = 0; i < n; i++) {
+    if (osc_a[i] < 0 || osc_a[i] >= h->cpg.n_osc || osc_b[i] >= h->cpg.n_osc) return fail("fb_set_cpg_springrefs: oscillator index out of range");
+    bool found = false;
+    for (int j = 0; j < m.njnt && !found; j++)
+      found = h->hm.I[m.o.jnt_qposadr + j] == qpos_adr[i] && h->hm.I[m.o.jnt_type + j] != FB_JNT_FREE;
+    if (!found) return fail("fb_set_cpg_springrefs: not the qpos address of a hinge or slide joint");
+    for (int k : adr) if (k == qpos_adr[i]) return fail("fb_set_cpg_springrefs: a joint is listed twice");
+    adr.push_back(qpos_adr[i]);
+  }
+  CpgDev &c = h->cpg;
+  c.n_spring = 0;
+  h->spring_qadr_host = adr;
+  if (upload_model(h)) return -1;                /* rebuilds the records with their spring rows */
+  if (n == 0) return 0;
+  int bad = 0;
+  bad |= cpg_upload(h, osc_a, n, &c.s_a);
+  bad |= cpg_upload(h, osc_b, n, &c.s_b);
+  bad |= cpg_upload(h, gain, n, &c.s_gain);
+  bad |= cpg_upload(h, offset, n, &c.s_off);
+  bad |= cpg_upload(h, adr.data(), n, &h->cpg_spring_qadr);
+  if (bad) return fail("fb_set_cpg_springrefs: device allocation / upload failed");
+  c.n_spring = n;
   return 0;
 }
 

@@ -453,6 +453,14 @@ FB_UNROLL
     *trq_log = lsum;
   }
 
+  /* qpos_spring ends a launch as the last sequence entry used, as if the host had set it step by
+   * step (task.py:338-346); `last` = that step's rows of this environment */
+  FB_MEM void store_springrefs(const float *last) const {
+    if (P.n_spring <= 0) return;
+    for (int b = 1; b < m.nbody; b++)
+      if (rec[b].sref >= 0) P.qpos_spring[(size_t)env*m.nq + rec[b].qa] = last[(long long)(m.nu + rec[b].sref)*P.env_pad];
+  }
+
   /* joint half of load_state: root state into registers, q / qd and the constant part of the
    * actuation of every joint into the scratch */
   FB_MEM void load_joints(const float *gq, const float *gv, const float *g_ctrl) {
@@ -1041,7 +1049,12 @@ FB_UNROLL
         } else {
           actuation_generic(rc, qj, qd, time, store_ctrl, seqk, &tau, &trq);
         }
-        if (rc.stiffness != 0.f) tau -= rc.stiffness*(qj - P.qpos_spring[(size_t)env*m.nq + rc.qa]);
+        if (rc.stiffness != 0.f) {
+          /* spring reference of this step: a row of the control sequence (on-device CPG), else held */
+          const float ref = (!LEAN && seqk && rc.sref >= 0) ? seqk[(long long)(m.nu + rc.sref)*P.env_pad]
+                                                           : P.qpos_spring[(size_t)env*m.nq + rc.qa];
+          tau -= rc.stiffness*(qj - ref);
+        }
         tau -= rc.damping*qd;
         if (MODE == 2) tau += fb_ld_scr(nblock(b) + NB_TAUC*BLK);
         float d, u;
@@ -1418,7 +1431,7 @@ FB_UNROLL
       if (!SYNC && dead) break;
       if (!dead && rec[1].jtype == FB_JNT_FREE) { rt[3] = rqn[0]; rt[4] = rqn[1]; rt[5] = rqn[2]; rt[6] = rqn[3]; }
       float aroot[6] = {0.f, 0.f, 0.f, -m.grav[0], -m.grav[1], -m.grav[2]};
-      const float *seqk = P.ctrl_seq ? P.ctrl_seq + ((size_t)(P.seq_pos + k)*m.nu)*P.env_pad + e : 0;
+      const float *seqk = P.ctrl_seq ? P.ctrl_seq + ((size_t)(P.seq_pos + k)*P.seq_stride)*P.env_pad + e : 0;
       fb_block_sync<SYNC>();
       if (!dead) pass_inertia(time, aroot, k == n - 1 && m.n_wc > 0, seqk);   /* ctrl is left as the team path leaves it */
       fb_block_sync<SYNC>();
@@ -1433,9 +1446,10 @@ FB_UNROLL
     if (!valid) return n;
     if (P.ctrl_seq && kdone == n) {
       /* ctrl ends as the last entry used, as if the host had set it step by step */
-      const float *last = P.ctrl_seq + ((size_t)(P.seq_pos + n - 1)*m.nu)*P.env_pad + e;
+      const float *last = P.ctrl_seq + ((size_t)(P.seq_pos + n - 1)*P.seq_stride)*P.env_pad + e;
       for (int a = 0; a < m.nu; a++)
         if (MI(ft_actwc, a) < 0) P.ctrl[e*m.nu + a] = last[(long long)a*P.env_pad];
+      this->store_springrefs(last);
     }
     store_state(P.it0 + kdone, coop, lane);
     return kdone;
@@ -1470,7 +1484,7 @@ FB_UNROLL
       idle = dead;
       if (role == 0 && !dead && rec[1].jtype == FB_JNT_FREE) { rt[3] = rqn[0]; rt[4] = rqn[1]; rt[5] = rqn[2]; rt[6] = rqn[3]; }
       float aroot[6] = {0.f, 0.f, 0.f, -m.grav[0], -m.grav[1], -m.grav[2]};
-      const float *seqk = P.ctrl_seq ? P.ctrl_seq + ((size_t)(P.seq_pos + k)*m.nu)*P.env_pad + e : 0;
+      const float *seqk = P.ctrl_seq ? P.ctrl_seq + ((size_t)(P.seq_pos + k)*P.seq_stride)*P.env_pad + e : 0;
       pass_inertia(time, aroot, k == n - 1 && m.n_wc > 0, seqk);
       FB_BLOCK_BARRIER();
       const int bad = pass_accel(aroot, row_joints, row_xfrc);
@@ -1483,9 +1497,10 @@ FB_UNROLL
     FB_BLOCK_BARRIER();
     if (role != 0 || !valid) return n;
     if (P.ctrl_seq && kdone == n) {
-      const float *last = P.ctrl_seq + ((size_t)(P.seq_pos + n - 1)*m.nu)*P.env_pad + e;
+      const float *last = P.ctrl_seq + ((size_t)(P.seq_pos + n - 1)*P.seq_stride)*P.env_pad + e;
       for (int a = 0; a < m.nu; a++)
         if (MI(ft_actwc, a) < 0) P.ctrl[e*m.nu + a] = last[(long long)a*P.env_pad];
+      this->store_springrefs(last);
     }
     store_state(P.it0 + kdone, coop, lane);
     return kdone;

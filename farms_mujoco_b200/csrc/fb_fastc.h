@@ -1247,7 +1247,7 @@ FB_UNROLL
       const int maybe = this->pass_poses(row_links);
       if (rec[1].jtype == FB_JNT_FREE) { rt[3] = rqn[0]; rt[4] = rqn[1]; rt[5] = rqn[2]; rt[6] = rqn[3]; }
       float aroot[6] = {0.f, 0.f, 0.f, -m.grav[0], -m.grav[1], -m.grav[2]};
-      const float *seqk = P.ctrl_seq ? P.ctrl_seq + ((size_t)(P.seq_pos + k)*m.nu)*P.env_pad + e : 0;
+      const float *seqk = P.ctrl_seq ? P.ctrl_seq + ((size_t)(P.seq_pos + k)*P.seq_stride)*P.env_pad + e : 0;
       const int store_ctrl = k == n - 1 && m.n_wc > 0;
       int mine = 0, bad;
       if (FB_ANY(maybe)) mine = detect();
@@ -1275,9 +1275,10 @@ FB_UNROLL
       if (bad) FB_FLAG_OR(P.flags + env, FB_FLAG_NONFINITE);
     }
     if (P.ctrl_seq) {
-      const float *last = P.ctrl_seq + ((size_t)(P.seq_pos + n - 1)*m.nu)*P.env_pad + e;
+      const float *last = P.ctrl_seq + ((size_t)(P.seq_pos + n - 1)*P.seq_stride)*P.env_pad + e;
       for (int a = 0; a < m.nu; a++)
         if (MI(ft_actwc, a) < 0) P.ctrl[e*m.nu + a] = last[(long long)a*P.env_pad];
+      this->store_springrefs(last);
     }
     P.con_dirty[env] = this->dirty_c;
     this->store_state(P.it0 + n, coop, lane);
@@ -1304,7 +1305,7 @@ FB_UNROLL
       const int maybe = rany(this->pass_poses(row_links));
       if (role == 0 && rec[1].jtype == FB_JNT_FREE) { rt[3] = rqn[0]; rt[4] = rqn[1]; rt[5] = rqn[2]; rt[6] = rqn[3]; }
       float aroot[6] = {0.f, 0.f, 0.f, -m.grav[0], -m.grav[1], -m.grav[2]};
-      const float *seqk = P.ctrl_seq ? P.ctrl_seq + ((size_t)(P.seq_pos + k)*m.nu)*P.env_pad + e : 0;
+      const float *seqk = P.ctrl_seq ? P.ctrl_seq + ((size_t)(P.seq_pos + k)*P.seq_stride)*P.env_pad + e : 0;
       const int store_ctrl = k == n - 1 && m.n_wc > 0;
       int mine = 0, bad;
       if (FB_ANY(maybe)) mine = rany(detect());
@@ -1338,9 +1339,10 @@ FB_UNROLL
     }
     if (role != 0) return;
     if (P.ctrl_seq) {
-      const float *last = P.ctrl_seq + ((size_t)(P.seq_pos + n - 1)*m.nu)*P.env_pad + e;
+      const float *last = P.ctrl_seq + ((size_t)(P.seq_pos + n - 1)*P.seq_stride)*P.env_pad + e;
       for (int a = 0; a < m.nu; a++)
         if (MI(ft_actwc, a) < 0) P.ctrl[e*m.nu + a] = last[(long long)a*P.env_pad];
+      this->store_springrefs(last);
     }
     P.con_dirty[env] = this->dirty_c;
     this->store_state(P.it0 + n, coop, lane);

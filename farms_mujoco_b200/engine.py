@@ -38,6 +38,8 @@ ABI_SYMBOLS = {
     'fb_set_env_phase': (ct.c_int, [_H, cabi.c_double_p]),
     'fb_set_wave_controller': (ct.c_int, [_H, ct.POINTER(cabi.FbWaveController)]),
     'fb_set_cpg': (ct.c_int, [_H, ct.POINTER(cabi.FbCpgNetwork)]),
+    'fb_set_cpg_springrefs': (ct.c_int, [_H, ct.c_int, ct.POINTER(ct.c_int32), ct.POINTER(ct.c_int32), ct.POINTER(ct.c_int32),
+                              cabi.c_double_p, cabi.c_double_p]),
     'fb_set_cpg_state': (ct.c_int, [_H, cabi.c_double_p, cabi.c_double_p]),
     'fb_get_cpg_state': (ct.c_int, [_H, cabi.c_double_p, cabi.c_double_p]),
     'fb_set_actuator_forcerange': (ct.c_int, [_H, ct.c_int, ct.POINTER(ct.c_int32), ct.POINTER(ct.c_int32), cabi.c_double_p]),
@@ -291,7 +293,9 @@ class BatchedPhysics:
         """On-device CPG (include/farms_b200.h FbCpgNetwork): ``network`` is a dict with the
         struct's array fields (``frequency, amplitude, rate, coupling_from, coupling_to,
         coupling_weight, coupling_bias, out_actuator, out_osc_a, out_osc_b, out_gain,
-        out_offset``), or None to switch it off."""
+        out_offset``), or None to switch it off.  Optional ``spring_qpos_adr, spring_osc_a,
+        spring_osc_b, spring_gain, spring_offset``: spring references the network drives
+        (fb_set_cpg_springrefs; task.py:338-346)."""
         if network is None:
             self._check(self.lib.fb_set_cpg(self._handle, None))
             self._cpg_n_osc = 0
@@ -306,6 +310,14 @@ class BatchedPhysics:
             keep.set_int(name, network[name])
         self._check(self.lib.fb_set_cpg(self._handle, keep.byref()))
         self._cpg_n_osc = int(s.n_osc)
+        adr = np.ascontiguousarray(network.get('spring_qpos_adr', ()), dtype=np.int32)
+        if len(adr):
+            ints = [np.ascontiguousarray(network[k], dtype=np.int32) for k in ('spring_osc_a', 'spring_osc_b')]
+            dbl = [np.ascontiguousarray(network[k], dtype=np.float64) for k in ('spring_gain', 'spring_offset')]
+            i32 = ct.POINTER(ct.c_int32)
+            self._check(self.lib.fb_set_cpg_springrefs(
+                self._handle, len(adr), adr.ctypes.data_as(i32), ints[0].ctypes.data_as(i32), ints[1].ctypes.data_as(i32),
+                dbl[0].ctypes.data_as(cabi.c_double_p), dbl[1].ctypes.data_as(cabi.c_double_p)))
 
     def set_cpg_state(self, phase, amplitude=None):
         """Oscillator phases (and amplitudes) ``[n_envs, n_osc]`` of the on-device CPG."""

@@ -188,7 +188,8 @@ class ExperimentTask:
             names = {ControlType.POSITION: 'actuator_position_{}', ControlType.TORQUE: 'actuator_torque_{}'}
             net = self._controller.device_cpg(
                 lambda joint, kind: ctrl_names.index(names[ControlType(kind)].format(joint)),
-                torque_unit=self.units.torques)
+                torque_unit=self.units.torques,
+                spring_index=lambda joint: self.maps['ctrl']['springref'][joint])
             physics.set_cpg(net)
             physics.set_cpg_state(net['phase0'], net['amplitude0'])
             self.device_controller = True

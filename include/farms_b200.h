@@ -210,6 +210,13 @@ int fb_set_wave_controller(FbHandle *h, const FbWaveController *c); /* NULL -> o
  * fb_set_cpg_state: phase [n_envs][n_osc] (and amplitude, NULL -> 0; rates of change start at 0);
  * fb_reset keeps the state (set it again for a new episode). */
 int fb_set_cpg(FbHandle *h, const FbCpgNetwork *net);
+/* Spring references driven by the network (task.py:338-346: model.qpos_spring[joint] =
+ * controller.springrefs()[joint], every iteration): output s sets qpos_spring[qpos_adr[s]] of every
+ * step of a launch to offset + gain * (the oscillator expression above), read by the step kernels
+ * from the same per-launch sequence as ctrl; qpos_spring ends a launch at the last value used.
+ * Call after fb_set_cpg (which clears them); n = 0 clears.  qpos_adr: hinge / slide joints. */
+int fb_set_cpg_springrefs(FbHandle *h, int n, const int32_t *qpos_adr, const int32_t *osc_a, const int32_t *osc_b,
+                          const double *gain, const double *offset);
 int fb_set_cpg_state(FbHandle *h, const double *phase, const double *amplitude);
 int fb_get_cpg_state(FbHandle *h, double *phase, double *amplitude);
 /* Model edit of ExperimentTask.initialize_control (task.py:262-286): the reference sets

@@ -298,10 +298,11 @@ def check_reset_clears_log(library, n_envs=4, ring=8):
         assert not logs['joints'][env][n_steps + 1:].any()
 
 
-def swimmer_cpg(n_envs, device, torque_joints=()):
+def swimmer_cpg(n_envs, device, torque_joints=(), spring_joints=()):
     """A salamander-type CPG for SWIMMER8: two oscillators per joint (left / right, antiphase),
     nearest-neighbour couplings with a head-to-tail phase lag, position targets = r_L (1 + cos) -
-    r_R (1 + cos); `torque_joints` are driven through their motor actuators instead."""
+    r_R (1 + cos); `torque_joints` are driven through their motor actuators instead, and the spring
+    references of `spring_joints` follow the network too."""
     from farms_mujoco_b200.control import CPGController, ControlType
     nj = 7
     freq, amp, rate = np.full(2*nj, 1.5), np.full(2*nj, 0.15), np.full(2*nj, 20.0)
@@ -321,28 +322,38 @@ def swimmer_cpg(n_envs, device, torque_joints=()):
             outputs.append((name, ControlType.POSITION, 2*j, 2*j + 1, 1.0, 0.0))
     rng = np.random.default_rng(4)
     phase0 = rng.uniform(0, 2*np.pi, (n_envs, 2*nj))
-    return CPGController(freq, amp, rate, couplings, outputs, phase0, amplitude0=0.05, device=device)
+    springs = [(name, 2*int(name.split('_')[1]), 2*int(name.split('_')[1]) + 1, 2.0, 0.05*(k + 1))
+               for k, name in enumerate(spring_joints)]
+    return CPGController(freq, amp, rate, couplings, outputs, phase0, amplitude0=0.05, device=device, springs=springs)
 
 
 def check_device_cpg(library, n_envs=3, n_it=40, chunk=8, tol=2e-5):
-    """On-device CPG (fb_set_cpg; position targets + torque commands) vs the same network evaluated
-    on the host through ExperimentTask.step_control (task.py:288-346), iteration by iteration."""
+    """On-device CPG (fb_set_cpg; position targets, torque commands and spring references) vs the
+    same network evaluated on the host through ExperimentTask.step_control (task.py:288-346),
+    iteration by iteration."""
+    import dataclasses
+    import re
     from farms_mujoco_b200 import models
     from farms_mujoco_b200.simulation.simulation import Simulation
     torque_joints = ('joint_5', 'joint_6')
-    logs = {}
+    logs, springs = {}, {}
     for device in (True, False):
         spec = models.swimmer8(n_iterations=n_it)
+        # the torque-controlled joints are elastic, and their spring references follow the network
+        mjcf, count = re.subn(r'(<joint name="joint_[56]"[^>]*?)stiffness="0.0"', r'\1stiffness="0.05"', spec.mjcf)
+        assert count == 2
+        spec = dataclasses.replace(spec, mjcf=mjcf)
         # joints 5 and 6 are torque-controlled: their motors lose the 'position' control type, so
         # initialize_control switches their position / velocity actuators off (task.py:274-286)
         for motor in spec.animat_options.control.motors:
             if motor['joint_name'] in torque_joints:
                 motor.control_types = ['torque']
         sim = Simulation.from_spec(spec, n_envs=n_envs, chunk=chunk, library=library,
-                                   controller=swimmer_cpg(n_envs, device, torque_joints))
+                                   controller=swimmer_cpg(n_envs, device, torque_joints, spring_joints=torque_joints))
         sim.run()
         assert sim.task.device_controller == device and sim.iteration == n_it - 1
         logs[device] = {k: getattr(sim.task.data.sensors, k).array.copy() for k in ('links', 'joints', 'xfrc')}
+        springs[device] = sim.physics.qpos_spring
         if device:
             phase, amplitude = sim.physics.cpg_state()
             assert np.isfinite(phase).all() and (amplitude > 0.05).all()
@@ -352,6 +363,9 @@ def check_device_cpg(library, n_envs=3, n_it=40, chunk=8, tol=2e-5):
     for kind in ('links', 'joints', 'xfrc'):
         err = log_error(kind, logs[True][kind], logs[False][kind])
         assert err < tol, (kind, err)
+    # model.qpos_spring ends where the host would have left it, and it moved
+    assert np.abs(springs[False][:, 7 + 5:]).max() > 0.05
+    assert np.abs(springs[True] - springs[False]).max() < 1e-5, np.abs(springs[True] - springs[False]).max()
 
 
 LEAN_TOL = 1e-5
