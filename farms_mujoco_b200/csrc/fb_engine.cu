@@ -498,7 +498,7 @@ static int upload_model(FbHandle *h) {
   for (size_t sx = 0; sx < h->spring_qadr_host.size(); sx++)
     for (size_t b = 1; b < h->hm.rec.size(); b++)
       if (h->hm.rec[b].jtype >= 0 && h->hm.rec[b].jtype != FB_JNT_FREE && h->hm.rec[b].qa == h->spring_qadr_host[sx])
-        h->hm.rec[b].sref = (int32_t)sx;
+        h->hm.rec[b].flags |= (int32_t)(sx + 1) << FT_SREF_SHIFT;
 #ifndef FB_HOST_EMU
   if (h->hm.m.X.ok) {
     if (!h->fastQ) h->fastQ = new FbFastParams();
@@ -1321,6 +1321,7 @@ int fb_set_cpg_springrefs(FbHandle *h, int n, const int32_t *qpos_adr, const int
   if (!h) return fail("null handle");
   if (!h->cpg_on) return fail("fb_set_cpg_springrefs: no CPG set (fb_set_cpg first)");
   if (n < 0 || (n > 0 && (!qpos_adr || !osc_a || !osc_b || !gain || !offset))) return fail("fb_set_cpg_springrefs: null argument");
+  if (n > FB_MAX_SPRINGREFS) return fail("fb_set_cpg_springrefs: at most 126 spring references");
   dev_sync(h->stream);
   const DevModel &m = h->hm.m;
   std::vector<int> adr;

@@ -458,7 +458,7 @@ FB_UNROLL
   FB_MEM void store_springrefs(const float *last) const {
     if (P.n_spring <= 0) return;
     for (int b = 1; b < m.nbody; b++)
-      if (rec[b].sref >= 0) P.qpos_spring[(size_t)env*m.nq + rec[b].qa] = last[(long long)(m.nu + rec[b].sref)*P.env_pad];
+      if (FT_SREF(rec[b].flags) >= 0) P.qpos_spring[(size_t)env*m.nq + rec[b].qa] = last[(long long)(m.nu + FT_SREF(rec[b].flags))*P.env_pad];
   }
 
   /* joint half of load_state: root state into registers, q / qd and the constant part of the
@@ -1051,7 +1051,7 @@ FB_UNROLL
         }
         if (rc.stiffness != 0.f) {
           /* spring reference of this step: a row of the control sequence (on-device CPG), else held */
-          const float ref = (!LEAN && seqk && rc.sref >= 0) ? seqk[(long long)(m.nu + rc.sref)*P.env_pad]
+          const float ref = (!LEAN && seqk && FT_SREF(flags) >= 0) ? seqk[(long long)(m.nu + FT_SREF(flags))*P.env_pad]
                                                            : P.qpos_spring[(size_t)env*m.nq + rc.qa];
           tau -= rc.stiffness*(qj - ref);
         }

@@ -73,11 +73,17 @@ struct DevOffsets {
 #define FT_ACT_SIMPLE 32    /* unclamped actuators, gear 1, all logged: one linear form */
 #define FT_HAS_WAVE 64
 #define FT_HAS_JPOS 128
+/* bits 24..30: 1 + row of the joint's spring reference behind the nu ctrl rows of a control-sequence
+ * step (fb_set_cpg_springrefs); 0: the joint's spring reference is qpos_spring */
+#define FT_SREF_SHIFT 24
+#define FT_SREF(flags_) ((((flags_) >> FT_SREF_SHIFT) & 0x7f) - 1)
+#define FB_MAX_SPRINGREFS 126
 #define FT_AXISYM 256        /* inertia = Ib[0]*1 + Ib[1]*n n', n = Ib[2..4] (capsule, cylinder, sphere) */
 
 /* Everything the recursion needs about one body, resolved at model build: no index
  * chasing in the kernel.  The table travels in the kernel parameters (constant bank),
- * so every lane of a warp reads it with uniform, hoistable loads.  73 words. */
+ * so every lane of a warp reads it with uniform, hoistable loads.  72 words = nine 32-byte lines:
+ * keep it that size (a 73rd word cost the swimming kernel 3 %, r3a). */
 struct FastRec {
   int32_t parent, jtype, qa, da;          /* joint type -1: welded; qa/da: qpos/qvel address */
   int32_t flags, slot, pslot, link;       /* link: farms link row, -1 */
@@ -96,8 +102,6 @@ struct FastRec {
   float T0U;                              /* farms joint_torque column does not log */
   int32_t bc0, bc1, pblk7;                /* candidates of the body: CandRec[bc0 .. bc1) (fb_fastc.h); 7*(parent-1) (SLIM blocks) */
   float chk[4];                           /* first conservative plane check (normal, offset) */
-  int32_t sref;                           /* row of the joint's spring reference behind the nu ctrl rows of a
-                                           * control-sequence step (fb_set_cpg_springrefs), -1: qpos_spring */
 };
 
 /* Tree split of the unconstrained kernel for SMALL batches (fb_fast.h, FbFast<.., SPLIT = 1>): the 32
@@ -659,7 +663,7 @@ inline bool fb_build_model(const FbModel *fm, const FbFarms *ff, const FbWaveCon
       if (a < 0 || a >= nu || actwc[a] >= 0) X.ok = 0; else actwc[a] = i;
     }
     int nslot = 0;
-    for (int b = 0; b < nb; b++) { rec[b].slot = rec[b].pslot = rec[b].link = rec[b].fj = rec[b].xr = rec[b].swim = -1; rec[b].jtype = -1; rec[b].jid = -1; rec[b].wave_act = -1; rec[b].sref = -1; }
+    for (int b = 0; b < nb; b++) { rec[b].slot = rec[b].pslot = rec[b].link = rec[b].fj = rec[b].xr = rec[b].swim = -1; rec[b].jtype = -1; rec[b].jid = -1; rec[b].wave_act = -1; }
     for (int b = 1; b < nb; b++) {
       FastRec &r = rec[b];
       int p = fm->body_parentid[b], dn = fm->body_dofnum[b], jid = fm->body_jntid[b];
