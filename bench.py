@@ -296,6 +296,9 @@ def kernel_name(physics, handed_over, n_local):
         return f'fb_step_kernel<{physics.team_lanes}>'
     lean = int(physics.fast_lean)
     if 2*handed_over > n_local:
+        if physics.constraint_path and physics.con_split and handed_over == n_local:
+            return (f'fb_fastc_split_kernel<{physics.fast_path},{lean}> '
+                    f'({len(physics.fast_split_schedule())} warps per {physics.fast_path} envs)')
         return (f'fb_fastc_kernel<{physics.fast_path},{lean}>' if physics.constraint_path
                 else f'fb_step_kernel<{physics.team_lanes}>')
     if physics.fast_split:
