@@ -17,4 +17,4 @@ t=time.time()
 for k in range(launches): ph.step(16, sync=False)
 ph.synchronize()
 f=ph.flags
-print(name, n, 'steps', launches*16, 'sec %.2f'%(time.time()-t), 'nonfinite', int(np.count_nonzero(f&1)), 'solver', int(np.count_nonzero(f&4)), 'slim', ph.fast_slim, 'blk', ph.fast_path, 'finite state', bool(np.isfinite(ph.qpos).all()), 'max|qvel| %.2f'%np.abs(ph.qvel).max())
+print(name, n, 'steps', launches*16, 'sec %.2f'%(time.time()-t), 'nonfinite', int(np.count_nonzero(f&1)), 'solver', int(np.count_nonzero(f&4)), 'slim', ph.fast_slim, 'blk', ph.fast_path, 'con_split', ph.con_split, 'finite state', bool(np.isfinite(ph.qpos).all()), 'max|qvel| %.2f'%np.abs(ph.qvel).max())
