@@ -642,7 +642,7 @@ FB_BODY_LOOP
     for (int i = 0; i <= n_it; i++) {
       if (SPLIT && i == ord_bnd) {
         split_barrier();                 /* the trunk is placed: the subtrees hanging off it start */
-        if (role != 0) {
+        if (role != 0 && rec[1].jtype == FB_JNT_FREE) {       /* (a fixed base: the anchors are measured from the world origin) */
 FB_UNROLL
           for (int k = 0; k < 3; k++) rootpos[k] = sroot[k*BLK];
         }

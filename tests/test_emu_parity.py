@@ -404,3 +404,10 @@ def test_con_split_variant(emu_library):
     """SPLIT variant of the constrained kernel under the same emulation (cross-warp sums included)."""
     import fastpath_cases
     fastpath_cases.check_con_split_variant(emu_library, n_envs=75, n_steps=(3, 2))
+
+
+def test_split_variant_fixed_base(emu_library):
+    """Tree-split kernel (emulated warps) on a branching tree without a floating root."""
+    import fastpath_cases
+    import variant_models
+    fastpath_cases.check_variant(emu_library, variant_models.salamander_swim_fixed_base(), free_base=False)

@@ -687,3 +687,33 @@ def test_con_split_variant(cuda_library, monkeypatch, block):
     import fastpath_cases
     monkeypatch.setenv('FARMS_B200_FAST_BLOCK', block)
     fastpath_cases.check_con_split_variant(cuda_library)
+
+
+def test_split_variant_fixed_base(cuda_library, monkeypatch):
+    """Tree-split kernel on a branching tree WITHOUT a floating root (the warps other than the trunk's
+    have no published root position to read): against the oracle and against the single-warp kernel."""
+    import fastpath_cases
+    import variant_models
+    from farms_mujoco_b200 import mjcf_subset
+    from farms_mujoco_b200.engine import BatchedPhysics
+    monkeypatch.setenv('FARMS_B200_FAST_BLOCK', '32')
+    spec = variant_models.salamander_swim_fixed_base()
+    fastpath_cases.check_variant(cuda_library, spec, free_base=False)
+    model = mjcf_subset.parse_mjcf(spec.mjcf)
+    n = 70
+    rng = np.random.default_rng(3)
+    qpos0 = np.tile(model.key_qpos, (n, 1)) + rng.uniform(-0.1, 0.1, (n, model.nq))
+    qvel0 = rng.uniform(-0.3, 0.3, (n, model.nv))
+    ctrl = rng.uniform(-0.3, 0.3, (n, model.nu))
+    outs = []
+    for split in (False, True):
+        physics = BatchedPhysics.from_spec(spec, n, buffer_size=9, library=cuda_library)
+        physics.set_fast_split(split)
+        assert bool(physics.fast_split) == split
+        physics.reset(qpos0, qvel0)
+        physics.set_ctrl(ctrl)
+        physics.step(8)
+        outs.append((physics.qpos, physics.qvel, physics.log_arrays()))
+    assert np.array_equal(outs[0][0], outs[1][0]) and np.array_equal(outs[0][1], outs[1][1])
+    for kind in ('links', 'joints', 'contacts', 'xfrc'):
+        assert np.array_equal(outs[0][2][kind], outs[1][2][kind]), kind

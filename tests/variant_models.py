@@ -50,10 +50,20 @@ def swimmer8_features():
 
 def swimmer8_fixed_base():
     """farms 'fixed_base' (mjcf.py:751-756): no free joint; the base links fuse into the world."""
-    spec = models.swimmer8()
+    return _fixed_base(models.swimmer8(), 'swimmer8_fixed')
+
+
+def salamander_swim_fixed_base():
+    """The same for a BRANCHING tree (legs and tail hang off a trunk whose first link is welded to
+    the world): the tree-split kernels without a floating root."""
+    return _fixed_base(models.salamander(swimming=True), 'salamander_swim_fixed')
+
+
+def _fixed_base(spec, name):
     x = spec.mjcf
-    assert '<freejoint name="root_swimmer"/>' in x
-    x = x.replace('      <freejoint name="root_swimmer"/>\n', '')
+    root = re.search(r' *<freejoint name="[^"]*"/>\n', x)
+    assert root, 'no free joint'
+    x = x.replace(root.group(0), '')
 
     def trim(match):
         values = match.group(2).split()
@@ -64,7 +74,7 @@ def swimmer8_fixed_base():
     links = spec.links_names[1:]        # link_0 is welded to the world now: not a moving body
     animat = copy.deepcopy(spec.animat_options)
     animat.morphology.links = [link for link in animat.morphology.links if link.name in links]
-    return dataclasses.replace(spec, name='swimmer8_fixed', mjcf=x, links_names=links,
+    return dataclasses.replace(spec, name=name, mjcf=x, links_names=links,
                                animat_options=animat,
                                xfrc_names=links, contacts_names=[c for c in spec.contacts_names
                                                                  if c[0] in links])
