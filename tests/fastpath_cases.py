@@ -498,3 +498,42 @@ def check_con_split_variant(library, n_envs=75, n_steps=(6, 5), names=('salamand
             assert val < (5e-4 if force else tol[name]), (name, key, worst)
         # the contacts rows are not all zero: the comparison above is about real forces
         assert np.abs(a[3]['contacts']).max() > 0, name
+
+
+def check_con_split_mixed_groups(library, n_envs=64, lift=0.06, fall=-1.0, n_steps=(1, 6, 6, 6)):
+    """The SPLIT constrained kernel takes only the groups whose environments were ALL handed over
+    before their first step; the single-warp kernel behind it takes the others.  The first half of
+    the batch stands on the ground; the second half starts `lift` above it (just outside the
+    conservative plane bound of the hand-over test) moving down at `fall` m/s and crosses the bound
+    in the middle of the third launch: in that launch every environment is handed over, the first
+    half at step 0 (SPLIT), the second wherever it crossed (single warp).  Against the same batch
+    with the SPLIT variant switched off."""
+    from farms_mujoco_b200.engine import BatchedPhysics
+    spec, model, qpos0, qvel0, ctrl = make_case('salamander', n_envs, qvel_scale=0.05)
+    qpos0[n_envs//2:, 2] += lift
+    qvel0[n_envs//2:, 2] = fall
+    outs, all_pending = [], []
+    for split in (False, True):
+        physics = BatchedPhysics.from_spec(spec, n_envs, buffer_size=sum(n_steps) + 1, library=library)
+        physics.set_con_split(split)
+        physics.reset(qpos0, qvel0)
+        physics.set_ctrl(ctrl)
+        pending = []
+        for n in n_steps:
+            physics.step(n)
+            pending.append(physics.last_pending)
+        all_pending.append(pending)
+        outs.append((physics.qpos, physics.qvel, physics.log_arrays(), physics.flags))
+    assert all_pending[0] == all_pending[1], all_pending
+    # the falling half is outside the bound for the first launches and joins in the middle of one
+    assert all_pending[0][0] == all_pending[0][1] == n_envs//2 and all_pending[0][2] == n_envs, all_pending
+    assert np.array_equal(outs[0][3], outs[1][3])
+    a, b = outs
+    for env in range(n_envs):
+        errs = state_errors(a[0][env], a[1][env], b[0][env], b[1][env])
+        assert max(errs.values()) < LEAN_TOL, (env, errs)
+        for kind in ('links', 'joints', 'contacts', 'xfrc'):
+            for group, val in log_errors(kind, a[2][kind][env], b[2][kind][env]).items():
+                force = kind == 'contacts' or group == 'limit_force'
+                assert val < (5e-4 if force else LEAN_TOL), (env, kind, group, val)
+    assert np.abs(a[2]['contacts'][:n_envs//2]).max() > 0

@@ -411,3 +411,8 @@ def test_split_variant_fixed_base(emu_library):
     import fastpath_cases
     import variant_models
     fastpath_cases.check_variant(emu_library, variant_models.salamander_swim_fixed_base(), free_base=False)
+
+
+def test_con_split_mixed_groups(emu_library):
+    import fastpath_cases
+    fastpath_cases.check_con_split_mixed_groups(emu_library, n_envs=16)

@@ -717,3 +717,12 @@ def test_split_variant_fixed_base(cuda_library, monkeypatch):
     assert np.array_equal(outs[0][0], outs[1][0]) and np.array_equal(outs[0][1], outs[1][1])
     for kind in ('links', 'joints', 'contacts', 'xfrc'):
         assert np.array_equal(outs[0][2][kind], outs[1][2][kind]), kind
+
+
+@pytest.mark.parametrize('block', ['16', '32'])
+def test_con_split_mixed_groups(cuda_library, monkeypatch, block):
+    """Groups handed over in full go to the SPLIT constrained kernel, late arrivals of the same launch
+    to the single-warp kernel behind it (the per-group flags of fb_fastc_split_kernel)."""
+    import fastpath_cases
+    monkeypatch.setenv('FARMS_B200_FAST_BLOCK', block)
+    fastpath_cases.check_con_split_mixed_groups(cuda_library)
