@@ -500,14 +500,15 @@ def check_con_split_variant(library, n_envs=75, n_steps=(6, 5), names=('salamand
         assert np.abs(a[3]['contacts']).max() > 0, name
 
 
-def check_con_split_mixed_groups(library, n_envs=64, lift=0.06, fall=-1.0, n_steps=(1, 6, 6, 6)):
+def check_con_split_mixed_groups(library, n_envs=64, lift=0.06, fall=-1.0, n_steps=(1, 6, 6, 6), tol=5e-5):
     """The SPLIT constrained kernel takes only the groups whose environments were ALL handed over
     before their first step; the single-warp kernel behind it takes the others.  The first half of
     the batch stands on the ground; the second half starts `lift` above it (just outside the
     conservative plane bound of the hand-over test) moving down at `fall` m/s and crosses the bound
     in the middle of the third launch: in that launch every environment is handed over, the first
     half at step 0 (SPLIT), the second wherever it crossed (single warp).  Against the same batch
-    with the SPLIT variant switched off."""
+    with the SPLIT variant switched off: rounding-level differences of the two summation orders,
+    grown over 19 steps of ground contact (the tolerance of the 20-step oracle comparisons)."""
     from farms_mujoco_b200.engine import BatchedPhysics
     spec, model, qpos0, qvel0, ctrl = make_case('salamander', n_envs, qvel_scale=0.05)
     qpos0[n_envs//2:, 2] += lift
@@ -531,9 +532,9 @@ def check_con_split_mixed_groups(library, n_envs=64, lift=0.06, fall=-1.0, n_ste
     a, b = outs
     for env in range(n_envs):
         errs = state_errors(a[0][env], a[1][env], b[0][env], b[1][env])
-        assert max(errs.values()) < LEAN_TOL, (env, errs)
+        assert max(errs.values()) < tol, (env, errs)
         for kind in ('links', 'joints', 'contacts', 'xfrc'):
             for group, val in log_errors(kind, a[2][kind][env], b[2][kind][env]).items():
                 force = kind == 'contacts' or group == 'limit_force'
-                assert val < (5e-4 if force else LEAN_TOL), (env, kind, group, val)
+                assert val < (5e-4 if force else tol), (env, kind, group, val)
     assert np.abs(a[2]['contacts'][:n_envs//2]).max() > 0
