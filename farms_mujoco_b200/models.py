@@ -80,6 +80,7 @@ class _Link:
     inertia: Tuple[float, float, float] = (0.0, 0.0, 0.0)   # diagonal, body axes
     geoms: List[_Geom] = field(default_factory=list)
     offdiag: Tuple[float, float, float] = (0.0, 0.0, 0.0)   # Ixy, Ixz, Iyz
+    jpos: Tuple[float, float, float] = (0.0, 0.0, 0.0)      # joint anchor in the link frame (SDF joint pose)
 
 
 @dataclass
@@ -114,7 +115,7 @@ def _emit_mjcf(model_name, links, joints_opts, motors, spawn_pose, sim, arena_z,
             joint_order.append(link.joint)
             out.append(
                 f'{pad}  <joint name="{link.joint}" type="hinge" axis="{_fmt(link.axis)}" '
-                f'pos="0.0 0.0 0.0" damping="{float(jo.damping)!r}" '
+                f'pos="{_fmt(link.jpos)}" damping="{float(jo.damping)!r}" '
                 f'stiffness="{float(jo.stiffness)!r}" springref="0.0" frictionloss="0.0" '
                 f'limited="true" range="{_fmt(link.limits)}"/>')
         for geom in link.geoms:

@@ -105,11 +105,18 @@ class Simulation:
 
     @classmethod
     def from_sdf(cls, simulation_options, animat_options, arena_options, **kwargs):
-        """The reference builds the MJCF from SDF files here (simulation.py:96-124, mjcf.py:1174);
-        that conversion needs farms_core's SDF reader, trimesh and dm_control.mjcf and is not
-        part of the stepping path: build the MJCF with farms_mujoco and use ``Simulation(...)``
-        or ``from_spec``."""
-        raise NotImplementedError(cls.from_sdf.__doc__)
+        """From SDF (simulation.py:96-124): the MJCF is built from ``animat_options.sdf`` by
+        ``sdf_subset.spec_from_sdf``, the part of ``setup_mjcf_xml`` / ``sdf2mjcf``
+        (mjcf.py:132-600, 1174-1512) the stepping path can run -- primitive collision shapes,
+        revolute / fixed joints, unrotated link frames, the flat arena of ``arena_options``;
+        anything else (meshes, heightmaps, rotated frames, prismatic joints) raises
+        ``NotImplementedError`` naming the element.  The reference's conversion proper needs
+        farms_core's SDF reader, trimesh and dm_control.mjcf, none of which exist here."""
+        from ..sdf_subset import spec_from_sdf  # pylint: disable=import-outside-toplevel
+        n_envs = kwargs.pop('n_envs', 1)
+        spec = spec_from_sdf(simulation_options, animat_options, arena_options,
+                             contacts_names=kwargs.pop('contacts_names', None))
+        return cls.from_spec(spec, n_envs=n_envs, **kwargs)
 
     def save_mjcf_xml(self, path, verbose=False):
         """Save simulation to mjcf xml (simulation.py:126-132)"""

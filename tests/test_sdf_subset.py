@@ -1,0 +1,132 @@
+"""SDF front-end (sdf_subset.py; the primitive-geometry subset of the reference's
+Simulation.from_sdf -> setup_mjcf_xml -> sdf2mjcf, simulation.py:96-124, mjcf.py:132-600)."""
+
+import numpy as np
+import pytest
+
+from farms_mujoco_b200 import mjcf_subset, models, sdf_subset
+from farms_mujoco_b200.options import (AnimatOptions, ArenaOptions, ControlOptions, JointOptions, LinkOptions,
+                                       MorphologyOptions, MotorOptions, SimulationOptions, SpawnOptions, WaterOptions)
+
+
+def swimmer8_sdf():
+    """SWIMMER8 (models.swimmer8) written as an SDF model: absolute link poses, capsules along x."""
+    radius, length = 0.02, 0.1
+    mass, axial, transverse = models.capsule_mass_inertia(radius, length)
+    out = ['<?xml version="1.0"?>', '<sdf version="1.6">', '  <model name="swimmer">']
+    for i in range(8):
+        out += [f'    <link name="link_{i}">', f'      <pose>{length*i!r} 0 0 0 0 0</pose>',
+                '      <inertial>', f'        <pose>{0.5*length!r} 0 0 0 0 0</pose>', f'        <mass>{mass!r}</mass>',
+                f'        <inertia><ixx>{axial!r}</ixx><iyy>{transverse!r}</iyy><izz>{transverse!r}</izz>'
+                '<ixy>0</ixy><ixz>0</ixz><iyz>0</iyz></inertia>', '      </inertial>',
+                f'      <collision name="link_{i}_collision">', f'        <pose>{0.5*length!r} 0 0 0 {0.5*np.pi!r} 0</pose>',
+                f'        <geometry><capsule><radius>{radius!r}</radius><length>{length!r}</length></capsule></geometry>',
+                '      </collision>', '    </link>']
+    for i in range(7):
+        out += [f'    <joint name="joint_{i}" type="revolute">', f'      <parent>link_{i}</parent>',
+                f'      <child>link_{i + 1}</child>', '      <axis><xyz>0 0 1</xyz><limit><lower>-1.0</lower><upper>1.0</upper></limit></axis>',
+                '    </joint>']
+    out += ['  </model>', '</sdf>']
+    return '\n'.join(out)
+
+
+def swimmer8_options(sdf):
+    reference = models.swimmer8()
+    animat = AnimatOptions(
+        name='swimmer', sdf=sdf, spawn=SpawnOptions(pose=list(reference.animat_options.spawn.pose)),
+        morphology=MorphologyOptions(
+            links=[LinkOptions(name=f'link_{i}', swimming=True, drag_coefficients=[[-0.1, -1.0, -1.0], [-1e-3]*3],
+                               friction=[1.0, 0.0, 0.0]) for i in range(8)],
+            joints=[JointOptions(name=f'joint_{i}', damping=1e-3, limits=[-1.0, 1.0]) for i in range(7)]),
+        control=ControlOptions(motors=[MotorOptions(joint_name=f'joint_{i}', gains=[1.0, 1e-3]) for i in range(7)]))
+    arena = ArenaOptions(ground_height=-2.0, water=WaterOptions(height=0.0, drag=True, buoyancy=True))
+    return reference, SimulationOptions(timestep=1e-3, n_iterations=reference.simulation_options.n_iterations), animat, arena
+
+
+def test_swimmer8_from_sdf_is_the_synthetic_model(tmp_path):
+    """The SDF description of SWIMMER8 yields the same compiled model as the generator of the
+    benchmark workload -- from text and from a file."""
+    path = tmp_path/'swimmer.sdf'
+    path.write_text(swimmer8_sdf())
+    for source in (swimmer8_sdf(), str(path)):
+        reference, sim, animat, arena = swimmer8_options(source)
+        spec = sdf_subset.spec_from_sdf(sim, animat, arena)
+        ours, ref = mjcf_subset.parse_mjcf(spec.mjcf), mjcf_subset.parse_mjcf(reference.mjcf)
+        assert spec.links_names == reference.links_names and spec.joints_names == reference.joints_names
+        assert spec.xfrc_names == reference.xfrc_names and spec.contacts_names == reference.contacts_names
+        for field in ('body_parentid', 'body_pos', 'body_mass', 'body_ipos', 'body_inertia', 'jnt_axis', 'jnt_range',
+                      'jnt_pos', 'geom_size', 'geom_pos', 'geom_quat', 'geom_type', 'key_qpos', 'actuator_gainprm',
+                      'actuator_biasprm', 'dof_damping'):
+            a, b = np.asarray(getattr(ours, field), dtype=float), np.asarray(getattr(ref, field), dtype=float)
+            assert a.shape == b.shape and np.allclose(a, b, rtol=1e-12, atol=1e-15), field
+
+
+def branching_sdf(extra=''):
+    """A trunk of two links with a sphere-footed leg on each side, the second joint anchored off its
+    link origin, and a fixed sensor link."""
+    return f"""<sdf version="1.6"><model name="walker">
+  <link name="trunk_0"><pose>0 0 0 0 0 0</pose>
+    <inertial><pose>0.05 0 0 0 0 0</pose><mass>0.2</mass><inertia><ixx>1e-4</ixx><iyy>3e-4</iyy><izz>3e-4</izz></inertia></inertial>
+    <collision name="trunk_0_c"><pose>0.05 0 0 0 1.5707963267948966 0</pose><geometry><capsule><radius>0.02</radius><length>0.1</length></capsule></geometry></collision></link>
+  <link name="trunk_1"><pose>0.1 0 0 0 0 0</pose>
+    <inertial><pose>0.05 0 0 0 0 0</pose><mass>0.2</mass><inertia><ixx>1e-4</ixx><iyy>3e-4</iyy><izz>3e-4</izz></inertia></inertial>
+    <collision name="trunk_1_c"><pose>0.05 0 0 0 0 0</pose><geometry><box><size>0.1 0.04 0.03</size></box></geometry></collision></link>
+  <link name="leg_L"><pose>0.05 0.04 0 0 0 0</pose>
+    <inertial><pose>0 0 -0.02 0 0 0</pose><mass>0.02</mass><inertia><ixx>4e-6</ixx><iyy>4e-6</iyy><izz>2e-6</izz><ixy>1e-7</ixy></inertia></inertial>
+    <collision name="foot_L"><pose>0 0 -0.04 0 0 0</pose><geometry><sphere><radius>0.01</radius></sphere></geometry></collision></link>
+  <link name="leg_R"><pose>0.05 -0.04 0 0 0 0</pose>
+    <inertial><pose>0 0 -0.02 0 0 0</pose><mass>0.02</mass><inertia><ixx>4e-6</ixx><iyy>4e-6</iyy><izz>2e-6</izz></inertia></inertial>
+    <collision name="foot_R"><pose>0 0 -0.04 0 0 0</pose><geometry><sphere><radius>0.01</radius></sphere></geometry></collision></link>
+  <link name="imu"><pose>0.02 0 0.02 0 0 0</pose><inertial><mass>0.001</mass><inertia><ixx>1e-9</ixx><iyy>1e-9</iyy><izz>1e-9</izz></inertia></inertial></link>
+  <joint name="spine" type="revolute"><parent>trunk_0</parent><child>trunk_1</child>
+    <axis><xyz>0 0 1</xyz><limit><lower>-0.8</lower><upper>0.8</upper></limit></axis></joint>
+  <joint name="hip_L" type="revolute"><parent>trunk_0</parent><child>leg_L</child><pose>0 -0.01 0 0 0 0</pose>
+    <axis><xyz>0 1 0</xyz><limit><lower>-0.5</lower><upper>0.5</upper></limit></axis></joint>
+  <joint name="hip_R" type="revolute"><parent>trunk_0</parent><child>leg_R</child>
+    <axis><xyz>0 1 0</xyz><limit><lower>-0.5</lower><upper>0.5</upper></limit></axis></joint>
+  <joint name="imu_mount" type="fixed"><parent>trunk_0</parent><child>imu</child></joint>
+  {extra}
+</model></sdf>"""
+
+
+def test_branching_sdf():
+    name, links = sdf_subset.read_sdf(branching_sdf())
+    assert name == 'walker'
+    assert [link.name for link in links] == ['trunk_0', 'trunk_1', 'leg_L', 'leg_R', 'imu']      # depth first, joint order
+    by_name = {link.name: link for link in links}
+    assert by_name['leg_L'].parent == 'trunk_0' and np.allclose(by_name['leg_L'].pos, [0.05, 0.04, 0.0])
+    assert by_name['leg_L'].jpos == (0.0, -0.01, 0.0) and by_name['leg_L'].offdiag == (1e-7, 0.0, 0.0)
+    assert by_name['imu'].joint == '' and by_name['trunk_1'].geoms[0].size == (0.05, 0.02, 0.015)
+    animat = AnimatOptions(sdf=branching_sdf(), spawn=SpawnOptions(pose=[0, 0, 0.05, 0, 0, 0]),
+                           control=ControlOptions(motors=[MotorOptions(joint_name='spine', gains=[0.5, 1e-3])]))
+    spec = sdf_subset.spec_from_sdf(SimulationOptions(), animat, ArenaOptions(ground_height=0.0))
+    model = mjcf_subset.parse_mjcf(spec.mjcf)
+    assert spec.joints_names == ['spine', 'hip_L', 'hip_R'] and model.nu == 3 and model.nv == 9
+    assert spec.contacts_names == [('trunk_0', ''), ('trunk_1', ''), ('leg_L', ''), ('leg_R', '')]
+    assert spec.base_link == 'trunk_0' and [j.name for j in animat.morphology.joints] == spec.joints_names
+
+
+@pytest.mark.parametrize('extra,message', [
+    ('<link name="m"><pose>0 0 0 0 0 0.3</pose></link>', 'rotated link frame'),
+    ('<link name="s"/><joint name="p" type="prismatic"><parent>trunk_0</parent><child>s</child></joint>', 'prismatic'),
+    ('<link name="h"><collision name="c"><geometry><mesh><uri>a.obj</uri></mesh></geometry></collision></link>', '<mesh>'),
+])
+def test_unsupported_elements_are_named(extra, message):
+    with pytest.raises(NotImplementedError, match=message):
+        sdf_subset.read_sdf(branching_sdf(extra))
+
+
+def test_simulation_from_sdf_runs(emu_library):
+    """Simulation.from_sdf end to end on the emulation build: the branching walker settles on its
+    feet, the log has the reference's shapes."""
+    from farms_mujoco_b200.simulation.simulation import Simulation
+    animat = AnimatOptions(sdf=branching_sdf(), spawn=SpawnOptions(pose=[0, 0, 0.06, 0, 0, 0]),
+                           control=ControlOptions(motors=[MotorOptions(joint_name=j, gains=[0.5, 1e-3])
+                                                          for j in ('spine', 'hip_L', 'hip_R')]))
+    sim = Simulation.from_sdf(SimulationOptions(timestep=1e-3, n_iterations=60), animat, ArenaOptions(ground_height=0.0),
+                              n_envs=2, library=emu_library)
+    sim.run()
+    sensors = sim.task.data.sensors
+    assert sensors.links.array.shape[-2:] == (5, 20) and sensors.joints.array.shape[-2:] == (3, 18)
+    assert np.isfinite(sensors.links.array).all()
+    assert np.abs(sensors.contacts.array[..., 2]).max() > 0.1          # the feet carry the weight (0.44 kg)
