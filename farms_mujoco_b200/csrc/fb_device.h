@@ -747,6 +747,7 @@ FB_UNROLL
       int c = c0 + lane;
       int hit = 0;
       float dist = 0.f, centre[3] = {0.f, 0.f, 0.f}, nrm[3] = {0.f, 0.f, 1.f}, R[9], radius = 0.f;
+      float sup[3] = {0.f, 0.f, 0.f};      /* contact point on the geom relative to `centre`, before the -dist/2 n shift */
       int b = 0;
       if (c < m.ncand) {
         b = MI(cand_body, c);
@@ -758,8 +759,23 @@ FB_UNROLL
         radius = MF(cand_radius, c);
         float cdist = centre[0]*nrm[0] + centre[1]*nrm[1] + centre[2]*nrm[2] - MF(cand_pd, c);
         dist = cdist - radius;
+        sup[0] = -nrm[0]*radius; sup[1] = -nrm[1]*radius; sup[2] = -nrm[2]*radius;
+        if (MI(cand_iscapsule, c) == 4) {
+          /* ellipsoid (mjc_PlaneConvex): support point along -normal, R Rg (s o normalize(s o (R Rg)'(-n))) */
+          const Quat gq = {MF(cand_gquat, 4*c), MF(cand_gquat, 4*c+1), MF(cand_gquat, 4*c+2), MF(cand_gquat, 4*c+3)};
+          float Rg[9], nb_[3], nl[3], w[3], wb[3];
+          q_mat(gq, Rg);
+          m_rot_t(R, nrm[0], nrm[1], nrm[2], nb_);
+          m_rot_t(Rg, nb_[0], nb_[1], nb_[2], nl);
+          for (int k = 0; k < 3; k++) w[k] = -nl[k]*MF(cand_laxis, 3*c+k);
+          v_normalize3(w);
+          for (int k = 0; k < 3; k++) w[k] *= MF(cand_laxis, 3*c+k);
+          m_rot(Rg, w[0], w[1], w[2], wb);
+          m_rot(R, wb[0], wb[1], wb[2], sup);
+          dist = cdist + sup[0]*nrm[0] + sup[1]*nrm[1] + sup[2]*nrm[2];
+        }
         hit = dist < MF(cand_margin, c) - MF(cand_gap, c);
-        if (MI(cand_iscapsule, c) >= 2) {
+        if ((MI(cand_iscapsule, c) & ~1) == 2) {
           /* box corner (mjc_PlaneBox): only while it is below the box centre along the normal.
            * (MuJoCo's cap of 4 corners per box only binds in degenerate poses and is not applied
            * here; the per-thread kernel and the oracle apply it.) */
@@ -777,7 +793,8 @@ FB_UNROLL
         g.d_con_dist[i] = dist;
         float f[9];
         for (int k = 0; k < 3; k++) {
-          g.d_con_pos[3*i + k] = centre[k] - nrm[k]*(radius + 0.5f*dist);
+          g.d_con_pos[3*i + k] = MI(cand_iscapsule, c) == 4 ? centre[k] + sup[k] - nrm[k]*0.5f*dist
+                                                            : centre[k] - nrm[k]*(radius + 0.5f*dist);
           f[k] = nrm[k];
         }
         if (MI(cand_iscapsule, c) == 1) {

@@ -253,8 +253,29 @@ FB_UNROLL
         /* plane offset first: both terms are small near the plane */
         const float dist = ((n[0]*rootpos[0] + n[1]*rootpos[1] + n[2]*rootpos[2]) - cr_.pd)
                            + (n[0]*(o[0] + t[0]) + n[1]*(o[1] + t[1]) + n[2]*(o[2] + t[2])) - radius;
-        int hit = dist < includemargin;
-        if (cr_.iscapsule >= 2) {
+        float dist_ = dist, pofs[3] = {0.f, 0.f, 0.f};
+        if (!LEAN && cr_.iscapsule == 4) {
+          /* ellipsoid (mjc_PlaneConvex): the support point along -normal, R Rg (s o normalize(s o
+           * (R Rg)'(-n))), in place of the sphere's -radius n (cr_.radius, pad: the geom's orientation) */
+          const float qx = cr_.radius, qy = cr_.pad[0], qz = cr_.pad[1];
+          const Quat gq = {sqrtf(fmaxf(0.f, 1.f - qx*qx - qy*qy - qz*qz)), qx, qy, qz};
+          float Rg[9], nb_[3], nl[3], w3[3], wb[3];
+          q_mat(gq, Rg);
+          m_rot_t(R, n[0], n[1], n[2], nb_);
+          m_rot_t(Rg, nb_[0], nb_[1], nb_[2], nl);
+FB_UNROLL
+          for (int k = 0; k < 3; k++) w3[k] = -nl[k]*cr_.laxis[k];
+          v_normalize3(w3);
+FB_UNROLL
+          for (int k = 0; k < 3; k++) w3[k] *= cr_.laxis[k];
+          m_rot(Rg, w3[0], w3[1], w3[2], wb);
+          m_rot(R, wb[0], wb[1], wb[2], pofs);
+          dist_ = ((n[0]*rootpos[0] + n[1]*rootpos[1] + n[2]*rootpos[2]) - cr_.pd)
+                  + (n[0]*(o[0] + t[0]) + n[1]*(o[1] + t[1]) + n[2]*(o[2] + t[2])) + (n[0]*pofs[0] + n[1]*pofs[1] + n[2]*pofs[2]);
+        }
+        const int ell = !LEAN && cr_.iscapsule == 4;
+        int hit = (ell ? dist_ : dist) < includemargin;
+        if ((cr_.iscapsule & ~1) == 2) {
           /* box corner: only while it is below the box centre along the normal, at most 4 per box */
           float u[3];
           m_rot(R, cr_.lpos[0] - cr_.laxis[0], cr_.lpos[1] - cr_.laxis[1], cr_.lpos[2] - cr_.laxis[2], u);
@@ -268,7 +289,8 @@ FB_UNROLL
         float *pc = ncand(fc);
         float r[3], f[9];
 FB_UNROLL
-        for (int k = 0; k < 3; k++) { r[k] = t[k] - n[k]*(radius + 0.5f*dist); f[k] = n[k]; }
+        for (int k = 0; k < 3; k++) { r[k] = ell ? t[k] + pofs[k] - n[k]*(0.5f*dist_) : t[k] - n[k]*(radius + 0.5f*dist); f[k] = n[k]; }
+        const float de = ell ? dist_ : dist;
         if (cr_.iscapsule == 1) m_rot(R, cr_.laxis[0], cr_.laxis[1], cr_.laxis[2], f + 3);
         else f[3] = f[4] = f[5] = 0.f;
         /* mju_makeFrame */
@@ -287,7 +309,7 @@ FB_UNROLL
         for (int k = 0; k < 5; k++) si5[k] = MF(cand_solimp, 5*c + k);
         const float tran = cr_.invw;
         float K, B, imp, Rr;
-        fb_row_params(m.timestep, sr, si5, dist - includemargin, tran + mu*mu*tran, &K, &B, &imp, &Rr);
+        fb_row_params(m.timestep, sr, si5, de - includemargin, tran + mu*mu*tran, &K, &B, &imp, &Rr);
         const float R1 = Rr/impratio;
         const float cmu2 = mu*mu*(R1/Rr);
         const float Rpy = fmaxf(FB_MINVAL, 2.f*cmu2*R1);
@@ -301,7 +323,7 @@ FB_UNROLL
         const float vt1 = f[3]*vp[0] + f[4]*vp[1] + f[5]*vp[2];
         const float vt2 = f[6]*vp[0] + f[7]*vp[1] + f[8]*vp[2];
         /* aref of the four pyramid rows = base +- bt1, base +- bt2 */
-        const float base = -B*vn - K*imp*(dist - includemargin);
+        const float base = -B*vn - K*imp*(de - includemargin);
 FB_UNROLL
         for (int k = 0; k < 3; k++) { fb_st_scr(pc + (NC_R + k)*BLK, r[k]); fb_st_scr(pc + (NC_T1 + k)*BLK, f[3 + k]); }
         fb_st_scr(pc + NC_D*BLK, hit ? 1.0f/Rpy : 0.f);

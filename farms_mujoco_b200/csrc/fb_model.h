@@ -46,6 +46,7 @@ struct DevOffsets {
   int body_pos, body_quat, body_ipos, body_iquat, body_mass, body_inertia, body_invw;
   int jnt_pos, jnt_axis, jnt_stiffness, jnt_range, jnt_margin, jnt_solref, jnt_solimp, jnt_qpos0;
   int dof_damping, dof_armature, dof_invw;
+  int cand_gquat;  /* float [ncand][4] geom orientation in the body frame (ellipsoids; identity otherwise) */
   int cand_lpos, cand_laxis, cand_radius, cand_pn, cand_pd, cand_friction, cand_solref,
       cand_solimp, cand_margin, cand_gap, cand_invw;
   int act_gain, act_bias, act_ctrlrange, act_forcerange, act_gear;
@@ -122,7 +123,9 @@ struct FastSplit {
 #define FB_FAST_MAXCAND 112
 struct CandRec {
   int32_t body, cid, iscapsule, pblk;     /* cid: index into the cand_* tables; pblk = FB_NF*(body-1);
-                                           * iscapsule: 0 sphere, 1 capsule end, 2 box corner, 3 first corner of a box */
+                                           * iscapsule: 0 sphere, 1 capsule end, 2 box corner, 3 first corner of a box,
+                                           * 4 ellipsoid (laxis = radii; radius, pad[0], pad[1] = x, y, z of the
+                                           * geom's orientation quaternion in the body frame, w >= 0) */
   float pn[3], mu;                        /* plane normal (world), friction */
   float lpos[3], radius;                  /* centre relative to the body's joint anchor (body axes) */
   float laxis[3], pd;                     /* capsule axis (body axes) / box centre relative to the anchor; plane offset */
@@ -509,7 +512,8 @@ inline bool fb_build_model(const FbModel *fm, const FbFarms *ff, const FbWaveCon
 
   /* collision candidates: plane (static, world frame) vs sphere / capsule end */
   std::vector<int32_t> cbody(nc), ccaps(nc);
-  std::vector<double> lpos(3*nc), laxis(3*nc), rad(nc), pn(3*nc), pd(nc), cinvw(nc);
+  std::vector<double> lpos(3*nc), laxis(3*nc), rad(nc), pn(3*nc), pd(nc), cinvw(nc), gquat(4*nc, 0.0);
+  bool any_ellipsoid = false;
   for (int c = 0; c < nc; c++) {
     int g1 = fm->cand_geom1[c], g2 = fm->cand_geom2[c];
     if (fm->geom_bodyid[g1] != 0 || fm->geom_type[g1] != FB_GEOM_PLANE) {
@@ -521,7 +525,19 @@ inline bool fb_build_model(const FbModel *fm, const FbFarms *ff, const FbWaveCon
     double n[3] = { pm[2], pm[5], pm[8] }, ax[3] = { gm[2], gm[5], gm[8] };
     const int end = fm->cand_end[c];
     cbody[c] = fm->geom_bodyid[g2];
-    if (end >= 2) {
+    gquat[4*c] = 1.0;
+    if (end == 10) {
+      /* ellipsoid (mjc_PlaneConvex): kind 4; lpos = centre, laxis = the three radii, gquat = the
+       * geom's orientation in the body frame; rad = the largest radius (conservative checks only) */
+      if (fm->geom_type[g2] != FB_GEOM_ELLIPSOID) { out.error = "cand_end 10 on a geom that is not an ellipsoid"; return false; }
+      ccaps[c] = 4;
+      any_ellipsoid = true;
+      const double *sz = fm->geom_size + 3*g2;
+      for (int k = 0; k < 3; k++) { lpos[3*c+k] = fm->geom_pos[3*g2+k]; laxis[3*c+k] = sz[k]; pn[3*c+k] = n[k]; }
+      rad[c] = std::max(sz[0], std::max(sz[1], sz[2]));
+      const double *gq = fm->geom_quat + 4*g2, sgn = gq[0] < 0 ? -1.0 : 1.0;
+      for (int k = 0; k < 4; k++) gquat[4*c+k] = sgn*gq[k];
+    } else if (end >= 2) {
       /* box corner end-2 (mjc_PlaneBox): a point of radius 0; kind 2, or 3 for the first corner
        * of its (plane, box) pair; laxis holds the box centre (the corner counts only while it is
        * below the centre along the plane normal) */
@@ -619,6 +635,7 @@ inline bool fb_build_model(const FbModel *fm, const FbFarms *ff, const FbWaveCon
   o.dof_damping = put_f(F, vd(fm->dof_damping, nv));
   o.dof_armature = put_f(F, vd(fm->dof_armature, nv));
   o.dof_invw = put_f(F, vd(fm->dof_invweight0, nv));
+  o.cand_gquat = put_f(F, gquat);
   o.cand_lpos = put_f(F, lpos);
   o.cand_laxis = put_f(F, laxis);
   o.cand_radius = put_f(F, rad);
@@ -849,9 +866,12 @@ inline bool fb_build_model(const FbModel *fm, const FbFarms *ff, const FbWaveCon
           for (int k = 0; k < 3; k++) {
             r.pn[k] = (float)pn[3*c + k];
             r.lpos[k] = (float)(lpos[3*c + k] - (double)rec[b].jpos[k]);
-            r.laxis[k] = (float)(ccaps[c] >= 2 ? laxis[3*c + k] - (double)rec[b].jpos[k] : laxis[3*c + k]);
+            r.laxis[k] = (float)(ccaps[c] == 2 || ccaps[c] == 3 ? laxis[3*c + k] - (double)rec[b].jpos[k] : laxis[3*c + k]);
           }
           r.mu = (float)fm->cand_friction[c]; r.radius = (float)rad[c]; r.pd = (float)pd[c];
+          if (ccaps[c] == 4) {     /* ellipsoid: laxis = radii; the vector part of its orientation (w >= 0) */
+            r.radius = (float)gquat[4*c + 1]; r.pad[0] = (float)gquat[4*c + 2]; r.pad[1] = (float)gquat[4*c + 3];
+          }
           r.includemargin = (float)(fm->cand_margin[c] - fm->cand_gap[c]);
           r.invw = (float)cinvw[c];
           fc_of[c] = (int)crec.size();
@@ -886,7 +906,7 @@ inline bool fb_build_model(const FbModel *fm, const FbFarms *ff, const FbWaveCon
       for (int b = 0; b < nb; b++) parent[b] = fm->body_parentid[b];
       fb_build_split(parent, X.ok ? FB_SPLIT_MAXW : 1, out.split);
     }
-    X.lean = X.ok && X.jrow_std;
+    X.lean = X.ok && X.jrow_std && !any_ellipsoid;      /* (the LEAN constrained kernel leaves the ellipsoid branch out) */
     for (int b = 1; b < nb; b++) {
       const FastRec &r = rec[b];
       if (r.flags & FT_HAS_JPOS) X.lean = 0;

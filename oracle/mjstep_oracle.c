@@ -365,6 +365,30 @@ void orc_collision(const FbModel *m, OrcData *d) {
     const double *pm = d->geom_xmat + 9*g1, *pp = d->geom_xpos + 3*g1;
     const double *gm = d->geom_xmat + 9*g2, *gp = d->geom_xpos + 3*g2;
     double n[3] = { pm[2], pm[5], pm[8] };
+    if (end == 10) {
+      /* plane-ellipsoid (mjc_PlaneConvex): the support point of the ellipsoid along -normal,
+       * centre + R (s o normalize(s o R'(-n))) (mjc_support, ellipsoid case); one contact while the
+       * point is inside the margin */
+      const double *sz = m->geom_size + 3*g2;
+      double w[3], sup[3];
+      for (int k = 0; k < 3; k++) w[k] = -(gm[k]*n[0] + gm[3+k]*n[1] + gm[6+k]*n[2])*sz[k];
+      normalize3(w);
+      for (int k = 0; k < 3; k++) w[k] *= sz[k];
+      for (int k = 0; k < 3; k++) sup[k] = gp[k] + gm[3*k]*w[0] + gm[3*k+1]*w[1] + gm[3*k+2]*w[2];
+      double dif[3] = { sup[0]-pp[0], sup[1]-pp[1], sup[2]-pp[2] };
+      double sdist = dot3(dif, n);
+      if (sdist > m->cand_margin[c]) continue;
+      int i = d->ncon++;
+      d->con_cand[i] = c;
+      d->con_dist[i] = sdist;
+      for (int k = 0; k < 3; k++) d->con_pos[3*i+k] = sup[k] - n[k]*0.5*sdist;
+      double *f = d->con_frame + 9*i;
+      memcpy(f, n, sizeof(n));
+      f[3] = f[4] = f[5] = 0;
+      make_frame(f);
+      d->con_efc_address[i] = -1;
+      continue;
+    }
     if (end >= 2) {
       /* plane-box (mjc_PlaneBox): corner end-2 (bit 0: x, 1: y, 2: z) of the half-sizes; kept when
        * it is below the box centre along the normal and inside the margin; at most 4 per pair */

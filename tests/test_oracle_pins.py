@@ -226,6 +226,50 @@ def test_plane_box_corners():
         assert np.allclose(span, [0.028*cs + 0.018*sn, 0.028*sn + 0.018*cs], atol=1e-9)
 
 
+def test_plane_ellipsoid_support_point():
+    """Plane-ellipsoid collision (mjc_PlaneConvex with the ellipsoid's support function): the one
+    contact of an ellipsoid foot is its lowest point -- on the surface, with the surface normal
+    along the plane normal, and no sampled surface point lower -- and sits halfway between that
+    point and the plane."""
+    import variant_models
+    from farms_mujoco_b200 import mjcf_subset
+    from farms_mujoco_b200.mjcf_subset import quat2mat
+    spec = variant_models.salamander_ellipsoid_feet()
+    model = mjcf_subset.parse_mjcf(spec.mjcf)
+    orc = OraclePhysics(model)
+    orc.reset(keyframe_id=0)
+    rng = np.random.default_rng(9)
+    qpos = np.array(model.key_qpos)
+    qpos[2] -= 0.012
+    qpos[3:7] = [0.999, 0.02, -0.03, 0.03]              # the trunk tilted: no principal axis is vertical
+    qpos[3:7] /= np.linalg.norm(qpos[3:7])
+    qpos[7:] += rng.uniform(-0.1, 0.1, model.nq - 7)
+    orc.data.qpos[:] = qpos
+    orc.forward()
+    n = orc.ncon
+    cand = orc.arrays['con_cand'][:n]
+    ends = np.asarray(model.cand_end)[cand]
+    assert (ends == 10).sum() >= 2
+    pos = orc.arrays['con_pos'].reshape(-1, 3)[:n]
+    dist = orc.arrays['con_dist'][:n]
+    gpos = orc.arrays['geom_xpos'].reshape(-1, 3)
+    gmat = orc.arrays['geom_xmat'].reshape(-1, 3, 3)
+    normal = np.array([0.0, 0.0, 1.0])
+    u, v = np.meshgrid(np.linspace(0, np.pi, 400), np.linspace(0, 2*np.pi, 800))
+    sphere = np.stack([np.sin(u)*np.cos(v), np.sin(u)*np.sin(v), np.cos(u)], axis=-1).reshape(-1, 3)
+    for i in np.flatnonzero(ends == 10):
+        g = int(np.asarray(model.cand_geom2)[cand[i]])
+        size, R, centre = np.asarray(model.geom_size).reshape(-1, 3)[g], gmat[g], gpos[g]
+        point = pos[i] + 0.5*dist[i]*normal              # the support point itself
+        local = R.T @ (point - centre)
+        assert abs(np.sum((local/size)**2) - 1.0) < 1e-12                      # on the surface
+        grad = R @ (local/size**2)
+        assert np.allclose(grad/np.linalg.norm(grad), -normal, atol=1e-12)     # lowest point: normal = -n
+        assert abs(point @ normal - dist[i]) < 1e-12                           # plane z = 0
+        heights = (centre + (sphere*size) @ R.T) @ normal
+        assert heights.min() >= point @ normal - 1e-12
+
+
 def test_instrumented_op_count_matches_stock_oracle(tmp_path):
     """oracle/opcount: the oracle compiled with the counting scalar reproduces the stock oracle's
     bits and reports the committed per-step operation counts (profiles/oracle_opcount.json,

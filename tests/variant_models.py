@@ -95,3 +95,20 @@ def salamander_box_feet():
     assert x.count(old) == 2, x.count(old)
     x = x.replace(old, 'type="box" size="0.05 0.02 0.018" pos="0.04 0.0 0.0" quat="1.0 0.0 0.0 0.0"')
     return dataclasses.replace(spec, name='salamander_box', mjcf=x)
+
+
+def salamander_ellipsoid_feet():
+    """SALAMANDER on the ground with ellipsoid feet (radii 16 x 8 x 10 mm, rotated about z and tilted
+    about x) and an ellipsoid trunk segment: plane-ellipsoid contacts, one contact at the support
+    point along the plane normal (mjc_PlaneConvex)."""
+    spec = models.salamander()
+    x = spec.mjcf
+    foot = 'type="sphere" size="0.01 0.01 0.01" pos="0.0 0.0 -0.04" quat="1.0 0.0 0.0 0.0"'
+    assert x.count(foot) == 8, x.count(foot)       # collision geom + visual twin of four feet
+    x = x.replace(foot, 'type="ellipsoid" size="0.016 0.008 0.01" pos="0.0 0.0 -0.04" '
+                        'quat="0.9736691213452591 0.1471556949711443 0.02601839493044343 0.17215309088585662"')
+    old = ('type="capsule" size="0.020000000000000004 0.04 0.0" pos="0.04 0.0 0.0" '
+           'quat="0.7071067811865476 0.0 0.7071067811865475 0.0"')
+    assert x.count(old) == 2, x.count(old)
+    x = x.replace(old, 'type="ellipsoid" size="0.05 0.02 0.018" pos="0.04 0.0 0.0" quat="1.0 0.0 0.0 0.0"')
+    return dataclasses.replace(spec, name='salamander_ellipsoid', mjcf=x)
