@@ -81,6 +81,7 @@ class _Link:
     geoms: List[_Geom] = field(default_factory=list)
     offdiag: Tuple[float, float, float] = (0.0, 0.0, 0.0)   # Ixy, Ixz, Iyz
     jpos: Tuple[float, float, float] = (0.0, 0.0, 0.0)      # joint anchor in the link frame (SDF joint pose)
+    quat: Tuple[float, float, float, float] = (1.0, 0.0, 0.0, 0.0)   # link frame in the parent's (wxyz)
 
 
 @dataclass
@@ -109,7 +110,7 @@ def _emit_mjcf(model_name, links, joints_opts, motors, spawn_pose, sim, arena_z,
 
     def emit_link(link, indent):
         pad = ' '*indent
-        out.append(f'{pad}<body name="{link.name}" pos="{_fmt(link.pos)}" quat="1.0 0.0 0.0 0.0">')
+        out.append(f'{pad}<body name="{link.name}" pos="{_fmt(link.pos)}" quat="{_fmt(link.quat)}">')
         if link.joint:
             jo = joints_opts[link.joint]
             joint_order.append(link.joint)

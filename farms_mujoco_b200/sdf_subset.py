@@ -5,8 +5,9 @@ dm_control (``setup_mjcf_xml`` farms_mujoco/simulation/mjcf.py:1174-1512, ``sdf2
 mjcf.py:132-600, called by ``Simulation.from_sdf`` simulation.py:96-124); neither exists in this
 image.  This module covers the subset of that conversion the stepping path can run: links with
 ``<inertial>`` and sphere / capsule / box / cylinder / ellipsoid ``<collision>`` geometry, revolute
-(and fixed) joints forming a tree, link frames parallel to the model frame.  Meshes, heightmaps,
-visuals, rotated link frames and prismatic joints raise ``NotImplementedError`` naming the element.
+(and fixed) joints forming a tree; link frames may be rotated against the model frame (the joint
+axis is read in the child link's frame, SDF 1.5+).  Meshes, heightmaps, visuals, rotated inertial
+or joint frames and prismatic joints raise ``NotImplementedError`` naming the element.
 The arena is the flat ground plane (and the water surface) of ``arena_options``; its own SDF is not
 read.  The MJCF text follows the reference's schema and naming rules through the same emitter as
 the synthetic models (models.py).
@@ -17,7 +18,7 @@ import xml.etree.ElementTree as ET
 
 import numpy as np
 
-from .mjcf_subset import euler_xyz2quat
+from .mjcf_subset import euler_xyz2quat, quat2mat, quat_mul
 from .models import AnimatSpec, _Geom, _Link, _emit_mjcf
 from .options import JointOptions, LinkOptions
 
@@ -72,9 +73,7 @@ def read_sdf(source):
     for node in model.findall('link'):
         name = node.get('name')
         pose = _pose(node)
-        if np.abs(pose[3:]).max() > 0:
-            raise NotImplementedError(f'link {name}: rotated link frame (<pose> with a rotation)')
-        poses[name] = pose[:3]
+        poses[name] = (pose[:3], np.asarray(euler_xyz2quat(pose[3:]), dtype=float))
         inertial = node.find('inertial')
         mass, ipos, diag, off = 0.0, np.zeros(3), (0.0, 0.0, 0.0), (0.0, 0.0, 0.0)
         if inertial is not None:
@@ -103,7 +102,11 @@ def read_sdf(source):
         children.setdefault(parent, []).append(child)
         link = links[child]
         link.parent = parent
-        link.pos = tuple(poses[child] - poses[parent])
+        # the child's frame in the parent's: both <pose>s are given in the model frame
+        (p_pos, p_quat), (c_pos, c_quat) = poses[parent], poses[child]
+        p_conj = p_quat*np.array([1.0, -1.0, -1.0, -1.0])
+        link.pos = tuple(quat2mat(p_quat).T @ (c_pos - p_pos))
+        link.quat = tuple(quat_mul(p_conj, c_quat))
         if kind == 'fixed':
             continue
         if kind not in ('revolute', 'continuous'):
@@ -129,6 +132,8 @@ def read_sdf(source):
 
     visit(bases[0])
     assert len(ordered) == len(links)
+    # the base link's own rotation (its frame in the model's)
+    ordered[0].pos, ordered[0].quat = tuple(poses[bases[0]][0]), tuple(poses[bases[0]][1])
     return model.get('name') or 'animat', ordered
 
 

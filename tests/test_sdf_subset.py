@@ -61,9 +61,19 @@ def test_swimmer8_from_sdf_is_the_synthetic_model(tmp_path):
             assert a.shape == b.shape and np.allclose(a, b, rtol=1e-12, atol=1e-15), field
 
 
-def branching_sdf(extra=''):
+def branching_sdf(extra='', leg_rpy=(0.0, 0.0, 0.0)):
     """A trunk of two links with a sphere-footed leg on each side, the second joint anchored off its
-    link origin, and a fixed sensor link."""
+    link origin, and a fixed sensor link.  ``leg_rpy`` turns the FRAME of the left leg (not the leg):
+    its inertial offset, inertia tensor, collision offset, joint anchor and joint axis are rewritten
+    in the turned frame, so the animat is physically the same."""
+    from farms_mujoco_b200.mjcf_subset import euler_xyz2quat, quat2mat
+    rot = quat2mat(np.asarray(euler_xyz2quat(leg_rpy), dtype=float))          # leg frame -> model frame
+    inertia = rot.T @ np.array([[4e-6, 1e-7, 0.0], [1e-7, 4e-6, 0.0], [0.0, 0.0, 2e-6]]) @ rot
+    vec = lambda v: ' '.join(repr(float(x)) for x in rot.T @ np.asarray(v, dtype=float))
+    leg = dict(rpy=' '.join(repr(float(a)) for a in leg_rpy), com=vec([0, 0, -0.02]), foot=vec([0, 0, -0.04]),
+               anchor=vec([0, -0.01, 0]), axis=vec([0, 1, 0]),
+               **{k: repr(float(inertia[i, j])) for k, (i, j) in dict(ixx=(0, 0), iyy=(1, 1), izz=(2, 2), ixy=(0, 1),
+                                                                        ixz=(0, 2), iyz=(1, 2)).items()})
     return f"""<sdf version="1.6"><model name="walker">
   <link name="trunk_0"><pose>0 0 0 0 0 0</pose>
     <inertial><pose>0.05 0 0 0 0 0</pose><mass>0.2</mass><inertia><ixx>1e-4</ixx><iyy>3e-4</iyy><izz>3e-4</izz></inertia></inertial>
@@ -71,17 +81,17 @@ def branching_sdf(extra=''):
   <link name="trunk_1"><pose>0.1 0 0 0 0 0</pose>
     <inertial><pose>0.05 0 0 0 0 0</pose><mass>0.2</mass><inertia><ixx>1e-4</ixx><iyy>3e-4</iyy><izz>3e-4</izz></inertia></inertial>
     <collision name="trunk_1_c"><pose>0.05 0 0 0 0 0</pose><geometry><box><size>0.1 0.04 0.03</size></box></geometry></collision></link>
-  <link name="leg_L"><pose>0.05 0.04 0 0 0 0</pose>
-    <inertial><pose>0 0 -0.02 0 0 0</pose><mass>0.02</mass><inertia><ixx>4e-6</ixx><iyy>4e-6</iyy><izz>2e-6</izz><ixy>1e-7</ixy></inertia></inertial>
-    <collision name="foot_L"><pose>0 0 -0.04 0 0 0</pose><geometry><sphere><radius>0.01</radius></sphere></geometry></collision></link>
+  <link name="leg_L"><pose>0.05 0.04 0 {leg['rpy']}</pose>
+    <inertial><pose>{leg['com']} 0 0 0</pose><mass>0.02</mass><inertia><ixx>{leg['ixx']}</ixx><iyy>{leg['iyy']}</iyy><izz>{leg['izz']}</izz><ixy>{leg['ixy']}</ixy><ixz>{leg['ixz']}</ixz><iyz>{leg['iyz']}</iyz></inertia></inertial>
+    <collision name="foot_L"><pose>{leg['foot']} 0 0 0</pose><geometry><sphere><radius>0.01</radius></sphere></geometry></collision></link>
   <link name="leg_R"><pose>0.05 -0.04 0 0 0 0</pose>
     <inertial><pose>0 0 -0.02 0 0 0</pose><mass>0.02</mass><inertia><ixx>4e-6</ixx><iyy>4e-6</iyy><izz>2e-6</izz></inertia></inertial>
     <collision name="foot_R"><pose>0 0 -0.04 0 0 0</pose><geometry><sphere><radius>0.01</radius></sphere></geometry></collision></link>
   <link name="imu"><pose>0.02 0 0.02 0 0 0</pose><inertial><mass>0.001</mass><inertia><ixx>1e-9</ixx><iyy>1e-9</iyy><izz>1e-9</izz></inertia></inertial></link>
   <joint name="spine" type="revolute"><parent>trunk_0</parent><child>trunk_1</child>
     <axis><xyz>0 0 1</xyz><limit><lower>-0.8</lower><upper>0.8</upper></limit></axis></joint>
-  <joint name="hip_L" type="revolute"><parent>trunk_0</parent><child>leg_L</child><pose>0 -0.01 0 0 0 0</pose>
-    <axis><xyz>0 1 0</xyz><limit><lower>-0.5</lower><upper>0.5</upper></limit></axis></joint>
+  <joint name="hip_L" type="revolute"><parent>trunk_0</parent><child>leg_L</child><pose>{leg['anchor']} 0 0 0</pose>
+    <axis><xyz>{leg['axis']}</xyz><limit><lower>-0.5</lower><upper>0.5</upper></limit></axis></joint>
   <joint name="hip_R" type="revolute"><parent>trunk_0</parent><child>leg_R</child>
     <axis><xyz>0 1 0</xyz><limit><lower>-0.5</lower><upper>0.5</upper></limit></axis></joint>
   <joint name="imu_mount" type="fixed"><parent>trunk_0</parent><child>imu</child></joint>
@@ -95,7 +105,7 @@ def test_branching_sdf():
     assert [link.name for link in links] == ['trunk_0', 'trunk_1', 'leg_L', 'leg_R', 'imu']      # depth first, joint order
     by_name = {link.name: link for link in links}
     assert by_name['leg_L'].parent == 'trunk_0' and np.allclose(by_name['leg_L'].pos, [0.05, 0.04, 0.0])
-    assert by_name['leg_L'].jpos == (0.0, -0.01, 0.0) and by_name['leg_L'].offdiag == (1e-7, 0.0, 0.0)
+    assert np.allclose(by_name['leg_L'].jpos, (0.0, -0.01, 0.0)) and np.allclose(by_name['leg_L'].offdiag, (1e-7, 0.0, 0.0))
     assert by_name['imu'].joint == '' and by_name['trunk_1'].geoms[0].size == (0.05, 0.02, 0.015)
     animat = AnimatOptions(sdf=branching_sdf(), spawn=SpawnOptions(pose=[0, 0, 0.05, 0, 0, 0]),
                            control=ControlOptions(motors=[MotorOptions(joint_name='spine', gains=[0.5, 1e-3])]))
@@ -107,7 +117,7 @@ def test_branching_sdf():
 
 
 @pytest.mark.parametrize('extra,message', [
-    ('<link name="m"><pose>0 0 0 0 0 0.3</pose></link>', 'rotated link frame'),
+    ('<link name="m"><inertial><pose>0 0 0 0 0 0.3</pose><mass>1</mass></inertial></link>', 'rotated <inertial> frame'),
     ('<link name="s"/><joint name="p" type="prismatic"><parent>trunk_0</parent><child>s</child></joint>', 'prismatic'),
     ('<link name="h"><collision name="c"><geometry><mesh><uri>a.obj</uri></mesh></geometry></collision></link>', '<mesh>'),
 ])
@@ -130,3 +140,28 @@ def test_simulation_from_sdf_runs(emu_library):
     assert sensors.links.array.shape[-2:] == (5, 20) and sensors.joints.array.shape[-2:] == (3, 18)
     assert np.isfinite(sensors.links.array).all()
     assert np.abs(sensors.contacts.array[..., 2]).max() > 0.1          # the feet carry the weight (0.44 kg)
+
+
+def test_rotated_link_frame_is_the_same_animat(emu_library):
+    """Turning the FRAME of a link (with everything expressed in it rewritten accordingly) changes
+    the MJCF -- body quaternion, joint axis, inertial -- but not the animat: world trajectories agree."""
+    from farms_mujoco_b200.simulation.simulation import Simulation
+    logs = []
+    for rpy in ((0.0, 0.0, 0.0), (0.4, -0.3, 0.7)):
+        animat = AnimatOptions(sdf=branching_sdf(leg_rpy=rpy), spawn=SpawnOptions(pose=[0, 0, 0.055, 0, 0, 0]),
+                               control=ControlOptions(motors=[MotorOptions(joint_name=j, gains=[0.5, 1e-3])
+                                                              for j in ('spine', 'hip_L', 'hip_R')]))
+        sim = Simulation.from_sdf(SimulationOptions(timestep=1e-3, n_iterations=40), animat, ArenaOptions(ground_height=0.0),
+                                  n_envs=1, library=emu_library)
+        if any(rpy):
+            leg = [line for line in sim._mjcf_model.splitlines() if '<body name="leg_L"' in line][0]
+            assert 'quat="1.0 0.0 0.0 0.0"' not in leg
+        sim.run()
+        sensors = sim.task.data.sensors
+        logs.append((sensors.links.array.copy(), sensors.joints.array.copy(), sensors.contacts.array.copy()))
+    links0, joints0, contacts0 = logs[0]
+    links1, joints1, contacts1 = logs[1]
+    assert np.abs(links0[..., :3] - links1[..., :3]).max() < 2e-6          # CoM positions [m]
+    assert np.abs(joints0[..., :2] - joints1[..., :2]).max() < 1e-4       # joint positions / velocities
+    assert np.abs(contacts0[..., :3] - contacts1[..., :3]).max() < 2e-3*np.abs(contacts0[..., :3]).max()
+    assert np.abs(contacts0[..., 2]).max() > 0.1
