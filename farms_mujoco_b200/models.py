@@ -82,6 +82,7 @@ class _Link:
     offdiag: Tuple[float, float, float] = (0.0, 0.0, 0.0)   # Ixy, Ixz, Iyz
     jpos: Tuple[float, float, float] = (0.0, 0.0, 0.0)      # joint anchor in the link frame (SDF joint pose)
     quat: Tuple[float, float, float, float] = (1.0, 0.0, 0.0, 0.0)   # link frame in the parent's (wxyz)
+    jtype: str = 'hinge'                                     # 'hinge' or 'slide' (SDF prismatic)
 
 
 @dataclass
@@ -115,7 +116,7 @@ def _emit_mjcf(model_name, links, joints_opts, motors, spawn_pose, sim, arena_z,
             jo = joints_opts[link.joint]
             joint_order.append(link.joint)
             out.append(
-                f'{pad}  <joint name="{link.joint}" type="hinge" axis="{_fmt(link.axis)}" '
+                f'{pad}  <joint name="{link.joint}" type="{link.jtype}" axis="{_fmt(link.axis)}" '
                 f'pos="{_fmt(link.jpos)}" damping="{float(jo.damping)!r}" '
                 f'stiffness="{float(jo.stiffness)!r}" springref="0.0" frictionloss="0.0" '
                 f'limited="true" range="{_fmt(link.limits)}"/>')

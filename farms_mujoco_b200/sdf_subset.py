@@ -5,9 +5,10 @@ dm_control (``setup_mjcf_xml`` farms_mujoco/simulation/mjcf.py:1174-1512, ``sdf2
 mjcf.py:132-600, called by ``Simulation.from_sdf`` simulation.py:96-124); neither exists in this
 image.  This module covers the subset of that conversion the stepping path can run: links with
 ``<inertial>`` and sphere / capsule / box / cylinder / ellipsoid ``<collision>`` geometry, revolute
-(and fixed) joints forming a tree; link frames may be rotated against the model frame (the joint
-axis is read in the child link's frame, SDF 1.5+).  Meshes, heightmaps, visuals, rotated inertial
-or joint frames and prismatic joints raise ``NotImplementedError`` naming the element.
+/ prismatic (and fixed) joints forming a tree; link, inertial and joint frames may be rotated (the
+joint axis is read in the joint frame, which sits in the child link's, SDF 1.5+).  Meshes,
+heightmaps, ball / universal joints and limitless joints raise ``NotImplementedError`` naming the
+element.
 The arena is the flat ground plane (and the water surface) of ``arena_options``; its own SDF is not
 read.  The MJCF text follows the reference's schema and naming rules through the same emitter as
 the synthetic models (models.py).
@@ -78,13 +79,15 @@ def read_sdf(source):
         mass, ipos, diag, off = 0.0, np.zeros(3), (0.0, 0.0, 0.0), (0.0, 0.0, 0.0)
         if inertial is not None:
             ipose = _pose(inertial)
-            if np.abs(ipose[3:]).max() > 0:
-                raise NotImplementedError(f'link {name}: rotated <inertial> frame')
             mass, ipos = _number(inertial, 'mass'), ipose[:3]
             inertia = inertial.find('inertia')
             if inertia is not None:
-                diag = tuple(_number(inertia, k, 0.0) for k in ('ixx', 'iyy', 'izz'))
-                off = tuple(_number(inertia, k, 0.0) for k in ('ixy', 'ixz', 'iyz'))
+                ixx, iyy, izz, ixy, ixz, iyz = (_number(inertia, k, 0.0) for k in ('ixx', 'iyy', 'izz', 'ixy', 'ixz', 'iyz'))
+                # the tensor is given in the inertial frame: express it in the link's axes
+                rot = quat2mat(np.asarray(euler_xyz2quat(ipose[3:]), dtype=float))
+                tensor = rot @ np.array([[ixx, ixy, ixz], [ixy, iyy, iyz], [ixz, iyz, izz]]) @ rot.T
+                diag = (tensor[0, 0], tensor[1, 1], tensor[2, 2])
+                off = (tensor[0, 1], tensor[0, 2], tensor[1, 2])
         if node.find('visual/geometry/mesh') is not None and node.find('collision') is None:
             raise NotImplementedError(f'link {name}: mesh-only link (no primitive <collision>)')
         geoms = [_geometry(collision, collision.get('name') or f'{name}_collision_{i}')
@@ -109,18 +112,19 @@ def read_sdf(source):
         link.quat = tuple(quat_mul(p_conj, c_quat))
         if kind == 'fixed':
             continue
-        if kind not in ('revolute', 'continuous'):
-            raise NotImplementedError(f'joint {name}: type {kind!r} (revolute and fixed joints only)')
+        if kind not in ('revolute', 'continuous', 'prismatic'):
+            raise NotImplementedError(f'joint {name}: type {kind!r} (revolute, prismatic and fixed joints only)')
         jpose = _pose(node)
-        if np.abs(jpose[3:]).max() > 0:
-            raise NotImplementedError(f'joint {name}: rotated joint frame')
         axis = node.find('axis')
         link.joint = name
+        link.jtype = 'slide' if kind == 'prismatic' else 'hinge'
         link.jpos = tuple(jpose[:3])
-        link.axis = tuple(float(v) for v in axis.find('xyz').text.split())
+        # <xyz> is given in the joint frame, which sits at <pose> in the child link's frame
+        jrot = quat2mat(np.asarray(euler_xyz2quat(jpose[3:]), dtype=float))
+        link.axis = tuple(jrot @ np.array([float(v) for v in axis.find('xyz').text.split()]))
         limit = axis.find('limit')
         link.limits = ((_number(limit, 'lower'), _number(limit, 'upper'))
-                       if limit is not None and kind == 'revolute' else None)
+                       if limit is not None and kind != 'continuous' else None)
     bases = [name for name in links if name not in is_child]
     assert len(bases) == 1, f'one base link expected, found {bases}'
     ordered = []

@@ -108,8 +108,8 @@ class Simulation:
         """From SDF (simulation.py:96-124): the MJCF is built from ``animat_options.sdf`` by
         ``sdf_subset.spec_from_sdf``, the part of ``setup_mjcf_xml`` / ``sdf2mjcf``
         (mjcf.py:132-600, 1174-1512) the stepping path can run -- primitive collision shapes,
-        revolute / fixed joints, link frames rotated or not, the flat arena of ``arena_options``;
-        anything else (meshes, heightmaps, rotated inertial / joint frames, prismatic joints) raises
+        revolute / prismatic / fixed joints, frames rotated or not, the flat arena of ``arena_options``;
+        anything else (meshes, heightmaps, ball / universal joints, joints without limits) raises
         ``NotImplementedError`` naming the element.  The reference's conversion proper needs
         farms_core's SDF reader, trimesh and dm_control.mjcf, none of which exist here."""
         from ..sdf_subset import spec_from_sdf  # pylint: disable=import-outside-toplevel

@@ -117,8 +117,7 @@ def test_branching_sdf():
 
 
 @pytest.mark.parametrize('extra,message', [
-    ('<link name="m"><inertial><pose>0 0 0 0 0 0.3</pose><mass>1</mass></inertial></link>', 'rotated <inertial> frame'),
-    ('<link name="s"/><joint name="p" type="prismatic"><parent>trunk_0</parent><child>s</child></joint>', 'prismatic'),
+    ('<link name="s"/><joint name="p" type="ball"><parent>trunk_0</parent><child>s</child></joint>', "'ball'"),
     ('<link name="h"><collision name="c"><geometry><mesh><uri>a.obj</uri></mesh></geometry></collision></link>', '<mesh>'),
 ])
 def test_unsupported_elements_are_named(extra, message):
@@ -165,3 +164,22 @@ def test_rotated_link_frame_is_the_same_animat(emu_library):
     assert np.abs(joints0[..., :2] - joints1[..., :2]).max() < 1e-4       # joint positions / velocities
     assert np.abs(contacts0[..., :3] - contacts1[..., :3]).max() < 2e-3*np.abs(contacts0[..., :3]).max()
     assert np.abs(contacts0[..., 2]).max() > 0.1
+
+
+def test_prismatic_joint_and_rotated_inertial_and_joint_frames():
+    """A prismatic joint becomes a slide joint; an <inertial> frame turned against the link's gives
+    the tensor in link axes; <xyz> is read in the (turned) joint frame."""
+    extra = """<link name="probe"><pose>0.1 0 0.03 0 0 0</pose>
+      <inertial><pose>0 0 0 0 0 1.5707963267948966</pose><mass>0.01</mass><inertia><ixx>1e-6</ixx><iyy>3e-6</iyy><izz>2e-6</izz></inertia></inertial>
+      <collision name="tip"><geometry><sphere><radius>0.005</radius></sphere></geometry></collision></link>
+    <joint name="extend" type="prismatic"><parent>trunk_1</parent><child>probe</child><pose>0 0 0 0 1.5707963267948966 0</pose>
+      <axis><xyz>0 0 1</xyz><limit><lower>0.0</lower><upper>0.02</upper></limit></axis></joint>"""
+    _, links = sdf_subset.read_sdf(branching_sdf(extra))
+    probe = [link for link in links if link.name == 'probe'][0]
+    assert probe.jtype == 'slide' and probe.parent == 'trunk_1' and probe.limits == (0.0, 0.02)
+    assert np.allclose(probe.inertia, (3e-6, 1e-6, 2e-6), atol=1e-18) and np.allclose(probe.offdiag, 0.0, atol=1e-18)   # x <-> y
+    assert np.allclose(probe.axis, (1.0, 0.0, 0.0), atol=1e-12)                  # joint z turned onto the link's x
+    animat = AnimatOptions(sdf=branching_sdf(extra), spawn=SpawnOptions(pose=[0, 0, 0.05, 0, 0, 0]))
+    spec = sdf_subset.spec_from_sdf(SimulationOptions(), animat, ArenaOptions(ground_height=0.0))
+    model = mjcf_subset.parse_mjcf(spec.mjcf)
+    assert 'type="slide"' in spec.mjcf and model.nv == 10 and list(model.jnt_type).count(2) == 1
