@@ -164,6 +164,34 @@ FB_DEV void m_rot(const float *R, float x, float y, float z, float *o) {
   o[1] = R[3]*x + R[4]*y + R[5]*z;
   o[2] = R[6]*x + R[7]*y + R[8]*z;
 }
+FB_DEV void m_rot_t(const float *R, float x, float y, float z, float *o);
+FB_DEV void v_cross(const float *a, const float *b, float *o);
+FB_DEV float v_normalize3(float *v);
+/* mjc_PlaneCylinder: point k (0: the lowest rim point, 1: the rim point at the other end, 2 / 3: the
+ * two points that make a triangle with it on the lower rim) of a cylinder (axis, x axis, radius,
+ * half length; centre at distance dist0 from the plane along n).  Returns the point's distance from
+ * the plane; p = the point relative to the centre. */
+FB_DEV float fb_plane_cylinder_point(const float *n, const float *axis_in, const float *xaxis, float radius,
+                                     float half, int k, float dist0, float *p) {
+  float axis[3] = {axis_in[0], axis_in[1], axis_in[2]}, vec[3], vec1[3];
+  float prjaxis = n[0]*axis[0] + n[1]*axis[1] + n[2]*axis[2];
+  if (prjaxis > 0.f) { axis[0] = -axis[0]; axis[1] = -axis[1]; axis[2] = -axis[2]; prjaxis = -prjaxis; }
+  for (int i = 0; i < 3; i++) vec[i] = axis[i]*prjaxis - n[i];
+  const float len = sqrtf(vec[0]*vec[0] + vec[1]*vec[1] + vec[2]*vec[2]);
+  if (len >= FB_MINVAL) { for (int i = 0; i < 3; i++) vec[i] *= radius/len; }
+  else { for (int i = 0; i < 3; i++) vec[i] = xaxis[i]*radius; }          /* disk parallel to the plane */
+  const float prjvec = vec[0]*n[0] + vec[1]*n[1] + vec[2]*n[2];
+  for (int i = 0; i < 3; i++) axis[i] *= half;
+  prjaxis *= half;
+  if (k == 0) { for (int i = 0; i < 3; i++) p[i] = vec[i] + axis[i]; return dist0 + prjaxis + prjvec; }
+  if (k == 1) { for (int i = 0; i < 3; i++) p[i] = vec[i] - axis[i]; return dist0 - prjaxis + prjvec; }
+  v_cross(vec, axis, vec1);
+  v_normalize3(vec1);
+  const float sg = k == 2 ? 0.8660254037844386f*radius : -0.8660254037844386f*radius;      /* sqrt(3)/2 */
+  for (int i = 0; i < 3; i++) p[i] = sg*vec1[i] + axis[i] - 0.5f*vec[i];
+  return dist0 + prjaxis - 0.5f*prjvec;
+}
+
 FB_DEV void m_rot_t(const float *R, float x, float y, float z, float *o) {
   o[0] = R[0]*x + R[3]*y + R[6]*z;
   o[1] = R[1]*x + R[4]*y + R[7]*z;
@@ -774,6 +802,16 @@ FB_UNROLL
           m_rot(R, wb[0], wb[1], wb[2], sup);
           dist = cdist + sup[0]*nrm[0] + sup[1]*nrm[1] + sup[2]*nrm[2];
         }
+        if (MI(cand_iscapsule, c) >= 5) {
+          /* cylinder point (mjc_PlaneCylinder) */
+          const Quat gq = {MF(cand_gquat, 4*c), MF(cand_gquat, 4*c+1), MF(cand_gquat, 4*c+2), MF(cand_gquat, 4*c+3)};
+          float Rg[9], axis[3], xaxis[3];
+          q_mat(gq, Rg);
+          m_rot(R, Rg[2], Rg[5], Rg[8], axis);
+          m_rot(R, Rg[0], Rg[3], Rg[6], xaxis);
+          dist = fb_plane_cylinder_point(nrm, axis, xaxis, MF(cand_laxis, 3*c), MF(cand_laxis, 3*c+1),
+                                         MI(cand_iscapsule, c) - 5, cdist, sup);
+        }
         hit = dist < MF(cand_margin, c) - MF(cand_gap, c);
         if ((MI(cand_iscapsule, c) & ~1) == 2) {
           /* box corner (mjc_PlaneBox): only while it is below the box centre along the normal.
@@ -793,7 +831,7 @@ FB_UNROLL
         g.d_con_dist[i] = dist;
         float f[9];
         for (int k = 0; k < 3; k++) {
-          g.d_con_pos[3*i + k] = MI(cand_iscapsule, c) == 4 ? centre[k] + sup[k] - nrm[k]*0.5f*dist
+          g.d_con_pos[3*i + k] = MI(cand_iscapsule, c) >= 4 ? centre[k] + sup[k] - nrm[k]*0.5f*dist
                                                             : centre[k] - nrm[k]*(radius + 0.5f*dist);
           f[k] = nrm[k];
         }

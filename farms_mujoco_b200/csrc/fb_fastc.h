@@ -273,7 +273,19 @@ FB_UNROLL
           dist_ = ((n[0]*rootpos[0] + n[1]*rootpos[1] + n[2]*rootpos[2]) - cr_.pd)
                   + (n[0]*(o[0] + t[0]) + n[1]*(o[1] + t[1]) + n[2]*(o[2] + t[2])) + (n[0]*pofs[0] + n[1]*pofs[1] + n[2]*pofs[2]);
         }
-        const int ell = !LEAN && cr_.iscapsule == 4;
+        if (!LEAN && cr_.iscapsule >= 5) {
+          /* cylinder point (mjc_PlaneCylinder): cr_.laxis = the geom's orientation, radius, pad[0] = half length */
+          const float qx = cr_.laxis[0], qy = cr_.laxis[1], qz = cr_.laxis[2];
+          const Quat gq = {sqrtf(fmaxf(0.f, 1.f - qx*qx - qy*qy - qz*qz)), qx, qy, qz};
+          float Rg[9], axis[3], xaxis[3];
+          q_mat(gq, Rg);
+          m_rot(R, Rg[2], Rg[5], Rg[8], axis);
+          m_rot(R, Rg[0], Rg[3], Rg[6], xaxis);
+          const float cdist = ((n[0]*rootpos[0] + n[1]*rootpos[1] + n[2]*rootpos[2]) - cr_.pd)
+                              + (n[0]*(o[0] + t[0]) + n[1]*(o[1] + t[1]) + n[2]*(o[2] + t[2]));
+          dist_ = fb_plane_cylinder_point(n, axis, xaxis, cr_.radius, cr_.pad[0], cr_.iscapsule - 5, cdist, pofs);
+        }
+        const int ell = !LEAN && cr_.iscapsule >= 4;       /* the contact point moves over the geom: dist_, pofs */
         int hit = (ell ? dist_ : dist) < includemargin;
         if ((cr_.iscapsule & ~1) == 2) {
           /* box corner: only while it is below the box centre along the normal, at most 4 per box */

@@ -125,7 +125,9 @@ struct CandRec {
   int32_t body, cid, iscapsule, pblk;     /* cid: index into the cand_* tables; pblk = FB_NF*(body-1);
                                            * iscapsule: 0 sphere, 1 capsule end, 2 box corner, 3 first corner of a box,
                                            * 4 ellipsoid (laxis = radii; radius, pad[0], pad[1] = x, y, z of the
-                                           * geom's orientation quaternion in the body frame, w >= 0) */
+                                           * geom's orientation quaternion in the body frame, w >= 0),
+                                           * 5..8 cylinder points (laxis = x, y, z of that quaternion; radius,
+                                           * pad[0] = half length) */
   float pn[3], mu;                        /* plane normal (world), friction */
   float lpos[3], radius;                  /* centre relative to the body's joint anchor (body axes) */
   float laxis[3], pd;                     /* capsule axis (body axes) / box centre relative to the anchor; plane offset */
@@ -513,7 +515,7 @@ inline bool fb_build_model(const FbModel *fm, const FbFarms *ff, const FbWaveCon
   /* collision candidates: plane (static, world frame) vs sphere / capsule end */
   std::vector<int32_t> cbody(nc), ccaps(nc);
   std::vector<double> lpos(3*nc), laxis(3*nc), rad(nc), pn(3*nc), pd(nc), cinvw(nc), gquat(4*nc, 0.0);
-  bool any_ellipsoid = false;
+  bool any_ellipsoid = false;      /* ... or cylinder: candidates whose contact point moves over the geom */
   for (int c = 0; c < nc; c++) {
     int g1 = fm->cand_geom1[c], g2 = fm->cand_geom2[c];
     if (fm->geom_bodyid[g1] != 0 || fm->geom_type[g1] != FB_GEOM_PLANE) {
@@ -535,6 +537,18 @@ inline bool fb_build_model(const FbModel *fm, const FbFarms *ff, const FbWaveCon
       const double *sz = fm->geom_size + 3*g2;
       for (int k = 0; k < 3; k++) { lpos[3*c+k] = fm->geom_pos[3*g2+k]; laxis[3*c+k] = sz[k]; pn[3*c+k] = n[k]; }
       rad[c] = std::max(sz[0], std::max(sz[1], sz[2]));
+      const double *gq = fm->geom_quat + 4*g2, sgn = gq[0] < 0 ? -1.0 : 1.0;
+      for (int k = 0; k < 4; k++) gquat[4*c+k] = sgn*gq[k];
+    } else if (end >= 11) {
+      /* cylinder (mjc_PlaneCylinder): kinds 5 .. 8 = the lowest rim point, the rim point at the other
+       * end, the two triangle points of the lower rim; lpos = centre, laxis = (radius, half length),
+       * gquat as for the ellipsoid; rad = the bounding radius (conservative checks only) */
+      if (fm->geom_type[g2] != FB_GEOM_CYLINDER) { out.error = "cand_end >= 11 on a geom that is not a cylinder"; return false; }
+      ccaps[c] = 5 + (end - 11);
+      any_ellipsoid = true;
+      const double *sz = fm->geom_size + 3*g2;
+      for (int k = 0; k < 3; k++) { lpos[3*c+k] = fm->geom_pos[3*g2+k]; laxis[3*c+k] = k < 2 ? sz[k] : 0.0; pn[3*c+k] = n[k]; }
+      rad[c] = std::sqrt(sz[0]*sz[0] + sz[1]*sz[1]);
       const double *gq = fm->geom_quat + 4*g2, sgn = gq[0] < 0 ? -1.0 : 1.0;
       for (int k = 0; k < 4; k++) gquat[4*c+k] = sgn*gq[k];
     } else if (end >= 2) {
@@ -872,6 +886,10 @@ inline bool fb_build_model(const FbModel *fm, const FbFarms *ff, const FbWaveCon
           if (ccaps[c] == 4) {     /* ellipsoid: laxis = radii; the vector part of its orientation (w >= 0) */
             r.radius = (float)gquat[4*c + 1]; r.pad[0] = (float)gquat[4*c + 2]; r.pad[1] = (float)gquat[4*c + 3];
           }
+          if (ccaps[c] >= 5) {     /* cylinder point: laxis = the vector part of its orientation; radius, half length */
+            for (int k = 0; k < 3; k++) r.laxis[k] = (float)gquat[4*c + 1 + k];
+            r.radius = (float)laxis[3*c]; r.pad[0] = (float)laxis[3*c + 1];
+          }
           r.includemargin = (float)(fm->cand_margin[c] - fm->cand_gap[c]);
           r.invw = (float)cinvw[c];
           fc_of[c] = (int)crec.size();
@@ -906,7 +924,7 @@ inline bool fb_build_model(const FbModel *fm, const FbFarms *ff, const FbWaveCon
       for (int b = 0; b < nb; b++) parent[b] = fm->body_parentid[b];
       fb_build_split(parent, X.ok ? FB_SPLIT_MAXW : 1, out.split);
     }
-    X.lean = X.ok && X.jrow_std && !any_ellipsoid;      /* (the LEAN constrained kernel leaves the ellipsoid branch out) */
+    X.lean = X.ok && X.jrow_std && !any_ellipsoid;      /* (the LEAN constrained kernel leaves the ellipsoid / cylinder branches out) */
     for (int b = 1; b < nb; b++) {
       const FastRec &r = rec[b];
       if (r.flags & FT_HAS_JPOS) X.lean = 0;

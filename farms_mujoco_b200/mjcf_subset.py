@@ -232,7 +232,7 @@ class Model:
     # collision candidates (plane vs sphere / capsule end), compile-time
     cand_geom1: np.ndarray = None      # plane geom id
     cand_geom2: np.ndarray = None      # animat geom id
-    cand_end: np.ndarray = None        # 0 sphere centre, +1 / -1 capsule ends, 2..9 box corner (end - 2), 10 ellipsoid
+    cand_end: np.ndarray = None        # 0 sphere centre, +1 / -1 capsule ends, 2..9 box corner (end - 2), 10 ellipsoid, 11..14 cylinder points
     cand_friction: np.ndarray = None   # mixed sliding friction
     cand_solref: np.ndarray = None     # [ncand, 2]
     cand_solimp: np.ndarray = None     # [ncand, 5]
@@ -811,7 +811,7 @@ def _mix_contact_params(model, g1, g2):
 
 
 def _compile_collision_candidates(model):
-    """Enumerate plane-vs-{sphere, capsule end, box corner, ellipsoid} candidates with mixed parameters.
+    """Enumerate plane-vs-{sphere, capsule end, box corner, ellipsoid} candidates (and the four points of a cylinder) with mixed parameters.
 
     Pair filter ``(contype1 & conaffinity2) || (contype2 & conaffinity1)``,
     same-body pairs skipped; the world's planes against tree geoms is what the
@@ -833,9 +833,9 @@ def _compile_collision_candidates(model):
             if model.geom_type[g1] != GEOM_PLANE:
                 raise NotImplementedError(
                     f'arena geom "{model.geom_names[g1]}": only planes collide in this round')
-            if model.geom_type[g2] not in (GEOM_SPHERE, GEOM_CAPSULE, GEOM_BOX, GEOM_ELLIPSOID):
+            if model.geom_type[g2] not in (GEOM_SPHERE, GEOM_CAPSULE, GEOM_BOX, GEOM_ELLIPSOID, GEOM_CYLINDER):
                 raise NotImplementedError(
-                    f'geom "{model.geom_names[g2]}": only sphere/capsule/box/ellipsoid vs plane in this round')
+                    f'geom "{model.geom_names[g2]}": only sphere/capsule/box/ellipsoid/cylinder vs plane in this round')
             if max(model.geom_condim[g1], model.geom_condim[g2]) != 3:
                 raise NotImplementedError('condim must be 3 (mjcf.py:256)')
             friction, solref, solimp = _mix_contact_params(model, g1, g2)
@@ -843,8 +843,10 @@ def _compile_collision_candidates(model):
             gap = max(model.geom_gap[g1], model.geom_gap[g2])
             # plane-box (mjc_PlaneBox): the eight corners in bit order, x fastest
             # plane-ellipsoid (mjc_PlaneConvex with the ellipsoid's support function): one candidate, 10
-            ends = {GEOM_SPHERE: [0], GEOM_CAPSULE: [1, -1], GEOM_BOX: list(range(2, 10)), GEOM_ELLIPSOID: [10]}[
-                int(model.geom_type[g2])]
+            # plane-cylinder (mjc_PlaneCylinder): lowest rim point, the rim point at the other end, and
+            # the two triangle points on the lower rim: 11 .. 14
+            ends = {GEOM_SPHERE: [0], GEOM_CAPSULE: [1, -1], GEOM_BOX: list(range(2, 10)), GEOM_ELLIPSOID: [10],
+                    GEOM_CYLINDER: [11, 12, 13, 14]}[int(model.geom_type[g2])]
             for end in ends:
                 cands.append((g1, g2, end, max(MJ_MINMU, friction[0]), solref, solimp, margin, gap))
     n = len(cands)

@@ -34,7 +34,7 @@ extern "C" {
 
 /* joint / geom enums follow MuJoCo's mjtJoint / mjtGeom numbering */
 enum { FB_JNT_FREE = 0, FB_JNT_BALL = 1, FB_JNT_SLIDE = 2, FB_JNT_HINGE = 3 };
-enum { FB_GEOM_PLANE = 0, FB_GEOM_SPHERE = 2, FB_GEOM_CAPSULE = 3, FB_GEOM_ELLIPSOID = 4, FB_GEOM_BOX = 6 };
+enum { FB_GEOM_PLANE = 0, FB_GEOM_SPHERE = 2, FB_GEOM_CAPSULE = 3, FB_GEOM_ELLIPSOID = 4, FB_GEOM_CYLINDER = 5, FB_GEOM_BOX = 6 };
 
 /* Compiled model: the mjModel subset the path reads.
  * Replaces: mjcf.Physics.from_mjcf_model(mjcf_model), simulation.py:53. */

@@ -357,6 +357,30 @@ static void make_frame(double *f) {
   cross3(f+6, f, f+3);
 }
 
+/* mjc_PlaneCylinder: point k (0: the lowest rim point, 1: the rim point straight above it at the
+ * other end, 2 / 3: the two points that make a triangle with it on the lower rim) of a cylinder
+ * (axis, x axis, radius, half length; centre at distance dist0 from the plane along n).  Returns
+ * the point's distance from the plane; p = the point relative to the centre. */
+static double plane_cylinder_point(const double *n, const double *axis_in, const double *xaxis, double radius,
+                                   double half, int k, double dist0, double *p) {
+  double axis[3] = { axis_in[0], axis_in[1], axis_in[2] }, vec[3], vec1[3];
+  double prjaxis = dot3(n, axis);
+  if (prjaxis > 0) { for (int i = 0; i < 3; i++) axis[i] = -axis[i]; prjaxis = -prjaxis; }
+  for (int i = 0; i < 3; i++) vec[i] = axis[i]*prjaxis - n[i];       /* -normal without its part along the axis */
+  double len = sqrt(dot3(vec, vec));
+  if (len >= MJ_MINVAL) { for (int i = 0; i < 3; i++) vec[i] *= radius/len; }
+  else { for (int i = 0; i < 3; i++) vec[i] = xaxis[i]*radius; }     /* disk parallel to the plane */
+  double prjvec = dot3(vec, n);
+  for (int i = 0; i < 3; i++) axis[i] *= half;
+  prjaxis *= half;
+  if (k == 0) { for (int i = 0; i < 3; i++) p[i] = vec[i] + axis[i]; return dist0 + prjaxis + prjvec; }
+  if (k == 1) { for (int i = 0; i < 3; i++) p[i] = vec[i] - axis[i]; return dist0 - prjaxis + prjvec; }
+  cross3(vec1, vec, axis);
+  normalize3(vec1);
+  for (int i = 0; i < 3; i++) p[i] = (k == 2 ? 1.0 : -1.0)*vec1[i]*radius*sqrt(3.0)/2 + axis[i] - 0.5*vec[i];
+  return dist0 + prjaxis - 0.5*prjvec;
+}
+
 void orc_collision(const FbModel *m, OrcData *d) {
   d->ncon = 0;
   int box_geom = -1, box_count = 0;
@@ -365,6 +389,25 @@ void orc_collision(const FbModel *m, OrcData *d) {
     const double *pm = d->geom_xmat + 9*g1, *pp = d->geom_xpos + 3*g1;
     const double *gm = d->geom_xmat + 9*g2, *gp = d->geom_xpos + 3*g2;
     double n[3] = { pm[2], pm[5], pm[8] };
+    if (end >= 11) {
+      /* plane-cylinder (mjc_PlaneCylinder): up to four contacts, each inside the margin on its own
+       * (the first is the lowest, so MuJoCo's early return never drops another) */
+      const double axis[3] = { gm[2], gm[5], gm[8] }, xaxis[3] = { gm[0], gm[3], gm[6] };
+      double dif[3] = { gp[0]-pp[0], gp[1]-pp[1], gp[2]-pp[2] }, p[3];
+      double cdist = plane_cylinder_point(n, axis, xaxis, m->geom_size[3*g2], m->geom_size[3*g2+1], end - 11,
+                                          dot3(dif, n), p);
+      if (cdist > m->cand_margin[c]) continue;
+      int i = d->ncon++;
+      d->con_cand[i] = c;
+      d->con_dist[i] = cdist;
+      for (int k = 0; k < 3; k++) d->con_pos[3*i+k] = gp[k] + p[k] - n[k]*0.5*cdist;
+      double *f = d->con_frame + 9*i;
+      memcpy(f, n, sizeof(n));
+      f[3] = f[4] = f[5] = 0;
+      make_frame(f);
+      d->con_efc_address[i] = -1;
+      continue;
+    }
     if (end == 10) {
       /* plane-ellipsoid (mjc_PlaneConvex): the support point of the ellipsoid along -normal,
        * centre + R (s o normalize(s o R'(-n))) (mjc_support, ellipsoid case); one contact while the

@@ -419,6 +419,38 @@ def test_con_split_mixed_groups(emu_library):
 
 
 @pytest.mark.parametrize('per_thread,tol', [(True, 2e-5), (False, 5e-4)])
+def test_cylinder_plane_contacts(emu_library, per_thread, tol):
+    """Plane-cylinder contacts (mjc_PlaneCylinder: up to four points per cylinder):
+    SALAMANDER with tilted cylinder feet and a cylinder trunk segment, both constraint paths (and the
+    SPLIT constrained kernel) vs the oracle."""
+    import fastpath_cases
+    import variant_models
+    from farms_mujoco_b200 import mjcf_subset
+    from farms_mujoco_b200.engine import BatchedPhysics
+    spec = variant_models.salamander_cylinder_feet()
+    model = mjcf_subset.parse_mjcf(spec.mjcf)
+    assert sum(e >= 11 for e in model.cand_end.tolist()) == 20          # four feet and a trunk segment x 4 points
+    n, n_steps = 4, 10
+    rng = np.random.default_rng(3)
+    qpos0 = np.tile(model.key_qpos, (n, 1))
+    qpos0[:, 7:] += rng.uniform(-0.1, 0.1, (n, model.nq - 7))
+    qvel0 = rng.uniform(-0.2, 0.2, (n, model.nv))
+    ctrl = rng.uniform(-0.3, 0.3, (n, model.nu))
+    for split in ((False, True) if per_thread else (False,)):
+        physics = BatchedPhysics.from_spec(spec, n, buffer_size=n_steps + 1, library=emu_library)
+        physics.set_constraint_path(per_thread)
+        physics.set_con_split(split)
+        assert not physics.fast_lean
+        physics.reset(qpos0, qvel0)
+        physics.set_ctrl(ctrl)
+        physics.step(n_steps)
+        logs = physics.log_arrays()
+        assert physics.last_pending == n and logs['contacts'][:, :, 12:].any()
+        fastpath_cases.compare_with_oracle(spec, model, physics, qpos0, qvel0, ctrl, range(n), n_steps, tol,
+                                           tol_contacts=max(tol, 2e-4))
+
+
+@pytest.mark.parametrize('per_thread,tol', [(True, 2e-5), (False, 5e-4)])
 def test_ellipsoid_plane_contacts(emu_library, per_thread, tol):
     """Plane-ellipsoid contacts (mjc_PlaneConvex: one contact at the ellipsoid's support point along
     the plane normal): SALAMANDER with rotated ellipsoid feet and an ellipsoid trunk

@@ -728,6 +728,34 @@ def test_con_split_mixed_groups(cuda_library, monkeypatch, block):
     fastpath_cases.check_con_split_mixed_groups(cuda_library)
 
 
+@pytest.mark.parametrize('path,tol', [('fast', 2e-5), ('fast_single_warp', 2e-5), ('team', 1e-3)])
+def test_cylinder_plane_contacts(cuda_library, path, tol):
+    """Plane-cylinder contacts (mjc_PlaneCylinder: up to four points per cylinder): SALAMANDER with
+    tilted cylinder feet and a cylinder trunk segment, against the oracle."""
+    import fastpath_cases
+    import variant_models
+    from farms_mujoco_b200 import mjcf_subset
+    from farms_mujoco_b200.engine import BatchedPhysics
+    spec = variant_models.salamander_cylinder_feet()
+    model = mjcf_subset.parse_mjcf(spec.mjcf)
+    n, n_steps = 70, 10
+    rng = np.random.default_rng(3)
+    qpos0 = np.tile(model.key_qpos, (n, 1))
+    qpos0[:, 7:] += rng.uniform(-0.1, 0.1, (n, model.nq - 7))
+    qvel0 = rng.uniform(-0.2, 0.2, (n, model.nv))
+    ctrl = rng.uniform(-0.3, 0.3, (n, model.nu))
+    physics = BatchedPhysics.from_spec(spec, n, buffer_size=n_steps + 1, library=cuda_library)
+    physics.set_fast_path(path != 'team')
+    physics.set_con_split(path == 'fast')
+    assert not physics.fast_lean
+    physics.reset(qpos0, qvel0)
+    physics.set_ctrl(ctrl)
+    physics.step(n_steps)
+    assert physics.log_arrays()['contacts'][:, :, 12:].any()
+    fastpath_cases.compare_with_oracle(spec, model, physics, qpos0, qvel0, ctrl, [0, 1, 35, n - 1], n_steps, tol,
+                                       tol_contacts=max(tol, 5e-4))
+
+
 @pytest.mark.parametrize('path,tol', [('fast', 2e-5), ('fast_single_warp', 2e-5), ('team', 5e-4)])
 def test_ellipsoid_plane_contacts(cuda_library, path, tol):
     """Plane-ellipsoid contacts (mjc_PlaneConvex: the support point along the plane normal): SALAMANDER

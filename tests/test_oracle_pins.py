@@ -270,6 +270,60 @@ def test_plane_ellipsoid_support_point():
         assert heights.min() >= point @ normal - 1e-12
 
 
+def test_plane_cylinder_points():
+    """Plane-cylinder collision (mjc_PlaneCylinder): every contact point lies on a rim of the
+    cylinder; the first is its lowest point (no sampled surface point is lower), the second the rim
+    point straight along the axis from it, the last two sit on the lower rim 120 degrees either side
+    of the first; each contact is halfway between its point and the plane."""
+    import variant_models
+    from farms_mujoco_b200 import mjcf_subset
+    spec = variant_models.salamander_cylinder_feet()
+    model = mjcf_subset.parse_mjcf(spec.mjcf)
+    orc = OraclePhysics(model)
+    orc.reset(keyframe_id=0)
+    rng = np.random.default_rng(9)
+    qpos = np.array(model.key_qpos)
+    qpos[2] -= 0.02
+    qpos[3:7] = [0.999, 0.02, -0.03, 0.03]
+    qpos[3:7] /= np.linalg.norm(qpos[3:7])
+    qpos[7:] += rng.uniform(-0.1, 0.1, model.nq - 7)
+    orc.data.qpos[:] = qpos
+    orc.forward()
+    n = orc.ncon
+    cand = orc.arrays['con_cand'][:n]
+    ends = np.asarray(model.cand_end)[cand]
+    geoms = np.asarray(model.cand_geom2)[cand]
+    pos = orc.arrays['con_pos'].reshape(-1, 3)[:n]
+    dist = orc.arrays['con_dist'][:n]
+    gpos = orc.arrays['geom_xpos'].reshape(-1, 3)
+    gmat = orc.arrays['geom_xmat'].reshape(-1, 3, 3)
+    normal = np.array([0.0, 0.0, 1.0])
+    checked = 0
+    for g in sorted(set(geoms[ends >= 11].tolist())):
+        radius, half = np.asarray(model.geom_size).reshape(-1, 3)[g][:2]
+        R, centre = gmat[g], gpos[g]
+        points = {}
+        for i in np.flatnonzero((geoms == g) & (ends >= 11)):
+            point = pos[i] + 0.5*dist[i]*normal
+            assert abs(point @ normal - dist[i]) < 1e-12
+            local = R.T @ (point - centre)
+            assert abs(np.hypot(local[0], local[1]) - radius) < 1e-12 and abs(abs(local[2]) - half) < 1e-12    # on a rim
+            points[int(ends[i]) - 11] = local
+        assert 0 in points                                   # the lowest point is always among them
+        u, v = np.meshgrid(np.linspace(0, 2*np.pi, 2000), [-half, half])
+        rim = np.stack([radius*np.cos(u), radius*np.sin(u), v], axis=-1).reshape(-1, 3)
+        assert ((centre + rim @ R.T) @ normal).min() >= (centre + R @ points[0]) @ normal - 1e-9
+        if 1 in points:
+            assert np.allclose(points[1][:2], points[0][:2], atol=1e-12) and np.isclose(points[1][2], -points[0][2])
+        for k in (2, 3):
+            if k in points:
+                assert np.isclose(points[k][2], points[0][2])
+                cosang = points[k][:2] @ points[0][:2]/radius**2
+                assert np.isclose(cosang, -0.5, atol=1e-12)
+                checked += 1
+    assert checked >= 2
+
+
 def test_instrumented_op_count_matches_stock_oracle(tmp_path):
     """oracle/opcount: the oracle compiled with the counting scalar reproduces the stock oracle's
     bits and reports the committed per-step operation counts (profiles/oracle_opcount.json,

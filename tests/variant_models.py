@@ -112,3 +112,21 @@ def salamander_ellipsoid_feet():
     assert x.count(old) == 2, x.count(old)
     x = x.replace(old, 'type="ellipsoid" size="0.05 0.02 0.018" pos="0.04 0.0 0.0" quat="1.0 0.0 0.0 0.0"')
     return dataclasses.replace(spec, name='salamander_ellipsoid', mjcf=x)
+
+
+def salamander_cylinder_feet():
+    """SALAMANDER on the ground with cylinder feet (radius 12 mm, half length 6 mm, tilted) and a
+    cylinder trunk segment lying along the body: plane-cylinder contacts, up to four points per
+    cylinder (mjc_PlaneCylinder)."""
+    spec = models.salamander()
+    x = spec.mjcf
+    foot = 'type="sphere" size="0.01 0.01 0.01" pos="0.0 0.0 -0.04" quat="1.0 0.0 0.0 0.0"'
+    assert x.count(foot) == 8, x.count(foot)
+    x = x.replace(foot, 'type="cylinder" size="0.012 0.006 0.0" pos="0.0 0.0 -0.04" '
+                        'quat="0.9736691213452591 0.1471556949711443 0.02601839493044343 0.17215309088585662"')
+    old = ('type="capsule" size="0.020000000000000004 0.04 0.0" pos="0.04 0.0 0.0" '
+           'quat="0.7071067811865476 0.0 0.7071067811865475 0.0"')
+    assert x.count(old) == 2, x.count(old)
+    x = x.replace(old, 'type="cylinder" size="0.02 0.04 0.0" pos="0.04 0.0 0.0" '
+                       'quat="0.7071067811865476 0.0 0.7071067811865475 0.0"')
+    return dataclasses.replace(spec, name='salamander_cylinder', mjcf=x)
