@@ -183,3 +183,26 @@ def test_prismatic_joint_and_rotated_inertial_and_joint_frames():
     spec = sdf_subset.spec_from_sdf(SimulationOptions(), animat, ArenaOptions(ground_height=0.0))
     model = mjcf_subset.parse_mjcf(spec.mjcf)
     assert 'type="slide"' in spec.mjcf and model.nv == 10 and list(model.jnt_type).count(2) == 1
+
+
+def test_from_sdf_with_cylinder_and_ellipsoid_collisions(emu_library):
+    """SDF <cylinder> and <ellipsoid> collisions reach the contact pipeline: a skid (cylinder lying
+    across the trunk, welded on) and an ellipsoid tail pad carry part of the walker's weight."""
+    from farms_mujoco_b200.simulation.simulation import Simulation
+    extra = """<link name="skid"><pose>0.05 0 -0.045 0 0 0</pose><inertial><mass>0.005</mass><inertia><ixx>1e-7</ixx><iyy>1e-7</iyy><izz>1e-7</izz></inertia></inertial>
+      <collision name="skid_c"><pose>0 0 0 1.5707963267948966 0 0</pose><geometry><cylinder><radius>0.008</radius><length>0.05</length></cylinder></geometry></collision></link>
+    <joint name="skid_mount" type="fixed"><parent>trunk_0</parent><child>skid</child></joint>
+    <link name="pad"><pose>0.2 0 -0.04 0 0 0</pose><inertial><mass>0.005</mass><inertia><ixx>1e-7</ixx><iyy>1e-7</iyy><izz>1e-7</izz></inertia></inertial>
+      <collision name="pad_c"><pose>0 0 0 0 0.2 0</pose><geometry><ellipsoid><radii>0.02 0.01 0.012</radii></ellipsoid></geometry></collision></link>
+    <joint name="pad_mount" type="fixed"><parent>trunk_1</parent><child>pad</child></joint>"""
+    animat = AnimatOptions(sdf=branching_sdf(extra), spawn=SpawnOptions(pose=[0, 0, 0.06, 0, 0, 0]),
+                           control=ControlOptions(motors=[MotorOptions(joint_name='spine', gains=[0.5, 1e-3])]))
+    sim = Simulation.from_sdf(SimulationOptions(timestep=1e-3, n_iterations=80), animat, ArenaOptions(ground_height=0.0),
+                              n_envs=2, library=emu_library)
+    assert 'type="cylinder"' in sim._mjcf_model and 'type="ellipsoid"' in sim._mjcf_model
+    sim.run()
+    contacts = sim.task.data.sensors.contacts.array
+    assert np.isfinite(contacts).all()
+    # contact sensors in link order (depth first): trunk_0, trunk_1, pad, leg_L, leg_R, skid
+    load = np.abs(contacts[..., 2]).max(axis=tuple(range(contacts.ndim - 2)))
+    assert load.shape == (6,) and load[2] > 0.5 and load[5] > 0.5, load
