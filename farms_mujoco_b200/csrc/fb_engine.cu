@@ -26,6 +26,7 @@
 
 #include "fb_fastc.h"
 #include "fb_cpg.h"
+#include "fb_drag.h"
 
 #ifndef FB_HOST_EMU
 #include <cuda_runtime.h>
@@ -226,6 +227,12 @@ fb_fastc_split_kernel(const __grid_constant__ FbFastConSplitParams Q) {
   st.con_split_setup(Q.split, extra + 4*BLK + lane);
   const int coop = BLK == 32 && P.m.X.coop_io && (grp + 1)*BLK <= P.n_envs;
   st.run_con_split(coop, lane);
+}
+
+/* Stand-alone drag operator (fb_drag_forces, fb_drag.h): one thread = one link row */
+__global__ void __launch_bounds__(128) fb_drag_forces_kernel(const FbDragArgs A) {
+  const int i = blockIdx.x*blockDim.x + threadIdx.x;
+  if (i < A.n) fb_drag_row(A, i);
 }
 
 /* ring row `row` of every environment -> dense [n_envs][row_floats] (the reference's row
@@ -1955,6 +1962,53 @@ int fb_fast_split(FbHandle *h) {
 #endif
   return h->hm.split.nwarps > 1 ? h->hm.split.nwarps : 0;
 }
+/* drag_forces (swimming/drag.pyx:152-268) as a stand-alone device operator, see include/farms_b200.h */
+int fb_drag_forces(int device, int n, const double *links, const double *coefficients, const double *mass,
+                   const double *height, const double *density, double surface, const double *water_velocity,
+                   double viscosity, double gravity, int use_buoyancy, double *xfrc, int32_t *applied) {
+  if (n < 0 || (n > 0 && (!links || !coefficients || !mass || !height || !density || !water_velocity || !xfrc || !applied)))
+    return fail("fb_drag_forces: null argument");
+  if (n == 0) return 0;
+  FbDragArgs A;
+  A.surface = surface; A.viscosity = viscosity; A.gravity = gravity;
+  for (int k = 0; k < 3; k++) A.wvel[k] = water_velocity[k];
+  A.use_buoyancy = use_buoyancy != 0; A.n = n;
+#ifdef FB_HOST_EMU
+  (void)device;
+  std::vector<int> flags((size_t)n);
+  A.links = links; A.coef = coefficients; A.mass = mass; A.height = height; A.density = density;
+  A.xfrc = xfrc; A.applied = flags.data();
+  for (int i = 0; i < n; i++) { fb_drag_row(A, i); applied[i] = flags[(size_t)i]; }
+  return 0;
+#else
+  if (cudaSetDevice(device) != cudaSuccess) return fail(std::string("fb_drag_forces: ") + dev_error());
+  const size_t nn = (size_t)n;
+  const size_t bytes_in = nn*(20 + 6 + 3)*sizeof(double), bytes_out = nn*6*sizeof(double) + nn*sizeof(int);
+  void *din = nullptr, *dout = nullptr;
+  if (dev_alloc(&din, bytes_in) || dev_alloc(&dout, bytes_out)) { if (din) dev_free(din); return fail("fb_drag_forces: device allocation failed"); }
+  double *d_links = static_cast<double *>(din), *d_coef = d_links + 20*nn, *d_mass = d_coef + 6*nn,
+         *d_height = d_mass + nn, *d_density = d_height + nn;
+  double *d_xfrc = static_cast<double *>(dout);
+  int *d_applied = reinterpret_cast<int *>(d_xfrc + 6*nn);
+  cudaError_t ce = cudaMemcpy(d_links, links, 20*nn*sizeof(double), cudaMemcpyHostToDevice);
+  if (ce == cudaSuccess) ce = cudaMemcpy(d_coef, coefficients, 6*nn*sizeof(double), cudaMemcpyHostToDevice);
+  if (ce == cudaSuccess) ce = cudaMemcpy(d_mass, mass, nn*sizeof(double), cudaMemcpyHostToDevice);
+  if (ce == cudaSuccess) ce = cudaMemcpy(d_height, height, nn*sizeof(double), cudaMemcpyHostToDevice);
+  if (ce == cudaSuccess) ce = cudaMemcpy(d_density, density, nn*sizeof(double), cudaMemcpyHostToDevice);
+  if (ce == cudaSuccess) ce = cudaMemcpy(d_xfrc, xfrc, 6*nn*sizeof(double), cudaMemcpyHostToDevice);     /* rows that are not applied keep their values */
+  if (ce == cudaSuccess) {
+    A.links = d_links; A.coef = d_coef; A.mass = d_mass; A.height = d_height; A.density = d_density;
+    A.xfrc = d_xfrc; A.applied = d_applied;
+    fb_drag_forces_kernel<<<(n + 127)/128, 128>>>(A);
+    ce = cudaGetLastError();
+  }
+  if (ce == cudaSuccess) ce = cudaMemcpy(xfrc, d_xfrc, 6*nn*sizeof(double), cudaMemcpyDeviceToHost);
+  if (ce == cudaSuccess) ce = cudaMemcpy(applied, d_applied, nn*sizeof(int), cudaMemcpyDeviceToHost);
+  dev_free(din); dev_free(dout);
+  return ce == cudaSuccess ? 0 : fail(std::string("fb_drag_forces: ") + cudaGetErrorString(ce));
+#endif
+}
+
 /* SPLIT variant of the constrained per-thread kernel (ground-contact batches) */
 int fb_set_con_split(FbHandle *h, int enable) {
   if (!h) return fail("fb_set_con_split: null handle");

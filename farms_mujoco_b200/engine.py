@@ -86,6 +86,9 @@ ABI_SYMBOLS = {
     'fb_fast_lean': (ct.c_int, [_H]),
     'fb_last_pending': (ct.c_int, [_H, ct.POINTER(ct.c_int)]),
     'fb_measure_fp32_peak': (ct.c_int, [ct.c_int, ct.POINTER(ct.c_double)]),
+    'fb_drag_forces': (ct.c_int, [ct.c_int, ct.c_int, cabi.c_double_p, cabi.c_double_p, cabi.c_double_p,
+                                  cabi.c_double_p, cabi.c_double_p, ct.c_double, cabi.c_double_p,
+                                  ct.c_double, ct.c_double, ct.c_int, cabi.c_double_p, ct.POINTER(ct.c_int32)]),
     'fb_team_lanes': (ct.c_int, [_H]),
     'fb_smem_bytes_per_env': (ct.c_int, [_H]),
     'fb_device_ptr_stream': (ct.c_int, [_H, ct.POINTER(ct.c_void_p)]),
@@ -125,6 +128,32 @@ def measure_fp32_peak(device=0, library=None):
     if lib.fb_measure_fp32_peak(int(device), ct.byref(out)) != 0:
         raise EngineError(lib.fb_last_error().decode())
     return float(out.value)
+
+
+def drag_forces_rows(links, coefficients, mass, height, density, surface, water_velocity, viscosity,
+                     gravity, use_buoyancy, xfrc, device=0, library=None):
+    """``fb_drag_forces``: the reference's ``drag_forces`` (drag.pyx:152-268) on ``n`` link rows at
+    once on the device, float64.  ``links`` [n, 20], ``coefficients`` [n, 2, 3] (or [n, 6]), ``mass``
+    / ``height`` / ``density`` [n]; ``xfrc`` [n, 6] float64 C-contiguous is updated in place where the
+    link is at or below the surface.  Returns the boolean ``applied`` [n] (drag_forces' return)."""
+    lib = load_library(library)
+    links = np.ascontiguousarray(links, dtype=np.float64)
+    n = links.shape[0]
+    if links.shape != (n, 20):
+        raise ValueError('links must be [n, 20]')
+    coef = np.ascontiguousarray(np.asarray(coefficients, dtype=np.float64).reshape(n, 6))
+    per = [np.ascontiguousarray(np.broadcast_to(np.asarray(a, dtype=np.float64), (n,))) for a in (mass, height, density)]
+    wvel = np.ascontiguousarray(water_velocity, dtype=np.float64).reshape(3)
+    if not (isinstance(xfrc, np.ndarray) and xfrc.dtype == np.float64 and xfrc.flags.c_contiguous
+            and xfrc.shape == (n, 6)):
+        raise ValueError('xfrc must be a C-contiguous float64 [n, 6] array (updated in place)')
+    applied = np.zeros(n, dtype=np.int32)
+    dp = lambda a: a.ctypes.data_as(cabi.c_double_p)
+    if lib.fb_drag_forces(int(device), int(n), dp(links), dp(coef), dp(per[0]), dp(per[1]), dp(per[2]),
+                          float(surface), dp(wvel), float(viscosity), float(gravity), int(bool(use_buoyancy)),
+                          dp(xfrc), applied.ctypes.data_as(ct.POINTER(ct.c_int32))) != 0:
+        raise EngineError(lib.fb_last_error().decode())
+    return applied.astype(bool)
 
 
 class _DeviceArray:

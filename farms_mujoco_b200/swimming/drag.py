@@ -4,11 +4,34 @@ The resistive-force model (``drag_forces`` drag.pyx:152-268, ``compute_buoyancy`
 :111-149) and the downstream applier that writes ``xfrc_applied`` are
 fused into the CUDA step: per swimming link, every step, for every environment, without
 leaving the SM.  The classes below keep the reference's construction / stepping protocol
-and forward the knobs to the engine.  There is deliberately no host ``drag_forces``: the
-arithmetic lives in csrc/fb_fast.h (pass_accel) and csrc/fb_device.h (write_log) only.
+and forward the knobs to the engine.  ``drag_forces`` below is the reference's operator of that
+name for callers that hold link rows of their own: it runs on the device too (``fb_drag_forces``,
+float64); there is no host arithmetic.
 """
 
 import numpy as np
+
+
+def drag_forces(iteration, data_links, links_index, data_xfrc, xfrc_index, coefficients, z3, z4,
+                water, mass, height, density, gravity, use_buoyancy):
+    """Drag swimming (drag.pyx:152-268, same arguments; ``z3`` / ``z4`` are the reference's
+    scratch arrays and are not used).  Forces and torques of link ``links_index`` at ``iteration``
+    are stored into ``data_xfrc.array[iteration, xfrc_index]`` in the CoM frame; returns whether
+    the link was at or below the water surface.  One row through ``fb_drag_forces``; for many rows
+    at once see ``engine.drag_forces_rows``."""
+    # pylint: disable=too-many-arguments
+    del z3, z4
+    from ..engine import drag_forces_rows  # pylint: disable=import-outside-toplevel
+    row = np.array(data_links.array[iteration, links_index], dtype=np.float64).reshape(1, 20)
+    out = np.array(data_xfrc.array[iteration, xfrc_index, 0:6], dtype=np.float64).reshape(1, 6)
+    pos = row[0, 0:3]
+    applied = drag_forces_rows(
+        row, np.asarray(coefficients, dtype=np.float64).reshape(1, 6), mass, height, density,
+        water.surface(pos[0], pos[1]), water.velocity(pos[0], pos[1], pos[2]),
+        water.viscosity(pos[0], pos[1], pos[2]), gravity, use_buoyancy, out)
+    if applied[0]:
+        data_xfrc.array[iteration, xfrc_index, 0:6] = out[0]
+    return bool(applied[0])
 
 
 class WaterProperties:

@@ -362,6 +362,19 @@ int fb_con_split(FbHandle *h);
 int fb_fast_slim(FbHandle *h);
 int fb_last_pending(FbHandle *h, int *count);
 
+/* drag_forces (swimming/drag.pyx:152-268; the operator SwimmingHandler.step calls per swimming link,
+ * drag.pyx:389-411) as a stand-alone device operator on n link rows at once, float64 like the
+ * reference.  fb_step computes the same forces fused into the step (fp32); this entry point exists
+ * for callers that hold link rows of their own.  links [n][20] (the farms links row, SI), coefficients
+ * [n][6] (linear x y z, angular x y z), mass / height / density [n] (drag.pyx:353-385), the water
+ * surface height, velocity [3] and viscosity, gravity (-9.81 in the reference's call) and the
+ * buoyancy flag.  xfrc [n][6] receives force and torque in the CoM frame where the link is at or
+ * below the surface and is left untouched where it is above (drag.pyx:192-194); applied [n] says
+ * which.  Host pointers; synchronous. */
+int fb_drag_forces(int device, int n, const double *links, const double *coefficients, const double *mass,
+                   const double *height, const double *density, double surface, const double *water_velocity,
+                   double viscosity, double gravity, int use_buoyancy, double *xfrc, int32_t *applied);
+
 /* introspection */
 /* Measured FP32 (FFMA, non-tensor) throughput of `device` in TFLOP/s: the denominator bench.py
  * quotes the step kernels' arithmetic against (nothing in the reference). */

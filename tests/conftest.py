@@ -28,7 +28,7 @@ def emu_library():
     fp32 arithmetic and indexing of the kernels can be checked without a GPU.
     It is test infrastructure: the product only ever loads libfarmsb200.so.
     """
-    sources = [os.path.join(CSRC, f) for f in ('fb_engine.cu', 'fb_device.h', 'fb_fast.h', 'fb_fastc.h', 'fb_model.h')]
+    sources = [os.path.join(CSRC, f) for f in ('fb_engine.cu', 'fb_device.h', 'fb_fast.h', 'fb_fastc.h', 'fb_model.h', 'fb_cpg.h', 'fb_drag.h')]
     sources.append(os.path.join(ROOT, 'include', 'farms_b200.h'))
     stale = (not os.path.exists(EMU_LIB)
              or any(os.path.getmtime(s) > os.path.getmtime(EMU_LIB) for s in sources))

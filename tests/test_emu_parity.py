@@ -480,3 +480,31 @@ def test_ellipsoid_plane_contacts(emu_library, per_thread, tol):
         assert physics.last_pending == n and logs['contacts'][:, :, 12:].any()      # the feet's sensors
         fastpath_cases.compare_with_oracle(spec, model, physics, qpos0, qvel0, ctrl, range(n), n_steps, tol,
                                            tol_contacts=max(tol, 2e-4))
+
+
+def test_drag_operator(emu_library):
+    """fb_drag_forces (the stand-alone drag_forces of drag.pyx:152-268, float64) against the oracle:
+    1e-12 relative (same formulae, other order of the quaternion products)."""
+    from drag_cases import check_operator
+    assert check_operator(emu_library) < 1e-12
+
+
+def test_drag_forces_reference_signature(emu_library, monkeypatch):
+    """swimming.drag.drag_forces with the reference's argument list on an AnimatData row."""
+    from farms_mujoco_b200 import engine
+    from farms_mujoco_b200.swimming.drag import drag_forces, WaterProperties
+    from drag_cases import make_rows, oracle_answer
+    monkeypatch.setattr(engine, 'DEFAULT_LIBRARY', emu_library)
+    case = make_rows(6)
+
+    class _Arr:      # the two attributes drag_forces touches
+        def __init__(self, array):
+            self.array = array
+    links, xfrc = _Arr(case['links'][None].copy()), _Arr(np.full((1, 6, 6), 0.25))
+    water = WaterProperties(case['surface'], 1000.0, case['wvel'], case['viscosity'])
+    ref, ref_applied = oracle_answer(case, True, xfrc.array[0])
+    for i in range(6):
+        got = drag_forces(0, links, i, xfrc, i, case['coef'][i], None, None, water, case['mass'][i],
+                          case['height'][i], case['density'][i], case['gravity'], True)
+        assert got == ref_applied[i]
+    assert np.abs(xfrc.array[0] - ref).max() < 1e-12

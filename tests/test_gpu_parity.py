@@ -783,3 +783,10 @@ def test_ellipsoid_plane_contacts(cuda_library, path, tol):
     assert physics.log_arrays()['contacts'][:, :, 12:].any()
     fastpath_cases.compare_with_oracle(spec, model, physics, qpos0, qvel0, ctrl, [0, 1, 35, n - 1], n_steps, tol,
                                        tol_contacts=max(tol, 5e-4))
+
+
+@pytest.mark.gpu
+def test_drag_operator(cuda_library):
+    """fb_drag_forces on the device (float64) against the oracle's drag_forces: 1e-12 relative."""
+    from drag_cases import check_operator
+    assert check_operator(cuda_library, n=4099) < 1e-12
