@@ -177,12 +177,18 @@ class BatchedPhysics:
 
     def __init__(self, model, n_envs, links_names, joints_names, contacts_names=(), xfrc_names=(),
                  animat_options=None, arena_options=None, units=None, buffer_size=1, device=0,
-                 team_lanes=0, library=None):
+                 team_lanes=0, library=None, log_stride=1):
         # pylint: disable=too-many-arguments,too-many-locals
         self.lib = load_library(library)
         self.model = model
         self.n_envs = int(n_envs)
         self.buffer_size = int(buffer_size)
+        # Physics steps per logged iteration (num_sub_steps x n_sub_steps of the reference's loop,
+        # task.py:168-186, 348-369).  The device writes a row after every physics step into a ring
+        # of buffer_size*log_stride rows; the reference's row `i` (the state at the full step of
+        # iteration i) is device row i*log_stride, which is what the accessors below return.
+        self.log_stride = max(1, int(log_stride))
+        self.device_ring = self.buffer_size*self.log_stride
         self.units = units if units is not None else SimulationUnitScaling()
         names = AnimatData.from_sensors_names(
             timestep=model.timestep, buffer_size=1, links=list(links_names),
@@ -197,7 +203,7 @@ class BatchedPhysics:
         handle = _H()
         self._handle = None
         self._check(self.lib.fb_create(self._cmodel.byref(), self._cfarms.byref(), self.n_envs,
-                                       int(device), self.buffer_size, int(team_lanes),
+                                       int(device), self.device_ring, int(team_lanes),
                                        ct.byref(handle)))
         self._handle = handle
         self._cpg_n_osc = 0
@@ -451,14 +457,14 @@ class BatchedPhysics:
             xfrc=(log.xfrc_dev, len(names.xfrc.names), sc.xfrc_size, log.xfrc_vec),
         )
         out = {}
-        ring, pad = self.buffer_size, int(log.env_pad)
+        ring, pad, stride = self.buffer_size, int(log.env_pad), self.log_stride
         for kind, (ptr, n_items, cols, vec) in shapes.items():
             if n_items == 0:
                 shape = (self.n_envs, ring, 0, cols)
                 out[kind] = np.zeros(shape if env is None else shape[1:], dtype=np.float32)
                 continue
             # device layout [ring][items][cols/V][env_pad][V] (include/farms_b200.h, FbLogView)
-            raw = self._read(ptr, (ring, n_items, cols//vec, pad, vec))
+            raw = self._read(ptr, (ring*stride, n_items, cols//vec, pad, vec))[::stride]
             if env is None:
                 arr = raw[:, :, :, :self.n_envs, :].transpose(3, 0, 1, 2, 4)
                 out[kind] = np.ascontiguousarray(arr).reshape(self.n_envs, ring, n_items, cols)
@@ -467,10 +473,12 @@ class BatchedPhysics:
                 out[kind] = np.ascontiguousarray(arr).reshape(ring, n_items, cols)
         return out
 
-    def log_row(self, kind, index):
+    def log_row(self, kind, index, latest=False):
         """Ring row ``index`` of one log kind for every environment: ``[n_envs, n_items,
         n_cols]`` float32 (what ``physics2data`` wrote into ``data.sensors.<kind>.array
-        [index]`` in the reference, physics.py:527-545)."""
+        [index]`` in the reference, physics.py:527-545).  ``latest``: the row of the last physics
+        step instead (``index`` ignored) -- what the reference's sensor refresh reads on a
+        sub-step, where the row it writes to is not the one the state belongs to."""
         log, names = self._log, self.names
         ptr, n_items, cols, vec = dict(
             links=(log.links_dev, len(names.links.names), sc.link_size, log.links_vec),
@@ -481,7 +489,8 @@ class BatchedPhysics:
         if n_items == 0:
             return np.zeros((self.n_envs, 0, cols), dtype=np.float32)
         pad = int(log.env_pad)
-        base = _ptr(ptr) + 4*int(index)*n_items*cols*pad
+        device_row = self.iteration % self.device_ring if latest else int(index)*self.log_stride
+        base = _ptr(ptr) + 4*device_row*n_items*cols*pad
         raw = self._read(base, (n_items, cols//vec, pad, vec))
         arr = raw[:, :, :self.n_envs, :].transpose(2, 0, 1, 3)
         return np.ascontiguousarray(arr).reshape(self.n_envs, n_items, cols)
@@ -494,6 +503,20 @@ class BatchedPhysics:
                 timestep=self.model.timestep, buffer_size=self.buffer_size,
                 links=names.links.names, joints=names.joints.names,
                 contacts=names.contacts.names, xfrc=names.xfrc.names)
+        if self.log_stride > 1:
+            # fb_export_farms writes every device row: export those, keep the full-step rows
+            full = AnimatData.from_sensors_names(
+                timestep=self.model.timestep, buffer_size=self.device_ring,
+                links=names.links.names, joints=names.joints.names,
+                contacts=names.contacts.names, xfrc=names.xfrc.names)
+            stride, self.log_stride = self.log_stride, 1
+            try:
+                self.export_farms(env, full)
+            finally:
+                self.log_stride = stride
+            for kind in ('links', 'joints', 'contacts', 'xfrc'):
+                getattr(data.sensors, kind).array[...] = getattr(full.sensors, kind).array[::stride]
+            return data
         ptrs = []
         for arr in (data.sensors.links.array, data.sensors.joints.array,
                     data.sensors.contacts.array, data.sensors.xfrc.array):
@@ -555,7 +578,9 @@ class BatchedPhysics:
         environment as float32 ``[n_rows, n_envs, n_items, n_cols]`` on the host: the streamed
         full-log export (fb_export_rows).  ``out``: a preallocated (pinned) torch tensor / array
         of that many float32 to fill.  ``out[r, e]`` is the reference's
-        ``data.sensors.<kind>.array[row0 + r]`` of environment ``e`` (task.py:158)."""
+        ``data.sensors.<kind>.array[row0 + r]`` of environment ``e`` (task.py:158).  Rows are
+        device rows: with ``log_stride`` > 1 the reference's row ``i`` is device row
+        ``i*log_stride``."""
         names = self.names
         n_items, cols, code = dict(
             links=(len(names.links.names), sc.link_size, 0), joints=(len(names.joints.names), sc.joint_size, 1),

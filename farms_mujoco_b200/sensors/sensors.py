@@ -16,4 +16,4 @@ def cycontacts2data(physics, iteration, data, geompair2data=None, meters=1.0, ne
     compiled into the engine's tables (FbFarms.cand_sensor, units) at construction."""
     del geompair2data, meters, newtons
     if data.array.shape[2]:
-        data.array[:, iteration] = physics.log_row('contacts', iteration)
+        data.array[:, iteration] = physics.log_row('contacts', iteration, physics.log_stride > 1)

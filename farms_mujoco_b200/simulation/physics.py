@@ -228,8 +228,16 @@ def physics2data(physics, iteration, data, maps, units, links_only=False):
     """
     del maps, units
     sensors = data.sensors
-    sensors.links.array[:, iteration] = physics.log_row('links', iteration)
+    # With several physics steps per iteration (log_stride > 1) the refresh reads the state the
+    # physics holds NOW, as the reference does: on a full step that is device row
+    # iteration*log_stride, on a sub-step (links_only) it is a row between two iterations.
+    latest = physics.log_stride > 1
+    sensors.links.array[:, iteration] = physics.log_row('links', iteration, latest)
+    if sensors.xfrc.array.shape[2]:
+        # the drag forces of this row (drag.pyx:389-411 computes them from the links row that was
+        # just refreshed, in the same before_step): the device wrote them with the row
+        sensors.xfrc.array[:, iteration] = physics.log_row('xfrc', iteration, latest)
     if not links_only:
-        sensors.joints.array[:, iteration] = physics.log_row('joints', iteration)
+        sensors.joints.array[:, iteration] = physics.log_row('joints', iteration, latest)
         if sensors.contacts.array.shape[2]:
-            sensors.contacts.array[:, iteration] = physics.log_row('contacts', iteration)
+            sensors.contacts.array[:, iteration] = physics.log_row('contacts', iteration, latest)

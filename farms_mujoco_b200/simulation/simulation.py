@@ -53,15 +53,12 @@ class Simulation:
             'device', 'team_lanes', 'library', 'qpos0', 'qvel0'))
         env_kwargs = extract_sub_dict(kwargs, ('control_timestep', 'n_sub_steps', 'flat_observation'))
         self.n_sub_steps = int(env_kwargs.get('n_sub_steps', 1) or 1)
-        # The device writes log row (physics step count) % ring after EVERY physics step
-        # (fb_device.h: fb_run_env); the reference logs on full steps only (task.py:168-186,
-        # row = iteration % buffer_size with iteration advancing once per `substeps` physics
-        # steps).  Until the row index is decoupled from the step count the two only agree for
-        # one physics step per iteration, so anything else is refused rather than logged wrongly.
-        if self.n_sub_steps != 1 or int(self.options.num_sub_steps or 1) != 1:
-            raise NotImplementedError(
-                'num_sub_steps / n_sub_steps > 1: the batched engine logs one row per physics step; '
-                'run with num_sub_steps=1 and the sub-step as timestep')
+        # The device writes a log row after EVERY physics step (fb_device.h: fb_run_env); the
+        # reference logs on full steps only (task.py:168-186: row = iteration % buffer_size, the
+        # iteration advancing once per `substeps` env.steps of `n_sub_steps` physics steps each).
+        # The device ring therefore holds log_stride = substeps*n_sub_steps rows per iteration and
+        # the reference's row i is device row i*log_stride (engine.BatchedPhysics.log_stride).
+        self.log_stride = self.n_sub_steps*max(1, int(self.options.num_sub_steps or 1))
         self.chunk = int(kwargs.pop('chunk', 0))
         assert self.options.headless, 'the viewer is outside the batched path'
         self._qpos0, self._qvel0 = engine_kwargs.pop('qpos0', None), engine_kwargs.pop('qvel0', None)
@@ -74,7 +71,13 @@ class Simulation:
             links_names=engine_kwargs.pop('links_names'), joints_names=engine_kwargs.pop('joints_names'),
             contacts_names=engine_kwargs.pop('contacts_names', ()), xfrc_names=engine_kwargs.pop('xfrc_names', ()),
             animat_options=animat_options, arena_options=engine_kwargs.pop('arena_options', None),
-            units=self.options.units, buffer_size=buffer_size, **engine_kwargs)
+            units=self.options.units, buffer_size=buffer_size, log_stride=self.log_stride, **engine_kwargs)
+        if self.n_sub_steps > 1 and len(self.physics.tables.swim_links_index):
+            # dm_control runs n_sub_steps physics steps inside one env.step with xfrc_applied held
+            # (no before_step in between); the fused drag is recomputed every physics step
+            raise NotImplementedError(
+                'n_sub_steps > 1 with swimming links: the engine refreshes the drag forces every '
+                'physics step, the reference holds them across n_sub_steps; use num_sub_steps')
         self.task = ExperimentTask(
             base_link=base_link,
             n_iterations=self.options.n_iterations,
@@ -82,6 +85,7 @@ class Simulation:
             units=self.options.units,
             substeps=self.options.num_sub_steps,
             restart=False,
+            device_control=self.log_stride == 1,
             **kwargs,
         )
         self._reset_next_step = True
@@ -195,8 +199,15 @@ class Simulation:
     def sync_data(self):
         """Device log -> ``task.data`` (every row written so far).  The per-iteration loop fills
         ``task.data`` as it goes; after fused launches this brings the host copy up to date."""
-        logs = self.physics.log_arrays()
         sensors = self.task.data.sensors
+        if self.log_stride > 1:
+            # never fused: the loop filled the rows as the reference does (including what its
+            # sub-step refreshes leave behind); only the row of the state after the last step
+            # is missing, when the buffer still has one
+            if self.task.iteration < self.task.n_iterations:
+                self.task.update_sensors(self.physics)
+            return
+        logs = self.physics.log_arrays()
         for kind in ('links', 'joints', 'contacts', 'xfrc'):
             target = getattr(sensors, kind).array
             if target.size:

@@ -60,6 +60,10 @@ class ExperimentTask:
             'muscles': {},
         }
         self.device_controller = False      # the controller runs inside the step kernel
+        # On-device controllers advance with every physics step; with several physics steps per
+        # iteration the reference holds ctrl between full steps (task.py:184-186), so the host
+        # evaluates the controller then (Simulation passes device_control=False).
+        self._device_control = bool(kwargs.pop('device_control', True))
         assert not kwargs, kwargs
         assert self._extras['hfield'] is None, 'height fields are outside the batched path'
 
@@ -174,7 +178,7 @@ class ExperimentTask:
                                  if t in jntname2actid[jnt_name]]
             if disabled:
                 physics.set_actuator_forcerange(disabled, True, [0.0, 0.0])
-        if hasattr(self._controller, 'device_parameters') and not self._callbacks_need_ctrl():
+        if self._device_control and hasattr(self._controller, 'device_parameters') and not self._callbacks_need_ctrl():
             params = self._controller.device_parameters()
             acts = [ctrl_names.index(f'actuator_position_{j}') for j in params['joints']]
             phase = np.broadcast_to(np.asarray(params['env_phase'], dtype=float), (physics.n_envs,))
@@ -182,7 +186,7 @@ class ExperimentTask:
             physics.set_wave_controller(acts, params['amplitude'], params['frequency'],
                                         params['phase_lag'], params.get('offset'))
             self.device_controller = True
-        if callable(getattr(self._controller, 'device_cpg', None)) and not self._callbacks_need_ctrl():
+        if self._device_control and callable(getattr(self._controller, 'device_cpg', None)) and not self._callbacks_need_ctrl():
             # coupled-oscillator network integrated on the device (fb_set_cpg): position targets and
             # torque commands (x units.torques, task.py:332) written inside every launch
             names = {ControlType.POSITION: 'actuator_position_{}', ControlType.TORQUE: 'actuator_torque_{}'}

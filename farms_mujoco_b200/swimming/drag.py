@@ -88,7 +88,7 @@ class SwimmingHandler:
         on the device; copy them to ``data.sensors.xfrc`` as the reference's step leaves
         them (drag.pyx:265-267)."""
         if (self.drag or self.sph) and self.xfrc.array.shape[2]:
-            self.xfrc.array[:, iteration] = self.physics.log_row('xfrc', iteration)
+            self.xfrc.array[:, iteration] = self.physics.log_row('xfrc', iteration, self.physics.log_stride > 1)
 
     def set_water_velocity(self, velocity):
         """Set water velocity (drag.pyx:417-419)"""

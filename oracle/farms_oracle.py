@@ -270,6 +270,60 @@ def reference_rollout(physics, spec, tables, n_iterations, controller=None, unit
     return data, states
 
 
+def reference_rollout_substeps(physics, spec, tables, n_iterations, substeps, timestep, controller=None,
+                               units=None, swimming=True, n_sub_steps=1, qpos0=None, qvel0=None):
+    """``Simulation.run`` with ``num_sub_steps = substeps`` physics steps per iteration, followed
+    literally: ``before_step`` (task.py:168-186: full_step = not sim_iteration % substeps, the
+    sensors refreshed on full steps and -- links only -- on sub-steps because the swimming callback
+    has ``substep=True``, the callback every sub-step, control on full steps with time =
+    iteration*timestep), ``n_sub_steps`` x ``mj_step``, ``after_step`` (task.py:348-369: iteration
+    advances when ``(sim_iteration + 1) % substeps == 0``, i.e. BEFORE the last sub-step of an
+    iteration, so that sub-step's links refresh lands in the next row and, for substeps >= 3, the
+    earlier ones overwrite the links of the current row).  ``timestep`` is the iteration's
+    (``options.timestep``); the model's is ``timestep/substeps`` (mjcf.py:1189).  The first
+    ``env.step`` is the reset, so ``n_iterations*substeps - 1`` steps are taken; the row of the
+    state after the last one is added when the buffer still has it."""
+    # pylint: disable=too-many-arguments,too-many-locals
+    units = units if units is not None else SimulationUnitScaling()
+    model = physics.model
+    data = AnimatData.from_sensors_names(
+        timestep=timestep, buffer_size=n_iterations, links=spec.links_names,
+        joints=spec.joints_names, contacts=spec.contacts_names, xfrc=spec.xfrc_names)
+    maps = make_maps(model, data)
+    handler = SwimmingHandlerOracle(data, tables)
+    swim = swimming and len(tables.swim_links_index)
+    physics.reset(keyframe_id=0)
+    if qpos0 is not None:
+        physics.data.qpos[:] = qpos0
+        if qvel0 is not None:
+            physics.data.qvel[:] = qvel0
+        physics.forward()
+    iteration, sim_iteration = 0, 0
+    for _ in range(1, n_iterations*substeps):
+        assert iteration < n_iterations
+        full_step = not sim_iteration % substeps
+        index = iteration % n_iterations
+        if full_step or swim:
+            physics2data(physics, index, data, maps, units, links_only=not full_step)
+        if swim:
+            handler.step(index)
+            apply_xfrc(physics, data, index, maps['sensors'], units)
+        if full_step and controller is not None:
+            ctrl = controller(iteration, iteration*timestep)
+            if ctrl is not None:
+                physics.data.ctrl[:] = ctrl
+        for _ in range(n_sub_steps):
+            physics.step()
+        sim_iteration += 1
+        if not (sim_iteration + 1) % substeps:
+            iteration += 1
+    if iteration < n_iterations:
+        physics2data(physics, iteration, data, maps, units)
+        if swim:
+            handler.step(iteration)
+    return data, (physics.data.qpos.copy(), physics.data.qvel.copy())
+
+
 # --------------------------------------------------------------------------
 # the same loop without the interpreter (oracle/farms_loop.c) -- the CPU baseline
 # --------------------------------------------------------------------------

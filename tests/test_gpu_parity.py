@@ -790,3 +790,18 @@ def test_drag_operator(cuda_library):
     """fb_drag_forces on the device (float64) against the oracle's drag_forces: 1e-12 relative."""
     from drag_cases import check_operator
     assert check_operator(cuda_library, n=4099) < 1e-12
+
+
+@pytest.mark.gpu
+def test_sub_steps_log_full_steps_only(cuda_library):
+    """num_sub_steps = 2 through the Simulation layer on the device: host rows = the reference's
+    full-step rows (device row 2i), against the oracle's literal replay of the sub-stepped loop."""
+    from test_simulation_loop import _substep_sim, _substep_check, HostWave
+    from farms_mujoco_b200.models import travelling_wave_parameters
+    n_it, phase = 8, [0.3, 1.1, 2.0]
+    spec = models.salamander(swimming=True, n_iterations=n_it)
+    wave = travelling_wave_parameters(spec)
+    sim = _substep_sim(spec, 2, cuda_library, n_envs=3, controller=HostWave(*wave, phase))
+    sim.run()
+    assert sim.physics.iteration == 2*n_it - 1 and sim.iteration == n_it
+    _substep_check(sim, spec, n_it, 2, phase, wave)

@@ -224,18 +224,94 @@ def test_open_loop_host_controller_is_fused(emu_library):
         assert np.array_equal(arr, logs[1][0][kind]), kind
 
 
-def test_sub_steps_are_refused_not_mislogged(emu_library):
-    """num_sub_steps / n_sub_steps > 1: the device ring is indexed by the physics step count, the
-    reference's by the iteration (task.py:156-186); the layer refuses instead of logging rows the
-    reference would not."""
+def _substep_sim(spec, substeps, library, n_envs=2, **kwargs):
     import dataclasses
+    opts = dataclasses.replace(spec.simulation_options, num_sub_steps=substeps,
+                               timestep=spec.simulation_options.timestep*substeps)
+    return Simulation(mjcf_model=spec.mjcf, base_link=spec.base_link, simulation_options=opts,
+                      animat_options=spec.animat_options, arena_options=spec.arena_options, n_envs=n_envs,
+                      links_names=spec.links_names, joints_names=spec.joints_names,
+                      contacts_names=spec.contacts_names, xfrc_names=spec.xfrc_names, library=library, **kwargs)
+
+
+def _substep_check(sim, spec, n_it, substeps, phase, wave, n_sub_steps=1, tol=2e-5):
+    from oracle.oracle import OraclePhysics
+    from oracle import farms_oracle as fo
+    model = mjcf_subset.parse_mjcf(spec.mjcf)
+    joints, amp, freq, lag = wave
+    acts = [model.actuator_id(f'actuator_position_{j}') for j in joints]
+    for env in range(sim.physics.n_envs):
+        def controller(iteration, time, env=env):
+            ctrl = np.zeros(model.nu)
+            ctrl[acts] = amp*np.sin(2*np.pi*freq*time - lag + phase[env])
+            return ctrl
+        data, (ref_q, _) = fo.reference_rollout_substeps(
+            OraclePhysics(model), spec, sim.physics.tables, n_it, substeps,
+            timestep=sim.options.timestep, controller=controller, n_sub_steps=n_sub_steps)
+        for kind in ('links', 'joints', 'contacts', 'xfrc'):
+            ours = getattr(sim.task.data.sensors, kind).array[env]
+            ref = getattr(data.sensors, kind).array
+            assert ours.shape == ref.shape
+            assert log_error(kind, ours, ref) < tol, kind
+        assert scaled_error(sim.physics.qpos[env], ref_q) < tol
+
+
+def test_sub_steps_log_full_steps_only(emu_library):
+    """num_sub_steps = 2: the device ring holds a row per physics step, the host rows
+    are the reference's -- the state at every full step, row 0 the reset state, control held
+    between full steps, drag refreshed every sub-step -- against the oracle's literal replay of
+    task.py:168-186, 348-369."""
+    n_it, phase = 6, [0.3, 1.1]
+    spec = models.salamander(swimming=True, n_iterations=n_it)
+    wave = travelling_wave_parameters(spec)
+    sim = _substep_sim(spec, 2, emu_library, controller=HostWave(*wave, phase))
+    assert sim.physics.log_stride == 2 and sim.physics.device_ring == 2*n_it
+    sim.run()
+    assert sim.task.sim_iterations == 2*n_it and sim.physics.iteration == 2*n_it - 1
+    assert sim.iteration == n_it
+    _substep_check(sim, spec, n_it, 2, phase, wave)
+    # the device-side accessors return the same rows
+    logs = sim.physics.log_arrays()
+    assert logs['links'].shape[1] == n_it
+    assert np.array_equal(logs['joints'][:, 2], sim.task.data.sensors.joints.array[:, 2].astype(np.float32))
+    exported = sim.physics.export_farms(1)
+    assert np.array_equal(exported.sensors.links.array[3], logs['links'][1, 3].astype(np.float64))
+
+
+def test_sub_steps_with_a_substep_callback(emu_library):
+    """num_sub_steps = 3 and a callback with substep=True: the links (and the drag forces computed
+    from them) are refreshed on every sub-step into the row the reference's bookkeeping points at
+    -- the current row on the first sub-step, the next row on the last (task.py:358-360) -- and
+    the device controller is replaced by the host's, evaluated on full steps."""
+    n_it, phase = 5, [0.0, 0.7]
+    spec = models.salamander(swimming=True, n_iterations=n_it)
+    wave = travelling_wave_parameters(spec)
+    ctl = TravellingWaveController(*wave, env_phase=phase)
+    cb = Recorder(substep=True)
+    sim = _substep_sim(spec, 3, emu_library, controller=ctl, callbacks=[cb])
+    sim.run()
+    assert sim.task.device_controller is False and sim.task.substeps_links
+    assert [c for c in cb.calls if c[0] == 'before'][:4] == [('before', 0), ('before', 0), ('before', 1), ('before', 1)]
+    _substep_check(sim, spec, n_it, 3, phase, wave)
+    links = sim.task.data.sensors.links.array
+    joints = sim.task.data.sensors.joints.array
+    # row 1: joints from the full step (3 physics steps), links from the sub-step after it (4)
+    assert np.allclose(joints[:, 1, :, 0], sim.physics.log_row('joints', 1)[:, :, 0])
+    assert not np.allclose(links[:, 1], sim.physics.log_row('links', 1))
+
+
+def test_dm_control_n_sub_steps(emu_library):
+    """n_sub_steps = 2 (dm_control's Environment: two physics steps inside one env.step) on the
+    ground; with swimming links it is refused (the reference holds the drag forces across them)."""
     import pytest
-    spec = models.swimmer8(n_iterations=6)
+    n_it, phase = 40, [0.2, 0.9]
+    spec = models.salamander(n_iterations=n_it)
+    wave = travelling_wave_parameters(spec)
+    sim = Simulation.from_spec(spec, n_envs=2, controller=HostWave(*wave, phase), n_sub_steps=2,
+                               library=emu_library)
+    sim.run()
+    assert sim.physics.iteration == 2*(n_it - 1)
+    _substep_check(sim, spec, n_it, 1, phase, wave, n_sub_steps=2, tol=1e-4)
+    assert sim.task.data.sensors.contacts.array.any()
     with pytest.raises(NotImplementedError):
-        Simulation.from_spec(spec, n_envs=2, library=emu_library, n_sub_steps=2)
-    opts = dataclasses.replace(spec.simulation_options, num_sub_steps=2)
-    with pytest.raises(NotImplementedError):
-        Simulation(mjcf_model=spec.mjcf, base_link=spec.base_link, simulation_options=opts,
-                   animat_options=spec.animat_options, arena_options=spec.arena_options, n_envs=2,
-                   links_names=spec.links_names, joints_names=spec.joints_names,
-                   contacts_names=spec.contacts_names, xfrc_names=spec.xfrc_names, library=emu_library)
+        Simulation.from_spec(models.swimmer8(n_iterations=4), n_envs=1, n_sub_steps=2, library=emu_library)
