@@ -797,6 +797,7 @@ def test_sub_steps_log_full_steps_only(cuda_library):
     """num_sub_steps = 2 through the Simulation layer on the device: host rows = the reference's
     full-step rows (device row 2i), against the oracle's literal replay of the sub-stepped loop."""
     from test_simulation_loop import _substep_sim, _substep_check, HostWave
+    from farms_mujoco_b200 import models
     from farms_mujoco_b200.models import travelling_wave_parameters
     n_it, phase = 8, [0.3, 1.1, 2.0]
     spec = models.salamander(swimming=True, n_iterations=n_it)
