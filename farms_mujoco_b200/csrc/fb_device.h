@@ -81,6 +81,7 @@ struct EnvPtrs {
   float *d_con_dist, *d_con_pos, *d_con_frame, *d_con_force;
   /* solver scratch */
   float *J3;     /* [3*maxcon][nv] contact-frame rows of the point Jacobian */
+  float *Hd;     /* [nv][nv] dense Newton Hessian, models with explicit <pair>s only (behind J3) */
   float *efc;    /* [5][maxefc]: aref, D, res, jp, force */
   float *prod3;  /* [2][3*maxcon] */
   /* log rows of this step: element (item, col) of a kind with C columns stored in vectors of
@@ -284,6 +285,7 @@ template <int TEAM> struct FbStep {
   unsigned mask;
   float comx, comy, comz;
   int ncon, nlim;
+  int npair_act;   /* active contacts of explicit pairs (two-body rows) */
 
   FB_MEM FbStep(const DevModel &m_, float *s_, int *si_, const EnvPtrs &g_, int lane_, int base_,
                 unsigned mask_)
@@ -770,7 +772,7 @@ FB_UNROLL
     }
     nlim = (int)(T::sum(mask, cnt) + 0.5f);
     /* plane vs sphere / capsule end; compact in candidate order */
-    int n = 0;
+    int n = 0, npair = 0;
     for (int c0 = 0; c0 < m.ncand; c0 += TEAM) {
       int c = c0 + lane;
       int hit = 0;
@@ -787,6 +789,19 @@ FB_UNROLL
         radius = MF(cand_radius, c);
         float cdist = centre[0]*nrm[0] + centre[1]*nrm[1] + centre[2]*nrm[2] - MF(cand_pd, c);
         dist = cdist - radius;
+        if (MI(cand_iscapsule, c) == 9) {
+          /* explicit <pair>, sphere-sphere (mjc_SphereSphere): the other sphere (geom1) sits on body
+           * cand_body1 at cand_pn, radius cand_pd; the normal runs from it to this one */
+          const int b1 = MI(cand_body1, c);
+          float R1[9], t1[3];
+          q_mat(body_quat(b1), R1);
+          m_rot(R1, nrm[0], nrm[1], nrm[2], t1);
+          float d[3] = {centre[0] - (xpos[b1] + t1[0]), centre[1] - (xpos[nb + b1] + t1[1]), centre[2] - (xpos[2*nb + b1] + t1[2])};
+          const float len = sqrtf(d[0]*d[0] + d[1]*d[1] + d[2]*d[2]);
+          if (len < FB_MINVAL) { nrm[0] = 1.f; nrm[1] = 0.f; nrm[2] = 0.f; }
+          else { nrm[0] = d[0]/len; nrm[1] = d[1]/len; nrm[2] = d[2]/len; }
+          dist = len - MF(cand_pd, c) - radius;
+        }
         sup[0] = -nrm[0]*radius; sup[1] = -nrm[1]*radius; sup[2] = -nrm[2]*radius;
         if (MI(cand_iscapsule, c) == 4) {
           /* ellipsoid (mjc_PlaneConvex): support point along -normal, R Rg (s o normalize(s o (R Rg)'(-n))) */
@@ -802,7 +817,7 @@ FB_UNROLL
           m_rot(R, wb[0], wb[1], wb[2], sup);
           dist = cdist + sup[0]*nrm[0] + sup[1]*nrm[1] + sup[2]*nrm[2];
         }
-        if (MI(cand_iscapsule, c) >= 5) {
+        if (MI(cand_iscapsule, c) >= 5 && MI(cand_iscapsule, c) <= 8) {
           /* cylinder point (mjc_PlaneCylinder) */
           const Quat gq = {MF(cand_gquat, 4*c), MF(cand_gquat, 4*c+1), MF(cand_gquat, 4*c+2), MF(cand_gquat, 4*c+3)};
           float Rg[9], axis[3], xaxis[3];
@@ -824,6 +839,7 @@ FB_UNROLL
         }
       }
       unsigned bits = T::ballot(mask, base, hit);
+      npair += FB_POPC(T::ballot(mask, base, hit && MI(cand_iscapsule, c) == 9));
       if (hit) {
         int i = n + FB_POPC(bits & ((1u << lane) - 1u));
         con_cand[i] = c;
@@ -855,6 +871,7 @@ FB_UNROLL
       n += FB_POPC(bits);
     }
     ncon = n;
+    npair_act = npair;
     if (lane == 0) *g.d_ncon = n;
     sync();
   }
@@ -866,16 +883,21 @@ FB_UNROLL
     const int *con_cand = si + m.L.con_cand;
     float *aref = g.efc, *D = g.efc + m.maxefc;
     for (int i = 0; i < ncon; i++) {
-      int c = con_cand[i], b = MI(cand_body, c);
+      int c = con_cand[i], b = MI(cand_body, c), b1 = MI(cand_body1, c);
       float off[3] = {g.d_con_pos[3*i] - comx, g.d_con_pos[3*i+1] - comy, g.d_con_pos[3*i+2] - comz};
       float f[9];
       for (int k = 0; k < 9; k++) f[k] = g.d_con_frame[9*i + k];
       for (int v = lane; v < nv; v += TEAM) {
         float j0 = 0.f, j1 = 0.f, j2 = 0.f;
-        if ((unsigned)MI(body_ancmask, b*m.nmaskw + (v >> 5)) >> (v & 31) & 1u) {
+        /* mj_jacDifPair: the point's velocity on geom2's body minus the one on geom1's (the world for
+         * plane candidates); dofs above both bodies cancel */
+        const int in2 = (int)((unsigned)MI(body_ancmask, b*m.nmaskw + (v >> 5)) >> (v & 31) & 1u);
+        const int in1 = b1 > 0 ? (int)((unsigned)MI(body_ancmask, b1*m.nmaskw + (v >> 5)) >> (v & 31) & 1u) : 0;
+        if (in2 != in1) {
           float ang[3] = {cdof[v], cdof[nv + v], cdof[2*nv + v]}, cr[3];
           v_cross(ang, off, cr);
-          float lx = cdof[3*nv + v] + cr[0], ly = cdof[4*nv + v] + cr[1], lz = cdof[5*nv + v] + cr[2];
+          const float sg = in2 ? 1.f : -1.f;
+          float lx = sg*(cdof[3*nv + v] + cr[0]), ly = sg*(cdof[4*nv + v] + cr[1]), lz = sg*(cdof[5*nv + v] + cr[2]);
           j0 = f[0]*lx + f[1]*ly + f[2]*lz;
           j1 = f[3]*lx + f[4]*ly + f[5]*lz;
           j2 = f[6]*lx + f[7]*ly + f[8]*lz;
@@ -1018,38 +1040,106 @@ FB_UNROLL
        * (limits: one dof; plane contacts: the chain of the touching body), so H has exactly the
        * tree sparsity of M: it is assembled in M's layout and factored by the same scheduled
        * sparse L'DL (leaves first), no dense 33x33 matrix. */
-      for (int e = lane; e < m.nM; e += TEAM) {
-        const int u = MI(ent_i, e), v = MI(ent_j, e);      /* v is u or an ancestor of u */
-        float h = qM[e];
-        if (u == v) {
-          int j = MI(dof_jnt, u);
-          if (MI(jnt_type, j) != FB_JNT_FREE) {
-            if (res[2*j] < 0.f) h += D[2*j];
-            if (res[2*j+1] < 0.f) h += D[2*j+1];
+      if (npair_act > 0) {
+        /* A contact of an explicit <pair> is active: its rows live on the chains of two bodies, so
+         * J'DJ couples dofs that are not ancestors of one another and H loses the tree sparsity.
+         * Dense H (lower triangle) behind J3, Cholesky in place, two triangular solves. */
+        float *H = g.Hd;
+        for (int idx = lane; idx < nv*nv; idx += TEAM) H[idx] = 0.f;
+        sync();
+        for (int e = lane; e < m.nM; e += TEAM) {
+          const int u = MI(ent_i, e), v = MI(ent_j, e);      /* v is u or an ancestor of u: v <= u */
+          float h = qM[e];
+          if (u == v) {
+            int j = MI(dof_jnt, u);
+            if (MI(jnt_type, j) != FB_JNT_FREE) {
+              if (res[2*j] < 0.f) h += D[2*j];
+              if (res[2*j+1] < 0.f) h += D[2*j+1];
+            }
           }
+          H[(u > v ? u : v)*nv + (u > v ? v : u)] = h;
         }
-        for (int i = 0; i < ncon; i++) {
-          int c = con_cand[i], b = MI(cand_body, c);
-          /* u on the chain of b implies v on it too */
-          if (!(((unsigned)MI(body_ancmask, b*m.nmaskw + (u >> 5)) >> (u & 31)) & 1u)) continue;
-          int r = 2*nj + 4*i;
-          float d = D[r], mu = MF(cand_friction, c);
-          float nu_ = g.J3[(3*i)*nv + u], nv_ = g.J3[(3*i)*nv + v];
-          float t1u = mu*g.J3[(3*i+1)*nv + u], t1v = mu*g.J3[(3*i+1)*nv + v];
-          float t2u = mu*g.J3[(3*i+2)*nv + u], t2v = mu*g.J3[(3*i+2)*nv + v];
-          if (res[r] < 0.f) h += d*(nu_ + t1u)*(nv_ + t1v);
-          if (res[r+1] < 0.f) h += d*(nu_ - t1u)*(nv_ - t1v);
-          if (res[r+2] < 0.f) h += d*(nu_ + t2u)*(nv_ + t2v);
-          if (res[r+3] < 0.f) h += d*(nu_ - t2u)*(nv_ - t2v);
+        sync();
+        for (int idx = lane; idx < nv*nv; idx += TEAM) {
+          const int u = idx/nv, v = idx - u*nv;
+          if (v > u) continue;
+          float h = H[idx];
+          for (int i = 0; i < ncon; i++) {
+            const int r = 2*nj + 4*i;
+            const float d = D[r], mu = MF(cand_friction, con_cand[i]);
+            const float nu_ = g.J3[(3*i)*nv + u], nv_ = g.J3[(3*i)*nv + v];
+            const float t1u = mu*g.J3[(3*i+1)*nv + u], t1v = mu*g.J3[(3*i+1)*nv + v];
+            const float t2u = mu*g.J3[(3*i+2)*nv + u], t2v = mu*g.J3[(3*i+2)*nv + v];
+            if (res[r] < 0.f) h += d*(nu_ + t1u)*(nv_ + t1v);
+            if (res[r+1] < 0.f) h += d*(nu_ - t1u)*(nv_ - t1v);
+            if (res[r+2] < 0.f) h += d*(nu_ + t2u)*(nv_ + t2v);
+            if (res[r+3] < 0.f) h += d*(nu_ - t2u)*(nv_ - t2v);
+          }
+          H[idx] = h;
         }
-        qLD[e] = h;
+        sync();
+        for (int k = 0; k < nv; k++) {
+          const float piv = sqrtf(H[k*nv + k]), inv = 1.0f/piv;
+          for (int i = k + 1 + lane; i < nv; i += TEAM) H[i*nv + k] *= inv;
+          sync();
+          if (lane == 0) H[k*nv + k] = piv;
+          for (int i = k + 1 + lane; i < nv; i += TEAM) {
+            const float lik = H[i*nv + k];
+            for (int j = k + 1; j <= i; j++) H[i*nv + j] -= lik*H[j*nv + k];
+          }
+          sync();
+        }
+        /* p = -H^-1 grad: L y = -grad, L' p = y */
+        for (int v = lane; v < nv; v += TEAM) p[v] = -grad[v];
+        sync();
+        for (int k = 0; k < nv; k++) {
+          const float yk = p[k]/H[k*nv + k];
+          sync();
+          if (lane == 0) p[k] = yk;
+          for (int i = k + 1 + lane; i < nv; i += TEAM) p[i] -= H[i*nv + k]*yk;
+          sync();
+        }
+        for (int k = nv - 1; k >= 0; k--) {
+          const float xk = p[k]/H[k*nv + k];
+          sync();
+          if (lane == 0) p[k] = xk;
+          for (int i = lane; i < k; i += TEAM) p[i] -= H[k*nv + i]*xk;
+          sync();
+        }
+      } else {
+        for (int e = lane; e < m.nM; e += TEAM) {
+          const int u = MI(ent_i, e), v = MI(ent_j, e);      /* v is u or an ancestor of u */
+          float h = qM[e];
+          if (u == v) {
+            int j = MI(dof_jnt, u);
+            if (MI(jnt_type, j) != FB_JNT_FREE) {
+              if (res[2*j] < 0.f) h += D[2*j];
+              if (res[2*j+1] < 0.f) h += D[2*j+1];
+            }
+          }
+          for (int i = 0; i < ncon; i++) {
+            int c = con_cand[i], b = MI(cand_body, c);
+            /* u on the chain of b implies v on it too */
+            if (!(((unsigned)MI(body_ancmask, b*m.nmaskw + (u >> 5)) >> (u & 31)) & 1u)) continue;
+            int r = 2*nj + 4*i;
+            float d = D[r], mu = MF(cand_friction, c);
+            float nu_ = g.J3[(3*i)*nv + u], nv_ = g.J3[(3*i)*nv + v];
+            float t1u = mu*g.J3[(3*i+1)*nv + u], t1v = mu*g.J3[(3*i+1)*nv + v];
+            float t2u = mu*g.J3[(3*i+2)*nv + u], t2v = mu*g.J3[(3*i+2)*nv + v];
+            if (res[r] < 0.f) h += d*(nu_ + t1u)*(nv_ + t1v);
+            if (res[r+1] < 0.f) h += d*(nu_ - t1u)*(nv_ - t1v);
+            if (res[r+2] < 0.f) h += d*(nu_ + t2u)*(nv_ + t2v);
+            if (res[r+3] < 0.f) h += d*(nu_ - t2u)*(nv_ - t2v);
+          }
+          qLD[e] = h;
+        }
+        sync();
+        eliminate();
+        /* p = -H^-1 grad */
+        for (int v = lane; v < nv; v += TEAM) p[v] = -grad[v];
+        sync();
+        solve_ld(p, tmp2);
       }
-      sync();
-      eliminate();
-      /* p = -H^-1 grad */
-      for (int v = lane; v < nv; v += TEAM) p[v] = -grad[v];
-      sync();
-      solve_ld(p, tmp2);
       /* exact line search on phi'(alpha) = g0 + alpha pMp + sum D jp min(0, res + alpha jp) */
       rows_apply(p, jp);
       mul_m(p, tmp2);
@@ -1429,6 +1519,18 @@ FB_DEV float *fb_log_row(float *base, long long it, long long floats_per_row, lo
   return base + it*floats_per_row*env_pad + env*vec;
 }
 
+/* per-environment floats behind FbParams::J3: the contact Jacobians and, for models with explicit
+ * <pair>s, the dense Hessian of the Newton step */
+#ifdef FB_HOST_EMU
+static inline
+#else
+__host__ __device__ __forceinline__
+#endif
+size_t fb_j3_stride(const DevModel &m) {
+  const size_t mc = m.maxcon > 0 ? m.maxcon : 1;
+  return 3*mc*m.nv + (m.n_pair > 0 ? (size_t)m.nv*m.nv : 0);
+}
+
 FB_DEV EnvPtrs fb_env_ptrs(const FbParams &P, int env) {
   const DevModel &m = P.m;
   EnvPtrs g;
@@ -1445,7 +1547,7 @@ FB_DEV EnvPtrs fb_env_ptrs(const FbParams &P, int env) {
   g.d_ncon = P.d_ncon + env; g.d_con_cand = P.d_con_cand + e*mc;
   g.d_con_dist = P.d_con_dist + e*mc; g.d_con_pos = P.d_con_pos + e*3*mc;
   g.d_con_frame = P.d_con_frame + e*9*mc; g.d_con_force = P.d_con_force + e*3*mc;
-  g.J3 = P.J3 + e*3*mc*m.nv; g.efc = P.efc + e*5*m.maxefc; g.prod3 = P.prod3 + e*6*mc;
+  g.J3 = P.J3 + e*fb_j3_stride(m); g.Hd = g.J3 + (size_t)3*mc*m.nv; g.efc = P.efc + e*5*m.maxefc; g.prod3 = P.prod3 + e*6*mc;
   g.row_links = g.row_joints = g.row_contacts = g.row_xfrc = 0;
   g.ev_links = P.env_pad*FB_VEC_LINKS; g.ev_joints = P.env_pad*FB_VEC_JOINTS;
   g.ev_contacts = P.env_pad*FB_VEC_CONTACTS; g.ev_xfrc = P.env_pad*FB_VEC_XFRC;

@@ -39,6 +39,7 @@ struct DevOffsets {
   int col_start, col_ent, col_dof;   /* per dof: entries (e, d) of descendants d whose row holds it */
   int st_pivstart, st_piv, fop_start, fop, sop_start, sop;   /* elimination schedule */
   int cand_body, cand_iscapsule, cand_sensor;
+  int cand_body1;  /* int [ncand] the body of geom1: 0 (the world) for plane candidates, the first sphere's body for pair candidates (kind 9) */
   int act_jnt, act_ctrllimited, act_forcelimited;
   int link_body, fj_qposadr, fj_dofadr, fj_jntid, fj_actpos, fj_actvel, fj_acttrq, xfrc_body,
       swim_link, swim_xfrc, body_xfrcrow, wc_act;
@@ -182,6 +183,7 @@ struct DevModel {
   int nround_anc, nround_sub; /* pointer-jumping rounds (ancestors), doubling rounds (subtrees) */    /* stages of the scheduled sparse factor/solve; lanes it was built for */
   int n_links, n_joints, n_contacts, n_xfrc, n_swim, n_wc;
   int maxcon, maxefc, npack; /* npack = nv*(nv+1)/2 */
+  int n_pair;                /* candidates of explicit <pair>s (two-body rows: team kernel only, dense Newton Hessian) */
   int solver_iterations, any_damping, any_stiffness, any_limit;
   int col_jpos, col_jvel, col_jtrq, col_jlim;
   int link_cols, joint_cols, contact_cols, xfrc_cols;
@@ -513,11 +515,32 @@ inline bool fb_build_model(const FbModel *fm, const FbFarms *ff, const FbWaveCon
   }
 
   /* collision candidates: plane (static, world frame) vs sphere / capsule end */
-  std::vector<int32_t> cbody(nc), ccaps(nc);
+  std::vector<int32_t> cbody(nc), ccaps(nc), cbody1(nc, 0);
   std::vector<double> lpos(3*nc), laxis(3*nc), rad(nc), pn(3*nc), pd(nc), cinvw(nc), gquat(4*nc, 0.0);
+  m.n_pair = 0;
   bool any_ellipsoid = false;      /* ... or cylinder: candidates whose contact point moves over the geom */
   for (int c = 0; c < nc; c++) {
     int g1 = fm->cand_geom1[c], g2 = fm->cand_geom2[c];
+    if (fm->cand_end[c] == 20) {
+      /* explicit <pair>, sphere-sphere (mjc_SphereSphere): kind 9.  cand_body / lpos / rad describe
+       * geom2 as for a plane candidate; geom1 travels in the plane's slots: cand_body1 = its body,
+       * pn = its centre in that body's frame, pd = its radius.  Rows of such a contact live on the
+       * chains of TWO bodies: the model runs on the team kernel, whose Newton step takes a dense
+       * Hessian while one of them is active (fb_device.h). */
+      if (fm->geom_type[g1] != FB_GEOM_SPHERE || fm->geom_type[g2] != FB_GEOM_SPHERE ||
+          fm->geom_bodyid[g1] < 1 || fm->geom_bodyid[g2] < 1 || fm->geom_bodyid[g1] == fm->geom_bodyid[g2]) {
+        out.error = "pair candidates (cand_end 20) must be spheres on two different bodies of the tree"; return false;
+      }
+      cbody[c] = fm->geom_bodyid[g2]; cbody1[c] = fm->geom_bodyid[g1];
+      ccaps[c] = 9;
+      gquat[4*c] = 1.0;
+      for (int k = 0; k < 3; k++) { lpos[3*c+k] = fm->geom_pos[3*g2+k]; laxis[3*c+k] = 0.0; pn[3*c+k] = fm->geom_pos[3*g1+k]; }
+      rad[c] = fm->geom_size[3*g2];
+      pd[c] = fm->geom_size[3*g1];
+      cinvw[c] = fm->body_invweight0[2*cbody1[c]] + fm->body_invweight0[2*cbody[c]];
+      m.n_pair++;
+      continue;
+    }
     if (fm->geom_bodyid[g1] != 0 || fm->geom_type[g1] != FB_GEOM_PLANE) {
       out.error = "collision candidates must be world planes vs tree geoms"; return false;
     }
@@ -584,6 +607,7 @@ inline bool fb_build_model(const FbModel *fm, const FbFarms *ff, const FbWaveCon
     cinvw[c] = fm->body_invweight0[2*0] + fm->body_invweight0[2*cbody[c]];
   }
   o.cand_body = put_i(I, cbody);
+  o.cand_body1 = put_i(I, cbody1);
   o.cand_iscapsule = put_i(I, ccaps);
   o.cand_sensor = put_i(I, ff ? vi(ff->cand_sensor, 4*nc) : std::vector<int32_t>(4*nc, -1));
   o.act_jnt = put_i(I, vi(fm->actuator_trnid, nu));
@@ -683,7 +707,7 @@ inline bool fb_build_model(const FbModel *fm, const FbFarms *ff, const FbWaveCon
   /* ---- environment-per-thread path (fb_fast.h): articulated-body recursion records */
   {
     DevFastLayout &X = m.X;
-    X.ok = nb <= FB_FAST_MAXBODY;
+    X.ok = nb <= FB_FAST_MAXBODY && m.n_pair == 0;    /* two-body rows: not on the per-thread kernels */
     std::vector<FastRec> &rec = out.rec;
     rec.assign(nb, FastRec());
     std::memset(rec.data(), 0, sizeof(FastRec)*nb);

@@ -771,11 +771,14 @@ def parse_mjcf(xml_text: str) -> Model:
         if key.get('ctrl') is not None:
             model.key_ctrl = _floats(key.get('ctrl'), nu)
 
-    if root.find('contact') is not None and len(root.find('contact')):
-        raise NotImplementedError(
-            'explicit <contact><pair> self-collisions are a "next" row (SURVEY.md section 8f-2)')
+    pairs = []
+    if root.find('contact') is not None:
+        for elem in root.find('contact'):
+            if elem.tag != 'pair':
+                raise NotImplementedError(f'<contact><{elem.tag}> is outside the batched path')
+            pairs.append(elem)
 
-    _compile_collision_candidates(model)
+    _compile_collision_candidates(model, pairs)
     _compile_invweight0(model)
     return model
 
@@ -810,7 +813,58 @@ def _mix_contact_params(model, g1, g2):
     return friction, solref, solimp
 
 
-def _compile_collision_candidates(model):
+PAIR_MIN_FRICTION = 0.1
+
+
+def _compile_pair_candidates(model, pairs):
+    """Explicit ``<contact><pair>`` self-collisions (mjcf.py:1012-1033: one pair per couple of
+    collision geoms of the two links, ``condim=3``, ``friction=[0]*5``, optionally ``solref``).
+    Sphere-sphere only (candidate kind 20, ``mjc_SphereSphere``).  An explicit pair bypasses the
+    contype / conaffinity and same-body / parent-child filters; attributes the element does not
+    give come from the two geoms by the mixing rule, as MuJoCo's compiler fills them in."""
+    cands = []
+    for elem in pairs:
+        names = [elem.get('geom1'), elem.get('geom2')]
+        for name in names:
+            if name not in model.geom_names:
+                raise ValueError(f'<pair>: unknown geom "{name}"')
+        g1, g2 = (model.geom_names.index(name) for name in names)
+        if model.geom_bodyid[g1] == 0 or model.geom_bodyid[g2] == 0:
+            raise NotImplementedError('<pair> with a world geom: use contype / conaffinity')
+        if model.geom_bodyid[g1] == model.geom_bodyid[g2]:
+            raise ValueError(f'<pair> {names}: both geoms on one body')
+        if model.geom_type[g1] != GEOM_SPHERE or model.geom_type[g2] != GEOM_SPHERE:
+            raise NotImplementedError(
+                f'<pair> {names}: only sphere-sphere self-collisions in this round (capsule pairs need mjc_CapsuleCapsule)')
+        if int(elem.get('condim', 3)) != 3:
+            raise NotImplementedError('condim must be 3 (mjcf.py:1029)')
+        friction, solref, solimp = _mix_contact_params(model, g1, g2)
+        if elem.get('friction') is not None:
+            given = _floats(elem.get('friction'))
+            if len(given) > 1 and given[1] != given[0]:
+                raise NotImplementedError('<pair> friction: the two tangential coefficients must be equal')
+            friction = [given[0]]
+        if elem.get('solref') is not None:
+            solref = _floats(elem.get('solref'), 2)
+        if elem.get('solimp') is not None:
+            given = _floats(elem.get('solimp'))
+            solimp = np.concatenate([given, np.array([0.9, 0.95, 0.001, 0.5, 2.0])[len(given):]])
+        margin = float(elem.get('margin')) if elem.get('margin') is not None else max(model.geom_margin[g1], model.geom_margin[g2])
+        gap = float(elem.get('gap')) if elem.get('gap') is not None else max(model.geom_gap[g1], model.geom_gap[g2])
+        if friction[0] < PAIR_MIN_FRICTION:
+            # A pyramidal contact's rows carry D = 1/(2 mu^2 R) (mj_makeImpedance): at the floor
+            # mu = 1e-5 that the reference's friction=[0]*5 pairs get (mjcf.py:1029), the normal
+            # direction is 1e10 times stiffer than at mu = 1 and its residual J.qacc - aref has to
+            # be resolved to 1e-11 relative -- out of reach of the fp32 primal Newton step
+            # (DESIGN.md section 8).
+            raise NotImplementedError(
+                f'<pair> {names}: friction {friction[0]:g} < {PAIR_MIN_FRICTION}: near-frictionless pyramidal '
+                'contacts are too stiff for the fp32 solver (DESIGN.md section 8)')
+        cands.append((g1, g2, 20, max(MJ_MINMU, friction[0]), solref, solimp, margin, gap))
+    return cands
+
+
+def _compile_collision_candidates(model, pairs=()):
     """Enumerate plane-vs-{sphere, capsule end, box corner, ellipsoid} candidates (and the four points of a cylinder) with mixed parameters.
 
     Pair filter ``(contype1 & conaffinity2) || (contype2 & conaffinity1)``,
@@ -849,6 +903,9 @@ def _compile_collision_candidates(model):
                     GEOM_CYLINDER: [11, 12, 13, 14]}[int(model.geom_type[g2])]
             for end in ends:
                 cands.append((g1, g2, end, max(MJ_MINMU, friction[0]), solref, solimp, margin, gap))
+    # explicit pairs come last (MuJoCo's broad phase lists them ahead of the filtered ones; the
+    # order of the contacts does not enter the solution, only the order of the rows)
+    cands += _compile_pair_candidates(model, pairs)
     n = len(cands)
     model.cand_geom1 = np.array([c[0] for c in cands], dtype=np.int32)
     model.cand_geom2 = np.array([c[1] for c in cands], dtype=np.int32)

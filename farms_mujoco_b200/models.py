@@ -101,7 +101,7 @@ class AnimatSpec:
 
 
 def _emit_mjcf(model_name, links, joints_opts, motors, spawn_pose, sim, arena_z,
-               water_height, friction):
+               water_height, friction, self_collisions=()):
     # pylint: disable=too-many-locals,too-many-arguments
     children = {}
     for link in links:
@@ -201,6 +201,17 @@ def _emit_mjcf(model_name, links, joints_opts, motors, spawn_pose, sim, arena_z,
             out.append(
                 f'    <actuatorfrc name="actuatorfrc_{tag}_{j}" actuator="actuator_{kind}_{j}"/>')
     out.append('  </sensor>')
+    # explicit self-collision pairs (mjcf.py:1012-1033): one per couple of collision geoms of the
+    # two links, condim 3, friction [0]*5
+    if self_collisions:
+        collision_map = {link.name: [geom.name for geom in link.geoms] for link in links}
+        out.append('  <contact>')
+        for pair_i, (link1, link2) in enumerate(self_collisions):
+            for col1_i, col1_name in enumerate(collision_map[link1]):
+                for col2_i, col2_name in enumerate(collision_map[link2]):
+                    out.append(f'    <pair name="contact_pair_{pair_i}_{col1_i}_{col2_i}" geom1="{col1_name}" '
+                               f'geom2="{col2_name}" condim="3" friction="0 0 0 0 0"/>')
+        out.append('  </contact>')
     # keyframe (mjcf.py:743-788)
     qpos = list(spawn_pose[:3]) + list(spawn_quat) + [joints_opts[j].initial[0] for j in joint_order]
     qvel = [0.0]*6 + [joints_opts[j].initial[1] for j in joint_order]

@@ -170,7 +170,8 @@ def spec_from_sdf(simulation_options, animat_options, arena_options, contacts_na
         model_name=name, links=links, joints_opts=joints_opts, motors=animat_options.control.motors,
         spawn_pose=list(animat_options.spawn.pose), sim=simulation_options,
         arena_z=arena_options.ground_height if arena_options.ground_height is not None else 0.0,
-        water_height=water.height, friction=friction)
+        water_height=water.height, friction=friction,
+        self_collisions=[tuple(pair) for pair in animat_options.morphology.self_collisions])
     if not animat_options.morphology.links:
         animat_options.morphology.links = [LinkOptions(name=link.name) for link in links]
     animat_options.morphology.joints = [joints_opts[j] for j in joint_order]

@@ -389,6 +389,25 @@ void orc_collision(const FbModel *m, OrcData *d) {
     const double *pm = d->geom_xmat + 9*g1, *pp = d->geom_xpos + 3*g1;
     const double *gm = d->geom_xmat + 9*g2, *gp = d->geom_xpos + 3*g2;
     double n[3] = { pm[2], pm[5], pm[8] };
+    if (end == 20) {
+      /* sphere-sphere of an explicit <pair> (mjc_SphereSphere): normal from geom1 to geom2, the
+       * point half way between the two surfaces */
+      double r1 = m->geom_size[3*g1], r2 = m->geom_size[3*g2];
+      double dif[3] = { gp[0]-pp[0], gp[1]-pp[1], gp[2]-pp[2] };
+      double cdist = normalize3(dif);
+      if (cdist > m->cand_margin[c] + r1 + r2) continue;
+      int i = d->ncon++;
+      double sdist = cdist - r1 - r2;
+      d->con_cand[i] = c;
+      d->con_dist[i] = sdist;
+      for (int k = 0; k < 3; k++) d->con_pos[3*i+k] = pp[k] + dif[k]*(r1 + 0.5*sdist);
+      double *f = d->con_frame + 9*i;
+      memcpy(f, dif, sizeof(dif));
+      f[3] = f[4] = f[5] = 0;
+      make_frame(f);
+      d->con_efc_address[i] = -1;
+      continue;
+    }
     if (end >= 11) {
       /* plane-cylinder (mjc_PlaneCylinder): up to four contacts, each inside the margin on its own
        * (the first is the lowest, so MuJoCo's early return never drops another) */
@@ -524,6 +543,7 @@ void orc_make_constraint(const FbModel *m, OrcData *d) {
   d->nefc = 0;
   double *jac = (double *)calloc(nv, sizeof(double));
   double *jacp = (double *)calloc(3*nv, sizeof(double));
+  double *jacp1 = (double *)calloc(3*nv, sizeof(double));
   for (int j = 0; j < m->njnt; j++) d->jnt_limit_row[j] = -1;
   /* joint limits (mj_instantiateLimit) */
   for (int j = 0; j < m->njnt; j++) {
@@ -547,7 +567,12 @@ void orc_make_constraint(const FbModel *m, OrcData *d) {
     if (d->con_dist[i] >= includemargin) { d->con_efc_address[i] = -1; continue; }
     int b2 = m->geom_bodyid[m->cand_geom2[c]], b1 = m->geom_bodyid[m->cand_geom1[c]];
     double mu = m->cand_friction[c];
-    jac_point(m, d, jacp, NULL, d->con_pos + 3*i, b2);   /* body1 is the world: zero */
+    jac_point(m, d, jacp, NULL, d->con_pos + 3*i, b2);   /* plane candidates: body1 is the world, zero */
+    if (b1 > 0) {
+      /* explicit pair between two bodies of the tree (mj_jacDifPair): jac2 - jac1 */
+      jac_point(m, d, jacp1, NULL, d->con_pos + 3*i, b1);
+      for (int v = 0; v < 3*nv; v++) jacp[v] -= jacp1[v];
+    }
     const double *f = d->con_frame + 9*i;
     double tran = m->body_invweight0[2*b1] + m->body_invweight0[2*b2];
     d->con_efc_address[i] = d->nefc;
@@ -574,6 +599,7 @@ void orc_make_constraint(const FbModel *m, OrcData *d) {
   for (int r = 0; r < d->nefc; r++) d->efc_D[r] = 1/d->efc_R[r];
   free(jac);
   free(jacp);
+  free(jacp1);
 }
 
 /* -------------------------------------------------------------------- A.4 */

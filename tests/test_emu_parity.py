@@ -508,3 +508,59 @@ def test_drag_forces_reference_signature(emu_library, monkeypatch):
                           case['height'][i], case['density'][i], case['gravity'], True)
         assert got == ref_applied[i]
     assert np.abs(xfrc.array[0] - ref).max() < 1e-12
+
+
+def _pair_case(n, seed=5):
+    import variant_models
+    from farms_mujoco_b200 import mjcf_subset
+    spec = variant_models.salamander_foot_pairs()
+    model = mjcf_subset.parse_mjcf(spec.mjcf)
+    rng = np.random.default_rng(seed)
+    qpos0 = np.tile(variant_models.folded_legs_qpos(model, 1.0), (n, 1))
+    qpos0[:, 7:] += rng.uniform(-0.03, 0.03, (n, model.nq - 7))
+    qpos0[n - 1] = model.key_qpos                      # one environment with the legs apart: no pair contact
+    qvel0 = rng.uniform(-0.2, 0.2, (n, model.nv))
+    ctrl = np.tile(qpos0[0, 7:][None], (n, 1))[:, :0]  # placeholder, replaced below
+    ctrl = rng.uniform(-0.3, 0.3, (n, model.nu))
+    return spec, model, qpos0, qvel0, ctrl
+
+
+def test_pair_self_collisions(emu_library):
+    """Explicit <contact><pair> self-collisions (mjcf.py:1012-1033; sphere-sphere, mjc_SphereSphere):
+    rows on two branches of the tree -> the team kernel with the dense Newton Hessian, vs the
+    oracle.  The pair sensor and the two single-link sensors see the contact with opposite signs."""
+    import fastpath_cases
+    from farms_mujoco_b200.engine import BatchedPhysics
+    n, n_steps = 3, 12
+    spec, model, qpos0, qvel0, ctrl = _pair_case(n)
+    assert (model.cand_end == 20).sum() == 2
+    physics = BatchedPhysics.from_spec(spec, n, buffer_size=n_steps + 1, library=emu_library)
+    assert physics.fast_path == 0                       # two-body rows: team kernel only
+    physics.reset(qpos0, qvel0)
+    physics.set_ctrl(ctrl)
+    physics.step(n_steps)
+    contacts = physics.log_arrays()['contacts']
+    names = [tuple(c) for c in spec.contacts_names]
+    pair = names.index(('link_leg_0_L_3', 'link_leg_0_R_3'))
+    left, right = names.index(('link_leg_0_L_3', '')), names.index(('link_leg_0_R_3', ''))
+    assert np.abs(contacts[0, 1:, pair, 6:9]).max() > 1e-3          # the feet push on one another
+    assert not contacts[n - 1, :, pair].any()                        # legs apart: nothing
+    # (g1, g2): -1 and (g1, -1): -1 on the left link, (g2, -1): +1 on the right (sensors.pyx:160-176)
+    assert np.allclose(contacts[0, :, pair, 6:9], contacts[0, :, left, 6:9], atol=1e-6)
+    assert np.allclose(contacts[0, :, pair, 6:9], -contacts[0, :, right, 6:9], atol=1e-6)
+    # team-kernel tolerances (the CRB + L'DL path accumulates more rounding than the recursions)
+    fastpath_cases.compare_with_oracle(spec, model, physics, qpos0, qvel0, ctrl, range(n), n_steps, 2e-4,
+                                       tol_contacts=2e-4)
+
+
+def test_pair_friction_floor():
+    """The reference's generated pairs are frictionless (friction=[0]*5 -> MuJoCo's floor 1e-5,
+    mjcf.py:1029): the pyramidal rows' D = 1/(2 mu^2 R) puts them out of reach of the fp32 solver;
+    the front-end says so instead of returning forces that are wrong."""
+    import variant_models
+    from farms_mujoco_b200 import mjcf_subset
+    with pytest.raises(NotImplementedError, match='friction'):
+        mjcf_subset.parse_mjcf(variant_models.salamander_foot_pairs(friction=0).mjcf)
+    with pytest.raises(NotImplementedError, match='sphere-sphere'):
+        spec = variant_models.salamander_foot_pairs()
+        mjcf_subset.parse_mjcf(spec.mjcf.replace('geom1="link_leg_0_L_3_foot"', 'geom1="link_body_3_collision"'))

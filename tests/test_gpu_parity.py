@@ -806,3 +806,25 @@ def test_sub_steps_log_full_steps_only(cuda_library):
     sim.run()
     assert sim.physics.iteration == 2*n_it - 1 and sim.iteration == n_it
     _substep_check(sim, spec, n_it, 2, phase, wave)
+
+
+@pytest.mark.gpu
+def test_pair_self_collisions(cuda_library):
+    """Explicit <contact><pair> sphere-sphere self-collisions on the device: the team kernel with the
+    dense Newton Hessian (rows on two branches of the tree), against the oracle."""
+    import fastpath_cases
+    from test_emu_parity import _pair_case
+    from farms_mujoco_b200.engine import BatchedPhysics
+    n, n_steps = 40, 12
+    spec, model, qpos0, qvel0, ctrl = _pair_case(n)
+    physics = BatchedPhysics.from_spec(spec, n, buffer_size=n_steps + 1, library=cuda_library)
+    assert physics.fast_path == 0 and physics.team_lanes > 1
+    physics.reset(qpos0, qvel0)
+    physics.set_ctrl(ctrl)
+    physics.step(n_steps)
+    contacts = physics.log_arrays()['contacts']
+    names = [tuple(c) for c in spec.contacts_names]
+    pair = names.index(('link_leg_0_L_3', 'link_leg_0_R_3'))
+    assert np.abs(contacts[0, 1:, pair, 6:9]).max() > 1e-3 and not contacts[n - 1, :, pair].any()
+    fastpath_cases.compare_with_oracle(spec, model, physics, qpos0, qvel0, ctrl, (0, 1, 17, n - 2, n - 1), n_steps, 2e-4,
+                                       tol_contacts=2e-4)

@@ -324,6 +324,41 @@ def test_plane_cylinder_points():
     assert checked >= 2
 
 
+def test_pair_sphere_sphere_contact():
+    """Explicit <pair>, sphere-sphere (mjc_SphereSphere): the contact sits half way between the two
+    surfaces on the line of centres, the normal runs from geom1 to geom2, the distance is the gap
+    between the surfaces; and the contact is an INTERNAL force -- the rows' Jacobian is the
+    difference of the two bodies' point Jacobians (mj_jacDifPair), so the constraint force has no
+    component on the six dofs of the floating root (Newton's third law)."""
+    import variant_models
+    from farms_mujoco_b200 import mjcf_subset
+    from oracle.oracle import OraclePhysics
+    spec = variant_models.salamander_foot_pairs()
+    model = mjcf_subset.parse_mjcf(spec.mjcf)
+    orc = OraclePhysics(model)
+    orc.reset(keyframe_id=0)
+    orc.data.qpos[:] = variant_models.folded_legs_qpos(model, 1.0)
+    orc.forward()
+    assert orc.ncon == 2
+    cand = orc.arrays['con_cand'][:2]
+    assert (np.asarray(model.cand_end)[cand] == 20).all()
+    radius = 0.017
+    for i, c in enumerate(cand):
+        g1, g2 = model.cand_geom1[c], model.cand_geom2[c]
+        gx = orc.arrays['geom_xpos'].reshape(-1, 3)
+        p1, p2 = gx[g1], gx[g2]
+        gap = np.linalg.norm(p2 - p1) - 2*radius
+        normal = (p2 - p1)/np.linalg.norm(p2 - p1)
+        assert gap < 0 and abs(orc.arrays['con_dist'][i] - gap) < 1e-14
+        assert np.allclose(orc.arrays['con_frame'].reshape(-1, 9)[i, :3], normal, atol=1e-14)
+        assert np.allclose(orc.arrays['con_pos'].reshape(-1, 3)[i], 0.5*(p1 + p2), atol=1e-14)   # equal radii
+        force = orc.contact_force(i)
+        assert force[0] > 0.1                                        # the feet push apart
+    qfrc = orc.arrays['qfrc_constraint']
+    assert np.abs(qfrc[6:]).max() > 1e-3
+    assert np.abs(qfrc[:6]).max() < 1e-9*np.abs(qfrc[6:]).max()
+
+
 def test_instrumented_op_count_matches_stock_oracle(tmp_path):
     """oracle/opcount: the oracle compiled with the counting scalar reproduces the stock oracle's
     bits and reports the committed per-step operation counts (profiles/oracle_opcount.json,

@@ -206,3 +206,30 @@ def test_from_sdf_with_cylinder_and_ellipsoid_collisions(emu_library):
     # contact sensors in link order (depth first): trunk_0, trunk_1, pad, leg_L, leg_R, skid
     load = np.abs(contacts[..., 2]).max(axis=tuple(range(contacts.ndim - 2)))
     assert load.shape == (6,) and load[2] > 0.5 and load[5] > 0.5, load
+
+
+def test_self_collisions_emit_the_reference_pairs(emu_library):
+    """morphology.self_collisions -> <contact><pair> as mjcf.py:1012-1033 writes them (one per couple
+    of collision geoms, condim 3, friction [0]*5).  Those frictionless pairs are refused with the
+    reason (fp32 conditioning); with a friction coefficient the same pair runs."""
+    from farms_mujoco_b200.options import MorphologyOptions
+    from farms_mujoco_b200.simulation.simulation import Simulation
+    animat = AnimatOptions(sdf=branching_sdf(), spawn=SpawnOptions(pose=[0, 0, 0.06, 0, 0, 0]),
+                           morphology=MorphologyOptions(self_collisions=[['leg_L', 'leg_R']]),
+                           control=ControlOptions(motors=[MotorOptions(joint_name=j, gains=[0.5, 1e-3])
+                                                          for j in ('spine', 'hip_L', 'hip_R')]))
+    spec = sdf_subset.spec_from_sdf(SimulationOptions(timestep=1e-3, n_iterations=20), animat,
+                                    ArenaOptions(ground_height=0.0))
+    line = '<pair name="contact_pair_0_0_0" geom1="foot_L" geom2="foot_R" condim="3" friction="0 0 0 0 0"/>'
+    assert line in spec.mjcf
+    with pytest.raises(NotImplementedError, match='friction'):
+        mjcf_subset.parse_mjcf(spec.mjcf)
+    import dataclasses
+    spec = dataclasses.replace(spec, mjcf=spec.mjcf.replace('friction="0 0 0 0 0"', 'friction="0.6 0.6 0 0 0"'),
+                               contacts_names=spec.contacts_names + [('leg_L', 'leg_R')])
+    model = mjcf_subset.parse_mjcf(spec.mjcf)
+    assert (model.cand_end == 20).sum() == 1 and model.cand_friction[model.cand_end == 20][0] == 0.6
+    sim = Simulation.from_spec(spec, n_envs=2, library=emu_library)
+    assert sim.physics.fast_path == 0
+    sim.run()
+    assert np.isfinite(sim.task.data.sensors.links.array).all()

@@ -130,3 +130,36 @@ def salamander_cylinder_feet():
     x = x.replace(old, 'type="cylinder" size="0.02 0.04 0.0" pos="0.04 0.0 0.0" '
                        'quat="0.7071067811865476 0.0 0.7071067811865475 0.0"')
     return dataclasses.replace(spec, name='salamander_cylinder', mjcf=x)
+
+
+def salamander_foot_pairs(swimming=True, foot_radius=0.017, friction=0.5):
+    """Explicit ``<contact><pair>`` self-collisions as ``mjcf.py:1012-1033`` writes them (condim 3,
+    friction 0 -> MuJoCo's floor 1e-5, solref of the animat) between the left and the right foot
+    of each girdle, with feet large enough to meet when the legs fold under the trunk; contact
+    sensors between the two links and on each foot alone.  The rows of such a contact live on two
+    branches of the tree."""
+    spec = models.salamander(swimming=swimming)
+    x = spec.mjcf
+    old = 'size="0.01 0.01 0.01"'
+    assert x.count(old) == 8, x.count(old)      # the four feet and their visual twins
+    x = x.replace(old, f'size="{foot_radius} {foot_radius} {foot_radius}"')
+    pairs = ''.join(
+        f'    <pair name="contact_pair_{i}_0_0" geom1="link_leg_{i}_L_3_foot" geom2="link_leg_{i}_R_3_foot" '
+        f'condim="3" friction="{friction} {friction} 0 0 0" solref="0.005 1"/>\n' for i in range(2))
+    assert '<contact>' not in x
+    x = x.replace('</mujoco>', f'  <contact>\n{pairs}  </contact>\n</mujoco>')
+    contacts = list(spec.contacts_names) + [(f'link_leg_{i}_L_3', f'link_leg_{i}_R_3') for i in range(2)]
+    return dataclasses.replace(spec, name='salamander_foot_pairs', mjcf=x, contacts_names=contacts)
+
+
+def folded_legs_qpos(model, fold=1.1):
+    """Keyframe with the four legs folded under the trunk (hip pitch and elbow at -/+ ``fold``):
+    the feet of one girdle overlap."""
+    import numpy as np
+    qpos = np.array(model.key_qpos, dtype=float)
+    for i in range(2):
+        for side, sgn in (('L', 1.0), ('R', -1.0)):
+            for k in (1, 3):
+                adr = model.jnt_qposadr[model.jnt_id(f'joint_leg_{i}_{side}_{k}')]
+                qpos[adr] = -sgn*fold
+    return qpos
