@@ -133,8 +133,13 @@ def test_mjcf_rejects_out_of_scope():
     spec = models.swimmer8()
     with pytest.raises(NotImplementedError):
         ms.parse_mjcf(spec.mjcf.replace('cone="pyramidal"', 'cone="elliptic"'))
-    with pytest.raises(NotImplementedError):
+    with pytest.raises(ValueError, match='unknown geom'):
         ms.parse_mjcf(spec.mjcf.replace('</mujoco>', '<contact><pair geom1="a" geom2="b"/></contact></mujoco>'))
+    with pytest.raises(NotImplementedError, match='sphere-sphere'):      # capsule pairs: not yet
+        ms.parse_mjcf(spec.mjcf.replace('</mujoco>', '<contact><pair geom1="link_0_collision" '
+                                        'geom2="link_2_collision"/></contact></mujoco>'))
+    with pytest.raises(NotImplementedError, match='exclude'):
+        ms.parse_mjcf(spec.mjcf.replace('</mujoco>', '<contact><exclude body1="link_0" body2="link_1"/></contact></mujoco>'))
 
 
 def test_abi_header_symbols_are_exported(cuda_library):
