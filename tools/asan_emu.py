@@ -29,3 +29,12 @@ for name in ('swimmer8','salamander_swim','salamander','centipede'):
 spec=variant_models.salamander_box_feet(); model=mjcf_subset.parse_mjcf(spec.mjcf)
 ph=BatchedPhysics.from_spec(spec,2,buffer_size=6,library=lib); ph.step(5); print('box ok')
 spec=variant_models.swimmer8_fixed_base(); ph=BatchedPhysics.from_spec(spec,2,buffer_size=6,library=lib); ph.step(5); print('fixed ok')
+# explicit <pair> self-collisions: the dense Newton Hessian behind the contact Jacobians
+sys.path.insert(0, '/root/repo/tests')
+from test_emu_parity import _pair_case
+spec, model, qpos0, qvel0, ctrl = _pair_case(3)
+ph = BatchedPhysics.from_spec(spec, 3, buffer_size=6, library=lib)
+ph.reset(qpos0, qvel0); ph.set_ctrl(ctrl); ph.step(5); assert ph.log_arrays()['contacts'].any(); print('pairs ok')
+# the stand-alone drag operator
+from drag_cases import check_operator
+print('drag operator', check_operator(lib, n=33))
