@@ -87,3 +87,35 @@ def test_hundred_steps_match_mj_step(name):
     _, _, mjd, orc = _both(name, 100, seed=1)
     assert np.allclose(orc.data.qpos, mjd.qpos, rtol=0, atol=1e-7)
     assert np.allclose(orc.data.qvel, mjd.qvel, rtol=1e-6, atol=1e-6)
+
+
+def test_pair_self_collision_matches_mj_step():
+    """Explicit <contact><pair> sphere-sphere contact (mjcf.py:1012-1033 with a friction coefficient):
+    contact geometry, the two-body rows (mj_jacDifPair) and mj_contactForce against MuJoCo."""
+    import variant_models
+    from farms_mujoco_b200 import mjcf_subset
+    from oracle.oracle import OraclePhysics
+    spec = variant_models.salamander_foot_pairs()
+    model = mjcf_subset.parse_mjcf(spec.mjcf)
+    mjm = mujoco.MjModel.from_xml_string(spec.mjcf)
+    mjd = mujoco.MjData(mjm)
+    qpos = variant_models.folded_legs_qpos(model, 1.0)
+    mujoco.mj_resetData(mjm, mjd)
+    mjd.qpos[:] = qpos
+    orc = OraclePhysics(model)
+    orc.reset(keyframe_id=0)
+    orc.data.qpos[:] = qpos
+    mujoco.mj_step(mjm, mjd)
+    orc.step()
+    assert orc.ncon == mjd.ncon == 2
+    assert np.allclose(orc.data.qvel, mjd.qvel, rtol=1e-8, atol=1e-9)
+    for i in range(mjd.ncon):
+        force = np.zeros(6)
+        mujoco.mj_contactForce(mjm, mjd, i, force)
+        ours = [k for k, c in enumerate(orc.data.contact)
+                if {c.geom1, c.geom2} == {int(mjd.contact[i].geom1), int(mjd.contact[i].geom2)}]
+        assert len(ours) == 1
+        c = orc.data.contact[ours[0]]
+        assert np.allclose(c.pos, mjd.contact[i].pos, atol=1e-12) and abs(c.dist - mjd.contact[i].dist) < 1e-12
+        assert np.allclose(c.frame[:3], mjd.contact[i].frame[:3], atol=1e-12)
+        assert np.allclose(orc.contact_force(ours[0])[:3], force[:3], rtol=1e-6, atol=1e-9)
