@@ -32,6 +32,22 @@ class Recorder(TaskCallback):
         self.calls.append(('after', task.iteration))
 
 
+class SwimmingCallback(TaskCallback):
+    """The swimming callback a farms experiment attaches (farms_sim): a ``SwimmingHandler`` stepped
+    in ``before_step``, on sub-steps too."""
+
+    def __init__(self, spec):
+        super().__init__(substep=True)
+        self.spec, self.handler = spec, None
+
+    def initialize_episode(self, task, physics):
+        self.handler = SwimmingHandler(task.data, self.spec.animat_options, self.spec.arena_options,
+                                       self.spec.simulation_options.units, physics)
+
+    def before_step(self, task, action, physics):
+        self.handler.step(task.iteration % task.buffer_size)
+
+
 class HostWave(AnimatController):
     """A controller with no device form: evaluated on the host every iteration."""
 
@@ -288,7 +304,7 @@ def test_sub_steps_with_a_substep_callback(emu_library):
     wave = travelling_wave_parameters(spec)
     ctl = TravellingWaveController(*wave, env_phase=phase)
     cb = Recorder(substep=True)
-    sim = _substep_sim(spec, 3, emu_library, controller=ctl, callbacks=[cb])
+    sim = _substep_sim(spec, 3, emu_library, controller=ctl, callbacks=[cb, SwimmingCallback(spec)])
     sim.run()
     assert sim.task.device_controller is False and sim.task.substeps_links
     assert [c for c in cb.calls if c[0] == 'before'][:4] == [('before', 0), ('before', 0), ('before', 1), ('before', 1)]
