@@ -81,7 +81,6 @@ struct EnvPtrs {
   float *d_con_dist, *d_con_pos, *d_con_frame, *d_con_force;
   /* solver scratch */
   float *J3;     /* [3*maxcon][nv] contact-frame rows of the point Jacobian */
-  float *Hd;     /* [nv][nv] dense Newton Hessian, models with explicit <pair>s only (behind J3) */
   float *efc;    /* [5][maxefc]: aref, D, res, jp, force */
   float *prod3;  /* [2][3*maxcon] */
   /* log rows of this step: element (item, col) of a kind with C columns stored in vectors of
@@ -1043,8 +1042,9 @@ FB_UNROLL
       if (npair_act > 0) {
         /* A contact of an explicit <pair> is active: its rows live on the chains of two bodies, so
          * J'DJ couples dofs that are not ancestors of one another and H loses the tree sparsity.
-         * Dense H (lower triangle) behind J3, Cholesky in place, two triangular solves. */
-        float *H = g.Hd;
+         * Dense H (lower triangle) in the environment's shared memory, Cholesky in place, two
+         * triangular solves. */
+        float *H = s + m.L.H;
         for (int idx = lane; idx < nv*nv; idx += TEAM) H[idx] = 0.f;
         sync();
         for (int e = lane; e < m.nM; e += TEAM) {
@@ -1519,18 +1519,6 @@ FB_DEV float *fb_log_row(float *base, long long it, long long floats_per_row, lo
   return base + it*floats_per_row*env_pad + env*vec;
 }
 
-/* per-environment floats behind FbParams::J3: the contact Jacobians and, for models with explicit
- * <pair>s, the dense Hessian of the Newton step */
-#ifdef FB_HOST_EMU
-static inline
-#else
-__host__ __device__ __forceinline__
-#endif
-size_t fb_j3_stride(const DevModel &m) {
-  const size_t mc = m.maxcon > 0 ? m.maxcon : 1;
-  return 3*mc*m.nv + (m.n_pair > 0 ? (size_t)m.nv*m.nv : 0);
-}
-
 FB_DEV EnvPtrs fb_env_ptrs(const FbParams &P, int env) {
   const DevModel &m = P.m;
   EnvPtrs g;
@@ -1547,7 +1535,7 @@ FB_DEV EnvPtrs fb_env_ptrs(const FbParams &P, int env) {
   g.d_ncon = P.d_ncon + env; g.d_con_cand = P.d_con_cand + e*mc;
   g.d_con_dist = P.d_con_dist + e*mc; g.d_con_pos = P.d_con_pos + e*3*mc;
   g.d_con_frame = P.d_con_frame + e*9*mc; g.d_con_force = P.d_con_force + e*3*mc;
-  g.J3 = P.J3 + e*fb_j3_stride(m); g.Hd = g.J3 + (size_t)3*mc*m.nv; g.efc = P.efc + e*5*m.maxefc; g.prod3 = P.prod3 + e*6*mc;
+  g.J3 = P.J3 + e*3*mc*m.nv; g.efc = P.efc + e*5*m.maxefc; g.prod3 = P.prod3 + e*6*mc;
   g.row_links = g.row_joints = g.row_contacts = g.row_xfrc = 0;
   g.ev_links = P.env_pad*FB_VEC_LINKS; g.ev_joints = P.env_pad*FB_VEC_JOINTS;
   g.ev_contacts = P.env_pad*FB_VEC_CONTACTS; g.ev_xfrc = P.env_pad*FB_VEC_XFRC;

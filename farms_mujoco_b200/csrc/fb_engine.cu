@@ -1143,7 +1143,7 @@ int fb_create(const FbModel *model, const FbFarms *farms, int n_envs, int device
   bad |= alloc_arr(h, &P.d_ncon, n); bad |= alloc_arr(h, &P.d_con_cand, n*mc);
   bad |= alloc_arr(h, &P.d_con_dist, n*mc); bad |= alloc_arr(h, &P.d_con_pos, n*3*mc);
   bad |= alloc_arr(h, &P.d_con_frame, n*9*mc); bad |= alloc_arr(h, &P.d_con_force, n*3*mc);
-  bad |= alloc_arr(h, &P.J3, n*fb_j3_stride(m)); bad |= alloc_arr(h, &P.efc, n*5*(m.maxefc > 0 ? m.maxefc : 1));
+  bad |= alloc_arr(h, &P.J3, n*3*mc*m.nv); bad |= alloc_arr(h, &P.efc, n*5*(m.maxefc > 0 ? m.maxefc : 1));
   bad |= alloc_arr(h, &P.prod3, n*6*mc);
   const size_t ep = (size_t)P.env_pad*ring_steps;
   bad |= alloc_arr(h, &P.log_links, ep*m.n_links*20);

@@ -1009,6 +1009,9 @@ inline bool fb_build_model(const FbModel *fm, const FbFarms *ff, const FbWaveCon
     L.H = L.scratch + pad4(m.npack);
     off += natural > need ? natural : need;
   }
+  /* models with explicit <pair>s: the dense Newton Hessian of the team kernel (nv x nv), a region of
+   * its own (the scratch aliases are live during the solve) */
+  if (m.n_pair > 0) L.H = take(nv*nv);
   L.n_float = off;
   L.con_cand = 0;
   L.n_int = (m.maxcon + 3) & ~3;
