@@ -24,6 +24,7 @@ import os
 import numpy as np
 import yaml
 
+from ..hdf5_min import write_hdf5
 from ..engine import BatchedPhysics
 from ..mjcf_subset import parse_mjcf
 from .task import ExperimentTask
@@ -221,7 +222,10 @@ class Simulation:
         our knowledge (UNVERIFIED): ``timestep``, ``sensors/<kind>/array``
         (here with a leading environment axis: ``[n_envs, iteration, n_items, n_cols]``) and
         ``sensors/<kind>/names``; the flat ``<kind>`` / ``<kind>_names`` keys of round 1 are kept.
-        Options go to the two YAML files as in the reference."""
+        ``simulation.hdf5`` is written too, by ``hdf5_min.write_hdf5`` (a hand-written subset of the
+        HDF5 format, read back by its own reader in the tests and by h5py only where h5py exists:
+        treat the .npz as the reference copy until it has been).  Options go to the two YAML files
+        as in the reference."""
         del kwargs
         assert not plot, 'plotting is outside the batched path'
         times = np.arange(0, self.task.timestep*self.task.n_iterations, self.task.timestep)[:iteration]
@@ -238,6 +242,16 @@ class Simulation:
                 payload[f'sensors/{kind}/array'] = arr.array[:, :iteration]
                 payload[f'sensors/{kind}/names'] = names
             np.savez_compressed(os.path.join(log_path, 'simulation.npz'), **payload)
+            # simulation.hdf5 (simulation.py:200-202) through the built-in minimal writer: the same
+            # tree as groups / datasets; one environment is written in the reference's shapes
+            # ([iteration, n_items, n_cols]), a batch keeps its leading environment axis
+            single = self.physics.n_envs == 1
+            tree = {'timestep': float(self.task.timestep), 'sensors': {}}
+            for kind in ('links', 'joints', 'contacts', 'xfrc'):
+                arr = getattr(sensors, kind)
+                rows = arr.array[:, :iteration]
+                tree['sensors'][kind] = {'array': rows[0] if single else rows, 'names': [str(n) for n in arr.names]}
+            write_hdf5(os.path.join(log_path, 'simulation.hdf5'), tree)
             with open(os.path.join(log_path, 'simulation_options.yaml'), 'w', encoding='utf-8') as out:
                 yaml.safe_dump(_plain(self.options), out)
             if self.task.animat_options is not None:
