@@ -828,3 +828,11 @@ def test_pair_self_collisions(cuda_library):
     assert np.abs(contacts[0, 1:, pair, 6:9]).max() > 1e-3 and not contacts[n - 1, :, pair].any()
     fastpath_cases.compare_with_oracle(spec, model, physics, qpos0, qvel0, ctrl, (0, 1, 17, n - 2, n - 1), n_steps, 2e-4,
                                        tol_contacts=2e-4)
+
+
+@pytest.mark.gpu
+def test_torque_control_disables_position_actuators(cuda_library):
+    """initialize_control's model edit (task.py:262-286), torque commands and spring references
+    through the Simulation layer on the device, against the oracle on the edited model."""
+    from test_simulation_loop import _torque_control_case
+    _torque_control_case(cuda_library)

@@ -179,7 +179,7 @@ class HostTorque(AnimatController):
         return {self.joints_names[ControlType.TORQUE][0]: 0.1}
 
 
-def test_torque_control_disables_position_actuators(emu_library):
+def _torque_control_case(library):
     """initialize_control (task.py:262-286): motors without the 'position' control type get
     their position / velocity actuators force-limited to [0, 0]; torques reach ctrl scaled by
     units.torques; springrefs land in qpos_spring."""
@@ -194,7 +194,7 @@ def test_torque_control_disables_position_actuators(emu_library):
         motor.control_types = ['torque']
     spec = dataclasses.replace(spec, animat_options=animat)
     sim = Simulation.from_spec(spec, n_envs=n_envs, controller=HostTorque(spec.joints_names, n_envs),
-                               library=emu_library)
+                               library=library)
     sim.run()
     model = sim.physics.model
     pos = [model.actuator_id(f'actuator_position_{j}') for j in spec.joints_names]
@@ -218,6 +218,10 @@ def test_torque_control_disables_position_actuators(emu_library):
         for kind in ('links', 'joints', 'xfrc'):
             ours = getattr(sim.task.data.sensors, kind).array[env]
             assert log_error(kind, ours, getattr(data.sensors, kind).array) < 2e-5, kind
+
+
+def test_torque_control_disables_position_actuators(emu_library):
+    _torque_control_case(emu_library)
 
 
 def test_open_loop_host_controller_is_fused(emu_library):
