@@ -564,3 +564,24 @@ def test_pair_friction_floor():
     with pytest.raises(NotImplementedError, match='sphere-sphere'):
         spec = variant_models.salamander_foot_pairs()
         mjcf_subset.parse_mjcf(spec.mjcf.replace('geom1="link_leg_0_L_3_foot"', 'geom1="link_body_3_collision"'))
+
+
+def test_drag_operator_edge_cases(emu_library):
+    """fb_drag_forces: no rows is a no-op, a null argument is an error with a message, the Python
+    wrapper refuses output arrays it could not update in place."""
+    import ctypes as ct
+    from farms_mujoco_b200 import cabi
+    from farms_mujoco_b200.engine import load_library, drag_forces_rows
+    lib = load_library(emu_library)
+    null = ct.cast(None, cabi.c_double_p)
+    assert lib.fb_drag_forces(0, 0, null, null, null, null, null, 0.0, null, 1.0, -9.81, 1, null, None) == 0
+    assert lib.fb_drag_forces(0, 2, null, null, null, null, null, 0.0, null, 1.0, -9.81, 1, null, None) != 0
+    assert b'null' in lib.fb_last_error()
+    links = np.zeros((2, 20)); links[:, 6] = links[:, 13] = 1.0
+    with pytest.raises(ValueError):
+        drag_forces_rows(links, np.zeros((2, 6)), 1.0, 0.1, 1000.0, 0.0, [0, 0, 0], 1.0, -9.81, True,
+                         np.zeros((2, 6), dtype=np.float32), library=emu_library)
+    xfrc = np.zeros((2, 6))
+    applied = drag_forces_rows(links, np.zeros((2, 6)), 1.0, 0.1, 1000.0, 0.0, [0, 0, 0], 1.0, -9.81, False,
+                               xfrc, library=emu_library)
+    assert applied.all() and not xfrc.any()                 # at the surface, at rest, no buoyancy: zero forces
