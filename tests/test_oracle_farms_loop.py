@@ -77,3 +77,32 @@ def test_compiled_loop_ring_reuse():
     loop.run(8)
     # same state sequence written over the same ring rows, time-dependent control aside
     assert np.abs(loop.data.sensors.contacts.array).max() < 2*np.abs(first).max() + 1e-12
+
+
+def test_compiled_loop_with_pair_contacts():
+    """The same on explicit <pair> self-collisions: the pair sensor (g1, g2) and the two single-link
+    sensors (g, -1) of sensors.pyx:160-176 see the two-body contact in the C loop as in NumPy."""
+    import variant_models
+    spec = variant_models.salamander_foot_pairs()
+    model = mjcf_subset.parse_mjcf(spec.mjcf)
+    data = AnimatData.from_sensors_names(model.timestep, 4, spec.links_names, spec.joints_names,
+                                         spec.contacts_names, spec.xfrc_names)
+    maps = fo.make_maps(model, data)
+    tables = FarmsTables(model, data.sensors, maps['sensors'], spec.animat_options, spec.arena_options,
+                         spec.simulation_options.units)
+    n_it = 12
+    qpos0 = variant_models.folded_legs_qpos(model, 1.0)
+    ref, states = fo.reference_rollout(OraclePhysics(model), spec, tables, n_it, qpos0=qpos0, qvel0=np.zeros(model.nv))
+    physics = OraclePhysics(model)
+    physics.reset(keyframe_id=0)
+    physics.data.qpos[:] = qpos0
+    physics.forward()
+    loop = fo.CompiledRollout(physics, spec, tables, n_it)
+    loop.run(n_it - 1)
+    loop.sensors()
+    assert np.allclose(physics.data.qpos, states[-1][0], rtol=0, atol=1e-13)
+    ours, want = loop.data.sensors.contacts.array, ref.sensors.contacts.array
+    names = [tuple(c) for c in spec.contacts_names]
+    pair = names.index(('link_leg_0_L_3', 'link_leg_0_R_3'))
+    assert np.abs(want[1:, pair, 6:9]).max() > 1e-3
+    assert np.allclose(ours, want, rtol=1e-11, atol=1e-12), np.abs(ours - want).max()
